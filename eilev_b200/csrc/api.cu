@@ -1,0 +1,213 @@
+// extern "C" surface of libvideoblip_b200.so — see include/videoblip_b200.h.
+#include <cstdio>
+#include <cstring>
+
+#include "gemm.h"
+#include "internal.h"
+
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(const char* where, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return 1;
+}
+int fail_msg(const char* where, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, msg);
+  return 1;
+}
+inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+#define VB_CHECK(where, expr)                       \
+  do {                                              \
+    cudaError_t _e = (expr);                        \
+    if (_e != cudaSuccess) return fail(where, _e);  \
+    return 0;                                       \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+int vb_abi_version(void) { return VB_ABI_VERSION; }
+const char* vb_last_error(void) { return g_err; }
+
+int vb_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return -1;
+  return major * 10 + minor;
+}
+
+int vb_gemm_uses_tcgen05(const vb_gemm_args* a) {
+  if (a == nullptr) return 0;
+  if (a->backend == VB_GEMM_GENERIC) return 0;
+  return vb::gemm_tcgen05_eligible(*a) ? 1 : 0;
+}
+
+int vb_gemm(const vb_gemm_args* a, void* stream) {
+  if (a == nullptr) return fail_msg("vb_gemm", "null args");
+  if (a->m < 0 || a->n < 0 || a->k <= 0) return fail_msg("vb_gemm", "bad shape");
+  if (a->m == 0 || a->n == 0) return 0;
+  if (a->a == nullptr || a->b == nullptr || a->c == nullptr) return fail_msg("vb_gemm", "null operand");
+  if (a->out_dtype != VB_BF16 && a->out_dtype != VB_F32) return fail_msg("vb_gemm", "bad out_dtype");
+  const bool elig = vb::gemm_tcgen05_eligible(*a);
+  if (a->backend == VB_GEMM_TCGEN05 && !elig)
+    return fail_msg("vb_gemm", "shape/alignment not eligible for the tcgen05 path");
+  if (a->backend != VB_GEMM_GENERIC && elig) VB_CHECK("vb_gemm[tcgen05]", vb::gemm_tcgen05_launch(*a, st(stream)));
+  VB_CHECK("vb_gemm[generic]", vb::gemm_generic_launch(*a, st(stream)));
+}
+
+int vb_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
+                 void* y, float* mean, float* rstd, int64_t rows, int64_t cols, int64_t ldx,
+                 int64_t ldr, int64_t ldy, float eps, void* stream) {
+  if (x == nullptr || y == nullptr || gamma == nullptr || beta == nullptr)
+    return fail_msg("vb_layernorm", "null operand");
+  VB_CHECK("vb_layernorm", vb::layernorm_fwd(x, residual, gamma, beta, y, mean, rstd, rows, cols,
+                                             ldx, ldr, ldy, eps, st(stream)));
+}
+
+int vb_layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
+                     const float* rstd, const void* dx_add, void* dx, float* dgamma, float* dbeta,
+                     int64_t rows, int64_t cols, float, void* stream) {
+  if (dy == nullptr || xin == nullptr || gamma == nullptr || mean == nullptr || rstd == nullptr ||
+      dx == nullptr)
+    return fail_msg("vb_layernorm_bwd", "null operand");
+  VB_CHECK("vb_layernorm_bwd", vb::layernorm_bwd(dy, xin, gamma, mean, rstd, dx_add, dx, dgamma,
+                                                 dbeta, rows, cols, st(stream)));
+}
+
+int vb_attention_fwd(const vb_attn_args* a, void* stream) {
+  if (a == nullptr || a->q == nullptr || a->k == nullptr || a->v == nullptr || a->o == nullptr)
+    return fail_msg("vb_attention_fwd", "null operand");
+  VB_CHECK("vb_attention_fwd", vb::attention_fwd_launch(*a, st(stream)));
+}
+
+int vb_attention_bwd(const vb_attn_bwd_args* a, void* stream) {
+  if (a == nullptr || a->d_o == nullptr || a->dq == nullptr || a->dk == nullptr || a->dv == nullptr)
+    return fail_msg("vb_attention_bwd", "null operand");
+  VB_CHECK("vb_attention_bwd", vb::attention_bwd_launch(*a, st(stream)));
+}
+
+int vb_patch_gather(const void* pixels, int32_t px_dtype, void* out, int64_t nv, int64_t c,
+                    int64_t t, int64_t h, int64_t w, int64_t patch, int64_t kpad, void* stream) {
+  if (pixels == nullptr || out == nullptr || patch <= 0 || kpad < c * patch * patch)
+    return fail_msg("vb_patch_gather", "bad arguments");
+  VB_CHECK("vb_patch_gather",
+           vb::patch_gather_launch(pixels, px_dtype, out, nv, c, t, h, w, patch, kpad, st(stream)));
+}
+
+int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
+                int64_t dim, void* stream) {
+  VB_CHECK("vb_cls_rows", vb::cls_rows_launch(cls, pos, hidden, frames, tokens, dim, st(stream)));
+}
+
+int vb_embed_splice(const int64_t* input_ids, const int64_t* attention_mask,
+                    const int64_t* video_mask, const void* embed_tokens,
+                    const void* video_features, const void* pos_table, int64_t pos_offset,
+                    void* inputs_embeds, void* hidden, int32_t* slot_index, int32_t* pos_ids,
+                    int32_t* status, int64_t batch, int64_t seq, int64_t dim, int64_t vocab,
+                    int64_t n_features, void* stream) {
+  if (input_ids == nullptr || embed_tokens == nullptr || slot_index == nullptr || pos_ids == nullptr)
+    return fail_msg("vb_embed_splice", "null operand");
+  if (video_mask != nullptr && video_features == nullptr && n_features > 0)
+    return fail_msg("vb_embed_splice", "video_mask without video_features");
+  VB_CHECK("vb_embed_splice",
+           vb::embed_splice_launch(reinterpret_cast<const long long*>(input_ids),
+                                   reinterpret_cast<const long long*>(attention_mask),
+                                   reinterpret_cast<const long long*>(video_mask), embed_tokens,
+                                   video_features, pos_table, pos_offset, inputs_embeds, hidden,
+                                   slot_index, pos_ids, status, batch, seq, dim, vocab, n_features,
+                                   st(stream)));
+}
+
+int vb_splice_bwd(const void* d_embeds, const int32_t* slot_index, void* d_features,
+                  int64_t positions, int64_t dim, int64_t n_features, void* stream) {
+  VB_CHECK("vb_splice_bwd",
+           vb::splice_bwd_launch(d_embeds, slot_index, d_features, positions, dim, n_features, st(stream)));
+}
+
+int vb_cross_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels, float* loss,
+                     float* row_lse, int32_t* n_valid, int64_t batch, int64_t seq, int64_t vocab,
+                     int64_t ldl, void* stream) {
+  if (logits == nullptr || labels == nullptr || loss == nullptr || row_lse == nullptr || n_valid == nullptr)
+    return fail_msg("vb_cross_entropy", "null operand");
+  VB_CHECK("vb_cross_entropy",
+           vb::ce_launch(logits, logits_dtype, reinterpret_cast<const long long*>(labels), loss,
+                         row_lse, n_valid, batch, seq, vocab, ldl, st(stream)));
+}
+
+int vb_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* labels,
+                         const float* row_lse, const int32_t* n_valid, const float* grad_scale,
+                         void* dlogits, int64_t batch, int64_t seq, int64_t vocab, int64_t ldl,
+                         int64_t ldd, void* stream) {
+  if (logits == nullptr || labels == nullptr || row_lse == nullptr || n_valid == nullptr || dlogits == nullptr)
+    return fail_msg("vb_cross_entropy_bwd", "null operand");
+  VB_CHECK("vb_cross_entropy_bwd",
+           vb::ce_bwd_launch(logits, logits_dtype, reinterpret_cast<const long long*>(labels),
+                             row_lse, n_valid, grad_scale, dlogits, batch, seq, vocab, ldl, ldd,
+                             st(stream)));
+}
+
+int vb_transpose(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in,
+                 int64_t ld_out, void* stream) {
+  VB_CHECK("vb_transpose", vb::transpose_launch(in, out, rows, cols, ld_in, ld_out, st(stream)));
+}
+
+int vb_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
+               void* stream) {
+  VB_CHECK("vb_convert", vb::convert_launch(src, src_dtype, dst, dst_dtype, n, st(stream)));
+}
+
+int vb_act_bwd(const void* dy, const void* saved, void* dx, int32_t epilogue, int64_t n,
+               void* stream) {
+  VB_CHECK("vb_act_bwd", vb::act_bwd_launch(dy, saved, dx, epilogue, n, st(stream)));
+}
+
+int vb_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx,
+              int32_t accumulate, void* stream) {
+  VB_CHECK("vb_colsum", vb::colsum_launch(x, out, rows, cols, ldx, accumulate, st(stream)));
+}
+
+int vb_add(const void* a, const void* b, void* y, int64_t n, void* stream) {
+  VB_CHECK("vb_add", vb::add_launch(a, b, y, n, st(stream)));
+}
+
+int vb_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+             float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+             const float* grad_scale, void* stream) {
+  if (step <= 0) return fail_msg("vb_adamw", "step must be >= 1");
+  VB_CHECK("vb_adamw", vb::adamw_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                        weight_decay, step, grad_scale, st(stream)));
+}
+
+int vb_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  VB_CHECK("vb_sumsq", vb::sumsq_launch(x, n, out, st(stream)));
+}
+
+int vb_gemv(const void* x, const void* w, const float* bias, const void* residual, void* y,
+            int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,
+            float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype, void* stream) {
+  VB_CHECK("vb_gemv", vb::gemv_launch(x, w, bias, residual, y, m, n, k, ldx, ldw, ldy, ldr, alpha,
+                                      alpha_cols, epilogue, out_dtype, st(stream)));
+}
+
+int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
+                              const int32_t* page_table, const int32_t* ctx_len,
+                              const int32_t* first_valid, void* out, int64_t batch, int64_t heads,
+                              int64_t d, int64_t page_size, int64_t max_pages, float scale,
+                              void* stream) {
+  VB_CHECK("vb_paged_decode_attention",
+           vb::paged_decode_attention_launch(qkv, k_cache, v_cache, page_table, ctx_len,
+                                             first_valid, out, batch, heads, d, page_size,
+                                             max_pages, scale, st(stream)));
+}
+
+int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,
+                      const int32_t* page_table, int64_t batch, int64_t seq, int64_t hd,
+                      int64_t page_size, int64_t max_pages, void* stream) {
+  VB_CHECK("vb_paged_kv_write", vb::paged_kv_write_launch(k, v, ld, k_cache, v_cache, page_table,
+                                                          batch, seq, hd, page_size, max_pages,
+                                                          st(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// Shared device helpers for the sm_100a kernels of the VideoBLIP hot path:
+// mbarrier / TMA / tcgen05 / TMEM inline-PTX wrappers, bf16 packing, epilogue math.
+// Everything here is header-only and compiled with
+//   nvcc -gencode arch=compute_100a,code=sm_100a
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VB_DEVICE __device__ __forceinline__
+
+namespace vb {
+
+// ---------------------------------------------------------------- misc
+VB_DEVICE uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+VB_DEVICE uint32_t lane_id() { return threadIdx.x & 31u; }
+
+VB_DEVICE bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------- mbarrier
+VB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+VB_DEVICE void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+VB_DEVICE void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+VB_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+VB_DEVICE void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+VB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline traps (surfacing as a CUDA error on the
+// host) instead of hanging the GPU box.
+VB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- TMA
+VB_DEVICE void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tiled load: c0 = innermost (contiguous) coordinate, c1 = row coordinate.
+VB_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+VB_DEVICE void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+VB_DEVICE void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+VB_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+VB_DEVICE void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+VB_DEVICE void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate, one issuing thread.
+VB_DEVICE void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on `bar` once all previously issued tcgen05.mma of this thread completed
+// (implies tcgen05.fence::before_thread_sync).
+VB_DEVICE void umma_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+VB_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base+i).
+VB_DEVICE void tmem_ld_16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major bf16 operand tile laid out by TMA with
+// the 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused: 1)
+//   bits [32,46) stride byte offset >> 4   bits [46,48) descriptor version (1 on sm_100)
+//   bits [61,64) layout type (2 = SWIZZLE_128B)
+VB_DEVICE uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- math / packing
+VB_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+VB_DEVICE float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+VB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+VB_DEVICE float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+VB_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+VB_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace vb
+
+// Epilogue selector shared by the tcgen05 and the generic GEMM (values are part of the
+// C ABI, see include/videoblip_b200.h).
+enum VbEpilogue : int {
+  VB_EPI_NONE = 0,       // C = alpha*(A.B^T) (+bias)
+  VB_EPI_GELU = 1,       // exact (erf) GELU
+  VB_EPI_RELU = 2,
+};

@@ -1,0 +1,528 @@
+// HBM-bound glue kernels of the VideoBLIP path: patch gather (im2col fused with the
+// (N,C,T,H,W)->(N*T,C,H,W) permute and the bf16 cast), CLS rows, LM input assembly
+// (embedding gather + video-feature splice + OPT learned positions), shifted cross
+// entropy forward/backward, transposes / conversions for the backward GEMM operands,
+// activation backward, column sums, fused AdamW.
+#include "common.cuh"
+#include "internal.h"
+
+namespace vb {
+
+// ------------------------------------------------------------------ dtype helpers
+template <typename T> VB_DEVICE float to_f32(T v);
+template <> VB_DEVICE float to_f32<float>(float v) { return v; }
+template <> VB_DEVICE float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> VB_DEVICE float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T> VB_DEVICE T from_f32(float v);
+template <> VB_DEVICE float from_f32<float>(float v) { return v; }
+template <> VB_DEVICE __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+template <> VB_DEVICE __half from_f32<__half>(float v) { return __float2half(v); }
+
+// ------------------------------------------------------------------ patch gather
+template <typename T>
+__global__ void __launch_bounds__(256)
+patch_gather_kernel(const T* __restrict__ px, __nv_bfloat16* __restrict__ out, long long nv,
+                    long long C, long long T_, long long H, long long W, long long P, long long gh,
+                    long long gw, long long kpad, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long col = idx % kpad;
+  const long long row = idx / kpad;
+  float v = 0.0f;
+  if (col < C * P * P) {
+    const long long pxx = col % P, pyy = (col / P) % P, c = col / (P * P);
+    const long long gx = row % gw, gy = (row / gw) % gh, f = row / (gw * gh);
+    const long long t = f % T_, vid = f / T_;
+    const long long y = gy * P + pyy, x = gx * P + pxx;
+    v = to_f32<T>(px[(((vid * C + c) * T_ + t) * H + y) * W + x]);
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+cudaError_t patch_gather_launch(const void* px, int dtype, void* out, long long nv, long long c,
+                                long long t, long long h, long long w, long long patch,
+                                long long kpad, cudaStream_t s) {
+  const long long gh = h / patch, gw = w / patch;
+  const long long total = nv * t * gh * gw * kpad;
+  if (total <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (dtype == VB_F32)
+    patch_gather_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(px), o, nv, c, t,
+                                                    h, w, patch, gh, gw, kpad, total);
+  else if (dtype == VB_BF16)
+    patch_gather_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(px), o, nv, c, t, h, w, patch, gh, gw, kpad, total);
+  else if (dtype == VB_F16)
+    patch_gather_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(px), o, nv, c,
+                                                     t, h, w, patch, gh, gw, kpad, total);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+__global__ void cls_rows_kernel(const __nv_bfloat16* cls, const __nv_bfloat16* pos,
+                                __nv_bfloat16* hidden, long long frames, long long tokens,
+                                long long dim) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= frames * dim) return;
+  const long long f = idx / dim, c = idx % dim;
+  hidden[f * tokens * dim + c] =
+      __float2bfloat16(__bfloat162float(cls[c]) + __bfloat162float(pos[c]));
+}
+
+cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long long frames,
+                            long long tokens, long long dim, cudaStream_t s) {
+  const long long total = frames * dim;
+  if (total <= 0) return cudaSuccess;
+  cls_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(cls), reinterpret_cast<const __nv_bfloat16*>(pos),
+      reinterpret_cast<__nv_bfloat16*>(hidden), frames, tokens, dim);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ LM input assembly
+// Single block: slot_index = exclusive rank among masked positions (row-major over
+// (batch, seq), the order of a boolean-mask assignment), pos_ids = OPT positions.
+__global__ void __launch_bounds__(1024)
+splice_index_kernel(const long long* attn, const long long* vmask, int* slot_index, int* pos_ids,
+                    int* status, long long batch, long long seq, long long pos_offset,
+                    long long n_features) {
+  __shared__ int partial[1024];
+  const long long n = batch * seq;
+  const int tid = threadIdx.x;
+  const long long chunk = (n + 1023) / 1024;
+  const long long lo = tid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+  int cnt = 0;
+  if (vmask != nullptr)
+    for (long long i = lo; i < hi; ++i) cnt += vmask[i] != 0;
+  partial[tid] = cnt;
+  __syncthreads();
+  // inclusive Hillis-Steele scan
+  for (int off = 1; off < 1024; off <<= 1) {
+    int v = tid >= off ? partial[tid - off] : 0;
+    __syncthreads();
+    partial[tid] += v;
+    __syncthreads();
+  }
+  int base = partial[tid] - cnt;
+  for (long long i = lo; i < hi; ++i) {
+    if (vmask != nullptr && vmask[i] != 0) slot_index[i] = base++;
+    else slot_index[i] = -1;
+  }
+  if (tid == 1023 && status != nullptr) {
+    const int total = partial[1023];
+    status[0] = (vmask != nullptr && total != n_features) ? 1 : 0;
+    status[1] = total;
+  }
+  // positions: one thread per batch row
+  for (long long b = tid; b < batch; b += 1024) {
+    long long run = 0;
+    for (long long l = 0; l < seq; ++l) {
+      const long long m = attn != nullptr ? (attn[b * seq + l] != 0) : 1;
+      run += m;
+      pos_ids[b * seq + l] = static_cast<int>(run * m - 1 + pos_offset);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+splice_gather_kernel(const long long* ids, const int* slot_index, const int* pos_ids,
+                     const __nv_bfloat16* embed, const __nv_bfloat16* feats,
+                     const __nv_bfloat16* pos_table, __nv_bfloat16* inputs_embeds,
+                     __nv_bfloat16* hidden, long long dim, long long vocab, long long n_features) {
+  const long long pos = blockIdx.x;
+  const int slot = slot_index[pos];
+  const __nv_bfloat16* src;
+  if (slot >= 0) {
+    src = feats + static_cast<long long>(slot < n_features ? slot : 0) * dim;
+  } else {
+    long long id = ids[pos];
+    if (id < 0 || id >= vocab) id = 0;
+    src = embed + id * dim;
+  }
+  const __nv_bfloat16* pt =
+      pos_table != nullptr ? pos_table + static_cast<long long>(pos_ids[pos]) * dim : nullptr;
+  for (long long c = threadIdx.x; c < dim; c += blockDim.x) {
+    const __nv_bfloat16 e = src[c];
+    if (inputs_embeds != nullptr) inputs_embeds[pos * dim + c] = e;
+    if (hidden != nullptr) {
+      float h = __bfloat162float(e);
+      if (pt != nullptr) h += __bfloat162float(pt[c]);
+      hidden[pos * dim + c] = __float2bfloat16(h);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+splice_bwd_kernel(const __nv_bfloat16* d_embeds, const int* slot_index, __nv_bfloat16* d_feats,
+                  long long dim, long long n_features) {
+  const long long pos = blockIdx.x;
+  const int slot = slot_index[pos];
+  if (slot < 0 || slot >= n_features) return;
+  for (long long c = threadIdx.x; c < dim; c += blockDim.x)
+    d_feats[static_cast<long long>(slot) * dim + c] = d_embeds[pos * dim + c];
+}
+
+// ------------------------------------------------------------------ cross entropy
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_row_kernel(const T* logits, const long long* labels, float* row_lse, long long seq,
+              long long vocab, long long ldl) {
+  // block r handles logits row (b, l); target = labels[b, l+1]
+  const long long r = blockIdx.x;
+  const long long l = r % seq;
+  bool valid = (l + 1 < seq);
+  long long target = -100;
+  if (valid) {
+    target = labels[r + 1];
+    valid = target >= 0 && target < vocab;
+  }
+  if (!valid) {
+    if (threadIdx.x == 0) row_lse[r] = 0.0f;
+    return;
+  }
+  const T* row = logits + r * ldl;
+  __shared__ float red[8];
+  float mx = -INFINITY;
+  for (long long c = threadIdx.x; c < vocab; c += 256) mx = fmaxf(mx, to_f32<T>(row[c]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (long long c = threadIdx.x; c < vocab; c += 256) sum += __expf(to_f32<T>(row[c]) - mx);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    row_lse[r] = mx + logf(tot);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_finalize_kernel(const T* logits, const long long* labels, const float* row_lse, float* loss,
+                   int* n_valid, long long rows, long long seq, long long vocab, long long ldl) {
+  __shared__ float ssum[256];
+  __shared__ int scnt[256];
+  float acc = 0.0f;
+  int cnt = 0;
+  for (long long r = threadIdx.x; r < rows; r += 256) {
+    const long long l = r % seq;
+    if (l + 1 >= seq) continue;
+    const long long target = labels[r + 1];
+    if (target < 0 || target >= vocab) continue;
+    acc += row_lse[r] - to_f32<T>(logits[r * ldl + target]);
+    cnt += 1;
+  }
+  ssum[threadIdx.x] = acc;
+  scnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + off];
+      scnt[threadIdx.x] += scnt[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *n_valid = scnt[0];
+    // torch: mean over zero valid targets is NaN
+    *loss = scnt[0] > 0 ? ssum[0] / static_cast<float>(scnt[0]) : __int_as_float(0x7fc00000);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const T* logits, const long long* labels, const float* row_lse, const int* n_valid,
+              const float* grad_scale, __nv_bfloat16* dlogits, long long seq, long long vocab,
+              long long ldl, long long ldd) {
+  const long long r = blockIdx.x;
+  const long long l = r % seq;
+  bool valid = (l + 1 < seq);
+  long long target = -100;
+  if (valid) {
+    target = labels[r + 1];
+    valid = target >= 0 && target < vocab;
+  }
+  __nv_bfloat16* out = dlogits + r * ldd;
+  if (!valid) {
+    for (long long c = threadIdx.x; c < vocab; c += 256) out[c] = __float2bfloat16(0.0f);
+    return;
+  }
+  const float gs = (grad_scale != nullptr ? *grad_scale : 1.0f) / static_cast<float>(*n_valid);
+  const float lse = row_lse[r];
+  const T* row = logits + r * ldl;
+  for (long long c = threadIdx.x; c < vocab; c += 256) {
+    float pr = __expf(to_f32<T>(row[c]) - lse);
+    if (c == target) pr -= 1.0f;
+    out[c] = __float2bfloat16(pr * gs);
+  }
+}
+
+cudaError_t ce_launch(const void* logits, int dtype, const long long* labels, float* loss,
+                      float* row_lse, int* n_valid, long long batch, long long seq,
+                      long long vocab, long long ldl, cudaStream_t s) {
+  const long long rows = batch * seq;
+  if (rows <= 0) return cudaErrorInvalidValue;
+  if (dtype == VB_BF16) {
+    const __nv_bfloat16* lg = reinterpret_cast<const __nv_bfloat16*>(logits);
+    ce_row_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl);
+    ce_finalize_kernel<__nv_bfloat16><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl);
+  } else if (dtype == VB_F32) {
+    const float* lg = reinterpret_cast<const float*>(logits);
+    ce_row_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl);
+    ce_finalize_kernel<float><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels,
+                          const float* row_lse, const int* n_valid, const float* grad_scale,
+                          void* dlogits, long long batch, long long seq, long long vocab,
+                          long long ldl, long long ldd, cudaStream_t s) {
+  const long long rows = batch * seq;
+  if (rows <= 0) return cudaErrorInvalidValue;
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dlogits);
+  if (dtype == VB_BF16)
+    ce_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd);
+  else if (dtype == VB_F32)
+    ce_bwd_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(
+        reinterpret_cast<const float*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ transpose / convert
+__global__ void __launch_bounds__(256)
+transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                 long long rows, long long cols, long long ld_in, long long ld_out) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const long long c0 = static_cast<long long>(blockIdx.x) * 32;
+  const long long r0 = static_cast<long long>(blockIdx.y) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const long long r = r0 + ty + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + i][tx] = in[r * ld_in + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const long long c = c0 + ty + i, r = r0 + tx;
+    if (r < rows && c < cols) out[c * ld_out + r] = tile[tx][ty + i];
+  }
+}
+
+cudaError_t transpose_launch(const void* in, void* out, long long rows, long long cols,
+                             long long ld_in, long long ld_out, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  if (grid.y > 65535) return cudaErrorInvalidValue;
+  transpose_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                        reinterpret_cast<__nv_bfloat16*>(out), rows, cols, ld_in,
+                                        ld_out);
+  return cudaGetLastError();
+}
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_kernel(const S* src, D* dst, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = from_f32<D>(to_f32<S>(src[i]));
+}
+
+template <typename S>
+static cudaError_t convert_from(const S* src, void* dst, int dd, long long n, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  if (dd == VB_BF16) convert_kernel<S, __nv_bfloat16><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  else if (dd == VB_F32) convert_kernel<S, float><<<grid, 256, 0, s>>>(src, reinterpret_cast<float*>(dst), n);
+  else if (dd == VB_F16) convert_kernel<S, __half><<<grid, 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t convert_launch(const void* src, int sd, void* dst, int dd, long long n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (sd == VB_BF16) return convert_from(reinterpret_cast<const __nv_bfloat16*>(src), dst, dd, n, s);
+  if (sd == VB_F32) return convert_from(reinterpret_cast<const float*>(src), dst, dd, n, s);
+  if (sd == VB_F16) return convert_from(reinterpret_cast<const __half*>(src), dst, dd, n, s);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ activation bwd, sums
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* saved, __nv_bfloat16* dx, int epi,
+               long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float g = __bfloat162float(dy[i]);
+    const float sv = __bfloat162float(saved[i]);
+    float d;
+    if (epi == VB_EPI_GELU) d = g * gelu_erf_grad(sv);
+    else if (epi == VB_EPI_RELU) d = sv > 0.0f ? g : 0.0f;
+    else d = g;
+    dx[i] = __float2bfloat16(d);
+  }
+}
+
+cudaError_t act_bwd_launch(const void* dy, const void* saved, void* dx, int epi, long long n,
+                           cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  act_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                      reinterpret_cast<const __nv_bfloat16*>(saved),
+                                      reinterpret_cast<__nv_bfloat16*>(dx), epi, n);
+  return cudaGetLastError();
+}
+
+// Block = 32 columns x 8 row lanes; grid.y splits rows; atomics only across grid.y.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* x, float* out, long long rows, long long cols, long long ldx) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const long long c = static_cast<long long>(blockIdx.x) * 32 + cx;
+  const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r_lo = static_cast<long long>(blockIdx.y) * rows_per;
+  const long long r_hi = r_lo + rows_per < rows ? r_lo + rows_per : rows;
+  float acc = 0.0f;
+  if (c < cols)
+    for (long long r = r_lo + ry; r < r_hi; r += 8) acc += __bfloat162float(x[r * ldx + c]);
+  sm[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    if (gridDim.y == 1) out[c] += t;
+    else atomicAdd(&out[c], t);
+  }
+}
+
+cudaError_t colsum_launch(const void* x, float* out, long long rows, long long cols, long long ldx,
+                          int accumulate, cudaStream_t s) {
+  if (cols <= 0) return cudaSuccess;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * cols, s);
+    if (e != cudaSuccess) return e;
+  }
+  if (rows <= 0) return cudaSuccess;
+  unsigned gy = static_cast<unsigned>(rows / 2048 + 1);
+  if (gy > 64) gy = 64;
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), gy);
+  colsum_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ldx);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
+cudaError_t add_launch(const void* a, const void* b, void* y, long long n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  add_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                  reinterpret_cast<const __nv_bfloat16*>(b),
+                                  reinterpret_cast<__nv_bfloat16*>(y), n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ optimizer
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
+             float b2, float eps, float wd, float bc1, float bc2_sqrt, const float* grad_scale) {
+  const float gs = grad_scale != nullptr ? *grad_scale : 1.0f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float grad = g[i] * gs;
+    float param = p[i];
+    param -= lr * wd * param;  // decoupled weight decay (torch.optim.AdamW)
+    const float mi = b1 * m[i] + (1.0f - b1) * grad;
+    const float vi = b2 * v[i] + (1.0f - b2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    param -= (lr / bc1) * (mi / denom);
+    p[i] = param;
+  }
+}
+
+cudaError_t adamw_launch(float* p, const float* g, float* m, float* v, long long n, float lr,
+                         float b1, float b2, float eps, float wd, long long step,
+                         const float* grad_scale, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const float bc1 = 1.0f - powf(b1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(b2, static_cast<float>(step));
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
+  adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* x, long long n, float* out) {
+  __shared__ float red[8];
+  float acc = 0.0f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc += x[i] * x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 4 ? n / 256 + 1 : 148 * 4);
+  sumsq_kernel<<<grid, 256, 0, s>>>(x, n, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ splice launchers
+cudaError_t embed_splice_launch(const long long* ids, const long long* attn, const long long* vmask,
+                                const void* embed, const void* feats, const void* pos_table,
+                                long long pos_offset, void* inputs_embeds, void* hidden,
+                                int* slot_index, int* pos_ids, int* status, long long batch,
+                                long long seq, long long dim, long long vocab, long long n_features,
+                                cudaStream_t s) {
+  const long long n = batch * seq;
+  if (n <= 0) return cudaErrorInvalidValue;
+  splice_index_kernel<<<1, 1024, 0, s>>>(attn, vmask, slot_index, pos_ids, status, batch, seq,
+                                         pos_offset, n_features);
+  splice_gather_kernel<<<static_cast<unsigned>(n), 128, 0, s>>>(
+      ids, slot_index, pos_ids, reinterpret_cast<const __nv_bfloat16*>(embed),
+      reinterpret_cast<const __nv_bfloat16*>(feats), reinterpret_cast<const __nv_bfloat16*>(pos_table),
+      reinterpret_cast<__nv_bfloat16*>(inputs_embeds), reinterpret_cast<__nv_bfloat16*>(hidden), dim,
+      vocab, n_features);
+  return cudaGetLastError();
+}
+
+cudaError_t splice_bwd_launch(const void* d_embeds, const int* slot_index, void* d_feats,
+                              long long positions, long long dim, long long n_features,
+                              cudaStream_t s) {
+  if (positions <= 0) return cudaSuccess;
+  splice_bwd_kernel<<<static_cast<unsigned>(positions), 128, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_embeds), slot_index,
+      reinterpret_cast<__nv_bfloat16*>(d_feats), dim, n_features);
+  return cudaGetLastError();
+}
+
+}  // namespace vb

@@ -1,0 +1,411 @@
+// bf16 GEMM on the 5th-generation tensor cores:  C = epi(A . B^T)
+//   A (M,K) and B (N,K) K-major bf16, fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, kStages ring)
+//   warp 1      MMA issuer     (one thread, tcgen05.mma cta_group::1, 128 x BN x 16)
+//   warp 2      TMEM allocator (512 columns = two accumulator stages)
+//   warps 4-11  epilogue       (tcgen05.ld -> bias / alpha / GELU|ReLU / residual -> global)
+// The two TMEM accumulator stages let the epilogue of tile i overlap the main loop of
+// tile i+1.  Used for every dense projection of the VideoBLIP path (see
+// include/videoblip_b200.h, vb_gemm).
+#include "common.cuh"
+#include "gemm.h"
+
+namespace vb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM column offset between the two accumulator stages
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+  static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
+};
+
+struct EpiParams {
+  void* c;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long m, n;
+  long long ldc, ldr;
+  float alpha, beta;
+  long long alpha_cols;
+  long long row_group;
+  int epilogue;
+  int out_f32;
+};
+
+// One thread finishes 16 consecutive columns of one row.
+VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
+                              const uint32_t (&acc)[16]) {
+  if (row >= p.m || col0 >= p.n) return;
+  long long out_row = row, res_row = row;
+  if (p.row_group > 0) {
+    out_row = row + row / p.row_group + 1;
+    res_row = 1 + row % p.row_group;
+  }
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  const bool full = (col0 + 16 <= p.n);
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.alpha != 1.0f) {
+    const long long ac = p.alpha_cols <= 0 ? p.n : p.alpha_cols;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < ac) v[j] *= p.alpha;
+  }
+  if (p.epilogue == VB_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.epilogue == VB_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.residual != nullptr) {
+    const __nv_bfloat16* r = p.residual + res_row * p.ldr + col0;
+    if (full) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(r + 8 * h));
+        float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+               f3 = unpack_bf16x2(u.w);
+        v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+        v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) v[j] += __bfloat162float(r[j]);
+    }
+  }
+  if (p.out_f32) {
+    float* c = reinterpret_cast<float*>(p.c) + out_row * p.ldc + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.beta != 0.0f) {
+          float4 old = *reinterpret_cast<const float4*>(c + j);
+          o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+        }
+        *reinterpret_cast<float4*>(c + j) = o;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) c[j] = v[j] + (p.beta != 0.0f ? p.beta * c[j] : 0.0f);
+    }
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row * p.ldc + col0;
+    if (full) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (p.beta != 0.0f) {
+          uint4 u = *reinterpret_cast<const uint4*>(c + 8 * h);
+          float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                 f3 = unpack_bf16x2(u.w);
+          v[8 * h + 0] += p.beta * f0.x; v[8 * h + 1] += p.beta * f0.y;
+          v[8 * h + 2] += p.beta * f1.x; v[8 * h + 3] += p.beta * f1.y;
+          v[8 * h + 4] += p.beta * f2.x; v[8 * h + 5] += p.beta * f2.y;
+          v[8 * h + 6] += p.beta * f3.x; v[8 * h + 7] += p.beta * f3.y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
+        o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+        o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
+        o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+        *reinterpret_cast<uint4*>(c + 8 * h) = o;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) {
+          float o = v[j] + (p.beta != 0.0f ? p.beta * __bfloat162float(c[j]) : 0.0f);
+          c[j] = __float2bfloat16(o);
+        }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const EpiParams p,
+                    const int num_k_blocks, const int m_tiles, const int n_tiles) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK,
+                      m_blk * kBM);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK,
+                      n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in >>4 units
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which half of the column chunks
+    constexpr int kChunks = BN / 16;
+    constexpr int kHalfChunks = (kChunks + 1) / 2;
+    const int c_begin = half * kHalfChunks;
+    const int c_end = (c_begin + kHalfChunks < kChunks) ? c_begin + kHalfChunks : kChunks;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = static_cast<long long>(m_blk) * kBM + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             acc * kAccStride;
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        uint32_t r[16];
+        tmem_ld_16(t_row + ch * 16, r);
+        tmem_ld_wait();
+        if (ch == c_end - 1) {
+          // all TMEM reads of this warp for this tile are done: release the stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + ch * 16, r);
+      }
+      if (c_begin >= c_end) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// (rows, cols) bf16 row-major matrix with row stride ld; box = 64 columns x box_rows rows.
+static bool make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols,
+                      long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool gemm_tcgen05_eligible(const vb_gemm_args& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (a.m <= 0 || a.n <= 0 || a.k <= 0) return false;
+  if (a.k % 8 != 0 || a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
+  if (!al16(a.a) || !al16(a.b) || !al16(a.c)) return false;
+  if (a.n % 8 != 0) return false;
+  if (a.out_dtype == VB_BF16 ? (a.ldc % 8 != 0) : (a.ldc % 4 != 0)) return false;
+  if (a.bias != nullptr && !al16(a.bias)) return false;
+  if (a.residual != nullptr && (!al16(a.residual) || a.ldr % 8 != 0)) return false;
+  if (a.m > (1ll << 31) - 256 || a.n > (1ll << 31) - 256 || a.k > (1ll << 31) - 256) return false;
+  return true;
+}
+
+static int pick_block_n(long long m, long long n) {
+  // Prefer the widest tile that divides N; 176 covers the ViT widths 1408 / 4224.
+  const int cands[4] = {256, 176, 128, 64};
+  int best = 64;
+  double best_cost = 1e300;
+  const long long m_tiles = (m + kBM - 1) / kBM;
+  for (int c = 0; c < 4; ++c) {
+    const int bn = cands[c];
+    const long long n_tiles = (n + bn - 1) / bn;
+    const long long tiles = m_tiles * n_tiles;
+    const long long waves = (tiles + 147) / 148;
+    // time ~ waves * tile cost; narrow tiles run at lower tensor efficiency (smem-bound)
+    const double eff = bn >= 176 ? 1.0 : (bn == 128 ? 0.9 : 0.6);
+    const double cost = static_cast<double>(waves) * bn / eff;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int BN>
+static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStream_t stream,
+                             int force_grid) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, a.a, a.m, a.k, a.lda, kBM)) return cudaErrorInvalidValue;
+  if (!make_tmap(&tb, a.b, a.n, a.k, a.ldb, BN)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int m_tiles = static_cast<int>((a.m + kBM - 1) / kBM);
+  const int n_tiles = static_cast<int>((a.n + BN - 1) / BN);
+  const int k_blocks = static_cast<int>((a.k + kBK - 1) / kBK);
+  int sms = 148;
+  {
+    static int cached = 0;
+    if (cached == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+      if (cached <= 0) cached = 148;
+    }
+    sms = cached;
+  }
+  long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  if (force_grid > 0 && force_grid < grid) grid = force_grid;
+  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ep, k_blocks,
+                                                                          m_tiles, n_tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
+  EpiParams ep;
+  ep.c = a.c;
+  ep.bias = a.bias;
+  ep.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+  ep.m = a.m; ep.n = a.n; ep.ldc = a.ldc; ep.ldr = a.ldr;
+  ep.alpha = a.alpha; ep.beta = a.beta;
+  ep.alpha_cols = a.alpha_cols;
+  ep.row_group = a.row_group;
+  ep.epilogue = a.epilogue;
+  ep.out_f32 = (a.out_dtype == VB_F32) ? 1 : 0;
+  int bn = a.reserved > 0 ? a.reserved : pick_block_n(a.m, a.n);
+  switch (bn) {
+    case 256: return launch_bn<256>(a, ep, stream, 0);
+    case 176: return launch_bn<176>(a, ep, stream, 0);
+    case 128: return launch_bn<128>(a, ep, stream, 0);
+    case 64: return launch_bn<64>(a, ep, stream, 0);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace vb

@@ -1,0 +1,69 @@
+// Internal launcher declarations (one per kernel family) used by api.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/videoblip_b200.h"
+
+namespace vb {
+
+struct LnParams;
+struct LnBwdParams;
+
+cudaError_t layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta,
+                          void* y, float* mean, float* rstd, long long rows, long long cols,
+                          long long ldx, long long ldr, long long ldy, float eps, cudaStream_t s);
+cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
+                          const float* rstd, const void* dx_add, void* dx, float* dgamma,
+                          float* dbeta, long long rows, long long cols, cudaStream_t s);
+
+cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream);
+cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream);
+
+cudaError_t patch_gather_launch(const void* px, int dtype, void* out, long long nv, long long c,
+                                long long t, long long h, long long w, long long patch,
+                                long long kpad, cudaStream_t s);
+cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long long frames,
+                            long long tokens, long long dim, cudaStream_t s);
+cudaError_t embed_splice_launch(const long long* ids, const long long* attn, const long long* vmask,
+                                const void* embed, const void* feats, const void* pos_table,
+                                long long pos_offset, void* inputs_embeds, void* hidden,
+                                int* slot_index, int* pos_ids, int* status, long long batch,
+                                long long seq, long long dim, long long vocab, long long n_features,
+                                cudaStream_t s);
+cudaError_t splice_bwd_launch(const void* d_embeds, const int* slot_index, void* d_feats,
+                              long long positions, long long dim, long long n_features,
+                              cudaStream_t s);
+cudaError_t ce_launch(const void* logits, int dtype, const long long* labels, float* loss,
+                      float* row_lse, int* n_valid, long long batch, long long seq,
+                      long long vocab, long long ldl, cudaStream_t s);
+cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels,
+                          const float* row_lse, const int* n_valid, const float* grad_scale,
+                          void* dlogits, long long batch, long long seq, long long vocab,
+                          long long ldl, long long ldd, cudaStream_t s);
+cudaError_t transpose_launch(const void* in, void* out, long long rows, long long cols,
+                             long long ld_in, long long ld_out, cudaStream_t s);
+cudaError_t convert_launch(const void* src, int sd, void* dst, int dd, long long n, cudaStream_t s);
+cudaError_t act_bwd_launch(const void* dy, const void* saved, void* dx, int epi, long long n,
+                           cudaStream_t s);
+cudaError_t colsum_launch(const void* x, float* out, long long rows, long long cols, long long ldx,
+                          int accumulate, cudaStream_t s);
+cudaError_t add_launch(const void* a, const void* b, void* y, long long n, cudaStream_t s);
+cudaError_t adamw_launch(float* p, const float* g, float* m, float* v, long long n, float lr,
+                         float b1, float b2, float eps, float wd, long long step,
+                         const float* grad_scale, cudaStream_t s);
+cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s);
+
+cudaError_t gemv_launch(const void* x, const void* w, const float* bias, const void* residual,
+                        void* y, long long m, long long n, long long k, long long ldx,
+                        long long ldw, long long ldy, long long ldr, float alpha,
+                        long long alpha_cols, int epilogue, int out_dtype, cudaStream_t s);
+cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* v_cache,
+                                          const int* page_table, const int* ctx_len,
+                                          const int* first_valid, void* out, long long batch,
+                                          long long heads, long long d, long long page_size,
+                                          long long max_pages, float scale, cudaStream_t s);
+cudaError_t paged_kv_write_launch(const void* k, const void* v, long long ld, void* k_cache,
+                                  void* v_cache, const int* page_table, long long batch,
+                                  long long seq, long long hd, long long page_size,
+                                  long long max_pages, cudaStream_t s);
+}  // namespace vb

@@ -1,0 +1,258 @@
+// LayerNorm forward / backward, one warp per row, bf16 I/O with fp32 statistics.
+// The row is held in registers between the statistics and the normalisation pass
+// (16-byte vector loads) so HBM sees one read and one write per element; a strided
+// multi-pass variant covers shapes that break the vector path (tiny test configs).
+#include "common.cuh"
+#include "internal.h"
+
+namespace vb {
+
+constexpr int kLnWarps = 4;
+
+struct LnParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* res;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* y;
+  float* mean;
+  float* rstd;
+  long long rows, cols, ldx, ldr, ldy;
+  float eps;
+};
+
+// VPL = 16-byte vectors per lane; cols <= VPL*256, cols % 8 == 0.
+template <int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nvec = static_cast<int>(p.cols / 8);
+  float v[VPL][8];
+  float sum = 0.0f;
+  const __nv_bfloat16* xr = p.x + row * p.ldx;
+  const __nv_bfloat16* rr = p.res != nullptr ? p.res + row * p.ldr : nullptr;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+             d = unpack_bf16x2(u.w);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = b.x; v[i][3] = b.y;
+      v[i][4] = c.x; v[i][5] = c.y; v[i][6] = d.x; v[i][7] = d.y;
+      if (rr != nullptr) {
+        uint4 w = *reinterpret_cast<const uint4*>(rr + vi * 8);
+        float2 a2 = unpack_bf16x2(w.x), b2 = unpack_bf16x2(w.y), c2 = unpack_bf16x2(w.z),
+               d2 = unpack_bf16x2(w.w);
+        v[i][0] += a2.x; v[i][1] += a2.y; v[i][2] += b2.x; v[i][3] += b2.y;
+        v[i][4] += c2.x; v[i][5] += c2.y; v[i][6] += d2.x; v[i][7] += d2.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(p.cols);
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.cols) + p.eps);
+  if (lane == 0) {
+    if (p.mean != nullptr) p.mean[row] = mean;
+    if (p.rstd != nullptr) p.rstd[row] = rstd;
+  }
+  __nv_bfloat16* yr = p.y + row * p.ldy;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + vi * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + vi * 8) = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_generic_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const __nv_bfloat16* xr = p.x + row * p.ldx;
+  const __nv_bfloat16* rr = p.res != nullptr ? p.res + row * p.ldr : nullptr;
+  auto at = [&](long long c) {
+    float v = __bfloat162float(xr[c]);
+    if (rr != nullptr) v += __bfloat162float(rr[c]);
+    return v;
+  };
+  float sum = 0.0f;
+  for (long long c = lane; c < p.cols; c += 32) sum += at(c);
+  const float mean = warp_sum(sum) / static_cast<float>(p.cols);
+  float sq = 0.0f;
+  for (long long c = lane; c < p.cols; c += 32) {
+    const float d = at(c) - mean;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.cols) + p.eps);
+  if (lane == 0) {
+    if (p.mean != nullptr) p.mean[row] = mean;
+    if (p.rstd != nullptr) p.rstd[row] = rstd;
+  }
+  for (long long c = lane; c < p.cols; c += 32)
+    p.y[row * p.ldy + c] = __float2bfloat16((at(c) - mean) * rstd * p.gamma[c] + p.beta[c]);
+}
+
+template <int VPL>
+static void launch_vec(const LnParams& p, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
+  ln_fwd_vec_kernel<VPL><<<grid, kLnWarps * 32, 0, s>>>(p);
+}
+
+cudaError_t layernorm_launch(const LnParams& p, cudaStream_t s) {
+  if (p.rows <= 0 || p.cols <= 0) return cudaSuccess;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool vec = p.cols % 8 == 0 && p.cols <= 12 * 256 && al(p.x) && al(p.y) && al(p.gamma) &&
+                   al(p.beta) && p.ldx % 8 == 0 && p.ldy % 8 == 0 &&
+                   (p.res == nullptr || (al(p.res) && p.ldr % 8 == 0));
+  if (vec) {
+    const int vpl = static_cast<int>((p.cols / 8 + 31) / 32);
+    if (vpl <= 1) launch_vec<1>(p, s);
+    else if (vpl <= 2) launch_vec<2>(p, s);
+    else if (vpl <= 3) launch_vec<3>(p, s);
+    else if (vpl <= 4) launch_vec<4>(p, s);
+    else if (vpl <= 6) launch_vec<6>(p, s);
+    else if (vpl <= 8) launch_vec<8>(p, s);
+    else if (vpl <= 10) launch_vec<10>(p, s);
+    else launch_vec<12>(p, s);
+  } else {
+    const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
+    ln_fwd_generic_kernel<<<grid, kLnWarps * 32, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ backward
+struct LnBwdParams {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* xin;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  const __nv_bfloat16* dx_add;
+  __nv_bfloat16* dx;
+  float* dgamma;
+  float* dbeta;
+  long long rows, cols;
+};
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.  One warp per row.
+__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_kernel(const LnBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const __nv_bfloat16* dyr = p.dy + row * p.cols;
+  const __nv_bfloat16* xr = p.xin + row * p.cols;
+  const float mean = p.mean[row], rstd = p.rstd[row];
+  float s1 = 0.0f, s2 = 0.0f;
+  for (long long c = lane; c < p.cols; c += 32) {
+    const float g = __bfloat162float(dyr[c]) * p.gamma[c];
+    const float xh = (__bfloat162float(xr[c]) - mean) * rstd;
+    s1 += g;
+    s2 += g * xh;
+  }
+  s1 = warp_sum(s1) / static_cast<float>(p.cols);
+  s2 = warp_sum(s2) / static_cast<float>(p.cols);
+  for (long long c = lane; c < p.cols; c += 32) {
+    const float g = __bfloat162float(dyr[c]) * p.gamma[c];
+    const float xh = (__bfloat162float(xr[c]) - mean) * rstd;
+    float d = rstd * (g - s1 - xh * s2);
+    if (p.dx_add != nullptr) d += __bfloat162float(p.dx_add[row * p.cols + c]);
+    p.dx[row * p.cols + c] = __float2bfloat16(d);
+  }
+}
+
+// dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy.  Block = 32 columns x 8 row lanes;
+// every column is owned by exactly one block, so the accumulation is deterministic.
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const LnBwdParams p) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const long long c = static_cast<long long>(blockIdx.x) * 32 + cx;
+  float ag = 0.0f, ab = 0.0f;
+  if (c < p.cols) {
+    for (long long r = ry; r < p.rows; r += 8) {
+      const float dyv = __bfloat162float(p.dy[r * p.cols + c]);
+      const float xh = (__bfloat162float(p.xin[r * p.cols + c]) - p.mean[r]) * p.rstd[r];
+      ag += dyv * xh;
+      ab += dyv;
+    }
+  }
+  sg[ry][cx] = ag;
+  sb[ry][cx] = ab;
+  __syncthreads();
+  if (ry == 0 && c < p.cols) {
+    float tg = 0.0f, tb = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tg += sg[i][cx]; tb += sb[i][cx]; }
+    p.dgamma[c] += tg;
+    p.dbeta[c] += tb;
+  }
+}
+
+cudaError_t layernorm_bwd_launch(const LnBwdParams& p, cudaStream_t s) {
+  if (p.rows <= 0 || p.cols <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
+  ln_bwd_dx_kernel<<<grid, kLnWarps * 32, 0, s>>>(p);
+  if (p.dgamma != nullptr && p.dbeta != nullptr) {
+    ln_bwd_param_kernel<<<static_cast<unsigned>((p.cols + 31) / 32), 256, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+
+cudaError_t layernorm_fwd(const void* x, const void* residual, const float* gamma, const float* beta,
+                          void* y, float* mean, float* rstd, long long rows, long long cols,
+                          long long ldx, long long ldr, long long ldy, float eps, cudaStream_t s) {
+  LnParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.gamma = gamma; p.beta = beta;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.mean = mean; p.rstd = rstd;
+  p.rows = rows; p.cols = cols; p.ldx = ldx; p.ldr = ldr; p.ldy = ldy; p.eps = eps;
+  return layernorm_launch(p, s);
+}
+
+cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
+                          const float* rstd, const void* dx_add, void* dx, float* dgamma,
+                          float* dbeta, long long rows, long long cols, cudaStream_t s) {
+  LnBwdParams p;
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+  p.xin = reinterpret_cast<const __nv_bfloat16*>(xin);
+  p.gamma = gamma; p.mean = mean; p.rstd = rstd;
+  p.dx_add = reinterpret_cast<const __nv_bfloat16*>(dx_add);
+  p.dx = reinterpret_cast<__nv_bfloat16*>(dx);
+  p.dgamma = dgamma; p.dbeta = dbeta; p.rows = rows; p.cols = cols;
+  return layernorm_bwd_launch(p, s);
+}
+
+}  // namespace vb

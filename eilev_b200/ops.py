@@ -1,0 +1,372 @@
+"""Tensor-level wrappers over the C ABI (``include/videoblip_b200.h``).
+
+PyTorch is used only for device memory and stream handles: each function takes CUDA
+tensors, enqueues one native kernel family on torch's current stream and returns.
+There is no CPU path — a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_GELU, EPI_NONE, EPI_RELU, GEMM_AUTO, GEMM_GENERIC,  # noqa: F401
+                   GEMM_TCGEN05, VB_BF16, VB_F16, VB_F32, AttnArgs, AttnBwdArgs, GemmArgs, check)
+
+_DT = {torch.bfloat16: VB_BF16, torch.float32: VB_F32, torch.float16: VB_F16}
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: torch.Tensor, dtype: torch.dtype | None, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.VbError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.VbError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
+         residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
+         epilogue: int = EPI_NONE, alpha: float = 1.0, alpha_cols: int = 0, beta: float = 0.0,
+         out_dtype: torch.dtype = torch.bfloat16, row_group: int = 0, out_rows: int | None = None,
+         backend: int = GEMM_AUTO, block_n: int = 0) -> torch.Tensor:
+    """``out = act(alpha * (a @ w.T + bias)) + residual (+ beta*out)``.
+
+    a: (M, K) bf16 (last dim contiguous), w: (N, K) bf16 — an ``nn.Linear`` weight.
+    """
+    _need(a, torch.bfloat16, "gemm.a")
+    _need(w, torch.bfloat16, "gemm.w")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    m, k = a.shape
+    n = w.shape[0]
+    if out is None:
+        rows = out_rows if out_rows is not None else m
+        out = torch.empty((rows, n), dtype=out_dtype, device=a.device)
+    else:
+        assert out.stride(-1) == 1
+        out_dtype = out.dtype
+    if bias is not None:
+        _need(bias, torch.float32, "gemm.bias")
+        assert bias.numel() == n
+    if residual is not None:
+        _need(residual, torch.bfloat16, "gemm.residual")
+        assert residual.stride(-1) == 1
+    args = GemmArgs()
+    args.a, args.b, args.c = a.data_ptr(), w.data_ptr(), out.data_ptr()
+    args.bias, args.residual = _ptr(bias), _ptr(residual)
+    args.m, args.n, args.k = m, n, k
+    args.lda, args.ldb = a.stride(0), w.stride(0)
+    args.ldc = out.stride(-2) if out.dim() >= 2 else n
+    args.ldr = residual.stride(-2) if residual is not None and residual.dim() >= 2 else 0
+    args.alpha, args.beta = alpha, beta
+    args.alpha_cols, args.row_group = alpha_cols, row_group
+    args.epilogue, args.out_dtype, args.backend = epilogue, _DT[out_dtype], backend
+    args.reserved = block_n
+    check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
+    return out
+
+
+def gemm_uses_tcgen05(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> bool:
+    args = GemmArgs()
+    args.a, args.b, args.c = a.data_ptr(), w.data_ptr(), out.data_ptr()
+    args.m, args.k = a.shape
+    args.n = w.shape[0]
+    args.lda, args.ldb, args.ldc = a.stride(0), w.stride(0), out.stride(0)
+    args.out_dtype = _DT[out.dtype]
+    return bool(_lib.lib().vb_gemm_uses_tcgen05(C.byref(args)))
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+              residual: torch.Tensor | None = None, save_stats: bool = False):
+    """LayerNorm over the last dim of a 2-D bf16 tensor (optionally of x + residual)."""
+    _need(x, torch.bfloat16, "layernorm.x")
+    _need(gamma, torch.float32, "layernorm.gamma")
+    _need(beta, torch.float32, "layernorm.beta")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    if residual is not None:
+        _need(residual, torch.bfloat16, "layernorm.residual")
+        assert residual.shape == x.shape and residual.stride(1) == 1
+    check(_lib.lib().vb_layernorm(x.data_ptr(), _ptr(residual), gamma.data_ptr(), beta.data_ptr(),
+                                  y.data_ptr(), _ptr(mean), _ptr(rstd), rows, cols, x.stride(0),
+                                  residual.stride(0) if residual is not None else 0, cols, eps,
+                                  _stream()), "vb_layernorm")
+    return (y, mean, rstd) if save_stats else y
+
+
+def layernorm_bwd(dy, xin, gamma, mean, rstd, *, dx_add=None, dgamma=None, dbeta=None):
+    _need(dy, torch.bfloat16, "layernorm_bwd.dy")
+    _need(xin, torch.bfloat16, "layernorm_bwd.xin")
+    assert dy.is_contiguous() and xin.is_contiguous()
+    rows, cols = dy.shape
+    dx = torch.empty_like(dy)
+    if dx_add is not None:
+        assert dx_add.is_contiguous()
+    check(_lib.lib().vb_layernorm_bwd(dy.data_ptr(), xin.data_ptr(), gamma.data_ptr(),
+                                      mean.data_ptr(), rstd.data_ptr(), _ptr(dx_add), dx.data_ptr(),
+                                      _ptr(dgamma), _ptr(dbeta), rows, cols, 0.0, _stream()),
+          "vb_layernorm_bwd")
+    return dx
+
+
+def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal) -> AttnArgs:
+    """q: (B, Sq, >=H*D) view, k/v: (B, Skv, ...) views; last dim contiguous."""
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.lse, a.key_mask = _ptr(lse), _ptr(key_mask)
+    a.batch, a.sq, a.skv = q.shape[0], q.shape[1], k.shape[1]
+    a.heads, a.d = heads, d
+    a.q_bs, a.q_rs = q.stride(0), q.stride(1)
+    a.k_bs, a.k_rs = k.stride(0), k.stride(1)
+    a.v_bs, a.v_rs = v.stride(0), v.stride(1)
+    a.o_bs, a.o_rs = o.stride(0), o.stride(1)
+    a.scale, a.causal = scale, 1 if causal else 0
+    return a
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float, *,
+              causal: bool = False, key_mask: torch.Tensor | None = None,
+              need_lse: bool = False):
+    """Softmax attention.  q: (B, Sq, H*D), k/v: (B, Skv, H*D) bf16 views whose last dim is
+    contiguous (they may be slices of one fused QKV buffer).  Returns o: (B, Sq, H*D)."""
+    for t, nme in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, torch.bfloat16, f"attention.{nme}")
+        assert t.dim() == 3 and t.stride(2) == 1
+    hd = q.shape[2]
+    d = hd // heads
+    o = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.bfloat16, device=q.device)
+    lse = None
+    if need_lse:
+        lse = torch.empty((q.shape[0], heads, q.shape[1]), dtype=torch.float32, device=q.device)
+    if key_mask is not None:
+        _need(key_mask, torch.uint8, "attention.key_mask")
+        assert key_mask.is_contiguous() and key_mask.shape == (k.shape[0], k.shape[1])
+    a = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal)
+    check(_lib.lib().vb_attention_fwd(C.byref(a), _stream()), "vb_attention_fwd")
+    return (o, lse) if need_lse else o
+
+
+def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: bool = False,
+                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None):
+    """Returns (dq, dk, dv) with the shapes of q, k, v (contiguous unless views are given)."""
+    hd = q.shape[2]
+    d = hd // heads
+    assert d_o.stride() == o.stride() and d_o.dtype == torch.bfloat16
+    dq = torch.empty(q.shape, dtype=torch.bfloat16, device=q.device) if dq is None else dq
+    dk = torch.empty(k.shape, dtype=torch.bfloat16, device=q.device) if dk is None else dk
+    dv = torch.empty(v.shape, dtype=torch.bfloat16, device=q.device) if dv is None else dv
+    delta = torch.empty((q.shape[0], heads, q.shape[1]), dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.float32, device=q.device)
+    b = AttnBwdArgs()
+    b.fwd = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal)
+    b.d_o, b.dq, b.dk, b.dv = d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    b.dq_bs, b.dq_rs = dq.stride(0), dq.stride(1)
+    b.dk_bs, b.dk_rs = dk.stride(0), dk.stride(1)
+    b.dv_bs, b.dv_rs = dv.stride(0), dv.stride(1)
+    b.delta, b.dq_acc, b.dq_scale = delta.data_ptr(), dq_acc.data_ptr(), dq_scale
+    check(_lib.lib().vb_attention_bwd(C.byref(b), _stream()), "vb_attention_bwd")
+    return dq, dk, dv
+
+
+def patch_gather(pixels: torch.Tensor, patch: int, kpad: int) -> torch.Tensor:
+    """(NV, C, T, H, W) -> (NV*T*gh*gw, kpad) bf16 patch matrix."""
+    _need(pixels, None, "patch_gather.pixels")
+    assert pixels.dim() == 5 and pixels.is_contiguous() and pixels.dtype in _DT
+    nv, c, t, h, w = pixels.shape
+    gh, gw = h // patch, w // patch
+    out = torch.empty((nv * t * gh * gw, kpad), dtype=torch.bfloat16, device=pixels.device)
+    check(_lib.lib().vb_patch_gather(pixels.data_ptr(), _DT[pixels.dtype], out.data_ptr(), nv, c, t,
+                                     h, w, patch, kpad, _stream()), "vb_patch_gather")
+    return out
+
+
+def cls_rows(cls: torch.Tensor, pos: torch.Tensor, hidden: torch.Tensor) -> None:
+    frames, tokens, dim = hidden.shape
+    check(_lib.lib().vb_cls_rows(cls.data_ptr(), pos.data_ptr(), hidden.data_ptr(), frames, tokens,
+                                 dim, _stream()), "vb_cls_rows")
+
+
+def embed_splice(input_ids, attention_mask, video_mask, embed_tokens, video_features, pos_table,
+                 pos_offset: int, *, want_embeds: bool = True, want_hidden: bool = True):
+    """Returns (inputs_embeds|None, hidden|None, slot_index, pos_ids, status)."""
+    _need(input_ids, torch.int64, "embed_splice.input_ids")
+    batch, seq = input_ids.shape
+    vocab, dim = embed_tokens.shape
+    dev = input_ids.device
+    input_ids = input_ids.contiguous()
+    if attention_mask is not None:
+        attention_mask = attention_mask.to(torch.int64).contiguous()
+    if video_mask is not None:
+        video_mask = video_mask.to(torch.int64).contiguous()
+    n_feat = 0 if video_features is None else video_features.shape[0]
+    if video_features is not None:
+        _need(video_features, torch.bfloat16, "embed_splice.video_features")
+        assert video_features.is_contiguous() and video_features.shape[1] == dim
+    emb = torch.empty((batch, seq, dim), dtype=torch.bfloat16, device=dev) if want_embeds else None
+    hid = torch.empty((batch, seq, dim), dtype=torch.bfloat16, device=dev) if want_hidden else None
+    slot = torch.empty(batch * seq, dtype=torch.int32, device=dev)
+    pos = torch.empty(batch * seq, dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    check(_lib.lib().vb_embed_splice(input_ids.data_ptr(), _ptr(attention_mask), _ptr(video_mask),
+                                     embed_tokens.data_ptr(), _ptr(video_features), _ptr(pos_table),
+                                     pos_offset, _ptr(emb), _ptr(hid), slot.data_ptr(),
+                                     pos.data_ptr(), status.data_ptr(), batch, seq, dim, vocab,
+                                     n_feat, _stream()), "vb_embed_splice")
+    return emb, hid, slot, pos, status
+
+
+def splice_bwd(d_embeds: torch.Tensor, slot_index: torch.Tensor, n_features: int) -> torch.Tensor:
+    dim = d_embeds.shape[-1]
+    positions = d_embeds.numel() // dim
+    out = torch.zeros((n_features, dim), dtype=torch.bfloat16, device=d_embeds.device)
+    check(_lib.lib().vb_splice_bwd(d_embeds.data_ptr(), slot_index.data_ptr(), out.data_ptr(),
+                                   positions, dim, n_features, _stream()), "vb_splice_bwd")
+    return out
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor):
+    """Shifted causal-LM loss.  logits (B, L, V) bf16|f32; labels (B, L) int64.
+    Returns (loss f32 scalar tensor, row_lse, n_valid)."""
+    assert logits.dim() == 3 and logits.stride(2) == 1 and logits.dtype in (torch.bfloat16, torch.float32)
+    b, l, v = logits.shape
+    assert logits.stride(0) == l * logits.stride(1)
+    labels = labels.contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    row_lse = torch.empty(b * l, dtype=torch.float32, device=logits.device)
+    n_valid = torch.empty((), dtype=torch.int32, device=logits.device)
+    check(_lib.lib().vb_cross_entropy(logits.data_ptr(), _DT[logits.dtype], labels.data_ptr(),
+                                      loss.data_ptr(), row_lse.data_ptr(), n_valid.data_ptr(), b, l,
+                                      v, logits.stride(1), _stream()), "vb_cross_entropy")
+    return loss, row_lse, n_valid
+
+
+def cross_entropy_bwd(logits, labels, row_lse, n_valid, grad_scale: torch.Tensor | None):
+    b, l, v = logits.shape
+    vpad = (v + 7) // 8 * 8
+    d = torch.empty((b * l, vpad), dtype=torch.bfloat16, device=logits.device)
+    if vpad != v:
+        d[:, v:].zero_()
+    check(_lib.lib().vb_cross_entropy_bwd(logits.data_ptr(), _DT[logits.dtype],
+                                          labels.contiguous().data_ptr(), row_lse.data_ptr(),
+                                          n_valid.data_ptr(), _ptr(grad_scale), d.data_ptr(), b, l,
+                                          v, logits.stride(1), vpad, _stream()),
+          "vb_cross_entropy_bwd")
+    return d[:, :v]
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """(rows, cols) bf16 -> contiguous (cols, rows_padded-to-8)[:, :rows]."""
+    _need(x, torch.bfloat16, "transpose.x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    ld = (rows + 7) // 8 * 8
+    out = torch.empty((cols, ld), dtype=torch.bfloat16, device=x.device)
+    if ld != rows:
+        out[:, rows:].zero_()
+    check(_lib.lib().vb_transpose(x.data_ptr(), out.data_ptr(), rows, cols, x.stride(0), ld,
+                                  _stream()), "vb_transpose")
+    return out[:, :rows]
+
+
+def convert(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _need(x, None, "convert.x")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(_lib.lib().vb_convert(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[dtype], x.numel(),
+                                _stream()), "vb_convert")
+    return out
+
+
+def act_bwd(dy: torch.Tensor, saved: torch.Tensor, epilogue: int) -> torch.Tensor:
+    assert dy.is_contiguous() and saved.is_contiguous() and dy.shape == saved.shape
+    dx = torch.empty_like(dy)
+    check(_lib.lib().vb_act_bwd(dy.data_ptr(), saved.data_ptr(), dx.data_ptr(), epilogue,
+                                dy.numel(), _stream()), "vb_act_bwd")
+    return dx
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """f32 column sums of a 2-D bf16 tensor (bias gradient); accumulates into `out` if given."""
+    _need(x, torch.bfloat16, "colsum.x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    acc = 1
+    if out is None:
+        out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+        acc = 0
+    check(_lib.lib().vb_colsum(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0),
+                               acc, _stream()), "vb_colsum")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    y = torch.empty_like(a)
+    check(_lib.lib().vb_add(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream()), "vb_add")
+    return y
+
+
+def adamw_(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay, step,
+           grad_scale: torch.Tensor | None = None) -> None:
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        _need(t, torch.float32, "adamw")
+        assert t.is_contiguous()
+    check(_lib.lib().vb_adamw(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                              exp_avg_sq.data_ptr(), param.numel(), lr, beta1, beta2, eps,
+                              weight_decay, step, _ptr(grad_scale), _stream()), "vb_adamw")
+
+
+def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
+    _need(x, torch.float32, "sumsq.x")
+    check(_lib.lib().vb_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vb_sumsq")
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, bias=None, *, residual=None, epilogue: int = EPI_NONE,
+         alpha: float = 1.0, alpha_cols: int = 0, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """Decode-time projection for M <= 16 rows (weight-streaming)."""
+    _need(x, torch.bfloat16, "gemv.x")
+    _need(w, torch.bfloat16, "gemv.w")
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=out_dtype, device=x.device)
+    check(_lib.lib().vb_gemv(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(),
+                             m, n, k, x.stride(0), w.stride(0), n,
+                             residual.stride(0) if residual is not None else 0, alpha, alpha_cols,
+                             epilogue, _DT[out_dtype], _stream()), "vb_gemv")
+    return y
+
+
+def paged_kv_write(k, v, k_cache, v_cache, page_table, page_size: int) -> None:
+    """k, v: (B, L, H*D) views with a common row stride."""
+    b, l, hd = k.shape
+    assert k.stride(2) == 1 and k.stride() == v.stride() and k.stride(0) == l * k.stride(1)
+    check(_lib.lib().vb_paged_kv_write(k.data_ptr(), v.data_ptr(), k.stride(1), k_cache.data_ptr(),
+                                       v_cache.data_ptr(), page_table.data_ptr(), b, l, hd,
+                                       page_size, page_table.shape[1], _stream()),
+          "vb_paged_kv_write")
+
+
+def paged_decode_attention(qkv, k_cache, v_cache, page_table, ctx_len, first_valid, heads: int,
+                           page_size: int, scale: float) -> torch.Tensor:
+    b = qkv.shape[0]
+    hd = qkv.shape[1] // 3
+    out = torch.empty((b, hd), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.lib().vb_paged_decode_attention(qkv.data_ptr(), k_cache.data_ptr(),
+                                               v_cache.data_ptr(), page_table.data_ptr(),
+                                               ctx_len.data_ptr(), _ptr(first_valid),
+                                               out.data_ptr(), b, heads, hd // heads, page_size,
+                                               page_table.shape[1], scale, _stream()),
+          "vb_paged_decode_attention")
+    return out

@@ -1,0 +1,251 @@
+/*
+ * videoblip_b200 — C ABI of the sm_100a kernels behind the VideoBLIP hot path.
+ *
+ * The reference (yukw777/EILEV) has no native layer: its hot path is
+ * eilev/model/v2.py calling HuggingFace modules, i.e. torch/ATen/cuBLAS/cuDNN
+ * library kernels.  Each entry point below replaces the library call sites the
+ * reference reaches (cited per function as  <file>:<line>, paths relative to the
+ * reference checkout, "HF:" = transformers/models/...).
+ *
+ * Conventions
+ *   - plain C types only: device pointers, int64 sizes/strides (in ELEMENTS),
+ *     floats, and the CUDA stream as an opaque void* (cudaStream_t).
+ *   - every function returns 0 on success, non-zero on failure; the message of
+ *     the last failure on the calling thread is vb_last_error().
+ *   - no allocation, no device synchronisation, no global mutable state;
+ *     all work is enqueued on `stream`.  Pointers must be device pointers.
+ *   - bf16 tensors are raw uint16 storage (`__nv_bfloat16`).
+ */
+#ifndef VIDEOBLIP_B200_H
+#define VIDEOBLIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_ABI_VERSION 1
+
+/* dtype tags */
+#define VB_BF16 0
+#define VB_F32 1
+#define VB_F16 2
+
+/* GEMM epilogue activation */
+#define VB_EPI_NONE 0
+#define VB_EPI_GELU 1 /* exact erf GELU  (HF:blip_2/modeling_blip_2.py:365-369, :686-689) */
+#define VB_EPI_RELU 2 /* OPT FFN        (HF:opt/modeling_opt.py:238-239) */
+
+/* GEMM backend selector (vb_gemm_args.backend) */
+#define VB_GEMM_AUTO 0    /* tcgen05 when the shape allows, else generic */
+#define VB_GEMM_TCGEN05 1 /* fail if the shape is not eligible */
+#define VB_GEMM_GENERIC 2 /* CUDA-core kernel, any shape/alignment */
+
+int vb_abi_version(void);
+const char* vb_last_error(void);
+/* Compute capability major*10+minor of the current device, or <0 on error. */
+int vb_device_arch(void);
+
+/* ------------------------------------------------------------------------
+ * C[m, n] = act(alpha_n * (sum_k A[m,k] * B[n,k] + bias[n])) + residual[m',n] + beta*C[m,n]
+ *
+ * A: (M,K) bf16 row-major (lda), B: (N,K) bf16 row-major (ldb) — i.e. exactly an
+ * nn.Linear weight — C: (M,N) bf16 or f32 (ldc).  bias: f32 (N) or NULL.
+ * residual: bf16 (ldr) or NULL.  alpha is applied to columns < alpha_cols only
+ * (alpha_cols <= 0: all columns) — OPT scales q but not k,v of a fused QKV.
+ * row_group P > 0 selects the patch-embedding store: GEMM row r is stored at
+ * row r + r/P + 1 (one CLS slot in front of every P patches) and the residual
+ * row is 1 + r%P (the position table).
+ *
+ * Replaces every nn.Linear / Conv2d(k=s=patch) on the path:
+ *   HF:blip_2/modeling_blip_2.py:246-254 (patch embedding as GEMM), :326-353 (qkv,
+ *   projection), :365-369 (fc1+GELU, fc2), :592-628 (Q-Former q/k/v), :644-648,
+ *   :686-689, :700-704; eilev/model/v2.py:201-203 (language_projection);
+ *   HF:opt/modeling_opt.py:151-181 (q,k,v,out_proj), :238-241 (fc1+ReLU, fc2), :512 (lm_head);
+ *   and their autograd backward (dgrad / wgrad with pre-transposed operands).
+ * ---------------------------------------------------------------------- */
+typedef struct vb_gemm_args {
+  const void* a;
+  const void* b;
+  void* c;
+  const float* bias;
+  const void* residual;
+  int64_t m, n, k;
+  int64_t lda, ldb, ldc, ldr;
+  float alpha;
+  float beta;
+  int64_t alpha_cols;
+  int64_t row_group;
+  int32_t epilogue;  /* VB_EPI_* */
+  int32_t out_dtype; /* VB_BF16 or VB_F32 */
+  int32_t backend;   /* VB_GEMM_* */
+  int32_t reserved;
+} vb_gemm_args;
+
+int vb_gemm(const vb_gemm_args* args, void* stream);
+/* 1 if vb_gemm would take the tcgen05 path for these args. */
+int vb_gemm_uses_tcgen05(const vb_gemm_args* args);
+
+/* ------------------------------------------------------------------------
+ * y = LayerNorm(x (+ residual)) * gamma + beta   (rows x cols, fp32 statistics)
+ * x, residual, y: bf16 (row strides ldx/ldr/ldy); gamma/beta: f32.
+ * mean/rstd (f32, rows) are written when non-NULL (saved for backward).
+ * HF:blip_2/modeling_blip_2.py:388-402, :522-526, :644-648, :700-704, :984-986;
+ * HF:opt/modeling_opt.py:206-207, :232-233, :370-371.
+ * ---------------------------------------------------------------------- */
+int vb_layernorm(const void* x, const void* residual, const float* gamma, const float* beta,
+                 void* y, float* mean, float* rstd, int64_t rows, int64_t cols, int64_t ldx,
+                 int64_t ldr, int64_t ldy, float eps, void* stream);
+
+/* dx (+ optional dgamma/dbeta accumulation, f32 atomics) of the LayerNorm above.
+ * xin is the tensor that was normalised (x + residual), bf16.  dx is bf16; when
+ * dx_add != NULL it is added to the result (gradient joining a residual branch). */
+int vb_layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
+                     const float* rstd, const void* dx_add, void* dx, float* dgamma, float* dbeta,
+                     int64_t rows, int64_t cols, float eps_unused, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused softmax attention, FlashAttention-style (online softmax, fp32 accumulate).
+ * Element (b, s, h, d) of q lives at q + b*q_bs + s*q_rs + h*D + d  (elements); same
+ * for k, v, o with their own strides, so the operands can alias a fused QKV buffer.
+ * scale multiplies q.k^T.  causal: key j visible to query i iff j <= i + (Skv - Sq).
+ * key_mask: optional uint8 (B, Skv), 0 = masked key.  lse: optional f32 (B,H,Sq).
+ * HF:blip_2/modeling_blip_2.py:326-353 (ViT, S=257 d=88), :592-628 (Q-Former self /
+ * cross, d=64), HF:opt/modeling_opt.py:135-181 (causal, d=80).
+ * ---------------------------------------------------------------------- */
+typedef struct vb_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  const uint8_t* key_mask;
+  int64_t batch, heads, sq, skv, d;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+  float scale;
+  int32_t causal;
+} vb_attn_args;
+int vb_attention_fwd(const vb_attn_args* args, void* stream);
+
+/* Backward of the above: dq, dk, dv (bf16, same addressing as q,k,v via the dq_, dk_, dv_
+ * strides).  delta: f32 workspace (B,H,Sq).  dq_acc: f32 workspace (B,Sq,H*D) zeroed by
+ * the call.  */
+typedef struct vb_attn_bwd_args {
+  vb_attn_args fwd; /* q,k,v,o,lse,key_mask and shapes as in the forward */
+  const void* d_o;  /* same addressing as o */
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  float* delta;
+  float* dq_acc;
+  float dq_scale; /* extra factor on dq (OPT: q was pre-scaled by the projection epilogue) */
+  int32_t reserved;
+} vb_attn_bwd_args;
+int vb_attention_bwd(const vb_attn_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Patch gather for the ViT patch embedding (Conv2d k=s=P as a GEMM):
+ * pixels (NV, C, T, H, W) of dtype px_dtype -> out (NV*T*gh*gw, kpad) bf16 where row
+ * ((v*T+t)*gh+gy)*gw+gx holds the C*P*P patch in (c, py, px) order (the Conv2d
+ * weight's flattening), zero padded to kpad.  Fuses the (N,C,T,H,W)->(N*T,C,H,W)
+ * permute of eilev/model/v2.py:57 and the cast.  HF:blip_2/modeling_blip_2.py:246-248.
+ * ---------------------------------------------------------------------- */
+int vb_patch_gather(const void* pixels, int32_t px_dtype, void* out, int64_t nv, int64_t c,
+                    int64_t t, int64_t h, int64_t w, int64_t patch, int64_t kpad, void* stream);
+/* hidden[f, 0, :] = cls + pos[0]  for every frame f (HF:...:249-254). bf16. */
+int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
+                int64_t dim, void* stream);
+
+/* ------------------------------------------------------------------------
+ * LM input assembly (eilev/model/v2.py:205-214 + HF:opt/modeling_opt.py:350-368):
+ *   e[b,l] = video_mask[b,l] ? video_features[rank of (b,l) among masked slots]
+ *                            : embed_tokens[input_ids[b,l]]
+ *   pos[b,l] = cumsum(attention_mask)[b,l]*attention_mask[b,l] - 1 + pos_offset
+ *   inputs_embeds = e ; hidden = e + pos_table[pos]   (pos_table NULL: hidden = e)
+ * ids/masks are int64; embeddings bf16.  slot_index (int32, B*L) receives the
+ * video-feature row of every position (-1 for text) for the backward gather, pos_ids
+ * (int32, B*L) the position-table rows.  status (int32[2]): status[0] = 1 if the mask
+ * count differs from n_features (the reference's index_put shape error), status[1] =
+ * the mask count.  inputs_embeds / hidden may be NULL.
+ * ---------------------------------------------------------------------- */
+int vb_embed_splice(const int64_t* input_ids, const int64_t* attention_mask,
+                    const int64_t* video_mask, const void* embed_tokens,
+                    const void* video_features, const void* pos_table, int64_t pos_offset,
+                    void* inputs_embeds, void* hidden, int32_t* slot_index, int32_t* pos_ids,
+                    int32_t* status, int64_t batch, int64_t seq, int64_t dim, int64_t vocab, int64_t n_features,
+                    void* stream);
+/* d_video_features[slot] = d_inputs_embeds[b,l] for masked slots (bf16). */
+int vb_splice_bwd(const void* d_embeds, const int32_t* slot_index, void* d_features,
+                  int64_t positions, int64_t dim, int64_t n_features, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Shifted causal-LM cross entropy (HF:loss/loss_utils.py:28-67): position l predicts
+ * labels[b, l+1]; ignore_index -100; mean over valid targets; fp32 math.
+ * logits (B, L, V) bf16|f32 (row stride ldl).  Outputs: loss (f32 scalar),
+ * row_lse (f32, B*L), n_valid (int32 scalar).
+ * ---------------------------------------------------------------------- */
+int vb_cross_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels, float* loss,
+                     float* row_lse, int32_t* n_valid, int64_t batch, int64_t seq, int64_t vocab,
+                     int64_t ldl, void* stream);
+/* dlogits (bf16, B*L x V, ldd) = grad_scale * (softmax - onehot) / n_valid on valid rows,
+ * 0 elsewhere. grad_scale: f32 device scalar (upstream d loss) or NULL (=1). */
+int vb_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* labels,
+                         const float* row_lse, const int32_t* n_valid, const float* grad_scale,
+                         void* dlogits, int64_t batch, int64_t seq, int64_t vocab, int64_t ldl,
+                         int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------ elementwise */
+/* out(cols, rows) = in(rows, cols)^T, bf16 (operand staging for dgrad / wgrad GEMMs). */
+int vb_transpose(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in,
+                 int64_t ld_out, void* stream);
+/* dtype conversion src -> dst (VB_BF16 / VB_F32 / VB_F16), n elements. */
+int vb_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
+               void* stream);
+/* dx = dy * act'(.)  bf16.  GELU: `saved` is the pre-activation; RELU: `saved` is the output. */
+int vb_act_bwd(const void* dy, const void* saved, void* dx, int32_t epilogue, int64_t n,
+               void* stream);
+/* out(f32, cols) (+)= column sums of x (bf16, rows x cols): bias gradients. */
+int vb_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int32_t accumulate,
+              void* stream);
+/* y = a + b (bf16) */
+int vb_add(const void* a, const void* b, void* y, int64_t n, void* stream);
+
+/* Fused AdamW over a flat f32 parameter/gradient/moment buffer (torch.optim.AdamW
+ * semantics, scripts/general/train_v2.py:99-101).  grad_scale (device f32 scalar or NULL)
+ * multiplies the gradient first: fold 1/world, 1/accum and the clip factor into it. */
+int vb_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+             float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+             const float* grad_scale, void* stream);
+/* out[0] += sum(x^2) over n f32 elements (global grad norm for clipping). */
+int vb_sumsq(const float* x, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------ decode */
+/* y[m, n] = act(x[m,:] . W[n,:] + bias[n]) (+ residual) for small m (<= 16):
+ * weight-streaming kernel for token-by-token generation (HBM bound).  bf16 in/out,
+ * out_dtype selects bf16|f32.  HF:opt/modeling_opt.py:135-253 at tgt_len == 1. */
+int vb_gemv(const void* x, const void* w, const float* bias, const void* residual, void* y,
+            int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,
+            float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype, void* stream);
+
+/* Append new K/V rows into a paged cache and run one-query-per-sequence attention over
+ * it.  Cache pages: (n_pages, page_size, H*D) bf16 for K and for V; page_table (B,
+ * max_pages) int32; ctx_len (B) int32 = number of cached tokens INCLUDING the new one;
+ * first_valid (B) int32 = index of the first non-padding token (left padding).
+ * qkv: (B, 3*H*D) bf16 (q pre-scaled).  out: (B, H*D) bf16.
+ * HF:opt/modeling_opt.py:159-161 (DynamicCache.update) + :163-176. */
+int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
+                              const int32_t* page_table, const int32_t* ctx_len,
+                              const int32_t* first_valid, void* out, int64_t batch, int64_t heads,
+                              int64_t d, int64_t page_size, int64_t max_pages, float scale,
+                              void* stream);
+/* Copy prefill K/V (B, L, ld) rows into the paged cache. */
+int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,
+                      const int32_t* page_table, int64_t batch, int64_t seq, int64_t hd,
+                      int64_t page_size, int64_t max_pages, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDEOBLIP_B200_H */

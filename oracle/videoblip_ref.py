@@ -1,0 +1,246 @@
+"""ORACLE — test infrastructure only.  NOT part of the product path.
+
+A CPU, fp32, plain-PyTorch restatement of the reference's VideoBLIP forward path
+(yukw777/EILEV ``eilev/model/v2.py`` and the HuggingFace modules it calls), written as
+pure functions over a ``state_dict`` with the reference's parameter names.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module, and only as the checker / the CPU baseline.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` runs the *real* reference
+(``/root/reference/eilev/model/v2.py`` on the installed transformers 5.5.0; the reference
+pins 4.33.1, whose equations for this path are the same) on seeded inputs and commits
+inputs + outputs under ``tests/golden/``; ``tests/test_oracle.py`` checks this restatement
+against those fixtures (and against the live reference when ``/root/reference`` exists).
+The reference's own tests pin shapes only (tests/model/test_model_v2.py:53-83,185-186).
+
+Citations: ``v2.py`` = eilev/model/v2.py; ``HF:`` = transformers/models/…
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _ln(x, sd, prefix, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"].float(), sd[prefix + ".bias"].float(), eps)
+
+
+def _lin(x, sd, prefix, bias=True):
+    b = sd.get(prefix + ".bias") if bias else None
+    return F.linear(x, sd[prefix + ".weight"].float(), None if b is None else b.float())
+
+
+# --------------------------------------------------------------------------- vision tower
+def vision_embeddings(sd, vcfg, frames, p="vision_model.embeddings."):
+    """HF:blip_2/modeling_blip_2.py:243-255 — Conv2d(k=s=patch) + [CLS] + position table."""
+    w = sd[p + "patch_embedding.weight"].float()
+    b = sd[p + "patch_embedding.bias"].float()
+    x = F.conv2d(frames.float(), w, b, stride=vcfg.patch_size)
+    x = x.flatten(2).transpose(1, 2)
+    cls = sd[p + "class_embedding"].float().expand(x.shape[0], 1, -1)
+    x = torch.cat([cls, x], dim=1)
+    return x + sd[p + "position_embedding"].float()[:, : x.shape[1]]
+
+
+def vision_layer(sd, vcfg, x, p):
+    """HF:blip_2/modeling_blip_2.py:383-402 (layer), :319-353 (attention), :365-369 (MLP)."""
+    h, d = vcfg.num_attention_heads, vcfg.hidden_size // vcfg.num_attention_heads
+    b, s, _ = x.shape
+    y = _ln(x, sd, p + "layer_norm1", vcfg.layer_norm_eps)
+    qkv = _lin(y, sd, p + "self_attn.qkv").reshape(b, s, 3, h, d).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1) @ qkv[2]
+    att = att.transpose(1, 2).reshape(b, s, h * d)
+    x = x + _lin(att, sd, p + "self_attn.projection")
+    y = _ln(x, sd, p + "layer_norm2", vcfg.layer_norm_eps)
+    act = F.gelu if vcfg.hidden_act == "gelu" else getattr(F, vcfg.hidden_act)
+    y = _lin(act(_lin(y, sd, p + "mlp.fc1")), sd, p + "mlp.fc2")
+    return x + y
+
+
+def vision_forward(sd, vcfg, pixel_values):
+    """v2.py:24-103 on top of HF:blip_2/modeling_blip_2.py:506-531.
+
+    pixel_values (N, C, T, H, W) -> last_hidden_state (N, T*S, D), pooler_output (N, T, D).
+    """
+    n, _, t, _, _ = pixel_values.shape
+    frames = pixel_values.permute(0, 2, 1, 3, 4).flatten(end_dim=1)  # v2.py:57
+    x = vision_embeddings(sd, vcfg, frames)
+    for i in range(vcfg.num_hidden_layers):
+        x = vision_layer(sd, vcfg, x, f"vision_model.encoder.layers.{i}.")
+    x = _ln(x, sd, "vision_model.post_layernorm", vcfg.layer_norm_eps)
+    pooled = _ln(x[:, 0], sd, "vision_model.post_layernorm", vcfg.layer_norm_eps)  # LN twice (:525-526)
+    s = x.shape[1]
+    return x.reshape(n, t * s, -1), pooled.reshape(n, t, -1)  # v2.py:69-75
+
+
+# --------------------------------------------------------------------------- Q-Former
+def _qf_attention(sd, qcfg, hidden, kv_src, p):
+    """HF:blip_2/modeling_blip_2.py:579-633 (eager, scores / sqrt(d); masks are all-ones here)
+    followed by Blip2QFormerSelfOutput :644-648 (dense + LN(residual))."""
+    h = qcfg.num_attention_heads
+    d = qcfg.hidden_size // h
+    b, sq, _ = hidden.shape
+
+    def heads(x):
+        return x.reshape(b, x.shape[1], h, d).permute(0, 2, 1, 3)
+
+    q = heads(_lin(hidden, sd, p + "attention.query"))
+    k = heads(_lin(kv_src, sd, p + "attention.key"))
+    v = heads(_lin(kv_src, sd, p + "attention.value"))
+    probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    ctx = (probs @ v).permute(0, 2, 1, 3).reshape(b, sq, h * d)
+    out = _lin(ctx, sd, p + "output.dense")
+    return _ln(out + hidden, sd, p + "output.LayerNorm", qcfg.layer_norm_eps)
+
+
+def qformer_forward(sd, qcfg, query_tokens, image_embeds):
+    """HF:blip_2/modeling_blip_2.py:962-1036, layers :729-780 (query-only path, dropout off)."""
+    x = _ln(query_tokens.float(), sd, "qformer.layernorm", qcfg.layer_norm_eps)  # :984-985
+    for i in range(qcfg.num_hidden_layers):
+        p = f"qformer.encoder.layer.{i}."
+        x = _qf_attention(sd, qcfg, x, x, p + "attention.")
+        if i % qcfg.cross_attention_frequency == 0:  # :716-720
+            x = _qf_attention(sd, qcfg, x, image_embeds.float(), p + "crossattention.")
+        act = F.gelu if qcfg.hidden_act == "gelu" else getattr(F, qcfg.hidden_act)
+        inter = act(_lin(x, sd, p + "intermediate_query.dense"))
+        x = _ln(_lin(inter, sd, p + "output_query.dense") + x, sd, p + "output_query.LayerNorm",
+                qcfg.layer_norm_eps)
+    return x
+
+
+# --------------------------------------------------------------------------- OPT
+def opt_positions(attention_mask):
+    """HF:opt/modeling_opt.py:350-354 + offset 2 (:45-70)."""
+    am = attention_mask.long()
+    return (torch.cumsum(am, dim=1) * am - 1) + 2
+
+
+def opt_decoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.model.decoder."):
+    """HF:opt/modeling_opt.py:321-396; layers :202-253; attention :135-181 (q scaled first)."""
+    assert tcfg.do_layer_norm_before and tcfg.word_embed_proj_dim == tcfg.hidden_size
+    b, l, _ = inputs_embeds.shape
+    h = tcfg.num_attention_heads
+    d = tcfg.hidden_size // h
+    pos = sd[p + "embed_positions.weight"].float()[opt_positions(attention_mask)]
+    x = inputs_embeds.float() + pos
+    neg = torch.finfo(torch.float32).min
+    causal = torch.ones(l, l, dtype=torch.bool).tril()
+    allowed = causal[None, None] & attention_mask.bool()[:, None, None, :]
+    bias = torch.zeros(b, 1, l, l).masked_fill(~allowed, neg)
+    for i in range(tcfg.num_hidden_layers):
+        lp = f"{p}layers.{i}."
+        y = _ln(x, sd, lp + "self_attn_layer_norm", 1e-5)
+
+        def heads(t):
+            return t.reshape(b, l, h, d).transpose(1, 2)
+
+        q = heads(_lin(y, sd, lp + "self_attn.q_proj") * d ** -0.5)
+        k = heads(_lin(y, sd, lp + "self_attn.k_proj"))
+        v = heads(_lin(y, sd, lp + "self_attn.v_proj"))
+        att = torch.softmax(q @ k.transpose(-1, -2) + bias, dim=-1) @ v
+        att = att.transpose(1, 2).reshape(b, l, h * d)
+        x = x + _lin(att, sd, lp + "self_attn.out_proj")
+        y = _ln(x, sd, lp + "final_layer_norm", 1e-5)
+        act = F.relu if tcfg.activation_function == "relu" else getattr(F, tcfg.activation_function)
+        x = x + _lin(act(_lin(y, sd, lp + "fc1")), sd, lp + "fc2")
+    return _ln(x, sd, p + "final_layer_norm", 1e-5)
+
+
+def causal_lm_loss(logits, labels):
+    """HF:loss/loss_utils.py:28-67 — shift, ignore_index=-100, mean over valid targets."""
+    v = logits.shape[-1]
+    return F.cross_entropy(logits[:, :-1].float().reshape(-1, v), labels[:, 1:].reshape(-1),
+                           ignore_index=-100)
+
+
+# --------------------------------------------------------------------------- full model
+def video_features(sd, config, pixel_values):
+    """v2.py:169-203 — ViT -> Q-Former -> language_projection; rows in (clip, query) order."""
+    image_embeds, pooled = vision_forward(sd, config.vision_config, pixel_values)
+    n = image_embeds.shape[0]
+    query = sd["query_tokens"].float().expand(n, -1, -1)
+    qout = qformer_forward(sd, config.qformer_config, query, image_embeds)
+    feats = _lin(qout.reshape(n * config.num_query_tokens, -1), sd, "language_projection")
+    return feats, qout, image_embeds, pooled
+
+
+def splice(sd, input_ids, video_input_mask, feats):
+    """v2.py:205-214 — boolean-mask assignment fills True slots in row-major order."""
+    emb = sd["language_model.model.decoder.embed_tokens.weight"].float()[input_ids]
+    if feats is not None:
+        emb = emb.clone()
+        emb[video_input_mask.bool()] = feats
+    return emb
+
+
+def videoblip_forward(sd, config, input_ids, attention_mask=None, pixel_values=None,
+                      video_input_mask=None, labels=None):
+    """v2.py:132-252 for the decoder-only (OPT) language model.  Returns a dict."""
+    out = {}
+    feats = None
+    if pixel_values is not None:
+        assert video_input_mask is not None  # v2.py:154-157
+        feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values)
+        out.update(video_features=feats, query_output=qout, image_embeds=image_embeds,
+                   pooler_output=pooled)
+    emb = splice(sd, input_ids, video_input_mask, feats)
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)  # v2.py:216-217
+    hidden = opt_decoder(sd, config.text_config, emb, attention_mask)
+    logits = F.linear(hidden, sd["language_model.model.decoder.embed_tokens.weight"].float())  # tied
+    out.update(inputs_embeds=emb, logits=logits)
+    if labels is not None:
+        out["loss"] = causal_lm_loss(logits, labels)
+    return out
+
+
+@torch.no_grad()
+def greedy_generate(sd, config, input_ids, attention_mask, pixel_values, video_input_mask,
+                    max_new_tokens, eos_token_id=None):
+    """v2.py:254-324 with greedy search (HF:generation/utils.py:2658-2790); returns only the new
+    tokens (decoder-only + inputs_embeds).  No KV cache: recomputes the prefix, small cases only."""
+    feats = None
+    if pixel_values is not None:
+        feats = video_features(sd, config, pixel_values)[0]
+    emb = splice(sd, input_ids, video_input_mask, feats)
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    table = sd["language_model.model.decoder.embed_tokens.weight"].float()
+    b = emb.shape[0]
+    new = []
+    done = torch.zeros(b, dtype=torch.bool)
+    pad = config.text_config.pad_token_id
+    for _ in range(max_new_tokens):
+        hidden = opt_decoder(sd, config.text_config, emb, attention_mask)
+        nxt = F.linear(hidden[:, -1], table).argmax(-1)
+        if eos_token_id is not None:
+            nxt = torch.where(done, torch.full_like(nxt, pad), nxt)
+            done = done | (nxt == eos_token_id)
+        new.append(nxt)
+        emb = torch.cat([emb, table[nxt][:, None]], dim=1)
+        attention_mask = torch.cat([attention_mask, torch.ones(b, 1, dtype=attention_mask.dtype)], 1)
+        if eos_token_id is not None and bool(done.all()):
+            break
+    return torch.stack(new, dim=1)
+
+
+def sane_init_(state_dict, seed=1234, std=0.02):
+    """Seeded, numerically sane re-initialisation (HF's default init is degenerate for this
+    model: ViT std 1e-10, zero query tokens — SURVEY §0.8).  Linear/conv/embedding weights
+    ~ N(0, std); LayerNorm gamma ~ 1 + N(0, 0.1), beta ~ N(0, 0.1); biases ~ N(0, std)."""
+    g = torch.Generator().manual_seed(seed)
+    for name in sorted(state_dict):
+        t = state_dict[name]
+        if not t.dtype.is_floating_point:
+            continue
+        lname = name.lower()
+        if "layernorm" in lname or "layer_norm" in lname:
+            if name.endswith("weight"):
+                t.copy_(1.0 + 0.1 * torch.randn(t.shape, generator=g))
+            else:
+                t.copy_(0.1 * torch.randn(t.shape, generator=g))
+        else:
+            t.copy_(std * torch.randn(t.shape, generator=g))
+    return state_dict

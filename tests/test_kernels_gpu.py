@@ -1,0 +1,308 @@
+"""Kernel-level numerics on the B200: every C-ABI kernel family against a plain PyTorch
+fp32 evaluation of the same op on the same (bf16-rounded) inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from eilev_b200 import ops
+    return ops
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _close(got, ref, atol, rtol, what=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} off, max err {err.max().item():.4g} (ref max {ref.abs().max().item():.4g})"
+
+
+GEMM_SHAPES = [
+    # (M, N, K, block_n)
+    (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 256, 256), (128, 128, 64, 128),
+    (128, 176, 64, 176), (128, 64, 64, 64), (300, 1408, 1408, 0), (257, 4224, 1408, 0),
+    (1000, 6144, 1408, 0), (520, 1408, 6144, 0), (544, 768, 768, 0), (976, 2560, 2560, 0),
+    (200, 264, 72, 0), (64, 50272, 256, 0), (4096, 1408, 592, 0),
+]
+
+
+@pytest.mark.parametrize("m,n,k,bn", GEMM_SHAPES)
+def test_gemm_tcgen05_plain(m, n, k, bn):
+    ops = _ops()
+    a, w = _rand(m, k, seed=1), _rand(n, k, seed=2)
+    out = ops.gemm(a, w, backend=ops.GEMM_TCGEN05, block_n=bn)
+    ref = a.float() @ w.float().t()
+    _close(out, ref, atol=0.02 * math.sqrt(k), rtol=0.01, what=f"gemm {m}x{n}x{k} bn={bn}")
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "generic"])
+@pytest.mark.parametrize("epi", ["none", "gelu", "relu"])
+def test_gemm_epilogues(backend, epi):
+    ops = _ops()
+    m, n, k = 384, 704, 320
+    a, w = _rand(m, k, scale=0.5, seed=3), _rand(n, k, scale=0.1, seed=4)
+    bias = torch.randn(n, device="cuda")
+    res = _rand(m, n, seed=5)
+    e = {"none": ops.EPI_NONE, "gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[epi]
+    be = ops.GEMM_TCGEN05 if backend == "tcgen05" else ops.GEMM_GENERIC
+    out = ops.gemm(a, w, bias, residual=res, epilogue=e, alpha=0.5, alpha_cols=352, backend=be)
+    pre = a.float() @ w.float().t() + bias
+    pre[:, :352] *= 0.5
+    act = {"none": lambda x: x, "gelu": torch.nn.functional.gelu, "relu": torch.relu}[epi](pre)
+    _close(out, act + res.float(), atol=0.03, rtol=0.01, what=f"{backend}/{epi}")
+    # f32 output with accumulation
+    c = torch.ones(m, n, device="cuda")
+    ops.gemm(a, w, bias, out=c, beta=1.0, backend=be)
+    _close(c, a.float() @ w.float().t() + bias + 1.0, atol=0.03, rtol=0.01, what="f32 beta")
+
+
+def test_gemm_generic_odd_shapes():
+    ops = _ops()
+    for (m, n, k) in [(5, 7, 3), (65, 24, 192), (130, 8, 8), (33, 100, 50)]:
+        a, w = _rand(m, k, seed=6), _rand(n, k, seed=7)
+        out = ops.gemm(a, w)
+        _close(out, a.float() @ w.float().t(), atol=0.05, rtol=0.01, what=f"generic {m}x{n}x{k}")
+
+
+def test_gemm_patch_rowgroup():
+    ops = _ops()
+    frames, p, dim, k = 3, 256, 1408, 640
+    a, w = _rand(frames * p, k, scale=0.3, seed=8), _rand(dim, k, scale=0.1, seed=9)
+    bias = torch.randn(dim, device="cuda")
+    pos = _rand(p + 1, dim, seed=10)
+    hidden = torch.zeros(frames, p + 1, dim, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, bias, residual=pos, out=hidden.view(-1, dim), row_group=p)
+    ref = (a.float() @ w.float().t() + bias).view(frames, p, dim) + pos[1:].float()
+    _close(hidden[:, 1:], ref, atol=0.03, rtol=0.01, what="patch rows")
+    assert hidden[:, 0].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("rows,cols", [(1000, 1408), (544, 768), (976, 2560), (37, 8), (64, 100)])
+def test_layernorm_fwd_bwd(rows, cols):
+    ops = _ops()
+    x, r = _rand(rows, cols, seed=11), _rand(rows, cols, seed=12)
+    g = torch.randn(cols, device="cuda")
+    b = torch.randn(cols, device="cuda")
+    y, mean, rstd = ops.layernorm(x, g, b, 1e-5, residual=r, save_stats=True)
+    xin = (x.float() + r.float()).requires_grad_(True)
+    gp, bp = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xin, (cols,), gp, bp, 1e-5)
+    _close(y, ref, atol=0.03, rtol=0.01, what="ln fwd")
+    dy = _rand(rows, cols, seed=13)
+    ref.backward(dy.float())
+    xin_bf = (x.float() + r.float()).to(torch.bfloat16)
+    dgamma = torch.zeros(cols, device="cuda")
+    dbeta = torch.zeros(cols, device="cuda")
+    dx = ops.layernorm_bwd(dy, xin_bf, g, mean, rstd, dgamma=dgamma, dbeta=dbeta)
+    _close(dx, xin.grad, atol=0.05, rtol=0.03, what="ln dx")
+    _close(dgamma, gp.grad, atol=0.02 * math.sqrt(rows) + 0.05, rtol=0.03, what="ln dgamma")
+    _close(dbeta, bp.grad, atol=0.02 * math.sqrt(rows) + 0.05, rtol=0.03, what="ln dbeta")
+
+
+def _attn_ref(q, k, v, heads, scale, causal, key_mask):
+    b, sq, hd = q.shape
+    skv = k.shape[1]
+    d = hd // heads
+    qh = q.float().view(b, sq, heads, d).transpose(1, 2)
+    kh = k.float().view(b, skv, heads, d).transpose(1, 2)
+    vh = v.float().view(b, skv, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        i = torch.arange(sq, device=q.device)[:, None]
+        j = torch.arange(skv, device=q.device)[None, :]
+        s = s.masked_fill(j > i + (skv - sq), -1e30)
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[:, None, None, :] == 0, -1e30)
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(b, sq, hd)
+
+
+ATTN_CASES = [
+    # b, heads, d, sq, skv, causal, masked
+    (3, 16, 88, 257, 257, False, False),
+    (2, 12, 64, 32, 32, False, False),
+    (2, 12, 64, 32, 2056, False, False),
+    (1, 32, 80, 976, 976, True, False),
+    (2, 32, 80, 200, 200, True, True),
+    (2, 4, 2, 11, 11, True, False),
+    (2, 4, 2, 5, 37, False, False),
+]
+
+
+@pytest.mark.parametrize("b,heads,d,sq,skv,causal,masked", ATTN_CASES)
+def test_attention_fwd_bwd(b, heads, d, sq, skv, causal, masked):
+    ops = _ops()
+    hd = heads * d
+    scale = d ** -0.5
+    if sq == skv:  # fused QKV buffer, as in the ViT / OPT
+        qkv = _rand(b, sq, 3 * hd, seed=20)
+        q, k, v = qkv[:, :, :hd], qkv[:, :, hd:2 * hd], qkv[:, :, 2 * hd:]
+    else:
+        q = _rand(b, sq, hd, seed=21)
+        kv = _rand(b, skv, 2 * hd, seed=22)
+        k, v = kv[:, :, :hd], kv[:, :, hd:]
+    key_mask = None
+    if masked:
+        key_mask = torch.ones(b, skv, dtype=torch.uint8, device="cuda")
+        key_mask[0, :17] = 0  # left padding on the first sequence
+    o, lse = ops.attention(q, k, v, heads, scale, causal=causal, key_mask=key_mask, need_lse=True)
+    qf = q.float().detach().clone().requires_grad_(True)
+    kf = k.float().detach().clone().requires_grad_(True)
+    vf = v.float().detach().clone().requires_grad_(True)
+    ref = _attn_ref(qf, kf, vf, heads, scale, causal, key_mask)
+    valid = torch.ones(b, sq, dtype=torch.bool, device="cuda")
+    if masked and causal:
+        valid[0, :17] = False  # fully masked query rows: undefined in the reference too
+    _close(o[valid], ref[valid], atol=0.02, rtol=0.02, what="attn fwd")
+    d_o = _rand(b, sq, hd, seed=23)
+    d_o = d_o * valid[:, :, None]
+    torch.nan_to_num(ref, nan=0.0).backward(d_o.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal, key_mask=key_mask)
+    for got, want, nm in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        want = torch.nan_to_num(want, nan=0.0)
+        if nm == "dq":
+            got, want = got[valid], want[valid]
+        _close(got, want, atol=0.03 + 0.02 * want.abs().max().item(), rtol=0.03, what=f"attn {nm}")
+
+
+def test_patch_gather_and_cls():
+    ops = _ops()
+    px = torch.randn(2, 3, 4, 28, 28, device="cuda")
+    out = ops.patch_gather(px, 14, 592)
+    frames = px.permute(0, 2, 1, 3, 4).flatten(end_dim=1)
+    ref = torch.nn.functional.unfold(frames, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    _close(out[:, :588], ref, atol=0.02, rtol=0.01, what="patch gather")
+    assert out[:, 588:].abs().max().item() == 0.0
+    # patch 12 on 28x28: the strided conv drops the remainder
+    out12 = ops.patch_gather(px.to(torch.bfloat16), 12, 432)
+    ref12 = torch.nn.functional.unfold(frames[:, :, :24, :24], kernel_size=12, stride=12).transpose(1, 2).reshape(-1, 432)
+    _close(out12, ref12.to(torch.bfloat16), atol=1e-6, rtol=0, what="patch gather 12")
+    hidden = torch.zeros(5, 7, 16, dtype=torch.bfloat16, device="cuda")
+    cls, pos = _rand(16, seed=30), _rand(7, 16, seed=31)
+    ops.cls_rows(cls, pos, hidden)
+    _close(hidden[:, 0], (cls.float() + pos[0].float()).expand(5, 16), atol=0.02, rtol=0.01)
+
+
+def test_embed_splice_and_bwd():
+    ops = _ops()
+    torch.manual_seed(0)
+    b, l, dim, vocab, nq = 2, 19, 24, 50, 4
+    ids = torch.randint(0, vocab, (b, l), device="cuda")
+    attn = torch.ones(b, l, dtype=torch.int64, device="cuda")
+    attn[0, :3] = 0
+    vmask = torch.zeros(b, l, dtype=torch.int64, device="cuda")
+    vmask[0, 4:8] = 1
+    vmask[1, 1:5] = 1
+    vmask[1, 9:13] = 1
+    emb = _rand(vocab, dim, seed=40)
+    feats = _rand(3 * nq, dim, seed=41)
+    ptab = _rand(l + 2, dim, seed=42)
+    e, h, slot, pos, status = ops.embed_splice(ids, attn, vmask, emb, feats, ptab, 2)
+    ref_e = emb[ids].clone()
+    ref_e[vmask.bool()] = feats
+    assert torch.equal(e, ref_e)
+    ref_pos = (torch.cumsum(attn, 1) * attn - 1) + 2
+    assert torch.equal(pos.view(b, l).long(), ref_pos)
+    _close(h, ref_e.float() + ptab[ref_pos].float(), atol=0.02, rtol=0.01)
+    assert status.tolist() == [0, 12]
+    d_e = _rand(b, l, dim, seed=43)
+    d_f = ops.splice_bwd(d_e, slot, 3 * nq)
+    assert torch.equal(d_f, d_e[vmask.bool()])
+    _, _, _, _, st2 = ops.embed_splice(ids, attn, vmask, emb, feats[:8], ptab, 2)
+    assert st2.tolist()[0] == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_cross_entropy(dtype):
+    ops = _ops()
+    torch.manual_seed(1)
+    b, l, v = 2, 13, 1003
+    logits = (torch.randn(b, l, v, device="cuda") * 3).to(dtype)
+    labels = torch.full((b, l), -100, dtype=torch.int64, device="cuda")
+    labels[0, 5:9] = torch.randint(0, v, (4,), device="cuda")
+    labels[1, 10:] = torch.randint(0, v, (3,), device="cuda")
+    loss, row_lse, n_valid = ops.cross_entropy(logits, labels)
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf[:, :-1].reshape(-1, v), labels[:, 1:].reshape(-1), ignore_index=-100)
+    assert n_valid.item() == 7
+    assert abs(loss.item() - ref.item()) < 2e-3, (loss.item(), ref.item())
+    ref.backward()
+    gs = torch.full((), 0.5, device="cuda")
+    dl = ops.cross_entropy_bwd(logits, labels, row_lse, n_valid, gs)
+    _close(dl.reshape(b, l, v), 0.5 * lf.grad, atol=2e-3, rtol=0.02, what="ce bwd")
+
+
+def test_transpose_convert_misc():
+    ops = _ops()
+    x = _rand(100, 37, seed=50)
+    assert torch.equal(ops.transpose(x), x.t())
+    xs = _rand(64, 96, seed=51)[:, :40]
+    assert torch.equal(ops.transpose(xs), xs.t())
+    f = torch.randn(1000, device="cuda")
+    assert torch.equal(ops.convert(f, torch.bfloat16), f.to(torch.bfloat16))
+    assert torch.equal(ops.convert(f.to(torch.bfloat16), torch.float32), f.to(torch.bfloat16).float())
+    dy, pre = _rand(50, 33, seed=52), _rand(50, 33, seed=53)
+    pf = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(pf).backward(dy.float())
+    _close(ops.act_bwd(dy, pre, ops.EPI_GELU), pf.grad, atol=0.02, rtol=0.02)
+    post = torch.relu(pre)
+    _close(ops.act_bwd(dy, post, ops.EPI_RELU), dy.float() * (post > 0), atol=1e-6, rtol=0)
+    big = _rand(5000, 70, seed=54)
+    _close(ops.colsum(big), big.float().sum(0), atol=0.5, rtol=0.01)
+    _close(ops.add(dy, pre), dy.float() + pre.float(), atol=0.02, rtol=0.01)
+
+
+def test_adamw_matches_torch():
+    ops = _ops()
+    torch.manual_seed(2)
+    p = torch.randn(10000, device="cuda")
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-2, weight_decay=0.05)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(10000, device="cuda")
+        ref_p.grad = g.clone()
+        opt.step()
+        ops.adamw_(p, g, m, v, lr=1e-2, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.05, step=step)
+    _close(p, ref_p.detach(), atol=1e-5, rtol=1e-5, what="adamw")
+    acc = torch.zeros((), device="cuda")
+    ops.sumsq(p, acc)
+    assert abs(acc.item() - (p.double() ** 2).sum().item()) < 1e-2 * acc.item()
+
+
+def test_gemv_and_paged_decode():
+    ops = _ops()
+    for m in (1, 3, 8):
+        x, w = _rand(m, 2560, seed=60), _rand(7680, 2560, scale=0.05, seed=61)
+        bias = torch.randn(7680, device="cuda")
+        y = ops.gemv(x, w, bias, alpha=0.25, alpha_cols=2560)
+        ref = x.float() @ w.float().t() + bias
+        ref[:, :2560] *= 0.25
+        _close(y, ref, atol=0.05, rtol=0.02, what="gemv")
+    heads, d, page, b, l = 4, 80, 16, 2, 37
+    hd = heads * d
+    max_pages = 4
+    kc = torch.zeros(b * max_pages, page, hd, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    table = torch.arange(b * max_pages, dtype=torch.int32, device="cuda").view(b, max_pages).flip(0).contiguous()
+    kv = _rand(b, l, 2 * hd, seed=62)
+    ops.paged_kv_write(kv[:, :, :hd], kv[:, :, hd:], kc, vc, table, page)
+    qkv = _rand(b, 3 * hd, seed=63)
+    ctx = torch.full((b,), l + 1, dtype=torch.int32, device="cuda")
+    first = torch.tensor([5, 0], dtype=torch.int32, device="cuda")
+    out = ops.paged_decode_attention(qkv, kc, vc, table, ctx, first, heads, page, 1.0)
+    k_all = torch.cat([kv[:, :, :hd], qkv[:, None, hd:2 * hd]], 1)
+    v_all = torch.cat([kv[:, :, hd:], qkv[:, None, 2 * hd:]], 1)
+    mask = torch.ones(b, l + 1, dtype=torch.uint8, device="cuda")
+    mask[0, :5] = 0
+    ref = _attn_ref(qkv[:, None, :hd], k_all, v_all, heads, 1.0, False, mask)[:, 0]
+    _close(out, ref, atol=0.02, rtol=0.02, what="paged decode")
