@@ -1,0 +1,254 @@
+"""OPT causal LM over the interleaved (32 video queries per clip + text) sequence.
+
+Restates OPTForCausalLM.forward (HF:opt/modeling_opt.py:464-524), OPTDecoder.forward
+(:321-396), OPTDecoderLayer (:202-253), OPTAttention (:135-181; q is scaled by
+head_dim**-0.5 right after q_proj and the softmax scale is 1.0) and the shifted causal-LM
+loss (HF:loss/loss_utils.py:28-67) as sm_100a launches:
+
+    embed_splice (token gather + video-feature splice + learned positions, offset 2)
+    32 x [LN, fused QKV GEMM (alpha on the q columns), causal flash attention with the
+          padding mask, out_proj GEMM(+residual), LN, fc1 GEMM(+ReLU), fc2 GEMM(+residual)]
+    final LN, tied lm_head GEMM, fused cross entropy.
+
+The LM is frozen in the reference recipe (train_v2.py:126-127): its backward is dgrad
+only — gradients flow through activations to the spliced video positions, no wgrad.
+Decode (``generate``) runs token-by-token on weight-streaming GEMV kernels over a paged KV
+cache.  Dropout (p=0.1 in train mode in the reference) is not applied.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from .packing import PackCache, bf16, cat_bf16, cat_f32, f32
+
+T = ops.transpose
+
+
+def _check_cfg(cfg) -> None:
+    if not cfg.do_layer_norm_before:
+        raise NotImplementedError("OPT with do_layer_norm_before=False (opt-350m) is not supported")
+    if cfg.word_embed_proj_dim != cfg.hidden_size:
+        raise NotImplementedError("OPT with word_embed_proj_dim != hidden_size is not supported")
+    if getattr(cfg, "_remove_final_layer_norm", False):
+        raise NotImplementedError("OPT without the final layer norm is not supported")
+    if cfg.activation_function not in ("relu", "gelu"):
+        raise NotImplementedError(f"OPT activation {cfg.activation_function!r} is not supported")
+
+
+def pack_opt(lm, cache: PackCache, need_backward: bool):
+    dec = lm.model.decoder
+    params = list(lm.parameters())
+
+    def build():
+        w = {
+            "embed": bf16(dec.embed_tokens.weight),
+            "pos": bf16(dec.embed_positions.weight),
+            "lnf_g": f32(dec.final_layer_norm.weight), "lnf_b": f32(dec.final_layer_norm.bias),
+            "layers": [],
+        }
+        for layer in dec.layers:
+            sa = layer.self_attn
+            has_b = sa.q_proj.bias is not None
+            w["layers"].append(dict(
+                ln1_g=f32(layer.self_attn_layer_norm.weight), ln1_b=f32(layer.self_attn_layer_norm.bias),
+                qkv_w=cat_bf16([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight]),
+                qkv_b=cat_f32([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias]) if has_b else None,
+                out_w=bf16(sa.out_proj.weight), out_b=f32(sa.out_proj.bias) if has_b else None,
+                ln2_g=f32(layer.final_layer_norm.weight), ln2_b=f32(layer.final_layer_norm.bias),
+                fc1_w=bf16(layer.fc1.weight), fc1_b=f32(layer.fc1.bias) if layer.fc1.bias is not None else None,
+                fc2_w=bf16(layer.fc2.weight), fc2_b=f32(layer.fc2.bias) if layer.fc2.bias is not None else None,
+            ))
+        return w
+
+    w = cache.get("opt", params, build)
+    if need_backward and "embed_t" not in w:
+        with torch.no_grad():  # dgrad operands: W^T, packed once (the LM is frozen)
+            w["embed_t"] = T(w["embed"])
+            for lw in w["layers"]:
+                for k in ("qkv_w", "out_w", "fc1_w", "fc2_w"):
+                    lw[k + "t"] = T(lw[k])
+    return w
+
+
+def _dims(cfg):
+    heads = cfg.num_attention_heads
+    return cfg.hidden_size, heads, cfg.hidden_size // heads
+
+
+def opt_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features,
+                labels=None, save: bool = False, want_logits: bool = True,
+                output_hidden_states: bool = False, kv_sink=None):
+    """Full-sequence forward.  Returns dict(inputs_embeds, logits, loss, hidden_states, ctx)."""
+    cfg = lm.config
+    _check_cfg(cfg)
+    w = pack_opt(lm, cache, need_backward=save)
+    dim, heads, hd = _dims(cfg)
+    act = ops.EPI_RELU if cfg.activation_function == "relu" else ops.EPI_GELU
+    scaling = hd ** -0.5
+    b, l = input_ids.shape
+    rows = b * l
+    emb, hidden, slot, pos_ids, status = ops.embed_splice(
+        input_ids, attention_mask, video_mask, w["embed"], video_features, w["pos"], 2)
+    key_mask = None
+    if attention_mask is not None:
+        key_mask = attention_mask.to(torch.uint8).contiguous()
+    x = hidden.view(rows, dim)
+    saved = []
+    all_hidden = [hidden] if output_hidden_states else None
+    for li, lw in enumerate(w["layers"]):
+        y, m1, r1 = ops.layernorm(x, lw["ln1_g"], lw["ln1_b"], 1e-5, save_stats=True)
+        qkv = ops.gemm(y, lw["qkv_w"], lw["qkv_b"], alpha=scaling, alpha_cols=dim).view(b, l, 3 * dim)
+        q, k, v = qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:]
+        if kv_sink is not None:
+            kv_sink(li, k, v)
+        o, lse = ops.attention(q, k, v, heads, 1.0, causal=True, key_mask=key_mask, need_lse=True)
+        x_mid = ops.gemm(o.view(rows, dim), lw["out_w"], lw["out_b"], residual=x)
+        y2, m2, r2 = ops.layernorm(x_mid, lw["ln2_g"], lw["ln2_b"], 1e-5, save_stats=True)
+        f1 = ops.gemm(y2, lw["fc1_w"], lw["fc1_b"], epilogue=act)
+        x_out = ops.gemm(f1, lw["fc2_w"], lw["fc2_b"], residual=x_mid)
+        if save:
+            s = dict(x_in=x, m1=m1, r1=r1, qkv=qkv, o=o, lse=lse, x_mid=x_mid, m2=m2, r2=r2, f1=f1)
+            if act == ops.EPI_GELU:
+                s["y2"] = y2
+            saved.append(s)
+        x = x_out
+        if output_hidden_states:
+            all_hidden.append(x.view(b, l, dim))
+    final, mf, rf = ops.layernorm(x, w["lnf_g"], w["lnf_b"], 1e-5, save_stats=True)
+    if output_hidden_states:
+        all_hidden[-1] = final.view(b, l, dim)  # HF reports the normalised last state
+    out = dict(inputs_embeds=emb, status=status, hidden_states=all_hidden, final=final.view(b, l, dim),
+               logits=None, loss=None, ctx=None)
+    if want_logits or labels is not None:
+        logits = ops.gemm(final, w["embed"]).view(b, l, -1)  # tied lm_head, no bias
+        out["logits"] = logits
+        if labels is not None:
+            loss, row_lse, n_valid = ops.cross_entropy(logits, labels)
+            out["loss"] = loss
+            if save:
+                out["ctx"] = dict(saved=saved, x_last=x, mf=mf, rf=rf, logits=logits, labels=labels,
+                                  row_lse=row_lse, n_valid=n_valid, slot=slot, key_mask=key_mask,
+                                  b=b, l=l, n_features=0 if video_features is None else video_features.shape[0])
+    return out
+
+
+def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None):
+    """dgrad-only backward: returns d(video_features) (n_features, D) bf16."""
+    cfg = lm.config
+    w = pack_opt(lm, cache, need_backward=True)
+    dim, heads, hd = _dims(cfg)
+    act = ops.EPI_RELU if cfg.activation_function == "relu" else ops.EPI_GELU
+    scaling = hd ** -0.5
+    b, l = ctx["b"], ctx["l"]
+    rows = b * l
+    gs = None
+    if grad_loss is not None:
+        gs = grad_loss.detach().to(torch.float32).reshape(()).contiguous()
+    dlogits = ops.cross_entropy_bwd(ctx["logits"], ctx["labels"], ctx["row_lse"], ctx["n_valid"], gs)
+    d_final = ops.gemm(dlogits, w["embed_t"])
+    dx = ops.layernorm_bwd(d_final, ctx["x_last"], w["lnf_g"], ctx["mf"], ctx["rf"])
+    del dlogits, d_final
+    for li in range(len(w["layers"]) - 1, -1, -1):
+        lw, s = w["layers"][li], ctx["saved"][li]
+        d_f1 = ops.gemm(dx, lw["fc2_wt"])
+        if act == ops.EPI_RELU:
+            d_pre = ops.act_bwd(d_f1, s["f1"], act)
+        else:
+            pre = ops.gemm(s["y2"], lw["fc1_w"], lw["fc1_b"])
+            d_pre = ops.act_bwd(d_f1, pre, act)
+        d_y2 = ops.gemm(d_pre, lw["fc1_wt"])
+        d_mid = ops.layernorm_bwd(d_y2, s["x_mid"], lw["ln2_g"], s["m2"], s["r2"], dx_add=dx)
+        d_o = ops.gemm(d_mid, lw["out_wt"]).view(b, l, dim)
+        qkv = s["qkv"]
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], s["o"], s["lse"],
+                          d_o, heads, 1.0, causal=True, key_mask=ctx["key_mask"], dq_scale=scaling,
+                          dq=dqkv[:, :, :dim], dk=dqkv[:, :, dim:2 * dim], dv=dqkv[:, :, 2 * dim:])
+        d_y = ops.gemm(dqkv.view(rows, 3 * dim), lw["qkv_wt"])
+        dx = ops.layernorm_bwd(d_y, s["x_in"], lw["ln1_g"], s["m1"], s["r1"], dx_add=d_mid)
+    if ctx["n_features"] == 0:
+        return None
+    return ops.splice_bwd(dx, ctx["slot"], ctx["n_features"])
+
+
+# --------------------------------------------------------------------------- decode
+class PagedKV:
+    """Paged KV cache: per layer K and V pools of (n_pages, page_size, H*D) bf16 and one page
+    table (B, max_pages) shared by all layers.  Beam reordering permutes table rows and copies
+    only partially filled tail pages."""
+
+    def __init__(self, n_layers: int, batch: int, max_len: int, hd: int, device, page_size: int = 64):
+        self.page_size = page_size
+        self.max_pages = (max_len + page_size - 1) // page_size
+        n_pages = batch * self.max_pages
+        self.k = [torch.empty((n_pages, page_size, hd), dtype=torch.bfloat16, device=device) for _ in range(n_layers)]
+        self.v = [torch.empty((n_pages, page_size, hd), dtype=torch.bfloat16, device=device) for _ in range(n_layers)]
+        self.table = torch.arange(n_pages, dtype=torch.int32, device=device).view(batch, self.max_pages).contiguous()
+        self.batch = batch
+
+    def reorder(self, beam_idx: torch.Tensor) -> None:
+        """Row i of the cache becomes old row beam_idx[i] (physical copy of the page contents;
+        pages stay owned by their row so no reference counting is needed)."""
+        idx = beam_idx.to(torch.long)
+        if bool((idx == torch.arange(idx.numel(), device=idx.device)).all()):
+            return
+        mp = self.max_pages
+        for pool in (self.k, self.v):
+            for li in range(len(pool)):
+                view = pool[li].view(self.batch, mp, self.page_size, -1)
+                pool[li] = view[idx].reshape(pool[li].shape).contiguous()
+
+
+def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features,
+                max_new_tokens: int):
+    """Runs the prompt, fills a paged KV cache, returns (last-position logits f32 (B, V), state)."""
+    cfg = lm.config
+    dim, heads, hd = _dims(cfg)
+    b, l = input_ids.shape
+    kv = PagedKV(cfg.num_hidden_layers, b, l + max_new_tokens, dim, input_ids.device)
+
+    def sink(li, k, v):
+        ops.paged_kv_write(k, v, kv.k[li], kv.v[li], kv.table, kv.page_size)
+
+    out = opt_forward(lm, cache, input_ids, attention_mask, video_mask, video_features,
+                      want_logits=False, kv_sink=sink)
+    w = pack_opt(lm, cache, need_backward=False)
+    last = out["final"][:, -1, :].contiguous()
+    logits = ops.gemv(last, w["embed"], out_dtype=torch.float32) if b <= 16 else \
+        ops.gemm(last, w["embed"], out_dtype=torch.float32)
+    am = attention_mask if attention_mask is not None else torch.ones_like(input_ids)
+    first_valid = (am != 0).to(torch.int32).argmax(dim=1).to(torch.int32).contiguous()
+    n_valid = am.sum(dim=1).to(torch.int32)
+    state = dict(kv=kv, ctx_len=torch.full((b,), l, dtype=torch.int32, device=input_ids.device),
+                 first_valid=first_valid, n_valid=n_valid, status=out["status"])
+    return logits, state
+
+
+def opt_decode_step(lm, cache: PackCache, tokens: torch.Tensor, state: dict) -> torch.Tensor:
+    """One token per sequence: tokens (B,) int64 -> next-position logits f32 (B, V)."""
+    cfg = lm.config
+    w = pack_opt(lm, cache, need_backward=False)
+    dim, heads, hd = _dims(cfg)
+    act = ops.EPI_RELU if cfg.activation_function == "relu" else ops.EPI_GELU
+    scaling = hd ** -0.5
+    kv: PagedKV = state["kv"]
+    b = tokens.shape[0]
+    if b > 16:
+        raise NotImplementedError("decode batch (incl. beams) > 16 is not supported yet")
+    # position of the new token = number of valid tokens so far - 1 + offset 2 (HF :350-354)
+    pos = (state["n_valid"].to(torch.long) + 2)
+    state["n_valid"] = state["n_valid"] + 1
+    state["ctx_len"] = state["ctx_len"] + 1
+    x = ops.add(w["embed"][tokens].contiguous(), w["pos"][pos].contiguous())
+    for li, lw in enumerate(w["layers"]):
+        y = ops.layernorm(x, lw["ln1_g"], lw["ln1_b"], 1e-5)
+        qkv = ops.gemv(y, lw["qkv_w"], lw["qkv_b"], alpha=scaling, alpha_cols=dim)
+        o = ops.paged_decode_attention(qkv, kv.k[li], kv.v[li], kv.table, state["ctx_len"],
+                                       state["first_valid"], heads, kv.page_size, 1.0)
+        x = ops.gemv(o, lw["out_w"], lw["out_b"], residual=x)
+        y = ops.layernorm(x, lw["ln2_g"], lw["ln2_b"], 1e-5)
+        f1 = ops.gemv(y, lw["fc1_w"], lw["fc1_b"], epilogue=act)
+        x = ops.gemv(f1, lw["fc2_w"], lw["fc2_b"], residual=x)
+    final = ops.layernorm(x, w["lnf_g"], w["lnf_b"], 1e-5)
+    return ops.gemv(final, w["embed"], out_dtype=torch.float32)

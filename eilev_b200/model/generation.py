@@ -1,0 +1,252 @@
+"""Native decoding loops over the paged-KV OPT engine.
+
+Mirrors what the reference reaches through ``language_model.generate(inputs_embeds=...,
+attention_mask=..., **generate_kwargs)`` (eilev/model/v2.py:318-322 ->
+HF:generation/utils.py ``_sample`` / ``_beam_search``) for the keyword arguments its callers
+use (samples/eilev_generate_action_narration.py:60-75, demo/eilev_demo.py:51-67,
+scripts/general/generate_narration_texts.py:116-123): ``max_new_tokens``, ``min_new_tokens``,
+``num_beams``, ``do_sample`` (+ ``temperature`` / ``top_k`` / ``top_p``), ``length_penalty``,
+``repetition_penalty``, ``eos_token_id``, ``pad_token_id``, ``early_stopping``.
+
+As in the reference (decoder-only LM fed with ``inputs_embeds``) only the NEW tokens are
+returned; finished rows are padded with ``pad_token_id``.  Prompts are expected
+left-padded when batched (generate_narration_texts.py:229-230).  The per-step logits come
+from the CUDA engine; the token bookkeeping on (B*beams,)-sized tensors is host-side torch.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..engine import opt as E_opt
+
+_UNSUPPORTED = ("penalty_alpha", "num_beam_groups", "diversity_penalty", "constraints",
+                "force_words_ids", "assistant_model", "prompt_lookup_num_tokens")
+
+
+def _as_list(x):
+    if x is None:
+        return []
+    if isinstance(x, (list, tuple)):
+        return list(x)
+    if isinstance(x, torch.Tensor):
+        return x.flatten().tolist()
+    return [int(x)]
+
+
+def _process_logits(logits, generated, step, *, min_new_tokens, eos_ids, repetition_penalty):
+    """Logit processors in HF order: repetition penalty, then min-length EOS suppression."""
+    if repetition_penalty and repetition_penalty != 1.0 and generated.shape[1] > 0:
+        score = torch.gather(logits, 1, generated)
+        score = torch.where(score < 0, score * repetition_penalty, score / repetition_penalty)
+        logits = logits.scatter(1, generated, score)
+    if eos_ids and step < min_new_tokens:
+        logits = logits.clone()
+        logits[:, eos_ids] = float("-inf")
+    return logits
+
+
+def _warp(logits, temperature, top_k, top_p):
+    if temperature and temperature != 1.0:
+        logits = logits / temperature
+    if top_k and top_k > 0:
+        k = min(int(top_k), logits.shape[-1])
+        kth = torch.topk(logits, k)[0][..., -1, None]
+        logits = logits.masked_fill(logits < kth, float("-inf"))
+    if top_p is not None and top_p < 1.0:
+        sorted_logits, sorted_idx = torch.sort(logits, descending=False)
+        cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+        remove = cum <= (1 - top_p)
+        remove[..., -1:] = False
+        remove = remove.scatter(1, sorted_idx, remove)
+        logits = logits.masked_fill(remove, float("-inf"))
+    return logits
+
+
+@torch.no_grad()
+def generate(model, input_ids, attention_mask, video_mask, video_features, **kw) -> torch.Tensor:
+    for k in _UNSUPPORTED:
+        if kw.get(k):
+            raise NotImplementedError(f"generate({k}=...) is not supported by the native decoder")
+    gcfg = kw.pop("generation_config", None)
+
+    def opt(name, default):
+        if name in kw and kw[name] is not None:
+            return kw[name]
+        if gcfg is not None and getattr(gcfg, name, None) is not None:
+            return getattr(gcfg, name)
+        mg = getattr(model, "generation_config", None)
+        if mg is not None and getattr(mg, name, None) is not None and name not in ("max_length",):
+            return getattr(mg, name)
+        return default
+
+    tcfg = model.config.text_config
+    max_new = kw.get("max_new_tokens")
+    if max_new is None and gcfg is not None:
+        max_new = getattr(gcfg, "max_new_tokens", None)
+    if max_new is None:
+        max_length = kw.get("max_length") or 20
+        max_new = max(int(max_length), 1)  # prompt is embeddings: length counts new tokens only
+    max_new = int(max_new)
+    min_new = int(opt("min_new_tokens", 0) or 0)
+    num_beams = int(opt("num_beams", 1) or 1)
+    do_sample = bool(opt("do_sample", False))
+    eos_ids = _as_list(kw["eos_token_id"] if "eos_token_id" in kw else
+                       (getattr(gcfg, "eos_token_id", None) if gcfg is not None else tcfg.eos_token_id))
+    pad_id = opt("pad_token_id", tcfg.pad_token_id)
+    if pad_id is None:
+        pad_id = eos_ids[0] if eos_ids else 0
+    rep = float(opt("repetition_penalty", 1.0) or 1.0)
+    temperature = float(opt("temperature", 1.0) or 1.0)
+    top_k = opt("top_k", 50 if do_sample else 0)
+    top_p = opt("top_p", 1.0)
+    length_penalty = float(opt("length_penalty", 1.0))
+    early_stopping = opt("early_stopping", False)
+    if int(opt("num_return_sequences", 1) or 1) != 1:
+        raise NotImplementedError("num_return_sequences > 1 is not supported")
+
+    lm = model.language_model
+    b = input_ids.shape[0]
+    dev = input_ids.device
+    if num_beams > 1:
+        # expand every prompt to num_beams rows (HF _expand_inputs_for_generation)
+        rep_idx = torch.arange(b, device=dev).repeat_interleave(num_beams)
+        n_per = None
+        if video_features is not None:
+            # features are spliced in row-major mask order: replicate each row's features
+            counts = video_mask.sum(dim=1).tolist()
+            chunks, start = [], 0
+            for c in counts:
+                chunks += [video_features[start:start + c]] * num_beams
+                start += c
+            video_features = torch.cat(chunks, dim=0) if chunks else video_features
+            del n_per
+        input_ids = input_ids[rep_idx]
+        attention_mask = attention_mask[rep_idx]
+        video_mask = video_mask[rep_idx] if video_mask is not None else None
+
+    logits, state = E_opt.opt_prefill(lm, lm._pack, input_ids, attention_mask, video_mask,
+                                      video_features, max_new)
+    model._last_splice_status = state["status"]
+    if num_beams > 1:
+        return _beam_search(lm, logits, state, b, num_beams, max_new, min_new, eos_ids, pad_id, rep,
+                            length_penalty, early_stopping, do_sample, temperature, top_k, top_p)
+
+    rows = input_ids.shape[0]
+    generated = torch.empty((rows, 0), dtype=torch.long, device=dev)
+    unfinished = torch.ones(rows, dtype=torch.bool, device=dev)
+    eos_t = torch.tensor(eos_ids, device=dev, dtype=torch.long) if eos_ids else None
+    for step in range(max_new):
+        scores = _process_logits(logits, generated, step, min_new_tokens=min_new, eos_ids=eos_ids,
+                                 repetition_penalty=rep)
+        if do_sample:
+            probs = _warp(scores, temperature, top_k, top_p).softmax(dim=-1)
+            nxt = torch.multinomial(probs, 1).squeeze(1)
+        else:
+            nxt = scores.argmax(dim=-1)
+        nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_id))
+        generated = torch.cat([generated, nxt[:, None]], dim=1)
+        if eos_t is not None:
+            unfinished = unfinished & ~torch.isin(nxt, eos_t)
+            if not bool(unfinished.any()):
+                break
+        if step + 1 < max_new:
+            logits = E_opt.opt_decode_step(lm, lm._pack, nxt, state)
+    return generated
+
+
+def _beam_search(lm, logits, state, batch, nb, max_new, min_new, eos_ids, pad_id, rep,
+                 length_penalty, early_stopping, do_sample, temperature, top_k, top_p):
+    """Standard beam search with HF's scoring: hypotheses are ranked by
+    sum_logprobs / generated_len**length_penalty (BeamHypotheses.add)."""
+    dev = logits.device
+    vocab = logits.shape[-1]
+    beam_scores = torch.zeros((batch, nb), device=dev)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.view(-1)
+    generated = torch.empty((batch * nb, 0), dtype=torch.long, device=dev)
+    finished: list[list[tuple[float, torch.Tensor]]] = [[] for _ in range(batch)]
+    done = [False] * batch
+    eos_set = set(eos_ids)
+
+    def worst(i):
+        return min(h[0] for h in finished[i])
+
+    for step in range(max_new):
+        scores = _process_logits(logits, generated, step, min_new_tokens=min_new, eos_ids=eos_ids,
+                                 repetition_penalty=rep)
+        logp = torch.log_softmax(scores, dim=-1)
+        if do_sample:
+            logp = torch.log_softmax(_warp(logp, temperature, top_k, top_p), dim=-1)
+        cand = (logp + beam_scores[:, None]).view(batch, nb * vocab)
+        if do_sample:
+            pick = torch.multinomial(cand.softmax(dim=-1), 2 * nb)
+            top_s = torch.gather(cand, 1, pick)
+            top_s, order = top_s.sort(dim=1, descending=True)
+            top_i = torch.gather(pick, 1, order)
+        else:
+            top_s, top_i = torch.topk(cand, 2 * nb, dim=1)
+        top_s_l, top_i_l = top_s.tolist(), top_i.tolist()
+        next_scores = torch.zeros((batch, nb), device=dev)
+        next_tokens = torch.full((batch, nb), pad_id, dtype=torch.long, device=dev)
+        next_src = torch.zeros((batch, nb), dtype=torch.long, device=dev)
+        gen_len = step + 1
+        for i in range(batch):
+            base = i * nb
+            if done[i]:
+                next_src[i] = base
+                continue
+            keep = []
+            for rank, (s, idx) in enumerate(zip(top_s_l[i], top_i_l[i])):
+                src, tok = idx // vocab, idx % vocab
+                if tok in eos_set:
+                    if rank >= nb:
+                        continue
+                    hyp = generated[base + src].clone()
+                    score = s / (gen_len ** length_penalty)
+                    if len(finished[i]) < nb or score > worst(i):
+                        finished[i].append((score, torch.cat([hyp, torch.tensor([tok], device=dev)])))
+                        if len(finished[i]) > nb:
+                            finished[i].remove(min(finished[i], key=lambda h: h[0]))
+                else:
+                    keep.append((s, tok, base + src))
+                if len(keep) == nb:
+                    break
+            for j, (s, tok, src) in enumerate(keep):
+                next_scores[i, j], next_tokens[i, j], next_src[i, j] = s, tok, src
+            if len(finished[i]) >= nb:
+                if early_stopping is True:
+                    done[i] = True
+                else:
+                    best_running = keep[0][0] if keep else -1e9
+                    if early_stopping == "never" and length_penalty > 0:
+                        bound = best_running / (max_new ** length_penalty)
+                    else:
+                        bound = best_running / (gen_len ** length_penalty)
+                    done[i] = worst(i) >= bound
+        beam_scores = next_scores.view(-1)
+        src = next_src.view(-1)
+        generated = torch.cat([generated[src], next_tokens.view(-1, 1)], dim=1)
+        if all(done) or step + 1 == max_new:
+            break
+        state["kv"].reorder(src)
+        for key in ("ctx_len", "first_valid", "n_valid"):
+            state[key] = state[key][src].contiguous()
+        logits = E_opt.opt_decode_step(lm, lm._pack, next_tokens.view(-1), state)
+
+    out = []
+    for i in range(batch):
+        if not done[i]:  # add the running beams as finished hypotheses (HF finalize)
+            for j in range(nb):
+                s = float(beam_scores[i * nb + j])
+                hyp = generated[i * nb + j]
+                score = s / (hyp.shape[0] ** length_penalty)
+                if len(finished[i]) < nb or score > worst(i):
+                    finished[i].append((score, hyp))
+                    if len(finished[i]) > nb:
+                        finished[i].remove(min(finished[i], key=lambda h: h[0]))
+        out.append(max(finished[i], key=lambda h: h[0])[1])
+    width = max(h.shape[0] for h in out)
+    res = torch.full((batch, width), pad_id, dtype=torch.long, device=dev)
+    for i, h in enumerate(out):
+        res[i, : h.shape[0]] = h
+    return res

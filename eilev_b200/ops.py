@@ -85,14 +85,19 @@ def gemm_uses_tcgen05(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> bo
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
-              residual: torch.Tensor | None = None, save_stats: bool = False):
+              residual: torch.Tensor | None = None, save_stats: bool = False,
+              out: torch.Tensor | None = None):
     """LayerNorm over the last dim of a 2-D bf16 tensor (optionally of x + residual)."""
     _need(x, torch.bfloat16, "layernorm.x")
     _need(gamma, torch.float32, "layernorm.gamma")
     _need(beta, torch.float32, "layernorm.beta")
     assert x.dim() == 2 and x.stride(1) == 1
     rows, cols = x.shape
-    y = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        y = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    else:
+        y = out
+        assert y.shape == (rows, cols) and y.stride(1) == 1 and y.dtype == torch.bfloat16
     mean = rstd = None
     if save_stats:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
@@ -102,7 +107,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         assert residual.shape == x.shape and residual.stride(1) == 1
     check(_lib.lib().vb_layernorm(x.data_ptr(), _ptr(residual), gamma.data_ptr(), beta.data_ptr(),
                                   y.data_ptr(), _ptr(mean), _ptr(rstd), rows, cols, x.stride(0),
-                                  residual.stride(0) if residual is not None else 0, cols, eps,
+                                  residual.stride(0) if residual is not None else 0, y.stride(0), eps,
                                   _stream()), "vb_layernorm")
     return (y, mean, rstd) if save_stats else y
 
