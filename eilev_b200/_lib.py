@@ -120,7 +120,19 @@ def lib() -> C.CDLL:
     return handle
 
 
+# kernels launched per successful C-ABI call (lower bounds), for bench.py's gpu_launches
+_KERNELS_PER_CALL = {"vb_cross_entropy": 2, "vb_embed_splice": 2, "vb_attention_bwd": 3}
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of native kernel launches issued through this binding so far."""
+    return _launches
+
+
 def check(status: int, what: str) -> None:
+    global _launches
+    _launches += _KERNELS_PER_CALL.get(what, 1)
     if status != 0:
         msg = lib().vb_last_error()
         raise VbError(f"{what} failed: {msg.decode() if msg else 'unknown error'}")

@@ -1,0 +1,162 @@
+"""Data-parallel training step for the VideoBLIP recipe (one process per GPU).
+
+Mirrors what ``scripts/general/train_v2.py:104-219`` obtains from HuggingFace ``Trainer`` +
+DDP for this model (README.md:139-164: bs 1 x grad-accum 16 x 8 GPUs, bf16, AdamW lr 1e-5,
+weight decay 0.05, max_grad_norm 1.0):
+
+    micro_step  = model(**batch).loss / accum ; backward  (accumulate, no communication)
+    every `accum` micro-steps:
+        ONE all-reduce (NCCL over NVLink / NVSwitch) of the flat gradient buffer of the 257
+        trainable tensors (107 M f32 = 428 MB) -> global-norm clip -> fused AdamW kernel,
+        all on the compute stream, no host synchronisation.
+
+The datapoints shard across ranks with no activation traffic; the frozen ViT
+and LM never communicate.  The trainable parameters and their gradients are re-pointed into
+two flat f32 buffers so the collective and the optimizer are single launches.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Iterable
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine.qformer import qformer_param_list
+
+
+def freeze_for_recipe(model) -> None:
+    """train_v2.py:123-130 — only Q-Former, query_tokens and language_projection train."""
+    for p in model.vision_model.parameters():
+        p.requires_grad = False
+    for p in model.language_model.parameters():
+        p.requires_grad = False
+    model.enable_input_require_grads()
+
+
+class FlatBuffers:
+    """f32 master parameters / gradients of the trainable tensors in two contiguous buffers;
+    ``param.data`` and ``param.grad`` become views, so autograd accumulates straight into the
+    buffer the collective and the optimizer consume."""
+
+    def __init__(self, named_params: Iterable[tuple[str, torch.nn.Parameter]]) -> None:
+        self.named = [(n, p) for n, p in named_params if p.requires_grad]
+        if not self.named:
+            raise ValueError("no trainable parameters")
+        dev = self.named[0][1].device
+        self.offsets = []
+        total = 0
+        for _, p in self.named:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.numel = total
+        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for (_, p), off in zip(self.named, self.offsets):
+                view = self.params[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data.float())
+                p.data = view
+                p.grad = self.grads[off:off + p.numel()].view(p.shape)
+
+    def zero_grad(self) -> None:
+        self.grads.zero_()
+        for (_, p), off in zip(self.named, self.offsets):  # re-attach (a caller may have set None)
+            if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * off:
+                p.grad = self.grads[off:off + p.numel()].view(p.shape)
+
+
+class DataParallelTrainer:
+    def __init__(self, model, *, lr: float = 1e-5, weight_decay: float = 0.05,
+                 betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: float = 1.0, grad_accum: int = 16, process_group=None,
+                 lr_schedule: Callable[[int], float] | None = None,
+                 update_fn: Callable | None = None) -> None:
+        self.model = model
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.max_grad_norm, self.grad_accum = max_grad_norm, grad_accum
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.lr_schedule = lr_schedule
+        self.flat = FlatBuffers(qformer_param_list(model))
+        self.exp_avg = torch.zeros_like(self.flat.params)
+        self.exp_avg_sq = torch.zeros_like(self.flat.params)
+        self.opt_step = 0
+        self.micro = 0
+        self._update = update_fn or self._fused_adamw
+        dev = self.flat.params.device
+        self._sumsq = torch.zeros((), dtype=torch.float32, device=dev)
+        self._scale = torch.ones((), dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ steps
+    def micro_step(self, batch: dict) -> torch.Tensor:
+        """One datapoint: forward + backward, gradients accumulate locally (DDP no_sync)."""
+        out = self.model(**batch)
+        loss = out.loss if hasattr(out, "loss") else out[0]
+        (loss / self.grad_accum).backward()
+        self.micro += 1
+        if self.micro % self.grad_accum == 0:
+            self.optimizer_step()
+        return loss.detach()
+
+    def grad_norm_and_scale(self) -> None:
+        """scale = clip / world: gradients were summed over ranks (already divided by accum in
+        micro_step); the clip coefficient uses the norm of the averaged gradient, as
+        torch.nn.utils.clip_grad_norm_ does inside Trainer."""
+        g = self.flat.grads
+        self._sumsq.zero_()
+        if g.is_cuda:
+            ops.sumsq(g, self._sumsq)
+        else:
+            self._sumsq += (g.double() ** 2).sum().float()
+        norm = torch.sqrt(self._sumsq) / self.world
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            clip = torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0)
+        else:
+            clip = torch.ones_like(norm)
+        self._scale.copy_(clip / self.world)
+        self.last_grad_norm = norm
+
+    def optimizer_step(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat.grads, op=dist.ReduceOp.SUM, group=self.group)
+        self.grad_norm_and_scale()
+        self.opt_step += 1
+        lr = self.lr_schedule(self.opt_step) if self.lr_schedule is not None else self.lr
+        self._update(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=lr,
+                     beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                     weight_decay=self.weight_decay, step=self.opt_step, grad_scale=self._scale)
+        # parameters changed in place through the flat buffer: drop the packed bf16 copies
+        self.model._pack.clear()
+        self.flat.zero_grad()
+
+    @staticmethod
+    def _fused_adamw(param, grad, exp_avg, exp_avg_sq, **kw) -> None:
+        ops.adamw_(param, grad, exp_avg, exp_avg_sq, **kw)
+
+
+def linear_schedule(base_lr: float, total_steps: int, warmup_steps: int = 0) -> Callable[[int], float]:
+    """HF ``get_linear_schedule_with_warmup`` (Trainer default lr_scheduler_type='linear')."""
+
+    def f(step: int) -> float:
+        s = step - 1
+        if s < warmup_steps:
+            return base_lr * s / max(1, warmup_steps)
+        return base_lr * max(0.0, (total_steps - s) / max(1, total_steps - warmup_steps))
+
+    return f
+
+
+def torch_adamw_reference(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay,
+                          step, grad_scale=None) -> None:
+    """Plain-torch AdamW with the kernel's contract — used by the CPU (gloo) tests of the
+    data-parallel host logic only."""
+    g = grad * (grad_scale if grad_scale is not None else 1.0)
+    param.mul_(1 - lr * weight_decay)
+    exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = exp_avg_sq.sqrt() / math.sqrt(bc2) + eps
+    param.addcdiv_(exp_avg, denom, value=-lr / bc1)

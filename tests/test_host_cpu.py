@@ -1,0 +1,229 @@
+"""Host-side logic that needs no GPU: HF-surface construction / state-dict contract,
+save/load round trip, error behaviour, tokeniser + collator golden vectors from the
+reference's tests/data/test_utils.py (replayed with a table-driven stub tokenizer)."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+from transformers import Blip2Config
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def small_cfg():
+    sys.path.insert(0, str(GOLDEN))
+    import make_golden as MG
+    return Blip2Config(**MG.CONFIGS["small_opt"]["config"])
+
+
+def test_state_dict_keys_match_the_reference_checkpoint_layout():
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    fx = torch.load(GOLDEN / "small_opt.pt", weights_only=False)
+    m = VideoBlipForConditionalGeneration(small_cfg())
+    assert set(m.state_dict()) == set(fx["state_dict"])
+    for k, v in m.state_dict().items():
+        assert v.shape == fx["state_dict"][k].shape, k
+    m.load_state_dict(fx["state_dict"], strict=True)
+    lm = m.language_model
+    assert lm.lm_head.weight.data_ptr() == lm.model.decoder.embed_tokens.weight.data_ptr()
+    assert m.get_input_embeddings() is lm.model.decoder.embed_tokens
+    assert float(VideoBlipForConditionalGeneration(small_cfg()).query_tokens.abs().sum()) == 0.0  # v2.py:115-117
+
+
+def test_save_and_from_pretrained_round_trip(tmp_path):
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    fx = torch.load(GOLDEN / "tiny_opt.pt", weights_only=False)
+    cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    m = VideoBlipForConditionalGeneration(cfg)
+    m.load_state_dict(fx["state_dict"])
+    m.save_pretrained(tmp_path)
+    m2 = VideoBlipForConditionalGeneration.from_pretrained(tmp_path, low_cpu_mem_usage=True)
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, fx["state_dict"][k]), k
+    m3 = VideoBlipForConditionalGeneration.from_pretrained(tmp_path, torch_dtype=torch.bfloat16)
+    assert m3.dtype == torch.bfloat16
+    assert m3.language_model.lm_head.weight.data_ptr() == m3.language_model.model.decoder.embed_tokens.weight.data_ptr()
+    assert m3.config.num_query_tokens == cfg.num_query_tokens
+    m3.config.text_config.eos_token_id = 7  # train_v2.py:122 writes this
+    assert m3.config.text_config.eos_token_id == 7
+
+
+def test_recipe_freezing_and_param_census():
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    from eilev_b200.train import freeze_for_recipe
+    m = VideoBlipForConditionalGeneration(small_cfg())
+    freeze_for_recipe(m)
+    trainable = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert all(n.startswith(("qformer.", "query_tokens", "language_projection.")) for n in trainable)
+    fx = torch.load(GOLDEN / "small_opt.pt", weights_only=False)
+    assert set(trainable) == set(fx["grads"])
+
+
+def test_forward_contract_errors_on_cpu():
+    from eilev_b200 import _lib
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration, VideoBlipVisionModel
+    cfg = small_cfg()
+    m = VideoBlipForConditionalGeneration(cfg)
+    with pytest.raises(AssertionError):  # pixel_values without video_input_mask (v2.py:154-157)
+        m(torch.ones(1, 4).long(), pixel_values=torch.zeros(1, 3, 1, 56, 56))
+    with pytest.raises(_lib.VbError):  # no silent CPU fallback
+        m(torch.ones(1, 4).long())
+    with pytest.raises(ValueError):  # v2.py:50-51
+        VideoBlipVisionModel(cfg.vision_config)(None)
+    with pytest.raises(NotImplementedError):
+        Blip2Config(text_config={"model_type": "t5", "d_model": 8, "d_kv": 4, "d_ff": 16, "num_layers": 2, "num_heads": 2}) and \
+            VideoBlipForConditionalGeneration(Blip2Config(
+                vision_config=cfg.vision_config.to_dict(), qformer_config=cfg.qformer_config.to_dict(),
+                text_config={"model_type": "t5", "d_model": 8, "d_kv": 4, "d_ff": 16, "num_layers": 2, "num_heads": 2}))
+
+
+# ------------------------------------------------------------------ tokeniser / collator
+class StubTokenizer:
+    """Table-driven tokenizer with the ids of the reference fixtures
+    (tests/data/test_utils.py:112-127, :463-474): OPT bos=eos=2 pad=1 '\\n'=50118."""
+
+    def __init__(self, table, bos, eos, pad, add_bos, add_eos, padding_side="right"):
+        self.table, self.bos_token_id, self.eos_token_id, self.pad_token_id = table, bos, eos, pad
+        self.add_bos, self.add_eos, self.padding_side = add_bos, add_eos, padding_side
+        self.model_input_names = ["input_ids", "attention_mask"]
+
+    def __call__(self, text, add_special_tokens=True, return_attention_mask=True, **_):
+        from transformers import BatchEncoding
+        ids = list(self.table[text])
+        if add_special_tokens:
+            if self.add_bos:
+                ids = [self.bos_token_id] + ids
+            if self.add_eos:
+                ids = ids + [self.eos_token_id]
+        return BatchEncoding({"input_ids": ids})
+
+    def pad(self, features, padding=True, max_length=None, pad_to_multiple_of=None, return_tensors=None, **_):
+        from transformers import BatchEncoding
+        width = max(len(f["input_ids"]) for f in features)
+        if pad_to_multiple_of:
+            width = (width + pad_to_multiple_of - 1) // pad_to_multiple_of * pad_to_multiple_of
+        out = {"input_ids": [], "attention_mask": []}
+        extra = [k for k in features[0] if k not in ("input_ids", "attention_mask")]
+        for k in extra:
+            out[k] = []
+        for f in features:
+            ids = list(map(int, f["input_ids"]))
+            n = width - len(ids)
+            if self.padding_side == "right":
+                out["input_ids"].append(ids + [self.pad_token_id] * n)
+                out["attention_mask"].append([1] * len(ids) + [0] * n)
+            else:
+                out["input_ids"].append([self.pad_token_id] * n + ids)
+                out["attention_mask"].append([0] * n + [1] * len(ids))
+            for k in extra:
+                out[k].append(list(map(int, f[k])))
+        return BatchEncoding({k: torch.tensor(v) for k, v in out.items()})
+
+
+OPT_TABLE = {"\n": [50118], "A prompt": [250, 14302], " A text\n": [83, 2788, 50118],
+             "Prompt 1 Text 1\n": [35396, 3320, 112, 14159, 112, 50118], "Prompt 2": [35396, 3320, 132],
+             " Text 2\n": [14159, 132, 50118]}
+T5_TABLE = {"\n": [3], "A prompt": [71, 9005], "A text": [71, 1499]}
+
+
+def opt_tok(side="right"):
+    return StubTokenizer(OPT_TABLE, 2, 2, 1, add_bos=True, add_eos=False, padding_side=side)
+
+
+def t5_tok():
+    return StubTokenizer(T5_TABLE, None, 1, 0, add_bos=False, add_eos=True)
+
+
+def test_interleaved_tokeniser_opt_golden():
+    """tests/data/test_utils.py:115-127 of the reference."""
+    from eilev_b200.data.utils import generate_input_ids_and_labels_from_interleaved as gen
+    r = gen(opt_tok(), [("A prompt", 1)], "A text", 2, True)
+    assert r["input_ids"].tolist() == [2, 1, 1, 50118, 250, 14302, 83, 2788, 50118, 2]
+    assert r["labels"].tolist() == [-100] * 6 + [83, 2788, 50118, 2]
+    assert r["video_input_mask"].tolist() == [0, 1, 1, 0, 0, 0, 0, 0, 0, 0]
+    r = gen(opt_tok(), [("Prompt 1 Text 1", 1), ("Prompt 2", 2)], "Text 2", 2, True)
+    assert r["input_ids"].tolist() == [2, 1, 1, 50118, 35396, 3320, 112, 14159, 112, 50118,
+                                       1, 1, 50118, 1, 1, 50118, 35396, 3320, 132, 14159, 132, 50118, 2]
+    assert r["video_input_mask"].tolist() == [0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0]
+    assert r["labels"].tolist() == [-100] * 19 + [14159, 132, 50118, 2]
+    r = gen(opt_tok(), [("A prompt", 1)], None, 2, True)  # generation: no target
+    assert r["input_ids"].tolist() == [2, 1, 1, 50118, 250, 14302]
+    assert r["labels"].tolist() == [-100] * 6
+
+
+def test_interleaved_tokeniser_t5_golden():
+    """tests/data/test_utils.py:466-474 of the reference."""
+    from eilev_b200.data.utils import generate_input_ids_and_labels_from_interleaved as gen
+    r = gen(t5_tok(), [("A prompt", 1)], "A text", 2, False)
+    assert r["input_ids"].tolist() == [0, 0, 3, 71, 9005, 1]
+    assert r["labels"].tolist() == [71, 1499, 1]
+    assert r["video_input_mask"].tolist() == [1, 1, 0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("side", ["right", "left"])
+@pytest.mark.parametrize("multiple", [None, 8])
+def test_interleaved_collator(side, multiple):
+    """Padding side x pad_to_multiple_of matrix of tests/data/test_utils.py:674-862."""
+    from eilev_b200.data.utils import DataCollatorForInterleavedVideoSeq2Seq
+    tok = opt_tok(side)
+    col = DataCollatorForInterleavedVideoSeq2Seq(tok, pad_to_multiple_of=multiple)
+    feats = [
+        {"input_ids": torch.tensor([2, 1, 1, 50118, 250]), "labels": torch.tensor([-100, -100, -100, -100, 250]),
+         "video_input_mask": torch.tensor([0, 1, 1, 0, 0]), "pixel_values": torch.zeros(1, 3, 2, 4, 4)},
+        {"input_ids": torch.tensor([2, 1, 1, 50118, 1, 1, 50118, 250, 14302]),
+         "labels": torch.tensor([-100] * 7 + [250, 14302]),
+         "video_input_mask": torch.tensor([0, 1, 1, 0, 1, 1, 0, 0, 0]), "pixel_values": torch.ones(2, 3, 2, 4, 4)},
+    ]
+    out = col(feats)
+    width = 16 if multiple else 9
+    assert out["input_ids"].shape == (2, width) and out["video_input_mask"].shape == (2, width)
+    assert out["pixel_values"].shape == (3, 3, 2, 4, 4)
+    assert float(out["pixel_values"][0].sum()) == 0 and float(out["pixel_values"][1:].min()) == 1  # batch order
+    n0 = width - 5
+    if side == "right":
+        assert out["video_input_mask"][0].tolist() == [0, 1, 1, 0, 0] + [0] * n0
+        assert out["input_ids"][0].tolist() == [2, 1, 1, 50118, 250] + [1] * n0
+        assert out["labels"][0].tolist() == [-100, -100, -100, -100, 250] + [-100] * n0
+        assert out["attention_mask"][0].tolist() == [1] * 5 + [0] * n0
+    else:
+        assert out["video_input_mask"][0].tolist() == [0] * n0 + [0, 1, 1, 0, 0]
+        assert out["input_ids"][0].tolist() == [1] * n0 + [2, 1, 1, 50118, 250]
+        assert out["labels"][0].tolist() == [-100] * n0 + [-100, -100, -100, -100, 250]
+    assert int(out["video_input_mask"].sum()) == 3 * 2
+
+
+def test_clean_narration_text_table():
+    """tests/data/test_utils.py:19-54 of the reference."""
+    from eilev_b200.data.utils import clean_narration_text as c
+    assert c("#C C drops a plate") == "The camera wearer drops a plate."
+    assert c("#c c looks around <|eos|>") == "The camera wearer looks around."
+    assert c("#C C picks #unsure") == "The camera wearer picks."
+    assert c("#C C holds #Unsure in hand") == "The camera wearer holds something in hand."
+    assert c("  already punctuated!  ") == "already punctuated!"
+    assert c("") == ""
+
+
+def test_single_clip_tokeniser():
+    from eilev_b200.data.utils import generate_input_ids_and_labels as gen
+    table = dict(OPT_TABLE)
+    table[" A text"] = [83, 2788]
+    tok = StubTokenizer(table, 2, 2, 1, add_bos=True, add_eos=False)
+    r = gen(tok, "A prompt", "A text", True)
+    assert r["input_ids"].tolist() == [2, 250, 14302, 83, 2788, 2]
+    assert r["labels"].tolist() == [-100, -100, -100, 83, 2788, 2]
+    r = gen(t5_tok(), "A prompt", "A text", False)
+    assert r["input_ids"].tolist() == [71, 9005, 1] and r["labels"].tolist() == [71, 1499, 1]
+
+
+def test_process_unfolds_time_axis():
+    """tests/model/test_model_utils.py of the reference (Mock processor)."""
+    from unittest.mock import Mock
+    from transformers import BatchEncoding
+    from eilev_b200.model.utils import process
+    proc = Mock(return_value=BatchEncoding({"pixel_values": torch.zeros(2 * 5, 3, 224, 224)}))
+    out = process(proc, video=torch.zeros(2, 3, 5, 32, 48, dtype=torch.uint8), text="hi")
+    assert out["pixel_values"].shape == (2, 3, 5, 224, 224)
+    assert proc.call_args.kwargs["images"].shape == (10, 3, 32, 48)
+    proc = Mock(return_value=BatchEncoding({"pixel_values": torch.zeros(5, 3, 224, 224)}))
+    assert process(proc, video=torch.zeros(3, 5, 32, 48))["pixel_values"].shape == (1, 3, 5, 224, 224)
