@@ -299,6 +299,13 @@ def gpu_arm(args) -> None:
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.profile:  # ncu --profile-from-start off: exactly one micro-step is captured
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -362,6 +369,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="run one profiler-bracketed step and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

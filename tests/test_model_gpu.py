@@ -244,4 +244,6 @@ def test_real_dims_shallow_against_oracle():
     assert r["logits"] < 0.025, r            # BASELINE.md §2.1 stated tolerance: rel-L2 <= 2.5 %
     assert r["logits_max_abs"] < 0.15, r     # and max-abs <= 0.15 at logit std ~1
     assert abs(r["loss"] - r["loss_ref"]) < 0.05, r
-    assert r["grad_rel_l2"] < 0.06, r
+    # yardstick: the reference itself, bf16 vs fp32 on CPU (tests/golden/bf16_yardstick.py),
+    # differs by 4.3 % (tiny_opt) / 8.9-9.6 % (small_opt) in global gradient rel-L2
+    assert r["grad_rel_l2"] < 0.10, r
