@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   float row_m[2] = {-INFINITY, -INFINITY};
   float row_l[2] = {0.0f, 0.0f};
   uint32_t qf[KS][4];
+  const bool warp_active = (m0 + warp * 16) < p.sq;
 
   for (int it = 0; it < n_tiles; ++it) {
     const int st = it & 1;
@@ -155,6 +156,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
 
     const __nv_bfloat16* ks_ = sk + st * 64 * LDS;
     const __nv_bfloat16* vs_ = sv + st * 64 * LDS;
+    // 16-key groups of this tile that hold at least one in-range key (S=257: the 5th tile
+    // has one) and whether this warp owns any in-range query row (the 5th query tile: one)
+    const int np_cnt = (((kv_end - n0 < kAN) ? kv_end - n0 : kAN) + 15) >> 4;
+    if (warp_active) {
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {  // pairs of 8-key blocks
+        if (np >= np_cnt) continue;
         uint32_t kf[4];
         ldsm_x4(kf, ks_ + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + ks * 16 +
                         ((lane >> 3) & 1) * 8);
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     // O += P . V
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 16-key steps
+      if (kk >= np_cnt) continue;
       uint32_t pf[4];
       pf[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
       pf[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
         mma_bf16(o_acc[2 * dp + 1], pf, vf[2], vf[3]);
       }
     }
+    }  // warp_active
     __syncthreads();  // everyone done with stage st before it is refilled
   }
   cp_async_wait<0>();

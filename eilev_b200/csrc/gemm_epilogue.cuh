@@ -1,0 +1,124 @@
+// Epilogue shared by the 1-CTA and 2-CTA tcgen05 GEMM kernels: one thread finishes 16
+// consecutive fp32 accumulator columns of one output row (bias, alpha, GELU/ReLU, residual,
+// beta*C, optional patch-embedding row remap) and stores bf16 / f32 with 16-byte accesses.
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+
+struct EpiParams {
+  void* c;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long m, n;
+  long long ldc, ldr;
+  float alpha, beta;
+  long long alpha_cols;
+  long long row_group;
+  int epilogue;
+  int out_f32;
+};
+
+// One thread finishes 16 consecutive columns of one row.
+VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
+                              const uint32_t (&acc)[16]) {
+  if (row >= p.m || col0 >= p.n) return;
+  long long out_row = row, res_row = row;
+  if (p.row_group > 0) {
+    out_row = row + row / p.row_group + 1;
+    res_row = 1 + row % p.row_group;
+  }
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  const bool full = (col0 + 16 <= p.n);
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.alpha != 1.0f) {
+    const long long ac = p.alpha_cols <= 0 ? p.n : p.alpha_cols;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < ac) v[j] *= p.alpha;
+  }
+  if (p.epilogue == VB_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+  } else if (p.epilogue == VB_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.residual != nullptr) {
+    const __nv_bfloat16* r = p.residual + res_row * p.ldr + col0;
+    if (full) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(r + 8 * h));
+        float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+               f3 = unpack_bf16x2(u.w);
+        v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+        v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) v[j] += __bfloat162float(r[j]);
+    }
+  }
+  if (p.out_f32) {
+    float* c = reinterpret_cast<float*>(p.c) + out_row * p.ldc + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.beta != 0.0f) {
+          float4 old = *reinterpret_cast<const float4*>(c + j);
+          o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+        }
+        *reinterpret_cast<float4*>(c + j) = o;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) c[j] = v[j] + (p.beta != 0.0f ? p.beta * c[j] : 0.0f);
+    }
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row * p.ldc + col0;
+    if (full) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (p.beta != 0.0f) {
+          uint4 u = *reinterpret_cast<const uint4*>(c + 8 * h);
+          float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                 f3 = unpack_bf16x2(u.w);
+          v[8 * h + 0] += p.beta * f0.x; v[8 * h + 1] += p.beta * f0.y;
+          v[8 * h + 2] += p.beta * f1.x; v[8 * h + 3] += p.beta * f1.y;
+          v[8 * h + 4] += p.beta * f2.x; v[8 * h + 5] += p.beta * f2.y;
+          v[8 * h + 6] += p.beta * f3.x; v[8 * h + 7] += p.beta * f3.y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
+        o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+        o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
+        o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+        *reinterpret_cast<uint4*>(c + 8 * h) = o;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) {
+          float o = v[j] + (p.beta != 0.0f ? p.beta * __bfloat162float(c[j]) : 0.0f);
+          c[j] = __float2bfloat16(o);
+        }
+    }
+  }
+}
+
+
+}  // namespace vb

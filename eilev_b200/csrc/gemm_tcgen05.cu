@@ -11,6 +11,7 @@
 // include/videoblip_b200.h, vb_gemm).
 #include "common.cuh"
 #include "gemm.h"
+#include "gemm_epilogue.cuh"
 
 namespace vb {
 
@@ -31,120 +32,6 @@ struct GemmCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
 };
-
-struct EpiParams {
-  void* c;
-  const float* bias;
-  const __nv_bfloat16* residual;
-  long long m, n;
-  long long ldc, ldr;
-  float alpha, beta;
-  long long alpha_cols;
-  long long row_group;
-  int epilogue;
-  int out_f32;
-};
-
-// One thread finishes 16 consecutive columns of one row.
-VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
-                              const uint32_t (&acc)[16]) {
-  if (row >= p.m || col0 >= p.n) return;
-  long long out_row = row, res_row = row;
-  if (p.row_group > 0) {
-    out_row = row + row / p.row_group + 1;
-    res_row = 1 + row % p.row_group;
-  }
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-  const bool full = (col0 + 16 <= p.n);
-  if (p.bias != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
-    }
-  }
-  if (p.alpha != 1.0f) {
-    const long long ac = p.alpha_cols <= 0 ? p.n : p.alpha_cols;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (col0 + j < ac) v[j] *= p.alpha;
-  }
-  if (p.epilogue == VB_EPI_GELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.epilogue == VB_EPI_RELU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-  }
-  if (p.residual != nullptr) {
-    const __nv_bfloat16* r = p.residual + res_row * p.ldr + col0;
-    if (full) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(r + 8 * h));
-        float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
-               f3 = unpack_bf16x2(u.w);
-        v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
-        v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
-      }
-    } else {
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < p.n) v[j] += __bfloat162float(r[j]);
-    }
-  }
-  if (p.out_f32) {
-    float* c = reinterpret_cast<float*>(p.c) + out_row * p.ldc + col0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (p.beta != 0.0f) {
-          float4 old = *reinterpret_cast<const float4*>(c + j);
-          o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
-        }
-        *reinterpret_cast<float4*>(c + j) = o;
-      }
-    } else {
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < p.n) c[j] = v[j] + (p.beta != 0.0f ? p.beta * c[j] : 0.0f);
-    }
-  } else {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row * p.ldc + col0;
-    if (full) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (p.beta != 0.0f) {
-          uint4 u = *reinterpret_cast<const uint4*>(c + 8 * h);
-          float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
-                 f3 = unpack_bf16x2(u.w);
-          v[8 * h + 0] += p.beta * f0.x; v[8 * h + 1] += p.beta * f0.y;
-          v[8 * h + 2] += p.beta * f1.x; v[8 * h + 3] += p.beta * f1.y;
-          v[8 * h + 4] += p.beta * f2.x; v[8 * h + 5] += p.beta * f2.y;
-          v[8 * h + 6] += p.beta * f3.x; v[8 * h + 7] += p.beta * f3.y;
-        }
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
-        o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
-        o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
-        o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
-        *reinterpret_cast<uint4*>(c + 8 * h) = o;
-      }
-    } else {
-      for (int j = 0; j < 16; ++j)
-        if (col0 + j < p.n) {
-          float o = v[j] + (p.beta != 0.0f ? p.beta * __bfloat162float(c[j]) : 0.0f);
-          c[j] = __float2bfloat16(o);
-        }
-    }
-  }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -305,8 +192,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // (rows, cols) bf16 row-major matrix with row stride ld; box = 64 columns x box_rows rows.
-static bool make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols,
-                      long long ld, int box_rows) {
+bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols,
+                       long long ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -356,8 +243,8 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
                              int force_grid) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
-  if (!make_tmap(&ta, a.a, a.m, a.k, a.lda, kBM)) return cudaErrorInvalidValue;
-  if (!make_tmap(&tb, a.b, a.n, a.k, a.ldb, BN)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, kBM)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, BN)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
@@ -387,8 +274,7 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
   return cudaGetLastError();
 }
 
-cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
-  EpiParams ep;
+void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {
   ep.c = a.c;
   ep.bias = a.bias;
   ep.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
@@ -398,6 +284,29 @@ cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
   ep.row_group = a.row_group;
   ep.epilogue = a.epilogue;
   ep.out_f32 = (a.out_dtype == VB_F32) ? 1 : 0;
+}
+
+cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t stream);
+
+// CTA-pair 256 x 256 tiles win on every large launch measured on B200 (sweep in
+// profiles/r01_gemm_tile_sweep.txt: +6..+12 % over the best 1-CTA tile, including N = 1408
+// where 8 % of the tile is padding); they need a few waves of pair-tiles to pay off.
+static int pick_2cta_block_n(long long m, long long n) {
+  if (m < 512) return 0;
+  const long long tiles = ((m + 255) / 256) * ((n + 255) / 256);
+  return tiles >= 3 * 74 ? 256 : 0;
+}
+
+// vb_gemm_args.reserved: 0 = automatic; 64/128/176/256 = force the 1-CTA kernel with that
+// BLOCK_N; 1000 + {128,176,256} = force the CTA-pair kernel (used by the tests).
+cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
+  if (a.reserved >= 1000) return gemm_tcgen05_2cta_launch(a, a.reserved - 1000, stream);
+  if (a.reserved == 0) {
+    const int bn2 = pick_2cta_block_n(a.m, a.n);
+    if (bn2 > 0) return gemm_tcgen05_2cta_launch(a, bn2, stream);
+  }
+  EpiParams ep;
+  fill_epi_params(ep, a);
   int bn = a.reserved > 0 ? a.reserved : pick_block_n(a.m, a.n);
   switch (bn) {
     case 256: return launch_bn<256>(a, ep, stream, 0);

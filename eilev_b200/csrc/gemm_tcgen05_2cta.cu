@@ -1,0 +1,230 @@
+// CTA-pair variant of the tcgen05 GEMM (tcgen05.mma.cta_group::2): two CTAs of one cluster
+// (one TPC) compute a 256 x BN tile together.  Each CTA stages its own 128 rows of A and
+// HALF of the B tile; the pair's tensor cores read both halves, so per-SM shared-memory fill
+// traffic and L2->SM traffic drop by a third against the single-CTA 128 x BN tile and the
+// freed shared memory buys a deeper TMA ring (6-7 stages).  Used for the large-M launches
+// (the ViT and the cross-attention K/V projection); small-M launches keep the 1-CTA kernel.
+//
+//   warp 0   TMA producer (both CTAs; transaction bytes are credited to the leader's barrier)
+//   warp 1   MMA issuer   (leader CTA only, one thread; commits multicast to both CTAs)
+//   warp 2   TMEM allocator (cta_group::2)
+//   warps 4-11 epilogue (each CTA drains its own 128 accumulator rows)
+#include "common.cuh"
+#include "gemm.h"
+#include "gemm_epilogue.cuh"
+
+namespace vb {
+
+constexpr int k2BM = 128;  // rows per CTA (256 per pair)
+constexpr int k2BK = 64;
+constexpr int k2Threads = 384;
+constexpr int k2EpiWarps = 8;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = k2BM * k2BK * 2;
+  static constexpr int kBBytes = (BN / 2) * k2BK * 2;  // this CTA's half of B
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(BN % 32 == 0 || BN == 176, "BN/2 must be a whole number of 8-row groups");
+  static_assert(kBBytes % 1024 == 0, "B half stage must keep 1024B alignment");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b, const EpiParams p,
+                         const int num_k_blocks, const int m_tiles, const int n_tiles) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_tiles = m_tiles * n_tiles;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // one arrival per CTA of the pair (used on the leader)
+      mbar_init(&empty_bar[s], 1);  // multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * k2EpiWarps);  // epilogue warps of both CTAs (leader only)
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row_a = m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
+        const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * k2BK, row_a);
+          tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * k2BK, row_b);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < k2BK / 16; ++k)
+            umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);  // accumulators of both CTAs complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (own 128 rows)
+    const int ew = warp - 4;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int kChunks = BN / 16;
+    constexpr int kHalfChunks = (kChunks + 1) / 2;
+    const int c_begin = half * kHalfChunks;
+    const int c_end = (c_begin + kHalfChunks < kChunks) ? c_begin + kHalfChunks : kChunks;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+      int ch = c_begin;
+      for (; ch + 1 < c_end; ch += 2) {  // two 16-column loads in flight per wait
+        uint32_t r0[16], r1[16];
+        tmem_ld_16(t_row + ch * 16, r0);
+        tmem_ld_16(t_row + (ch + 1) * 16, r1);
+        tmem_ld_wait();
+        if (ch + 2 >= c_end) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+        }
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + ch * 16, r0);
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + (ch + 1) * 16, r1);
+      }
+      if (ch < c_end) {
+        uint32_t r0[16];
+        tmem_ld_16(t_row + ch * 16, r0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + ch * 16, r0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs are done with TMEM / remote barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols,
+                       long long ld, int box_rows);
+void fill_epi_params(EpiParams& ep, const vb_gemm_args& a);
+
+template <int BN>
+static cudaError_t launch_2cta(const vb_gemm_args& a, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap ta, tb;
+  if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, k2BM)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, BN / 2)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  EpiParams ep;
+  fill_epi_params(ep, a);
+  const int m_tiles = static_cast<int>((a.m + 2 * k2BM - 1) / (2 * k2BM));
+  const int n_tiles = static_cast<int>((a.n + BN - 1) / BN);
+  const int k_blocks = static_cast<int>((a.k + k2BK - 1) / k2BK);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  long long pairs = sms / 2;
+  if (tiles < pairs) pairs = tiles;
+  gemm_tcgen05_2cta_kernel<BN><<<static_cast<unsigned>(2 * pairs), k2Threads, Cfg::kSmemBytes, stream>>>(
+      ta, tb, ep, k_blocks, m_tiles, n_tiles);
+  return cudaGetLastError();
+}
+
+// bn: 256 or 176 (the ViT widths 1408 / 4224 are multiples of 176)
+cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_2cta<256>(a, stream);
+    case 176: return launch_2cta<176>(a, stream);
+    case 128: return launch_2cta<128>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace vb

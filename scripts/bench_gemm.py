@@ -39,7 +39,23 @@ def timeit(fn, iters=5):
     return min(ts), sum(ts) / len(ts)
 
 
+def sweep():
+    """--sweep: every tile variant (1-CTA 64..256, CTA-pair 1000+BN) on the big ViT shapes."""
+    for name, m, n, k, epi in SHAPES[:5]:
+        a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
+        w = (torch.randn(n, k, device="cuda") * 0.05).to(torch.bfloat16)
+        bias = torch.randn(n, device="cuda")
+        out = torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
+        res = {}
+        for bn in (128, 176, 256, 1128, 1176, 1256):
+            best, _ = timeit(lambda: ops.gemm(a, w, bias, out=out, epilogue=epi, block_n=bn), iters=3)
+            res[bn] = round(2.0 * m * n * k / best / 1e9)
+        print(name, res, flush=True)
+
+
 def main():
+    if "--sweep" in sys.argv:
+        return sweep()
     only = sys.argv[1:]
     rows = []
     for name, m, n, k, epi in SHAPES:

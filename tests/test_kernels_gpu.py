@@ -32,6 +32,10 @@ GEMM_SHAPES = [
     (128, 176, 64, 176), (128, 64, 64, 64), (300, 1408, 1408, 0), (257, 4224, 1408, 0),
     (1000, 6144, 1408, 0), (520, 1408, 6144, 0), (544, 768, 768, 0), (976, 2560, 2560, 0),
     (200, 264, 72, 0), (64, 50272, 256, 0), (4096, 1408, 592, 0),
+    # CTA-pair kernel (block_n = 1000 + BN): M tails, a fully out-of-range peer CTA, K tails
+    (512, 512, 256, 1256), (300, 1408, 1408, 1176), (257, 4224, 1408, 1256), (1000, 6144, 1408, 1176),
+    (520, 1408, 6144, 1256), (200, 264, 72, 1128), (100, 256, 64, 1256), (8200, 1408, 1408, 0),
+    (5000, 6144, 1408, 0), (4100, 768, 1408, 1128),
 ]
 
 
@@ -44,7 +48,7 @@ def test_gemm_tcgen05_plain(m, n, k, bn):
     _close(out, ref, atol=0.02 * math.sqrt(k), rtol=0.01, what=f"gemm {m}x{n}x{k} bn={bn}")
 
 
-@pytest.mark.parametrize("backend", ["tcgen05", "generic"])
+@pytest.mark.parametrize("backend", ["tcgen05", "tcgen05_2cta", "generic"])
 @pytest.mark.parametrize("epi", ["none", "gelu", "relu"])
 def test_gemm_epilogues(backend, epi):
     ops = _ops()
@@ -53,15 +57,16 @@ def test_gemm_epilogues(backend, epi):
     bias = torch.randn(n, device="cuda")
     res = _rand(m, n, seed=5)
     e = {"none": ops.EPI_NONE, "gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[epi]
-    be = ops.GEMM_TCGEN05 if backend == "tcgen05" else ops.GEMM_GENERIC
-    out = ops.gemm(a, w, bias, residual=res, epilogue=e, alpha=0.5, alpha_cols=352, backend=be)
+    be = ops.GEMM_GENERIC if backend == "generic" else ops.GEMM_TCGEN05
+    bn = 1176 if backend == "tcgen05_2cta" else 0
+    out = ops.gemm(a, w, bias, residual=res, epilogue=e, alpha=0.5, alpha_cols=352, backend=be, block_n=bn)
     pre = a.float() @ w.float().t() + bias
     pre[:, :352] *= 0.5
     act = {"none": lambda x: x, "gelu": torch.nn.functional.gelu, "relu": torch.relu}[epi](pre)
     _close(out, act + res.float(), atol=0.03, rtol=0.01, what=f"{backend}/{epi}")
     # f32 output with accumulation
     c = torch.ones(m, n, device="cuda")
-    ops.gemm(a, w, bias, out=c, beta=1.0, backend=be)
+    ops.gemm(a, w, bias, out=c, beta=1.0, backend=be, block_n=bn)
     _close(c, a.float() @ w.float().t() + bias + 1.0, atol=0.03, rtol=0.01, what="f32 beta")
 
 
