@@ -61,6 +61,7 @@ SIGNATURES: dict[str, list] = {
     "vb_layernorm": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp],
     "vb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, vp],
     "vb_attention_fwd": [C.POINTER(AttnArgs), vp],
+    "vb_attention_uses_tcgen05": [C.POINTER(AttnArgs)],
     "vb_attention_bwd": [C.POINTER(AttnBwdArgs), vp],
     "vb_patch_gather": [vp, i32, vp, i64, i64, i64, i64, i64, i64, i64, vp],
     "vb_cls_rows": [vp, vp, vp, i64, i64, i64, vp],

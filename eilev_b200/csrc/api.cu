@@ -82,6 +82,10 @@ int vb_attention_fwd(const vb_attn_args* a, void* stream) {
   VB_CHECK("vb_attention_fwd", vb::attention_fwd_launch(*a, st(stream)));
 }
 
+int vb_attention_uses_tcgen05(const vb_attn_args* a) {
+  return (a != nullptr && vb::attention_tcgen05_eligible(*a)) ? 1 : 0;
+}
+
 int vb_attention_bwd(const vb_attn_bwd_args* a, void* stream) {
   if (a == nullptr || a->d_o == nullptr || a->dq == nullptr || a->dk == nullptr || a->dv == nullptr)
     return fail_msg("vb_attention_bwd", "null operand");

@@ -295,6 +295,7 @@ static bool attn_vec_ok(const vb_attn_args& a) {
 cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream) {
   if (a.batch <= 0 || a.heads <= 0 || a.sq <= 0) return cudaSuccess;
   if (a.d <= 0 || a.d > 128 || a.skv <= 0) return cudaErrorInvalidValue;
+  if (attention_tcgen05_eligible(a)) return attention_tcgen05_launch(a, stream);
   if (a.heads > 65535 || a.batch > 65535) return cudaErrorInvalidValue;
   AttnParams p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(a.q);

@@ -1,0 +1,417 @@
+// Non-causal self-attention for the ViT tower on the 5th-gen tensor cores.
+//
+// Shape class: one (frame, head) has S <= 272 keys (ViT-g: 257) and head dim d <= 128
+// (ViT-g: 88), so the whole score row fits TMEM and the softmax is single-pass — no online
+// rescaling.  One persistent CTA per SM walks (frame, head) items:
+//
+//   warp 0   TMA producer: Q tile (128 rows), K, V via 3-D tensor maps (d, head, token);
+//            d is the innermost dim with extent 88, so the 64-wide 128B-swizzled boxes are
+//            zero-filled beyond the head (no padding pass, no transposes).
+//   warp 1   MMA issuer:  S = Q K^T   (tcgen05.mma SS, M=128, N=256 (+16), K-major operands)
+//                         O = P V     (tcgen05.mma TS: P is read from TMEM where it aliases S,
+//                                      V is the MN-major B operand straight from its row layout)
+//   warps 4-7 softmax + epilogue: thread = query row (TMEM lane): tcgen05.ld the row, max,
+//            exp2, sum, bf16 P back into TMEM (tcgen05.st), later O * 1/sum -> global.
+//
+// TMEM columns: [0,272) S (fp32) / [0,136) P (bf16x2, in place), [288,416) O.
+#include "common.cuh"
+#include "internal.h"
+
+namespace vb {
+
+constexpr int kTaThreads = 256;
+constexpr int kTaQRows = 128;
+constexpr int kTaKRows = 272;            // keys padded to a multiple of 16
+constexpr int kTaHalf = 136;             // K/V are loaded as two boxes of 136 rows
+constexpr int kTaChunkBytesQ = kTaQRows * 128;   // one 64-wide d chunk of a Q tile
+constexpr int kTaChunkBytesK = kTaKRows * 128;   // one 64-wide d chunk of K or V
+constexpr int kTaSmem = 2 * 2 * kTaChunkBytesQ + 2 * 2 * kTaChunkBytesK + 1024 + 256;
+constexpr uint32_t kTaColO = 288;
+
+VB_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// A operand from TMEM (bf16 pairs per 32-bit column), B from shared memory.
+VB_DEVICE void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+VB_DEVICE void tmem_ld_32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+VB_DEVICE void tmem_st_16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+VB_DEVICE void tmem_st_8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+VB_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// MN-major bf16 operand (rows = K index, 64 contiguous elements of the MN index per 128-byte
+// swizzled row): stride between 8-row (K) groups = 1024 B, between 64-element MN groups = lbo.
+VB_DEVICE uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+struct TaParams {
+  __nv_bfloat16* o;
+  long long o_rs;      // row stride of o (elements); rows are batch*S contiguous
+  int items;           // batch * heads
+  int heads, s, d;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kTaThreads, 1)
+attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const TaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                               // [2 buffers][2 chunks][128 rows][128 B]
+  uint8_t* sK = sQ + 4 * kTaChunkBytesQ;            // [2 chunks][272 rows][128 B]
+  uint8_t* sV = sK + 2 * kTaChunkBytesK;            // [2 chunks][272 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kTaChunkBytesK);
+  uint64_t* q_full = bars;        // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_empty = bars + 5;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 8;
+  uint64_t* p_ready = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.s + kTaQRows - 1) / kTaQRows;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0};
+      int qt = 0;  // running Q tile counter -> buffer = qt & 1
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int b = item / p.heads, h = item % p.heads;
+        const int row0 = b * p.s;
+        auto load_q = [&](int t) {
+          const int buf = qt & 1;
+          mbar_wait(&q_empty[buf], q_ph[buf] ^ 1u);
+          q_ph[buf] ^= 1u;
+          mbar_expect_tx(&q_full[buf], 2 * kTaChunkBytesQ);
+          uint8_t* dst = sQ + buf * 2 * kTaChunkBytesQ;
+          tma_load_3d(dst, &tmap_q, &q_full[buf], 0, h, row0 + t * kTaQRows);
+          tma_load_3d(dst + kTaChunkBytesQ, &tmap_q, &q_full[buf], 64, h, row0 + t * kTaQRows);
+          ++qt;
+        };
+        mbar_wait(k_empty, k_ph ^ 1u);
+        k_ph ^= 1u;
+        mbar_expect_tx(k_full, 2 * kTaChunkBytesK);
+        for (int c = 0; c < 2; ++c)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sK + c * kTaChunkBytesK + hf * kTaHalf * 128, &tmap_k, k_full, c * 64, h,
+                        row0 + hf * kTaHalf);
+        load_q(0);
+        if (m_tiles > 1) load_q(1);
+        mbar_wait(v_empty, v_ph ^ 1u);
+        v_ph ^= 1u;
+        mbar_expect_tx(v_full, 2 * kTaChunkBytesK);
+        for (int c = 0; c < 2; ++c)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sV + c * kTaChunkBytesK + hf * kTaHalf * 128, &tmap_v, v_full, c * 64, h,
+                        row0 + hf * kTaHalf);
+        for (int t = 2; t < m_tiles; ++t) load_q(t);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
+      const uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 128) | (1u << 16);  // B is MN-major
+      const int k_steps = (p.d + 15) / 16;            // 16-wide steps along d (6 for d = 88)
+      const int kv_steps = (p.s + 15) / 16;           // 16-key steps of P.V (17 for S = 257)
+      const bool tail16 = p.s > 256;
+      uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0}, p_ph = 0;
+      int qt = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        mbar_wait(k_full, k_ph);
+        k_ph ^= 1u;
+        for (int t = 0; t < m_tiles; ++t) {
+          const int buf = qt & 1;
+          ++qt;
+          mbar_wait(&q_full[buf], q_ph[buf]);
+          q_ph[buf] ^= 1u;
+          tc_fence_after();
+          // ---- S = Q K^T
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const int c = ks >> 2, kk = ks & 3;
+            const uint64_t a_desc =
+                umma_desc_k_sw128(smem_u32(sQ + buf * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
+            umma_bf16(tmem_base, a_desc, b_desc, idesc_s256, ks != 0 ? 1u : 0u);
+            if (tail16) {
+              const uint64_t b16 = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK + 256 * 128)) + 2 * kk;
+              umma_bf16(tmem_base + 256, a_desc, b16, idesc_s16, ks != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&q_empty[buf]);
+          if (t == m_tiles - 1) umma_commit(k_empty);
+          umma_commit(s_full);
+          // ---- O = P V  (P written by the softmax warps into TMEM columns [0, 136))
+          if (t == 0) {
+            mbar_wait(v_full, v_ph);
+            v_ph ^= 1u;
+          }
+          mbar_wait(p_ready, p_ph);
+          p_ph ^= 1u;
+          tc_fence_after();
+          for (int js = 0; js < kv_steps; ++js) {
+            const uint64_t b_desc = umma_desc_mn_sw128(smem_u32(sV + js * 16 * 128), kTaChunkBytesK);
+            umma_bf16_ts(tmem_base + kTaColO, tmem_base + js * 8, b_desc, idesc_o, js != 0 ? 1u : 0u);
+          }
+          if (t == m_tiles - 1) umma_commit(v_empty);
+          umma_commit(o_full);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax + epilogue
+    const int quarter = warp & 3;
+    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t s_ph = 0, o_ph = 0;
+    const int n_chunks = (p.s + 31) / 32;  // 32-column chunks holding in-range keys (9 for 257)
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.heads, h = item % p.heads;
+      for (int t = 0; t < m_tiles; ++t) {
+        const int qi = t * kTaQRows + r_in_tile;
+        const bool warp_has_rows = (t * kTaQRows + quarter * 32) < p.s;
+        mbar_wait(s_full, s_ph);
+        s_ph ^= 1u;
+        tc_fence_after();
+        float inv_sum = 0.0f;
+        if (warp_has_rows) {
+          // pass 1: row maximum
+          float mx = -INFINITY;
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32(t_lane + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ch * 32 + j < p.s) mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
+          const float mxs = mx * p.scale_log2;
+          // pass 2: p = 2^(s*c - max*c), bf16 pairs written in place (P column = S column / 2)
+          float sum = 0.0f;
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32(t_lane + ch * 32, r);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int k0 = ch * 32 + 2 * j;
+              const float p0 = k0 < p.s ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs)) : 0.0f;
+              const float p1 = k0 + 1 < p.s ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs)) : 0.0f;
+              sum += p0 + p1;
+              pk[j] = pack_bf16x2(p0, p1);
+            }
+            if (ch * 32 + 32 <= kTaKRows) {
+              tmem_st_16(t_lane + ch * 16, pk);
+            } else {  // last chunk of S = 257: only 16 key columns (256..271) exist
+              uint32_t pk8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
+              tmem_st_8(t_lane + ch * 16, pk8);
+            }
+          }
+          inv_sum = 1.0f / sum;
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        // ---- epilogue: O * 1/sum -> global
+        mbar_wait(o_full, o_ph);
+        o_ph ^= 1u;
+        tc_fence_after();
+        if (warp_has_rows) {
+          __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.s + qi) * p.o_rs + h * p.d;
+          for (int ch = 0; ch * 32 < p.d; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32(t_lane + kTaColO + ch * 32, r);
+            tmem_ld_wait();
+            if (qi < p.s) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const int c0 = ch * 32 + j;
+                if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
+                  uint4 u;
+                  u.x = pack_bf16x2(__uint_as_float(r[j]) * inv_sum, __uint_as_float(r[j + 1]) * inv_sum);
+                  u.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv_sum, __uint_as_float(r[j + 3]) * inv_sum);
+                  u.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv_sum, __uint_as_float(r[j + 5]) * inv_sum);
+                  u.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv_sum, __uint_as_float(r[j + 7]) * inv_sum);
+                  *reinterpret_cast<uint4*>(orow + c0) = u;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();  // O reads retire before the next P.V overwrites the accumulator
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn3 encode_fn3() {
+  static EncodeTiledFn3 fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn3>(sym);
+  }
+  return fn;
+}
+
+// (rows, heads, d) view of a (rows, >= heads*d) bf16 buffer; box = 64 x 1 x box_rows.
+static bool make_tmap_heads(CUtensorMap* map, const void* ptr, long long rows, long long heads,
+                            long long d, long long row_stride, int box_rows) {
+  EncodeTiledFn3 fn = encode_fn3();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(heads),
+                        static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d) * 2, static_cast<cuuint64_t>(row_stride) * 2};
+  cuuint32_t box[3] = {64, 1, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool attention_tcgen05_eligible(const vb_attn_args& a) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (a.causal || a.key_mask != nullptr || a.lse != nullptr) return false;
+  if (a.sq != a.skv || a.sq > kTaKRows || a.sq < 64) return false;
+  if (a.d % 8 != 0 || a.d > 128 || a.d < 16) return false;
+  if (!al(a.q) || !al(a.k) || !al(a.v) || !al(a.o)) return false;
+  if (a.q_rs % 8 || a.k_rs % 8 || a.v_rs % 8 || a.o_rs % 8) return false;
+  // frames must be back to back: row of (b, s) = b*S + s
+  if (a.q_bs != a.sq * a.q_rs || a.k_bs != a.skv * a.k_rs || a.v_bs != a.skv * a.v_rs ||
+      a.o_bs != a.sq * a.o_rs)
+    return false;
+  if ((a.d * 2) % 16 != 0) return false;
+  if (a.batch * a.heads > (1ll << 30)) return false;
+  return true;
+}
+
+cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv;
+  const long long rows = a.batch * a.sq;
+  if (!make_tmap_heads(&tq, a.q, rows, a.heads, a.d, a.q_rs, kTaQRows)) return cudaErrorInvalidValue;
+  if (!make_tmap_heads(&tk, a.k, rows, a.heads, a.d, a.k_rs, kTaHalf)) return cudaErrorInvalidValue;
+  if (!make_tmap_heads(&tv, a.v, rows, a.heads, a.d, a.v_rs, kTaHalf)) return cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTaSmem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  TaParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a.o);
+  p.o_rs = a.o_rs;
+  p.items = static_cast<int>(a.batch * a.heads);
+  p.heads = static_cast<int>(a.heads);
+  p.s = static_cast<int>(a.sq);
+  p.d = static_cast<int>(a.d);
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int grid = p.items < sms ? p.items : sms;
+  attn_tcgen05_kernel<<<grid, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+
+}  // namespace vb

@@ -18,6 +18,8 @@ cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, c
 
 cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream);
 cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream);
+bool attention_tcgen05_eligible(const vb_attn_args& a);
+cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream);
 
 cudaError_t patch_gather_launch(const void* px, int dtype, void* out, long long nv, long long c,
                                 long long t, long long h, long long w, long long patch,

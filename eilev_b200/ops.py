@@ -164,6 +164,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     return (o, lse) if need_lse else o
 
 
+def attention_uses_tcgen05(q, k, v, heads: int, *, causal=False, key_mask=None, need_lse=False) -> bool:
+    hd = q.shape[2]
+    o = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(1, device=q.device) if need_lse else None
+    a = _attn_args(q, k, v, o, lse, key_mask, heads, hd // heads, 1.0, causal)
+    return bool(_lib.lib().vb_attention_uses_tcgen05(C.byref(a)))
+
+
 def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: bool = False,
                   key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None):
     """Returns (dq, dk, dv) with the shapes of q, k, v (contiguous unless views are given)."""

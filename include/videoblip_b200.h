@@ -127,6 +127,9 @@ typedef struct vb_attn_args {
   int32_t causal;
 } vb_attn_args;
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
+/* 1 if vb_attention_fwd takes the tcgen05/TMEM kernel (non-causal, unmasked, no lse,
+ * 64 <= S <= 272, d <= 128: the ViT shape class), 0 for the mma.sync flash kernel. */
+int vb_attention_uses_tcgen05(const vb_attn_args* args);
 
 /* Backward of the above: dq, dk, dv (bf16, same addressing as q,k,v via the dq_, dk_, dv_
  * strides).  delta: f32 workspace (B,H,Sq).  dq_acc: f32 workspace (B,Sq,H*D) zeroed by

@@ -179,6 +179,24 @@ def test_attention_fwd_bwd(b, heads, d, sq, skv, causal, masked):
         _close(got, want, atol=0.03 + 0.02 * want.abs().max().item(), rtol=0.03, what=f"attn {nm}")
 
 
+@pytest.mark.parametrize("b,heads,d,s", [(3, 16, 88, 257), (2, 4, 64, 128), (2, 2, 128, 272),
+                                          (1, 3, 40, 200), (19, 16, 88, 257), (2, 5, 96, 65)])
+def test_attention_tcgen05_vit_class(b, heads, d, s):
+    """Non-causal, unmasked, no-lse self attention with S <= 272 takes the TMEM kernel."""
+    ops = _ops()
+    hd = heads * d
+    qkv = _rand(b, s, 3 * hd, seed=70 + d)
+    q, k, v = qkv[:, :, :hd], qkv[:, :, hd:2 * hd], qkv[:, :, 2 * hd:]
+    assert ops.attention_uses_tcgen05(q, k, v, heads)
+    assert not ops.attention_uses_tcgen05(q, k, v, heads, need_lse=True)
+    scale = d ** -0.5
+    o = ops.attention(q, k, v, heads, scale)
+    ref = _attn_ref(q, k, v, heads, scale, False, None)
+    _close(o, ref, atol=0.02, rtol=0.02, what="attn tcgen05")
+    o2, _ = ops.attention(q, k, v, heads, scale, need_lse=True)  # mma.sync kernel, same inputs
+    _close(o, o2, atol=0.02, rtol=0.02, what="tcgen05 vs mma.sync")
+
+
 def test_patch_gather_and_cls():
     ops = _ops()
     px = torch.randn(2, 3, 4, 28, 28, device="cuda")
