@@ -10,8 +10,9 @@
 //   warp 1   MMA issuer:  S = Q K^T   (tcgen05.mma SS, M=128, N=256 (+16), K-major operands)
 //                         O = P V     (tcgen05.mma TS: P is read from TMEM where it aliases S,
 //                                      V is the MN-major B operand straight from its row layout)
-//   warps 4-7 softmax + epilogue: thread = query row (TMEM lane): tcgen05.ld the row, max,
-//            exp2, sum, bf16 P back into TMEM (tcgen05.st), later O * 1/sum -> global.
+//   warps 4-11 softmax + epilogue: thread = query row (TMEM lane), two warps per lane quarter
+//            split the columns: tcgen05.ld the row, max, exp2, sum (combined through smem),
+//            bf16 P back into TMEM (tcgen05.st), later O * 1/sum -> global.
 //
 // TMEM columns: [0,272) S (fp32) / [0,136) P (bf16x2, in place), [288,416) O.
 #include "common.cuh"
@@ -19,13 +20,13 @@
 
 namespace vb {
 
-constexpr int kTaThreads = 256;
+constexpr int kTaThreads = 384;
 constexpr int kTaQRows = 128;
 constexpr int kTaKRows = 272;            // keys padded to a multiple of 16
 constexpr int kTaHalf = 136;             // K/V are loaded as two boxes of 136 rows
 constexpr int kTaChunkBytesQ = kTaQRows * 128;   // one 64-wide d chunk of a Q tile
 constexpr int kTaChunkBytesK = kTaKRows * 128;   // one 64-wide d chunk of K or V
-constexpr int kTaSmem = 2 * 2 * kTaChunkBytesQ + 2 * 2 * kTaChunkBytesK + 1024 + 256;
+constexpr int kTaSmem = 2 * 2 * kTaChunkBytesQ + 2 * 2 * kTaChunkBytesK + 1024 + 128 + 1024 + 64;
 constexpr uint32_t kTaColO = 288;
 
 VB_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -134,7 +135,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -238,11 +239,21 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax + epilogue
+    // Two warps share every TMEM lane quarter and split the score columns: `half` 0 owns the
+    // 32-column chunks [0, split), half 1 owns [split, n_chunks).  Row max / row sum are
+    // combined through shared memory with a 64-thread named barrier per quarter.
     const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int r_in_tile = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t s_ph = 0, o_ph = 0;
     const int n_chunks = (p.s + 31) / 32;  // 32-column chunks holding in-range keys (9 for 257)
+    const int split = (n_chunks + 1) / 2;
+    const int c_lo = half == 0 ? 0 : split;
+    const int c_hi = half == 0 ? split : n_chunks;
+    const int my_chunks = c_hi - c_lo;     // <= 5
+    float* xch = reinterpret_cast<float*>(bars + 16);  // [2 halves][128 rows] exchange buffer
+    const uint32_t bar_id = 1 + quarter;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int b = item / p.heads, h = item % p.heads;
       for (int t = 0; t < m_tiles; ++t) {
@@ -253,61 +264,107 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tc_fence_after();
         float inv_sum = 0.0f;
         if (warp_has_rows) {
-          // pass 1: row maximum
-          float mx = -INFINITY;
-          for (int ch = 0; ch < n_chunks; ++ch) {
+          // ---- pass 1: partial row maximum over this warp's columns
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          for (int ch = c_lo; ch < c_hi; ++ch) {
             uint32_t r[32];
             tmem_ld_32(t_lane + ch * 32, r);
             tmem_ld_wait();
+            if (ch * 32 + 32 <= p.s) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ch * 32 + j < p.s) mx = fmaxf(mx, __uint_as_float(r[j]));
+              for (int j = 0; j < 32; j += 4) {
+                m0 = fmaxf(m0, __uint_as_float(r[j]));
+                m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+                m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+                m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ch * 32 + j < p.s) m0 = fmaxf(m0, __uint_as_float(r[j]));
+            }
           }
+          float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          xch[half * 128 + r_in_tile] = mx;
+          asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+          mx = fmaxf(mx, xch[(half ^ 1) * 128 + r_in_tile]);
           const float mxs = mx * p.scale_log2;
-          // pass 2: p = 2^(s*c - max*c), bf16 pairs written in place (P column = S column / 2)
-          float sum = 0.0f;
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            uint32_t r[32];
-            tmem_ld_32(t_lane + ch * 32, r);
-            tmem_ld_wait();
-            uint32_t pk[16];
+          // ---- pass 2: p = 2^(s*c - max*c) packed to bf16 pairs (P column = S column / 2)
+          uint32_t pk[5][16];
+          float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int k0 = ch * 32 + 2 * j;
-              const float p0 = k0 < p.s ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs)) : 0.0f;
-              const float p1 = k0 + 1 < p.s ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs)) : 0.0f;
-              sum += p0 + p1;
-              pk[j] = pack_bf16x2(p0, p1);
-            }
-            if (ch * 32 + 32 <= kTaKRows) {
-              tmem_st_16(t_lane + ch * 16, pk);
-            } else {  // last chunk of S = 257: only 16 key columns (256..271) exist
-              uint32_t pk8[8];
+          for (int ci = 0; ci < 5; ++ci) {
+            if (ci < my_chunks) {
+              const int ch = c_lo + ci;
+              uint32_t r[32];
+              tmem_ld_32(t_lane + ch * 32, r);
+              tmem_ld_wait();
+              if (ch * 32 + 32 <= p.s) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
-              tmem_st_8(t_lane + ch * 16, pk8);
+                for (int j = 0; j < 16; j += 2) {
+                  const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs));
+                  const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs));
+                  const float p2 = exp2f(fmaf(__uint_as_float(r[2 * j + 2]), p.scale_log2, -mxs));
+                  const float p3 = exp2f(fmaf(__uint_as_float(r[2 * j + 3]), p.scale_log2, -mxs));
+                  s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                  pk[ci][j] = pack_bf16x2(p0, p1);
+                  pk[ci][j + 1] = pack_bf16x2(p2, p3);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int k0 = ch * 32 + 2 * j;
+                  const float p0 = k0 < p.s ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs)) : 0.0f;
+                  const float p1 = k0 + 1 < p.s ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs)) : 0.0f;
+                  s0 += p0; s1 += p1;
+                  pk[ci][j] = pack_bf16x2(p0, p1);
+                }
+              }
             }
           }
+          float sum = (s0 + s1) + (s2 + s3);
+          asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");  // max exchange slot free
+          xch[half * 128 + r_in_tile] = sum;
+          // both warps of the quarter have now consumed all of S: P may overwrite it in place
+          asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+          sum += xch[(half ^ 1) * 128 + r_in_tile];
           inv_sum = 1.0f / sum;
+#pragma unroll
+          for (int ci = 0; ci < 5; ++ci) {
+            if (ci < my_chunks) {
+              const int ch = c_lo + ci;
+              if (ch * 32 + 32 <= kTaKRows) {
+                tmem_st_16(t_lane + ch * 16, pk[ci]);
+              } else {  // last chunk of S = 257: only 16 key columns (256..271) exist
+                uint32_t pk8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk8[j] = pk[ci][j];
+                tmem_st_8(t_lane + ch * 16, pk8);
+              }
+            }
+          }
           tmem_st_wait();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready);
-        // ---- epilogue: O * 1/sum -> global
+        // ---- epilogue: O * 1/sum -> global (each half stores its share of the d columns)
         mbar_wait(o_full, o_ph);
         o_ph ^= 1u;
         tc_fence_after();
         if (warp_has_rows) {
           __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.s + qi) * p.o_rs + h * p.d;
-          for (int ch = 0; ch * 32 < p.d; ++ch) {
-            uint32_t r[32];
-            tmem_ld_32(t_lane + kTaColO + ch * 32, r);
+          const int n16 = (p.d + 15) / 16;             // 16-column groups of O (6 for d = 88)
+          const int g_lo = half == 0 ? 0 : (n16 + 1) / 2;
+          const int g_hi = half == 0 ? (n16 + 1) / 2 : n16;
+          for (int gi = g_lo; gi < g_hi; ++gi) {
+            uint32_t r[16];
+            tmem_ld_16(t_lane + kTaColO + gi * 16, r);
             tmem_ld_wait();
             if (qi < p.s) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const int c0 = ch * 32 + j;
+              for (int j = 0; j < 16; j += 8) {
+                const int c0 = gi * 16 + j;
                 if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
                   uint4 u;
                   u.x = pack_bf16x2(__uint_as_float(r[j]) * inv_sum, __uint_as_float(r[j + 1]) * inv_sum);
