@@ -297,6 +297,8 @@ def gpu_arm(args) -> None:
         loss = trainer.micro_step(batch)
         return float(loss)  # device -> host read of the step's result
 
+    if not args.no_graph:
+        trainer.capture_graph(resident)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     if args.profile:  # ncu --profile-from-start off: exactly one micro-step is captured
@@ -312,11 +314,14 @@ def gpu_arm(args) -> None:
     calls0 = _lib.launch_count()
     ms = timed_region(step_resident, args.steps)
     launches = _lib.launch_count() - calls0
+    if getattr(trainer, "_graph", None) is not None:  # replayed launches are not re-counted
+        launches += trainer.launches_per_graph * args.steps
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
     ms_e2e = timed_region(step_e2e, args.steps)
 
-    # roofline of the dominant kernel: one instrumented step
+    # roofline of the dominant kernel: one instrumented (eager, un-graphed) step
+    trainer._graph = None
     with GemmProfiler() as prof:
         trainer.micro_step(resident)
     g_flops, g_ms, g_n = prof.summary()
@@ -341,7 +346,7 @@ def gpu_arm(args) -> None:
                        "global_batch": world, "seq_len": int(host["input_ids"].shape[1]),
                        "parallelism": f"dp{world}", "weights": "random-init (seeded N(0,0.02))",
                        "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
-                       "dropout": "off"},
+                       "dropout": "off", "cuda_graph": not args.no_graph},
             "clocks": clocks,
             "e2e": {"value": e2e_clips, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -370,6 +375,7 @@ def main() -> None:
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="run one profiler-bracketed step and exit")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

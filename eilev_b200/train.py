@@ -90,15 +90,53 @@ class DataParallelTrainer:
         self._scale = torch.ones((), dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ steps
-    def micro_step(self, batch: dict) -> torch.Tensor:
-        """One datapoint: forward + backward, gradients accumulate locally (DDP no_sync)."""
+    def _fwd_bwd(self, batch: dict) -> torch.Tensor:
         out = self.model(**batch)
         loss = out.loss if hasattr(out, "loss") else out[0]
         (loss / self.grad_accum).backward()
+        return loss.detach()
+
+    def capture_graph(self, example_batch: dict) -> None:
+        """Capture one micro-step (forward + backward, ~1 400 kernel launches) into a CUDA graph
+        so a step costs one graph launch instead of ~1 400 Python/ctypes launches.  Batches fed
+        to micro_step() afterwards must have the shapes of `example_batch` (the recipe's
+        fixed-shape datapoints do; any other shape falls back to eager launches).  Call at an
+        accumulation boundary: the warm-up steps' gradients are discarded."""
+        assert self.micro % self.grad_accum == 0, "capture at an accumulation boundary"
+        self._static = {k: v.clone() for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up: packs the frozen towers, sets kernel attributes
+                self._fwd_bwd(self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        self.flat.zero_grad()
+        self.model._pack.clear()  # the Q-Former re-pack must be part of the captured step
+        from . import _lib
+        before = _lib.launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._fwd_bwd(self._static)
+        self.launches_per_graph = _lib.launch_count() - before
+        self.flat.zero_grad()  # capture itself does not execute, but keep the contract explicit
+
+    def micro_step(self, batch: dict) -> torch.Tensor:
+        """One datapoint: forward + backward, gradients accumulate locally (DDP no_sync)."""
+        graph = getattr(self, "_graph", None)
+        if graph is not None and all(
+                k in self._static and v.shape == self._static[k].shape and v.dtype == self._static[k].dtype
+                for k, v in batch.items()) and len(batch) == len(self._static):
+            for k, v in batch.items():
+                if v.data_ptr() != self._static[k].data_ptr():
+                    self._static[k].copy_(v, non_blocking=True)
+            graph.replay()
+            loss = self._static_loss
+        else:
+            loss = self._fwd_bwd(batch)
         self.micro += 1
         if self.micro % self.grad_accum == 0:
             self.optimizer_step()
-        return loss.detach()
+        return loss
 
     def grad_norm_and_scale(self) -> None:
         """scale = clip / world: gradients were summed over ranks (already divided by accum in
