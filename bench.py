@@ -74,6 +74,18 @@ def synthetic_batch(seed: int, clips: int = CLIPS, frames: int = FRAMES, pad_to:
     )
 
 
+def workload_config(world: int, seq_len: int, cuda_graph):
+    cfg = {"workload": "eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 per GPU "
+                       "(17 clips, L=976), grad-accum 16 with all-reduce + AdamW every 16th step",
+           "global_batch": world, "seq_len": seq_len, "parallelism": f"dp{world}",
+           "weights": "random-init (seeded N(0,0.02))",
+           "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
+           "dropout": "off"}
+    if cuda_graph is not None:
+        cfg["cuda_graph"] = cuda_graph
+    return cfg
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -173,8 +185,7 @@ def reference_arm(args) -> None:
         "unit": "clips/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(0, min(args.warmup, 1)),
         "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 (CPU sample: "
-                               f"{clips} clip(s) per step)", "parallelism": "host threads"},
+        "config": workload_config(args.gpus, 976, None),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -246,6 +257,40 @@ class GemmProfiler:
                 ms += s.elapsed_time(e)
                 n += 1
         return flops, ms, n
+
+
+def measure_decode(model, device, batch: int = 1):
+    """BASELINE configs[4]: greedy generate() after the 16-context prompt (17 clips, L = 958).
+    tok/s of the decode loop from the slope between 16 and 80 new tokens (vision tower, prefill
+    and graph capture cancel); bytes per token = 5.293 GB of bf16 weights + the KV pages read."""
+    import time
+
+    was_training = model.training
+    model.eval()
+    one = synthetic_batch(7)
+    n = int(one["attention_mask"].sum()) - TARGET_TOKENS
+    ids = one["input_ids"][:, :n].repeat(batch, 1).to(device)
+    vm = one["video_input_mask"][:, :n].repeat(batch, 1).to(device)
+    px = one["pixel_values"].to(device)
+    if batch > 1:
+        px = px.repeat(batch, 1, 1, 1, 1)
+
+    def run(new):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.generate(ids, pixel_values=px, video_input_mask=vm, attention_mask=torch.ones_like(ids),
+                       max_new_tokens=new, min_new_tokens=new, do_sample=False, eos_token_id=None)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    run(12)
+    t16, t80 = run(16), run(80)
+    per_tok = (t80 - t16) / 64
+    model.train(was_training)
+    return {"metric": "decode tok/s (greedy, 16-ctx prompt, batch %d)" % batch, "value": batch / per_tok,
+            "unit": "tok/s", "ms_per_token": per_tok * 1e3, "prompt_len": n, "batch": batch,
+            "bytes_per_token": 5.293e9 + 327680.0 * (n + 48) * batch,
+            "prefill_plus_fixed_ms": (t16 - 16 * per_tok) * 1e3}
 
 
 def gpu_arm(args) -> None:
@@ -326,6 +371,9 @@ def gpu_arm(args) -> None:
         trainer.micro_step(resident)
     g_flops, g_ms, g_n = prof.summary()
 
+    decode = None
+    if rank == 0 and not args.no_decode:
+        decode = measure_decode(model, device)
     if rank == 0:
         peaks = {}
         pfile = ROOT / "MEASURED_PEAKS.json"
@@ -341,12 +389,7 @@ def gpu_arm(args) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 per GPU "
-                                   "(17 clips, L=976), grad-accum 16 with all-reduce + AdamW every 16th step",
-                       "global_batch": world, "seq_len": int(host["input_ids"].shape[1]),
-                       "parallelism": f"dp{world}", "weights": "random-init (seeded N(0,0.02))",
-                       "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
-                       "dropout": "off", "cuda_graph": not args.no_graph},
+            "config": workload_config(world, int(host["input_ids"].shape[1]), not args.no_graph),
             "clocks": clocks,
             "e2e": {"value": e2e_clips, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -358,7 +401,13 @@ def gpu_arm(args) -> None:
                          if peaks else "fallback 1400"},
             "step_flops_frac": FLOPS_PER_DATAPOINT * args.steps / (ms * 1e-3) / (peak * 1e12) if peak else None,
         }
-        if not args.no_cpu_baseline:
+        if decode is not None:
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            decode["roofline"] = {"bound": "hbm", "achieved": decode["bytes_per_token"] / (decode["ms_per_token"] * 1e-3) / 1e9,
+                                  "peak": hbm, "unit": "GB/s",
+                                  "frac": decode["bytes_per_token"] / (decode["ms_per_token"] * 1e-3) / 1e9 / hbm}
+            line["decode"] = decode
+        if not args.no_cpu_baseline and world == 1:
             res = run_cpu_baseline(cfg, clips=args.cpu_clips, steps=1, warmup=0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -376,6 +425,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="run one profiler-bracketed step and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA graph")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode tok/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -76,8 +76,8 @@ SIGNATURES: dict[str, list] = {
     "vb_add": [vp, vp, vp, i64, vp],
     "vb_adamw": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, vp],
     "vb_sumsq": [vp, i64, vp, vp],
-    "vb_gemv": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, f32, i64, i32, i32, vp],
-    "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp],
+    "vb_gemv": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, f32, i64, i32, i32, vp, vp, f32, vp],
+    "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, vp],
     "vb_paged_kv_write": [vp, vp, i64, vp, vp, vp, i64, i64, i64, i64, i64, vp],
 }
 

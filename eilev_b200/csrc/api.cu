@@ -190,20 +190,23 @@ int vb_sumsq(const float* x, int64_t n, float* out, void* stream) {
 
 int vb_gemv(const void* x, const void* w, const float* bias, const void* residual, void* y,
             int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,
-            float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype, void* stream) {
+            float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype,
+            const float* ln_gamma, const float* ln_beta, float ln_eps, void* stream) {
+  if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return fail_msg("vb_gemv", "ln_gamma/ln_beta must come together");
   VB_CHECK("vb_gemv", vb::gemv_launch(x, w, bias, residual, y, m, n, k, ldx, ldw, ldy, ldr, alpha,
-                                      alpha_cols, epilogue, out_dtype, st(stream)));
+                                      alpha_cols, epilogue, out_dtype, ln_gamma, ln_beta, ln_eps, st(stream)));
 }
 
 int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
                               const int32_t* page_table, const int32_t* ctx_len,
-                              const int32_t* first_valid, void* out, int64_t batch, int64_t heads,
+                              const int32_t* first_valid, void* out, float* workspace,
+                              int32_t* counters, int64_t splits, int64_t batch, int64_t heads,
                               int64_t d, int64_t page_size, int64_t max_pages, float scale,
                               void* stream) {
   VB_CHECK("vb_paged_decode_attention",
            vb::paged_decode_attention_launch(qkv, k_cache, v_cache, page_table, ctx_len,
-                                             first_valid, out, batch, heads, d, page_size,
-                                             max_pages, scale, st(stream)));
+                                             first_valid, out, workspace, counters, splits, batch,
+                                             heads, d, page_size, max_pages, scale, st(stream)));
 }
 
 int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,

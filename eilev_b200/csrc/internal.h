@@ -58,10 +58,12 @@ cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s
 cudaError_t gemv_launch(const void* x, const void* w, const float* bias, const void* residual,
                         void* y, long long m, long long n, long long k, long long ldx,
                         long long ldw, long long ldy, long long ldr, float alpha,
-                        long long alpha_cols, int epilogue, int out_dtype, cudaStream_t s);
+                        long long alpha_cols, int epilogue, int out_dtype, const float* ln_gamma,
+                        const float* ln_beta, float ln_eps, cudaStream_t s);
 cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* v_cache,
                                           const int* page_table, const int* ctx_len,
-                                          const int* first_valid, void* out, long long batch,
+                                          const int* first_valid, void* out, float* workspace,
+                                          int* counters, long long splits, long long batch,
                                           long long heads, long long d, long long page_size,
                                           long long max_pages, float scale, cudaStream_t s);
 cudaError_t paged_kv_write_launch(const void* k, const void* v, long long ld, void* k_cache,

@@ -191,6 +191,70 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_kernel(const LnBwdPar
   }
 }
 
+// Vectorised variant: the row (g = dy*gamma and xhat) is held in registers between the two
+// reductions and the store, 16-byte loads/stores (cols % 8 == 0, cols <= VPL*256).
+template <int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nvec = static_cast<int>(p.cols / 8);
+  const __nv_bfloat16* dyr = p.dy + row * p.cols;
+  const __nv_bfloat16* xr = p.xin + row * p.cols;
+  const float mean = p.mean[row], rstd = p.rstd[row];
+  float g[VPL][8], xh[VPL][8];
+  float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 ud = *reinterpret_cast<const uint4*>(dyr + vi * 8);
+      const uint4 ux = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const uint32_t dw[4] = {ud.x, ud.y, ud.z, ud.w};
+      const uint32_t xw[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 d2 = unpack_bf16x2(dw[j]);
+        const float2 x2 = unpack_bf16x2(xw[j]);
+        g[i][2 * j] = d2.x * gm[2 * j];
+        g[i][2 * j + 1] = d2.y * gm[2 * j + 1];
+        xh[i][2 * j] = (x2.x - mean) * rstd;
+        xh[i][2 * j + 1] = (x2.y - mean) * rstd;
+        s1 += g[i][2 * j] + g[i][2 * j + 1];
+        s2 += g[i][2 * j] * xh[i][2 * j] + g[i][2 * j + 1] * xh[i][2 * j + 1];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / static_cast<float>(p.cols);
+  s2 = warp_sum(s2) / static_cast<float>(p.cols);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+      if (p.dx_add != nullptr) {
+        const uint4 ua = *reinterpret_cast<const uint4*>(p.dx_add + row * p.cols + vi * 8);
+        const uint32_t aw[4] = {ua.x, ua.y, ua.z, ua.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a2 = unpack_bf16x2(aw[j]);
+          d[2 * j] += a2.x;
+          d[2 * j + 1] += a2.y;
+        }
+      }
+      uint4 u;
+      u.x = pack_bf16x2(d[0], d[1]); u.y = pack_bf16x2(d[2], d[3]);
+      u.z = pack_bf16x2(d[4], d[5]); u.w = pack_bf16x2(d[6], d[7]);
+      *reinterpret_cast<uint4*>(p.dx + row * p.cols + vi * 8) = u;
+    }
+  }
+}
+
 // dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy.  Block = 32 columns x 8 row lanes;
 // every column is owned by exactly one block, so the accumulation is deterministic.
 __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const LnBwdParams p) {
@@ -221,7 +285,16 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const LnBwdParams p) 
 cudaError_t layernorm_bwd_launch(const LnBwdParams& p, cudaStream_t s) {
   if (p.rows <= 0 || p.cols <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
-  ln_bwd_dx_kernel<<<grid, kLnWarps * 32, 0, s>>>(p);
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool vec = p.cols % 8 == 0 && p.cols <= 12 * 256 && al(p.dy) && al(p.xin) && al(p.dx) &&
+                   al(p.gamma) && (p.dx_add == nullptr || al(p.dx_add));
+  const int vpl = static_cast<int>((p.cols / 8 + 31) / 32);
+  if (!vec) ln_bwd_dx_kernel<<<grid, kLnWarps * 32, 0, s>>>(p);
+  else if (vpl <= 1) ln_bwd_dx_vec_kernel<1><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else if (vpl <= 3) ln_bwd_dx_vec_kernel<3><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else if (vpl <= 6) ln_bwd_dx_vec_kernel<6><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else if (vpl <= 10) ln_bwd_dx_vec_kernel<10><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else ln_bwd_dx_vec_kernel<12><<<grid, kLnWarps * 32, 0, s>>>(p);
   if (p.dgamma != nullptr && p.dbeta != nullptr) {
     ln_bwd_param_kernel<<<static_cast<unsigned>((p.cols + 31) / 32), 256, 0, s>>>(p);
   }

@@ -219,14 +219,20 @@ def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
         ops.gemm(last, w["embed"], out_dtype=torch.float32)
     am = attention_mask if attention_mask is not None else torch.ones_like(input_ids)
     first_valid = (am != 0).to(torch.int32).argmax(dim=1).to(torch.int32).contiguous()
-    n_valid = am.sum(dim=1).to(torch.int32)
+    n_valid = am.sum(dim=1).to(torch.int32).contiguous()
     state = dict(kv=kv, ctx_len=torch.full((b,), l, dtype=torch.int32, device=input_ids.device),
                  first_valid=first_valid, n_valid=n_valid, status=out["status"])
+    splits = 8 if l + max_new_tokens > 256 else 2
+    state["attn_splits"] = splits
+    state["attn_ws"] = torch.empty(b * heads * splits * (hd + 2), dtype=torch.float32, device=input_ids.device)
+    state["attn_cnt"] = torch.zeros(b * heads, dtype=torch.int32, device=input_ids.device)
     return logits, state
 
 
 def opt_decode_step(lm, cache: PackCache, tokens: torch.Tensor, state: dict) -> torch.Tensor:
-    """One token per sequence: tokens (B,) int64 -> next-position logits f32 (B, V)."""
+    """One token per sequence: tokens (B,) int64 -> next-position logits f32 (B, V).
+    Stream-ordered and allocation-stable, so it can be captured into a CUDA graph
+    (``DecodeGraph``): the per-sequence counters are advanced in place."""
     cfg = lm.config
     w = pack_opt(lm, cache, need_backward=False)
     dim, heads, hd = _dims(cfg)
@@ -238,17 +244,43 @@ def opt_decode_step(lm, cache: PackCache, tokens: torch.Tensor, state: dict) -> 
         raise NotImplementedError("decode batch (incl. beams) > 16 is not supported yet")
     # position of the new token = number of valid tokens so far - 1 + offset 2 (HF :350-354)
     pos = (state["n_valid"].to(torch.long) + 2)
-    state["n_valid"] = state["n_valid"] + 1
-    state["ctx_len"] = state["ctx_len"] + 1
+    state["n_valid"].add_(1)
+    state["ctx_len"].add_(1)
     x = ops.add(w["embed"][tokens].contiguous(), w["pos"][pos].contiguous())
     for li, lw in enumerate(w["layers"]):
-        y = ops.layernorm(x, lw["ln1_g"], lw["ln1_b"], 1e-5)
-        qkv = ops.gemv(y, lw["qkv_w"], lw["qkv_b"], alpha=scaling, alpha_cols=dim)
+        qkv = ops.gemv(x, lw["qkv_w"], lw["qkv_b"], alpha=scaling, alpha_cols=dim,
+                       ln=(lw["ln1_g"], lw["ln1_b"], 1e-5))
         o = ops.paged_decode_attention(qkv, kv.k[li], kv.v[li], kv.table, state["ctx_len"],
-                                       state["first_valid"], heads, kv.page_size, 1.0)
+                                       state["first_valid"], heads, kv.page_size, 1.0,
+                                       workspace=state["attn_ws"], counters=state["attn_cnt"],
+                                       splits=state["attn_splits"])
         x = ops.gemv(o, lw["out_w"], lw["out_b"], residual=x)
-        y = ops.layernorm(x, lw["ln2_g"], lw["ln2_b"], 1e-5)
-        f1 = ops.gemv(y, lw["fc1_w"], lw["fc1_b"], epilogue=act)
+        f1 = ops.gemv(x, lw["fc1_w"], lw["fc1_b"], epilogue=act, ln=(lw["ln2_g"], lw["ln2_b"], 1e-5))
         x = ops.gemv(f1, lw["fc2_w"], lw["fc2_b"], residual=x)
-    final = ops.layernorm(x, w["lnf_g"], w["lnf_b"], 1e-5)
-    return ops.gemv(final, w["embed"], out_dtype=torch.float32)
+    return ops.gemv(x, w["embed"], out_dtype=torch.float32, ln=(w["lnf_g"], w["lnf_b"], 1e-5))
+
+
+class DecodeGraph:
+    """CUDA graph of one decode step (~230 launches -> one graph launch): static token
+    buffer in, static logits buffer out; the KV cache and the counters live in `state`."""
+
+    def __init__(self, lm, cache: PackCache, state: dict, batch: int, device) -> None:
+        self.tokens = torch.zeros(batch, dtype=torch.long, device=device)
+        snap = {k: state[k].clone() for k in ("n_valid", "ctx_len")}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            opt_decode_step(lm, cache, self.tokens, state)  # warm-up (allocator, attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        for k, v in snap.items():
+            state[k].copy_(v)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = opt_decode_step(lm, cache, self.tokens, state)
+        for k, v in snap.items():  # capture does not execute; restore defensively anyway
+            state[k].copy_(v)
+
+    def step(self, tokens: torch.Tensor) -> torch.Tensor:
+        self.tokens.copy_(tokens)
+        self.graph.replay()
+        return self.logits

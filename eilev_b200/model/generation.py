@@ -132,6 +132,8 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
                             length_penalty, early_stopping, do_sample, temperature, top_k, top_p)
 
     rows = input_ids.shape[0]
+    use_graph = bool(kw.get("use_cuda_graph", max_new >= 8)) and rows <= 16
+    dgraph = E_opt.DecodeGraph(lm, lm._pack, state, rows, dev) if use_graph and max_new > 1 else None
     generated = torch.empty((rows, 0), dtype=torch.long, device=dev)
     unfinished = torch.ones(rows, dtype=torch.bool, device=dev)
     eos_t = torch.tensor(eos_ids, device=dev, dtype=torch.long) if eos_ids else None
@@ -150,7 +152,7 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
             if not bool(unfinished.any()):
                 break
         if step + 1 < max_new:
-            logits = E_opt.opt_decode_step(lm, lm._pack, nxt, state)
+            logits = dgraph.step(nxt) if dgraph is not None else E_opt.opt_decode_step(lm, lm._pack, nxt, state)
     return generated
 
 

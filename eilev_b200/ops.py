@@ -347,17 +347,22 @@ def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def gemv(x: torch.Tensor, w: torch.Tensor, bias=None, *, residual=None, epilogue: int = EPI_NONE,
-         alpha: float = 1.0, alpha_cols: int = 0, out_dtype=torch.bfloat16) -> torch.Tensor:
-    """Decode-time projection for M <= 16 rows (weight-streaming)."""
+         alpha: float = 1.0, alpha_cols: int = 0, out_dtype=torch.bfloat16, ln=None) -> torch.Tensor:
+    """Decode-time projection for M <= 16 rows (weight-streaming).  ln = (gamma, beta, eps)
+    fuses the LayerNorm of x into the kernel's staging pass."""
     _need(x, torch.bfloat16, "gemv.x")
     _need(w, torch.bfloat16, "gemv.w")
     m, k = x.shape
     n = w.shape[0]
+    if ln is not None and (k % 256 != 0 or max(1, 1 << (m - 1).bit_length()) * k * 2 > 160 * 1024):
+        x = layernorm(x, ln[0], ln[1], ln[2])  # shapes the staged kernel does not take
+        ln = None
     y = torch.empty((m, n), dtype=out_dtype, device=x.device)
     check(_lib.lib().vb_gemv(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(),
                              m, n, k, x.stride(0), w.stride(0), n,
                              residual.stride(0) if residual is not None else 0, alpha, alpha_cols,
-                             epilogue, _DT[out_dtype], _stream()), "vb_gemv")
+                             epilogue, _DT[out_dtype], _ptr(ln[0]) if ln else None,
+                             _ptr(ln[1]) if ln else None, float(ln[2]) if ln else 0.0, _stream()), "vb_gemv")
     return y
 
 
@@ -372,14 +377,21 @@ def paged_kv_write(k, v, k_cache, v_cache, page_table, page_size: int) -> None:
 
 
 def paged_decode_attention(qkv, k_cache, v_cache, page_table, ctx_len, first_valid, heads: int,
-                           page_size: int, scale: float) -> torch.Tensor:
+                           page_size: int, scale: float, *, workspace=None, counters=None,
+                           splits: int = 8) -> torch.Tensor:
     b = qkv.shape[0]
     hd = qkv.shape[1] // 3
+    d = hd // heads
     out = torch.empty((b, hd), dtype=torch.bfloat16, device=qkv.device)
+    if workspace is None:
+        workspace = torch.empty(b * heads * splits * (d + 2), dtype=torch.float32, device=qkv.device)
+    if counters is None:
+        counters = torch.zeros(b * heads, dtype=torch.int32, device=qkv.device)
     check(_lib.lib().vb_paged_decode_attention(qkv.data_ptr(), k_cache.data_ptr(),
                                                v_cache.data_ptr(), page_table.data_ptr(),
                                                ctx_len.data_ptr(), _ptr(first_valid),
-                                               out.data_ptr(), b, heads, hd // heads, page_size,
+                                               out.data_ptr(), workspace.data_ptr(),
+                                               counters.data_ptr(), splits, b, heads, d, page_size,
                                                page_table.shape[1], scale, _stream()),
           "vb_paged_decode_attention")
     return out

@@ -225,22 +225,30 @@ int vb_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
 int vb_sumsq(const float* x, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------ decode */
-/* y[m, n] = act(x[m,:] . W[n,:] + bias[n]) (+ residual) for small m (<= 16):
+/* y[m, n] = act(alpha_n * (LN?(x)[m,:] . W[n,:] + bias[n])) (+ residual) for small m (<= 16):
  * weight-streaming kernel for token-by-token generation (HBM bound).  bf16 in/out,
- * out_dtype selects bf16|f32.  HF:opt/modeling_opt.py:135-253 at tgt_len == 1. */
+ * out_dtype selects bf16|f32.  When ln_gamma/ln_beta (f32, k) are given, x is
+ * LayerNorm-ed (eps ln_eps, rounded to bf16 like vb_layernorm) while it is staged in
+ * shared memory — the pre-LN of an OPT block costs no launch.
+ * HF:opt/modeling_opt.py:135-253 at tgt_len == 1. */
 int vb_gemv(const void* x, const void* w, const float* bias, const void* residual, void* y,
             int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,
-            float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype, void* stream);
+            float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype,
+            const float* ln_gamma, const float* ln_beta, float ln_eps, void* stream);
 
 /* Append new K/V rows into a paged cache and run one-query-per-sequence attention over
  * it.  Cache pages: (n_pages, page_size, H*D) bf16 for K and for V; page_table (B,
  * max_pages) int32; ctx_len (B) int32 = number of cached tokens INCLUDING the new one;
  * first_valid (B) int32 = index of the first non-padding token (left padding).
  * qkv: (B, 3*H*D) bf16 (q pre-scaled).  out: (B, H*D) bf16.
+ * The context is processed in `splits` independent CTAs per (sequence, head)
+ * (flash-decoding); workspace: f32 (B*H*splits*(D+2)); counters: int32 (B*H), zero on
+ * entry and left zero on exit.
  * HF:opt/modeling_opt.py:159-161 (DynamicCache.update) + :163-176. */
 int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
                               const int32_t* page_table, const int32_t* ctx_len,
-                              const int32_t* first_valid, void* out, int64_t batch, int64_t heads,
+                              const int32_t* first_valid, void* out, float* workspace,
+                              int32_t* counters, int64_t splits, int64_t batch, int64_t heads,
                               int64_t d, int64_t page_size, int64_t max_pages, float scale,
                               void* stream);
 /* Copy prefill K/V (B, L, ld) rows into the paged cache. */

@@ -311,6 +311,13 @@ def test_gemv_and_paged_decode():
         ref = x.float() @ w.float().t() + bias
         ref[:, :2560] *= 0.25
         _close(y, ref, atol=0.05, rtol=0.02, what="gemv")
+        g, bt = torch.randn(2560, device="cuda"), torch.randn(2560, device="cuda")
+        res = _rand(m, 7680, seed=64)
+        y2 = ops.gemv(x, w, bias, residual=res, epilogue=ops.EPI_RELU, ln=(g, bt, 1e-5))
+        xn = torch.nn.functional.layer_norm(x.float(), (2560,), g, bt, 1e-5).to(torch.bfloat16).float()
+        _close(y2, torch.relu(xn @ w.float().t() + bias) + res.float(), atol=0.08, rtol=0.02, what="ln+gemv")
+    xo, wo = _rand(2, 200, seed=65), _rand(33, 200, seed=66)  # odd shapes: legacy kernel
+    _close(ops.gemv(xo, wo), xo.float() @ wo.float().t(), atol=0.05, rtol=0.02, what="gemv odd")
     heads, d, page, b, l = 4, 80, 16, 2, 37
     hd = heads * d
     max_pages = 4
