@@ -230,14 +230,15 @@ VB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067
 // orders below bf16 rounding), one MUFU.RCP + one MUFU.EX2 + 8 FMAs instead of erff's two
 // divergent branches.  The negative side is formed without cancellation.
 VB_DEVICE float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float y = fmaf(t, 1.061405429f, -1.453152027f);
-  y = fmaf(t, y, 1.421413741f);
-  y = fmaf(t, y, -0.284496736f);
-  y = fmaf(t, y, 0.254829592f);
-  const float half_erfc = 0.5f * t * y * exp2f(-1.4426950408889634f * z * z);
-  return x * (x >= 0.0f ? 1.0f - half_erfc : half_erfc);
+  // t = 1 / (1 + p |x| / sqrt2); the 0.5 of Phi is folded into the polynomial coefficients
+  const float t = __fdividef(1.0f, fmaf(0.2316418882f, fabsf(x), 1.0f));
+  float y = fmaf(t, 0.5307027145f, -0.7265760135f);
+  y = fmaf(t, y, 0.7107068705f);
+  y = fmaf(t, y, -0.142248368f);
+  y = fmaf(t, y, 0.127414796f);
+  const float e = exp2f(-0.7213475204f * x * x);  // exp(-x^2 / 2)
+  const float xh = x * (t * y * e);               // x * 0.5 erfc(|x| / sqrt2)
+  return x >= 0.0f ? x - xh : xh;
 }
 VB_DEVICE float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
