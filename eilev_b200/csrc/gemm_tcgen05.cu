@@ -294,7 +294,7 @@ cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t
 static int pick_2cta_block_n(long long m, long long n) {
   if (m < 512) return 0;
   const long long tiles = ((m + 255) / 256) * ((n + 255) / 256);
-  return tiles >= 3 * 74 ? 256 : 0;
+  return tiles >= 100 ? 256 : 0;  // >= ~1.4 waves of the 74 CTA pairs (OPT qkv / fc1 at M = 976)
 }
 
 // vb_gemm_args.reserved: 0 = automatic; 64/128/176/256 = force the 1-CTA kernel with that

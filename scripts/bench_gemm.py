@@ -41,13 +41,14 @@ def timeit(fn, iters=5):
 
 def sweep():
     """--sweep: every tile variant (1-CTA 64..256, CTA-pair 1000+BN) on the big ViT shapes."""
-    for name, m, n, k, epi in SHAPES[:5]:
+    which = SHAPES[5:9] if "--opt" in sys.argv else SHAPES[:5]
+    for name, m, n, k, epi in which:
         a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
         w = (torch.randn(n, k, device="cuda") * 0.05).to(torch.bfloat16)
         bias = torch.randn(n, device="cuda")
         out = torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
         res = {}
-        for bn in (128, 176, 256, 1128, 1176, 1256):
+        for bn in (64, 128, 176, 256, 1128, 1256):
             best, _ = timeit(lambda: ops.gemm(a, w, bias, out=out, epilogue=epi, block_n=bn), iters=3)
             res[bn] = round(2.0 * m * n * k / best / 1e9)
         print(name, res, flush=True)
