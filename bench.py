@@ -37,7 +37,9 @@ GRAD_ACCUM = 16
 FLOPS_PER_DATAPOINT = 83.88e12
 
 
-def full_config():
+def full_config(dropout: float = 0.0):
+    """eilev-blip2-opt-2.7b architecture.  dropout = 0.1 is the checkpoint's / recipe's value
+    (Q-Former hidden + attention-probs dropout, OPT hidden dropout; OPT attention_dropout 0)."""
     from transformers import Blip2Config
 
     return Blip2Config(
@@ -46,10 +48,10 @@ def full_config():
                            layer_norm_eps=1e-6, qkv_bias=True),
         qformer_config=dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                             intermediate_size=3072, encoder_hidden_size=1408, cross_attention_frequency=2,
-                            vocab_size=30522, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
+                            vocab_size=30522, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout),
         text_config=dict(model_type="opt", hidden_size=2560, num_hidden_layers=32, ffn_dim=10240,
                          num_attention_heads=32, vocab_size=50272, max_position_embeddings=2048,
-                         word_embed_proj_dim=2560, dropout=0.0, attention_dropout=0.0),
+                         word_embed_proj_dim=2560, dropout=dropout, attention_dropout=0.0),
         num_query_tokens=QUERY_TOKENS)
 
 
@@ -74,13 +76,14 @@ def synthetic_batch(seed: int, clips: int = CLIPS, frames: int = FRAMES, pad_to:
     )
 
 
-def workload_config(world: int, seq_len: int, cuda_graph):
+def workload_config(world: int, seq_len: int, cuda_graph, dropout: float = 0.1):
     cfg = {"workload": "eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 per GPU "
                        "(17 clips, L=976), grad-accum 16 with all-reduce + AdamW every 16th step",
            "global_batch": world, "seq_len": seq_len, "parallelism": f"dp{world}",
            "weights": "random-init (seeded N(0,0.02))",
            "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
-           "dropout": "off"}
+           "dropout": ("recipe: p=%.2f in train mode (Q-Former hidden + attention probs, OPT hidden)" % dropout)
+           if dropout > 0 else "off"}
     if cuda_graph is not None:
         cfg["cuda_graph"] = cuda_graph
     return cfg
@@ -185,7 +188,7 @@ def reference_arm(args) -> None:
         "unit": "clips/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(0, min(args.warmup, 1)),
         "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, 976, None),
+        "config": workload_config(args.gpus, 976, None, args.dropout),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -313,7 +316,7 @@ def gpu_arm(args) -> None:
         dist.init_process_group("nccl", device_id=device)
     _lib.lib()  # fail loudly if the extension is missing
 
-    cfg = full_config()
+    cfg = full_config(args.dropout)
     model = build_gpu_model(cfg, device)
     decode = None
     if rank == 0 and not args.no_decode and not args.profile:
@@ -394,7 +397,7 @@ def gpu_arm(args) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world, int(host["input_ids"].shape[1]), not args.no_graph),
+            "config": workload_config(world, int(host["input_ids"].shape[1]), not args.no_graph, args.dropout),
             "clocks": clocks,
             "e2e": {"value": e2e_clips, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -433,6 +436,8 @@ def main() -> None:
     ap.add_argument("--profile", action="store_true", help="run one profiler-bracketed step and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA graph")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tok/s measurement")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="dropout of the training step (0.1 = the reference recipe; 0 = parity configuration)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

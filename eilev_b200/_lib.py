@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("alpha", f32), ("beta", f32),
         ("alpha_cols", i64), ("row_group", i64),
         ("epilogue", i32), ("out_dtype", i32), ("backend", i32), ("reserved", i32),
+        ("dropout_p", f32), ("reserved2", i32), ("dropout_seed", vp), ("dropout_salt", C.c_uint64),
     ]
 
 
@@ -39,6 +40,7 @@ class AttnArgs(C.Structure):
         ("q_bs", i64), ("q_rs", i64), ("k_bs", i64), ("k_rs", i64),
         ("v_bs", i64), ("v_rs", i64), ("o_bs", i64), ("o_rs", i64),
         ("scale", f32), ("causal", i32),
+        ("dropout_p", f32), ("reserved", i32), ("dropout_seed", vp), ("dropout_salt", C.c_uint64),
     ]
 
 
@@ -73,6 +75,7 @@ SIGNATURES: dict[str, list] = {
     "vb_convert": [vp, i32, vp, i32, i64, vp],
     "vb_act_bwd": [vp, vp, vp, i32, i64, vp],
     "vb_colsum": [vp, vp, i64, i64, i64, i32, vp],
+    "vb_dropout": [vp, vp, i64, i64, i64, i64, f32, vp, C.c_uint64, vp],
     "vb_add": [vp, vp, vp, i64, vp],
     "vb_adamw": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, vp],
     "vb_sumsq": [vp, i64, vp, vp],

@@ -172,6 +172,12 @@ int vb_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx
   VB_CHECK("vb_colsum", vb::colsum_launch(x, out, rows, cols, ldx, accumulate, st(stream)));
 }
 
+int vb_dropout(const void* x, void* y, int64_t rows, int64_t cols, int64_t ldx, int64_t ldy, float p,
+               const uint64_t* seed, uint64_t salt, void* stream) {
+  VB_CHECK("vb_dropout", vb::dropout_launch(x, y, rows, cols, ldx, ldy, p,
+                                            reinterpret_cast<const unsigned long long*>(seed), salt, st(stream)));
+}
+
 int vb_add(const void* a, const void* b, void* y, int64_t n, void* stream) {
   VB_CHECK("vb_add", vb::add_launch(a, b, y, n, st(stream)));
 }

@@ -81,6 +81,10 @@ struct AttnParams {
   int causal;
   int vec;
   int o_vec2;
+  const unsigned long long* drop_seed;
+  unsigned long long drop_salt;
+  unsigned int drop_thresh;  // 0 = no dropout on the probabilities
+  float drop_scale;
 };
 
 template <int DP>
@@ -223,6 +227,20 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
         o_acc[nb][2 * r + 1] *= corr;
       }
     }
+    if (p.drop_thresh != 0u) {  // dropout on the probabilities; the normaliser stays undropped
+      const uint64_t seed = *p.drop_seed + p.drop_salt;
+      const uint64_t bh = static_cast<uint64_t>(b) * p.heads + h;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t key = n0 + nb * 8 + 2 * t + (j & 1);
+          const uint64_t qi = qi0 + (j >> 1) * 8;
+          const uint64_t idx = (bh * p.sq + qi) * p.skv + key;
+          s[nb][j] = dropout_keep(seed, idx, p.drop_thresh) ? s[nb][j] * p.drop_scale : 0.0f;
+        }
+      }
+    }
     // O += P . V
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 16-key steps
@@ -310,6 +328,13 @@ cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream) {
   p.v_bs = a.v_bs; p.v_rs = a.v_rs; p.o_bs = a.o_bs; p.o_rs = a.o_rs;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.causal = a.causal;
+  {
+    const bool drop = a.dropout_p > 0.0f && a.dropout_seed != nullptr;
+    p.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+    p.drop_salt = a.dropout_salt;
+    p.drop_thresh = drop ? dropout_threshold(a.dropout_p) : 0u;
+    p.drop_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+  }
   p.vec = attn_vec_ok(a) ? 1 : 0;
   // o is written with 4-byte stores when every (row, head) start is 4-byte aligned
   p.o_vec2 = (a.d % 2 == 0 && a.o_rs % 2 == 0 && a.o_bs % 2 == 0 &&
@@ -470,8 +495,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
         if (p.causal) ok = ok && (key <= qi + causal_off);
         if (km != nullptr && ok) ok = km[key] != 0;
         const float pr = ok ? exp2f(s[nb][j] * p.scale_log2 - lse2[r]) : 0.0f;
-        s[nb][j] = pr;
-        dp[nb][j] = pr * (dp[nb][j] - dl[r]);
+        float p_used = pr, dpv = dp[nb][j];
+        if (p.drop_thresh != 0u) {  // regenerate the forward mask
+          const uint64_t idx = ((static_cast<uint64_t>(b) * p.heads + h) * p.sq + qi) * p.skv + key;
+          const bool keep = dropout_keep(*p.drop_seed + p.drop_salt, idx, p.drop_thresh);
+          p_used = keep ? pr * p.drop_scale : 0.0f;
+          dpv = keep ? dpv * p.drop_scale : 0.0f;
+        }
+        s[nb][j] = p_used;                 // P actually multiplied with V in the forward -> dV
+        dp[nb][j] = pr * (dpv - dl[r]);    // dS
       }
     }
     // stash P and dS (bf16) for the transposed products
@@ -613,6 +645,13 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   p.v_bs = f.v_bs; p.v_rs = f.v_rs; p.o_bs = f.o_bs; p.o_rs = f.o_rs;
   p.scale_log2 = f.scale * 1.4426950408889634f;
   p.causal = f.causal;
+  {
+    const bool drop = f.dropout_p > 0.0f && f.dropout_seed != nullptr;
+    p.drop_seed = reinterpret_cast<const unsigned long long*>(f.dropout_seed);
+    p.drop_salt = f.dropout_salt;
+    p.drop_thresh = drop ? dropout_threshold(f.dropout_p) : 0u;
+    p.drop_scale = drop ? 1.0f / (1.0f - f.dropout_p) : 1.0f;
+  }
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   p.vec = (attn_vec_ok(f) && al(a.d_o) && f.o_rs % 8 == 0 && f.o_bs % 8 == 0) ? 1 : 0;
   p.o_vec2 = 0;

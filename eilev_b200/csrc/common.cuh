@@ -246,6 +246,23 @@ VB_DEVICE float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Counter-based dropout: keep(seed, idx) is a pure function, so the backward pass regenerates
+// the forward mask instead of storing it.  `thresh` = p * 2^32; an element is kept when the
+// 32-bit hash of (seed, idx) is >= thresh.
+VB_DEVICE bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
+  uint32_t h = static_cast<uint32_t>(idx) * 0x9E3779B1u ^ static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u ^
+               static_cast<uint32_t>(seed);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  h += static_cast<uint32_t>(seed >> 32);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  return h >= thresh;
+}
+__host__ __device__ inline uint32_t dropout_threshold(float p) {
+  if (!(p > 0.0f)) return 0u;
+  if (p >= 1.0f) return 0xFFFFFFFFu;
+  return static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+}
+
 VB_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -441,6 +441,33 @@ cudaError_t add_launch(const void* a, const void* b, void* y, long long n, cudaS
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256)
+dropout_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, long long rows, long long cols, long long ldx,
+               long long ldy, unsigned int thresh, float scale, const unsigned long long* seed_ptr,
+               unsigned long long salt) {
+  const uint64_t seed = *seed_ptr + salt;
+  const long long total = rows * cols;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / cols, c = i % cols;
+    const float v = __bfloat162float(x[r * ldx + c]);
+    y[r * ldy + c] = __float2bfloat16(dropout_keep(seed, static_cast<uint64_t>(i), thresh) ? v * scale : 0.0f);
+  }
+}
+
+cudaError_t dropout_launch(const void* x, void* y, long long rows, long long cols, long long ldx,
+                           long long ldy, float p, const unsigned long long* seed, unsigned long long salt,
+                           cudaStream_t s) {
+  const long long n = rows * cols;
+  if (n <= 0) return cudaSuccess;
+  if (seed == nullptr || !(p >= 0.0f) || p >= 1.0f) return cudaErrorInvalidValue;
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  dropout_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                      reinterpret_cast<__nv_bfloat16*>(y), rows, cols, ldx, ldy,
+                                      dropout_threshold(p), 1.0f / (1.0f - p), seed, salt);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ optimizer
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,

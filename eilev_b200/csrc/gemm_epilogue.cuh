@@ -15,6 +15,10 @@ struct EpiParams {
   float alpha, beta;
   long long alpha_cols;
   long long row_group;
+  const unsigned long long* drop_seed;
+  unsigned long long drop_salt;
+  unsigned int drop_thresh;  // 0 = no dropout
+  float drop_scale;
   int epilogue;
   int out_f32;
 };
@@ -56,6 +60,12 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
   } else if (p.epilogue == VB_EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.drop_thresh != 0u) {
+    const uint64_t seed = *p.drop_seed + p.drop_salt;
+    const uint64_t base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.n) + static_cast<uint64_t>(col0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = dropout_keep(seed, base + j, p.drop_thresh) ? v[j] * p.drop_scale : 0.0f;
   }
   if (p.residual != nullptr) {
     const __nv_bfloat16* r = p.residual + res_row * p.ldr + col0;

@@ -21,6 +21,10 @@ struct GenParams {
   float alpha, beta;
   long long alpha_cols, row_group;
   int epilogue, out_f32;
+  const unsigned long long* drop_seed;
+  unsigned long long drop_salt;
+  unsigned int drop_thresh;
+  float drop_scale;
 };
 
 __global__ void __launch_bounds__(256) gemm_generic_kernel(const GenParams p) {
@@ -83,6 +87,9 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(const GenParams p) {
       if (col < ac) v *= p.alpha;
       if (p.epilogue == VB_EPI_GELU) v = gelu_erf(v);
       else if (p.epilogue == VB_EPI_RELU) v = fmaxf(v, 0.0f);
+      if (p.drop_thresh != 0u)
+        v = dropout_keep(*p.drop_seed + p.drop_salt, static_cast<uint64_t>(row) * p.n + col, p.drop_thresh)
+                ? v * p.drop_scale : 0.0f;
       if (p.residual != nullptr) v += __bfloat162float(p.residual[res_row * p.ldr + col]);
       if (p.out_f32) {
         float* c = reinterpret_cast<float*>(p.c) + out_row * p.ldc + col;
@@ -108,6 +115,11 @@ cudaError_t gemm_generic_launch(const vb_gemm_args& a, cudaStream_t stream) {
   p.m = a.m; p.n = a.n; p.k = a.k; p.lda = a.lda; p.ldb = a.ldb; p.ldc = a.ldc; p.ldr = a.ldr;
   p.alpha = a.alpha; p.beta = a.beta; p.alpha_cols = a.alpha_cols; p.row_group = a.row_group;
   p.epilogue = a.epilogue; p.out_f32 = (a.out_dtype == VB_F32) ? 1 : 0;
+  const bool drop = a.dropout_p > 0.0f && a.dropout_seed != nullptr;
+  p.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+  p.drop_salt = a.dropout_salt;
+  p.drop_thresh = drop ? dropout_threshold(a.dropout_p) : 0u;
+  p.drop_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   dim3 grid(static_cast<unsigned>((a.m + GT - 1) / GT), static_cast<unsigned>((a.n + GT - 1) / GT));
   if (grid.y > 65535) return cudaErrorInvalidValue;
   gemm_generic_kernel<<<grid, 256, 0, stream>>>(p);

@@ -284,6 +284,11 @@ void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {
   ep.row_group = a.row_group;
   ep.epilogue = a.epilogue;
   ep.out_f32 = (a.out_dtype == VB_F32) ? 1 : 0;
+  const bool drop = a.dropout_p > 0.0f && a.dropout_seed != nullptr;
+  ep.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
+  ep.drop_salt = a.dropout_salt;
+  ep.drop_thresh = drop ? dropout_threshold(a.dropout_p) : 0u;
+  ep.drop_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
 }
 
 cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t stream);

@@ -49,6 +49,9 @@ cudaError_t act_bwd_launch(const void* dy, const void* saved, void* dx, int epi,
                            cudaStream_t s);
 cudaError_t colsum_launch(const void* x, float* out, long long rows, long long cols, long long ldx,
                           int accumulate, cudaStream_t s);
+cudaError_t dropout_launch(const void* x, void* y, long long rows, long long cols, long long ldx,
+                           long long ldy, float p, const unsigned long long* seed, unsigned long long salt,
+                           cudaStream_t s);
 cudaError_t add_launch(const void* a, const void* b, void* y, long long n, cudaStream_t s);
 cudaError_t adamw_launch(float* p, const float* g, float* m, float* v, long long n, float lr,
                          float b1, float b2, float eps, float wd, long long step,

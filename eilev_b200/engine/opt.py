@@ -13,7 +13,9 @@ loss (HF:loss/loss_utils.py:28-67) as sm_100a launches:
 The LM is frozen in the reference recipe (train_v2.py:126-127): its backward is dgrad
 only — gradients flow through activations to the spliced video positions, no wgrad.
 Decode (``generate``) runs token-by-token on weight-streaming GEMV kernels over a paged KV
-cache.  Dropout (p=0.1 in train mode in the reference) is not applied.
+cache.  Dropout (config.dropout after out_proj and fc2, config.attention_dropout on the
+probabilities; active in train mode as in the reference — the frozen LM is still in
+train mode under HF Trainer) uses counter-hash masks regenerated in the backward pass.
 """
 from __future__ import annotations
 
@@ -76,9 +78,16 @@ def _dims(cfg):
     return cfg.hidden_size, heads, cfg.hidden_size // heads
 
 
+_SALT_OPT = 1 << 17
+
+
+def _drop(p: float, seed, layer: int, site: int):
+    return (p, seed, _SALT_OPT + layer * 8 + site) if (seed is not None and p > 0.0) else None
+
+
 def opt_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features,
                 labels=None, save: bool = False, want_logits: bool = True,
-                output_hidden_states: bool = False, kv_sink=None):
+                output_hidden_states: bool = False, kv_sink=None, seed=None):
     """Full-sequence forward.  Returns dict(inputs_embeds, logits, loss, hidden_states, ctx)."""
     cfg = lm.config
     _check_cfg(cfg)
@@ -88,6 +97,10 @@ def opt_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
     scaling = hd ** -0.5
     b, l = input_ids.shape
     rows = b * l
+    p_h = float(cfg.dropout) if seed is not None else 0.0
+    p_a = float(cfg.attention_dropout) if seed is not None else 0.0
+    if seed is not None and float(getattr(cfg, "layerdrop", 0.0)) > 0.0:
+        raise NotImplementedError("OPT layerdrop > 0 is not supported")
     emb, hidden, slot, pos_ids, status = ops.embed_splice(
         input_ids, attention_mask, video_mask, w["embed"], video_features, w["pos"], 2)
     key_mask = None
@@ -102,11 +115,12 @@ def opt_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
         q, k, v = qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:]
         if kv_sink is not None:
             kv_sink(li, k, v)
-        o, lse = ops.attention(q, k, v, heads, 1.0, causal=True, key_mask=key_mask, need_lse=True)
-        x_mid = ops.gemm(o.view(rows, dim), lw["out_w"], lw["out_b"], residual=x)
+        o, lse = ops.attention(q, k, v, heads, 1.0, causal=True, key_mask=key_mask, need_lse=True,
+                               dropout=_drop(p_a, seed, li, 0))
+        x_mid = ops.gemm(o.view(rows, dim), lw["out_w"], lw["out_b"], residual=x, dropout=_drop(p_h, seed, li, 1))
         y2, m2, r2 = ops.layernorm(x_mid, lw["ln2_g"], lw["ln2_b"], 1e-5, save_stats=True)
         f1 = ops.gemm(y2, lw["fc1_w"], lw["fc1_b"], epilogue=act)
-        x_out = ops.gemm(f1, lw["fc2_w"], lw["fc2_b"], residual=x_mid)
+        x_out = ops.gemm(f1, lw["fc2_w"], lw["fc2_b"], residual=x_mid, dropout=_drop(p_h, seed, li, 2))
         if save:
             s = dict(x_in=x, m1=m1, r1=r1, qkv=qkv, o=o, lse=lse, x_mid=x_mid, m2=m2, r2=r2, f1=f1)
             if act == ops.EPI_GELU:
@@ -129,6 +143,7 @@ def opt_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
             if save:
                 out["ctx"] = dict(saved=saved, x_last=x, mf=mf, rf=rf, logits=logits, labels=labels,
                                   row_lse=row_lse, n_valid=n_valid, slot=slot, key_mask=key_mask,
+                                  seed=seed, p_h=p_h, p_a=p_a,
                                   b=b, l=l, n_features=0 if video_features is None else video_features.shape[0])
     return out
 
@@ -149,9 +164,15 @@ def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None
     d_final = ops.gemm(dlogits, w["embed_t"])
     dx = ops.layernorm_bwd(d_final, ctx["x_last"], w["lnf_g"], ctx["mf"], ctx["rf"])
     del dlogits, d_final
+    seed, p_h, p_a = ctx["seed"], ctx["p_h"], ctx["p_a"]
+
+    def masked(t, layer, site):
+        d = _drop(p_h, seed, layer, site)
+        return t if d is None else ops.dropout(t, d[0], d[1], d[2])
+
     for li in range(len(w["layers"]) - 1, -1, -1):
         lw, s = w["layers"][li], ctx["saved"][li]
-        d_f1 = ops.gemm(dx, lw["fc2_wt"])
+        d_f1 = ops.gemm(masked(dx, li, 2), lw["fc2_wt"])
         if act == ops.EPI_RELU:
             d_pre = ops.act_bwd(d_f1, s["f1"], act)
         else:
@@ -159,12 +180,13 @@ def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None
             d_pre = ops.act_bwd(d_f1, pre, act)
         d_y2 = ops.gemm(d_pre, lw["fc1_wt"])
         d_mid = ops.layernorm_bwd(d_y2, s["x_mid"], lw["ln2_g"], s["m2"], s["r2"], dx_add=dx)
-        d_o = ops.gemm(d_mid, lw["out_wt"]).view(b, l, dim)
+        d_o = ops.gemm(masked(d_mid, li, 1), lw["out_wt"]).view(b, l, dim)
         qkv = s["qkv"]
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], s["o"], s["lse"],
                           d_o, heads, 1.0, causal=True, key_mask=ctx["key_mask"], dq_scale=scaling,
-                          dq=dqkv[:, :, :dim], dk=dqkv[:, :, dim:2 * dim], dv=dqkv[:, :, 2 * dim:])
+                          dq=dqkv[:, :, :dim], dk=dqkv[:, :, dim:2 * dim], dv=dqkv[:, :, 2 * dim:],
+                          dropout=_drop(p_a, seed, li, 0))
         d_y = ops.gemm(dqkv.view(rows, 3 * dim), lw["qkv_wt"])
         dx = ops.layernorm_bwd(d_y, s["x_in"], lw["ln1_g"], s["m1"], s["r1"], dx_add=d_mid)
     if ctx["n_features"] == 0:

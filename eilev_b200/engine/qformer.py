@@ -14,7 +14,8 @@ B200-first choices:
     is written by hand: dgrad and wgrad GEMMs on the same tcgen05 kernel (operands staged
     by a transpose kernel), flash-attention backward, LayerNorm backward with
     deterministic dgamma/dbeta.
-Dropout of the reference (p=0.1 in train mode) is not applied.
+Dropout (hidden_dropout_prob / attention_probs_dropout_prob, active in train mode exactly as
+in the reference) uses counter-hash masks regenerated in the backward pass; nothing is stored.
 """
 from __future__ import annotations
 
@@ -89,9 +90,16 @@ def pack_qformer(model, cache: PackCache):
     return cache.get("qformer", params, build)
 
 
-def qformer_forward(model, cache: PackCache, image_embeds: torch.Tensor, save: bool):
+_SALT_QF = 1 << 16  # salts of the Q-Former dropout sites: _SALT_QF + layer*8 + site
+
+
+def _drop(p: float, seed, layer: int, site: int):
+    return (p, seed, _SALT_QF + layer * 8 + site) if (seed is not None and p > 0.0) else None
+
+
+def qformer_forward(model, cache: PackCache, image_embeds: torch.Tensor, save: bool, seed=None):
     """image_embeds (N, Skv, Dv) bf16 -> (video_features (N*Q, Dt) bf16, query_output (N, Q, Dq)
-    bf16, ctx for backward | None)."""
+    bf16, ctx for backward | None).  seed: device int64 tensor -> dropout is applied."""
     cfg = model.qformer.config
     w = pack_qformer(model, cache)
     n, skv, dv = image_embeds.shape
@@ -104,18 +112,23 @@ def qformer_forward(model, cache: PackCache, image_embeds: torch.Tensor, save: b
     rows = n * nq
     img2 = image_embeds.reshape(n * skv, dv)
 
+    p_h = float(cfg.hidden_dropout_prob) if seed is not None else 0.0
+    p_a = float(cfg.attention_probs_dropout_prob) if seed is not None else 0.0
     x0 = bf16(model.query_tokens).reshape(1, nq, dq).expand(n, nq, dq).reshape(rows, dq).contiguous()
     x, m0, r0 = ops.layernorm(x0, w["ln0_g"], w["ln0_b"], eps, save_stats=True)
+    if p_h > 0.0:
+        x = ops.dropout(x, p_h, seed, _SALT_QF + 7)
     ckv = None
     if "ckv_w" in w:
         ckv = ops.gemm(img2, w["ckv_w"], w["ckv_b"]).view(n, skv, -1)
     saved = []
-    for lw in w["layers"]:
+    for li, lw in enumerate(w["layers"]):
         s = {"x": x}
         qkv = ops.gemm(x, lw["qkv_w"], lw["qkv_b"]).view(n, nq, 3 * dq)
         ctx, lse = ops.attention(qkv[:, :, :dq], qkv[:, :, dq:2 * dq], qkv[:, :, 2 * dq:], heads, scale,
-                                 need_lse=True)
-        a = ops.gemm(ctx.view(rows, dq), lw["o_w"], lw["o_b"], residual=x)  # dense(ctx) + x
+                                 need_lse=True, dropout=_drop(p_a, seed, li, 0))
+        a = ops.gemm(ctx.view(rows, dq), lw["o_w"], lw["o_b"], residual=x,
+                     dropout=_drop(p_h, seed, li, 1))  # dropout(dense(ctx)) + x
         x1, m1, r1 = ops.layernorm(a, lw["ln1_g"], lw["ln1_b"], eps, save_stats=True)
         s.update(qkv=qkv, ctx=ctx, lse=lse, xin1=a, m1=m1, r1=r1, x1=x1)
         if lw["cross"] is not None:
@@ -123,15 +136,16 @@ def qformer_forward(model, cache: PackCache, image_embeds: torch.Tensor, save: b
             kc = ckv[:, :, (2 * c) * dq:(2 * c + 1) * dq]
             vc = ckv[:, :, (2 * c + 1) * dq:(2 * c + 2) * dq]
             qc = ops.gemm(x1, lw["cq_w"], lw["cq_b"]).view(n, nq, dq)
-            cctx, clse = ops.attention(qc, kc, vc, heads, scale, need_lse=True)
-            a2 = ops.gemm(cctx.view(rows, dq), lw["co_w"], lw["co_b"], residual=x1)
+            cctx, clse = ops.attention(qc, kc, vc, heads, scale, need_lse=True, dropout=_drop(p_a, seed, li, 2))
+            a2 = ops.gemm(cctx.view(rows, dq), lw["co_w"], lw["co_b"], residual=x1,
+                          dropout=_drop(p_h, seed, li, 3))
             x2, m2, r2 = ops.layernorm(a2, lw["ln2_g"], lw["ln2_b"], eps, save_stats=True)
             s.update(qc=qc, cctx=cctx, clse=clse, xin2=a2, m2=m2, r2=r2)
         else:
             x2 = x1
         s["x2"] = x2
         inter = ops.gemm(x2, lw["i_w"], lw["i_b"], epilogue=act)
-        a3 = ops.gemm(inter, lw["o2_w"], lw["o2_b"], residual=x2)
+        a3 = ops.gemm(inter, lw["o2_w"], lw["o2_b"], residual=x2, dropout=_drop(p_h, seed, li, 4))
         x, m3, r3 = ops.layernorm(a3, lw["ln3_g"], lw["ln3_b"], eps, save_stats=True)
         s.update(inter=inter, xin3=a3, m3=m3, r3=r3)
         saved.append(s)
@@ -139,7 +153,7 @@ def qformer_forward(model, cache: PackCache, image_embeds: torch.Tensor, save: b
     ctx_out = None
     if save:
         ctx_out = dict(saved=saved, x0=x0, m0=m0, r0=r0, ckv=ckv, img2=img2, qout=x, n=n, nq=nq,
-                       skv=skv)
+                       skv=skv, seed=seed, p_h=p_h, p_a=p_a)
     return feats, x.view(n, nq, dq), ctx_out
 
 
@@ -164,6 +178,13 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
     def zeros(k):
         return torch.zeros(k, dtype=torch.float32, device=dev)
 
+    seed, p_h, p_a = ctx["seed"], ctx["p_h"], ctx["p_a"]
+
+    def masked(t, layer, site):
+        """gradient entering a dense layer whose OUTPUT was dropped in the forward"""
+        d = _drop(p_h, seed, layer, site)
+        return t if d is None else ops.dropout(t, d[0], d[1], d[2])
+
     d_feats = d_feats.contiguous()
     g["language_projection.weight"] = _wgrad(d_feats, ctx["qout"])
     g["language_projection.bias"] = ops.colsum(d_feats)
@@ -178,9 +199,10 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
         dg, db = zeros(dq), zeros(dq)
         ds = ops.layernorm_bwd(dx, s["xin3"], lw["ln3_g"], s["m3"], s["r3"], dgamma=dg, dbeta=db)
         g[p + "output_query.LayerNorm.weight"], g[p + "output_query.LayerNorm.bias"] = dg, db
-        g[p + "output_query.dense.weight"] = _wgrad(ds, s["inter"])
-        g[p + "output_query.dense.bias"] = ops.colsum(ds)
-        d_inter = ops.gemm(ds, lw["o2_wt"])
+        dsm = masked(ds, i, 4)
+        g[p + "output_query.dense.weight"] = _wgrad(dsm, s["inter"])
+        g[p + "output_query.dense.bias"] = ops.colsum(dsm)
+        d_inter = ops.gemm(dsm, lw["o2_wt"])
         if act == ops.EPI_GELU:
             pre = ops.gemm(s["x2"], lw["i_w"], lw["i_b"])  # recompute the pre-activation
             d_pre = ops.act_bwd(d_inter, pre, act)
@@ -196,15 +218,16 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
             ds2 = ops.layernorm_bwd(dx2, s["xin2"], lw["ln2_g"], s["m2"], s["r2"], dgamma=dg, dbeta=db)
             g[p + "crossattention.output.LayerNorm.weight"] = dg
             g[p + "crossattention.output.LayerNorm.bias"] = db
-            g[p + "crossattention.output.dense.weight"] = _wgrad(ds2, s["cctx"].view(rows, dq))
-            g[p + "crossattention.output.dense.bias"] = ops.colsum(ds2)
-            d_cctx = ops.gemm(ds2, lw["co_wt"]).view(n, nq, dq)
+            ds2m = masked(ds2, i, 3)
+            g[p + "crossattention.output.dense.weight"] = _wgrad(ds2m, s["cctx"].view(rows, dq))
+            g[p + "crossattention.output.dense.bias"] = ops.colsum(ds2m)
+            d_cctx = ops.gemm(ds2m, lw["co_wt"]).view(n, nq, dq)
             kc = ctx["ckv"][:, :, (2 * c) * dq:(2 * c + 1) * dq]
             vc = ctx["ckv"][:, :, (2 * c + 1) * dq:(2 * c + 2) * dq]
             dkc = d_ckv[:, :, (2 * c) * dq:(2 * c + 1) * dq]
             dvc = d_ckv[:, :, (2 * c + 1) * dq:(2 * c + 2) * dq]
             dqc, _, _ = ops.attention_bwd(s["qc"], kc, vc, s["cctx"], s["clse"], d_cctx, heads, scale,
-                                          dk=dkc, dv=dvc)
+                                          dk=dkc, dv=dvc, dropout=_drop(p_a, seed, i, 2))
             dqc2 = dqc.view(rows, dq)
             g[p + "crossattention.attention.query.weight"] = _wgrad(dqc2, s["x1"])
             g[p + "crossattention.attention.query.bias"] = ops.colsum(dqc2)
@@ -215,14 +238,15 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
         dg, db = zeros(dq), zeros(dq)
         ds1 = ops.layernorm_bwd(dx1, s["xin1"], lw["ln1_g"], s["m1"], s["r1"], dgamma=dg, dbeta=db)
         g[p + "attention.output.LayerNorm.weight"], g[p + "attention.output.LayerNorm.bias"] = dg, db
-        g[p + "attention.output.dense.weight"] = _wgrad(ds1, s["ctx"].view(rows, dq))
-        g[p + "attention.output.dense.bias"] = ops.colsum(ds1)
-        d_ctx = ops.gemm(ds1, lw["o_wt"]).view(n, nq, dq)
+        ds1m = masked(ds1, i, 1)
+        g[p + "attention.output.dense.weight"] = _wgrad(ds1m, s["ctx"].view(rows, dq))
+        g[p + "attention.output.dense.bias"] = ops.colsum(ds1m)
+        d_ctx = ops.gemm(ds1m, lw["o_wt"]).view(n, nq, dq)
         qkv = s["qkv"]
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :, :dq], qkv[:, :, dq:2 * dq], qkv[:, :, 2 * dq:], s["ctx"], s["lse"],
                           d_ctx, heads, scale, dq=dqkv[:, :, :dq], dk=dqkv[:, :, dq:2 * dq],
-                          dv=dqkv[:, :, 2 * dq:])
+                          dv=dqkv[:, :, 2 * dq:], dropout=_drop(p_a, seed, i, 0))
         dqkv2 = dqkv.view(rows, 3 * dq)
         dw = _wgrad(dqkv2, s["x"])
         dbias = ops.colsum(dqkv2)
@@ -248,6 +272,8 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
 
     # ---- initial LayerNorm over the expanded query tokens
     dg, db = zeros(dq), zeros(dq)
+    if p_h > 0.0:
+        dx = ops.dropout(dx, p_h, seed, _SALT_QF + 7)
     d0 = ops.layernorm_bwd(dx, ctx["x0"], w["ln0_g"], ctx["m0"], ctx["r0"], dgamma=dg, dbeta=db)
     g["qformer.layernorm.weight"], g["qformer.layernorm.bias"] = dg, db
     g["query_tokens"] = ops.colsum(d0.view(n, nq * dq)).view(1, nq, dq)

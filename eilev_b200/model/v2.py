@@ -299,8 +299,8 @@ class _QFormerProjectFn(torch.autograd.Function):
     """ViT output -> Q-Former -> language_projection with the hand-written backward."""
 
     @staticmethod
-    def forward(ctx, model, image_embeds, *params):
-        feats, qout, saved = E_qf.qformer_forward(model, model._pack, image_embeds, save=True)
+    def forward(ctx, model, image_embeds, seed, *params):
+        feats, qout, saved = E_qf.qformer_forward(model, model._pack, image_embeds, save=True, seed=seed)
         ctx.model, ctx.saved = model, saved
         ctx.param_meta = [(p.dtype, p.requires_grad) for p in params]
         ctx.mark_non_differentiable(qout)
@@ -315,17 +315,17 @@ class _QFormerProjectFn(torch.autograd.Function):
         for (name, _), (dtype, need) in zip(E_qf.qformer_param_list(model), ctx.param_meta):
             g = grads.get(name) if need else None
             out.append(None if g is None else g.to(dtype))
-        return (None, None, *out)
+        return (None, None, None, *out)
 
 
 class _LMLossFn(torch.autograd.Function):
     """Splice + OPT + shifted cross entropy; backward is dgrad-only down to the video slots."""
 
     @staticmethod
-    def forward(ctx, model, video_features, input_ids, attention_mask, video_mask, labels):
+    def forward(ctx, model, video_features, input_ids, attention_mask, video_mask, labels, seed):
         lm = model.language_model
         out = E_opt.opt_forward(lm, lm._pack, input_ids, attention_mask, video_mask, video_features,
-                                labels=labels, save=True)
+                                labels=labels, save=True, seed=seed)
         ctx.model, ctx.saved = model, out["ctx"]
         ctx.feat_dtype = video_features.dtype
         ctx.mark_non_differentiable(out["logits"], out["status"])
@@ -336,7 +336,7 @@ class _LMLossFn(torch.autograd.Function):
         lm = ctx.model.language_model
         d_feats = E_opt.opt_backward(lm, lm._pack, ctx.saved, grad_loss)
         ctx.saved = None
-        return None, d_feats.to(ctx.feat_dtype), None, None, None, None
+        return None, d_feats.to(ctx.feat_dtype), None, None, None, None, None
 
 
 # =============================================================================== full model
@@ -393,7 +393,20 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         self._input_require_grads = False
 
     # ------------------------------------------------------------------ encode
-    def _video_features(self, pixel_values: torch.Tensor, output_hidden_states: bool, train: bool):
+    def _next_dropout_seed(self, device):
+        """Device-resident dropout seed, advanced once per training forward (in place, so a
+        captured CUDA graph draws fresh masks on every replay).  None in eval mode."""
+        if not self.training:
+            return None
+        seed = getattr(self, "_dropout_seed", None)
+        if seed is None or seed.device != device:
+            seed = torch.full((1,), int(torch.initial_seed()) & 0x7FFFFFFF, dtype=torch.int64, device=device)
+            self._dropout_seed = seed
+        seed.add_(1 << 20)  # sites add salts < 2^20
+        return seed
+
+    def _video_features(self, pixel_values: torch.Tensor, output_hidden_states: bool, train: bool,
+                        seed=None):
         vis_last, vis_pooled, vis_hidden = None, None, None
         with torch.no_grad():
             vis_last, vis_pooled, vis_hidden = E_vis.vision_forward(
@@ -403,7 +416,7 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         image_embeds = vis_last.view(n, t * s, -1)
         if train:
             params = [p for _, p in E_qf.qformer_param_list(self)]
-            feats, qout = _QFormerProjectFn.apply(self, image_embeds, *params)
+            feats, qout = _QFormerProjectFn.apply(self, image_embeds, seed, *params)
         else:
             with torch.no_grad():
                 feats, qout, _ = E_qf.qformer_forward(self, self._pack, image_embeds, save=False)
@@ -453,9 +466,10 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         vision_outputs = None
         query_outputs = None
         feats = None
+        seed = self._next_dropout_seed(input_ids.device) if train else None
         if pixel_values is not None:
             _require_cuda(pixel_values, "VideoBlipForConditionalGeneration.forward")
-            feats, qout, vis = self._video_features(pixel_values, want_hidden, train)
+            feats, qout, vis = self._video_features(pixel_values, want_hidden, train, seed)
             vision_outputs = self._pack_vision_outputs(vis, return_dict)
             q = qout.to(self.dtype)
             query_outputs = (BaseModelOutputWithPoolingAndCrossAttentions(last_hidden_state=q, pooler_output=q[:, 0])
@@ -466,7 +480,7 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         lm = self.language_model
         if train:
             loss, logits, status = _LMLossFn.apply(self, feats, input_ids, attention_mask,
-                                                   video_input_mask, labels)
+                                                   video_input_mask, labels, seed)
             hidden_states = None
         else:
             with torch.no_grad():

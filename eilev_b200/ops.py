@@ -36,7 +36,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
          residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
          epilogue: int = EPI_NONE, alpha: float = 1.0, alpha_cols: int = 0, beta: float = 0.0,
          out_dtype: torch.dtype = torch.bfloat16, row_group: int = 0, out_rows: int | None = None,
-         backend: int = GEMM_AUTO, block_n: int = 0) -> torch.Tensor:
+         backend: int = GEMM_AUTO, block_n: int = 0, dropout=None) -> torch.Tensor:
     """``out = act(alpha * (a @ w.T + bias)) + residual (+ beta*out)``.
 
     a: (M, K) bf16 (last dim contiguous), w: (N, K) bf16 — an ``nn.Linear`` weight.
@@ -70,6 +70,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
     args.alpha_cols, args.row_group = alpha_cols, row_group
     args.epilogue, args.out_dtype, args.backend = epilogue, _DT[out_dtype], backend
     args.reserved = block_n
+    if dropout is not None and dropout[0] > 0.0:  # (p, seed tensor (uint64/int64 on device), salt)
+        args.dropout_p, args.dropout_seed, args.dropout_salt = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
     check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
     return out
 
@@ -127,7 +129,7 @@ def layernorm_bwd(dy, xin, gamma, mean, rstd, *, dx_add=None, dgamma=None, dbeta
     return dx
 
 
-def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal) -> AttnArgs:
+def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout=None) -> AttnArgs:
     """q: (B, Sq, >=H*D) view, k/v: (B, Skv, ...) views; last dim contiguous."""
     a = AttnArgs()
     a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
@@ -139,12 +141,14 @@ def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal) -> AttnArgs:
     a.v_bs, a.v_rs = v.stride(0), v.stride(1)
     a.o_bs, a.o_rs = o.stride(0), o.stride(1)
     a.scale, a.causal = scale, 1 if causal else 0
+    if dropout is not None and dropout[0] > 0.0:
+        a.dropout_p, a.dropout_seed, a.dropout_salt = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
     return a
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float, *,
               causal: bool = False, key_mask: torch.Tensor | None = None,
-              need_lse: bool = False):
+              need_lse: bool = False, dropout=None):
     """Softmax attention.  q: (B, Sq, H*D), k/v: (B, Skv, H*D) bf16 views whose last dim is
     contiguous (they may be slices of one fused QKV buffer).  Returns o: (B, Sq, H*D)."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v")):
@@ -159,7 +163,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     if key_mask is not None:
         _need(key_mask, torch.uint8, "attention.key_mask")
         assert key_mask.is_contiguous() and key_mask.shape == (k.shape[0], k.shape[1])
-    a = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal)
+    a = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout)
     check(_lib.lib().vb_attention_fwd(C.byref(a), _stream()), "vb_attention_fwd")
     return (o, lse) if need_lse else o
 
@@ -173,7 +177,7 @@ def attention_uses_tcgen05(q, k, v, heads: int, *, causal=False, key_mask=None, 
 
 
 def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: bool = False,
-                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None):
+                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None, dropout=None):
     """Returns (dq, dk, dv) with the shapes of q, k, v (contiguous unless views are given)."""
     hd = q.shape[2]
     d = hd // heads
@@ -184,7 +188,7 @@ def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: boo
     delta = torch.empty((q.shape[0], heads, q.shape[1]), dtype=torch.float32, device=q.device)
     dq_acc = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.float32, device=q.device)
     b = AttnBwdArgs()
-    b.fwd = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal)
+    b.fwd = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout)
     b.d_o, b.dq, b.dk, b.dv = d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     b.dq_bs, b.dq_rs = dq.stride(0), dq.stride(1)
     b.dk_bs, b.dk_rs = dk.stride(0), dk.stride(1)
@@ -322,6 +326,16 @@ def colsum(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     check(_lib.lib().vb_colsum(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0),
                                acc, _stream()), "vb_colsum")
     return out
+
+
+def dropout(x: torch.Tensor, p: float, seed: torch.Tensor, salt: int) -> torch.Tensor:
+    """y = x * mask / (1 - p) with the counter-hash mask of (seed + salt, flat index); 2-D bf16."""
+    _need(x, torch.bfloat16, "dropout.x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().vb_dropout(x.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], x.stride(0), y.stride(0),
+                                float(p), seed.data_ptr(), int(salt), _stream()), "vb_dropout")
+    return y
 
 
 def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -81,6 +81,14 @@ typedef struct vb_gemm_args {
   int32_t out_dtype; /* VB_BF16 or VB_F32 */
   int32_t backend;   /* VB_GEMM_* */
   int32_t reserved;
+  /* Dropout on act(...) BEFORE the residual is added (HF: dropout(dense(x)) + residual):
+   * kept elements are scaled by 1/(1-p).  The mask is a counter hash of
+   * (*dropout_seed + dropout_salt, row*n + col) — vb_dropout with the same seed/salt
+   * regenerates it in the backward pass.  dropout_p == 0 or dropout_seed == NULL: off. */
+  float dropout_p;
+  int32_t reserved2;
+  const uint64_t* dropout_seed; /* device pointer */
+  uint64_t dropout_salt;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
@@ -125,6 +133,12 @@ typedef struct vb_attn_args {
   int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
   float scale;
   int32_t causal;
+  /* Dropout on the attention probabilities (HF:blip_2/modeling_blip_2.py:621-624): mask =
+   * hash(*dropout_seed + dropout_salt, ((b*H + h)*Sq + i)*Skv + j); off when p == 0 / NULL. */
+  float dropout_p;
+  int32_t reserved;
+  const uint64_t* dropout_seed;
+  uint64_t dropout_salt;
 } vb_attn_args;
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
 /* 1 if vb_attention_fwd takes the tcgen05/TMEM kernel (non-causal, unmasked, no lse,
@@ -212,6 +226,11 @@ int vb_act_bwd(const void* dy, const void* saved, void* dx, int32_t epilogue, in
 /* out(f32, cols) (+)= column sums of x (bf16, rows x cols): bias gradients. */
 int vb_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int32_t accumulate,
               void* stream);
+/* y[r, c] = keep(*seed + salt, r*cols + c) ? x[r, c] / (1 - p) : 0   (bf16, row strides ldx/ldy).
+ * The same counter hash as the GEMM-epilogue dropout: used for the backward mask and for
+ * stand-alone dropouts (HF:blip_2/modeling_blip_2.py:985, HF:opt/modeling_opt.py:219,243). */
+int vb_dropout(const void* x, void* y, int64_t rows, int64_t cols, int64_t ldx, int64_t ldy,
+               float p, const uint64_t* seed, uint64_t salt, void* stream);
 /* y = a + b (bf16) */
 int vb_add(const void* a, const void* b, void* y, int64_t n, void* stream);
 

@@ -76,7 +76,11 @@ def vision_forward(sd, vcfg, pixel_values):
 
 
 # --------------------------------------------------------------------------- Q-Former
-def _qf_attention(sd, qcfg, hidden, kv_src, p):
+def _no_drop(site, t):
+    return t
+
+
+def _qf_attention(sd, qcfg, hidden, kv_src, p, drop=_no_drop, sites=(None, None)):
     """HF:blip_2/modeling_blip_2.py:579-633 (eager, scores / sqrt(d); masks are all-ones here)
     followed by Blip2QFormerSelfOutput :644-648 (dense + LN(residual))."""
     h = qcfg.num_attention_heads
@@ -90,23 +94,29 @@ def _qf_attention(sd, qcfg, hidden, kv_src, p):
     k = heads(_lin(kv_src, sd, p + "attention.key"))
     v = heads(_lin(kv_src, sd, p + "attention.value"))
     probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    probs = drop(sites[0], probs)  # attention_probs dropout (:621-624)
     ctx = (probs @ v).permute(0, 2, 1, 3).reshape(b, sq, h * d)
-    out = _lin(ctx, sd, p + "output.dense")
+    out = drop(sites[1], _lin(ctx, sd, p + "output.dense"))  # hidden dropout (:646)
     return _ln(out + hidden, sd, p + "output.LayerNorm", qcfg.layer_norm_eps)
 
 
-def qformer_forward(sd, qcfg, query_tokens, image_embeds):
-    """HF:blip_2/modeling_blip_2.py:962-1036, layers :729-780 (query-only path, dropout off)."""
+def qformer_forward(sd, qcfg, query_tokens, image_embeds, drop=_no_drop):
+    """HF:blip_2/modeling_blip_2.py:962-1036, layers :729-780 (query-only path).
+    `drop(site, tensor)` injects dropout masks (tests only; identity = eval mode); sites are
+    ("qf", layer, k) with k = 0 self-attn probs, 1 self-output, 2 cross probs, 3 cross-output,
+    4 FFN output, and ("qf", -1, 7) for the embedding dropout (:985)."""
     x = _ln(query_tokens.float(), sd, "qformer.layernorm", qcfg.layer_norm_eps)  # :984-985
+    x = drop(("qf", -1, 7), x)
     for i in range(qcfg.num_hidden_layers):
         p = f"qformer.encoder.layer.{i}."
-        x = _qf_attention(sd, qcfg, x, x, p + "attention.")
+        x = _qf_attention(sd, qcfg, x, x, p + "attention.", drop, (("qf", i, 0), ("qf", i, 1)))
         if i % qcfg.cross_attention_frequency == 0:  # :716-720
-            x = _qf_attention(sd, qcfg, x, image_embeds.float(), p + "crossattention.")
+            x = _qf_attention(sd, qcfg, x, image_embeds.float(), p + "crossattention.", drop,
+                              (("qf", i, 2), ("qf", i, 3)))
         act = F.gelu if qcfg.hidden_act == "gelu" else getattr(F, qcfg.hidden_act)
         inter = act(_lin(x, sd, p + "intermediate_query.dense"))
-        x = _ln(_lin(inter, sd, p + "output_query.dense") + x, sd, p + "output_query.LayerNorm",
-                qcfg.layer_norm_eps)
+        x = _ln(drop(("qf", i, 4), _lin(inter, sd, p + "output_query.dense")) + x, sd,
+                p + "output_query.LayerNorm", qcfg.layer_norm_eps)
     return x
 
 
@@ -117,8 +127,9 @@ def opt_positions(attention_mask):
     return (torch.cumsum(am, dim=1) * am - 1) + 2
 
 
-def opt_decoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.model.decoder."):
-    """HF:opt/modeling_opt.py:321-396; layers :202-253; attention :135-181 (q scaled first)."""
+def opt_decoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.model.decoder.", drop=_no_drop):
+    """HF:opt/modeling_opt.py:321-396; layers :202-253; attention :135-181 (q scaled first).
+    drop sites: ("opt", layer, 0) attention probs, 1 after out_proj (:219), 2 after fc2 (:243)."""
     assert tcfg.do_layer_norm_before and tcfg.word_embed_proj_dim == tcfg.hidden_size
     b, l, _ = inputs_embeds.shape
     h = tcfg.num_attention_heads
@@ -139,12 +150,12 @@ def opt_decoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.model
         q = heads(_lin(y, sd, lp + "self_attn.q_proj") * d ** -0.5)
         k = heads(_lin(y, sd, lp + "self_attn.k_proj"))
         v = heads(_lin(y, sd, lp + "self_attn.v_proj"))
-        att = torch.softmax(q @ k.transpose(-1, -2) + bias, dim=-1) @ v
+        att = drop(("opt", i, 0), torch.softmax(q @ k.transpose(-1, -2) + bias, dim=-1)) @ v
         att = att.transpose(1, 2).reshape(b, l, h * d)
-        x = x + _lin(att, sd, lp + "self_attn.out_proj")
+        x = x + drop(("opt", i, 1), _lin(att, sd, lp + "self_attn.out_proj"))
         y = _ln(x, sd, lp + "final_layer_norm", 1e-5)
         act = F.relu if tcfg.activation_function == "relu" else getattr(F, tcfg.activation_function)
-        x = x + _lin(act(_lin(y, sd, lp + "fc1")), sd, lp + "fc2")
+        x = x + drop(("opt", i, 2), _lin(act(_lin(y, sd, lp + "fc1")), sd, lp + "fc2"))
     return _ln(x, sd, p + "final_layer_norm", 1e-5)
 
 
@@ -156,12 +167,12 @@ def causal_lm_loss(logits, labels):
 
 
 # --------------------------------------------------------------------------- full model
-def video_features(sd, config, pixel_values):
+def video_features(sd, config, pixel_values, drop=_no_drop):
     """v2.py:169-203 — ViT -> Q-Former -> language_projection; rows in (clip, query) order."""
     image_embeds, pooled = vision_forward(sd, config.vision_config, pixel_values)
     n = image_embeds.shape[0]
     query = sd["query_tokens"].float().expand(n, -1, -1)
-    qout = qformer_forward(sd, config.qformer_config, query, image_embeds)
+    qout = qformer_forward(sd, config.qformer_config, query, image_embeds, drop)
     feats = _lin(qout.reshape(n * config.num_query_tokens, -1), sd, "language_projection")
     return feats, qout, image_embeds, pooled
 
@@ -176,19 +187,19 @@ def splice(sd, input_ids, video_input_mask, feats):
 
 
 def videoblip_forward(sd, config, input_ids, attention_mask=None, pixel_values=None,
-                      video_input_mask=None, labels=None):
+                      video_input_mask=None, labels=None, drop=_no_drop):
     """v2.py:132-252 for the decoder-only (OPT) language model.  Returns a dict."""
     out = {}
     feats = None
     if pixel_values is not None:
         assert video_input_mask is not None  # v2.py:154-157
-        feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values)
+        feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values, drop)
         out.update(video_features=feats, query_output=qout, image_embeds=image_embeds,
                    pooler_output=pooled)
     emb = splice(sd, input_ids, video_input_mask, feats)
     if attention_mask is None:
         attention_mask = torch.ones_like(input_ids)  # v2.py:216-217
-    hidden = opt_decoder(sd, config.text_config, emb, attention_mask)
+    hidden = opt_decoder(sd, config.text_config, emb, attention_mask, drop=drop)
     logits = F.linear(hidden, sd["language_model.model.decoder.embed_tokens.weight"].float())  # tied
     out.update(inputs_embeds=emb, logits=logits)
     if labels is not None:

@@ -284,6 +284,63 @@ def test_transpose_convert_misc():
     _close(ops.add(dy, pre), dy.float() + pre.float(), atol=0.02, rtol=0.01)
 
 
+def test_dropout_mask_is_shared_by_gemm_epilogue_and_elementwise_kernel():
+    ops = _ops()
+    seed = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    p, salt = 0.1, 77
+    m, n, k = 300, 512, 256
+    ones = torch.ones(m, n, dtype=torch.bfloat16, device="cuda")
+    mask = ops.dropout(ones, p, seed, salt).float()          # 0 or 1/(1-p)
+    keep = (mask > 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.01, keep
+    assert torch.allclose(mask[mask > 0], torch.tensor(1 / 0.9, device="cuda"), atol=5e-3)
+    assert not torch.equal(mask, ops.dropout(ones, p, seed, salt + 1).float())
+    a, w = _rand(m, k, scale=0.5, seed=80), _rand(n, k, scale=0.1, seed=81)
+    bias = torch.randn(n, device="cuda")
+    res = _rand(m, n, seed=82)
+    ref = torch.relu(a.float() @ w.float().t() + bias) * mask + res.float()
+    for be in (ops.GEMM_TCGEN05, ops.GEMM_GENERIC):
+        out = ops.gemm(a, w, bias, residual=res, epilogue=ops.EPI_RELU, backend=be, dropout=(p, seed, salt))
+        _close(out, ref, atol=0.03, rtol=0.01, what=f"gemm dropout backend {be}")
+    seed.add_(1)  # a new step draws a new mask
+    assert not torch.equal(mask, ops.dropout(ones, p, seed, salt).float())
+
+
+@pytest.mark.parametrize("b,heads,d,sq,skv,causal", [(2, 12, 64, 32, 32, False), (2, 12, 64, 32, 300, False),
+                                                      (1, 4, 80, 200, 200, True)])
+def test_attention_dropout_fwd_bwd(b, heads, d, sq, skv, causal):
+    ops = _ops()
+    hd = heads * d
+    scale = d ** -0.5
+    seed = torch.tensor([999], dtype=torch.int64, device="cuda")
+    p, salt = 0.1, 5
+    q = _rand(b, sq, hd, seed=90)
+    kv = _rand(b, skv, 2 * hd, seed=91)
+    k, v = kv[:, :, :hd], kv[:, :, hd:]
+    drop = (p, seed, salt)
+    o, lse = ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=drop)
+    mask = ops.dropout(torch.ones(b * heads * sq, skv, dtype=torch.bfloat16, device="cuda"), p, seed, salt)
+    mask = mask.float().view(b, heads, sq, skv)
+    qf = q.float().detach().clone().requires_grad_(True)
+    kf = k.float().detach().clone().requires_grad_(True)
+    vf = v.float().detach().clone().requires_grad_(True)
+    qh = qf.view(b, sq, heads, d).transpose(1, 2)
+    kh = kf.view(b, skv, heads, d).transpose(1, 2)
+    vh = vf.view(b, skv, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        i = torch.arange(sq, device="cuda")[:, None]
+        j = torch.arange(skv, device="cuda")[None, :]
+        s = s.masked_fill(j > i + (skv - sq), -1e30)
+    ref = ((torch.softmax(s, -1) * mask) @ vh).transpose(1, 2).reshape(b, sq, hd)
+    _close(o, ref, atol=0.03, rtol=0.02, what="attn dropout fwd")
+    d_o = _rand(b, sq, hd, seed=92)
+    ref.backward(d_o.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=drop)
+    for got, want, nm in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        _close(got, want, atol=0.03 + 0.02 * want.abs().max().item(), rtol=0.03, what=f"attn dropout {nm}")
+
+
 def test_adamw_matches_torch():
     ops = _ops()
     torch.manual_seed(2)

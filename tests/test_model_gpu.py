@@ -172,14 +172,70 @@ def test_errors_match_reference_contract():
         m.check_splice()
 
 
+def test_train_mode_dropout_matches_oracle_with_injected_masks():
+    """Recipe mode (dropout p = 0.1 in the Q-Former and the frozen-but-training OPT): the masks
+    are counter hashes, so the oracle can replay them: loss, logits and gradients must agree."""
+    from eilev_b200 import ops
+    from eilev_b200.engine import opt as E_opt, qformer as E_qf
+    from oracle import videoblip_ref as R
+    fx, cfg = load("small_opt")
+    cfg.qformer_config.hidden_dropout_prob = 0.1
+    cfg.qformer_config.attention_probs_dropout_prob = 0.1
+    cfg.text_config.dropout = 0.1
+    cfg.text_config.attention_dropout = 0.1
+    m = build(cfg, fx["state_dict"]).train()
+    for p_ in m.vision_model.parameters():
+        p_.requires_grad = False
+    for p_ in m.language_model.parameters():
+        p_.requires_grad = False
+    out = m(**cuda(fx["inputs"]), return_dict=True)
+    out.loss.backward()
+    seed = m._dropout_seed
+
+    def drop(site, t):
+        if site is None:
+            return t
+        tower, layer, k = site
+        salt = (E_qf._SALT_QF if tower == "qf" else E_opt._SALT_OPT) + (layer * 8 + k if layer >= 0 else k)
+        rows = t.numel() // t.shape[-1]
+        mask = ops.dropout(torch.ones(rows, t.shape[-1], dtype=torch.bfloat16, device="cuda"), 0.1, seed, salt)
+        return t * mask.float().cpu().view(t.shape)
+
+    sd = {k: v.clone() for k, v in fx["state_dict"].items()}
+    for k in fx["grads"]:
+        sd[k].requires_grad_(True)
+    ref = R.videoblip_forward(sd, cfg, **fx["inputs"], drop=drop)
+    ref["loss"].backward()
+    assert abs(float(out.loss) - float(ref["loss"])) < 0.05, (float(out.loss), float(ref["loss"]))
+    assert abs(float(ref["loss"]) - float(fx["loss"])) > 1e-3  # the masks really changed the computation
+    assert rel_l2(out.logits, ref["logits"]) < 0.03
+    num = den = 0.0
+    for n_, p_ in m.named_parameters():
+        if p_.grad is not None:
+            rg = sd[n_].grad
+            num += float((p_.grad.float().cpu() - rg).pow(2).sum())
+            den += float(rg.pow(2).sum())
+    glob = (num / den) ** 0.5
+    _dump("dropout/small_opt", loss=float(out.loss), loss_ref=float(ref["loss"]), grad_rel_l2=glob,
+          logits=rel_l2(out.logits, ref["logits"]))
+    assert glob < 0.10, glob
+    # a second step draws different masks; eval mode is deterministic and mask-free
+    out2 = m(**cuda(fx["inputs"]), return_dict=True)
+    assert abs(float(out2.loss) - float(out.loss)) > 1e-4
+    m.eval()
+    with torch.no_grad():
+        e1 = m(**cuda(fx["inputs"]), return_dict=True)
+    assert abs(float(e1.loss) - float(fx["loss"])) < 0.03
+
+
 REAL_DIMS = dict(
     vision_config=dict(hidden_size=1408, intermediate_size=6144, num_hidden_layers=2, num_attention_heads=16,
                        patch_size=14, image_size=224),
     qformer_config=dict(hidden_size=768, num_hidden_layers=2, num_attention_heads=12, intermediate_size=3072,
-                        encoder_hidden_size=1408),
+                        encoder_hidden_size=1408, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
     text_config=dict(model_type="opt", hidden_size=2560, num_hidden_layers=2, ffn_dim=10240,
                      num_attention_heads=32, vocab_size=50272, max_position_embeddings=2048,
-                     word_embed_proj_dim=2560),
+                     word_embed_proj_dim=2560, dropout=0.0, attention_dropout=0.0),
     num_query_tokens=32)
 
 
