@@ -82,6 +82,27 @@ VB_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       : "memory");
 }
 
+// 2-D tiled store smem -> global (bulk async group); rows/cols outside the tensor are clipped.
+VB_DEVICE void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+VB_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// wait until at most N committed bulk groups of this thread still READ their smem source
+template <int N>
+VB_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+VB_DEVICE void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+VB_DEVICE void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+VB_DEVICE void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 VB_DEVICE void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(

@@ -19,6 +19,7 @@ struct EpiParams {
   unsigned long long drop_salt;
   unsigned int drop_thresh;  // 0 = no dropout
   float drop_scale;
+  int tma_store;             // 1: bf16 tile staged in smem and written with one TMA store per slab
   int epilogue;
   int out_f32;
 };
@@ -130,5 +131,65 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
   }
 }
 
+
+
+// Staged epilogue (CTA-pair kernel): 16 accumulator columns of one row -> bias / GELU|ReLU /
+// dropout / residual (already sitting in the swizzled slab) -> bf16 back into the slab.
+// `slab_row` points at this thread's 128-byte row of a [128 rows][64 cols] SWIZZLE_128B slab,
+// `row7` = row & 7 (swizzle phase), `c16` = 16-column chunk inside the slab (0..3).
+VB_DEVICE void epilogue_row16_staged(const EpiParams& p, long long row, long long col0, const uint32_t (&acc)[16],
+                                     uint8_t* slab_row, int row7, int c16, bool has_res) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.bias != nullptr) {
+    if (col0 + 16 <= p.n) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < p.n) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.alpha != 1.0f) {
+    const long long ac = p.alpha_cols <= 0 ? p.n : p.alpha_cols;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < ac) v[j] *= p.alpha;
+  }
+  if (p.epilogue == VB_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+  } else if (p.epilogue == VB_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (p.drop_thresh != 0u) {
+    const uint64_t seed = *p.drop_seed + p.drop_salt;
+    const uint64_t base = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.n) + static_cast<uint64_t>(col0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = dropout_keep(seed, base + j, p.drop_thresh) ? v[j] * p.drop_scale : 0.0f;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4* cell = reinterpret_cast<uint4*>(slab_row + (((2 * c16 + h) ^ row7) << 4));
+    if (has_res) {
+      const uint4 u = *cell;
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+      v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
+    o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+    o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
+    o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+    *cell = o;
+  }
+}
 
 }  // namespace vb

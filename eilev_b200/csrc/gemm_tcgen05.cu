@@ -284,6 +284,7 @@ void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {
   ep.row_group = a.row_group;
   ep.epilogue = a.epilogue;
   ep.out_f32 = (a.out_dtype == VB_F32) ? 1 : 0;
+  ep.tma_store = 0;
   const bool drop = a.dropout_p > 0.0f && a.dropout_seed != nullptr;
   ep.drop_seed = reinterpret_cast<const unsigned long long*>(a.dropout_seed);
   ep.drop_salt = a.dropout_salt;

@@ -25,8 +25,13 @@ struct Gemm2Cfg {
   static constexpr int kABytes = k2BM * k2BK * 2;
   static constexpr int kBBytes = (BN / 2) * k2BK * 2;  // this CTA's half of B
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  // output staging for the TMA-store epilogue: [2 column halves][2 ping-pong slabs] of
+  // 128 rows x 64 cols bf16 (SWIZZLE_128B) = 64 KB
+  static constexpr int kSlabBytes = k2BM * 128;
+  static constexpr int kStagingBytes = 4 * kSlabBytes;
+  static constexpr int kStages = (226 * 1024 - kStagingBytes - 1280) / kStageBytes > 8
+                                     ? 8 : (226 * 1024 - kStagingBytes - 1280) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
   static_assert(BN % 32 == 0 || BN == 176, "BN/2 must be a whole number of 8-row groups");
   static_assert(kBBytes % 1024 == 0, "B half stage must keep 1024B alignment");
 };
@@ -34,7 +39,8 @@ struct Gemm2Cfg {
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_b, const EpiParams p,
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const EpiParams p,
                          const int num_k_blocks, const int m_tiles, const int n_tiles) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -43,7 +49,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_c = smem + kStages * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -60,6 +67,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (p.tma_store) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -145,6 +153,62 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const long long row = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+      if (BN == 256 && p.tma_store) {
+        // ---- staged path: this warp group (`half`) owns columns [128*half, 128*half+128) of the
+        // tile = two 64-column slabs; the four quarter-warps fill a slab, one thread TMA-stores it.
+        const int row_in = quarter * 32 + lane;              // row inside this CTA's 128 rows
+        const long long tile_row0 = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM;
+        const bool has_res = p.residual != nullptr;
+#pragma unroll 1
+        for (int sl = 0; sl < 2; ++sl) {
+          const long long col_slab = static_cast<long long>(n_blk) * BN + half * 128 + sl * 64;
+          uint8_t* slab = smem_c + (half * 2 + sl) * Cfg::kSlabBytes;
+          const bool slab_live = col_slab < p.n;
+          // the TMA store that last read this slab (previous tile) must have drained
+          if (ew % 4 == 0 && lane == 0) bulk_wait_read<1>();
+          named_bar_sync(1 + half, 128);
+          if (has_res && slab_live) {
+            // coalesced residual fetch: 8 lanes cover one 128-byte row, 4 rows per instruction
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = quarter * 32 + i * 4 + (lane >> 3);
+              const int c16b = lane & 7;
+              const long long grow = tile_row0 + r, gcol = col_slab + c16b * 8;
+              uint8_t* dst = slab + r * 128 + ((c16b ^ (r & 7)) << 4);
+              if (grow < p.m && gcol + 8 <= p.n) cp_async_16(dst, p.residual + grow * p.ldr + gcol);
+              else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+            }
+            cp_async_commit_wait_all();
+            __syncwarp();  // each warp reads back only rows it fetched itself
+          }
+#pragma unroll
+          for (int c16 = 0; c16 < 4; c16 += 2) {
+            uint32_t r0[16], r1[16];
+            const int ch = (half * 128 + sl * 64) / 16 + c16;
+            tmem_ld_16(t_row + ch * 16, r0);
+            tmem_ld_16(t_row + (ch + 1) * 16, r1);
+            tmem_ld_wait();
+            if (sl == 1 && c16 == 2) {  // last TMEM read of this warp for this tile
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+            }
+            if (slab_live) {
+              uint8_t* slab_row = slab + row_in * 128;
+              epilogue_row16_staged(p, row, col_slab + c16 * 16, r0, slab_row, row_in & 7, c16, has_res);
+              epilogue_row16_staged(p, row, col_slab + (c16 + 1) * 16, r1, slab_row, row_in & 7, c16 + 1, has_res);
+            }
+          }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+          named_bar_sync(1 + half, 128);
+          if (ew % 4 == 0 && lane == 0) {
+            if (slab_live) tma_store_2d(&tmap_c, slab, static_cast<int>(col_slab), static_cast<int>(tile_row0));
+            bulk_commit();  // (an empty group keeps the wait_group bookkeeping uniform)
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       int ch = c_begin;
       for (; ch + 1 < c_end; ch += 2) {  // two 16-column loads in flight per wait
         uint32_t r0[16], r1[16];
@@ -172,6 +236,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   }
 
+  if (warp >= 4 && ((warp - 4) & 3) == 0 && lane == 0) bulk_wait_read<0>();  // smem must outlive the stores
   tc_fence_before();
   cluster_sync_all();  // both CTAs are done with TMEM / remote barriers
   if (warp == 2) {
@@ -199,6 +264,12 @@ static cudaError_t launch_2cta(const vb_gemm_args& a, cudaStream_t stream) {
   }
   EpiParams ep;
   fill_epi_params(ep, a);
+  // TMA-store epilogue: bf16 output, plain row mapping, no accumulation into C
+  CUtensorMap tc = ta;
+  ep.tma_store = 0;
+  if (BN == 256 && a.out_dtype == VB_BF16 && a.beta == 0.0f && a.row_group == 0) {
+    if (make_tmap_bf16_2d(&tc, a.c, a.m, a.n, a.ldc, k2BM)) ep.tma_store = 1;
+  }
   const int m_tiles = static_cast<int>((a.m + 2 * k2BM - 1) / (2 * k2BM));
   const int n_tiles = static_cast<int>((a.n + BN - 1) / BN);
   const int k_blocks = static_cast<int>((a.k + k2BK - 1) / k2BK);
@@ -213,7 +284,7 @@ static cudaError_t launch_2cta(const vb_gemm_args& a, cudaStream_t stream) {
   long long pairs = sms / 2;
   if (tiles < pairs) pairs = tiles;
   gemm_tcgen05_2cta_kernel<BN><<<static_cast<unsigned>(2 * pairs), k2Threads, Cfg::kSmemBytes, stream>>>(
-      ta, tb, ep, k_blocks, m_tiles, n_tiles);
+      ta, tb, tc, ep, k_blocks, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
