@@ -323,6 +323,10 @@ def gpu_arm(args) -> None:
         decode = measure_decode(model, device)  # independent workload, measured before the training loop
     trainer = DataParallelTrainer(model, lr=1e-5, weight_decay=0.05, max_grad_norm=1.0,
                                   grad_accum=GRAD_ACCUM)
+    if world > 1:  # NCCL communicator / NVLink connection set-up happens on the first collective
+        for _ in range(2):
+            dist.all_reduce(trainer.flat.grads)
+        torch.cuda.synchronize()
     host = synthetic_batch(1000 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(device) for k, v in host.items()}
