@@ -1,9 +1,23 @@
 #!/usr/bin/env bash
 # Builds eilev_b200/libvideoblip_b200.so for sm_100a (in-tree, travels with gpurun).
+# One nvcc per translation unit, in parallel; objects are rebuilt only when a source is newer.
 set -euo pipefail
 cd "$(dirname "$0")"
 SRC=eilev_b200/csrc
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math \
-  -Xcompiler -fPIC -shared ${NVCC_EXTRA:-} \
-  $SRC/api.cu $SRC/gemm_tcgen05.cu $SRC/gemm_tcgen05_2cta.cu $SRC/gemm_generic.cu $SRC/attention.cu $SRC/attention_tcgen05.cu $SRC/layernorm.cu \
-  $SRC/elementwise.cu $SRC/decode.cu -o eilev_b200/libvideoblip_b200.so
+OBJ=build/obj
+mkdir -p "$OBJ"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math -Xcompiler -fPIC ${NVCC_EXTRA:-}"
+UNITS="api gemm_tcgen05 gemm_tcgen05_2cta gemm_generic attention attention_tcgen05 layernorm elementwise decode"
+newest_hdr=$(ls -t $SRC/*.cuh $SRC/*.h include/*.h build.sh | head -1)
+pids=()
+for u in $UNITS; do
+  o="$OBJ/$u.o"
+  if [ ! -f "$o" ] || [ "$SRC/$u.cu" -nt "$o" ] || [ "$newest_hdr" -nt "$o" ]; then
+    nvcc $FLAGS -c "$SRC/$u.cu" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+OBJS=""
+for u in $UNITS; do OBJS="$OBJS $OBJ/$u.o"; done
+nvcc -shared -gencode arch=compute_100a,code=sm_100a $OBJS -o eilev_b200/libvideoblip_b200.so

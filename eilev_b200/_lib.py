@@ -71,6 +71,8 @@ SIGNATURES: dict[str, list] = {
     "vb_splice_bwd": [vp, vp, vp, i64, i64, i64, vp],
     "vb_cross_entropy": [vp, i32, vp, vp, vp, vp, i64, i64, i64, i64, vp],
     "vb_cross_entropy_bwd": [vp, i32, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
+    "vb_attention_merge": [vp, vp, i64, vp, vp, i64, vp, i64, i64, i64, vp],
+    "vb_token_logprob": [vp, i32, vp, vp, vp, i64, i64, i64, vp],
     "vb_transpose": [vp, vp, i64, i64, i64, i64, vp],
     "vb_convert": [vp, i32, vp, i32, i64, vp],
     "vb_act_bwd": [vp, vp, vp, i32, i64, vp],
@@ -80,6 +82,8 @@ SIGNATURES: dict[str, list] = {
     "vb_adamw": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, vp],
     "vb_sumsq": [vp, i64, vp, vp],
     "vb_gemv": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, f32, i64, i32, i32, vp, vp, f32, vp],
+    "vb_decode_embed": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
+    "vb_decode_step": [vp, vp, i32, i32, vp, vp],
     "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, vp],
     "vb_paged_kv_write": [vp, vp, i64, vp, vp, vp, i64, i64, i64, i64, i64, vp],
 }

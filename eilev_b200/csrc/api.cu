@@ -152,6 +152,21 @@ int vb_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t
                              st(stream)));
 }
 
+int vb_attention_merge(const void* o1, const float* lse1, int64_t s1, const void* o2, const float* lse2,
+                       int64_t s2, void* out, int64_t rows, int64_t heads, int64_t d, void* stream) {
+  VB_CHECK("vb_attention_merge",
+           vb::attn_merge_launch(o1, lse1, s1, o2, lse2, s2, out, rows, heads, d, st(stream)));
+}
+
+int vb_token_logprob(const void* logits, int32_t logits_dtype, const int64_t* row_index,
+                     const int64_t* targets, float* out, int64_t n, int64_t vocab, int64_t ldl,
+                     void* stream) {
+  VB_CHECK("vb_token_logprob",
+           vb::token_logprob_launch(logits, logits_dtype, reinterpret_cast<const long long*>(row_index),
+                                    reinterpret_cast<const long long*>(targets), out, n, vocab, ldl,
+                                    st(stream)));
+}
+
 int vb_transpose(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in,
                  int64_t ld_out, void* stream) {
   VB_CHECK("vb_transpose", vb::transpose_launch(in, out, rows, cols, ld_in, ld_out, st(stream)));
@@ -201,6 +216,19 @@ int vb_gemv(const void* x, const void* w, const float* bias, const void* residua
   if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return fail_msg("vb_gemv", "ln_gamma/ln_beta must come together");
   VB_CHECK("vb_gemv", vb::gemv_launch(x, w, bias, residual, y, m, n, k, ldx, ldw, ldy, ldr, alpha,
                                       alpha_cols, epilogue, out_dtype, ln_gamma, ln_beta, ln_eps, st(stream)));
+}
+
+int vb_decode_embed(const int64_t* tokens, const void* embed, const void* pos_table, int32_t* n_valid,
+                    int32_t* ctx_len, void* x, int64_t batch, int64_t dim, int64_t vocab,
+                    int64_t pos_rows, int64_t pos_offset, void* stream) {
+  VB_CHECK("vb_decode_embed",
+           vb::decode_embed_launch(reinterpret_cast<const long long*>(tokens), embed, pos_table, n_valid,
+                                   ctx_len, x, batch, dim, vocab, pos_rows, pos_offset, st(stream)));
+}
+
+int vb_decode_step(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int32_t n_ops, int32_t m,
+                   uint32_t* barrier, void* stream) {
+  VB_CHECK("vb_decode_step", vb::decode_step_launch(ops_host, ops_dev, n_ops, m, barrier, st(stream)));
 }
 
 int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,

@@ -89,6 +89,15 @@ VB_DEVICE void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both sides 16-byte aligned); completion is
+// signalled on `bar` as transaction bytes.
+VB_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 VB_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 // wait until at most N committed bulk groups of this thread still READ their smem source
 template <int N>
@@ -293,6 +302,46 @@ VB_DEVICE float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
+// serialization attribute may become resident while its predecessor is still running.
+// Everything before pdl_wait() must touch only data no earlier kernel of the stream writes
+// (weights); pdl_wait() returns once the predecessor grid has completed and flushed.
+VB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+VB_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Asks the L2 to fetch [p, p+bytes) from HBM (bytes % 16 == 0, p 16-byte aligned).
+VB_DEVICE void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+}  // namespace vb
+
+#include <cstdlib>
+namespace vb {
+// VB_PDL=0 turns programmatic dependent launch off (A/B measurements).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("VB_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+// Launch `kern` allowing it to overlap the tail of the previous kernel of the stream.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(static_cast<Args&&>(args))...);
 }
 
 }  // namespace vb

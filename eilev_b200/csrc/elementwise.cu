@@ -523,6 +523,98 @@ cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ classify helpers
+// Merges two softmax-attention partial results over disjoint key sets (the shared prompt
+// context and the per-class continuation): out = (e^{l1} o1 + e^{l2} o2) / (e^{l1} + e^{l2}).
+// Rows are (H*D)-wide and contiguous; partial i keeps its log-sum-exp as (rows/S_i, H, S_i).
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(const __nv_bfloat16* o1, const float* lse1, long long s1, const __nv_bfloat16* o2,
+                  const float* lse2, long long s2, __nv_bfloat16* out, long long rows, int heads, int d) {
+  const long long hd = static_cast<long long>(heads) * d;
+  const long long total = rows * hd;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / hd;
+    const int h = static_cast<int>((i % hd) / d);
+    const float l1 = lse1[((r / s1) * heads + h) * s1 + r % s1];
+    const float l2 = lse2[((r / s2) * heads + h) * s2 + r % s2];
+    const float m = fmaxf(l1, l2);
+    float w1 = 0.0f, w2 = 0.0f;
+    if (m != -INFINITY) {
+      w1 = __expf(l1 - m);
+      w2 = __expf(l2 - m);
+    }
+    const float den = w1 + w2;
+    const float inv = den > 0.0f ? 1.0f / den : 0.0f;
+    out[i] = __float2bfloat16((w1 * __bfloat162float(o1[i]) + w2 * __bfloat162float(o2[i])) * inv);
+  }
+}
+
+cudaError_t attn_merge_launch(const void* o1, const float* lse1, long long s1, const void* o2,
+                              const float* lse2, long long s2, void* out, long long rows,
+                              long long heads, long long d, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if (s1 <= 0 || s2 <= 0 || rows % s1 != 0 || rows % s2 != 0) return cudaErrorInvalidValue;
+  const long long total = rows * heads * d;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  attn_merge_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o1), lse1, s1, reinterpret_cast<const __nv_bfloat16*>(o2),
+      lse2, s2, reinterpret_cast<__nv_bfloat16*>(out), rows, static_cast<int>(heads), static_cast<int>(d));
+  return cudaGetLastError();
+}
+
+// out[i] = log softmax(logits[row_i, :])[target_i]  (0 when target_i is outside [0, vocab):
+// the ignore_index rows of nn.CrossEntropyLoss(reduction="none")); row_i = row_index[i] or i.
+template <typename T>
+__global__ void __launch_bounds__(256)
+token_logprob_kernel(const T* logits, const long long* row_index, const long long* targets, float* out,
+                     long long vocab, long long ldl) {
+  const long long i = blockIdx.x;
+  const long long target = targets[i];
+  if (target < 0 || target >= vocab) {
+    if (threadIdx.x == 0) out[i] = 0.0f;
+    return;
+  }
+  const T* row = logits + (row_index != nullptr ? row_index[i] : i) * ldl;
+  __shared__ float red[8];
+  float mx = -INFINITY;
+  for (long long c = threadIdx.x; c < vocab; c += 256) mx = fmaxf(mx, to_f32<T>(row[c]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) mx = fmaxf(mx, red[j]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (long long c = threadIdx.x; c < vocab; c += 256) sum += __expf(to_f32<T>(row[c]) - mx);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += red[j];
+    out[i] = to_f32<T>(row[target]) - (mx + logf(tot));
+  }
+}
+
+cudaError_t token_logprob_launch(const void* logits, int dtype, const long long* row_index,
+                                 const long long* targets, float* out, long long n, long long vocab,
+                                 long long ldl, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (dtype == VB_BF16)
+    token_logprob_kernel<__nv_bfloat16><<<static_cast<unsigned>(n), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(logits), row_index, targets, out, vocab, ldl);
+  else if (dtype == VB_F32)
+    token_logprob_kernel<float><<<static_cast<unsigned>(n), 256, 0, s>>>(
+        reinterpret_cast<const float*>(logits), row_index, targets, out, vocab, ldl);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ splice launchers
 cudaError_t embed_splice_launch(const long long* ids, const long long* attn, const long long* vmask,
                                 const void* embed, const void* feats, const void* pos_table,

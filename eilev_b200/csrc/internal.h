@@ -42,6 +42,12 @@ cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels
                           const float* row_lse, const int* n_valid, const float* grad_scale,
                           void* dlogits, long long batch, long long seq, long long vocab,
                           long long ldl, long long ldd, cudaStream_t s);
+cudaError_t attn_merge_launch(const void* o1, const float* lse1, long long s1, const void* o2,
+                              const float* lse2, long long s2, void* out, long long rows,
+                              long long heads, long long d, cudaStream_t s);
+cudaError_t token_logprob_launch(const void* logits, int dtype, const long long* row_index,
+                                 const long long* targets, float* out, long long n, long long vocab,
+                                 long long ldl, cudaStream_t s);
 cudaError_t transpose_launch(const void* in, void* out, long long rows, long long cols,
                              long long ld_in, long long ld_out, cudaStream_t s);
 cudaError_t convert_launch(const void* src, int sd, void* dst, int dd, long long n, cudaStream_t s);
@@ -63,6 +69,12 @@ cudaError_t gemv_launch(const void* x, const void* w, const float* bias, const v
                         long long ldw, long long ldy, long long ldr, float alpha,
                         long long alpha_cols, int epilogue, int out_dtype, const float* ln_gamma,
                         const float* ln_beta, float ln_eps, cudaStream_t s);
+cudaError_t decode_embed_launch(const long long* tokens, const void* embed, const void* pos_table,
+                                int* n_valid, int* ctx_len, void* x, long long batch, long long dim,
+                                long long vocab, long long pos_rows, long long pos_offset,
+                                cudaStream_t s);
+cudaError_t decode_step_launch(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int n_ops, int m,
+                               unsigned* barrier, cudaStream_t s);
 cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* v_cache,
                                           const int* page_table, const int* ctx_len,
                                           const int* first_valid, void* out, float* workspace,

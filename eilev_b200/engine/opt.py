@@ -19,6 +19,8 @@ train mode under HF Trainer) uses counter-hash masks regenerated in the backward
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import ops
@@ -194,6 +196,86 @@ def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None
     return ops.splice_bwd(dx, ctx["slot"], ctx["n_features"])
 
 
+# --------------------------------------------------------------------------- classify
+def opt_classify(lm, cache: PackCache, prompt_ids, prompt_mask, video_mask, video_features,
+                 class_ids, class_mask=None, class_batch_size: int | None = None) -> torch.Tensor:
+    """Mean log-likelihood of every class continuation given the (left-padded) prompt:
+    eilev/model/v2.py:326-501 (``classify`` step 4 + ``_calc_class_log_likelihood``).
+
+    The prompt runs once; its per-layer K/V stay where the fused QKV GEMM wrote them.  Class
+    tokens of all (sequence, class) pairs form one (B*C*Lc)-row batch; in every layer they
+    attend (i) to the shared prompt K/V — one non-causal launch per layer with all C*Lc
+    queries of a sequence stacked, instead of the reference's ``repeat_interleave`` of the
+    cache (:457-460) — and (ii) causally to their own continuation; the two partial
+    softmaxes are merged by their log-sum-exps.  Returns (B, num_classes) f32."""
+    cfg = lm.config
+    _check_cfg(cfg)
+    w = pack_opt(lm, cache, need_backward=False)
+    dim, heads, hd = _dims(cfg)
+    act = ops.EPI_RELU if cfg.activation_function == "relu" else ops.EPI_GELU
+    scaling = hd ** -0.5
+    b, lp = prompt_ids.shape
+    n_cls, lc = class_ids.shape
+    dev = prompt_ids.device
+    if prompt_mask is None:
+        prompt_mask = torch.ones_like(prompt_ids)
+    if class_mask is None:
+        class_mask = torch.ones_like(class_ids)
+    class_ids = class_ids.to(dev).contiguous()
+    class_mask = class_mask.to(dev).to(torch.long).contiguous()
+
+    prompt_kv: list = []
+    out = opt_forward(lm, cache, prompt_ids, prompt_mask, video_mask, video_features, want_logits=False,
+                      kv_sink=lambda li, k, v: prompt_kv.append((k, v)))
+    status = out["status"]
+    last = out["final"][:, -1, :].contiguous()
+    prompt_logits = (ops.gemv(last, w["embed"], out_dtype=torch.float32) if b <= 16
+                     else ops.gemm(last, w["embed"], out_dtype=torch.float32))  # (B, V)
+    key_mask = prompt_mask.to(torch.uint8).contiguous()
+    n_valid = prompt_mask.sum(dim=1).tolist()  # positions of the continuation start here
+
+    # labels: class token j is scored by the logits of position j-1 (the prompt's last
+    # position for j == 0); padded class tokens are ignored (v2.py:474-494)
+    labels = torch.where(class_mask != 0, class_ids, torch.full_like(class_ids, -100))
+    step = n_cls if class_batch_size is None else int(class_batch_size)
+    chunks = []
+    for c0 in range(0, n_cls, step):
+        ids_c, mask_c, lab_c = class_ids[c0:c0 + step], class_mask[c0:c0 + step], labels[c0:c0 + step]
+        ncc = ids_c.shape[0]
+        rows = b * ncc * lc
+        hidden = torch.cat([
+            ops.embed_splice(ids_c, mask_c, None, w["embed"], None, w["pos"], 2 + int(n_valid[bi]),
+                             want_embeds=False)[1].view(1, ncc * lc, dim)
+            for bi in range(b)], dim=0)
+        x = hidden.view(rows, dim)
+        for li, lw in enumerate(w["layers"]):
+            y = ops.layernorm(x, lw["ln1_g"], lw["ln1_b"], 1e-5)
+            qkv = ops.gemm(y, lw["qkv_w"], lw["qkv_b"], alpha=scaling, alpha_cols=dim)
+            pk, pv = prompt_kv[li]
+            q_all = qkv.view(b, ncc * lc, 3 * dim)[:, :, :dim]
+            o1, lse1 = ops.attention(q_all, pk, pv, heads, 1.0, causal=False, key_mask=key_mask, need_lse=True)
+            qc = qkv.view(b * ncc, lc, 3 * dim)
+            o2, lse2 = ops.attention(qc[:, :, :dim], qc[:, :, dim:2 * dim], qc[:, :, 2 * dim:], heads, 1.0,
+                                     causal=True, need_lse=True)
+            o = ops.attention_merge(o1, lse1, o2, lse2, heads)
+            x_mid = ops.gemm(o.view(rows, dim), lw["out_w"], lw["out_b"], residual=x)
+            y2 = ops.layernorm(x_mid, lw["ln2_g"], lw["ln2_b"], 1e-5)
+            f1 = ops.gemm(y2, lw["fc1_w"], lw["fc1_b"], epilogue=act)
+            x = ops.gemm(f1, lw["fc2_w"], lw["fc2_b"], residual=x_mid)
+        final = ops.layernorm(x, w["lnf_g"], w["lnf_b"], 1e-5)
+        logits = ops.gemm(final, w["embed"], out_dtype=torch.float32)  # (rows, V), tied head
+        # row (b, c, j) scores class token j+1
+        nxt = torch.cat([lab_c[:, 1:], torch.full_like(lab_c[:, :1], -100)], dim=1)
+        lp_rest = ops.token_logprob(logits, nxt.unsqueeze(0).expand(b, -1, -1).contiguous())
+        first_rows = torch.arange(b, device=dev, dtype=torch.long).repeat_interleave(ncc)
+        lp_first = ops.token_logprob(prompt_logits, lab_c[:, 0].repeat(b).contiguous(), first_rows)
+        total = lp_rest.view(b, ncc, lc).sum(dim=-1) + lp_first.view(b, ncc)
+        lengths = mask_c.sum(dim=-1).to(torch.float32).unsqueeze(0)
+        chunks.append(total / lengths)
+    res = torch.cat(chunks, dim=1)
+    return res, status
+
+
 # --------------------------------------------------------------------------- decode
 class PagedKV:
     """Paged KV cache: per layer K and V pools of (n_pages, page_size, H*D) bf16 and one page
@@ -219,7 +301,7 @@ class PagedKV:
         for pool in (self.k, self.v):
             for li in range(len(pool)):
                 view = pool[li].view(self.batch, mp, self.page_size, -1)
-                pool[li] = view[idx].reshape(pool[li].shape).contiguous()
+                pool[li].copy_(view[idx].reshape(pool[li].shape))  # in place: pointers stay valid
 
 
 def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features,
@@ -244,31 +326,120 @@ def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
     n_valid = am.sum(dim=1).to(torch.int32).contiguous()
     state = dict(kv=kv, ctx_len=torch.full((b,), l, dtype=torch.int32, device=input_ids.device),
                  first_valid=first_valid, n_valid=n_valid, status=out["status"])
-    splits = 8 if l + max_new_tokens > 256 else 2
+    total = l + max_new_tokens
+    splits = 16 if total > 512 else (8 if total > 256 else 2)
     state["attn_splits"] = splits
     state["attn_ws"] = torch.empty(b * heads * splits * (hd + 2), dtype=torch.float32, device=input_ids.device)
     state["attn_cnt"] = torch.zeros(b * heads, dtype=torch.int32, device=input_ids.device)
     return logits, state
 
 
+class DecodeProgram:
+    """One decode step as a ``vb_decode_op`` program for the persistent kernel
+    (``vb_decode_step``): embed, 32 x [LN+qkv, paged attention, out_proj+residual,
+    LN+fc1+act, fc2+residual], final LN + tied head.  All activation buffers are owned by the
+    program, so the step is allocation-free and CUDA-graph replayable."""
+
+    def __init__(self, lm, cache: PackCache, state: dict, batch: int, device) -> None:
+        import numpy as np
+
+        cfg = lm.config
+        w = pack_opt(lm, cache, need_backward=False)
+        dim, heads, hd = _dims(cfg)
+        act = ops.EPI_RELU if cfg.activation_function == "relu" else ops.EPI_GELU
+        kv: PagedKV = state["kv"]
+        ffn = w["layers"][0]["fc1_w"].shape[0]
+        vocab = w["embed"].shape[0]
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.tokens = torch.zeros(batch, dtype=torch.long, device=device)
+        self.xa, self.xb = torch.empty((batch, dim), **bf), torch.empty((batch, dim), **bf)
+        self.qkv = torch.empty((batch, 3 * dim), **bf)
+        self.att = torch.empty((batch, dim), **bf)
+        self.f1 = torch.empty((batch, ffn), **bf)
+        self.logits = torch.empty((batch, vocab), dtype=torch.float32, device=device)
+        # (head, sequence, split) units: at most two 128-thread units per SM in one round
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        splits = max(1, min(16, (2 * sms) // max(1, heads * batch)))
+        max_ctx = kv.page_size * kv.max_pages
+        chunk_cap = (max_ctx + splits - 1) // splits
+        self.ws = torch.empty(batch * heads * splits * (hd + 2), dtype=torch.float32, device=device)
+        self.cnt = torch.zeros(batch * heads, dtype=torch.int32, device=device)
+        self.barrier = torch.zeros(1, dtype=torch.int32, device=device)
+        self.batch = batch
+        self._keep = (w, kv, state["n_valid"], state["ctx_len"], state["first_valid"])
+
+        recs = []
+
+        def rec(kind, ptr=(), i64=(), i32=(), f32=()):
+            r = np.zeros((), dtype=ops.op_dtype())
+            r["type"] = kind
+            for name, vals in (("ptr", ptr), ("i64", i64), ("i32", i32), ("f32", f32)):
+                for j, v in enumerate(vals):
+                    r[name][j] = 0 if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
+            recs.append(r)
+
+        def gemv(x, wt, bias, y, *, residual=None, ln=(None, None), alpha=1.0, alpha_cols=0, epilogue=ops.EPI_NONE):
+            n, k = wt.shape
+            rec(ops.OP_GEMV, ptr=(wt, bias, residual, x, y, ln[0], ln[1]),
+                i64=(n, k, wt.stride(0), x.stride(0), y.stride(0), 0 if residual is None else residual.stride(0),
+                     alpha_cols),
+                f32=(alpha, 1e-5), i32=(epilogue, 1 if y.dtype == torch.float32 else 0))
+
+        rec(ops.OP_EMBED, ptr=(self.tokens, w["embed"], w["pos"], state["n_valid"], state["ctx_len"], self.xa),
+            i64=(dim, vocab, w["pos"].shape[0], 2))
+        for li, lw in enumerate(w["layers"]):
+            gemv(self.xa, lw["qkv_w"], lw["qkv_b"], self.qkv, ln=(lw["ln1_g"], lw["ln1_b"]),
+                 alpha=hd ** -0.5, alpha_cols=dim)
+            rec(ops.OP_ATTN, ptr=(self.qkv, kv.k[li], kv.v[li], kv.table, state["ctx_len"], state["first_valid"],
+                                  self.att, self.ws, self.cnt),
+                i32=(heads, hd, kv.page_size, kv.max_pages, splits, chunk_cap), f32=(1.0,))
+            gemv(self.att, lw["out_w"], lw["out_b"], self.xb, residual=self.xa)
+            gemv(self.xb, lw["fc1_w"], lw["fc1_b"], self.f1, ln=(lw["ln2_g"], lw["ln2_b"]), epilogue=act)
+            gemv(self.f1, lw["fc2_w"], lw["fc2_b"], self.xa, residual=self.xb)
+        gemv(self.xa, w["embed"], None, self.logits, ln=(w["lnf_g"], w["lnf_b"]))
+        self.host = np.stack(recs)
+        self.dev = torch.from_numpy(self.host.view(np.uint8).reshape(-1).copy()).to(device)
+
+    def step(self, tokens: torch.Tensor) -> torch.Tensor:
+        if tokens.data_ptr() != self.tokens.data_ptr():
+            self.tokens.copy_(tokens)
+        ops.decode_step(self.host, self.dev, self.batch, self.barrier)
+        return self.logits
+
+
+def _decode_program(lm, cache: PackCache, state: dict, batch: int, device):
+    """The persistent-kernel program of this generation state, or None when the shapes are
+    outside what ``vb_decode_step`` takes (batch > 8, feature sizes not a multiple of 64)."""
+    if "program" not in state:
+        prog = None
+        dim = lm.config.hidden_size
+        if (batch <= 8 and dim % 64 == 0 and lm.config.ffn_dim % 64 == 0
+                and os.environ.get("VB_DECODE_PERSISTENT", "1") != "0"):
+            prog = DecodeProgram(lm, cache, state, batch, device)
+        state["program"] = prog
+    return state["program"]
+
+
 def opt_decode_step(lm, cache: PackCache, tokens: torch.Tensor, state: dict) -> torch.Tensor:
     """One token per sequence: tokens (B,) int64 -> next-position logits f32 (B, V).
     Stream-ordered and allocation-stable, so it can be captured into a CUDA graph
-    (``DecodeGraph``): the per-sequence counters are advanced in place."""
+    (``DecodeGraph``): the per-sequence counters are advanced in place.  Batches of up to 8
+    sequences run as ONE persistent launch (``DecodeProgram``); larger ones (beam search over
+    several prompts) go op by op."""
     cfg = lm.config
+    b = tokens.shape[0]
+    if b > 16:
+        raise NotImplementedError("decode batch (incl. beams) > 16 is not supported yet")
+    prog = _decode_program(lm, cache, state, b, tokens.device)
+    if prog is not None:
+        return prog.step(tokens)
     w = pack_opt(lm, cache, need_backward=False)
     dim, heads, hd = _dims(cfg)
     act = ops.EPI_RELU if cfg.activation_function == "relu" else ops.EPI_GELU
     scaling = hd ** -0.5
     kv: PagedKV = state["kv"]
-    b = tokens.shape[0]
-    if b > 16:
-        raise NotImplementedError("decode batch (incl. beams) > 16 is not supported yet")
     # position of the new token = number of valid tokens so far - 1 + offset 2 (HF :350-354)
-    pos = (state["n_valid"].to(torch.long) + 2)
-    state["n_valid"].add_(1)
-    state["ctx_len"].add_(1)
-    x = ops.add(w["embed"][tokens].contiguous(), w["pos"][pos].contiguous())
+    x = ops.decode_embed(tokens, w["embed"], w["pos"], state["n_valid"], state["ctx_len"], 2)
     for li, lw in enumerate(w["layers"]):
         qkv = ops.gemv(x, lw["qkv_w"], lw["qkv_b"], alpha=scaling, alpha_cols=dim,
                        ln=(lw["ln1_g"], lw["ln1_b"], 1e-5))

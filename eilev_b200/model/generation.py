@@ -232,7 +232,7 @@ def _beam_search(lm, logits, state, batch, nb, max_new, min_new, eos_ids, pad_id
             break
         state["kv"].reorder(src)
         for key in ("ctx_len", "first_valid", "n_valid"):
-            state[key] = state[key][src].contiguous()
+            state[key].copy_(state[key][src])  # in place: the decode program holds these pointers
         logits = E_opt.opt_decode_step(lm, lm._pack, next_tokens.view(-1), state)
 
     out = []

@@ -536,7 +536,35 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         return generation.generate(self, input_ids, attention_mask, video_input_mask, feats,
                                    **generate_kwargs)
 
-    # ------------------------------------------------------------------ classify (next row, §8f)
-    def classify(self, *args, **kwargs):
-        raise NotImplementedError(
-            "classify() (v2.py:326-501) is the first 'next' row of the scope table and is not built yet")
+    # ------------------------------------------------------------------ classify
+    @torch.no_grad()
+    def classify(
+        self,
+        prompt_input_ids: torch.Tensor,
+        class_input_ids: torch.Tensor,
+        prompt_attention_mask: torch.Tensor | None = None,
+        pixel_values: torch.Tensor | None = None,
+        prompt_video_input_mask: torch.Tensor | None = None,
+        class_attention_mask: torch.Tensor | None = None,
+        class_batch_size: int | None = None,
+    ) -> torch.Tensor:
+        """Same contract as v2.py:326-424: mean log-likelihood (batch, num_classes) of every
+        class continuation given the left-padded prompt (decoder-only LM only, :351)."""
+        assert self.config.use_decoder_only_language_model  # v2.py:351
+        if pixel_values is not None:
+            assert prompt_video_input_mask is not None  # v2.py:355
+            prompt_video_input_mask = prompt_video_input_mask.bool()
+        _require_cuda(prompt_input_ids, "VideoBlipForConditionalGeneration.classify")
+        feats = None
+        if pixel_values is not None:
+            _require_cuda(pixel_values, "VideoBlipForConditionalGeneration.classify")
+            feats, _, _ = self._video_features(pixel_values, False, train=False)
+        if prompt_attention_mask is None:
+            prompt_attention_mask = torch.ones_like(prompt_input_ids)
+        lm = self.language_model
+        scores, status = E_opt.opt_classify(
+            lm, lm._pack, prompt_input_ids, prompt_attention_mask,
+            prompt_video_input_mask if pixel_values is not None else None, feats,
+            class_input_ids, class_attention_mask, class_batch_size)
+        self._last_splice_status = status
+        return scores  # f32 (the reference returns the LM dtype; f32 keeps the sums exact)

@@ -198,6 +198,42 @@ def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: boo
     return dq, dk, dv
 
 
+def attention_merge(o1: torch.Tensor, lse1: torch.Tensor, o2: torch.Tensor, lse2: torch.Tensor,
+                    heads: int) -> torch.Tensor:
+    """Merges two attention partials over disjoint key sets.  o_i: (B_i, S_i, H*D) bf16
+    contiguous with B_1*S_1 == B_2*S_2 rows in the same order; lse_i: (B_i, H, S_i) f32."""
+    _need(o1, torch.bfloat16, "attention_merge.o1")
+    _need(o2, torch.bfloat16, "attention_merge.o2")
+    assert o1.is_contiguous() and o2.is_contiguous() and lse1.is_contiguous() and lse2.is_contiguous()
+    rows = o1.shape[0] * o1.shape[1]
+    assert rows == o2.shape[0] * o2.shape[1] and o1.shape[2] == o2.shape[2]
+    hd = o1.shape[2]
+    out = torch.empty_like(o2)
+    check(_lib.lib().vb_attention_merge(o1.data_ptr(), lse1.data_ptr(), o1.shape[1], o2.data_ptr(),
+                                        lse2.data_ptr(), o2.shape[1], out.data_ptr(), rows, heads,
+                                        hd // heads, _stream()), "vb_attention_merge")
+    return out
+
+
+def token_logprob(logits: torch.Tensor, targets: torch.Tensor, row_index: torch.Tensor | None = None) -> torch.Tensor:
+    """log_softmax(logits[row])[target] per target (0 for targets outside the vocabulary)."""
+    _need(logits, None, "token_logprob.logits")
+    _need(targets, torch.int64, "token_logprob.targets")
+    assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in (torch.bfloat16, torch.float32)
+    targets = targets.contiguous().view(-1)
+    if row_index is not None:
+        _need(row_index, torch.int64, "token_logprob.row_index")
+        row_index = row_index.contiguous().view(-1)
+        assert row_index.numel() == targets.numel()
+    else:
+        assert targets.numel() == logits.shape[0]
+    out = torch.empty(targets.numel(), dtype=torch.float32, device=logits.device)
+    check(_lib.lib().vb_token_logprob(logits.data_ptr(), _DT[logits.dtype], _ptr(row_index),
+                                      targets.data_ptr(), out.data_ptr(), targets.numel(), logits.shape[1],
+                                      logits.stride(0), _stream()), "vb_token_logprob")
+    return out
+
+
 def patch_gather(pixels: torch.Tensor, patch: int, kpad: int) -> torch.Tensor:
     """(NV, C, T, H, W) -> (NV*T*gh*gw, kpad) bf16 patch matrix."""
     _need(pixels, None, "patch_gather.pixels")
@@ -378,6 +414,50 @@ def gemv(x: torch.Tensor, w: torch.Tensor, bias=None, *, residual=None, epilogue
                              epilogue, _DT[out_dtype], _ptr(ln[0]) if ln else None,
                              _ptr(ln[1]) if ln else None, float(ln[2]) if ln else 0.0, _stream()), "vb_gemv")
     return y
+
+
+def decode_embed(tokens: torch.Tensor, embed: torch.Tensor, pos_table: torch.Tensor,
+                 n_valid: torch.Tensor, ctx_len: torch.Tensor, pos_offset: int = 2) -> torch.Tensor:
+    """x[b] = embed[tokens[b]] + pos_table[n_valid[b] + pos_offset]; advances n_valid / ctx_len
+    in place (HF:opt/modeling_opt.py:45-70,350-354)."""
+    _need(embed, torch.bfloat16, "decode_embed.embed")
+    _need(pos_table, torch.bfloat16, "decode_embed.pos_table")
+    _need(tokens, torch.int64, "decode_embed.tokens")
+    _need(n_valid, torch.int32, "decode_embed.n_valid")
+    _need(ctx_len, torch.int32, "decode_embed.ctx_len")
+    assert embed.is_contiguous() and pos_table.is_contiguous() and tokens.is_contiguous()
+    b, dim = tokens.shape[0], embed.shape[1]
+    x = torch.empty((b, dim), dtype=torch.bfloat16, device=tokens.device)
+    check(_lib.lib().vb_decode_embed(tokens.data_ptr(), embed.data_ptr(), pos_table.data_ptr(),
+                                     n_valid.data_ptr(), ctx_len.data_ptr(), x.data_ptr(), b, dim,
+                                     embed.shape[0], pos_table.shape[0], pos_offset, _stream()),
+          "vb_decode_embed")
+    return x
+
+
+# ---- decode-step programs (vb_decode_op records, include/videoblip_b200.h) ----------------
+OP_GEMV, OP_ATTN, OP_EMBED = 1, 2, 3
+_OP_DTYPE = None
+
+
+def op_dtype():
+    """numpy mirror of ``vb_decode_op`` (192 bytes)."""
+    global _OP_DTYPE
+    if _OP_DTYPE is None:
+        import numpy as np
+        _OP_DTYPE = np.dtype([("type", "<i4"), ("i32", "<i4", (7,)), ("ptr", "<u8", (10,)),
+                              ("i64", "<i8", (8,)), ("f32", "<f4", (4,))])
+        assert _OP_DTYPE.itemsize == 192
+    return _OP_DTYPE
+
+
+def decode_step(ops_host, ops_dev: torch.Tensor, m: int, barrier: torch.Tensor) -> None:
+    """Runs a decode-step program (numpy record array + its device copy) as one persistent
+    cooperative launch."""
+    _need(ops_dev, torch.uint8, "decode_step.ops_dev")
+    _need(barrier, torch.int32, "decode_step.barrier")
+    check(_lib.lib().vb_decode_step(ops_host.ctypes.data, ops_dev.data_ptr(), int(ops_host.shape[0]), int(m),
+                                    barrier.data_ptr(), _stream()), "vb_decode_step")
 
 
 def paged_kv_write(k, v, k_cache, v_cache, page_table, page_size: int) -> None:

@@ -243,6 +243,23 @@ int vb_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
 /* out[0] += sum(x^2) over n f32 elements (global grad norm for clipping). */
 int vb_sumsq(const float* x, int64_t n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------ classify
+ * eilev/model/v2.py:326-501 scores every class continuation against ONE cached prompt.  The
+ * reference replicates the prompt's K/V num_classes times (:457-460); here each class token
+ * attends to the shared prompt K/V once (vb_attention_fwd, non-causal, key_mask, lse) and to
+ * its own continuation (causal, lse), and the two partial softmaxes are merged:
+ *   out = (e^{lse1} o1 + e^{lse2} o2) / (e^{lse1} + e^{lse2}).
+ * o1, o2, out: (rows, heads*d) bf16 contiguous; lse_i: f32 laid out (rows / s_i, heads, s_i)
+ * exactly as vb_attention_fwd writes it for a batch of rows/s_i sequences of s_i queries. */
+int vb_attention_merge(const void* o1, const float* lse1, int64_t s1, const void* o2, const float* lse2,
+                       int64_t s2, void* out, int64_t rows, int64_t heads, int64_t d, void* stream);
+/* out[i] = log_softmax(logits[row_index ? row_index[i] : i, :])[targets[i]], or 0 when
+ * targets[i] is outside [0, vocab) (ignore_index): nn.CrossEntropyLoss(reduction="none")
+ * negated, eilev/model/v2.py:486-494.  logits bf16|f32 with row stride ldl. */
+int vb_token_logprob(const void* logits, int32_t logits_dtype, const int64_t* row_index,
+                     const int64_t* targets, float* out, int64_t n, int64_t vocab, int64_t ldl,
+                     void* stream);
+
 /* ------------------------------------------------------------------------ decode */
 /* y[m, n] = act(alpha_n * (LN?(x)[m,:] . W[n,:] + bias[n])) (+ residual) for small m (<= 16):
  * weight-streaming kernel for token-by-token generation (HBM bound).  bf16 in/out,
@@ -254,6 +271,52 @@ int vb_gemv(const void* x, const void* w, const float* bias, const void* residua
             int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,
             float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype,
             const float* ln_gamma, const float* ln_beta, float ln_eps, void* stream);
+
+/* Prologue of one generation step: x[b,:] = embed[tokens[b],:] + pos_table[n_valid[b] +
+ * pos_offset,:] (bf16), then n_valid[b] += 1 and ctx_len[b] += 1 (device-resident per-sequence
+ * counters, so the step is CUDA-graph replayable).  tokens: (B) int64.
+ * HF:opt/modeling_opt.py:45-70 (learned positions, offset 2), :350-354, :363. */
+int vb_decode_embed(const int64_t* tokens, const void* embed, const void* pos_table, int32_t* n_valid,
+                    int32_t* ctx_len, void* x, int64_t batch, int64_t dim, int64_t vocab,
+                    int64_t pos_rows, int64_t pos_offset, void* stream);
+
+/* ---- one generated token as ONE launch ------------------------------------------------
+ * A decode step is a short program of vb_decode_op records executed by a persistent
+ * cooperative kernel (one CTA per SM) with grid barriers between the ops; while a CTA waits
+ * at a barrier the first weight loads of the next projection are already in flight, so the
+ * HBM stream does not drain at every op boundary (~160 per token otherwise).
+ * HF:opt/modeling_opt.py:321-396 at tgt_len == 1, all layers.
+ *
+ * Slot meaning per op type (unused slots must be zero):
+ *  VB_OP_GEMV   y = act(alpha_n (LN?(x) . W^T + bias)) (+ residual), as vb_gemv with m rows
+ *    ptr: 0 W (n,k) bf16 | 1 bias f32 | 2 residual bf16 | 3 x bf16 | 4 y | 5 ln_gamma | 6 ln_beta
+ *    i64: 0 n | 1 k | 2 ldw | 3 ldx | 4 ldy | 5 ldr | 6 alpha_cols     f32: 0 alpha | 1 ln_eps
+ *    i32: 0 epilogue (VB_EPI_*) | 1 output is f32
+ *  VB_OP_ATTN   as vb_paged_decode_attention with batch = m
+ *    ptr: 0 qkv | 1 k_cache | 2 v_cache | 3 page_table | 4 ctx_len | 5 first_valid | 6 out
+ *         | 7 workspace | 8 counters
+ *    i32: 0 heads | 1 d | 2 page_size | 3 max_pages | 4 splits | 5 ceil(page_size*max_pages/splits)
+ *    f32: 0 scale
+ *  VB_OP_EMBED  as vb_decode_embed with batch = m
+ *    ptr: 0 tokens | 1 embed | 2 pos_table | 3 n_valid | 4 ctx_len | 5 x
+ *    i64: 0 dim | 1 vocab | 2 pos_rows | 3 pos_offset */
+#define VB_OP_GEMV 1
+#define VB_OP_ATTN 2
+#define VB_OP_EMBED 3
+typedef struct vb_decode_op {
+  int32_t type;
+  int32_t i32[7];
+  const void* ptr[10];
+  int64_t i64[8];
+  float f32[4];
+} vb_decode_op; /* 192 bytes */
+/* Runs ops[0..n_ops) for m <= 8 sequences.  ops_host / ops_dev: the same records in host
+ * and in device memory (the host copy sizes the launch; the kernel reads the device copy).
+ * barrier: one device uint32 owned by this program (zeroed by the call).  Every GEMV op
+ * needs k % 64 == 0 and 16-byte aligned rows; returns an error otherwise (callers fall back
+ * to the per-op entry points above).  Stream-ordered, CUDA-graph capturable. */
+int vb_decode_step(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int32_t n_ops, int32_t m,
+                   uint32_t* barrier, void* stream);
 
 /* Append new K/V rows into a paged cache and run one-query-per-sequence attention over
  * it.  Cache pages: (n_pages, page_size, H*D) bf16 for K and for V; page_table (B,

@@ -237,6 +237,41 @@ def greedy_generate(sd, config, input_ids, attention_mask, pixel_values, video_i
     return torch.stack(new, dim=1)
 
 
+@torch.no_grad()
+def classify(sd, config, prompt_input_ids, class_input_ids, prompt_attention_mask=None, pixel_values=None,
+             prompt_video_input_mask=None, class_attention_mask=None):
+    """v2.py:326-501 — mean log-likelihood (batch, num_classes) of each class continuation
+    after the (left-padded) prompt.  The reference feeds the class tokens on top of the
+    prompt's KV cache (:462-467); without a cache that is the decoder run on the
+    concatenation [prompt ; class] under the concatenated mask (:443-455) — positions come
+    from the mask cumsum either way (HF:opt/modeling_opt.py:350-354).  Class token j is
+    scored by the logits of the position before it (the prompt's last position for j = 0,
+    :469-478); padded class tokens are ignored (:480-481) and the sum is divided by the
+    class length (:497-501).  Small cases only (one decoder pass per (row, class))."""
+    feats = None
+    if pixel_values is not None:
+        feats = video_features(sd, config, pixel_values)[0]
+    prompt_emb = splice(sd, prompt_input_ids, prompt_video_input_mask, feats)
+    if prompt_attention_mask is None:
+        prompt_attention_mask = torch.ones_like(prompt_input_ids)
+    if class_attention_mask is None:
+        class_attention_mask = torch.ones_like(class_input_ids)
+    table = sd["language_model.model.decoder.embed_tokens.weight"].float()
+    b, lp = prompt_input_ids.shape
+    n_cls, lc = class_input_ids.shape
+    out = torch.zeros(b, n_cls)
+    for bi in range(b):
+        for ci in range(n_cls):
+            emb = torch.cat([prompt_emb[bi:bi + 1], table[class_input_ids[ci]][None]], dim=1)
+            mask = torch.cat([prompt_attention_mask[bi:bi + 1], class_attention_mask[ci:ci + 1]], dim=1)
+            hidden = opt_decoder(sd, config.text_config, emb, mask)
+            logp = F.log_softmax(F.linear(hidden[0, lp - 1:lp + lc - 1], table), dim=-1)  # (lc, V)
+            tok = logp.gather(1, class_input_ids[ci][:, None])[:, 0]
+            valid = class_attention_mask[ci] != 0
+            out[bi, ci] = (tok * valid).sum() / valid.sum()
+    return out
+
+
 def sane_init_(state_dict, seed=1234, std=0.02):
     """Seeded, numerically sane re-initialisation (HF's default init is degenerate for this
     model: ViT std 1e-10, zero query tokens — SURVEY §0.8).  Linear/conv/embedding weights

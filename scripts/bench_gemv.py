@@ -9,9 +9,10 @@ from eilev_b200 import ops  # noqa: E402
 def ev():
     return torch.cuda.Event(enable_timing=True)
 
-m = 1
+m = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1
 layers = 32
 shapes = [("qkv", 7680, 2560), ("out", 2560, 2560), ("fc1", 10240, 2560), ("fc2", 2560, 10240)]
+head = (torch.randn(50272, 2560, device="cuda") * 0.02).to(torch.bfloat16)
 W = {n: [(torch.randn(nn, k, device="cuda") * 0.02).to(torch.bfloat16) for _ in range(layers)] for n, nn, k in shapes}
 g = torch.ones(2560, device="cuda"); b = torch.zeros(2560, device="cuda")
 for name, nn, k in shapes:
@@ -24,6 +25,13 @@ for name, nn, k in shapes:
         e.record(); torch.cuda.synchronize()
         us = s.elapsed_time(e) * 1e3 / layers
         print(f"{name:4s} N={nn:5d} K={k:5d} ln={ln is not None!s:5s}: {us:7.1f} us/launch  {nn * k * 2 / us / 1e3:7.1f} GB/s", flush=True)
+xh = torch.randn(m, 2560, device="cuda").to(torch.bfloat16)
+for _ in range(3): ops.gemv(xh, head, out_dtype=torch.float32)
+s, e = ev(), ev(); s.record()
+for _ in range(5): ops.gemv(xh, head, out_dtype=torch.float32, ln=(g, b, 1e-5))
+e.record(); torch.cuda.synchronize()
+us = s.elapsed_time(e) * 1e3 / 5
+print(f"head N=50272 K= 2560 (L2-warm x5): {us:7.1f} us/launch  {50272 * 2560 * 2 / us / 1e3:7.1f} GB/s", flush=True)
 # graph of the whole chain
 x = torch.randn(m, 2560, device="cuda").to(torch.bfloat16)
 PREFETCH = "--prefetch" in sys.argv

@@ -393,3 +393,112 @@ def test_gemv_and_paged_decode():
     mask[0, :5] = 0
     ref = _attn_ref(qkv[:, None, :hd], k_all, v_all, heads, 1.0, False, mask)[:, 0]
     _close(out, ref, atol=0.02, rtol=0.02, what="paged decode")
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 2560, 10240), (1, 1003, 2560), (2, 10240, 2560), (4, 50272, 2560),
+                                   (8, 2560, 2560), (16, 2560, 2560), (16, 3000, 1024), (1, 77, 256),
+                                   (3, 2560, 10240), (8, 640, 10240)])
+def test_gemv_bulk_ring_shapes(m, n, k):
+    """Weight-streaming GEMV (bulk-copy ring kernel and its fall-backs) across the decode
+    shapes: ragged N, every M bucket, K walked in slices, f32 output, residual + bias."""
+    ops = _ops()
+    x, w = _rand(m, k, seed=70), _rand(n, k, scale=0.03, seed=71)
+    bias = torch.randn(n, device="cuda")
+    res = _rand(m, n, seed=72)
+    ref = x.float() @ w.float().t() + bias
+    tol = dict(atol=0.02 * (k / 2560) ** 0.5 + 0.03, rtol=0.02)
+    _close(ops.gemv(x, w, bias), ref, what="gemv", **tol)
+    _close(ops.gemv(x, w, bias, residual=res, epilogue=ops.EPI_RELU), torch.relu(ref) + res.float(),
+           what="gemv relu+res", **tol)
+    y32 = ops.gemv(x, w, out_dtype=torch.float32)
+    assert y32.dtype == torch.float32
+    _close(y32, x.float() @ w.float().t(), atol=2e-3 * (k / 256) ** 0.5, rtol=1e-3, what="gemv f32")
+    if k <= 4096:
+        g, bt = torch.randn(k, device="cuda"), torch.randn(k, device="cuda")
+        xn = torch.nn.functional.layer_norm(x.float(), (k,), g, bt, 1e-5).to(torch.bfloat16).float()
+        _close(ops.gemv(x, w, bias, ln=(g, bt, 1e-5)), xn @ w.float().t() + bias, what="ln+gemv",
+               atol=0.08, rtol=0.02)
+
+
+def test_gemv_back_to_back_pdl_chain():
+    """A chain of dependent GEMVs on one stream (programmatic dependent launch lets each
+    prefetch weights under its predecessor): results must equal the serial composition."""
+    ops = _ops()
+    x = _rand(1, 2560, seed=80)
+    ws = [_rand(2560, 2560, scale=0.02, seed=81 + i) for i in range(6)]
+    y = x
+    ref = x.float()
+    for w in ws:
+        y = ops.gemv(y, w, residual=y)
+        ref = (ref @ w.float().t() + ref).to(torch.bfloat16).float()
+    _close(y, ref, atol=0.05, rtol=0.03, what="gemv chain")
+
+
+def test_decode_embed_advances_counters():
+    ops = _ops()
+    emb, pos = _rand(100, 256, seed=90), _rand(40, 256, seed=91)
+    tok = torch.tensor([3, 99, 0], device="cuda")
+    nv = torch.tensor([5, 0, 30], dtype=torch.int32, device="cuda")
+    cl = torch.tensor([9, 1, 31], dtype=torch.int32, device="cuda")
+    x = ops.decode_embed(tok, emb, pos, nv, cl, 2)
+    ref = emb[tok].float() + pos[torch.tensor([7, 2, 32], device="cuda")].float()
+    _close(x, ref, atol=0.02, rtol=0.01, what="decode_embed")
+    assert nv.tolist() == [6, 1, 31] and cl.tolist() == [10, 2, 32]
+
+
+def test_paged_decode_long_context_splits():
+    ops = _ops()
+    heads, d, page, b, l = 8, 80, 64, 2, 1000
+    hd = heads * d
+    max_pages = 17
+    kc = torch.zeros(b * max_pages, page, hd, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    table = torch.arange(b * max_pages, dtype=torch.int32, device="cuda").view(b, max_pages).contiguous()
+    kv = _rand(b, l, 2 * hd, seed=92)
+    ops.paged_kv_write(kv[:, :, :hd], kv[:, :, hd:], kc, vc, table, page)
+    qkv = _rand(b, 3 * hd, seed=93)
+    ctx = torch.full((b,), l + 1, dtype=torch.int32, device="cuda")
+    first = torch.tensor([17, 0], dtype=torch.int32, device="cuda")
+    k_all = torch.cat([kv[:, :, :hd], qkv[:, None, hd:2 * hd]], 1)
+    v_all = torch.cat([kv[:, :, hd:], qkv[:, None, 2 * hd:]], 1)
+    mask = torch.ones(b, l + 1, dtype=torch.uint8, device="cuda")
+    mask[0, :17] = 0
+    ref = _attn_ref(qkv[:, None, :hd], k_all, v_all, heads, 1.0, False, mask)[:, 0]
+    for splits in (1, 8, 16, 33):
+        out = ops.paged_decode_attention(qkv, kc, vc, table, ctx, first, heads, page, 1.0, splits=splits)
+        _close(out, ref, atol=0.02, rtol=0.02, what=f"paged decode splits={splits}")
+
+
+def test_attention_merge_equals_joint_softmax():
+    """classify(): attention over [prompt keys ; own continuation] == merge of the two partials."""
+    ops = _ops()
+    heads, d, b, ncls, lc, lp = 4, 80, 2, 3, 5, 37
+    hd = heads * d
+    q = _rand(b * ncls, lc, hd, seed=100)
+    kc_, vc_ = _rand(b * ncls, lc, hd, seed=101), _rand(b * ncls, lc, hd, seed=102)
+    kp, vp = _rand(b, lp, hd, seed=103), _rand(b, lp, hd, seed=104)
+    pmask = torch.ones(b, lp, dtype=torch.uint8, device="cuda")
+    pmask[1, :9] = 0
+    o1, l1 = ops.attention(q.view(b, ncls * lc, hd), kp, vp, heads, 0.3, key_mask=pmask, need_lse=True)
+    o2, l2 = ops.attention(q, kc_, vc_, heads, 0.3, causal=True, need_lse=True)
+    got = ops.attention_merge(o1, l1, o2, l2, heads)
+    k_all = torch.cat([kp.repeat_interleave(ncls, 0), kc_], 1)
+    v_all = torch.cat([vp.repeat_interleave(ncls, 0), vc_], 1)
+    m_all = torch.cat([pmask.repeat_interleave(ncls, 0), torch.ones(b * ncls, lc, dtype=torch.uint8, device="cuda")], 1)
+    ref = _attn_ref(q, k_all, v_all, heads, 0.3, True, m_all)
+    _close(got, ref, atol=0.02, rtol=0.02, what="attention merge")
+
+
+def test_token_logprob():
+    ops = _ops()
+    logits = torch.randn(7, 1000, device="cuda") * 3
+    tg = torch.tensor([0, 999, -100, 5, 1000, 17, 3], device="cuda")
+    got = ops.token_logprob(logits, tg)
+    ref = torch.log_softmax(logits, -1)
+    for i, t in enumerate(tg.tolist()):
+        want = ref[i, t].item() if 0 <= t < 1000 else 0.0
+        assert abs(got[i].item() - want) < 1e-4, (i, got[i].item(), want)
+    rows = torch.tensor([6, 6, 0], device="cuda")
+    got2 = ops.token_logprob(logits.to(torch.bfloat16), torch.tensor([1, 2, 3], device="cuda"), rows)
+    ref2 = torch.log_softmax(logits.to(torch.bfloat16).float(), -1)
+    assert torch.allclose(got2, torch.stack([ref2[6, 1], ref2[6, 2], ref2[0, 3]]), atol=1e-3)

@@ -303,3 +303,79 @@ def test_real_dims_shallow_against_oracle():
     # yardstick: the reference itself, bf16 vs fp32 on CPU (tests/golden/bf16_yardstick.py),
     # differs by 4.3 % (tiny_opt) / 8.9-9.6 % (small_opt) in global gradient rel-L2
     assert r["grad_rel_l2"] < 0.10, r
+
+
+@pytest.mark.parametrize("name", ["tiny_opt", "small_opt"])
+@pytest.mark.parametrize("class_batch_size", [None, 2])
+def test_classify_matches_reference_golden(name, class_batch_size):
+    """classify (v2.py:326-501): mean class log-likelihoods vs the real reference's scores.
+    Tolerance: |d| <= 0.08 nats on scores of magnitude 3-7 (bf16 LM, fp32 log-softmax)."""
+    fx, cfg = load(name)
+    cx = torch.load(GOLDEN / f"classify_{name}.pt", weights_only=False)
+    m = build(cfg, fx["state_dict"])
+    p = cuda(fx["gen_inputs"])
+    got = m.classify(p["input_ids"], cx["class_input_ids"].cuda(), p["attention_mask"], p["pixel_values"],
+                     p["video_input_mask"], cx["class_attention_mask"].cuda(), class_batch_size=class_batch_size)
+    m.check_splice()
+    assert got.shape == cx["scores"].shape
+    d = max_abs(got, cx["scores"])
+    _dump(f"classify/{name}/{class_batch_size}", max_abs=d, ref=cx["scores"].tolist(), got=got.cpu().tolist())
+    assert d < 0.08, (got, cx["scores"])
+    # text-only prompt and default masks
+    got2 = m.classify(p["input_ids"], cx["class_input_ids"].cuda(), p["attention_mask"])
+    assert got2.shape == cx["scores"].shape and torch.isfinite(got2).all()
+    with pytest.raises(AssertionError):  # v2.py:355
+        m.classify(p["input_ids"], cx["class_input_ids"].cuda(), pixel_values=p["pixel_values"])
+
+
+@pytest.mark.parametrize("batch", [1, 3, 8])
+def test_persistent_decode_step_matches_op_by_op(batch):
+    """vb_decode_step (one cooperative launch per token: embed, per-layer projections,
+    paged attention, head, grid barriers in between) against the same step issued op by op,
+    on a left-padded batch, eagerly and through the CUDA graph.  The two paths share the
+    kernels' arithmetic, so the logits agree to bf16 rounding of the split-merge order."""
+    from transformers import OPTConfig
+    from eilev_b200.engine import opt as E
+    from eilev_b200.model.v2 import OPTForCausalLM
+    from oracle import videoblip_ref as R
+
+    torch.manual_seed(0)
+    cfg = OPTConfig(hidden_size=128, num_hidden_layers=3, ffn_dim=256, num_attention_heads=2, vocab_size=300,
+                    max_position_embeddings=256, word_embed_proj_dim=128)
+    lm = OPTForCausalLM(cfg)
+    sd = R.sane_init_({k: v.clone() for k, v in lm.state_dict().items()}, seed=9, std=0.08)
+    sd["lm_head.weight"] = sd["model.decoder.embed_tokens.weight"]
+    lm.load_state_dict(sd)
+    lm = lm.to("cuda", torch.bfloat16).eval()
+    g = torch.Generator().manual_seed(batch)
+    L = 70
+    ids = torch.randint(4, 290, (batch, L), generator=g)
+    am = torch.ones(batch, L, dtype=torch.long)
+    for b in range(1, batch):
+        am[b, : 3 * b] = 0  # left padding
+        ids[b, : 3 * b] = 1
+    ids, am = ids.cuda(), am.cuda()
+    steps = 5
+    forced = torch.randint(4, 290, (steps, batch), generator=g).cuda()  # same tokens on every path
+    outs = {}
+    for mode in ("persistent", "op_by_op", "graph"):
+        with torch.no_grad():
+            logits, state = E.opt_prefill(lm, lm._pack, ids, am, None, None, steps + 2)
+            if mode == "op_by_op":
+                state["program"] = None
+            else:
+                assert E._decode_program(lm, lm._pack, state, batch, ids.device) is not None
+            runner = E.DecodeGraph(lm, lm._pack, state, batch, ids.device) if mode == "graph" else None
+            seq = [logits.clone()]
+            for i in range(steps):
+                tok = forced[i]
+                logits = runner.step(tok) if runner is not None else E.opt_decode_step(lm, lm._pack, tok, state)
+                seq.append(logits.clone())
+            outs[mode] = (torch.stack(seq), state["ctx_len"].clone(), state["n_valid"].clone())
+    ref = outs["op_by_op"]
+    for mode in ("persistent", "graph"):
+        got = outs[mode]
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+        d = max_abs(got[0], ref[0])
+        _dump(f"persistent_decode/{mode}/b{batch}", max_abs=d, ref_absmax=float(ref[0].abs().max()))
+        assert d < 0.03 * float(ref[0].abs().max()) + 0.02, (mode, d)

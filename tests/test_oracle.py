@@ -95,3 +95,16 @@ def test_oracle_matches_live_reference_random_case():
     out = R.videoblip_forward(model.state_dict(), cfg, **inputs)
     assert torch.allclose(out["logits"], ref.logits, atol=5e-5, rtol=1e-4)
     assert abs(float(out["loss"]) - float(ref.loss)) < 1e-5
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_classify_matches_reference_golden(name):
+    """classify (v2.py:326-501): golden scores come from the real reference's classify
+    (tests/golden/make_golden_classify.py)."""
+    fx, cfg = load(name)
+    cx = torch.load(GOLDEN / f"classify_{name}.pt", weights_only=False)
+    p = fx["gen_inputs"]
+    got = R.classify(fx["state_dict"], cfg, p["input_ids"], cx["class_input_ids"], p["attention_mask"],
+                     p["pixel_values"], p["video_input_mask"], cx["class_attention_mask"])
+    assert got.shape == cx["scores"].shape
+    assert torch.allclose(got, cx["scores"], atol=2e-4, rtol=1e-4), (got, cx["scores"])
