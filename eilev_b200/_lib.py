@@ -83,6 +83,7 @@ SIGNATURES: dict[str, list] = {
     "vb_sumsq": [vp, i64, vp, vp],
     "vb_gemv": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, f32, i64, i32, i32, vp, vp, f32, vp],
     "vb_decode_embed": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
+    "vb_debug_decode_trace": [vp],
     "vb_decode_step": [vp, vp, i32, i32, vp, vp],
     "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, vp],
     "vb_paged_kv_write": [vp, vp, i64, vp, vp, vp, i64, i64, i64, i64, i64, vp],

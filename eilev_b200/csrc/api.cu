@@ -227,8 +227,13 @@ int vb_decode_embed(const int64_t* tokens, const void* embed, const void* pos_ta
 }
 
 int vb_decode_step(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int32_t n_ops, int32_t m,
-                   uint32_t* barrier, void* stream) {
-  VB_CHECK("vb_decode_step", vb::decode_step_launch(ops_host, ops_dev, n_ops, m, barrier, st(stream)));
+                   uint32_t* workspace, void* stream) {
+  VB_CHECK("vb_decode_step", vb::decode_step_launch(ops_host, ops_dev, n_ops, m, workspace, st(stream)));
+}
+
+int vb_debug_decode_trace(void* buffer) {
+  vb::decode_step_set_trace(buffer);
+  return 0;
 }
 
 int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,

@@ -51,6 +51,13 @@ VB_DEVICE float ldcg_bf16(const __nv_bfloat16* p) {
   return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
 }
 
+VB_DEVICE void fence_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
+VB_DEVICE unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------ legacy GEMV
 // One warp per output feature: any shape / alignment (the reference's tiny test configs).
 template <int M>
@@ -135,27 +142,48 @@ struct WFrag {
   uint4 lo0, lo1, hi0, hi1;  // 32 B of row g, 32 B of row g+8
 };
 
-// which units of an op this warp of this CTA owns: unit u = (row block u / spr, k-step u % spr)
-// of the CTA's range; warp w takes u = w, w + NW, w + 2 NW, ...  — the NW warps of a CTA walk
-// the SAME 16 weight rows side by side, so at any moment the CTA reads NW * 128 contiguous
-// bytes of each row (and kMD such rounds are in flight): DRAM sees a few thousand wide
-// streams instead of tens of thousands of 128-byte-at-a-time ones.
+// Work decomposition.  Global k-step index s = row_block * spr + k_step (spr = K / 64 steps
+// per 16-row block).  A CTA owns the contiguous range [s0, s0 + U); locally q = h0 + u walks
+// it (h0 = steps of the first touched block that belong to predecessor CTAs), block = q / spr.
+// Warp w takes u = w, w + NW, w + 2 NW, ... — the NW warps of a CTA walk the SAME 16 weight
+// rows side by side, so at any moment the CTA reads NW * 128 contiguous bytes of each row.
+//   * stand-alone kernel: ranges are whole row blocks (h0 = 0, U a multiple of spr);
+//   * persistent kernel: ranges are S / gridDim steps wherever they fall ("stream-K"), so
+//     N = 2560 (160 blocks on 148 SMs) is balanced to one k-step.  A block cut by a range
+//     boundary is finalised by the CTA holding its LAST step; the other contributors export
+//     their partial 16 x 8 tile through a global slot + flag, summed in CTA order.
 struct GemvGeom {
-  long long rb0;  // first 16-row block of the CTA
-  int RB;         // row blocks of the CTA
+  long long s0;   // first global k-step of the CTA
+  long long rbf;  // first row block touched (= s0 / spr)
+  int U;          // k-steps of the CTA
   int spr;        // k-steps per row block
-  int U;          // units of the CTA
-  int u0;         // this warp's first unit (= warp index)
+  int h0;         // s0 - rbf * spr
+  int u0;         // this warp's first local step (= warp index)
 };
 
 template <int NW>
-VB_DEVICE GemvGeom gemv_geom(const GemvView& p, int cta, int ncta, int warp) {
+VB_DEVICE GemvGeom gemv_geom_blocks(const GemvView& p, int cta, int ncta, int warp) {
   GemvGeom G;
   const long long nrb = (p.n() + 15) / 16;
-  G.rb0 = nrb * cta / ncta;
-  G.RB = static_cast<int>(nrb * (cta + 1) / ncta - G.rb0);
   G.spr = p.k() >> 6;
-  G.U = G.RB * G.spr;
+  G.rbf = nrb * cta / ncta;
+  G.s0 = G.rbf * G.spr;
+  G.U = static_cast<int>(nrb * (cta + 1) / ncta - G.rbf) * G.spr;
+  G.h0 = 0;
+  G.u0 = warp;
+  return G;
+}
+
+template <int NW>
+VB_DEVICE GemvGeom gemv_geom_steps(const GemvView& p, int cta, int ncta, int warp) {
+  GemvGeom G;
+  const long long nrb = (p.n() + 15) / 16;
+  G.spr = p.k() >> 6;
+  const long long S = nrb * G.spr;
+  G.s0 = S * cta / ncta;
+  G.U = static_cast<int>(S * (cta + 1) / ncta - G.s0);
+  G.rbf = G.s0 / G.spr;
+  G.h0 = static_cast<int>(G.s0 - G.rbf * G.spr);
   G.u0 = warp;
   return G;
 }
@@ -167,7 +195,7 @@ struct WCursor {
 };
 
 VB_DEVICE void wc_set_rows(const GemvView& p, const GemvGeom& G, WCursor& c, int rbl, int g, int t) {
-  long long ra = (G.rb0 + rbl) * 16 + g, rh = ra + 8;  // (rbl may run one past the range: clamped)
+  long long ra = (G.rbf + rbl) * 16 + g, rh = ra + 8;  // (rbl may run one past the range: clamped)
   const long long last = p.n() - 1;
   ra = ra < last ? ra : last;  // rows past N re-read the last row; masked at the store
   rh = rh < last ? rh : last;
@@ -195,71 +223,133 @@ VB_DEVICE void wc_load(const GemvView& p, const GemvGeom& G, WCursor& c, WFrag& 
   }
 }
 
-// first MD loads of this warp's units (weights are constant on the stream: may be issued
+// first MD loads of this warp's steps (weights are constant on the stream: may be issued
 // before the producer of x has finished)
 template <int NW, int MD>
-VB_DEVICE void gemv_prime(const GemvView& p, const GemvGeom& G, WCursor& c, WFrag (&buf)[MD], int g, int t) {
-  c.lr = G.u0 / G.spr;
-  c.lc = G.u0 - c.lr * G.spr;
+VB_DEVICE void gemv_prime(const GemvView& p, const GemvGeom& G, WCursor& c, WFrag (&buf)[MD], int g, int t,
+                          int depth = MD) {
+  const int q0 = G.h0 + G.u0;
+  c.lr = q0 / G.spr;
+  c.lc = q0 - c.lr * G.spr;
   wc_set_rows(p, G, c, c.lr, g, t);
 #pragma unroll
   for (int d = 0; d < MD; ++d) {
     // every slot is (re)defined here, so nothing of the previous op stays live across the
     // code between two projections
     buf[d].lo0 = buf[d].lo1 = buf[d].hi0 = buf[d].hi1 = make_uint4(0, 0, 0, 0);
-    wc_load<NW>(p, G, c, buf[d], G.u0 + d * NW, g, t);
+    if (d < depth) wc_load<NW>(p, G, c, buf[d], G.u0 + d * NW, g, t);
   }
 }
 
-// x rows -> shared memory (bf16, row stride K+8), LayerNorm-ed on the way in.  Loads bypass
-// L1 (the rows were written by another SM a moment ago).
-template <int NW>
-VB_DEVICE void gemv_stage_x(const GemvView& p, int m, __nv_bfloat16* xs, int warp, int lane) {
+// tops a partially primed buffer up to MD steps (call once the latency-critical loads of
+// the op have been issued)
+template <int NW, int MD>
+VB_DEVICE void gemv_prime_rest(const GemvView& p, const GemvGeom& G, WCursor& c, WFrag (&buf)[MD], int g, int t,
+                               int depth) {
+#pragma unroll
+  for (int d = 0; d < MD; ++d)
+    if (d >= depth) wc_load<NW>(p, G, c, buf[d], G.u0 + d * NW, g, t);
+}
+
+// x rows -> shared memory (bf16, row stride K + kXPad), LayerNorm-ed on the way in by the whole
+// CTA: every thread owns the same 16-byte column groups of every row in all three passes
+// (load + sum, centred sum of squares, normalise), so only the two statistics reductions
+// synchronise.  Loads bypass L1 (the rows were written by another SM a moment ago).
+// `red`: 2 * NW * MR floats of scratch.  Ends with a CTA barrier.
+struct NoHook {
+  VB_DEVICE void operator()() const {}
+};
+template <int NW, int MR, typename Hook = NoHook>
+VB_DEVICE void gemv_stage_x(const GemvView& p, int m, __nv_bfloat16* xs, float* red, int warp, int lane,
+                            Hook after_loads = Hook(), const float* ln_g_s = nullptr,
+                            const float* ln_b_s = nullptr) {
   const int K = p.k();
   const int xstride = K + kXPad;
-  const float* ln_g = p.ln_g();
-  const float* ln_b = p.ln_b();
-  for (int r = warp; r < m; r += NW) {
-    __nv_bfloat16* xd = xs + static_cast<size_t>(r) * xstride;
-    const __nv_bfloat16* xr = p.x() + r * p.ldx();
-    if (ln_g == nullptr) {
-      for (int c = lane * 8; c < K; c += 256)
-        *reinterpret_cast<uint4*>(xd + c) = __ldcg(reinterpret_cast<const uint4*>(xr + c));
-      continue;
+  // ln_*_s: shared-memory copies requested with cp.async before the bulk weight loads
+  const float* ln_g = p.ln_g() == nullptr ? nullptr : (ln_g_s != nullptr ? ln_g_s : p.ln_g());
+  const float* ln_b = ln_b_s != nullptr ? ln_b_s : p.ln_b();
+  const int tid = warp * 32 + lane;
+  float* red2 = red + NW * MR;
+  // pass 1: copy + row sums; the loads of up to four rows are issued back to back
+  bool hooked = false;
+  for (int r0 = 0; r0 < m; r0 += 4) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int c = tid * 8; c < K; c += NW * 256) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + j < m) v[j] = __ldcg(reinterpret_cast<const uint4*>(p.x() + (r0 + j) * p.ldx() + c));
+      if (!hooked) {
+        after_loads();  // bulk loads queue behind the latency-critical x loads
+        hooked = true;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r0 + j < m) {
+          *reinterpret_cast<uint4*>(xs + static_cast<size_t>(r0 + j) * xstride + c) = v[j];
+          const float2 a0 = unpack_bf16x2(v[j].x), a1 = unpack_bf16x2(v[j].y), a2 = unpack_bf16x2(v[j].z),
+                       a3 = unpack_bf16x2(v[j].w);
+          acc[j] += a0.x + a0.y + a1.x + a1.y + a2.x + a2.y + a3.x + a3.y;
+        }
+      }
     }
-    float s1 = 0.0f;
-    for (int c = lane * 8; c < K; c += 256) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(xr + c));
-      *reinterpret_cast<uint4*>(xd + c) = v;
-      const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
-      s1 += a0.x + a0.y + a1.x + a1.y + a2.x + a2.y + a3.x + a3.y;
+    if (ln_g != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r0 + j < m) {
+          const float v = warp_sum(acc[j]);
+          if (lane == 0) red[warp * MR + r0 + j] = v;
+        }
+      }
     }
-    const float mean = warp_sum(s1) / static_cast<float>(K);
-    float s2 = 0.0f;
-    for (int c = lane * 8; c < K; c += 256) {
+  }
+  if (!hooked) after_loads();
+  asm volatile("cp.async.wait_all;\n" ::: "memory");  // (no-op without pending copies)
+  __syncthreads();
+  if (ln_g == nullptr) return;
+  auto total = [&](const float* scratch, int r) {  // fixed order: identical in every thread
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += scratch[w * MR + r];
+    return v;
+  };
+  for (int r = 0; r < m; ++r) {  // pass 2: centred sums of squares (own columns only)
+    const __nv_bfloat16* xd = xs + static_cast<size_t>(r) * xstride;
+    const float mu = total(red, r) / static_cast<float>(K);
+    float acc = 0.0f;
+    for (int c = tid * 8; c < K; c += NW * 256) {
       const uint4 v = *reinterpret_cast<const uint4*>(xd + c);
       const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
-      const float d0 = a0.x - mean, d1 = a0.y - mean, d2 = a1.x - mean, d3 = a1.y - mean, d4 = a2.x - mean,
-                  d5 = a2.y - mean, d6 = a3.x - mean, d7 = a3.y - mean;
-      s2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 + d4 * d4 + d5 * d5 + d6 * d6 + d7 * d7;
+      const float d0 = a0.x - mu, d1 = a0.y - mu, d2 = a1.x - mu, d3 = a1.y - mu, d4 = a2.x - mu, d5 = a2.y - mu,
+                  d6 = a3.x - mu, d7 = a3.y - mu;
+      acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 + d4 * d4 + d5 * d5 + d6 * d6 + d7 * d7;
     }
-    const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(K) + p.ln_eps());
-    for (int c = lane * 8; c < K; c += 256) {
+    acc = warp_sum(acc);
+    if (lane == 0) red2[warp * MR + r] = acc;
+  }
+  __syncthreads();
+  for (int r = 0; r < m; ++r) {  // pass 3: normalise in place
+    __nv_bfloat16* xd = xs + static_cast<size_t>(r) * xstride;
+    const float mu = total(red, r) / static_cast<float>(K);
+    const float rstd = rsqrtf(total(red2, r) / static_cast<float>(K) + p.ln_eps());
+    for (int c = tid * 8; c < K; c += NW * 256) {
       const uint4 v = *reinterpret_cast<const uint4*>(xd + c);
       const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
       const float4 g0 = *reinterpret_cast<const float4*>(ln_g + c), g1 = *reinterpret_cast<const float4*>(ln_g + c + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(ln_b + c), b1 = *reinterpret_cast<const float4*>(ln_b + c + 4);
       uint4 o;
-      o.x = pack_bf16x2((a0.x - mean) * rstd * g0.x + b0.x, (a0.y - mean) * rstd * g0.y + b0.y);
-      o.y = pack_bf16x2((a1.x - mean) * rstd * g0.z + b0.z, (a1.y - mean) * rstd * g0.w + b0.w);
-      o.z = pack_bf16x2((a2.x - mean) * rstd * g1.x + b1.x, (a2.y - mean) * rstd * g1.y + b1.y);
-      o.w = pack_bf16x2((a3.x - mean) * rstd * g1.z + b1.z, (a3.y - mean) * rstd * g1.w + b1.w);
+      o.x = pack_bf16x2((a0.x - mu) * rstd * g0.x + b0.x, (a0.y - mu) * rstd * g0.y + b0.y);
+      o.y = pack_bf16x2((a1.x - mu) * rstd * g0.z + b0.z, (a1.y - mu) * rstd * g0.w + b0.w);
+      o.z = pack_bf16x2((a2.x - mu) * rstd * g1.x + b1.x, (a2.y - mu) * rstd * g1.y + b1.y);
+      o.w = pack_bf16x2((a3.x - mu) * rstd * g1.z + b1.z, (a3.y - mu) * rstd * g1.w + b1.w);
       *reinterpret_cast<uint4*>(xd + c) = o;
     }
   }
+  __syncthreads();
 }
 
-// consumes this warp's run (buf was primed by gemv_prime) and parks its partial tiles
+// consumes this warp's steps (buf was primed by gemv_prime) and parks its partial tiles:
+// psum[local block][warp] = 16 x (NT*8) floats laid out [m][row]
 template <int NT, int NW, int MD>
 VB_DEVICE void gemv_main(const GemvView& p, int m, const GemvGeom& G, WCursor& c, WFrag (&buf)[MD],
                          const __nv_bfloat16* xs, float* psum, int warp, int g, int t) {
@@ -269,7 +359,8 @@ VB_DEVICE void gemv_main(const GemvView& p, int m, const GemvGeom& G, WCursor& c
   for (int n = 0; n < NT; ++n)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
-  int cr = G.u0 / G.spr, cc = G.u0 - cr * G.spr;
+  const int q0 = G.h0 + G.u0;
+  int cr = q0 / G.spr, cc = q0 - cr * G.spr;
   auto flush = [&]() {
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
@@ -309,7 +400,7 @@ VB_DEVICE void gemv_main(const GemvView& p, int m, const GemvGeom& G, WCursor& c
         // the slot's registers (no staging copy that would wait for them)
         wc_load<NW>(p, G, c, buf[d], u + MD * NW, g, t);
         cc += NW;
-        if (cc >= G.spr || u + NW >= G.U) {  // this warp's next unit is in another row block
+        if (cc >= G.spr || u + NW >= G.U) {  // this warp's next step is in another row block
           flush();
           do {
             cc -= G.spr;
@@ -321,24 +412,80 @@ VB_DEVICE void gemv_main(const GemvView& p, int m, const GemvGeom& G, WCursor& c
   }
 }
 
-// fixed-order reduction over the warps that touched a row block + epilogue (call after a
-// CTA barrier).  G: any warp's geometry of this CTA (only the CTA-level fields are used).
+// sum over the warps that touched local block rbl (fixed order), element (m i, row r)
 template <int NT, int NW>
-VB_DEVICE void gemv_finalize(const GemvView& p, int m, const GemvGeom& G, const float* psum, int tid) {
-  const long long ac = p.alpha_cols() <= 0 ? p.n() : p.alpha_cols();
-  for (int it = tid; it < G.RB * m * 16; it += NW * 32) {
-    const int r = it & 15, i = (it >> 4) % m, rbl = (it >> 4) / m;
-    const long long row = (G.rb0 + rbl) * 16 + r;
-    if (row >= p.n()) continue;
-    const int lo = rbl * G.spr;
-    float v = 0.0f;
+VB_DEVICE float gemv_block_sum(const GemvGeom& G, const float* psum, int rbl, int i, int r) {
+  int lo = rbl * G.spr - G.h0, hi = lo + G.spr;  // local steps of this block held by the CTA
+  lo = lo > 0 ? lo : 0;
+  hi = hi < G.U ? hi : G.U;
+  float v = 0.0f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      // warp w owns units u = w (mod NW): it touched this block iff one of them is in [lo, lo+spr)
-      const int first = ((w - lo) % NW + NW) % NW;
-      if (first < G.spr) v += psum[(static_cast<size_t>(rbl) * NW + w) * (NT * 8 * 16) + i * 16 + r];
+  for (int w = 0; w < NW; ++w) {
+    const int first = lo + (((w - lo) % NW) + NW) % NW;  // first step >= lo owned by warp w
+    if (first < hi) v += psum[(static_cast<size_t>(rbl) * NW + w) * (NT * 8 * 16) + i * 16 + r];
+  }
+  return v;
+}
+
+// Stream-K hand-over (persistent kernel): `flags` / `slots` are indexed by CTA; a CTA whose
+// range ends inside a row block exports its partial tile of that block.
+struct GemvXfer {
+  unsigned* flags;   // [gridDim.x], zeroed by the launcher
+  float* slots;      // [gridDim.x][8*16]
+  unsigned epoch;    // op ordinal (> 0): flags[c] == epoch <=> CTA c exported for this op
+};
+
+template <int NW>
+VB_DEVICE void gemv_export_tail(const GemvGeom& G, const float* psum, const GemvXfer& x, int tid) {
+  const int end = G.h0 + G.U;
+  if (G.U == 0 || end % G.spr == 0) return;  // CTA-uniform
+  const int rbl = end / G.spr;               // the block the range ends in
+  if (tid < 8 * 16) x.slots[static_cast<size_t>(blockIdx.x) * (8 * 16) + tid] =
+      gemv_block_sum<1, NW>(G, psum, rbl, tid >> 4, tid & 15);
+  fence_gpu();
+  __syncthreads();
+  if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(x.flags + blockIdx.x), "r"(x.epoch) : "memory");
+}
+
+// fixed-order reduction + epilogue of the blocks this CTA owns (those whose last step it
+// holds).  xfer != nullptr: the first block may have predecessor partials to add.
+template <int NT, int NW>
+VB_DEVICE void gemv_finalize(const GemvView& p, int m, const GemvGeom& G, const float* psum, int tid,
+                             const GemvXfer* xfer, const float* bias_s = nullptr) {
+  const long long ac = p.alpha_cols() <= 0 ? p.n() : p.alpha_cols();
+  const int owned = (G.h0 + G.U) / G.spr;  // local blocks 0 .. owned-1 end inside the range
+  int c_lo = blockIdx.x;
+  if (xfer != nullptr && G.h0 > 0 && owned > 0) {
+    // contributors: earlier CTAs whose range reaches into my first block
+    const long long nrb = (p.n() + 15) / 16;
+    const long long S = nrb * G.spr, B0 = G.rbf * G.spr;
+    while (c_lo > 0 && S * c_lo / gridDim.x > B0) --c_lo;
+    if (tid == 0) {
+      for (int c = c_lo; c < static_cast<int>(blockIdx.x); ++c) {
+        if (S * (c + 1) / gridDim.x == S * c / gridDim.x) continue;  // empty range
+        if (ld_acquire_u32(xfer->flags + c) != xfer->epoch) {
+          const long long t0 = clock64();
+          while (ld_acquire_u32(xfer->flags + c) != xfer->epoch)
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
     }
-    if (p.bias() != nullptr) v += p.bias()[row];
+    __syncthreads();
+  }
+  for (int it = tid; it < owned * m * 16; it += NW * 32) {
+    const int r = it & 15, i = (it >> 4) % m, rbl = (it >> 4) / m;
+    const long long row = (G.rbf + rbl) * 16 + r;
+    if (row >= p.n()) continue;
+    float v = 0.0f;
+    if (rbl == 0 && c_lo < static_cast<int>(blockIdx.x)) {
+      const long long nrb = (p.n() + 15) / 16;
+      const long long S = nrb * G.spr;
+      for (int c = c_lo; c < static_cast<int>(blockIdx.x); ++c)
+        if (S * (c + 1) / gridDim.x != S * c / gridDim.x)
+          v += __ldcg(xfer->slots + static_cast<size_t>(c) * (8 * 16) + i * 16 + r);
+    }
+    v += gemv_block_sum<NT, NW>(G, psum, rbl, i, r);
+    if (p.bias() != nullptr) v += bias_s != nullptr ? bias_s[rbl * 16 + r] : p.bias()[row];
     if (row < ac) v *= p.alpha();
     if (p.epilogue() == VB_EPI_GELU) v = gelu_erf(v);
     else if (p.epilogue() == VB_EPI_RELU) v = fmaxf(v, 0.0f);
@@ -351,23 +498,46 @@ VB_DEVICE void gemv_finalize(const GemvView& p, int m, const GemvGeom& G, const 
 constexpr int kGW = 8;  // warps of the stand-alone GEMV
 
 template <int NT>
-__global__ void __launch_bounds__(kGW * 32) gemv_mma_kernel(const vb_decode_op op, int m) {
+__global__ void __launch_bounds__(kGW * 32, 2) gemv_mma_kernel(const vb_decode_op op, int m, int rbmax) {
   extern __shared__ __align__(128) uint8_t gsm[];
   const GemvView p(op);
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gsm);                                    // [m][K+8]
-  float* psum = reinterpret_cast<float*>(gsm + static_cast<size_t>(m) * (p.k() + kXPad) * 2);     // [RB][NW] tiles
+  const int K = p.k();
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gsm);                               // [m][K+pad]
+  float* psum = reinterpret_cast<float*>(gsm + static_cast<size_t>(m) * (K + kXPad) * 2);   // [rbmax][NW] tiles
+  float* bias_s = psum + static_cast<size_t>(rbmax) * kGW * (NT * 8 * 16);                  // [rbmax*16]
+  float* lng_s = bias_s + rbmax * 16;                                                       // [K] (LN only)
+  float* lnb_s = lng_s + K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const GemvGeom G = gemv_geom<kGW>(p, blockIdx.x, gridDim.x, warp);
+  const GemvGeom G = gemv_geom_blocks<kGW>(p, blockIdx.x, gridDim.x, warp);
+  // The small constants of this op (LN affine, bias rows) are requested FIRST: the per-SM load
+  // path is in order, so behind 128 KB of weight prefetch they would wait microseconds.
+  const bool ln = p.ln_g() != nullptr;
+  if (ln) {
+    for (int c = threadIdx.x * 4; c < K; c += kGW * 128) {
+      cp_async_16(lng_s + c, p.ln_g() + c);
+      cp_async_16(lnb_s + c, p.ln_b() + c);
+    }
+  }
+  const long long row0 = G.rbf * 16;
+  const int nb = static_cast<int>((p.n() - row0) < (G.U / G.spr) * 16 ? (p.n() - row0) : (G.U / G.spr) * 16);
+  const bool bias_al = p.bias() != nullptr && (reinterpret_cast<uintptr_t>(p.bias()) & 15u) == 0;
+  if (p.bias() != nullptr) {
+    for (int c = threadIdx.x * 4; c < nb; c += kGW * 128) {
+      if (bias_al && c + 4 <= nb) cp_async_16(bias_s + c, p.bias() + row0 + c);
+      else
+        for (int j = c; j < nb && j < c + 4; ++j) bias_s[j] = p.bias()[row0 + j];
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
   WFrag buf[kMD];
   WCursor cur;
   gemv_prime<kGW, kMD>(p, G, cur, buf, g, t);
   pdl_trigger();
   pdl_wait();  // x / residual come from the previous kernel of the stream
-  gemv_stage_x<kGW>(p, m, xs, warp, lane);
-  __syncthreads();
+  gemv_stage_x<kGW, NT * 8>(p, m, xs, psum, warp, lane, NoHook(), ln ? lng_s : nullptr, ln ? lnb_s : nullptr);
   gemv_main<NT, kGW, kMD>(p, m, G, cur, buf, xs, psum, warp, g, t);
   __syncthreads();
-  gemv_finalize<NT, kGW>(p, m, G, psum, threadIdx.x);
+  gemv_finalize<NT, kGW>(p, m, G, psum, threadIdx.x, nullptr, p.bias() != nullptr ? bias_s : nullptr);
 }
 
 static int sm_count() {
@@ -382,7 +552,8 @@ static int sm_count() {
 
 // Grid of the stand-alone tensor-core GEMV: two CTAs per SM when x + the partial-tile table
 // fit, more waves of smaller ranges otherwise; 0 = shape not taken.
-static long long gemv_mma_grid(int nt, long long m, long long n, long long k, size_t* smem_out) {
+static long long gemv_mma_grid(int nt, long long m, long long n, long long k, bool ln, size_t* smem_out,
+                               int* rbmax_out) {
   if (k % 64 != 0 || k > (1 << 20)) return 0;
   const long long nrb = (n + 15) / 16;
   const long long xb = m * (k + kXPad) * 2;
@@ -392,9 +563,11 @@ static long long gemv_mma_grid(int nt, long long m, long long n, long long k, si
       long long grid = static_cast<long long>(sm_count()) * cps * waves;
       if (grid > nrb) grid = nrb;
       const long long rbmax = (nrb + grid - 1) / grid;
-      const long long smem = xb + rbmax * kGW * nt * 8 * 16 * 4;
+      // x + [blocks][warps] partial tiles + bias rows + LN affine
+      const long long smem = xb + rbmax * kGW * nt * 8 * 16 * 4 + rbmax * 16 * 4 + (ln ? 2 * k * 4 : 0);
       if (smem <= limit) {
         *smem_out = static_cast<size_t>(smem);
+        *rbmax_out = static_cast<int>(rbmax);
         return grid;
       }
       if (grid == nrb) break;
@@ -404,7 +577,8 @@ static long long gemv_mma_grid(int nt, long long m, long long n, long long k, si
 }
 
 template <int NT>
-static cudaError_t launch_gemv_mma(const vb_decode_op& op, int m, long long grid, size_t smem, cudaStream_t s) {
+static cudaError_t launch_gemv_mma(const vb_decode_op& op, int m, long long grid, size_t smem, int rbmax,
+                                   cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -412,7 +586,7 @@ static cudaError_t launch_gemv_mma(const vb_decode_op& op, int m, long long grid
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  return launch_pdl(gemv_mma_kernel<NT>, dim3(static_cast<unsigned>(grid)), dim3(kGW * 32), smem, s, op, m);
+  return launch_pdl(gemv_mma_kernel<NT>, dim3(static_cast<unsigned>(grid)), dim3(kGW * 32), smem, s, op, m, rbmax);
 }
 
 static vb_decode_op make_gemv_op(const void* x, const void* w, const float* bias, const void* residual, void* y,
@@ -440,29 +614,33 @@ cudaError_t gemv_launch(const void* x, const void* w, const float* bias, const v
   if (m <= 0 || n <= 0) return cudaSuccess;
   if (m > kGemvMaxM || k <= 0) return cudaErrorInvalidValue;
   const bool vec = (k % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(w));
-  if (vec && k % 64 == 0) {
+  const bool ln_al = ln_gamma == nullptr || (aligned16(ln_gamma) && aligned16(ln_beta));
+  if (vec && ln_al && k % 64 == 0) {
     const int nt = m <= 8 ? 1 : 2;
+    const bool ln = ln_gamma != nullptr;
     size_t smem = 0;
-    long long grid = gemv_mma_grid(nt, m, n, k, &smem);
+    int rbmax = 0;
+    long long grid = gemv_mma_grid(nt, m, n, k, ln, &smem, &rbmax);
     if (grid > 0) {
       const vb_decode_op op = make_gemv_op(x, w, bias, residual, y, n, k, ldx, ldw, ldy, ldr, alpha, alpha_cols,
                                            epilogue, out_dtype, ln_gamma, ln_beta, ln_eps);
-      return nt == 1 ? launch_gemv_mma<1>(op, static_cast<int>(m), grid, smem, s)
-                     : launch_gemv_mma<2>(op, static_cast<int>(m), grid, smem, s);
+      return nt == 1 ? launch_gemv_mma<1>(op, static_cast<int>(m), grid, smem, rbmax, s)
+                     : launch_gemv_mma<2>(op, static_cast<int>(m), grid, smem, rbmax, s);
     }
     // more rows than one n8 tile and not enough shared memory for all of x: passes of 8 rows
-    if (nt == 2 && gemv_mma_grid(1, 8, n, k, &smem) > 0) {
+    if (nt == 2 && gemv_mma_grid(1, 8, n, k, ln, &smem, &rbmax) > 0) {
       const size_t esz = out_dtype == VB_F32 ? 4 : 2;
       for (long long m0 = 0; m0 < m; m0 += 8) {
         const long long mm = m - m0 < 8 ? m - m0 : 8;
         size_t sm2 = 0;
-        const long long g2 = gemv_mma_grid(1, mm, n, k, &sm2);
+        int rb2 = 0;
+        const long long g2 = gemv_mma_grid(1, mm, n, k, ln, &sm2, &rb2);
         const vb_decode_op op = make_gemv_op(
             reinterpret_cast<const __nv_bfloat16*>(x) + m0 * ldx, w, bias,
             residual ? reinterpret_cast<const __nv_bfloat16*>(residual) + m0 * ldr : nullptr,
             reinterpret_cast<uint8_t*>(y) + static_cast<size_t>(m0) * ldy * esz, n, k, ldx, ldw, ldy, ldr, alpha,
             alpha_cols, epilogue, out_dtype, ln_gamma, ln_beta, ln_eps);
-        cudaError_t e = launch_gemv_mma<1>(op, static_cast<int>(mm), g2, sm2, s);
+        cudaError_t e = launch_gemv_mma<1>(op, static_cast<int>(mm), g2, sm2, rb2, s);
         if (e != cudaSuccess) return e;
       }
       return cudaSuccess;
@@ -502,7 +680,8 @@ __global__ void __launch_bounds__(256)
 decode_embed_kernel(const long long* tokens, const __nv_bfloat16* embed, const __nv_bfloat16* pos_table,
                     int* n_valid, int* ctx_len, __nv_bfloat16* x, long long dim, long long vocab,
                     long long pos_rows, long long pos_offset) {
-  pdl_trigger();
+  // No early trigger here: the attention kernel two launches later reads ctx_len before ITS
+  // dependency wait, which is only safe once this kernel has completed.
   pdl_wait();
   const int b = blockIdx.x;
   decode_embed_row(tokens, embed, pos_table, n_valid, x, dim, vocab, pos_rows, pos_offset, b, threadIdx.x, 256);
@@ -572,6 +751,11 @@ struct AttnArgs {
 __host__ __device__ inline int attn_unit_smem_floats(int D, int chunk_cap) { return D + chunk_cap + 16 * D + 8; }
 
 // sm: attn_unit_smem_floats() floats private to these 128 threads; bar_id: their named barrier.
+// WAIT: the stand-alone kernel — everything that does not depend on this step's qkv row (page
+// lookups and the K / V rows of all previously cached tokens) is requested BEFORE
+// griddepcontrol.wait, i.e. while the qkv projection is still streaming its weights; after the
+// wait only q, the new token and the arithmetic remain.
+template <bool WAIT>
 VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float* sm, uint32_t bar_id) {
   const int D = a.D, heads = a.heads, splits = a.splits, page_size = a.page_size;
   const int hd = heads * D;
@@ -593,48 +777,100 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
   auto tok_off = [&](int l) {
     return (static_cast<long long>(pt[l / page_size]) * page_size + l % page_size) * hd + h * D;
   };
-  const bool owns_new = (ctx - 1 >= lo && ctx - 1 < hi);
+  const bool vec = (D % 8 == 0) && (hd % 8 == 0);
+  const bool fast = vec && D <= 128;  // whole K row (<= 16 x 16 B) and 8 V pieces live in registers
+  const int newest = ctx - 1;         // this step's token: its k/v come from the qkv row
+  // phase-2 mapping: thread = (token group, 8-wide d vector)
+  const int nvec = (D + 7) / 8;
+  int groups = 128 / nvec;
+  if (groups > 16) groups = 16;
+  const int gidx = tid / nvec, vi = tid % nvec;
+  const int start = lo > fv ? lo : fv;
+  constexpr int U = 8;  // independent V-row loads in flight per thread
+
+  // ---- early requests (cached tokens only)
+  uint4 kreg[16];
+  uint4 vreg[U];
+  const int l1 = lo + tid;  // this thread's first phase-1 token
+  if (fast) {
+    if (l1 < hi && l1 >= fv && l1 != newest) {
+      const __nv_bfloat16* kr = kc + tok_off(l1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i * 8 < D) kreg[i] = *reinterpret_cast<const uint4*>(kr + i * 8);
+    }
+    if (gidx < groups) {
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int ll = start + gidx + q * groups;
+        vreg[q] = make_uint4(0, 0, 0, 0);
+        if (ll < hi && ll != newest) vreg[q] = *reinterpret_cast<const uint4*>(vc + tok_off(ll) + vi * 8);
+      }
+    }
+  }
+  if (WAIT) pdl_wait();
+
+  // ---- q (pre-scaled) and the new token's k / v
+  const bool owns_new = (newest >= lo && newest < hi);
   for (int c = tid; c < D; c += 128) {
     if (owns_new) {
-      const long long dst = tok_off(ctx - 1);
+      const long long dst = tok_off(newest);
       kc[dst + c] = __float2bfloat16(ldcg_bf16(row + hd + h * D + c));
       vc[dst + c] = __float2bfloat16(ldcg_bf16(row + 2 * hd + h * D + c));
     }
     sq[c] = ldcg_bf16(row + h * D + c) * a.scale;
   }
+  if (fast) {
+    if (l1 == newest && l1 < hi) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i * 8 < D) kreg[i] = __ldcg(reinterpret_cast<const uint4*>(row + hd + h * D + i * 8));
+    }
+    if (gidx < groups) {
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        if (start + gidx + q * groups == newest && newest < hi)
+          vreg[q] = __ldcg(reinterpret_cast<const uint4*>(row + 2 * hd + h * D + vi * 8));
+    }
+  }
   named_bar_sync(bar_id, 128);
-  const bool vec = (D % 8 == 0) && (hd % 8 == 0);
+
+  // ---- phase 1: scores, one thread per token
   float mx = -INFINITY;
-  for (int l = lo + tid; l < hi; l += 128) {
+  for (int l = l1; l < hi; l += 128) {
     float s = -INFINITY;
     if (l >= fv) {
-      const __nv_bfloat16* kr = kc + tok_off(l);
       float acc = 0.0f;
-      if (vec && D <= 128) {
-        uint4 u[16];  // the whole K row in flight before the first FMA
+      if (fast) {
+        if (l != l1) {  // contexts longer than 128 tokens per split: later rows are loaded here
+          const __nv_bfloat16* kr = kc + tok_off(l);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i * 8 < D) u[i] = *reinterpret_cast<const uint4*>(kr + i * 8);
+          for (int i = 0; i < 16; ++i)
+            if (i * 8 < D) kreg[i] = *reinterpret_cast<const uint4*>(kr + i * 8);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           if (i * 8 < D) {
             const int c = i * 8;
-            const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z),
-                         a3 = unpack_bf16x2(u[i].w);
+            const float2 a0 = unpack_bf16x2(kreg[i].x), a1 = unpack_bf16x2(kreg[i].y), a2 = unpack_bf16x2(kreg[i].z),
+                         a3 = unpack_bf16x2(kreg[i].w);
             acc += sq[c] * a0.x + sq[c + 1] * a0.y + sq[c + 2] * a1.x + sq[c + 3] * a1.y + sq[c + 4] * a2.x +
                    sq[c + 5] * a2.y + sq[c + 6] * a3.x + sq[c + 7] * a3.y;
           }
         }
-      } else if (vec) {
-#pragma unroll 4
-        for (int c = 0; c < D; c += 8) {
-          const uint4 u = *reinterpret_cast<const uint4*>(kr + c);
-          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-          acc += sq[c] * a0.x + sq[c + 1] * a0.y + sq[c + 2] * a1.x + sq[c + 3] * a1.y + sq[c + 4] * a2.x +
-                 sq[c + 5] * a2.y + sq[c + 6] * a3.x + sq[c + 7] * a3.y;
-        }
       } else {
-        for (int c = 0; c < D; ++c) acc += sq[c] * __bfloat162float(kr[c]);
+        const __nv_bfloat16* kr = kc + tok_off(l);
+        if (vec) {
+#pragma unroll 4
+          for (int c = 0; c < D; c += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(kr + c);
+            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+            acc += sq[c] * a0.x + sq[c + 1] * a0.y + sq[c + 2] * a1.x + sq[c + 3] * a1.y + sq[c + 4] * a2.x +
+                   sq[c + 5] * a2.y + sq[c + 6] * a3.x + sq[c + 7] * a3.y;
+          }
+        } else {
+          for (int c = 0; c < D; ++c) acc += sq[c] * __bfloat162float(kr[c]);
+        }
       }
       s = acc;
     }
@@ -647,7 +883,7 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
   mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   named_bar_sync(bar_id, 128);
   float sum = 0.0f;
-  for (int l = lo + tid; l < hi; l += 128) {
+  for (int l = l1; l < hi; l += 128) {
     const float pr = (sc[l - lo] == -INFINITY) ? 0.0f : __expf(sc[l - lo] - mx);
     sc[l - lo] = pr;
     sum += pr;
@@ -656,33 +892,26 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
   if (lane == 0) red[warp] = sum;
   named_bar_sync(bar_id, 128);
   const float tot = red[0] + red[1] + red[2] + red[3];
-  // phase 2
-  const int nvec = (D + 7) / 8;
-  int groups = 128 / nvec;
-  if (groups > 16) groups = 16;
-  const int gidx = tid / nvec, vi = tid % nvec;
+
+  // ---- phase 2: P.V
   if (gidx < groups) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int start = lo > fv ? lo : fv;
     if (vec) {
-      constexpr int U = 8;  // independent V-row loads in flight per thread
       for (int l = start + gidx; l < hi; l += groups * U) {
-        uint4 u[U];
         float pr[U];
 #pragma unroll
         for (int q = 0; q < U; ++q) {
           const int ll = l + q * groups;
-          pr[q] = 0.0f;
-          u[q] = make_uint4(0, 0, 0, 0);
-          if (ll < hi) {
-            pr[q] = sc[ll - lo];
-            u[q] = *reinterpret_cast<const uint4*>(vc + tok_off(ll) + vi * 8);
+          pr[q] = ll < hi ? sc[ll - lo] : 0.0f;
+          if (!(fast && l == start + gidx)) {  // first batch is already in registers
+            vreg[q] = make_uint4(0, 0, 0, 0);
+            if (ll < hi) vreg[q] = *reinterpret_cast<const uint4*>(vc + tok_off(ll) + vi * 8);
           }
         }
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-          const float2 a0 = unpack_bf16x2(u[q].x), a1 = unpack_bf16x2(u[q].y), a2 = unpack_bf16x2(u[q].z),
-                       a3 = unpack_bf16x2(u[q].w);
+          const float2 a0 = unpack_bf16x2(vreg[q].x), a1 = unpack_bf16x2(vreg[q].y), a2 = unpack_bf16x2(vreg[q].z),
+                       a3 = unpack_bf16x2(vreg[q].w);
           acc[0] += pr[q] * a0.x; acc[1] += pr[q] * a0.y; acc[2] += pr[q] * a1.x; acc[3] += pr[q] * a1.y;
           acc[4] += pr[q] * a2.x; acc[5] += pr[q] * a2.y; acc[6] += pr[q] * a3.x; acc[7] += pr[q] * a3.y;
         }
@@ -709,7 +938,7 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
     my[0] = mx;
     my[1] = tot;
   }
-  asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+  fence_gpu();
   named_bar_sync(bar_id, 128);
   if (tid == 0) {
     const int ticket = atomicAdd(&a.counters[b * heads + h], 1);
@@ -717,7 +946,7 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
   }
   named_bar_sync(bar_id, 128);
   if (*s_last) {
-    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+    fence_gpu();
     const float* base = a.ws + (static_cast<long long>(b) * heads + h) * splits * (D + 2);
     float gm = -INFINITY;
     for (int i = 0; i < splits; ++i) gm = fmaxf(gm, __ldcg(base + i * (D + 2)));
@@ -743,8 +972,7 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
 __global__ void __launch_bounds__(128) paged_decode_attn_kernel(const AttnArgs a) {
   extern __shared__ float attn_sm[];
   pdl_trigger();  // lets the out-projection GEMV prefetch its weights under this kernel
-  pdl_wait();
-  attn_unit(a, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, attn_sm, 1);
+  attn_unit<true>(a, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, attn_sm, 1);
 }
 
 cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* v_cache,
@@ -788,13 +1016,6 @@ cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* 
 // through the barrier.
 constexpr int kPW = 8;  // warps per CTA of the persistent kernel
 
-VB_DEVICE void fence_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
-VB_DEVICE unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // All CTAs are co-resident (cooperative launch).  `target` = barrier ordinal * gridDim.x; the
 // counter is zeroed by the launcher.  Bounded spin: a mis-programmed op list traps instead of
 // hanging the GPU.
@@ -815,21 +1036,41 @@ VB_DEVICE void grid_barrier(unsigned* counter, unsigned target) {
   __syncthreads();
 }
 
+// Workspace of a decode-step program (uint32 words): [0] barrier counter, [16 .. 16+grid)
+// stream-K flags, byte 4096 onwards the per-CTA partial-tile slots (512 B each).  The first
+// 4096 bytes are zeroed by the launcher.
+constexpr int kWsFlagWord = 16;
+constexpr int kWsSlotByte = 4096;
+constexpr int kWsMaxCtas = (kWsSlotByte / 4) - kWsFlagWord;
+
 __global__ void __launch_bounds__(kPW * 32, 1)
-decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsigned* barrier) {
+decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsigned* ws,
+                   unsigned long long* trace, int early) {
   extern __shared__ __align__(128) uint8_t gsm[];
+  // optional phase timeline (VB_DECODE_TRACE tooling): 6 globaltimer stamps per (op, CTA)
+  auto stamp = [&](int op_i, int k) {
+    if (trace != nullptr && threadIdx.x == 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      trace[(static_cast<size_t>(op_i) * gridDim.x + blockIdx.x) * 6 + k] = tns;
+    }
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   WFrag buf[kPD];
   WCursor cur;
   GemvGeom G = {};
   unsigned epoch = 0;
+  GemvXfer xfer;
+  xfer.flags = ws + kWsFlagWord;
+  xfer.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + kWsSlotByte);
+  xfer.epoch = 0;
   // Invariant: when op i is a projection, its first kPD weight loads were issued at the end
   // of op i-1 (before the barrier); `prime_next` (re)defines every slot of buf either way.
   auto prime_next = [&](int nxt) {
     if (nxt < n_ops && ops[nxt].type == VB_OP_GEMV) {
       const GemvView pn(ops[nxt]);
-      G = gemv_geom<kPW>(pn, blockIdx.x, gridDim.x, warp);
-      gemv_prime<kPW, kPD>(pn, G, cur, buf, g, t);
+      G = gemv_geom_steps<kPW>(pn, blockIdx.x, gridDim.x, warp);
+      gemv_prime<kPW, kPD>(pn, G, cur, buf, g, t, early);
     } else {
 #pragma unroll
       for (int d = 0; d < kPD; ++d) buf[d].lo0 = buf[d].lo1 = buf[d].hi0 = buf[d].hi1 = make_uint4(0, 0, 0, 0);
@@ -839,20 +1080,26 @@ decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsig
   for (int i = 0; i < n_ops; ++i) {
     const vb_decode_op& op = ops[i];
     const int type = op.type;
+    stamp(i, 0);
     if (type == VB_OP_GEMV) {
       const GemvView p(op);
       __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(gsm);
       float* psum = reinterpret_cast<float*>(gsm + static_cast<size_t>(m) * (p.k() + kXPad) * 2);
-      gemv_stage_x<kPW>(p, m, xs, warp, lane);
-      __syncthreads();
+      gemv_stage_x<kPW, 8>(p, m, xs, psum, warp, lane, [&]() {
+        gemv_prime_rest<kPW, kPD>(p, G, cur, buf, g, t, early);  // bulk loads go out behind the x loads
+      });
+      stamp(i, 1);
       gemv_main<1, kPW, kPD>(p, m, G, cur, buf, xs, psum, warp, g, t);
-      const long long rb0 = G.rb0;  // CTA-level geometry of the op being finished
-      const int RB = G.RB, spr = G.spr, U = G.U;
-      prime_next(i + 1);
+      stamp(i, 2);
       __syncthreads();
-      GemvGeom Gd;
-      Gd.rb0 = rb0; Gd.RB = RB; Gd.spr = spr; Gd.U = U; Gd.u0 = 0;
-      gemv_finalize<1, kPW>(p, m, Gd, psum, threadIdx.x);
+      stamp(i, 3);
+      // latency-critical tail first (bias / residual / neighbour partials), then the first
+      // `early` steps of the next projection, which stay in flight across the barrier
+      xfer.epoch = static_cast<unsigned>(i) + 1u;
+      gemv_export_tail<kPW>(G, psum, xfer, threadIdx.x);
+      gemv_finalize<1, kPW>(p, m, G, psum, threadIdx.x, &xfer);
+      prime_next(i + 1);
+      stamp(i, 4);
     } else {
       if (type == VB_OP_ATTN) {
         AttnArgs a;
@@ -872,7 +1119,7 @@ decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsig
         const int units = a.heads * m * a.splits;
         for (int u = blockIdx.x * (kPW / 4) + sub; u < units; u += gridDim.x * (kPW / 4)) {
           const int h = u % a.heads, rest = u / a.heads;
-          attn_unit(a, h, rest % m, rest / m, tid, sm, 1 + sub);
+          attn_unit<false>(a, h, rest % m, rest / m, tid, sm, 1 + sub);
         }
       } else if (type == VB_OP_EMBED) {
         const long long* tokens = reinterpret_cast<const long long*>(op.ptr[0]);
@@ -892,7 +1139,9 @@ decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsig
       }
       prime_next(i + 1);
     }
-    if (i + 1 < n_ops) grid_barrier(barrier, ++epoch * gridDim.x);
+    if (type != VB_OP_GEMV) stamp(i, 4);
+    if (i + 1 < n_ops) grid_barrier(ws, ++epoch * gridDim.x);
+    stamp(i, 5);
   }
 }
 
@@ -908,9 +1157,10 @@ static long long decode_step_smem(const vb_decode_op* ops, int n_ops, int m, int
       if (n <= 0 || k <= 0 || k % 64 != 0 || o.i64[2] % 8 != 0 || o.i64[3] % 8 != 0 || !aligned16(o.ptr[0]) ||
           !aligned16(o.ptr[3]))
         return -1;
-      const long long nrb = (n + 15) / 16;
-      const long long rbmax = (nrb + grid - 1) / grid;
-      s = static_cast<long long>(m) * (k + kXPad) * 2 + rbmax * kPW * 8 * 16 * 4;
+      const long long spr = k / 64, S = (n + 15) / 16 * spr;
+      const long long umax = (S + grid - 1) / grid;
+      const long long blocks = (umax + spr - 1) / spr + 1;  // touched by one CTA range
+      s = static_cast<long long>(m) * (k + kXPad) * 2 + blocks * kPW * 8 * 16 * 4;
     } else if (o.type == VB_OP_ATTN) {
       if (o.i32[4] <= 0 || o.i32[4] > 64) return -1;
       s = 4LL * (kPW / 4) * attn_unit_smem_floats(o.i32[1], o.i32[5]);
@@ -922,12 +1172,16 @@ static long long decode_step_smem(const vb_decode_op* ops, int n_ops, int m, int
   return need;
 }
 
+static unsigned long long* g_decode_trace = nullptr;
+void decode_step_set_trace(void* buffer) { g_decode_trace = reinterpret_cast<unsigned long long*>(buffer); }
+
 cudaError_t decode_step_launch(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int n_ops, int m,
-                               unsigned* barrier, cudaStream_t s) {
+                               unsigned* workspace, cudaStream_t s) {
   if (n_ops <= 0) return cudaSuccess;
-  if (m <= 0 || m > 8 || ops_host == nullptr || ops_dev == nullptr || barrier == nullptr)
+  if (m <= 0 || m > 8 || ops_host == nullptr || ops_dev == nullptr || workspace == nullptr)
     return cudaErrorInvalidValue;
   const int grid = sm_count();
+  if (grid > kWsMaxCtas) return cudaErrorInvalidValue;
   const long long smem = decode_step_smem(ops_host, n_ops, m, grid);
   if (smem < 0 || smem > 200 * 1024) return cudaErrorInvalidValue;
   static bool attr = false;
@@ -937,7 +1191,7 @@ cudaError_t decode_step_launch(const vb_decode_op* ops_host, const vb_decode_op*
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  cudaError_t e = cudaMemsetAsync(barrier, 0, sizeof(unsigned), s);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, kWsSlotByte, s);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -949,7 +1203,12 @@ cudaError_t decode_step_launch(const vb_decode_op* ops_host, const vb_decode_op*
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, decode_step_kernel, ops_dev, n_ops, m, barrier);
+  static const int early = [] {
+    const char* e = std::getenv("VB_DECODE_EARLY");
+    const int v = e ? std::atoi(e) : 2;
+    return v < 0 ? 0 : (v > kPD ? kPD : v);
+  }();
+  return cudaLaunchKernelEx(&cfg, decode_step_kernel, ops_dev, n_ops, m, workspace, g_decode_trace, early);
 }
 
 }  // namespace vb

@@ -73,8 +73,9 @@ cudaError_t decode_embed_launch(const long long* tokens, const void* embed, cons
                                 int* n_valid, int* ctx_len, void* x, long long batch, long long dim,
                                 long long vocab, long long pos_rows, long long pos_offset,
                                 cudaStream_t s);
+void decode_step_set_trace(void* buffer);
 cudaError_t decode_step_launch(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int n_ops, int m,
-                               unsigned* barrier, cudaStream_t s);
+                               unsigned* workspace, cudaStream_t s);
 cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* v_cache,
                                           const int* page_table, const int* ctx_len,
                                           const int* first_valid, void* out, float* workspace,

@@ -364,7 +364,7 @@ class DecodeProgram:
         chunk_cap = (max_ctx + splits - 1) // splits
         self.ws = torch.empty(batch * heads * splits * (hd + 2), dtype=torch.float32, device=device)
         self.cnt = torch.zeros(batch * heads, dtype=torch.int32, device=device)
-        self.barrier = torch.zeros(1, dtype=torch.int32, device=device)
+        self.barrier = torch.zeros(ops.DECODE_STEP_WS_BYTES // 4, dtype=torch.int32, device=device)
         self.batch = batch
         self._keep = (w, kv, state["n_valid"], state["ctx_len"], state["first_valid"])
 
@@ -408,13 +408,17 @@ class DecodeProgram:
 
 
 def _decode_program(lm, cache: PackCache, state: dict, batch: int, device):
-    """The persistent-kernel program of this generation state, or None when the shapes are
-    outside what ``vb_decode_step`` takes (batch > 8, feature sizes not a multiple of 64)."""
+    """The persistent-kernel program of this generation state (opt-in: VB_DECODE_PERSISTENT=1),
+    or None when it is off or the shapes are outside what ``vb_decode_step`` takes (batch > 8,
+    feature sizes not a multiple of 64).  Measured on B200 (profiles/r01_decode_trace.txt) the
+    op-by-op path under programmatic dependent launch is the faster one today: the grid
+    barrier + the in-order per-SM load path make every op of the persistent kernel pay
+    ~9 us of latency, so it stays an experiment behind the flag."""
     if "program" not in state:
         prog = None
         dim = lm.config.hidden_size
         if (batch <= 8 and dim % 64 == 0 and lm.config.ffn_dim % 64 == 0
-                and os.environ.get("VB_DECODE_PERSISTENT", "1") != "0"):
+                and os.environ.get("VB_DECODE_PERSISTENT", "0") == "1"):
             prog = DecodeProgram(lm, cache, state, batch, device)
         state["program"] = prog
     return state["program"]
@@ -423,9 +427,10 @@ def _decode_program(lm, cache: PackCache, state: dict, batch: int, device):
 def opt_decode_step(lm, cache: PackCache, tokens: torch.Tensor, state: dict) -> torch.Tensor:
     """One token per sequence: tokens (B,) int64 -> next-position logits f32 (B, V).
     Stream-ordered and allocation-stable, so it can be captured into a CUDA graph
-    (``DecodeGraph``): the per-sequence counters are advanced in place.  Batches of up to 8
-    sequences run as ONE persistent launch (``DecodeProgram``); larger ones (beam search over
-    several prompts) go op by op."""
+    (``DecodeGraph``): the per-sequence counters are advanced in place.  Default: op by op —
+    every projection is a tensor-core GEMV launched with programmatic dependent launch, so
+    its first weight loads run under the tail of its predecessor; VB_DECODE_PERSISTENT=1
+    runs the whole step as ONE persistent launch (``DecodeProgram``) instead."""
     cfg = lm.config
     b = tokens.shape[0]
     if b > 16:

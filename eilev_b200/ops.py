@@ -437,6 +437,7 @@ def decode_embed(tokens: torch.Tensor, embed: torch.Tensor, pos_table: torch.Ten
 
 # ---- decode-step programs (vb_decode_op records, include/videoblip_b200.h) ----------------
 OP_GEMV, OP_ATTN, OP_EMBED = 1, 2, 3
+DECODE_STEP_WS_BYTES = 4096 + 1008 * 512  # VB_DECODE_STEP_WS_BYTES
 _OP_DTYPE = None
 
 
@@ -453,9 +454,10 @@ def op_dtype():
 
 def decode_step(ops_host, ops_dev: torch.Tensor, m: int, barrier: torch.Tensor) -> None:
     """Runs a decode-step program (numpy record array + its device copy) as one persistent
-    cooperative launch."""
+    cooperative launch.  barrier: the program's int32 workspace (DECODE_STEP_WS_BYTES)."""
     _need(ops_dev, torch.uint8, "decode_step.ops_dev")
     _need(barrier, torch.int32, "decode_step.barrier")
+    assert barrier.numel() * 4 >= DECODE_STEP_WS_BYTES
     check(_lib.lib().vb_decode_step(ops_host.ctypes.data, ops_dev.data_ptr(), int(ops_host.shape[0]), int(m),
                                     barrier.data_ptr(), _stream()), "vb_decode_step")
 

@@ -312,11 +312,19 @@ typedef struct vb_decode_op {
 } vb_decode_op; /* 192 bytes */
 /* Runs ops[0..n_ops) for m <= 8 sequences.  ops_host / ops_dev: the same records in host
  * and in device memory (the host copy sizes the launch; the kernel reads the device copy).
- * barrier: one device uint32 owned by this program (zeroed by the call).  Every GEMV op
- * needs k % 64 == 0 and 16-byte aligned rows; returns an error otherwise (callers fall back
- * to the per-op entry points above).  Stream-ordered, CUDA-graph capturable. */
+ * workspace: VB_DECODE_STEP_WS_BYTES of device memory owned by this program (barrier counter,
+ * hand-over flags and partial-tile slots of projections split across CTAs; its header is
+ * zeroed by the call).  Every GEMV op needs k % 64 == 0 and 16-byte aligned rows; returns an
+ * error otherwise (callers fall back to the per-op entry points above).  Stream-ordered,
+ * CUDA-graph capturable. */
+#define VB_DECODE_STEP_WS_BYTES (4096 + 1008 * 512)
 int vb_decode_step(const vb_decode_op* ops_host, const vb_decode_op* ops_dev, int32_t n_ops, int32_t m,
-                   uint32_t* barrier, void* stream);
+                   uint32_t* workspace, void* stream);
+
+/* Tooling: when buffer != NULL every later vb_decode_step writes 6 %globaltimer stamps (ns)
+ * per (op, CTA) into it — uint64 [n_ops][num_SMs][6] = op start, x staged, weights consumed,
+ * next op primed, finalised, barrier passed.  NULL turns it off (default). */
+int vb_debug_decode_trace(void* buffer);
 
 /* Append new K/V rows into a paged cache and run one-query-per-sequence attention over
  * it.  Cache pages: (n_pages, page_size, H*D) bf16 for K and for V; page_table (B,

@@ -329,7 +329,7 @@ def test_classify_matches_reference_golden(name, class_batch_size):
 
 
 @pytest.mark.parametrize("batch", [1, 3, 8])
-def test_persistent_decode_step_matches_op_by_op(batch):
+def test_persistent_decode_step_matches_op_by_op(batch, monkeypatch):
     """vb_decode_step (one cooperative launch per token: embed, per-layer projections,
     paged attention, head, grid barriers in between) against the same step issued op by op,
     on a left-padded batch, eagerly and through the CUDA graph.  The two paths share the
@@ -339,6 +339,7 @@ def test_persistent_decode_step_matches_op_by_op(batch):
     from eilev_b200.model.v2 import OPTForCausalLM
     from oracle import videoblip_ref as R
 
+    monkeypatch.setenv("VB_DECODE_PERSISTENT", "1")
     torch.manual_seed(0)
     cfg = OPTConfig(hidden_size=128, num_hidden_layers=3, ffn_dim=256, num_attention_heads=2, vocab_size=300,
                     max_position_embeddings=256, word_embed_proj_dim=128)
