@@ -318,9 +318,12 @@ def gpu_arm(args) -> None:
 
     cfg = full_config(args.dropout)
     model = build_gpu_model(cfg, device)
-    decode = None
+    decode = decode8 = None
     if rank == 0 and not args.no_decode and not args.profile:
-        decode = measure_decode(model, device)  # independent workload, measured before the training loop
+        # independent workloads (BASELINE configs[4], batch sweep ends), measured before the training loop
+        decode = measure_decode(model, device)
+        decode8 = measure_decode(model, device, batch=8)
+        torch.cuda.empty_cache()
     trainer = DataParallelTrainer(model, lr=1e-5, weight_decay=0.05, max_grad_norm=1.0,
                                   grad_accum=GRAD_ACCUM)
     if world > 1:  # NCCL communicator / NVLink connection set-up happens on the first collective
@@ -422,6 +425,11 @@ def gpu_arm(args) -> None:
                                   "peak": hbm, "unit": "GB/s",
                                   "frac": decode["bytes_per_token"] / (decode["ms_per_token"] * 1e-3) / 1e9 / hbm}
             line["decode"] = decode
+            if decode8 is not None:
+                decode8["roofline"] = {"bound": "hbm", "achieved": decode8["bytes_per_token"] / (decode8["ms_per_token"] * 1e-3) / 1e9,
+                                       "peak": hbm, "unit": "GB/s",
+                                       "frac": decode8["bytes_per_token"] / (decode8["ms_per_token"] * 1e-3) / 1e9 / hbm}
+                line["decode_batch8"] = decode8
         if not args.no_cpu_baseline and world == 1:
             res = run_cpu_baseline(cfg, clips=args.cpu_clips, steps=1, warmup=0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -97,8 +97,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
   __nv_bfloat16* sk = sq + 64 * LDS;      // 2 stages
   __nv_bfloat16* sv = sk + 2 * 64 * LDS;  // 2 stages
 
-  const int m0 = blockIdx.x * kAM;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // grid = (heads, q tiles, batch).  Causal tiles are issued heaviest first (the last q tile
+  // sees every key tile) across ALL heads, so the light tiles fill the tail of the launch.
+  const int mt = p.causal ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int m0 = mt * kAM;
+  const int h = blockIdx.x, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int D = p.d;
@@ -299,7 +302,7 @@ static cudaError_t launch_fwd(const AttnParams& p, int batch, cudaStream_t strea
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid((p.sq + kAM - 1) / kAM, p.heads, batch);
+  dim3 grid(p.heads, (p.sq + kAM - 1) / kAM, batch);
   attn_fwd_kernel<DP><<<grid, kAttnThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
@@ -404,8 +407,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   __nv_bfloat16* sP = sdO + 64 * LDS;
   __nv_bfloat16* sdS = sP + 64 * LDP;
 
-  const int n0 = blockIdx.x * kAN;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // grid = (heads, key tiles, batch): with a causal mask key tile 0 is the heaviest, and it
+  // is issued first for every head
+  const int n0 = blockIdx.y * kAN;
+  const int h = blockIdx.x, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int D = p.d;
@@ -620,7 +625,7 @@ static cudaError_t launch_bwd(const AttnBwdParams& bp, int batch, cudaStream_t s
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid((bp.f.skv + kAN - 1) / kAN, bp.f.heads, batch);
+  dim3 grid(bp.f.heads, (bp.f.skv + kAN - 1) / kAN, batch);
   attn_bwd_kernel<DP><<<grid, kAttnThreads, smem, stream>>>(bp);
   return cudaGetLastError();
 }

@@ -237,6 +237,134 @@ def greedy_generate(sd, config, input_ids, attention_mask, pixel_values, video_i
     return torch.stack(new, dim=1)
 
 
+# --------------------------------------------------------------------------- flan-T5 (seq2seq LM)
+def _rms(x, w, eps):
+    """HF:t5/modeling_t5.py T5LayerNorm — scale only, fp32 variance without mean subtraction."""
+    return w.float() * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+
+
+def t5_relative_bucket(rel, bidirectional, num_buckets, max_distance):
+    """HF:t5/modeling_t5.py T5Attention._relative_position_bucket (rel = key - query)."""
+    ret = torch.zeros_like(rel)
+    if bidirectional:
+        num_buckets //= 2
+        ret = ret + (rel > 0).long() * num_buckets
+        rel = rel.abs()
+    else:
+        rel = -torch.minimum(rel, torch.zeros_like(rel))
+    max_exact = num_buckets // 2
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (num_buckets - max_exact)).long()
+    large = torch.minimum(large, torch.full_like(large, num_buckets - 1))
+    return ret + torch.where(rel < max_exact, rel, large)
+
+
+def t5_position_bias(table, lq, lk, bidirectional, tcfg):
+    """compute_bias: (1, heads, lq, lk) from the (buckets, heads) embedding of block 0."""
+    rel = torch.arange(lk)[None, :] - torch.arange(lq)[:, None]
+    bucket = t5_relative_bucket(rel, bidirectional, tcfg.relative_attention_num_buckets,
+                                tcfg.relative_attention_max_distance)
+    return table.float()[bucket].permute(2, 0, 1)[None]
+
+
+def _t5_attention(sd, tcfg, x, kv, p, bias):
+    """T5Attention.forward: no 1/sqrt(d) scaling, no projection biases, additive bias."""
+    b, lq, _ = x.shape
+    lk = kv.shape[1]
+    h, d = tcfg.num_heads, tcfg.d_kv
+    q = _lin(x, sd, p + "q", bias=False).reshape(b, lq, h, d).transpose(1, 2)
+    k = _lin(kv, sd, p + "k", bias=False).reshape(b, lk, h, d).transpose(1, 2)
+    v = _lin(kv, sd, p + "v", bias=False).reshape(b, lk, h, d).transpose(1, 2)
+    probs = torch.softmax(q @ k.transpose(-1, -2) + bias, dim=-1)
+    return _lin((probs @ v).transpose(1, 2).reshape(b, lq, h * d), sd, p + "o", bias=False)
+
+
+def _t5_ff(sd, tcfg, x, p):
+    """T5DenseGatedActDense (gated-gelu: gelu_new(wi_0 x) * wi_1 x) or T5DenseActDense (relu)."""
+    if tcfg.is_gated_act:
+        act = F.gelu(_lin(x, sd, p + "wi_0", bias=False), approximate="tanh")
+        return _lin(act * _lin(x, sd, p + "wi_1", bias=False), sd, p + "wo", bias=False)
+    return _lin(F.relu(_lin(x, sd, p + "wi", bias=False)), sd, p + "wo", bias=False)
+
+
+def t5_encoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.encoder."):
+    """T5Stack (encoder): pre-RMSNorm blocks; block 0 owns the bidirectional relative bias."""
+    b, l, _ = inputs_embeds.shape
+    eps = tcfg.layer_norm_epsilon
+    neg = torch.finfo(torch.float32).min
+    bias = t5_position_bias(sd[p + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"], l, l, True, tcfg)
+    bias = bias + (1.0 - attention_mask[:, None, None, :].float()) * neg
+    x = inputs_embeds.float()
+    for i in range(tcfg.num_layers):
+        bp = f"{p}block.{i}."
+        y = _rms(x, sd[bp + "layer.0.layer_norm.weight"], eps)
+        x = x + _t5_attention(sd, tcfg, y, y, bp + "layer.0.SelfAttention.", bias)
+        x = x + _t5_ff(sd, tcfg, _rms(x, sd[bp + "layer.1.layer_norm.weight"], eps), bp + "layer.1.DenseReluDense.")
+    return _rms(x, sd[p + "final_layer_norm.weight"], eps)
+
+
+def t5_decoder(sd, tcfg, decoder_input_ids, enc, enc_mask, p="language_model.decoder."):
+    """T5Stack (decoder): causal self-attention with the unidirectional relative bias,
+    cross-attention over the encoder states (mask only), feed-forward."""
+    b, l = decoder_input_ids.shape
+    eps = tcfg.layer_norm_epsilon
+    neg = torch.finfo(torch.float32).min
+    x = sd["language_model.shared.weight"].float()[decoder_input_ids]
+    self_bias = t5_position_bias(sd[p + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"], l, l, False, tcfg)
+    self_bias = self_bias.masked_fill(~torch.ones(l, l, dtype=torch.bool).tril()[None, None], neg)
+    cross_bias = (1.0 - enc_mask[:, None, None, :].float()) * neg
+    for i in range(tcfg.num_decoder_layers):
+        bp = f"{p}block.{i}."
+        y = _rms(x, sd[bp + "layer.0.layer_norm.weight"], eps)
+        x = x + _t5_attention(sd, tcfg, y, y, bp + "layer.0.SelfAttention.", self_bias)
+        y = _rms(x, sd[bp + "layer.1.layer_norm.weight"], eps)
+        x = x + _t5_attention(sd, tcfg, y, enc, bp + "layer.1.EncDecAttention.", cross_bias)
+        x = x + _t5_ff(sd, tcfg, _rms(x, sd[bp + "layer.2.layer_norm.weight"], eps), bp + "layer.2.DenseReluDense.")
+    return _rms(x, sd[p + "final_layer_norm.weight"], eps)
+
+
+def t5_shift_right(labels, tcfg):
+    """T5ForConditionalGeneration._shift_right: start token first, -100 -> pad."""
+    out = labels.new_zeros(labels.shape)
+    out[:, 1:] = labels[:, :-1]
+    out[:, 0] = tcfg.decoder_start_token_id
+    return out.masked_fill(out == -100, tcfg.pad_token_id)
+
+
+def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_values=None,
+                         video_input_mask=None, labels=None, decoder_input_ids=None):
+    """v2.py:132-252 with the seq2seq branch (:228-238) -> T5ForConditionalGeneration.forward:
+    encoder over the interleaved embeddings, decoder over shift_right(labels), untied or tied
+    (x d_model**-0.5) head, unshifted CE with ignore_index -100."""
+    tcfg = config.text_config
+    out = {}
+    feats = None
+    if pixel_values is not None:
+        assert video_input_mask is not None
+        feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values)
+        out.update(video_features=feats, query_output=qout, image_embeds=image_embeds, pooler_output=pooled)
+    emb = sd["language_model.shared.weight"].float()[input_ids]
+    if feats is not None:
+        emb = emb.clone()
+        emb[video_input_mask.bool()] = feats
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    enc = t5_encoder(sd, tcfg, emb, attention_mask)
+    if decoder_input_ids is None:
+        decoder_input_ids = t5_shift_right(labels, tcfg)
+    dec = t5_decoder(sd, tcfg, decoder_input_ids, enc, attention_mask)
+    if tcfg.tie_word_embeddings:
+        dec = dec * tcfg.d_model ** -0.5
+        head = sd["language_model.shared.weight"]
+    else:
+        head = sd["language_model.lm_head.weight"]
+    logits = F.linear(dec, head.float())
+    out.update(inputs_embeds=emb, encoder_last_hidden_state=enc, logits=logits)
+    if labels is not None:
+        out["loss"] = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1), ignore_index=-100)
+    return out
+
+
 @torch.no_grad()
 def classify(sd, config, prompt_input_ids, class_input_ids, prompt_attention_mask=None, pixel_values=None,
              prompt_video_input_mask=None, class_attention_mask=None):
