@@ -41,6 +41,7 @@ class AttnArgs(C.Structure):
         ("v_bs", i64), ("v_rs", i64), ("o_bs", i64), ("o_rs", i64),
         ("scale", f32), ("causal", i32),
         ("dropout_p", f32), ("reserved", i32), ("dropout_seed", vp), ("dropout_salt", C.c_uint64),
+        ("rel_bias", vp), ("rel_bias_stride", i64),
     ]
 
 
@@ -69,8 +70,13 @@ SIGNATURES: dict[str, list] = {
     "vb_cls_rows": [vp, vp, vp, i64, i64, i64, vp],
     "vb_embed_splice": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
     "vb_splice_bwd": [vp, vp, vp, i64, i64, i64, vp],
-    "vb_cross_entropy": [vp, i32, vp, vp, vp, vp, i64, i64, i64, i64, vp],
-    "vb_cross_entropy_bwd": [vp, i32, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
+    "vb_cross_entropy": [vp, i32, vp, vp, vp, vp, i64, i64, i64, i64, i32, vp],
+    "vb_cross_entropy_bwd": [vp, i32, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i32, vp],
+    "vb_rmsnorm": [vp, vp, vp, vp, i64, i64, i64, i64, f32, vp],
+    "vb_rmsnorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, vp],
+    "vb_gated_gelu": [vp, vp, i64, i64, vp],
+    "vb_gated_gelu_bwd": [vp, vp, vp, i64, i64, vp],
+    "vb_embedding": [vp, vp, vp, i64, i64, i64, vp],
     "vb_attention_merge": [vp, vp, i64, vp, vp, i64, vp, i64, i64, i64, vp],
     "vb_token_logprob": [vp, i32, vp, vp, vp, i64, i64, i64, vp],
     "vb_transpose": [vp, vp, i64, i64, i64, i64, vp],
@@ -123,7 +129,7 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "vb_last_error" else C.c_int
-    if handle.vb_abi_version() != 1:
+    if handle.vb_abi_version() != 2:
         raise VbError("ABI version mismatch between eilev_b200/_lib.py and the built library")
     _lib = handle
     return handle

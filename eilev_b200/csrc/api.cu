@@ -132,23 +132,23 @@ int vb_splice_bwd(const void* d_embeds, const int32_t* slot_index, void* d_featu
 
 int vb_cross_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels, float* loss,
                      float* row_lse, int32_t* n_valid, int64_t batch, int64_t seq, int64_t vocab,
-                     int64_t ldl, void* stream) {
+                     int64_t ldl, int32_t shift, void* stream) {
   if (logits == nullptr || labels == nullptr || loss == nullptr || row_lse == nullptr || n_valid == nullptr)
     return fail_msg("vb_cross_entropy", "null operand");
   VB_CHECK("vb_cross_entropy",
            vb::ce_launch(logits, logits_dtype, reinterpret_cast<const long long*>(labels), loss,
-                         row_lse, n_valid, batch, seq, vocab, ldl, st(stream)));
+                         row_lse, n_valid, batch, seq, vocab, ldl, shift, st(stream)));
 }
 
 int vb_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* labels,
                          const float* row_lse, const int32_t* n_valid, const float* grad_scale,
                          void* dlogits, int64_t batch, int64_t seq, int64_t vocab, int64_t ldl,
-                         int64_t ldd, void* stream) {
+                         int64_t ldd, int32_t shift, void* stream) {
   if (logits == nullptr || labels == nullptr || row_lse == nullptr || n_valid == nullptr || dlogits == nullptr)
     return fail_msg("vb_cross_entropy_bwd", "null operand");
   VB_CHECK("vb_cross_entropy_bwd",
            vb::ce_bwd_launch(logits, logits_dtype, reinterpret_cast<const long long*>(labels),
-                             row_lse, n_valid, grad_scale, dlogits, batch, seq, vocab, ldl, ldd,
+                             row_lse, n_valid, grad_scale, dlogits, batch, seq, vocab, ldl, ldd, shift,
                              st(stream)));
 }
 
@@ -165,6 +165,30 @@ int vb_token_logprob(const void* logits, int32_t logits_dtype, const int64_t* ro
            vb::token_logprob_launch(logits, logits_dtype, reinterpret_cast<const long long*>(row_index),
                                     reinterpret_cast<const long long*>(targets), out, n, vocab, ldl,
                                     st(stream)));
+}
+
+int vb_rmsnorm(const void* x, const float* gamma, void* y, float* rstd, int64_t rows, int64_t cols,
+               int64_t ldx, int64_t ldy, float eps, void* stream) {
+  VB_CHECK("vb_rmsnorm", vb::rmsnorm_fwd_launch(x, gamma, y, rstd, rows, cols, ldx, ldy, eps, st(stream)));
+}
+
+int vb_rmsnorm_bwd(const void* dy, const void* x, const float* gamma, const float* rstd, const void* dx_add,
+                   void* dx, int64_t rows, int64_t cols, void* stream) {
+  VB_CHECK("vb_rmsnorm_bwd", vb::rmsnorm_bwd_launch(dy, x, gamma, rstd, dx_add, dx, rows, cols, st(stream)));
+}
+
+int vb_gated_gelu(const void* h01, void* out, int64_t rows, int64_t dff, void* stream) {
+  VB_CHECK("vb_gated_gelu", vb::gated_gelu_fwd_launch(h01, out, rows, dff, st(stream)));
+}
+
+int vb_gated_gelu_bwd(const void* d_out, const void* h01, void* d_h01, int64_t rows, int64_t dff, void* stream) {
+  VB_CHECK("vb_gated_gelu_bwd", vb::gated_gelu_bwd_launch(d_out, h01, d_h01, rows, dff, st(stream)));
+}
+
+int vb_embedding(const int64_t* ids, const void* table, void* out, int64_t n, int64_t dim, int64_t vocab,
+                 void* stream) {
+  VB_CHECK("vb_embedding", vb::embedding_launch(reinterpret_cast<const long long*>(ids), table, out, n, dim,
+                                                vocab, st(stream)));
 }
 
 int vb_transpose(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in,

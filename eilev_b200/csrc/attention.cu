@@ -85,6 +85,8 @@ struct AttnParams {
   unsigned long long drop_salt;
   unsigned int drop_thresh;  // 0 = no dropout on the probabilities
   float drop_scale;
+  const float* rel_bias;      // T5 relative-position bias table [heads][sq + skv - 1] or nullptr
+  long long rel_bias_stride;
 };
 
 template <int DP>
@@ -188,6 +190,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     // scale + mask (log2 domain)
     const int qi0 = m0 + warp * 16 + g;
     const uint8_t* km = p.key_mask != nullptr ? p.key_mask + static_cast<long long>(b) * p.skv : nullptr;
+    constexpr float kLog2e = 1.4426950408889634f;
+    // rb[key - qi]: entry (key - qi) + (sq - 1) of this head's relative-position table
+    const float* rb = p.rel_bias != nullptr ? p.rel_bias + h * p.rel_bias_stride + (p.sq - 1) : nullptr;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
@@ -197,7 +202,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
         bool ok = key < p.skv;
         if (p.causal) ok = ok && (key <= qi + causal_off);
         if (km != nullptr && ok) ok = km[key] != 0;
-        s[nb][j] = ok ? s[nb][j] * p.scale_log2 : -INFINITY;
+        float sv = s[nb][j] * p.scale_log2;
+        if (rb != nullptr && ok) sv += rb[key - qi] * kLog2e;
+        s[nb][j] = ok ? sv : -INFINITY;
       }
     }
     // online softmax for the two rows this thread owns (g, g+8)
@@ -338,6 +345,8 @@ cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream) {
     p.drop_thresh = drop ? dropout_threshold(a.dropout_p) : 0u;
     p.drop_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
   }
+  p.rel_bias = a.rel_bias;
+  p.rel_bias_stride = a.rel_bias_stride;
   p.vec = attn_vec_ok(a) ? 1 : 0;
   // o is written with 4-byte stores when every (row, head) start is 4-byte aligned
   p.o_vec2 = (a.d % 2 == 0 && a.o_rs % 2 == 0 && a.o_bs % 2 == 0 &&
@@ -439,6 +448,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   }
   const int m_tiles = (p.sq + kAM - 1) / kAM;
   const uint8_t* km = p.key_mask != nullptr ? p.key_mask + static_cast<long long>(b) * p.skv : nullptr;
+  const float* rb = p.rel_bias != nullptr ? p.rel_bias + h * p.rel_bias_stride + (p.sq - 1) : nullptr;
   const float* lse_bh = p.lse + (static_cast<long long>(b) * p.heads + h) * p.sq;
   const float* delta_bh = bp.delta + (static_cast<long long>(b) * p.heads + h) * p.sq;
 
@@ -499,7 +509,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
         bool ok = key < p.skv && qi < p.sq && lse2[r] != -INFINITY;
         if (p.causal) ok = ok && (key <= qi + causal_off);
         if (km != nullptr && ok) ok = km[key] != 0;
-        const float pr = ok ? exp2f(s[nb][j] * p.scale_log2 - lse2[r]) : 0.0f;
+        float sv = s[nb][j] * p.scale_log2;
+        if (rb != nullptr && ok) sv += rb[key - qi] * kLog2e;
+        const float pr = ok ? exp2f(sv - lse2[r]) : 0.0f;
         float p_used = pr, dpv = dp[nb][j];
         if (p.drop_thresh != 0u) {  // regenerate the forward mask
           const uint64_t idx = ((static_cast<uint64_t>(b) * p.heads + h) * p.sq + qi) * p.skv + key;
@@ -657,6 +669,8 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
     p.drop_thresh = drop ? dropout_threshold(f.dropout_p) : 0u;
     p.drop_scale = drop ? 1.0f / (1.0f - f.dropout_p) : 1.0f;
   }
+  p.rel_bias = f.rel_bias;
+  p.rel_bias_stride = f.rel_bias_stride;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   p.vec = (attn_vec_ok(f) && al(a.d_o) && f.o_rs % 8 == 0 && f.o_bs % 8 == 0) ? 1 : 0;
   p.o_vec2 = 0;

@@ -425,7 +425,7 @@ static bool make_tmap_heads(CUtensorMap* map, const void* ptr, long long rows, l
 
 bool attention_tcgen05_eligible(const vb_attn_args& a) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  if (a.causal || a.key_mask != nullptr || a.lse != nullptr) return false;
+  if (a.causal || a.key_mask != nullptr || a.lse != nullptr || a.rel_bias != nullptr) return false;
   if (a.dropout_p > 0.0f && a.dropout_seed != nullptr) return false;
   if (a.sq != a.skv || a.sq > kTaKRows || a.sq < 64) return false;
   if (a.d % 8 != 0 || a.d > 128 || a.d < 16) return false;

@@ -168,14 +168,14 @@ splice_bwd_kernel(const __nv_bfloat16* d_embeds, const int* slot_index, __nv_bfl
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_row_kernel(const T* logits, const long long* labels, float* row_lse, long long seq,
-              long long vocab, long long ldl) {
-  // block r handles logits row (b, l); target = labels[b, l+1]
+              long long vocab, long long ldl, int shift) {
+  // block r handles logits row (b, l); target = labels[b, l+shift] (1: causal LM, 0: seq2seq)
   const long long r = blockIdx.x;
   const long long l = r % seq;
-  bool valid = (l + 1 < seq);
+  bool valid = (l + shift < seq);
   long long target = -100;
   if (valid) {
-    target = labels[r + 1];
+    target = labels[r + shift];
     valid = target >= 0 && target < vocab;
   }
   if (!valid) {
@@ -209,15 +209,15 @@ ce_row_kernel(const T* logits, const long long* labels, float* row_lse, long lon
 template <typename T>
 __global__ void __launch_bounds__(256)
 ce_finalize_kernel(const T* logits, const long long* labels, const float* row_lse, float* loss,
-                   int* n_valid, long long rows, long long seq, long long vocab, long long ldl) {
+                   int* n_valid, long long rows, long long seq, long long vocab, long long ldl, int shift) {
   __shared__ float ssum[256];
   __shared__ int scnt[256];
   float acc = 0.0f;
   int cnt = 0;
   for (long long r = threadIdx.x; r < rows; r += 256) {
     const long long l = r % seq;
-    if (l + 1 >= seq) continue;
-    const long long target = labels[r + 1];
+    if (l + shift >= seq) continue;
+    const long long target = labels[r + shift];
     if (target < 0 || target >= vocab) continue;
     acc += row_lse[r] - to_f32<T>(logits[r * ldl + target]);
     cnt += 1;
@@ -243,13 +243,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ce_bwd_kernel(const T* logits, const long long* labels, const float* row_lse, const int* n_valid,
               const float* grad_scale, __nv_bfloat16* dlogits, long long seq, long long vocab,
-              long long ldl, long long ldd) {
+              long long ldl, long long ldd, int shift) {
   const long long r = blockIdx.x;
   const long long l = r % seq;
-  bool valid = (l + 1 < seq);
+  bool valid = (l + shift < seq);
   long long target = -100;
   if (valid) {
-    target = labels[r + 1];
+    target = labels[r + shift];
     valid = target >= 0 && target < vocab;
   }
   __nv_bfloat16* out = dlogits + r * ldd;
@@ -269,17 +269,17 @@ ce_bwd_kernel(const T* logits, const long long* labels, const float* row_lse, co
 
 cudaError_t ce_launch(const void* logits, int dtype, const long long* labels, float* loss,
                       float* row_lse, int* n_valid, long long batch, long long seq,
-                      long long vocab, long long ldl, cudaStream_t s) {
+                      long long vocab, long long ldl, int shift, cudaStream_t s) {
   const long long rows = batch * seq;
-  if (rows <= 0) return cudaErrorInvalidValue;
+  if (rows <= 0 || shift < 0 || shift > 1) return cudaErrorInvalidValue;
   if (dtype == VB_BF16) {
     const __nv_bfloat16* lg = reinterpret_cast<const __nv_bfloat16*>(logits);
-    ce_row_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl);
-    ce_finalize_kernel<__nv_bfloat16><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl);
+    ce_row_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl, shift);
+    ce_finalize_kernel<__nv_bfloat16><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl, shift);
   } else if (dtype == VB_F32) {
     const float* lg = reinterpret_cast<const float*>(logits);
-    ce_row_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl);
-    ce_finalize_kernel<float><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl);
+    ce_row_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl, shift);
+    ce_finalize_kernel<float><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl, shift);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -289,16 +289,16 @@ cudaError_t ce_launch(const void* logits, int dtype, const long long* labels, fl
 cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels,
                           const float* row_lse, const int* n_valid, const float* grad_scale,
                           void* dlogits, long long batch, long long seq, long long vocab,
-                          long long ldl, long long ldd, cudaStream_t s) {
+                          long long ldl, long long ldd, int shift, cudaStream_t s) {
   const long long rows = batch * seq;
-  if (rows <= 0) return cudaErrorInvalidValue;
+  if (rows <= 0 || shift < 0 || shift > 1) return cudaErrorInvalidValue;
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dlogits);
   if (dtype == VB_BF16)
     ce_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd);
+        reinterpret_cast<const __nv_bfloat16*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd, shift);
   else if (dtype == VB_F32)
     ce_bwd_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(
-        reinterpret_cast<const float*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd);
+        reinterpret_cast<const float*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd, shift);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

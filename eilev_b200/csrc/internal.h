@@ -37,17 +37,26 @@ cudaError_t splice_bwd_launch(const void* d_embeds, const int* slot_index, void*
                               cudaStream_t s);
 cudaError_t ce_launch(const void* logits, int dtype, const long long* labels, float* loss,
                       float* row_lse, int* n_valid, long long batch, long long seq,
-                      long long vocab, long long ldl, cudaStream_t s);
+                      long long vocab, long long ldl, int shift, cudaStream_t s);
 cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels,
                           const float* row_lse, const int* n_valid, const float* grad_scale,
                           void* dlogits, long long batch, long long seq, long long vocab,
-                          long long ldl, long long ldd, cudaStream_t s);
+                          long long ldl, long long ldd, int shift, cudaStream_t s);
 cudaError_t attn_merge_launch(const void* o1, const float* lse1, long long s1, const void* o2,
                               const float* lse2, long long s2, void* out, long long rows,
                               long long heads, long long d, cudaStream_t s);
 cudaError_t token_logprob_launch(const void* logits, int dtype, const long long* row_index,
                                  const long long* targets, float* out, long long n, long long vocab,
                                  long long ldl, cudaStream_t s);
+cudaError_t rmsnorm_fwd_launch(const void* x, const float* gamma, void* y, float* rstd, long long rows,
+                               long long cols, long long ldx, long long ldy, float eps, cudaStream_t s);
+cudaError_t rmsnorm_bwd_launch(const void* dy, const void* x, const float* gamma, const float* rstd,
+                               const void* dx_add, void* dx, long long rows, long long cols, cudaStream_t s);
+cudaError_t gated_gelu_fwd_launch(const void* h01, void* out, long long rows, long long dff, cudaStream_t s);
+cudaError_t gated_gelu_bwd_launch(const void* d_out, const void* h01, void* d_h01, long long rows,
+                                  long long dff, cudaStream_t s);
+cudaError_t embedding_launch(const long long* ids, const void* table, void* out, long long n, long long dim,
+                             long long vocab, cudaStream_t s);
 cudaError_t transpose_launch(const void* in, void* out, long long rows, long long cols,
                              long long ld_in, long long ld_out, cudaStream_t s);
 cudaError_t convert_launch(const void* src, int sd, void* dst, int dd, long long n, cudaStream_t s);

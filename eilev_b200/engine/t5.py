@@ -1,0 +1,267 @@
+"""flan-T5 encoder-decoder LM over the interleaved (32 video queries per clip + text) sequence
+— the seq2seq branch of eilev/model/v2.py:228-238.
+
+Restates T5ForConditionalGeneration.forward (HF:t5/modeling_t5.py: T5Stack, T5Block,
+T5Attention — no 1/sqrt(d) scaling, no projection biases, bucketed relative-position bias
+owned by block 0 of each stack —, T5LayerNorm = RMSNorm, T5DenseGatedActDense with the tanh
+GELU, ``_shift_right`` and the unshifted cross entropy) as sm_100a launches:
+
+    encoder: embed_splice, N x [RMSNorm, fused QKV GEMM, flash attention with the bias table
+             and the padding mask, o GEMM(+residual), RMSNorm, fused wi_0|wi_1 GEMM,
+             gelu_new(h0)*h1, wo GEMM(+residual)], RMSNorm
+    decoder: shared-embedding gather of shift_right(labels), ONE GEMM for the cross-attention
+             K|V of all layers off the encoder output, M x [causal self-attention block,
+             cross-attention block, gated FFN], RMSNorm, (untied) head GEMM, fused CE.
+
+The LM is frozen in the recipe (train_v2.py:126-127): the backward is dgrad only, down through
+the decoder, the cross-attention K/V projection, the encoder and the splice to the video slots.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import ops
+from .packing import PackCache, bf16, cat_bf16, f32
+
+T = ops.transpose
+
+
+def _check_cfg(cfg) -> None:
+    if not (cfg.is_gated_act and cfg.dense_act_fn == "gelu_new"):
+        raise NotImplementedError(
+            f"T5 feed_forward_proj {cfg.feed_forward_proj!r}: only gated-gelu (flan-T5) is built")
+    if cfg.num_heads * cfg.d_kv % 8 != 0:
+        raise NotImplementedError("T5 inner dim must be a multiple of 8")
+
+
+def scale_decoder_outputs(cfg) -> bool:
+    """transformers 4.33.1 scales the decoder output by d_model**-0.5 iff tie_word_embeddings;
+    5.x froze that decision into config.scale_decoder_outputs (flan-T5: untied, unscaled)."""
+    return bool(getattr(cfg, "scale_decoder_outputs", cfg.tie_word_embeddings))
+
+
+def pack_t5(lm, cache: PackCache, need_backward: bool):
+    params = list(lm.parameters())
+
+    def ff(layer_ff):
+        d = layer_ff.DenseReluDense
+        return dict(ln=f32(layer_ff.layer_norm.weight), wi_w=cat_bf16([d.wi_0.weight, d.wi_1.weight]),
+                    wo_w=bf16(d.wo.weight))
+
+    def att(a):
+        return dict(qkv_w=cat_bf16([a.q.weight, a.k.weight, a.v.weight]), o_w=bf16(a.o.weight))
+
+    def build():
+        w = {"shared": bf16(lm.shared.weight), "head": bf16(lm.lm_head.weight), "enc": [], "dec": [],
+             "enc_ln": f32(lm.encoder.final_layer_norm.weight), "dec_ln": f32(lm.decoder.final_layer_norm.weight),
+             "enc_rel": f32(lm.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight),
+             "dec_rel": f32(lm.decoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight)}
+        for blk in lm.encoder.block:
+            e = dict(ln1=f32(blk.layer[0].layer_norm.weight), **att(blk.layer[0].SelfAttention))
+            e["ff"] = ff(blk.layer[1])
+            w["enc"].append(e)
+        ckv = []
+        for blk in lm.decoder.block:
+            ca = blk.layer[1].EncDecAttention
+            d = dict(ln1=f32(blk.layer[0].layer_norm.weight), **att(blk.layer[0].SelfAttention),
+                     ln2=f32(blk.layer[1].layer_norm.weight), cq_w=bf16(ca.q.weight), co_w=bf16(ca.o.weight))
+            d["ff"] = ff(blk.layer[2])
+            ckv += [ca.k.weight, ca.v.weight]
+            w["dec"].append(d)
+        w["ckv_w"] = cat_bf16(ckv)  # (layers * 2 * inner, d_model): every layer's cross K|V in one GEMM
+        return w
+
+    w = cache.get("t5", params, build)
+    if need_backward and "head_t" not in w:
+        with torch.no_grad():  # dgrad operands, packed once (the LM is frozen)
+            w["head_t"] = T(w["head"])
+            w["ckv_wt"] = T(w["ckv_w"])
+            for lw in w["enc"] + w["dec"]:
+                for k in ("qkv_w", "o_w", "cq_w", "co_w"):
+                    if k in lw:
+                        lw[k + "t"] = T(lw[k])
+                for k in ("wi_w", "wo_w"):
+                    lw["ff"][k + "t"] = T(lw["ff"][k])
+    return w
+
+
+_REL_CACHE: dict = {}
+
+
+def rel_bias_table(weight: torch.Tensor, sq: int, skv: int, bidirectional: bool, cfg) -> torch.Tensor:
+    """(heads, sq + skv - 1) f32: entry (j - i) + (sq - 1) = bias of key j seen from query i
+    (T5Attention.compute_bias / _relative_position_bucket; the bias depends on j - i only).
+    The bucket indices are integer bookkeeping computed once per shape ON THE HOST with the
+    reference's own float32 expression: the log-spaced bucket edges (distance 16, 32, 64 ...)
+    sit exactly on integers, where a device log() one ulp lower would pick the other bucket."""
+    nb_all, maxd = int(cfg.relative_attention_num_buckets), int(cfg.relative_attention_max_distance)
+    key = (sq, skv, bidirectional, nb_all, maxd, str(weight.device))
+    bucket = _REL_CACHE.get(key)
+    if bucket is None:
+        rel = torch.arange(-(sq - 1), skv, dtype=torch.long)
+        nb = nb_all
+        ret = torch.zeros_like(rel)
+        if bidirectional:
+            nb //= 2
+            ret = ret + (rel > 0).long() * nb
+            rel = rel.abs()
+        else:
+            rel = -torch.minimum(rel, torch.zeros_like(rel))
+        max_exact = nb // 2
+        large = max_exact + (torch.log(rel.float() / max_exact) / math.log(maxd / max_exact) * (nb - max_exact)).long()
+        large = torch.minimum(large, torch.full_like(large, nb - 1))
+        bucket = (ret + torch.where(rel < max_exact, rel, large)).to(weight.device)
+        _REL_CACHE[key] = bucket
+    return weight[bucket].t().contiguous()
+
+
+def shift_right(labels: torch.Tensor, cfg) -> torch.Tensor:
+    """T5ForConditionalGeneration._shift_right (token bookkeeping)."""
+    out = torch.empty_like(labels)
+    out[:, 1:] = labels[:, :-1]
+    out[:, 0] = cfg.decoder_start_token_id
+    return out.masked_fill(out == -100, cfg.pad_token_id)
+
+
+def _ff_fwd(x, lw, eps):
+    y, r = ops.rmsnorm(x, lw["ln"], eps, save_stats=True)
+    h01 = ops.gemm(y, lw["wi_w"])
+    out = ops.gemm(ops.gated_gelu(h01), lw["wo_w"], residual=x)
+    return out, dict(x=x, r=r, h01=h01)
+
+
+def _ff_bwd(dx, lw, s):
+    d_h01 = ops.gated_gelu_bwd(ops.gemm(dx, lw["wo_wt"]), s["h01"])
+    return ops.rmsnorm_bwd(ops.gemm(d_h01, lw["wi_wt"]), s["x"], lw["ln"], s["r"], dx_add=dx)
+
+
+def t5_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features, labels=None,
+               decoder_input_ids=None, save: bool = False):
+    """Returns dict(logits (B, Ld, V), loss, encoder_last_hidden_state, status, ctx)."""
+    cfg = lm.config
+    _check_cfg(cfg)
+    w = pack_t5(lm, cache, need_backward=save)
+    dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
+    inner = heads * dkv
+    eps = float(cfg.layer_norm_epsilon)
+    b, l = input_ids.shape
+    rows = b * l
+    emb, _, slot, _, status = ops.embed_splice(input_ids, attention_mask, video_mask, w["shared"],
+                                               video_features, None, 0, want_hidden=False)
+    key_mask = attention_mask.to(torch.uint8).contiguous()
+    enc_bias = rel_bias_table(w["enc_rel"], l, l, True, cfg)
+    x = emb.view(rows, dm)
+    enc_saved = []
+    for lw in w["enc"]:
+        y, r1 = ops.rmsnorm(x, lw["ln1"], eps, save_stats=True)
+        qkv = ops.gemm(y, lw["qkv_w"]).view(b, l, 3 * inner)
+        o, lse = ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], heads, 1.0,
+                               key_mask=key_mask, need_lse=True, rel_bias=enc_bias)
+        x_mid = ops.gemm(o.view(rows, inner), lw["o_w"], residual=x)
+        x_out, sff = _ff_fwd(x_mid, lw["ff"], eps)
+        if save:
+            enc_saved.append(dict(x=x, r1=r1, qkv=qkv, o=o, lse=lse, ff=sff))
+        x = x_out
+    enc_out, r_enc = ops.rmsnorm(x, w["enc_ln"], eps, save_stats=True)
+    x_enc_last = x
+
+    if decoder_input_ids is None:
+        if labels is None:
+            raise ValueError("You have to specify either decoder_input_ids or labels")
+        decoder_input_ids = shift_right(labels, cfg)
+    ld = decoder_input_ids.shape[1]
+    rows_d = b * ld
+    n_dec = len(w["dec"])
+    xd = ops.embedding(decoder_input_ids, w["shared"]).view(rows_d, dm)
+    ckv = ops.gemm(enc_out, w["ckv_w"]).view(b, l, n_dec * 2 * inner)
+    dec_bias = rel_bias_table(w["dec_rel"], ld, ld, False, cfg)
+    dec_saved = []
+    for li, lw in enumerate(w["dec"]):
+        y, r1 = ops.rmsnorm(xd, lw["ln1"], eps, save_stats=True)
+        qkv = ops.gemm(y, lw["qkv_w"]).view(b, ld, 3 * inner)
+        o, lse = ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], heads, 1.0,
+                               causal=True, need_lse=True, rel_bias=dec_bias)
+        x1 = ops.gemm(o.view(rows_d, inner), lw["o_w"], residual=xd)
+        y2, r2 = ops.rmsnorm(x1, lw["ln2"], eps, save_stats=True)
+        cq = ops.gemm(y2, lw["cq_w"]).view(b, ld, inner)
+        ck = ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner]
+        cv = ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner]
+        co, clse = ops.attention(cq, ck, cv, heads, 1.0, key_mask=key_mask, need_lse=True)
+        x2 = ops.gemm(co.view(rows_d, inner), lw["co_w"], residual=x1)
+        x3, sff = _ff_fwd(x2, lw["ff"], eps)
+        if save:
+            dec_saved.append(dict(x=xd, r1=r1, qkv=qkv, o=o, lse=lse, x1=x1, r2=r2, cq=cq, co=co, clse=clse, ff=sff))
+        xd = x3
+    final, r_dec = ops.rmsnorm(xd, w["dec_ln"], eps, save_stats=True)
+    alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
+    logits = ops.gemm(final, w["head"], alpha=alpha).view(b, ld, -1)
+    out = dict(logits=logits, loss=None, status=status, ctx=None,
+               encoder_last_hidden_state=enc_out.view(b, l, dm))
+    if labels is not None:
+        loss, row_lse, n_valid = ops.cross_entropy(logits, labels, shift=0)
+        out["loss"] = loss
+        if save:
+            out["ctx"] = dict(enc=enc_saved, dec=dec_saved, x_enc_last=x_enc_last, r_enc=r_enc, x_dec_last=xd,
+                              r_dec=r_dec, ckv=ckv, logits=logits, labels=labels, row_lse=row_lse,
+                              n_valid=n_valid, slot=slot, key_mask=key_mask, enc_bias=enc_bias, dec_bias=dec_bias,
+                              alpha=alpha, b=b, l=l, ld=ld,
+                              n_features=0 if video_features is None else video_features.shape[0])
+    return out
+
+
+def t5_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None):
+    """dgrad-only backward: returns d(video_features) (n_features, d_model) bf16."""
+    cfg = lm.config
+    w = pack_t5(lm, cache, need_backward=True)
+    heads, dkv = cfg.num_heads, cfg.d_kv
+    inner = heads * dkv
+    b, l, ld = ctx["b"], ctx["l"], ctx["ld"]
+    rows, rows_d = b * l, b * ld
+    gs = None
+    if grad_loss is not None:
+        gs = grad_loss.detach().to(torch.float32).reshape(()).contiguous()
+    dlogits = ops.cross_entropy_bwd(ctx["logits"], ctx["labels"], ctx["row_lse"], ctx["n_valid"], gs, shift=0)
+    d_final = ops.gemm(dlogits, w["head_t"], alpha=ctx["alpha"])
+    dx = ops.rmsnorm_bwd(d_final, ctx["x_dec_last"], w["dec_ln"], ctx["r_dec"])
+    del dlogits, d_final
+    d_ckv = torch.empty_like(ctx["ckv"])  # every layer writes its own K | V slice
+    ckv = ctx["ckv"]
+    for li in range(len(w["dec"]) - 1, -1, -1):
+        lw, s = w["dec"][li], ctx["dec"][li]
+        d_x2 = _ff_bwd(dx, lw["ff"], s["ff"])
+        d_co = ops.gemm(d_x2, lw["co_wt"]).view(b, ld, inner)
+        ck = ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner]
+        cv = ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner]
+        dcq, _, _ = ops.attention_bwd(s["cq"], ck, cv, s["co"], s["clse"], d_co, heads, 1.0,
+                                      key_mask=ctx["key_mask"],
+                                      dk=d_ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner],
+                                      dv=d_ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner])
+        d_x1 = ops.rmsnorm_bwd(ops.gemm(dcq.view(rows_d, inner), lw["cq_wt"]), s["x1"], lw["ln2"], s["r2"],
+                               dx_add=d_x2)
+        d_o = ops.gemm(d_x1, lw["o_wt"]).view(b, ld, inner)
+        qkv = s["qkv"]
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], s["o"], s["lse"],
+                          d_o, heads, 1.0, causal=True, rel_bias=ctx["dec_bias"],
+                          dq=dqkv[:, :, :inner], dk=dqkv[:, :, inner:2 * inner], dv=dqkv[:, :, 2 * inner:])
+        dx = ops.rmsnorm_bwd(ops.gemm(dqkv.view(rows_d, 3 * inner), lw["qkv_wt"]), s["x"], lw["ln1"], s["r1"],
+                             dx_add=d_x1)
+    # encoder output <- all cross-attention K / V projections at once
+    d_enc = ops.gemm(d_ckv.view(rows, -1), w["ckv_wt"])
+    dx = ops.rmsnorm_bwd(d_enc, ctx["x_enc_last"], w["enc_ln"], ctx["r_enc"])
+    for li in range(len(w["enc"]) - 1, -1, -1):
+        lw, s = w["enc"][li], ctx["enc"][li]
+        d_mid = _ff_bwd(dx, lw["ff"], s["ff"])
+        d_o = ops.gemm(d_mid, lw["o_wt"]).view(b, l, inner)
+        qkv = s["qkv"]
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], s["o"], s["lse"],
+                          d_o, heads, 1.0, key_mask=ctx["key_mask"], rel_bias=ctx["enc_bias"],
+                          dq=dqkv[:, :, :inner], dk=dqkv[:, :, inner:2 * inner], dv=dqkv[:, :, 2 * inner:])
+        dx = ops.rmsnorm_bwd(ops.gemm(dqkv.view(rows, 3 * inner), lw["qkv_wt"]), s["x"], lw["ln1"], s["r1"],
+                             dx_add=d_mid)
+    if ctx["n_features"] == 0:
+        return None
+    return ops.splice_bwd(dx, ctx["slot"], ctx["n_features"])

@@ -21,15 +21,18 @@ from transformers.modeling_outputs import (
     BaseModelOutputWithPooling,
     BaseModelOutputWithPoolingAndCrossAttentions,
     CausalLMOutputWithPast,
+    Seq2SeqLMOutput,
 )
 from transformers.models.blip_2.modeling_blip_2 import Blip2ForConditionalGenerationModelOutput
 
 from .. import _lib
 from ..engine import opt as E_opt
+from ..engine import t5 as E_t5
 from ..engine import qformer as E_qf
 from ..engine import vision as E_vis
 from ..engine.packing import PackCache
 from . import generation
+from .t5 import T5ForConditionalGeneration
 
 
 # =============================================================================== containers
@@ -339,6 +342,28 @@ class _LMLossFn(torch.autograd.Function):
         return None, d_feats.to(ctx.feat_dtype), None, None, None, None, None
 
 
+class _Seq2SeqLossFn(torch.autograd.Function):
+    """Splice + flan-T5 encoder/decoder + cross entropy (v2.py:228-238); backward is dgrad-only
+    through decoder, cross-attention K/V, encoder and splice down to the video slots."""
+
+    @staticmethod
+    def forward(ctx, model, video_features, input_ids, attention_mask, video_mask, labels):
+        lm = model.language_model
+        out = E_t5.t5_forward(lm, lm._pack, input_ids, attention_mask, video_mask, video_features,
+                              labels=labels, save=True)
+        ctx.model, ctx.saved = model, out["ctx"]
+        ctx.feat_dtype = video_features.dtype
+        ctx.mark_non_differentiable(out["logits"], out["status"], out["encoder_last_hidden_state"])
+        return out["loss"], out["logits"], out["status"], out["encoder_last_hidden_state"]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gl, _gs, _ge):
+        lm = ctx.model.language_model
+        d_feats = E_t5.t5_backward(lm, lm._pack, ctx.saved, grad_loss)
+        ctx.saved = None
+        return None, d_feats.to(ctx.feat_dtype), None, None, None, None
+
+
 # =============================================================================== full model
 class VideoBlipForConditionalGeneration(PreTrainedModel):
     """Drop-in for eilev.model.v2.VideoBlipForConditionalGeneration (v2.py:106-501)."""
@@ -364,9 +389,10 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
                     f"decoder-only language model {config.text_config.model_type!r}: only OPT is built")
             self.language_model = OPTForCausalLM(config.text_config)
         else:
-            raise NotImplementedError(
-                "encoder-decoder language models (flan-T5) are the next row of the scope table "
-                "(SURVEY.md §8f) and are not built yet")
+            if config.text_config.model_type != "t5":
+                raise NotImplementedError(
+                    f"encoder-decoder language model {config.text_config.model_type!r}: only T5 is built")
+            self.language_model = T5ForConditionalGeneration(config.text_config)
         self._pack = PackCache()
         self.post_init()
 
@@ -478,6 +504,10 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
             attention_mask = torch.ones_like(input_ids)  # v2.py:216-217
 
         lm = self.language_model
+        if not self.config.use_decoder_only_language_model:
+            return self._forward_seq2seq(input_ids, attention_mask, video_input_mask, feats, labels,
+                                         decoder_input_ids, decoder_attention_mask, want_hidden, train,
+                                         vision_outputs, query_outputs, return_dict)
         if train:
             loss, logits, status = _LMLossFn.apply(self, feats, input_ids, attention_mask,
                                                    video_input_mask, labels, seed)
@@ -491,6 +521,32 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         if hidden_states is not None:
             hidden_states = tuple(h.to(self.dtype) for h in hidden_states)
         lm_outputs = CausalLMOutputWithPast(loss=loss, logits=logits, hidden_states=hidden_states)
+        if not return_dict:
+            output = (logits, vision_outputs, query_outputs, tuple(v for v in (loss, logits) if v is not None))
+            return ((loss,) + output) if loss is not None else output
+        return Blip2ForConditionalGenerationModelOutput(
+            loss=loss, logits=logits, vision_outputs=vision_outputs,
+            qformer_outputs=query_outputs, language_model_outputs=lm_outputs)
+
+    def _forward_seq2seq(self, input_ids, attention_mask, video_input_mask, feats, labels, decoder_input_ids,
+                         decoder_attention_mask, want_hidden, train, vision_outputs, query_outputs, return_dict):
+        """v2.py:228-238: the interleaved embeddings go to the T5 encoder, the labels
+        (shifted right) to the decoder."""
+        if want_hidden:
+            raise NotImplementedError("output_hidden_states=True is not supported for the seq2seq LM")
+        if decoder_attention_mask is not None and not bool(decoder_attention_mask.all()):
+            raise NotImplementedError("decoder_attention_mask with zeros is not supported (labels use -100)")
+        lm = self.language_model
+        if train:
+            loss, logits, status, enc = _Seq2SeqLossFn.apply(self, feats, input_ids, attention_mask,
+                                                             video_input_mask, labels)
+        else:
+            with torch.no_grad():
+                out = E_t5.t5_forward(lm, lm._pack, input_ids, attention_mask, video_input_mask, feats,
+                                      labels=labels, decoder_input_ids=decoder_input_ids)
+            loss, logits, status, enc = out["loss"], out["logits"], out["status"], out["encoder_last_hidden_state"]
+        self._last_splice_status = status
+        lm_outputs = Seq2SeqLMOutput(loss=loss, logits=logits, encoder_last_hidden_state=enc.to(self.dtype))
         if not return_dict:
             output = (logits, vision_outputs, query_outputs, tuple(v for v in (loss, logits) if v is not None))
             return ((loss,) + output) if loss is not None else output
@@ -523,6 +579,9 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         """Same contract as v2.py:254-324: returns only the newly generated token ids
         (decoder-only LM fed with embeddings)."""
         assert not (input_ids is None and pixel_values is None)  # v2.py:271
+        if not self.config.use_decoder_only_language_model:
+            raise NotImplementedError("generate() with the flan-T5 language model is not built yet "
+                                      "(forward / backward are; SURVEY.md §8f rank 2)")
         if pixel_values is not None:
             assert video_input_mask is not None  # v2.py:274
             video_input_mask = video_input_mask.bool()

@@ -129,7 +129,7 @@ def layernorm_bwd(dy, xin, gamma, mean, rstd, *, dx_add=None, dgamma=None, dbeta
     return dx
 
 
-def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout=None) -> AttnArgs:
+def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout=None, rel_bias=None) -> AttnArgs:
     """q: (B, Sq, >=H*D) view, k/v: (B, Skv, ...) views; last dim contiguous."""
     a = AttnArgs()
     a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
@@ -143,12 +143,17 @@ def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout=None)
     a.scale, a.causal = scale, 1 if causal else 0
     if dropout is not None and dropout[0] > 0.0:
         a.dropout_p, a.dropout_seed, a.dropout_salt = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
+    if rel_bias is not None:  # (heads, Sq + Skv - 1) f32 relative-position table (T5)
+        _need(rel_bias, torch.float32, "attention.rel_bias")
+        assert rel_bias.dim() == 2 and rel_bias.stride(1) == 1 and rel_bias.shape[0] == heads
+        assert rel_bias.shape[1] == q.shape[1] + k.shape[1] - 1
+        a.rel_bias, a.rel_bias_stride = rel_bias.data_ptr(), rel_bias.stride(0)
     return a
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float, *,
               causal: bool = False, key_mask: torch.Tensor | None = None,
-              need_lse: bool = False, dropout=None):
+              need_lse: bool = False, dropout=None, rel_bias: torch.Tensor | None = None):
     """Softmax attention.  q: (B, Sq, H*D), k/v: (B, Skv, H*D) bf16 views whose last dim is
     contiguous (they may be slices of one fused QKV buffer).  Returns o: (B, Sq, H*D)."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v")):
@@ -163,7 +168,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     if key_mask is not None:
         _need(key_mask, torch.uint8, "attention.key_mask")
         assert key_mask.is_contiguous() and key_mask.shape == (k.shape[0], k.shape[1])
-    a = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout)
+    a = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout, rel_bias)
     check(_lib.lib().vb_attention_fwd(C.byref(a), _stream()), "vb_attention_fwd")
     return (o, lse) if need_lse else o
 
@@ -177,7 +182,7 @@ def attention_uses_tcgen05(q, k, v, heads: int, *, causal=False, key_mask=None, 
 
 
 def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: bool = False,
-                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None, dropout=None):
+                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None, dropout=None, rel_bias=None):
     """Returns (dq, dk, dv) with the shapes of q, k, v (contiguous unless views are given)."""
     hd = q.shape[2]
     d = hd // heads
@@ -188,7 +193,7 @@ def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: boo
     delta = torch.empty((q.shape[0], heads, q.shape[1]), dtype=torch.float32, device=q.device)
     dq_acc = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.float32, device=q.device)
     b = AttnBwdArgs()
-    b.fwd = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout)
+    b.fwd = _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout, rel_bias)
     b.d_o, b.dq, b.dk, b.dv = d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     b.dq_bs, b.dq_rs = dq.stride(0), dq.stride(1)
     b.dk_bs, b.dk_rs = dk.stride(0), dk.stride(1)
@@ -290,9 +295,10 @@ def splice_bwd(d_embeds: torch.Tensor, slot_index: torch.Tensor, n_features: int
     return out
 
 
-def cross_entropy(logits: torch.Tensor, labels: torch.Tensor):
-    """Shifted causal-LM loss.  logits (B, L, V) bf16|f32; labels (B, L) int64.
-    Returns (loss f32 scalar tensor, row_lse, n_valid)."""
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, shift: int = 1):
+    """Mean CE with ignore_index -100.  shift=1: causal-LM loss (position l is scored against
+    labels[l+1]); shift=0: seq2seq loss (T5, labels aligned with the logits).
+    logits (B, L, V) bf16|f32; labels (B, L) int64.  Returns (loss f32 scalar, row_lse, n_valid)."""
     assert logits.dim() == 3 and logits.stride(2) == 1 and logits.dtype in (torch.bfloat16, torch.float32)
     b, l, v = logits.shape
     assert logits.stride(0) == l * logits.stride(1)
@@ -302,11 +308,11 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor):
     n_valid = torch.empty((), dtype=torch.int32, device=logits.device)
     check(_lib.lib().vb_cross_entropy(logits.data_ptr(), _DT[logits.dtype], labels.data_ptr(),
                                       loss.data_ptr(), row_lse.data_ptr(), n_valid.data_ptr(), b, l,
-                                      v, logits.stride(1), _stream()), "vb_cross_entropy")
+                                      v, logits.stride(1), int(shift), _stream()), "vb_cross_entropy")
     return loss, row_lse, n_valid
 
 
-def cross_entropy_bwd(logits, labels, row_lse, n_valid, grad_scale: torch.Tensor | None):
+def cross_entropy_bwd(logits, labels, row_lse, n_valid, grad_scale: torch.Tensor | None, shift: int = 1):
     b, l, v = logits.shape
     vpad = (v + 7) // 8 * 8
     d = torch.empty((b * l, vpad), dtype=torch.bfloat16, device=logits.device)
@@ -315,9 +321,63 @@ def cross_entropy_bwd(logits, labels, row_lse, n_valid, grad_scale: torch.Tensor
     check(_lib.lib().vb_cross_entropy_bwd(logits.data_ptr(), _DT[logits.dtype],
                                           labels.contiguous().data_ptr(), row_lse.data_ptr(),
                                           n_valid.data_ptr(), _ptr(grad_scale), d.data_ptr(), b, l,
-                                          v, logits.stride(1), vpad, _stream()),
+                                          v, logits.stride(1), vpad, int(shift), _stream()),
           "vb_cross_entropy_bwd")
     return d[:, :v]
+
+
+def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, *, save_stats: bool = False):
+    """T5LayerNorm over the last dim of a 2-D bf16 tensor: gamma * x * rsqrt(mean(x^2) + eps)."""
+    _need(x, torch.bfloat16, "rmsnorm.x")
+    _need(gamma, torch.float32, "rmsnorm.gamma")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    check(_lib.lib().vb_rmsnorm(x.data_ptr(), gamma.data_ptr(), y.data_ptr(), _ptr(rstd), rows, cols,
+                                x.stride(0), y.stride(0), float(eps), _stream()), "vb_rmsnorm")
+    return (y, rstd) if save_stats else y
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, rstd: torch.Tensor, *, dx_add=None):
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape
+    if dx_add is not None:
+        assert dx_add.is_contiguous() and dx_add.shape == x.shape
+    dx = torch.empty_like(dy)
+    check(_lib.lib().vb_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rstd.data_ptr(),
+                                    _ptr(dx_add), dx.data_ptr(), x.shape[0], x.shape[1], _stream()),
+          "vb_rmsnorm_bwd")
+    return dx
+
+
+def gated_gelu(h01: torch.Tensor) -> torch.Tensor:
+    """(rows, 2*dff) [wi_0 x | wi_1 x] -> gelu_new(first half) * second half, (rows, dff)."""
+    _need(h01, torch.bfloat16, "gated_gelu.h01")
+    assert h01.dim() == 2 and h01.is_contiguous() and h01.shape[1] % 2 == 0
+    rows, dff = h01.shape[0], h01.shape[1] // 2
+    out = torch.empty((rows, dff), dtype=torch.bfloat16, device=h01.device)
+    check(_lib.lib().vb_gated_gelu(h01.data_ptr(), out.data_ptr(), rows, dff, _stream()), "vb_gated_gelu")
+    return out
+
+
+def gated_gelu_bwd(d_out: torch.Tensor, h01: torch.Tensor) -> torch.Tensor:
+    assert d_out.is_contiguous() and h01.is_contiguous() and h01.shape[1] == 2 * d_out.shape[1]
+    d = torch.empty_like(h01)
+    check(_lib.lib().vb_gated_gelu_bwd(d_out.data_ptr(), h01.data_ptr(), d.data_ptr(), d_out.shape[0],
+                                       d_out.shape[1], _stream()), "vb_gated_gelu_bwd")
+    return d
+
+
+def embedding(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """table[ids] for a bf16 table; ids int64 of any shape -> (*ids.shape, dim)."""
+    _need(ids, torch.int64, "embedding.ids")
+    _need(table, torch.bfloat16, "embedding.table")
+    assert table.is_contiguous()
+    flat = ids.contiguous().view(-1)
+    out = torch.empty((flat.numel(), table.shape[1]), dtype=torch.bfloat16, device=table.device)
+    check(_lib.lib().vb_embedding(flat.data_ptr(), table.data_ptr(), out.data_ptr(), flat.numel(),
+                                  table.shape[1], table.shape[0], _stream()), "vb_embedding")
+    return out.view(*ids.shape, table.shape[1])
 
 
 def transpose(x: torch.Tensor) -> torch.Tensor:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+#define VB_ABI_VERSION 2
 
 /* dtype tags */
 #define VB_BF16 0
@@ -139,6 +139,11 @@ typedef struct vb_attn_args {
   int32_t reserved;
   const uint64_t* dropout_seed;
   uint64_t dropout_salt;
+  /* Additive relative-position bias (T5: HF:t5/modeling_t5.py compute_bias): f32 table
+   * rel_bias[h * rel_bias_stride + (j - i) + (Sq - 1)] added to scale * q_i.k_j; NULL: none.
+   * The table has Sq + Skv - 1 entries per head; no gradient is produced for it. */
+  const float* rel_bias;
+  int64_t rel_bias_stride;
 } vb_attn_args;
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
 /* 1 if vb_attention_fwd takes the tcgen05/TMEM kernel (non-causal, unmasked, no lse,
@@ -205,13 +210,31 @@ int vb_splice_bwd(const void* d_embeds, const int32_t* slot_index, void* d_featu
  * ---------------------------------------------------------------------- */
 int vb_cross_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels, float* loss,
                      float* row_lse, int32_t* n_valid, int64_t batch, int64_t seq, int64_t vocab,
-                     int64_t ldl, void* stream);
+                     int64_t ldl, int32_t shift, void* stream);
 /* dlogits (bf16, B*L x V, ldd) = grad_scale * (softmax - onehot) / n_valid on valid rows,
  * 0 elsewhere. grad_scale: f32 device scalar (upstream d loss) or NULL (=1). */
 int vb_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* labels,
                          const float* row_lse, const int32_t* n_valid, const float* grad_scale,
                          void* dlogits, int64_t batch, int64_t seq, int64_t vocab, int64_t ldl,
-                         int64_t ldd, void* stream);
+                         int64_t ldd, int32_t shift, void* stream);
+
+/* ------------------------------------------------------------------------ flan-T5 LM
+ * (eilev/model/v2.py:228-238 -> HF:t5/modeling_t5.py)
+ * y = gamma * x * rsqrt(mean(x^2) + eps)  — T5LayerNorm: no mean subtraction, no bias; fp32
+ * statistics, bf16 in/out; rstd (f32, rows) is written when non-NULL (saved for backward). */
+int vb_rmsnorm(const void* x, const float* gamma, void* y, float* rstd, int64_t rows, int64_t cols,
+               int64_t ldx, int64_t ldy, float eps, void* stream);
+/* dx = rstd * (g - x * rstd^2 * mean(g * x)), g = gamma * dy  (+ dx_add when non-NULL); contiguous bf16. */
+int vb_rmsnorm_bwd(const void* dy, const void* x, const float* gamma, const float* rstd, const void* dx_add,
+                   void* dx, int64_t rows, int64_t cols, void* stream);
+/* T5DenseGatedActDense middle: h01 = [wi_0 x | wi_1 x] (rows, 2*dff) bf16 ->
+ * out = gelu_new(h01[:, :dff]) * h01[:, dff:]  (tanh approximation), and its backward
+ * d_h01 = [d_out * h1 * gelu_new'(h0) | d_out * gelu_new(h0)]. */
+int vb_gated_gelu(const void* h01, void* out, int64_t rows, int64_t dff, void* stream);
+int vb_gated_gelu_bwd(const void* d_out, const void* h01, void* d_h01, int64_t rows, int64_t dff, void* stream);
+/* out[i, :] = table[ids[i], :] (bf16): decoder_input_ids -> shared embedding (ids clamped to the table). */
+int vb_embedding(const int64_t* ids, const void* table, void* out, int64_t n, int64_t dim, int64_t vocab,
+                 void* stream);
 
 /* ------------------------------------------------------------------------ elementwise */
 /* out(cols, rows) = in(rows, cols)^T, bf16 (operand staging for dgrad / wgrad GEMMs). */

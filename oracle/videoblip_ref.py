@@ -353,11 +353,11 @@ def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_value
     if decoder_input_ids is None:
         decoder_input_ids = t5_shift_right(labels, tcfg)
     dec = t5_decoder(sd, tcfg, decoder_input_ids, enc, attention_mask)
-    if tcfg.tie_word_embeddings:
+    # 4.33.1 scales the decoder output by d_model**-0.5 iff tie_word_embeddings; 5.5.0 froze that
+    # decision into config.scale_decoder_outputs (flan-t5: untied head, no scaling, in both)
+    if getattr(tcfg, "scale_decoder_outputs", tcfg.tie_word_embeddings):
         dec = dec * tcfg.d_model ** -0.5
-        head = sd["language_model.shared.weight"]
-    else:
-        head = sd["language_model.lm_head.weight"]
+    head = sd["language_model.lm_head.weight"]
     logits = F.linear(dec, head.float())
     out.update(inputs_embeds=emb, encoder_last_hidden_state=enc, logits=logits)
     if labels is not None:

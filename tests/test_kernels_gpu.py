@@ -502,3 +502,89 @@ def test_token_logprob():
     got2 = ops.token_logprob(logits.to(torch.bfloat16), torch.tensor([1, 2, 3], device="cuda"), rows)
     ref2 = torch.log_softmax(logits.to(torch.bfloat16).float(), -1)
     assert torch.allclose(got2, torch.stack([ref2[6, 1], ref2[6, 2], ref2[0, 3]]), atol=1e-3)
+
+
+def test_rmsnorm_fwd_bwd_matches_torch():
+    ops = _ops()
+    for rows, cols in ((37, 2048), (5, 128), (9, 72)):
+        x = _rand(rows, cols, seed=110)
+        g = (1 + 0.1 * torch.randn(cols, device="cuda")).float()
+        y, rstd = ops.rmsnorm(x, g, 1e-6, save_stats=True)
+        xf = x.float().requires_grad_(True)
+        ref = g * xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+        _close(y, ref, atol=0.03, rtol=0.02, what="rmsnorm")
+        dy = _rand(rows, cols, seed=111)
+        add = _rand(rows, cols, seed=112)
+        ref.backward(dy.float())
+        dx = ops.rmsnorm_bwd(dy, x, g, rstd, dx_add=add)
+        _close(dx, xf.grad + add.float(), atol=0.04, rtol=0.03, what="rmsnorm bwd")
+
+
+def test_gated_gelu_fwd_bwd_matches_torch():
+    ops = _ops()
+    rows, dff = 33, 256
+    h01 = _rand(rows, 2 * dff, seed=113) * 2
+    out = ops.gated_gelu(h01)
+    hf = h01.float().requires_grad_(True)
+    ref = torch.nn.functional.gelu(hf[:, :dff], approximate="tanh") * hf[:, dff:]
+    _close(out, ref, atol=0.03, rtol=0.02, what="gated gelu")
+    d_out = _rand(rows, dff, seed=114)
+    ref.backward(d_out.float())
+    _close(ops.gated_gelu_bwd(d_out, h01), hf.grad, atol=0.04, rtol=0.03, what="gated gelu bwd")
+
+
+@pytest.mark.parametrize("causal,sq,skv", [(False, 104, 104), (True, 9, 9), (False, 9, 104), (True, 70, 70)])
+def test_attention_relative_bias_fwd_bwd(causal, sq, skv):
+    """T5 attention: unscaled scores + per-head relative-position table (+ masks)."""
+    ops = _ops()
+    b, heads, d = 2, 3, 64
+    hd = heads * d
+    q, k, v = _rand(b, sq, hd, seed=120), _rand(b, skv, hd, seed=121), _rand(b, skv, hd, seed=122)
+    tab = torch.randn(heads, sq + skv - 1, device="cuda")
+    mask = torch.ones(b, skv, dtype=torch.uint8, device="cuda")
+    if not causal:
+        mask[1, skv - 5:] = 0
+    km = None if causal else mask
+    o, lse = ops.attention(q, k, v, heads, 0.2, causal=causal, key_mask=km, need_lse=True, rel_bias=tab)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = qf.view(b, sq, heads, d).transpose(1, 2)
+    kh = kf.view(b, skv, heads, d).transpose(1, 2)
+    vh = vf.view(b, skv, heads, d).transpose(1, 2)
+    i = torch.arange(sq, device="cuda")[:, None]
+    j = torch.arange(skv, device="cuda")[None, :]
+    s = qh @ kh.transpose(-1, -2) * 0.2 + tab[:, (j - i) + (sq - 1)][None]
+    if causal:
+        s = s.masked_fill(j > i + (skv - sq), -1e30)
+    else:
+        s = s.masked_fill(mask[:, None, None, :] == 0, -1e30)
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(b, sq, hd)
+    _close(o, ref, atol=0.03, rtol=0.03, what="attention rel_bias")
+    d_o = _rand(b, sq, hd, seed=123)
+    ref.backward(d_o.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, heads, 0.2, causal=causal, key_mask=km, rel_bias=tab)
+    _close(dq, qf.grad, atol=0.05, rtol=0.05, what="rel_bias dq")
+    _close(dk, kf.grad, atol=0.05, rtol=0.05, what="rel_bias dk")
+    _close(dv, vf.grad, atol=0.05, rtol=0.05, what="rel_bias dv")
+
+
+def test_cross_entropy_unshifted():
+    ops = _ops()
+    b, l, v = 2, 9, 264
+    logits = (torch.randn(b, l, v, device="cuda") * 2).to(torch.bfloat16)
+    labels = torch.randint(0, v, (b, l), device="cuda")
+    labels[1, 6:] = -100
+    loss, row_lse, n_valid = ops.cross_entropy(logits, labels, shift=0)
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf.view(-1, v), labels.view(-1), ignore_index=-100)
+    assert abs(float(loss) - float(ref)) < 2e-3 and int(n_valid) == 15
+    ref.backward()
+    d = ops.cross_entropy_bwd(logits, labels, row_lse, n_valid, None, shift=0)
+    _close(d.view(b, l, v), lf.grad, atol=2e-3, rtol=0.05, what="ce bwd unshifted")
+
+
+def test_embedding_gather():
+    ops = _ops()
+    table = _rand(50, 128, seed=130)
+    ids = torch.tensor([[0, 49, 7], [3, 3, 60]], device="cuda")
+    out = ops.embedding(ids, table)
+    assert torch.equal(out, table[ids.clamp(max=49)])

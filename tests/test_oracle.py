@@ -108,3 +108,36 @@ def test_oracle_classify_matches_reference_golden(name):
                      p["pixel_values"], p["video_input_mask"], cx["class_attention_mask"])
     assert got.shape == cx["scores"].shape
     assert torch.allclose(got, cx["scores"], atol=2e-4, rtol=1e-4), (got, cx["scores"])
+
+
+def _load_t5():
+    fx = torch.load(GOLDEN / "small_t5.pt", weights_only=False)
+    cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    return fx, cfg
+
+
+def test_oracle_t5_forward_matches_reference_golden():
+    """flan-T5 branch (v2.py:228-238 -> T5ForConditionalGeneration): golden from the real reference
+    (tests/golden/make_golden_t5.py)."""
+    fx, cfg = _load_t5()
+    out = R.videoblip_forward_t5(fx["state_dict"], cfg, **fx["inputs"])
+    assert torch.allclose(out["query_output"], fx["query_output"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(out["encoder_last_hidden_state"], fx["encoder_last_hidden_state"], atol=3e-4, rtol=1e-4)
+    assert torch.allclose(out["logits"], fx["logits"], atol=1e-3, rtol=1e-4)
+    assert abs(float(out["loss"]) - float(fx["loss"])) < 1e-4
+
+
+def test_oracle_t5_gradients_match_reference_golden():
+    fx, cfg = _load_t5()
+    sd = {k: v.clone() for k, v in fx["state_dict"].items()}
+    trainable = [k for k in sd if k in fx["grads"]]
+    assert len(trainable) == len(fx["grads"]) > 0
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    out = R.videoblip_forward_t5(sd, cfg, **fx["inputs"])
+    out["loss"].backward()
+    for k in trainable:
+        g, ref = sd[k].grad, fx["grads"][k]
+        assert g is not None, k
+        # this fixture's gradients are O(100): compare in relative L2 (fp32 summation order)
+        assert float((g - ref).norm()) < 2e-3 * float(ref.norm()) + 1e-4, k  # (key biases have zero gradient)
