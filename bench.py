@@ -37,11 +37,25 @@ GRAD_ACCUM = 16
 FLOPS_PER_DATAPOINT = 83.88e12
 
 
-def full_config(dropout: float = 0.0):
-    """eilev-blip2-opt-2.7b architecture.  dropout = 0.1 is the checkpoint's / recipe's value
-    (Q-Former hidden + attention-probs dropout, OPT hidden dropout; OPT attention_dropout 0)."""
+def full_config(dropout: float = 0.0, lm: str = "opt"):
+    """eilev-blip2-opt-2.7b architecture (lm="opt") or eilev-blip2-flan-t5-xl (lm="t5",
+    BASELINE configs[3]).  dropout = 0.1 is the checkpoint's / recipe's value (Q-Former hidden +
+    attention-probs dropout, OPT hidden dropout; OPT attention_dropout 0)."""
     from transformers import Blip2Config
 
+    if lm == "t5":
+        text = dict(model_type="t5", d_model=2048, d_kv=64, d_ff=5120, num_layers=24, num_decoder_layers=24,
+                    num_heads=32, vocab_size=32128, feed_forward_proj="gated-gelu", tie_word_embeddings=False,
+                    decoder_start_token_id=0, pad_token_id=0, eos_token_id=1, dropout_rate=0.0,
+                    relative_attention_num_buckets=32, relative_attention_max_distance=128)
+        return Blip2Config(
+            vision_config=dict(hidden_size=1408, intermediate_size=6144, num_hidden_layers=39,
+                               num_attention_heads=16, patch_size=14, image_size=224, hidden_act="gelu",
+                               layer_norm_eps=1e-6, qkv_bias=True),
+            qformer_config=dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                                intermediate_size=3072, encoder_hidden_size=1408, cross_attention_frequency=2,
+                                vocab_size=30522, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout),
+            text_config=text, num_query_tokens=QUERY_TOKENS)
     return Blip2Config(
         vision_config=dict(hidden_size=1408, intermediate_size=6144, num_hidden_layers=39,
                            num_attention_heads=16, patch_size=14, image_size=224, hidden_act="gelu",
@@ -55,11 +69,29 @@ def full_config(dropout: float = 0.0):
         num_query_tokens=QUERY_TOKENS)
 
 
-def synthetic_batch(seed: int, clips: int = CLIPS, frames: int = FRAMES, pad_to: int = 8):
+def synthetic_batch(seed: int, clips: int = CLIPS, frames: int = FRAMES, pad_to: int = 8, lm: str = "opt"):
     """[bos] + clips x (32 pad-id slots + '\\n' + 24 text ids), right
-    padded to a multiple of 8 (train_v2.py:214); labels = last 12 text tokens."""
+    padded to a multiple of 8 (train_v2.py:214); labels = last 12 text tokens.
+    lm="t5" (config 4, eilev/data/utils.py:200-217): no bos, pad id 0, '\\n' = 3, eos = 1 after
+    the last prompt; labels = 12 target ids for the decoder."""
     g = torch.Generator().manual_seed(seed)
     px = torch.randn(clips, 3, frames, 224, 224, generator=g)
+    if lm == "t5":
+        ids, vm = [], []
+        for _ in range(clips):
+            ids += [0] * QUERY_TOKENS + [3] + torch.randint(4, 32000, (TEXT_PER_CLIP,), generator=g).tolist()
+            vm += [1] * QUERY_TOKENS + [0] * (1 + TEXT_PER_CLIP)
+        ids += [1]
+        vm += [0]
+        n = len(ids)
+        pad = (-n) % pad_to
+        return dict(
+            pixel_values=px,
+            input_ids=torch.tensor([ids + [0] * pad]),
+            attention_mask=torch.tensor([[1] * n + [0] * pad]),
+            video_input_mask=torch.tensor([vm + [0] * pad]),
+            labels=torch.randint(4, 32000, (1, TARGET_TOKENS), generator=g),
+        )
     ids, vm = [2], [0]
     for _ in range(clips):
         ids += [1] * QUERY_TOKENS + [50118] + torch.randint(4, 50000, (TEXT_PER_CLIP,), generator=g).tolist()
@@ -76,9 +108,24 @@ def synthetic_batch(seed: int, clips: int = CLIPS, frames: int = FRAMES, pad_to:
     )
 
 
-def workload_config(world: int, seq_len: int, cuda_graph, dropout: float = 0.1):
-    cfg = {"workload": "eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 per GPU "
-                       "(17 clips, L=976), grad-accum 16 with all-reduce + AdamW every 16th step",
+def t5_flops_per_datapoint(l: int = 976, ld: int = TARGET_TOKENS) -> float:
+    """ViT + Q-Former (as for OPT) + flan-t5-xl fwd and dgrad-only bwd (attention bwd 2.5x)."""
+    d, inner, dff, v, layers = 2048, 2048, 5120, 32128, 24
+    enc_lin = 2.0 * l * (3 * d * inner + inner * d + 3 * d * dff) * layers
+    enc_att = 4.0 * l * l * inner * layers
+    dec_lin = 2.0 * ld * (3 * d * inner + inner * d + 2 * d * inner + 3 * d * dff) * layers + 2.0 * ld * d * v
+    ckv = 2.0 * l * d * 2 * inner * layers
+    dec_att = (2.0 * ld * ld + 4.0 * ld * l) * inner * layers
+    fwd = enc_lin + enc_att + dec_lin + ckv + dec_att
+    bwd = enc_lin + dec_lin + ckv + 2.5 * (enc_att + dec_att)
+    return 70.82e12 + 1.028e12 + 1.150e12 + 0.0064e12 * 2048 / 2560 + fwd + bwd
+
+
+def workload_config(world: int, seq_len: int, cuda_graph, dropout: float = 0.1, lm: str = "opt"):
+    name = ("eilev-blip2-flan-t5-xl 16-ctx x 8-frame fwd+bwd bs=1 per GPU (17 clips, encoder L=976, 12 target "
+            "tokens)" if lm == "t5" else
+            "eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 per GPU (17 clips, L=976)")
+    cfg = {"workload": name + ", grad-accum 16 with all-reduce + AdamW every 16th step",
            "global_batch": world, "seq_len": seq_len, "parallelism": f"dp{world}",
            "weights": "random-init (seeded N(0,0.02))",
            "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
@@ -316,10 +363,10 @@ def gpu_arm(args) -> None:
         dist.init_process_group("nccl", device_id=device)
     _lib.lib()  # fail loudly if the extension is missing
 
-    cfg = full_config(args.dropout)
+    cfg = full_config(args.dropout, args.lm)
     model = build_gpu_model(cfg, device)
     decode = decode8 = None
-    if rank == 0 and not args.no_decode and not args.profile:
+    if rank == 0 and not args.no_decode and not args.profile and args.lm == "opt":
         # independent workloads (BASELINE configs[4], batch sweep ends), measured before the training loop
         decode = measure_decode(model, device)
         decode8 = measure_decode(model, device, batch=8)
@@ -330,7 +377,7 @@ def gpu_arm(args) -> None:
         for _ in range(2):
             dist.all_reduce(trainer.flat.grads)
         torch.cuda.synchronize()
-    host = synthetic_batch(1000 + rank)
+    host = synthetic_batch(1000 + rank, lm=args.lm)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(device) for k, v in host.items()}
 
@@ -405,7 +452,8 @@ def gpu_arm(args) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world, int(host["input_ids"].shape[1]), not args.no_graph, args.dropout),
+            "config": workload_config(world, int(host["input_ids"].shape[1]), not args.no_graph, args.dropout,
+                                      args.lm),
             "clocks": clocks,
             "e2e": {"value": e2e_clips, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -417,7 +465,8 @@ def gpu_arm(args) -> None:
                          "kernel": "gemm_tcgen05_kernel (ViT/Q-Former launches with M>=4096)",
                          "launches": g_n, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"
                          if peaks else "fallback 1400"},
-            "step_flops_frac": FLOPS_PER_DATAPOINT * args.steps / (ms * 1e-3) / (peak * 1e12) if peak else None,
+            "step_flops_frac": (FLOPS_PER_DATAPOINT if args.lm == "opt" else t5_flops_per_datapoint())
+            * args.steps / (ms * 1e-3) / (peak * 1e12) if peak else None,
         }
         if decode is not None:
             hbm = peaks.get("hbm_gbs", 6650.0)
@@ -430,7 +479,7 @@ def gpu_arm(args) -> None:
                                        "peak": hbm, "unit": "GB/s",
                                        "frac": decode8["bytes_per_token"] / (decode8["ms_per_token"] * 1e-3) / 1e9 / hbm}
                 line["decode_batch8"] = decode8
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.lm == "opt":
             res = run_cpu_baseline(cfg, clips=args.cpu_clips, steps=1, warmup=0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -449,6 +498,9 @@ def main() -> None:
     ap.add_argument("--profile", action="store_true", help="run one profiler-bracketed step and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA graph")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tok/s measurement")
+    ap.add_argument("--lm", default="opt", choices=["opt", "t5"],
+                    help="language model of the workload: opt = eilev-blip2-opt-2.7b (the headline), "
+                         "t5 = eilev-blip2-flan-t5-xl (BASELINE configs[3], fwd+bwd only)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="dropout of the training step (0.1 = the reference recipe; 0 = parity configuration)")
     args = ap.parse_args()

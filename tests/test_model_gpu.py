@@ -446,3 +446,68 @@ def test_t5_generate_not_built_and_text_only():
     with torch.no_grad():
         out = m(i["input_ids"], attention_mask=i["attention_mask"], labels=i["labels"], return_dict=True)
     assert torch.isfinite(out.loss)
+
+
+def test_t5_real_dims_shallow_against_oracle():
+    """flan-t5-xl layer shapes (d_model 2048, 32 heads x 64, d_ff 5120, vocab 32128) with 2 + 2
+    layers behind the real-width ViT / Q-Former: exercises the tcgen05 tiles on the T5 GEMM
+    shapes (6144 / 2048 / 10240 wide), the biased flash attention at L = 160 and the
+    cross-attention K|V batching.  q / k projections are shrunk as in the golden fixture
+    (unscaled attention).  Tolerance: logits rel-L2 <= 2.5 %, loss |d| <= 0.05, grads <= 10 %."""
+    from oracle import videoblip_ref as R
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    from eilev_b200.train import freeze_for_recipe
+    torch.manual_seed(0)
+    spec = dict(REAL_DIMS)
+    spec["text_config"] = dict(model_type="t5", d_model=2048, d_kv=64, d_ff=5120, num_layers=2, num_decoder_layers=2,
+                               num_heads=32, vocab_size=32128, feed_forward_proj="gated-gelu",
+                               tie_word_embeddings=False, decoder_start_token_id=0, pad_token_id=0, eos_token_id=1,
+                               dropout_rate=0.0)
+    cfg = Blip2Config(**spec)
+    m = VideoBlipForConditionalGeneration(cfg)
+    sd = R.sane_init_({k: v.clone() for k, v in m.state_dict().items()}, seed=6, std=0.02)
+    for k in sd:
+        if k.startswith("language_model.") and k.endswith((".q.weight", ".k.weight")):
+            sd[k] = sd[k] * 0.25
+    sd["language_model.encoder.embed_tokens.weight"] = sd["language_model.shared.weight"]
+    sd["language_model.decoder.embed_tokens.weight"] = sd["language_model.shared.weight"]
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(4)
+    nv, t, nq = 2, 2, 32
+    px = torch.randn(nv, 3, t, 224, 224, generator=g)
+    ids, vm = [], []
+    for _ in range(nv):
+        ids += [0] * nq + [3] + torch.randint(4, 32000, (43,), generator=g).tolist()
+        vm += [1] * nq + [0] * 44
+    ids += [1]; vm += [0]
+    pad = (-len(ids)) % 8
+    attn = [1] * len(ids) + [0] * pad
+    ids += [0] * pad; vm += [0] * pad
+    labels = torch.randint(4, 32000, (1, 10), generator=g)
+    labels[0, 8:] = -100
+    inputs = dict(input_ids=torch.tensor([ids]), attention_mask=torch.tensor([attn]), pixel_values=px,
+                  video_input_mask=torch.tensor([vm]), labels=labels)
+    trainable = [k for k in sd if k.startswith(("qformer.", "query_tokens", "language_projection."))]
+    sdg = {k: v.clone() for k, v in sd.items()}
+    for k in trainable:
+        sdg[k].requires_grad_(True)
+    ref = R.videoblip_forward_t5(sdg, cfg, **inputs)
+    ref["loss"].backward()
+
+    m = m.to("cuda", torch.bfloat16).train()
+    freeze_for_recipe(m)
+    out = m(**cuda(inputs), return_dict=True)
+    out.loss.backward()
+    r = dict(logits=rel_l2(out.logits, ref["logits"]), logits_max_abs=max_abs(out.logits, ref["logits"]),
+             logits_std=float(ref["logits"].std()), loss=float(out.loss.detach()), loss_ref=float(ref["loss"]))
+    num = den = 0.0
+    for n_, p in m.named_parameters():
+        if p.grad is not None:
+            rg = sdg[n_].grad
+            num += float((p.grad.float().cpu() - rg).pow(2).sum())
+            den += float(rg.pow(2).sum())
+    r["grad_rel_l2"] = (num / den) ** 0.5
+    _dump("t5_real_dims_shallow", **r)
+    assert r["logits"] < 0.025, r
+    assert abs(r["loss"] - r["loss_ref"]) < 0.05, r
+    assert r["grad_rel_l2"] < 0.10, r
