@@ -211,6 +211,66 @@ def t5_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vide
     return out
 
 
+# --------------------------------------------------------------------------- generate
+def t5_encode(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features) -> dict:
+    """Encoder pass + the cross-attention K|V of every decoder layer (computed once per prompt;
+    HF keeps them in the EncoderDecoderCache).  Returns the state consumed by t5_decode_logits."""
+    cfg = lm.config
+    _check_cfg(cfg)
+    w = pack_t5(lm, cache, need_backward=False)
+    dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
+    inner = heads * dkv
+    eps = float(cfg.layer_norm_epsilon)
+    b, l = input_ids.shape
+    rows = b * l
+    emb, _, _, _, status = ops.embed_splice(input_ids, attention_mask, video_mask, w["shared"],
+                                            video_features, None, 0, want_hidden=False)
+    key_mask = attention_mask.to(torch.uint8).contiguous()
+    enc_bias = rel_bias_table(w["enc_rel"], l, l, True, cfg)
+    x = emb.view(rows, dm)
+    for lw in w["enc"]:
+        y = ops.rmsnorm(x, lw["ln1"], eps)
+        qkv = ops.gemm(y, lw["qkv_w"]).view(b, l, 3 * inner)
+        o = ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], heads, 1.0,
+                          key_mask=key_mask, rel_bias=enc_bias)
+        x_mid = ops.gemm(o.view(rows, inner), lw["o_w"], residual=x)
+        x, _ = _ff_fwd(x_mid, lw["ff"], eps)
+    enc_out = ops.rmsnorm(x, w["enc_ln"], eps)
+    ckv = ops.gemm(enc_out, w["ckv_w"]).view(b, l, len(w["dec"]) * 2 * inner)
+    return dict(ckv=ckv, key_mask=key_mask, status=status, b=b, l=l, enc_out=enc_out.view(b, l, dm))
+
+
+def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.Tensor) -> torch.Tensor:
+    """Next-token logits f32 (B, V) after the decoder prefix (B, t).  The prefix is re-run every
+    step: a decode step is bound by streaming the 2.7 GB of decoder weights, which a t-row
+    GEMM does exactly once, so caching the self-attention K/V would not change the traffic."""
+    cfg = lm.config
+    w = pack_t5(lm, cache, need_backward=False)
+    dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
+    inner = heads * dkv
+    eps = float(cfg.layer_norm_epsilon)
+    b, t = decoder_input_ids.shape
+    rows_d = b * t
+    ckv, key_mask = enc["ckv"], enc["key_mask"]
+    xd = ops.embedding(decoder_input_ids, w["shared"]).view(rows_d, dm)
+    dec_bias = rel_bias_table(w["dec_rel"], t, t, False, cfg)
+    for li, lw in enumerate(w["dec"]):
+        y = ops.rmsnorm(xd, lw["ln1"], eps)
+        qkv = ops.gemm(y, lw["qkv_w"]).view(b, t, 3 * inner)
+        o = ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], heads, 1.0,
+                          causal=True, rel_bias=dec_bias)
+        x1 = ops.gemm(o.view(rows_d, inner), lw["o_w"], residual=xd)
+        cq = ops.gemm(ops.rmsnorm(x1, lw["ln2"], eps), lw["cq_w"]).view(b, t, inner)
+        co = ops.attention(cq, ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner],
+                           ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner], heads, 1.0, key_mask=key_mask)
+        x2 = ops.gemm(co.view(rows_d, inner), lw["co_w"], residual=x1)
+        xd, _ = _ff_fwd(x2, lw["ff"], eps)
+    last = xd.view(b, t, dm)[:, -1, :].contiguous()
+    final = ops.rmsnorm(last, w["dec_ln"], eps)
+    alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
+    return ops.gemm(final, w["head"], alpha=alpha, out_dtype=torch.float32)
+
+
 def t5_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None):
     """dgrad-only backward: returns d(video_features) (n_features, d_model) bf16."""
     cfg = lm.config

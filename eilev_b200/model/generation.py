@@ -18,6 +18,59 @@ from __future__ import annotations
 import torch
 
 from ..engine import opt as E_opt
+from ..engine import t5 as E_t5
+
+class _OptStepper:
+    """Decoder-only LM: prompt prefill into the paged KV cache, then one token per step."""
+
+    start_token = None
+
+    def __init__(self, lm) -> None:
+        self.lm = lm
+
+    def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
+        logits, self.state = E_opt.opt_prefill(self.lm, self.lm._pack, input_ids, attention_mask, video_mask,
+                                               feats, max_new)
+        self.status = self.state["status"]
+        return logits
+
+    def graph(self, rows, dev):
+        return E_opt.DecodeGraph(self.lm, self.lm._pack, self.state, rows, dev)
+
+    def step(self, tokens):
+        return E_opt.opt_decode_step(self.lm, self.lm._pack, tokens, self.state)
+
+    def reorder(self, src) -> None:
+        self.state["kv"].reorder(src)
+        for key in ("ctx_len", "first_valid", "n_valid"):
+            self.state[key].copy_(self.state[key][src])  # in place: the decode program holds these pointers
+
+
+class _T5Stepper:
+    """Encoder-decoder LM (flan-T5): the encoder and the cross-attention K|V run once, every
+    step re-runs the decoder over the generated prefix (see engine/t5.py::t5_decode_logits)."""
+
+    def __init__(self, lm) -> None:
+        self.lm = lm
+        self.start_token = int(lm.config.decoder_start_token_id)
+
+    def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
+        self.enc = E_t5.t5_encode(self.lm, self.lm._pack, input_ids, attention_mask, video_mask, feats)
+        self.status = self.enc["status"]
+        self.prefix = torch.full((input_ids.shape[0], 1), self.start_token, dtype=torch.long,
+                                 device=input_ids.device)
+        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.prefix)
+
+    def graph(self, rows, dev):
+        return None  # the prefix grows every step
+
+    def step(self, tokens):
+        self.prefix = torch.cat([self.prefix, tokens.view(-1, 1)], dim=1)
+        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.prefix)
+
+    def reorder(self, src) -> None:
+        self.prefix = self.prefix[src]  # beams of one prompt share its encoder rows
+
 
 _UNSUPPORTED = ("penalty_alpha", "num_beam_groups", "diversity_penalty", "constraints",
                 "force_words_ids", "assistant_model", "prompt_lookup_num_tokens")
@@ -124,16 +177,25 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
         attention_mask = attention_mask[rep_idx]
         video_mask = video_mask[rep_idx] if video_mask is not None else None
 
-    logits, state = E_opt.opt_prefill(lm, lm._pack, input_ids, attention_mask, video_mask,
-                                      video_features, max_new)
-    model._last_splice_status = state["status"]
+    stepper = _OptStepper(lm) if model.config.use_decoder_only_language_model else _T5Stepper(lm)
+    logits = stepper.prefill(input_ids, attention_mask, video_mask, video_features, max_new)
+    model._last_splice_status = stepper.status
+
+    def finish(tokens):
+        """HF returns only the new tokens for a decoder-only LM fed with embeddings, and
+        [decoder_start_token] + new tokens for an encoder-decoder LM."""
+        if stepper.start_token is None:
+            return tokens
+        return torch.cat([torch.full((tokens.shape[0], 1), stepper.start_token, dtype=torch.long, device=dev),
+                          tokens], dim=1)
+
     if num_beams > 1:
-        return _beam_search(lm, logits, state, b, num_beams, max_new, min_new, eos_ids, pad_id, rep,
-                            length_penalty, early_stopping, do_sample, temperature, top_k, top_p)
+        return finish(_beam_search(stepper, logits, b, num_beams, max_new, min_new, eos_ids, pad_id, rep,
+                                   length_penalty, early_stopping, do_sample, temperature, top_k, top_p))
 
     rows = input_ids.shape[0]
     use_graph = bool(kw.get("use_cuda_graph", max_new >= 8)) and rows <= 16
-    dgraph = E_opt.DecodeGraph(lm, lm._pack, state, rows, dev) if use_graph and max_new > 1 else None
+    dgraph = stepper.graph(rows, dev) if use_graph and max_new > 1 else None
     generated = torch.empty((rows, 0), dtype=torch.long, device=dev)
     unfinished = torch.ones(rows, dtype=torch.bool, device=dev)
     eos_t = torch.tensor(eos_ids, device=dev, dtype=torch.long) if eos_ids else None
@@ -152,11 +214,11 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
             if not bool(unfinished.any()):
                 break
         if step + 1 < max_new:
-            logits = dgraph.step(nxt) if dgraph is not None else E_opt.opt_decode_step(lm, lm._pack, nxt, state)
-    return generated
+            logits = dgraph.step(nxt) if dgraph is not None else stepper.step(nxt)
+    return finish(generated)
 
 
-def _beam_search(lm, logits, state, batch, nb, max_new, min_new, eos_ids, pad_id, rep,
+def _beam_search(stepper, logits, batch, nb, max_new, min_new, eos_ids, pad_id, rep,
                  length_penalty, early_stopping, do_sample, temperature, top_k, top_p):
     """Standard beam search with HF's scoring: hypotheses are ranked by
     sum_logprobs / generated_len**length_penalty (BeamHypotheses.add)."""
@@ -230,10 +292,8 @@ def _beam_search(lm, logits, state, batch, nb, max_new, min_new, eos_ids, pad_id
         generated = torch.cat([generated[src], next_tokens.view(-1, 1)], dim=1)
         if all(done) or step + 1 == max_new:
             break
-        state["kv"].reorder(src)
-        for key in ("ctx_len", "first_valid", "n_valid"):
-            state[key].copy_(state[key][src])  # in place: the decode program holds these pointers
-        logits = E_opt.opt_decode_step(lm, lm._pack, next_tokens.view(-1), state)
+        stepper.reorder(src)
+        logits = stepper.step(next_tokens.view(-1))
 
     out = []
     for i in range(batch):

@@ -579,9 +579,6 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         """Same contract as v2.py:254-324: returns only the newly generated token ids
         (decoder-only LM fed with embeddings)."""
         assert not (input_ids is None and pixel_values is None)  # v2.py:271
-        if not self.config.use_decoder_only_language_model:
-            raise NotImplementedError("generate() with the flan-T5 language model is not built yet "
-                                      "(forward / backward are; SURVEY.md §8f rank 2)")
         if pixel_values is not None:
             assert video_input_mask is not None  # v2.py:274
             video_input_mask = video_input_mask.bool()

@@ -145,7 +145,7 @@ def _attn_args(q, k, v, o, lse, key_mask, heads, d, scale, causal, dropout=None,
         a.dropout_p, a.dropout_seed, a.dropout_salt = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
     if rel_bias is not None:  # (heads, Sq + Skv - 1) f32 relative-position table (T5)
         _need(rel_bias, torch.float32, "attention.rel_bias")
-        assert rel_bias.dim() == 2 and rel_bias.stride(1) == 1 and rel_bias.shape[0] == heads
+        assert rel_bias.dim() == 2 and rel_bias.shape[0] == heads and (rel_bias.shape[1] == 1 or rel_bias.stride(1) == 1)
         assert rel_bias.shape[1] == q.shape[1] + k.shape[1] - 1
         a.rel_bias, a.rel_bias_stride = rel_bias.data_ptr(), rel_bias.stride(0)
     return a

@@ -366,6 +366,39 @@ def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_value
 
 
 @torch.no_grad()
+def greedy_generate_t5(sd, config, input_ids, attention_mask, pixel_values, video_input_mask, max_new_tokens,
+                       eos_token_id=None):
+    """v2.py:254-324 with the seq2seq LM and greedy search: encoder once, decoder re-run on the
+    growing prefix (no cache; small cases only).  Returns [decoder_start] + new tokens, rows that
+    hit eos are padded afterwards (HF:generation/utils.py greedy loop)."""
+    tcfg = config.text_config
+    feats = None
+    if pixel_values is not None:
+        feats = video_features(sd, config, pixel_values)[0]
+    emb = sd["language_model.shared.weight"].float()[input_ids]
+    if feats is not None:
+        emb = emb.clone()
+        emb[video_input_mask.bool()] = feats
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    enc = t5_encoder(sd, tcfg, emb, attention_mask)
+    b = input_ids.shape[0]
+    seq = torch.full((b, 1), tcfg.decoder_start_token_id, dtype=torch.long)
+    done = torch.zeros(b, dtype=torch.bool)
+    scale = tcfg.d_model ** -0.5 if getattr(tcfg, "scale_decoder_outputs", tcfg.tie_word_embeddings) else 1.0
+    for _ in range(max_new_tokens):
+        dec = t5_decoder(sd, tcfg, seq, enc, attention_mask)
+        nxt = F.linear(dec[:, -1] * scale, sd["language_model.lm_head.weight"].float()).argmax(-1)
+        if eos_token_id is not None:
+            nxt = torch.where(done, torch.full_like(nxt, tcfg.pad_token_id), nxt)
+            done = done | (nxt == eos_token_id)
+        seq = torch.cat([seq, nxt[:, None]], dim=1)
+        if eos_token_id is not None and bool(done.all()):
+            break
+    return seq
+
+
+@torch.no_grad()
 def classify(sd, config, prompt_input_ids, class_input_ids, prompt_attention_mask=None, pixel_values=None,
              prompt_video_input_mask=None, class_attention_mask=None):
     """v2.py:326-501 — mean log-likelihood (batch, num_classes) of each class continuation

@@ -87,12 +87,16 @@ def main():
     out.loss.backward()
     hook.remove()
     grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
-    fixture = dict(config=cfg.to_dict(), state_dict={k: v.clone() for k, v in model.state_dict().items()},
+    gen_inputs = {k: v for k, v in inputs.items() if k != "labels"}
+    with torch.no_grad():
+        gen = model.generate(**gen_inputs, max_new_tokens=6, do_sample=False, num_beams=1)
+    fixture = dict(generated=gen, config=cfg.to_dict(), state_dict={k: v.clone() for k, v in model.state_dict().items()},
                    inputs=inputs, loss=out.loss.detach(), logits=out.logits.detach(),
                    encoder_last_hidden_state=out.language_model_outputs.encoder_last_hidden_state.detach(),
                    query_output=out.qformer_outputs.last_hidden_state.detach(), grads=grads)
     path = Path(__file__).resolve().parent / "small_t5.pt"
     torch.save(fixture, path)
+    print("generated", gen.tolist())
     print("loss", float(out.loss), "L", tuple(input_ids.shape), "grads", len(grads), "bytes", path.stat().st_size)
 
 

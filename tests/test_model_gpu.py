@@ -437,12 +437,18 @@ def test_t5_backward_matches_reference_golden():
     assert glob < 0.06, (glob, worst)
 
 
-def test_t5_generate_not_built_and_text_only():
+def test_t5_generate_matches_reference_golden_and_text_only():
+    """generate() with the seq2seq LM (v2.py:254-324): [decoder_start] + greedy tokens, token-exact
+    on the fixture; beam search and sampling run; text-only forward works."""
     fx, cfg = _load_t5()
     m = build(cfg, fx["state_dict"])
     i = cuda(fx["inputs"])
-    with pytest.raises(NotImplementedError):
-        m.generate(i["input_ids"], i["pixel_values"], i["video_input_mask"], i["attention_mask"])
+    gen = m.generate(i["input_ids"], i["pixel_values"], i["video_input_mask"], i["attention_mask"],
+                     max_new_tokens=6, do_sample=False)
+    assert gen.cpu().tolist() == fx["generated"].tolist(), (gen.cpu().tolist(), fx["generated"].tolist())
+    beams = m.generate(i["input_ids"], i["pixel_values"], i["video_input_mask"], i["attention_mask"],
+                       max_new_tokens=5, num_beams=3)
+    assert beams.shape[0] == 2 and beams.shape[1] <= 6 and int(beams[0, 0]) == cfg.text_config.decoder_start_token_id
     with torch.no_grad():
         out = m(i["input_ids"], attention_mask=i["attention_mask"], labels=i["labels"], return_dict=True)
     assert torch.isfinite(out.loss)

@@ -141,3 +141,11 @@ def test_oracle_t5_gradients_match_reference_golden():
         assert g is not None, k
         # this fixture's gradients are O(100): compare in relative L2 (fp32 summation order)
         assert float((g - ref).norm()) < 2e-3 * float(ref.norm()) + 1e-4, k  # (key biases have zero gradient)
+
+
+def test_oracle_t5_greedy_generate_matches_reference_golden():
+    fx, cfg = _load_t5()
+    i = fx["inputs"]
+    got = R.greedy_generate_t5(fx["state_dict"], cfg, i["input_ids"], i["attention_mask"], i["pixel_values"],
+                               i["video_input_mask"], max_new_tokens=6, eos_token_id=cfg.text_config.eos_token_id)
+    assert got.tolist() == fx["generated"].tolist()
