@@ -89,15 +89,6 @@ VB_DEVICE void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
-// 1-D bulk copy global -> shared (bytes % 16 == 0, both sides 16-byte aligned); completion is
-// signalled on `bar` as transaction bytes.
-VB_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 VB_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 // wait until at most N committed bulk groups of this thread still READ their smem source
 template <int N>
@@ -310,11 +301,6 @@ VB_DEVICE float warp_max(float v) {
 // (weights); pdl_wait() returns once the predecessor grid has completed and flushed.
 VB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 VB_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// Asks the L2 to fetch [p, p+bytes) from HBM (bytes % 16 == 0, p 16-byte aligned).
-VB_DEVICE void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 }  // namespace vb
 
 #include <cstdlib>

@@ -326,8 +326,15 @@ def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
     n_valid = am.sum(dim=1).to(torch.int32).contiguous()
     state = dict(kv=kv, ctx_len=torch.full((b,), l, dtype=torch.int32, device=input_ids.device),
                  first_valid=first_valid, n_valid=n_valid, status=out["status"])
+    # flash-decoding splits: enough (head, sequence, split) units to cover the SMs, no more —
+    # every extra split adds to the merge (measured at ctx ~ 1000: batch 1 best at 8, batch 8 at 4)
     total = l + max_new_tokens
-    splits = 16 if total > 512 else (8 if total > 256 else 2)
+    hb = heads * b
+    splits = 8 if hb <= 64 else (4 if hb <= 256 else 2)
+    if total <= 256:
+        splits = min(splits, 2)
+    if os.environ.get("VB_ATTN_SPLITS"):  # measurement knob
+        splits = int(os.environ["VB_ATTN_SPLITS"])
     state["attn_splits"] = splits
     state["attn_ws"] = torch.empty(b * heads * splits * (hd + 2), dtype=torch.float32, device=input_ids.device)
     state["attn_cnt"] = torch.zeros(b * heads, dtype=torch.int32, device=input_ids.device)
