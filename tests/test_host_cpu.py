@@ -227,3 +227,72 @@ def test_process_unfolds_time_axis():
     assert proc.call_args.kwargs["images"].shape == (10, 3, 32, 48)
     proc = Mock(return_value=BatchEncoding({"pixel_values": torch.zeros(5, 3, 224, 224)}))
     assert process(proc, video=torch.zeros(3, 5, 32, 48))["pixel_values"].shape == (1, 3, 5, 224, 224)
+
+
+# ------------------------------------------------------------------ flan-T5 host logic
+def _t5_fixture():
+    fx = torch.load(GOLDEN / "small_t5.pt", weights_only=False)
+    cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    return fx, cfg
+
+
+def test_t5_state_dict_keys_match_the_reference_checkpoint_layout(tmp_path):
+    """Blip2Config with a T5 text_config builds the seq2seq model with HF T5's key names
+    (shared / encoder.block.N.layer.* / decoder.block.N.layer.* / lm_head), embeddings aliased."""
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    fx, cfg = _t5_fixture()
+    m = VideoBlipForConditionalGeneration(cfg)
+    assert set(m.state_dict()) == set(fx["state_dict"])
+    for k, v in m.state_dict().items():
+        assert v.shape == fx["state_dict"][k].shape, k
+    m.load_state_dict(fx["state_dict"], strict=True)
+    lm = m.language_model
+    assert lm.encoder.embed_tokens.weight.data_ptr() == lm.shared.weight.data_ptr()
+    assert lm.decoder.embed_tokens.weight.data_ptr() == lm.shared.weight.data_ptr()
+    assert m.get_input_embeddings() is lm.shared
+    assert not m.config.use_decoder_only_language_model
+    m.save_pretrained(tmp_path)
+    m2 = VideoBlipForConditionalGeneration.from_pretrained(tmp_path)
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, fx["state_dict"][k]), k
+    with pytest.raises(AssertionError):  # classify is decoder-only in the reference (v2.py:351)
+        m.classify(torch.zeros(1, 4, dtype=torch.long), torch.zeros(2, 3, dtype=torch.long))
+
+
+@pytest.mark.parametrize("sq,skv,bidir", [(104, 104, True), (9, 9, False), (1, 1, False), (300, 300, True), (40, 40, False)])
+def test_t5_relative_bias_table_matches_the_oracle(sq, skv, bidir):
+    """engine/t5.py::rel_bias_table (heads, sq+skv-1) vs T5Attention.compute_bias restated by the
+    oracle: entry (j - i) + (sq - 1) is the bias of key j seen from query i — bit-exact."""
+    from eilev_b200.engine import t5 as E
+    from oracle import videoblip_ref as R
+    _, cfg = _t5_fixture()
+    tc = cfg.text_config
+    w = torch.randn(tc.relative_attention_num_buckets, tc.num_heads)
+    tab = E.rel_bias_table(w, sq, skv, bidir, tc)
+    ref = R.t5_position_bias(w, sq, skv, bidir, tc)[0]  # (heads, sq, skv)
+    i = torch.arange(sq)[:, None]
+    j = torch.arange(skv)[None, :]
+    assert tab.shape == (tc.num_heads, sq + skv - 1)
+    assert torch.equal(tab[:, (j - i) + (sq - 1)], ref)
+
+
+def test_t5_shift_right_matches_the_oracle():
+    from eilev_b200.engine import t5 as E
+    from oracle import videoblip_ref as R
+    _, cfg = _t5_fixture()
+    labels = torch.tensor([[5, 9, 7, -100, -100], [3, 4, 8, 2, 1]])
+    assert torch.equal(E.shift_right(labels, cfg.text_config), R.t5_shift_right(labels, cfg.text_config))
+
+
+def test_decode_op_record_layout_matches_the_header():
+    """numpy mirror of vb_decode_op (ops.op_dtype) vs the struct in include/videoblip_b200.h."""
+    import re
+    from eilev_b200 import ops
+    header = (Path(__file__).resolve().parent.parent / "include" / "videoblip_b200.h").read_text()
+    body = re.search(r"typedef struct vb_decode_op \{(.*?)\} vb_decode_op;", header, re.S).group(1)
+    fields = re.findall(r"(\w+)\s*(?:\[(\d+)\])?;", body)
+    dt = ops.op_dtype()
+    assert [f[0] for f in fields] == list(dt.names) == ["type", "i32", "ptr", "i64", "f32"]
+    assert dt.itemsize == 192 and dt.fields["ptr"][1] == 32 and dt.fields["i64"][1] == 112 and dt.fields["f32"][1] == 176
+    assert int(re.search(r"#define VB_DECODE_STEP_WS_BYTES \((\d+) \+ (\d+) \* (\d+)\)", header).group(1)) == 4096
+    assert ops.DECODE_STEP_WS_BYTES == 4096 + 1008 * 512
