@@ -162,8 +162,46 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return ops.gemm(T(dy), T(x), out_dtype=torch.float32)
 
 
-def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) -> dict:
-    """Returns {parameter name: f32 gradient} for every entry of qformer_param_list."""
+class _GradOut(dict):
+    """name -> gradient.  Parameters listed in `sink` (their pre-allocated f32 ``.grad`` views of
+    the trainer's flat buffer) are accumulated IN PLACE by the producing kernel — wgrad GEMM with
+    beta = 1, column sums / LayerNorm parameter gradients in accumulate mode — and are not
+    returned, so autograd issues no ``grad += g`` kernel for them (257 small launches per
+    micro-step otherwise)."""
+
+    def __init__(self, sink: dict | None, device) -> None:
+        super().__init__()
+        self.sink = sink or {}
+        self.device = device
+
+    def weight(self, name: str, dy: torch.Tensor, x: torch.Tensor) -> None:
+        dst = self.sink.get(name)
+        if dst is not None:
+            ops.gemm(T(dy), T(x), out=dst, beta=1.0)
+        else:
+            self[name] = _wgrad(dy, x)
+
+    def bias(self, name: str, dy: torch.Tensor) -> None:
+        dst = self.sink.get(name)
+        if dst is not None:
+            ops.colsum(dy, out=dst)
+        else:
+            self[name] = ops.colsum(dy)
+
+    def ln(self, wname: str, bname: str, cols: int):
+        """(dgamma, dbeta) buffers for vb_layernorm_bwd, which accumulates into them."""
+        dg, db = self.sink.get(wname), self.sink.get(bname)
+        if dg is not None and db is not None:
+            return dg, db
+        dg = torch.zeros(cols, dtype=torch.float32, device=self.device)
+        db = torch.zeros(cols, dtype=torch.float32, device=self.device)
+        self[wname], self[bname] = dg, db
+        return dg, db
+
+
+def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor, sink: dict | None = None) -> dict:
+    """Returns {parameter name: f32 gradient} for the entries of qformer_param_list that were
+    not accumulated straight into `sink` (see _GradOut)."""
     cfg = model.qformer.config
     w = pack_qformer(model, cache)
     n, nq, skv = ctx["n"], ctx["nq"], ctx["skv"]
@@ -173,10 +211,7 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
     act = _act(cfg)
     rows = n * nq
     dev = d_feats.device
-    g: dict[str, torch.Tensor] = {}
-
-    def zeros(k):
-        return torch.zeros(k, dtype=torch.float32, device=dev)
+    g = _GradOut(sink, dev)
 
     seed, p_h, p_a = ctx["seed"], ctx["p_h"], ctx["p_a"]
 
@@ -186,8 +221,8 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
         return t if d is None else ops.dropout(t, d[0], d[1], d[2])
 
     d_feats = d_feats.contiguous()
-    g["language_projection.weight"] = _wgrad(d_feats, ctx["qout"])
-    g["language_projection.bias"] = ops.colsum(d_feats)
+    g.weight("language_projection.weight", d_feats, ctx["qout"])
+    g.bias("language_projection.bias", d_feats)
     dx = ops.gemm(d_feats, w["proj_wt"])
 
     d_ckv = torch.zeros_like(ctx["ckv"]) if ctx["ckv"] is not None else None
@@ -196,31 +231,28 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
         lw, s = w["layers"][i], ctx["saved"][i]
         p = f"qformer.encoder.layer.{i}."
         # ---- output_query: x = LN3(inter W2^T + b2 + x2)
-        dg, db = zeros(dq), zeros(dq)
+        dg, db = g.ln(p + "output_query.LayerNorm.weight", p + "output_query.LayerNorm.bias", dq)
         ds = ops.layernorm_bwd(dx, s["xin3"], lw["ln3_g"], s["m3"], s["r3"], dgamma=dg, dbeta=db)
-        g[p + "output_query.LayerNorm.weight"], g[p + "output_query.LayerNorm.bias"] = dg, db
         dsm = masked(ds, i, 4)
-        g[p + "output_query.dense.weight"] = _wgrad(dsm, s["inter"])
-        g[p + "output_query.dense.bias"] = ops.colsum(dsm)
+        g.weight(p + "output_query.dense.weight", dsm, s["inter"])
+        g.bias(p + "output_query.dense.bias", dsm)
         d_inter = ops.gemm(dsm, lw["o2_wt"])
         if act == ops.EPI_GELU:
             pre = ops.gemm(s["x2"], lw["i_w"], lw["i_b"])  # recompute the pre-activation
             d_pre = ops.act_bwd(d_inter, pre, act)
         else:
             d_pre = ops.act_bwd(d_inter, s["inter"], act)
-        g[p + "intermediate_query.dense.weight"] = _wgrad(d_pre, s["x2"])
-        g[p + "intermediate_query.dense.bias"] = ops.colsum(d_pre)
+        g.weight(p + "intermediate_query.dense.weight", d_pre, s["x2"])
+        g.bias(p + "intermediate_query.dense.bias", d_pre)
         dx2 = ops.gemm(d_pre, lw["i_wt"], residual=ds)
         # ---- cross attention: x2 = LN2(cctx Wo^T + bo + x1)
         if lw["cross"] is not None:
             c = lw["cross"]
-            dg, db = zeros(dq), zeros(dq)
+            dg, db = g.ln(p + "crossattention.output.LayerNorm.weight", p + "crossattention.output.LayerNorm.bias", dq)
             ds2 = ops.layernorm_bwd(dx2, s["xin2"], lw["ln2_g"], s["m2"], s["r2"], dgamma=dg, dbeta=db)
-            g[p + "crossattention.output.LayerNorm.weight"] = dg
-            g[p + "crossattention.output.LayerNorm.bias"] = db
             ds2m = masked(ds2, i, 3)
-            g[p + "crossattention.output.dense.weight"] = _wgrad(ds2m, s["cctx"].view(rows, dq))
-            g[p + "crossattention.output.dense.bias"] = ops.colsum(ds2m)
+            g.weight(p + "crossattention.output.dense.weight", ds2m, s["cctx"].view(rows, dq))
+            g.bias(p + "crossattention.output.dense.bias", ds2m)
             d_cctx = ops.gemm(ds2m, lw["co_wt"]).view(n, nq, dq)
             kc = ctx["ckv"][:, :, (2 * c) * dq:(2 * c + 1) * dq]
             vc = ctx["ckv"][:, :, (2 * c + 1) * dq:(2 * c + 2) * dq]
@@ -229,18 +261,17 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
             dqc, _, _ = ops.attention_bwd(s["qc"], kc, vc, s["cctx"], s["clse"], d_cctx, heads, scale,
                                           dk=dkc, dv=dvc, dropout=_drop(p_a, seed, i, 2))
             dqc2 = dqc.view(rows, dq)
-            g[p + "crossattention.attention.query.weight"] = _wgrad(dqc2, s["x1"])
-            g[p + "crossattention.attention.query.bias"] = ops.colsum(dqc2)
+            g.weight(p + "crossattention.attention.query.weight", dqc2, s["x1"])
+            g.bias(p + "crossattention.attention.query.bias", dqc2)
             dx1 = ops.gemm(dqc2, lw["cq_wt"], residual=ds2)
         else:
             dx1 = dx2
         # ---- self attention: x1 = LN1(ctx Wo^T + bo + x)
-        dg, db = zeros(dq), zeros(dq)
+        dg, db = g.ln(p + "attention.output.LayerNorm.weight", p + "attention.output.LayerNorm.bias", dq)
         ds1 = ops.layernorm_bwd(dx1, s["xin1"], lw["ln1_g"], s["m1"], s["r1"], dgamma=dg, dbeta=db)
-        g[p + "attention.output.LayerNorm.weight"], g[p + "attention.output.LayerNorm.bias"] = dg, db
         ds1m = masked(ds1, i, 1)
-        g[p + "attention.output.dense.weight"] = _wgrad(ds1m, s["ctx"].view(rows, dq))
-        g[p + "attention.output.dense.bias"] = ops.colsum(ds1m)
+        g.weight(p + "attention.output.dense.weight", ds1m, s["ctx"].view(rows, dq))
+        g.bias(p + "attention.output.dense.bias", ds1m)
         d_ctx = ops.gemm(ds1m, lw["o_wt"]).view(n, nq, dq)
         qkv = s["qkv"]
         dqkv = torch.empty_like(qkv)
@@ -271,10 +302,9 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor) 
             g[p + "value.bias"] = dbias[(2 * c + 1) * dq:(2 * c + 2) * dq]
 
     # ---- initial LayerNorm over the expanded query tokens
-    dg, db = zeros(dq), zeros(dq)
+    dg, db = g.ln("qformer.layernorm.weight", "qformer.layernorm.bias", dq)
     if p_h > 0.0:
         dx = ops.dropout(dx, p_h, seed, _SALT_QF + 7)
     d0 = ops.layernorm_bwd(dx, ctx["x0"], w["ln0_g"], ctx["m0"], ctx["r0"], dgamma=dg, dbeta=db)
-    g["qformer.layernorm.weight"], g["qformer.layernorm.bias"] = dg, db
     g["query_tokens"] = ops.colsum(d0.view(n, nq * dq)).view(1, nq, dq)
     return g

@@ -517,3 +517,58 @@ def test_t5_real_dims_shallow_against_oracle():
     assert r["logits"] < 0.025, r
     assert abs(r["loss"] - r["loss_ref"]) < 0.05, r
     assert r["grad_rel_l2"] < 0.10, r
+
+
+def test_trainer_graphs_and_inplace_grad_accumulation_match_plain_autograd():
+    """DataParallelTrainer (flat f32 grad views filled in place by the wgrad kernels, one CUDA
+    graph with the Q-Former re-pack + one without) against plain autograd on a second copy of
+    the model: accumulated gradients after 2 micro-steps and parameters after the optimizer
+    step, then one more micro-step through the re-pack graph."""
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    from eilev_b200.train import DataParallelTrainer, freeze_for_recipe
+    fx, cfg = load("small_opt")
+
+    def fresh():
+        m = VideoBlipForConditionalGeneration(cfg)
+        m.load_state_dict(fx["state_dict"])
+        m = m.to("cuda").train()
+        freeze_for_recipe(m)
+        return m
+
+    batch = cuda(fx["inputs"])
+    ref = fresh()
+    tr_model = fresh()
+    tr = DataParallelTrainer(tr_model, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0, grad_accum=2)
+    tr.capture_graph(batch)
+    names = [n for n, p in ref.named_parameters() if p.requires_grad]
+
+    def ref_micro():
+        out = ref(**batch, return_dict=True)
+        (out.loss / 2).backward()
+        return float(out.loss.detach())
+
+    l_ref = [ref_micro(), ref_micro()]
+    l_tr = [float(tr.micro_step(batch)) for _ in range(1)]
+    # gradients after the first micro-step (re-pack graph) + second (warm graph) before the update
+    g_mid = {n: p.grad.clone() for n, p in tr_model.named_parameters() if p.requires_grad}
+    ref1 = fresh()
+    o1 = ref1(**batch, return_dict=True)
+    (o1.loss / 2).backward()
+    num = sum(float((g_mid[n] - p.grad).pow(2).sum()) for n, p in ref1.named_parameters() if p.requires_grad)
+    den = sum(float(p.grad.pow(2).sum()) for n, p in ref1.named_parameters() if p.requires_grad)
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5  # same kernels, bf16 wgrad operands
+    l_tr.append(float(tr.micro_step(batch)))  # second micro-step -> optimizer step
+    assert abs(l_tr[0] - l_ref[0]) < 1e-3 and abs(l_tr[1] - l_ref[1]) < 1e-3, (l_tr, l_ref)
+    opt = torch.optim.AdamW([p for p in ref.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.05,
+                            betas=(0.9, 0.999), eps=1e-8)
+    torch.nn.utils.clip_grad_norm_([p for p in ref.parameters() if p.requires_grad], 1.0)
+    opt.step()
+    pr = dict(ref.named_parameters())
+    pt = dict(tr_model.named_parameters())
+    worst = max(float((pt[n].detach() - pr[n].detach()).abs().max()) for n in names)
+    assert worst < 2e-3, worst  # lr 1e-3: one Adam step moves every weight by ~1e-3
+    # next micro-step runs the re-pack graph on the UPDATED parameters
+    ref.zero_grad(set_to_none=True)
+    l3_ref = ref_micro()
+    l3_tr = float(tr.micro_step(batch))
+    assert abs(l3_tr - l3_ref) < 5e-3, (l3_tr, l3_ref)
