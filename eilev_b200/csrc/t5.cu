@@ -61,26 +61,60 @@ cudaError_t rmsnorm_fwd_launch(const void* x, const float* gamma, void* y, float
   return cudaGetLastError();
 }
 
-// dx_j = r * (g_j - x_j * r^2 * mean_i(g_i x_i)),  g = gamma * dy   (+ dx_add)
+// dx_j = r * (g_j - x_j * r^2 * mean_i(g_i x_i)),  g = gamma * dy   (+ dx_add).  One warp per
+// row, 16-byte accesses when the row length is a multiple of 8.
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const float* __restrict__ gamma, const float* __restrict__ rstd,
                    const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx, long long rows,
-                   int cols) {
+                   int cols, int vec) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const __nv_bfloat16* dyr = dy + row * cols;
   const __nv_bfloat16* xr = x + row * cols;
   float dot = 0.0f;
-  for (int c = lane; c < cols; c += 32)
-    dot += gamma[c] * __bfloat162float(dyr[c]) * __bfloat162float(xr[c]);
+  if (vec) {
+    for (int c = lane * 8; c < cols; c += 256) {
+      const uint4 d = *reinterpret_cast<const uint4*>(dyr + c);
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+      const float2 x0 = unpack_bf16x2(v.x), x1 = unpack_bf16x2(v.y), x2 = unpack_bf16x2(v.z), x3 = unpack_bf16x2(v.w);
+      dot += g0.x * d0.x * x0.x + g0.y * d0.y * x0.y + g0.z * d1.x * x1.x + g0.w * d1.y * x1.y +
+             g1.x * d2.x * x2.x + g1.y * d2.y * x2.y + g1.z * d3.x * x3.x + g1.w * d3.y * x3.y;
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32)
+      dot += gamma[c] * __bfloat162float(dyr[c]) * __bfloat162float(xr[c]);
+  }
   const float r = rstd[row];
   const float k = warp_sum(dot) / static_cast<float>(cols) * r * r;
-  for (int c = lane; c < cols; c += 32) {
-    float v = r * (gamma[c] * __bfloat162float(dyr[c]) - __bfloat162float(xr[c]) * k);
-    if (dx_add != nullptr) v += __bfloat162float(dx_add[row * cols + c]);
-    dx[row * cols + c] = __float2bfloat16(v);
+  if (vec) {
+    for (int c = lane * 8; c < cols; c += 256) {
+      const uint4 d = *reinterpret_cast<const uint4*>(dyr + c);
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+      const float2 x0 = unpack_bf16x2(v.x), x1 = unpack_bf16x2(v.y), x2 = unpack_bf16x2(v.z), x3 = unpack_bf16x2(v.w);
+      float o[8] = {r * (g0.x * d0.x - x0.x * k), r * (g0.y * d0.y - x0.y * k), r * (g0.z * d1.x - x1.x * k),
+                    r * (g0.w * d1.y - x1.y * k), r * (g1.x * d2.x - x2.x * k), r * (g1.y * d2.y - x2.y * k),
+                    r * (g1.z * d3.x - x3.x * k), r * (g1.w * d3.y - x3.y * k)};
+      if (dx_add != nullptr) {
+        const uint4 a = *reinterpret_cast<const uint4*>(dx_add + row * cols + c);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+        o[0] += a0.x; o[1] += a0.y; o[2] += a1.x; o[3] += a1.y; o[4] += a2.x; o[5] += a2.y; o[6] += a3.x; o[7] += a3.y;
+      }
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + row * cols + c) = w;
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      float v = r * (gamma[c] * __bfloat162float(dyr[c]) - __bfloat162float(xr[c]) * k);
+      if (dx_add != nullptr) v += __bfloat162float(dx_add[row * cols + c]);
+      dx[row * cols + c] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -89,10 +123,12 @@ cudaError_t rmsnorm_bwd_launch(const void* dy, const void* x, const float* gamma
   if (rows <= 0 || cols <= 0) return cudaSuccess;
   if (dy == nullptr || x == nullptr || gamma == nullptr || rstd == nullptr || dx == nullptr)
     return cudaErrorInvalidValue;
+  auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const int vec = (cols % 8 == 0 && al(dy) && al(x) && al(gamma) && al(dx_add) && al(dx)) ? 1 : 0;
   rmsnorm_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, rstd,
       reinterpret_cast<const __nv_bfloat16*>(dx_add), reinterpret_cast<__nv_bfloat16*>(dx), rows,
-      static_cast<int>(cols));
+      static_cast<int>(cols), vec);
   return cudaGetLastError();
 }
 
@@ -108,34 +144,69 @@ VB_DEVICE float gelu_tanh_grad(float x) {
   return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * du;
 }
 
+// vec: dff % 8 == 0 and 16-byte aligned buffers -> one thread handles 8 consecutive columns
 __global__ void __launch_bounds__(256)
 gated_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h01, __nv_bfloat16* __restrict__ out, long long rows,
-                      long long dff) {
-  const long long total = rows * dff;
+                      long long dff, int vec) {
+  const long long step = vec ? 8 : 1;
+  const long long total = rows * dff / step;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / dff, c = i - r * dff;
-    const float h0 = __bfloat162float(h01[r * 2 * dff + c]);
-    const float h1 = __bfloat162float(h01[r * 2 * dff + dff + c]);
-    out[i] = __float2bfloat16(gelu_tanh(h0) * h1);
+    const long long e = i * step;
+    const long long r = e / dff, c = e - r * dff;
+    if (vec) {
+      const uint4 a = *reinterpret_cast<const uint4*>(h01 + r * 2 * dff + c);
+      const uint4 b = *reinterpret_cast<const uint4*>(h01 + r * 2 * dff + dff + c);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+      uint4 o;
+      o.x = pack_bf16x2(gelu_tanh(a0.x) * b0.x, gelu_tanh(a0.y) * b0.y);
+      o.y = pack_bf16x2(gelu_tanh(a1.x) * b1.x, gelu_tanh(a1.y) * b1.y);
+      o.z = pack_bf16x2(gelu_tanh(a2.x) * b2.x, gelu_tanh(a2.y) * b2.y);
+      o.w = pack_bf16x2(gelu_tanh(a3.x) * b3.x, gelu_tanh(a3.y) * b3.y);
+      *reinterpret_cast<uint4*>(out + e) = o;
+    } else {
+      const float h0 = __bfloat162float(h01[r * 2 * dff + c]);
+      const float h1 = __bfloat162float(h01[r * 2 * dff + dff + c]);
+      out[e] = __float2bfloat16(gelu_tanh(h0) * h1);
+    }
   }
 }
 
 __global__ void __launch_bounds__(256)
 gated_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ h01,
-                      __nv_bfloat16* __restrict__ d_h01, long long rows, long long dff) {
-  const long long total = rows * dff;
+                      __nv_bfloat16* __restrict__ d_h01, long long rows, long long dff, int vec) {
+  const long long step = vec ? 8 : 1;
+  const long long total = rows * dff / step;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / dff, c = i - r * dff;
-    const float h0 = __bfloat162float(h01[r * 2 * dff + c]);
-    const float h1 = __bfloat162float(h01[r * 2 * dff + dff + c]);
-    const float g = __bfloat162float(d_out[i]);
-    d_h01[r * 2 * dff + c] = __float2bfloat16(g * h1 * gelu_tanh_grad(h0));
-    d_h01[r * 2 * dff + dff + c] = __float2bfloat16(g * gelu_tanh(h0));
+    const long long e = i * step;
+    const long long r = e / dff, c = e - r * dff;
+    if (vec) {
+      const uint4 a = *reinterpret_cast<const uint4*>(h01 + r * 2 * dff + c);
+      const uint4 b = *reinterpret_cast<const uint4*>(h01 + r * 2 * dff + dff + c);
+      const uint4 gq = *reinterpret_cast<const uint4*>(d_out + e);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, gw[4] = {gq.x, gq.y, gq.z, gq.w};
+      uint32_t o0[4], o1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 h0 = unpack_bf16x2(aw[j]), h1 = unpack_bf16x2(bw[j]), g = unpack_bf16x2(gw[j]);
+        o0[j] = pack_bf16x2(g.x * h1.x * gelu_tanh_grad(h0.x), g.y * h1.y * gelu_tanh_grad(h0.y));
+        o1[j] = pack_bf16x2(g.x * gelu_tanh(h0.x), g.y * gelu_tanh(h0.y));
+      }
+      *reinterpret_cast<uint4*>(d_h01 + r * 2 * dff + c) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+      *reinterpret_cast<uint4*>(d_h01 + r * 2 * dff + dff + c) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    } else {
+      const float h0 = __bfloat162float(h01[r * 2 * dff + c]);
+      const float h1 = __bfloat162float(h01[r * 2 * dff + dff + c]);
+      const float g = __bfloat162float(d_out[e]);
+      d_h01[r * 2 * dff + c] = __float2bfloat16(g * h1 * gelu_tanh_grad(h0));
+      d_h01[r * 2 * dff + dff + c] = __float2bfloat16(g * gelu_tanh(h0));
+    }
   }
 }
 
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 static unsigned ew_grid(long long total) {
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -144,17 +215,19 @@ static unsigned ew_grid(long long total) {
 
 cudaError_t gated_gelu_fwd_launch(const void* h01, void* out, long long rows, long long dff, cudaStream_t s) {
   if (rows * dff <= 0) return cudaSuccess;
-  gated_gelu_fwd_kernel<<<ew_grid(rows * dff), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(h01),
-                                                            reinterpret_cast<__nv_bfloat16*>(out), rows, dff);
+  const int vec = (dff % 8 == 0 && al16(h01) && al16(out)) ? 1 : 0;
+  gated_gelu_fwd_kernel<<<ew_grid(rows * dff / (vec ? 8 : 1)), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h01), reinterpret_cast<__nv_bfloat16*>(out), rows, dff, vec);
   return cudaGetLastError();
 }
 
 cudaError_t gated_gelu_bwd_launch(const void* d_out, const void* h01, void* d_h01, long long rows,
                                   long long dff, cudaStream_t s) {
   if (rows * dff <= 0) return cudaSuccess;
-  gated_gelu_bwd_kernel<<<ew_grid(rows * dff), 256, 0, s>>>(
+  const int vec = (dff % 8 == 0 && al16(d_out) && al16(h01) && al16(d_h01)) ? 1 : 0;
+  gated_gelu_bwd_kernel<<<ew_grid(rows * dff / (vec ? 8 : 1)), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_out), reinterpret_cast<const __nv_bfloat16*>(h01),
-      reinterpret_cast<__nv_bfloat16*>(d_h01), rows, dff);
+      reinterpret_cast<__nv_bfloat16*>(d_h01), rows, dff, vec);
   return cudaGetLastError();
 }
 
