@@ -312,11 +312,15 @@ class _QFormerProjectFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_feats, _d_qout):
         model = ctx.model
-        # gradients whose .grad is a pre-allocated contiguous f32 buffer (the trainer's flat
-        # views) are accumulated in place by the kernels that produce them
-        sink = {name: p.grad for name, p in E_qf.qformer_param_list(model)
-                if p.requires_grad and p.grad is not None and p.grad.dtype == torch.float32
-                and p.grad.is_contiguous() and p.grad.is_cuda}
+        # Opt-in (DataParallelTrainer sets model._grad_sink): gradients whose .grad is a
+        # pre-allocated contiguous f32 buffer (the trainer's flat views) are accumulated in place by
+        # the kernels that produce them.  Off by default: under torch DistributedDataParallel every
+        # gradient has to come back through autograd so the reducer's hooks fire.
+        sink = None
+        if getattr(model, "_grad_sink", False):
+            sink = {name: p.grad for name, p in E_qf.qformer_param_list(model)
+                    if p.requires_grad and p.grad is not None and p.grad.dtype == torch.float32
+                    and p.grad.is_contiguous() and p.grad.is_cuda}
         grads = E_qf.qformer_backward(model, model._pack, ctx.saved, d_feats.to(torch.bfloat16), sink)
         ctx.saved = None
         out = []

@@ -80,6 +80,7 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.lr_schedule = lr_schedule
         self.flat = FlatBuffers(qformer_param_list(model))
+        model._grad_sink = True  # wgrad kernels accumulate straight into the flat f32 grad views
         self.exp_avg = torch.zeros_like(self.flat.params)
         self.exp_avg_sq = torch.zeros_like(self.flat.params)
         self.opt_step = 0
