@@ -348,6 +348,46 @@ def measure_decode(model, device, batch: int = 1):
             "bytes_per_token": 5.293e9 + 327680.0 * (n + 3 + steps / 2) * batch}
 
 
+def measure_decode_t5(model, device, steps: int = 32):
+    """BASELINE configs[3] inference side: greedy generate() with the flan-t5-xl LM after the
+    16-context prompt (encoder + cross-attention K|V once, excluded; the decoder re-runs its
+    prefix every step).  Bytes per token = decoder + head weights (bf16) + the cross K|V read."""
+    from eilev_b200.model.generation import _T5Stepper
+
+    was_training = model.training
+    model.eval()
+    one = synthetic_batch(7, lm="t5")
+    ids, am = one["input_ids"].to(device), one["attention_mask"].to(device)
+    vm, px = one["video_input_mask"].to(device), one["pixel_values"].to(device)
+    cfg = model.config.text_config
+    inner = cfg.num_heads * cfg.d_kv
+    per_layer = 4 * cfg.d_model * inner + 2 * cfg.d_model * inner + 3 * cfg.d_model * cfg.d_ff
+    weight_bytes = 2.0 * (cfg.num_decoder_layers * per_layer + cfg.vocab_size * cfg.d_model)
+    kv_bytes = 2.0 * cfg.num_decoder_layers * 2 * ids.shape[1] * inner
+    with torch.no_grad():
+        feats, _, _ = model._video_features(px, False, train=False)
+        stepper = _T5Stepper(model.language_model)
+        logits = stepper.prefill(ids, am, vm.bool(), feats, steps + 4)
+        stepper.graph(1, device)  # the CUDA-graphed fixed-length step generate() uses
+        tok = logits.argmax(-1)
+        for _ in range(3):
+            tok = stepper.step(tok).argmax(-1)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            tok = stepper.step(tok).argmax(-1)
+        e.record()
+        torch.cuda.synchronize()
+    per_tok = s.elapsed_time(e) * 1e-3 / steps
+    model.train(was_training)
+    return {"metric": "decode tok/s (greedy, flan-t5-xl, 16-ctx prompt, batch 1)", "value": 1.0 / per_tok,
+            "unit": "tok/s", "ms_per_token": per_tok * 1e3, "prompt_len": int(ids.shape[1]), "batch": 1,
+            "steps": steps, "bytes_per_token": weight_bytes + kv_bytes,
+            "note": "decoder re-run over a fixed-length prefix buffer per token (tcgen05 GEMMs at M = max_new + 1 "
+                    "rows), one CUDA graph"}
+
+
 def gpu_arm(args) -> None:
     import torch.distributed as dist
 
@@ -371,6 +411,8 @@ def gpu_arm(args) -> None:
         decode = measure_decode(model, device)
         decode8 = measure_decode(model, device, batch=8)
         torch.cuda.empty_cache()
+    if rank == 0 and not args.no_decode and not args.profile and args.lm == "t5":
+        decode = measure_decode_t5(model, device)
     trainer = DataParallelTrainer(model, lr=1e-5, weight_decay=0.05, max_grad_norm=1.0,
                                   grad_accum=GRAD_ACCUM)
     if world > 1:  # NCCL communicator / NVLink connection set-up happens on the first collective

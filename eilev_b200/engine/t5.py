@@ -240,10 +240,14 @@ def t5_encode(lm, cache: PackCache, input_ids, attention_mask, video_mask, video
     return dict(ckv=ckv, key_mask=key_mask, status=status, b=b, l=l, enc_out=enc_out.view(b, l, dm))
 
 
-def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.Tensor) -> torch.Tensor:
+def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.Tensor,
+                     pos: torch.Tensor | None = None) -> torch.Tensor:
     """Next-token logits f32 (B, V) after the decoder prefix (B, t).  The prefix is re-run every
     step: a decode step is bound by streaming the 2.7 GB of decoder weights, which a t-row
-    GEMM does exactly once, so caching the self-attention K/V would not change the traffic."""
+    GEMM does exactly once, so caching the self-attention K/V would not change the traffic.
+    pos (device int64 (B,)): read the logits at these positions instead of the last one — the
+    causal mask makes positions <= pos independent of whatever follows, so a fixed-length
+    buffer (CUDA-graph friendly) can stand in for the growing prefix."""
     cfg = lm.config
     w = pack_t5(lm, cache, need_backward=False)
     dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
@@ -265,7 +269,10 @@ def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.T
                            ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner], heads, 1.0, key_mask=key_mask)
         x2 = ops.gemm(co.view(rows_d, inner), lw["co_w"], residual=x1)
         xd, _ = _ff_fwd(x2, lw["ff"], eps)
-    last = xd.view(b, t, dm)[:, -1, :].contiguous()
+    if pos is None:
+        last = xd.view(b, t, dm)[:, -1, :].contiguous()
+    else:
+        last = xd.view(b, t, dm)[torch.arange(b, device=xd.device), pos].contiguous()
     final = ops.rmsnorm(last, w["dec_ln"], eps)
     alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
     return ops.gemm(final, w["head"], alpha=alpha, out_dtype=torch.float32)

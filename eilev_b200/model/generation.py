@@ -47,29 +47,53 @@ class _OptStepper:
 
 
 class _T5Stepper:
-    """Encoder-decoder LM (flan-T5): the encoder and the cross-attention K|V run once, every
-    step re-runs the decoder over the generated prefix (see engine/t5.py::t5_decode_logits)."""
+    """Encoder-decoder LM (flan-T5): the encoder and the cross-attention K|V run once; every step
+    re-runs the decoder over the prefix (see engine/t5.py::t5_decode_logits).  With a CUDA graph
+    the prefix lives in a fixed-length buffer and the logits are read at the current position, so
+    one captured step serves every token."""
 
     def __init__(self, lm) -> None:
         self.lm = lm
         self.start_token = int(lm.config.decoder_start_token_id)
+        self.pad = int(lm.config.pad_token_id if lm.config.pad_token_id is not None else 0)
+        self._graph = None
 
     def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
         self.enc = E_t5.t5_encode(self.lm, self.lm._pack, input_ids, attention_mask, video_mask, feats)
         self.status = self.enc["status"]
-        self.prefix = torch.full((input_ids.shape[0], 1), self.start_token, dtype=torch.long,
-                                 device=input_ids.device)
-        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.prefix)
+        b, dev = input_ids.shape[0], input_ids.device
+        self.max_new = max_new
+        self.buf = torch.full((b, max_new + 1), self.pad, dtype=torch.long, device=dev)
+        self.buf[:, 0] = self.start_token
+        self.t = 0  # position of the newest prefix token
+        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf[:, :1])
 
     def graph(self, rows, dev):
-        return None  # the prefix grows every step
+        """Captures the fixed-length decoder step; returns an object with .step(tokens)."""
+        if self.max_new < 4:
+            return None
+        self.pos = torch.zeros(rows, dtype=torch.long, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up: packs, kernel attributes, allocator
+            E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf, self.pos)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._logits = E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf, self.pos)
+        return self
 
     def step(self, tokens):
-        self.prefix = torch.cat([self.prefix, tokens.view(-1, 1)], dim=1)
-        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.prefix)
+        self.t += 1
+        self.buf[:, self.t] = tokens.view(-1)
+        if self._graph is not None:
+            self.pos.fill_(self.t)
+            self._graph.replay()
+            return self._logits
+        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf[:, : self.t + 1])
 
     def reorder(self, src) -> None:
-        self.prefix = self.prefix[src]  # beams of one prompt share its encoder rows
+        self.buf.copy_(self.buf[src])  # beams of one prompt share its encoder rows
 
 
 _UNSUPPORTED = ("penalty_alpha", "num_beam_groups", "diversity_penalty", "constraints",
