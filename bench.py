@@ -384,8 +384,7 @@ def measure_decode_t5(model, device, steps: int = 32):
     return {"metric": "decode tok/s (greedy, flan-t5-xl, 16-ctx prompt, batch 1)", "value": 1.0 / per_tok,
             "unit": "tok/s", "ms_per_token": per_tok * 1e3, "prompt_len": int(ids.shape[1]), "batch": 1,
             "steps": steps, "bytes_per_token": weight_bytes + kv_bytes,
-            "note": "decoder re-run over a fixed-length prefix buffer per token (tcgen05 GEMMs at M = max_new + 1 "
-                    "rows), one CUDA graph"}
+            "note": "KV-cached decoder step on the weight-streaming GEMV kernels, one CUDA graph"}
 
 
 def gpu_arm(args) -> None:

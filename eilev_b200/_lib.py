@@ -91,7 +91,8 @@ SIGNATURES: dict[str, list] = {
     "vb_decode_embed": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
     "vb_debug_decode_trace": [vp],
     "vb_decode_step": [vp, vp, i32, i32, vp, vp],
-    "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, vp],
+    "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32,
+                                  vp, i64, i64, vp],
     "vb_paged_kv_write": [vp, vp, i64, vp, vp, vp, i64, i64, i64, i64, i64, vp],
 }
 
@@ -129,7 +130,7 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "vb_last_error" else C.c_int
-    if handle.vb_abi_version() != 2:
+    if handle.vb_abi_version() != 3:
         raise VbError("ABI version mismatch between eilev_b200/_lib.py and the built library")
     _lib = handle
     return handle

@@ -265,11 +265,13 @@ int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
                               const int32_t* first_valid, void* out, float* workspace,
                               int32_t* counters, int64_t splits, int64_t batch, int64_t heads,
                               int64_t d, int64_t page_size, int64_t max_pages, float scale,
+                              const float* rel_bias, int64_t rel_stride, int64_t rel_center,
                               void* stream) {
   VB_CHECK("vb_paged_decode_attention",
            vb::paged_decode_attention_launch(qkv, k_cache, v_cache, page_table, ctx_len,
                                              first_valid, out, workspace, counters, splits, batch,
-                                             heads, d, page_size, max_pages, scale, st(stream)));
+                                             heads, d, page_size, max_pages, scale, rel_bias, rel_stride,
+                                             rel_center, st(stream)));
 }
 
 int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,

@@ -746,6 +746,10 @@ struct AttnArgs {
   int* counters;
   int heads, D, page_size, max_pages, splits, chunk_cap;
   float scale;
+  // T5: additive relative-position bias of key l seen from the newest position ctx-1:
+  // rel_bias[h * rel_stride + rel_center + (l - (ctx - 1))]; nullptr = none
+  const float* rel_bias;
+  int rel_stride, rel_center;
 };
 
 __host__ __device__ inline int attn_unit_smem_floats(int D, int chunk_cap) { return D + chunk_cap + 16 * D + 8; }
@@ -873,6 +877,7 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
         }
       }
       s = acc;
+      if (a.rel_bias != nullptr) s += a.rel_bias[h * a.rel_stride + a.rel_center + (l - newest)];
     }
     sc[l - lo] = s;
     mx = fmaxf(mx, s);
@@ -980,7 +985,8 @@ cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* 
                                           const int* first_valid, void* out, float* workspace,
                                           int* counters, long long splits, long long batch,
                                           long long heads, long long d, long long page_size,
-                                          long long max_pages, float scale, cudaStream_t s) {
+                                          long long max_pages, float scale, const float* rel_bias,
+                                          long long rel_stride, long long rel_center, cudaStream_t s) {
   if (batch <= 0 || heads <= 0) return cudaSuccess;
   if (splits <= 0 || splits > 64 || workspace == nullptr || counters == nullptr) return cudaErrorInvalidValue;
   const long long max_ctx = page_size * max_pages;
@@ -1004,6 +1010,7 @@ cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* 
   a.heads = static_cast<int>(heads); a.D = static_cast<int>(d); a.page_size = static_cast<int>(page_size);
   a.max_pages = static_cast<int>(max_pages); a.splits = static_cast<int>(splits);
   a.chunk_cap = static_cast<int>(chunk_cap); a.scale = scale;
+  a.rel_bias = rel_bias; a.rel_stride = static_cast<int>(rel_stride); a.rel_center = static_cast<int>(rel_center);
   dim3 grid(static_cast<unsigned>(heads), static_cast<unsigned>(batch), static_cast<unsigned>(splits));
   return launch_pdl(paged_decode_attn_kernel, grid, dim3(128), smem, s, a);
 }
@@ -1114,6 +1121,7 @@ decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsig
         a.counters = reinterpret_cast<int*>(const_cast<void*>(op.ptr[8]));
         a.heads = op.i32[0]; a.D = op.i32[1]; a.page_size = op.i32[2]; a.max_pages = op.i32[3];
         a.splits = op.i32[4]; a.chunk_cap = op.i32[5]; a.scale = op.f32[0];
+        a.rel_bias = nullptr; a.rel_stride = 0; a.rel_center = 0;
         const int sub = threadIdx.x >> 7, tid = threadIdx.x & 127;
         float* sm = reinterpret_cast<float*>(gsm) + static_cast<size_t>(sub) * attn_unit_smem_floats(a.D, a.chunk_cap);
         const int units = a.heads * m * a.splits;

@@ -240,14 +240,9 @@ def t5_encode(lm, cache: PackCache, input_ids, attention_mask, video_mask, video
     return dict(ckv=ckv, key_mask=key_mask, status=status, b=b, l=l, enc_out=enc_out.view(b, l, dm))
 
 
-def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.Tensor,
-                     pos: torch.Tensor | None = None) -> torch.Tensor:
-    """Next-token logits f32 (B, V) after the decoder prefix (B, t).  The prefix is re-run every
-    step: a decode step is bound by streaming the 2.7 GB of decoder weights, which a t-row
-    GEMM does exactly once, so caching the self-attention K/V would not change the traffic.
-    pos (device int64 (B,)): read the logits at these positions instead of the last one — the
-    causal mask makes positions <= pos independent of whatever follows, so a fixed-length
-    buffer (CUDA-graph friendly) can stand in for the growing prefix."""
+def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.Tensor) -> torch.Tensor:
+    """Next-token logits f32 (B, V) after the decoder prefix (B, t), re-running the whole prefix
+    (the path for more than 16 rows; up to 16 rows use the KV-cached t5_decode_step)."""
     cfg = lm.config
     w = pack_t5(lm, cache, need_backward=False)
     dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
@@ -269,13 +264,61 @@ def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.T
                            ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner], heads, 1.0, key_mask=key_mask)
         x2 = ops.gemm(co.view(rows_d, inner), lw["co_w"], residual=x1)
         xd, _ = _ff_fwd(x2, lw["ff"], eps)
-    if pos is None:
-        last = xd.view(b, t, dm)[:, -1, :].contiguous()
-    else:
-        last = xd.view(b, t, dm)[torch.arange(b, device=xd.device), pos].contiguous()
+    last = xd.view(b, t, dm)[:, -1, :].contiguous()
     final = ops.rmsnorm(last, w["dec_ln"], eps)
     alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
     return ops.gemm(final, w["head"], alpha=alpha, out_dtype=torch.float32)
+
+
+def t5_decode_init(lm, cache: PackCache, enc: dict, max_new: int) -> dict:
+    """State of the KV-cached decoder step: a paged self-attention cache per decoder layer
+    (the cross-attention K|V already live in `enc`), the per-sequence length counter and the
+    unidirectional relative-position table for up to max_new + 1 positions."""
+    from .opt import PagedKV
+
+    cfg = lm.config
+    w = pack_t5(lm, cache, need_backward=False)
+    heads, inner = cfg.num_heads, cfg.num_heads * cfg.d_kv
+    b = enc["b"]
+    dev = enc["ckv"].device
+    tmax = max_new + 1
+    kv = PagedKV(len(w["dec"]), b, tmax, inner, dev)
+    return dict(kv=kv, tmax=tmax, bias=rel_bias_table(w["dec_rel"], tmax, tmax, False, cfg),
+                ctx_len=torch.zeros(b, dtype=torch.int32, device=dev),
+                first_valid=torch.zeros(b, dtype=torch.int32, device=dev),
+                ws=torch.empty(b * heads * (cfg.d_kv + 2), dtype=torch.float32, device=dev),
+                cnt=torch.zeros(b * heads, dtype=torch.int32, device=dev))
+
+
+def t5_decode_step(lm, cache: PackCache, enc: dict, st: dict, tokens: torch.Tensor) -> torch.Tensor:
+    """One decoder token per sequence on the weight-streaming kernels: tokens (B,) int64 ->
+    next-token logits f32 (B, V).  Self-attention reads / appends the paged cache with the
+    relative bias of the newest position; cross-attention is a one-query pass over the encoder
+    K|V.  Stream-ordered and allocation-stable (CUDA-graph capturable)."""
+    cfg = lm.config
+    w = pack_t5(lm, cache, need_backward=False)
+    dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
+    inner = heads * dkv
+    eps = float(cfg.layer_norm_epsilon)
+    kv, ckv, key_mask = st["kv"], enc["ckv"], enc["key_mask"]
+    b = tokens.shape[0]
+    st["ctx_len"].add_(1)
+    x = ops.embedding(tokens, w["shared"])
+    for li, lw in enumerate(w["dec"]):
+        qkv = ops.gemv(ops.rmsnorm(x, lw["ln1"], eps), lw["qkv_w"])
+        o = ops.paged_decode_attention(qkv, kv.k[li], kv.v[li], kv.table, st["ctx_len"], st["first_valid"], heads,
+                                       kv.page_size, 1.0, workspace=st["ws"], counters=st["cnt"], splits=1,
+                                       rel_bias=st["bias"], rel_center=st["tmax"] - 1)
+        x1 = ops.gemv(o, lw["o_w"], residual=x)
+        cq = ops.gemv(ops.rmsnorm(x1, lw["ln2"], eps), lw["cq_w"]).view(b, 1, inner)
+        co = ops.attention(cq, ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner],
+                           ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner], heads, 1.0, key_mask=key_mask)
+        x2 = ops.gemv(co.view(b, inner), lw["co_w"], residual=x1)
+        ff = lw["ff"]
+        h01 = ops.gemv(ops.rmsnorm(x2, ff["ln"], eps), ff["wi_w"])
+        x = ops.gemv(ops.gated_gelu(h01), ff["wo_w"], residual=x2)
+    alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
+    return ops.gemv(ops.rmsnorm(x, w["dec_ln"], eps), w["head"], alpha=alpha, out_dtype=torch.float32)
 
 
 def t5_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None):

@@ -47,53 +47,66 @@ class _OptStepper:
 
 
 class _T5Stepper:
-    """Encoder-decoder LM (flan-T5): the encoder and the cross-attention K|V run once; every step
-    re-runs the decoder over the prefix (see engine/t5.py::t5_decode_logits).  With a CUDA graph
-    the prefix lives in a fixed-length buffer and the logits are read at the current position, so
-    one captured step serves every token."""
+    """Encoder-decoder LM (flan-T5): the encoder and the cross-attention K|V run once.  Up to 16
+    rows (batch x beams) decode token by token on the weight-streaming kernels with a paged
+    self-attention cache (engine/t5.py::t5_decode_step), one CUDA graph per generate call;
+    larger batches re-run the decoder over the prefix (t5_decode_logits)."""
 
     def __init__(self, lm) -> None:
         self.lm = lm
         self.start_token = int(lm.config.decoder_start_token_id)
-        self.pad = int(lm.config.pad_token_id if lm.config.pad_token_id is not None else 0)
         self._graph = None
+        self.cached = False
 
     def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
-        self.enc = E_t5.t5_encode(self.lm, self.lm._pack, input_ids, attention_mask, video_mask, feats)
+        lm = self.lm
+        self.enc = E_t5.t5_encode(lm, lm._pack, input_ids, attention_mask, video_mask, feats)
         self.status = self.enc["status"]
         b, dev = input_ids.shape[0], input_ids.device
-        self.max_new = max_new
-        self.buf = torch.full((b, max_new + 1), self.pad, dtype=torch.long, device=dev)
-        self.buf[:, 0] = self.start_token
-        self.t = 0  # position of the newest prefix token
-        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf[:, :1])
+        start = torch.full((b,), self.start_token, dtype=torch.long, device=dev)
+        self.cached = b <= 16 and (lm.config.num_heads * lm.config.d_kv) % 8 == 0
+        if self.cached:
+            self.st = E_t5.t5_decode_init(lm, lm._pack, self.enc, max_new)
+            return E_t5.t5_decode_step(lm, lm._pack, self.enc, self.st, start)
+        self.prefix = start.view(b, 1)
+        return E_t5.t5_decode_logits(lm, lm._pack, self.enc, self.prefix)
 
     def graph(self, rows, dev):
-        """Captures the fixed-length decoder step; returns an object with .step(tokens)."""
-        if self.max_new < 4:
+        """Captures the cached decoder step; returns an object with .step(tokens)."""
+        if not self.cached:
             return None
-        self.pos = torch.zeros(rows, dtype=torch.long, device=dev)
+        lm = self.lm
+        self._tokens = torch.zeros(rows, dtype=torch.long, device=dev)
+        snap = self.st["ctx_len"].clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up: packs, kernel attributes, allocator
-            E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf, self.pos)
+        with torch.cuda.stream(side):  # warm-up: kernel attributes, allocator
+            E_t5.t5_decode_step(lm, lm._pack, self.enc, self.st, self._tokens)
         torch.cuda.current_stream().wait_stream(side)
+        self.st["ctx_len"].copy_(snap)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._logits = E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf, self.pos)
+            self._logits = E_t5.t5_decode_step(lm, lm._pack, self.enc, self.st, self._tokens)
+        self.st["ctx_len"].copy_(snap)
         return self
 
     def step(self, tokens):
-        self.t += 1
-        self.buf[:, self.t] = tokens.view(-1)
+        lm = self.lm
         if self._graph is not None:
-            self.pos.fill_(self.t)
+            self._tokens.copy_(tokens.view(-1))
             self._graph.replay()
             return self._logits
-        return E_t5.t5_decode_logits(self.lm, self.lm._pack, self.enc, self.buf[:, : self.t + 1])
+        if self.cached:
+            return E_t5.t5_decode_step(lm, lm._pack, self.enc, self.st, tokens.view(-1))
+        self.prefix = torch.cat([self.prefix, tokens.view(-1, 1)], dim=1)
+        return E_t5.t5_decode_logits(lm, lm._pack, self.enc, self.prefix)
 
     def reorder(self, src) -> None:
-        self.buf.copy_(self.buf[src])  # beams of one prompt share its encoder rows
+        # beams of one prompt share its encoder rows and all rows have the same length
+        if self.cached:
+            self.st["kv"].reorder(src)
+        else:
+            self.prefix = self.prefix[src]
 
 
 _UNSUPPORTED = ("penalty_alpha", "num_beam_groups", "diversity_penalty", "constraints",

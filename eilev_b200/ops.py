@@ -534,7 +534,9 @@ def paged_kv_write(k, v, k_cache, v_cache, page_table, page_size: int) -> None:
 
 def paged_decode_attention(qkv, k_cache, v_cache, page_table, ctx_len, first_valid, heads: int,
                            page_size: int, scale: float, *, workspace=None, counters=None,
-                           splits: int = 8) -> torch.Tensor:
+                           splits: int = 8, rel_bias=None, rel_center: int = 0) -> torch.Tensor:
+    """rel_bias (heads, n) f32 + rel_center: T5 decoder self-attention bias of cached token l seen
+    from the newest position, rel_bias[h, rel_center + l - (ctx - 1)]."""
     b = qkv.shape[0]
     hd = qkv.shape[1] // 3
     d = hd // heads
@@ -548,6 +550,8 @@ def paged_decode_attention(qkv, k_cache, v_cache, page_table, ctx_len, first_val
                                                ctx_len.data_ptr(), _ptr(first_valid),
                                                out.data_ptr(), workspace.data_ptr(),
                                                counters.data_ptr(), splits, b, heads, d, page_size,
-                                               page_table.shape[1], scale, _stream()),
+                                               page_table.shape[1], scale, _ptr(rel_bias),
+                                               rel_bias.stride(0) if rel_bias is not None else 0,
+                                               int(rel_center), _stream()),
           "vb_paged_decode_attention")
     return out

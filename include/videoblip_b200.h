@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 2
+#define VB_ABI_VERSION 3
 
 /* dtype tags */
 #define VB_BF16 0
@@ -357,12 +357,16 @@ int vb_debug_decode_trace(void* buffer);
  * The context is processed in `splits` independent CTAs per (sequence, head)
  * (flash-decoding); workspace: f32 (B*H*splits*(D+2)); counters: int32 (B*H), zero on
  * entry and left zero on exit.
+ * rel_bias (f32 or NULL): T5 decoder self-attention — rel_bias[h * rel_stride + rel_center +
+ * (l - (ctx - 1))] is added to the score of cached token l (HF:t5/modeling_t5.py compute_bias
+ * with the newest token as the only query).
  * HF:opt/modeling_opt.py:159-161 (DynamicCache.update) + :163-176. */
 int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
                               const int32_t* page_table, const int32_t* ctx_len,
                               const int32_t* first_valid, void* out, float* workspace,
                               int32_t* counters, int64_t splits, int64_t batch, int64_t heads,
                               int64_t d, int64_t page_size, int64_t max_pages, float scale,
+                              const float* rel_bias, int64_t rel_stride, int64_t rel_center,
                               void* stream);
 /* Copy prefill K/V (B, L, ld) rows into the paged cache. */
 int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,
