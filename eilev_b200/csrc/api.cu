@@ -237,7 +237,7 @@ int vb_gemv(const void* x, const void* w, const float* bias, const void* residua
             int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,
             float alpha, int64_t alpha_cols, int32_t epilogue, int32_t out_dtype,
             const float* ln_gamma, const float* ln_beta, float ln_eps, void* stream) {
-  if ((ln_gamma == nullptr) != (ln_beta == nullptr)) return fail_msg("vb_gemv", "ln_gamma/ln_beta must come together");
+  if (ln_gamma == nullptr && ln_beta != nullptr) return fail_msg("vb_gemv", "ln_beta without ln_gamma");
   VB_CHECK("vb_gemv", vb::gemv_launch(x, w, bias, residual, y, m, n, k, ldx, ldw, ldy, ldr, alpha,
                                       alpha_cols, epilogue, out_dtype, ln_gamma, ln_beta, ln_eps, st(stream)));
 }

@@ -268,6 +268,7 @@ VB_DEVICE void gemv_stage_x(const GemvView& p, int m, __nv_bfloat16* xs, float* 
   // ln_*_s: shared-memory copies requested with cp.async before the bulk weight loads
   const float* ln_g = p.ln_g() == nullptr ? nullptr : (ln_g_s != nullptr ? ln_g_s : p.ln_g());
   const float* ln_b = ln_b_s != nullptr ? ln_b_s : p.ln_b();
+  const bool rms = ln_b == nullptr;  // gamma without beta: T5LayerNorm (no mean subtraction, no bias)
   const int tid = warp * 32 + lane;
   float* red2 = red + NW * MR;
   // pass 1: copy + row sums; the loads of up to four rows are issued back to back
@@ -315,7 +316,7 @@ VB_DEVICE void gemv_stage_x(const GemvView& p, int m, __nv_bfloat16* xs, float* 
   };
   for (int r = 0; r < m; ++r) {  // pass 2: centred sums of squares (own columns only)
     const __nv_bfloat16* xd = xs + static_cast<size_t>(r) * xstride;
-    const float mu = total(red, r) / static_cast<float>(K);
+    const float mu = rms ? 0.0f : total(red, r) / static_cast<float>(K);
     float acc = 0.0f;
     for (int c = tid * 8; c < K; c += NW * 256) {
       const uint4 v = *reinterpret_cast<const uint4*>(xd + c);
@@ -330,13 +331,15 @@ VB_DEVICE void gemv_stage_x(const GemvView& p, int m, __nv_bfloat16* xs, float* 
   __syncthreads();
   for (int r = 0; r < m; ++r) {  // pass 3: normalise in place
     __nv_bfloat16* xd = xs + static_cast<size_t>(r) * xstride;
-    const float mu = total(red, r) / static_cast<float>(K);
+    const float mu = rms ? 0.0f : total(red, r) / static_cast<float>(K);
     const float rstd = rsqrtf(total(red2, r) / static_cast<float>(K) + p.ln_eps());
     for (int c = tid * 8; c < K; c += NW * 256) {
       const uint4 v = *reinterpret_cast<const uint4*>(xd + c);
       const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
       const float4 g0 = *reinterpret_cast<const float4*>(ln_g + c), g1 = *reinterpret_cast<const float4*>(ln_g + c + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(ln_b + c), b1 = *reinterpret_cast<const float4*>(ln_b + c + 4);
+      const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const float4 b0 = rms ? zero4 : *reinterpret_cast<const float4*>(ln_b + c);
+      const float4 b1 = rms ? zero4 : *reinterpret_cast<const float4*>(ln_b + c + 4);
       uint4 o;
       o.x = pack_bf16x2((a0.x - mu) * rstd * g0.x + b0.x, (a0.y - mu) * rstd * g0.y + b0.y);
       o.y = pack_bf16x2((a1.x - mu) * rstd * g0.z + b0.z, (a1.y - mu) * rstd * g0.w + b0.w);
@@ -511,11 +514,11 @@ __global__ void __launch_bounds__(kGW * 32, 2) gemv_mma_kernel(const vb_decode_o
   const GemvGeom G = gemv_geom_blocks<kGW>(p, blockIdx.x, gridDim.x, warp);
   // The small constants of this op (LN affine, bias rows) are requested FIRST: the per-SM load
   // path is in order, so behind 128 KB of weight prefetch they would wait microseconds.
-  const bool ln = p.ln_g() != nullptr;
+  const bool ln = p.ln_g() != nullptr, ln_bias = p.ln_b() != nullptr;
   if (ln) {
     for (int c = threadIdx.x * 4; c < K; c += kGW * 128) {
       cp_async_16(lng_s + c, p.ln_g() + c);
-      cp_async_16(lnb_s + c, p.ln_b() + c);
+      if (ln_bias) cp_async_16(lnb_s + c, p.ln_b() + c);
     }
   }
   const long long row0 = G.rbf * 16;
@@ -534,7 +537,8 @@ __global__ void __launch_bounds__(kGW * 32, 2) gemv_mma_kernel(const vb_decode_o
   gemv_prime<kGW, kMD>(p, G, cur, buf, g, t);
   pdl_trigger();
   pdl_wait();  // x / residual come from the previous kernel of the stream
-  gemv_stage_x<kGW, NT * 8>(p, m, xs, psum, warp, lane, NoHook(), ln ? lng_s : nullptr, ln ? lnb_s : nullptr);
+  gemv_stage_x<kGW, NT * 8>(p, m, xs, psum, warp, lane, NoHook(), ln ? lng_s : nullptr,
+                            (ln && ln_bias) ? lnb_s : nullptr);
   gemv_main<NT, kGW, kMD>(p, m, G, cur, buf, xs, psum, warp, g, t);
   __syncthreads();
   gemv_finalize<NT, kGW>(p, m, G, psum, threadIdx.x, nullptr, p.bias() != nullptr ? bias_s : nullptr);
@@ -614,7 +618,7 @@ cudaError_t gemv_launch(const void* x, const void* w, const float* bias, const v
   if (m <= 0 || n <= 0) return cudaSuccess;
   if (m > kGemvMaxM || k <= 0) return cudaErrorInvalidValue;
   const bool vec = (k % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(w));
-  const bool ln_al = ln_gamma == nullptr || (aligned16(ln_gamma) && aligned16(ln_beta));
+  const bool ln_al = ln_gamma == nullptr || (aligned16(ln_gamma) && (ln_beta == nullptr || aligned16(ln_beta)));
   if (vec && ln_al && k % 64 == 0) {
     const int nt = m <= 8 ? 1 : 2;
     const bool ln = ln_gamma != nullptr;

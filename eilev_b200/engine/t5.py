@@ -305,20 +305,20 @@ def t5_decode_step(lm, cache: PackCache, enc: dict, st: dict, tokens: torch.Tens
     st["ctx_len"].add_(1)
     x = ops.embedding(tokens, w["shared"])
     for li, lw in enumerate(w["dec"]):
-        qkv = ops.gemv(ops.rmsnorm(x, lw["ln1"], eps), lw["qkv_w"])
+        qkv = ops.gemv(x, lw["qkv_w"], ln=(lw["ln1"], None, eps))  # RMSNorm fused into the staging
         o = ops.paged_decode_attention(qkv, kv.k[li], kv.v[li], kv.table, st["ctx_len"], st["first_valid"], heads,
                                        kv.page_size, 1.0, workspace=st["ws"], counters=st["cnt"], splits=1,
                                        rel_bias=st["bias"], rel_center=st["tmax"] - 1)
         x1 = ops.gemv(o, lw["o_w"], residual=x)
-        cq = ops.gemv(ops.rmsnorm(x1, lw["ln2"], eps), lw["cq_w"]).view(b, 1, inner)
+        cq = ops.gemv(x1, lw["cq_w"], ln=(lw["ln2"], None, eps)).view(b, 1, inner)
         co = ops.attention(cq, ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner],
                            ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner], heads, 1.0, key_mask=key_mask)
         x2 = ops.gemv(co.view(b, inner), lw["co_w"], residual=x1)
         ff = lw["ff"]
-        h01 = ops.gemv(ops.rmsnorm(x2, ff["ln"], eps), ff["wi_w"])
+        h01 = ops.gemv(x2, ff["wi_w"], ln=(ff["ln"], None, eps))
         x = ops.gemv(ops.gated_gelu(h01), ff["wo_w"], residual=x2)
     alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
-    return ops.gemv(ops.rmsnorm(x, w["dec_ln"], eps), w["head"], alpha=alpha, out_dtype=torch.float32)
+    return ops.gemv(x, w["head"], alpha=alpha, out_dtype=torch.float32, ln=(w["dec_ln"], None, eps))
 
 
 def t5_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None):

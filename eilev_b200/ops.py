@@ -459,13 +459,14 @@ def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
 def gemv(x: torch.Tensor, w: torch.Tensor, bias=None, *, residual=None, epilogue: int = EPI_NONE,
          alpha: float = 1.0, alpha_cols: int = 0, out_dtype=torch.bfloat16, ln=None) -> torch.Tensor:
     """Decode-time projection for M <= 16 rows (weight-streaming).  ln = (gamma, beta, eps)
-    fuses the LayerNorm of x into the kernel's staging pass."""
+    fuses the LayerNorm of x into the kernel's staging pass; beta = None selects RMSNorm (T5)."""
     _need(x, torch.bfloat16, "gemv.x")
     _need(w, torch.bfloat16, "gemv.w")
     m, k = x.shape
     n = w.shape[0]
-    if ln is not None and (k % 256 != 0 or max(1, 1 << (m - 1).bit_length()) * k * 2 > 160 * 1024):
-        x = layernorm(x, ln[0], ln[1], ln[2])  # shapes the staged kernel does not take
+    if ln is not None and (k % 64 != 0 or m * (k + 32) * 2 + 8 * k + 16384 > 190 * 1024):
+        # shapes the staged kernel does not take
+        x = layernorm(x, ln[0], ln[1], ln[2]) if ln[1] is not None else rmsnorm(x, ln[0], ln[2])
         ln = None
     y = torch.empty((m, n), dtype=out_dtype, device=x.device)
     check(_lib.lib().vb_gemv(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(),

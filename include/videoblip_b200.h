@@ -288,7 +288,8 @@ int vb_token_logprob(const void* logits, int32_t logits_dtype, const int64_t* ro
  * weight-streaming kernel for token-by-token generation (HBM bound).  bf16 in/out,
  * out_dtype selects bf16|f32.  When ln_gamma/ln_beta (f32, k) are given, x is
  * LayerNorm-ed (eps ln_eps, rounded to bf16 like vb_layernorm) while it is staged in
- * shared memory — the pre-LN of an OPT block costs no launch.
+ * shared memory — the pre-LN of an OPT block costs no launch.  ln_gamma without ln_beta selects
+ * RMSNorm (T5LayerNorm: no mean subtraction, no bias).
  * HF:opt/modeling_opt.py:135-253 at tgt_len == 1. */
 int vb_gemv(const void* x, const void* w, const float* bias, const void* residual, void* y,
             int64_t m, int64_t n, int64_t k, int64_t ldx, int64_t ldw, int64_t ldy, int64_t ldr,

@@ -588,3 +588,15 @@ def test_embedding_gather():
     ids = torch.tensor([[0, 49, 7], [3, 3, 60]], device="cuda")
     out = ops.embedding(ids, table)
     assert torch.equal(out, table[ids.clamp(max=49)])
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 6144, 2048), (3, 384, 128), (8, 2048, 2048), (2, 300, 192)])
+def test_gemv_fused_rmsnorm(m, n, k):
+    """vb_gemv with ln_gamma and no ln_beta = T5LayerNorm (RMSNorm) fused into the x staging."""
+    ops = _ops()
+    x, w = _rand(m, k, seed=150), _rand(n, k, scale=0.03, seed=151)
+    g = (1 + 0.1 * torch.randn(k, device="cuda")).float()
+    xf = x.float()
+    xn = (g * xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(torch.bfloat16).float()
+    got = ops.gemv(x, w, ln=(g, None, 1e-6), out_dtype=torch.float32)
+    _close(got, xn @ w.float().t(), atol=0.03, rtol=0.02, what="rms+gemv")
