@@ -9,8 +9,11 @@ legs may import this module, and only as the checker / the CPU baseline.
 Parity status: PINNED.  ``tests/golden/make_golden.py`` runs the *real* reference
 (``/root/reference/eilev/model/v2.py`` on the installed transformers 5.5.0; the reference
 pins 4.33.1, whose equations for this path are the same) on seeded inputs and commits
-inputs + outputs under ``tests/golden/``; ``tests/test_oracle.py`` checks this restatement
-against those fixtures (and against the live reference when ``/root/reference`` exists).
+inputs + outputs under ``tests/golden/`` (``make_golden_classify.py`` does the same for ``classify``
+— the reference's own method behind a tuple<->Cache shim —, ``make_golden_t5.py`` for the flan-T5
+branch incl. greedy ``generate``, ``make_golden_beams.py`` for HF beam search / repetition penalty);
+``tests/test_oracle.py`` checks this restatement against those fixtures (and against the live
+reference when ``/root/reference`` exists).
 The reference's own tests pin shapes only (tests/model/test_model_v2.py:53-83,185-186).
 
 Citations: ``v2.py`` = eilev/model/v2.py; ``HF:`` = transformers/models/…
