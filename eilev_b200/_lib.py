@@ -93,6 +93,7 @@ SIGNATURES: dict[str, list] = {
     "vb_decode_step": [vp, vp, i32, i32, vp, vp],
     "vb_paged_decode_attention": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32,
                                   vp, i64, i64, vp],
+    "vb_decode_cross_attention": [vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp],
     "vb_paged_kv_write": [vp, vp, i64, vp, vp, vp, i64, i64, i64, i64, i64, vp],
 }
 

@@ -274,6 +274,16 @@ int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
                                              rel_center, st(stream)));
 }
 
+int vb_decode_cross_attention(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_stride,
+                              const int32_t* seq_ids, const int32_t* ctx_len, const int32_t* first_valid,
+                              void* out, float* workspace, int32_t* counters, int64_t splits, int64_t batch,
+                              int64_t heads, int64_t d, int64_t max_ctx, float scale, void* stream) {
+  VB_CHECK("vb_decode_cross_attention",
+           vb::decode_cross_attention_launch(q, q_stride, k, v, kv_stride, seq_ids, ctx_len, first_valid, out,
+                                             workspace, counters, splits, batch, heads, d, max_ctx, scale,
+                                             st(stream)));
+}
+
 int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,
                       const int32_t* page_table, int64_t batch, int64_t seq, int64_t hd,
                       int64_t page_size, int64_t max_pages, void* stream) {

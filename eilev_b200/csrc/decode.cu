@@ -754,6 +754,11 @@ struct AttnArgs {
   // rel_bias[h * rel_stride + rel_center + (l - (ctx - 1))]; nullptr = none
   const float* rel_bias;
   int rel_stride, rel_center;
+  // generalisations for the one-query cross-attention of an encoder-decoder LM: elements
+  // between consecutive cached tokens (0 = heads*D), between the q rows of consecutive
+  // sequences (0 = 3*heads*D), and whether this step's k/v row is appended (self-attention)
+  long long kv_stride, q_stride;
+  int append;
 };
 
 __host__ __device__ inline int attn_unit_smem_floats(int D, int chunk_cap) { return D + chunk_cap + 16 * D + 8; }
@@ -778,16 +783,18 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
   float* red = part + 16 * D;        // 4
   int* s_last = reinterpret_cast<int*>(red + 4);
   const int* pt = a.page_table + static_cast<long long>(b) * a.max_pages;
-  const __nv_bfloat16* row = a.qkv + static_cast<long long>(b) * 3 * hd;
+  const long long kvs = a.kv_stride > 0 ? a.kv_stride : hd;
+  const __nv_bfloat16* row = a.qkv + static_cast<long long>(b) * (a.q_stride > 0 ? a.q_stride : 3 * hd);
   const int warp = tid >> 5, lane = tid & 31;
   __nv_bfloat16* kc = a.kc;
   __nv_bfloat16* vc = a.vc;
   auto tok_off = [&](int l) {
-    return (static_cast<long long>(pt[l / page_size]) * page_size + l % page_size) * hd + h * D;
+    return (static_cast<long long>(pt[l / page_size]) * page_size + l % page_size) * kvs + h * D;
   };
-  const bool vec = (D % 8 == 0) && (hd % 8 == 0);
+  const bool vec = (D % 8 == 0) && (hd % 8 == 0) && (kvs % 8 == 0);
   const bool fast = vec && D <= 128;  // whole K row (<= 16 x 16 B) and 8 V pieces live in registers
-  const int newest = ctx - 1;         // this step's token: its k/v come from the qkv row
+  // this step's token: its k/v come from the qkv row (self-attention); none for cross-attention
+  const int newest = a.append ? ctx - 1 : -1;
   // phase-2 mapping: thread = (token group, 8-wide d vector)
   const int nvec = (D + 7) / 8;
   int groups = 128 / nvec;
@@ -819,7 +826,7 @@ VB_DEVICE void attn_unit(const AttnArgs& a, int h, int b, int sp, int tid, float
   if (WAIT) pdl_wait();
 
   // ---- q (pre-scaled) and the new token's k / v
-  const bool owns_new = (newest >= lo && newest < hi);
+  const bool owns_new = a.append && (newest >= lo && newest < hi);
   for (int c = tid; c < D; c += 128) {
     if (owns_new) {
       const long long dst = tok_off(newest);
@@ -1015,6 +1022,42 @@ cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* 
   a.max_pages = static_cast<int>(max_pages); a.splits = static_cast<int>(splits);
   a.chunk_cap = static_cast<int>(chunk_cap); a.scale = scale;
   a.rel_bias = rel_bias; a.rel_stride = static_cast<int>(rel_stride); a.rel_center = static_cast<int>(rel_center);
+  a.kv_stride = 0; a.q_stride = 0; a.append = 1;
+  dim3 grid(static_cast<unsigned>(heads), static_cast<unsigned>(batch), static_cast<unsigned>(splits));
+  return launch_pdl(paged_decode_attn_kernel, grid, dim3(128), smem, s, a);
+}
+
+// One query per sequence over a dense (B, L, stride) key / value buffer — the cross-attention of
+// a decoder step over the encoder's projected K|V (no append, no paging: page b = sequence b).
+cudaError_t decode_cross_attention_launch(const void* q, long long q_stride, const void* k, const void* v,
+                                          long long kv_stride, const int* seq_ids, const int* ctx_len,
+                                          const int* first_valid, void* out, float* workspace, int* counters,
+                                          long long splits, long long batch, long long heads, long long d,
+                                          long long max_ctx, float scale, cudaStream_t s) {
+  if (batch <= 0 || heads <= 0) return cudaSuccess;
+  if (splits <= 0 || splits > 64 || workspace == nullptr || counters == nullptr || seq_ids == nullptr ||
+      out == nullptr || max_ctx <= 0)
+    return cudaErrorInvalidValue;
+  const long long chunk_cap = (max_ctx + splits - 1) / splits;
+  const size_t smem = sizeof(float) * static_cast<size_t>(attn_unit_smem_floats(static_cast<int>(d), static_cast<int>(chunk_cap)));
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(paged_decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  AttnArgs a;
+  a.qkv = reinterpret_cast<const __nv_bfloat16*>(q);
+  a.kc = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(k));
+  a.vc = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(v));
+  a.page_table = seq_ids; a.ctx_len = ctx_len; a.first_valid = first_valid;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.ws = workspace; a.counters = counters;
+  a.heads = static_cast<int>(heads); a.D = static_cast<int>(d); a.page_size = static_cast<int>(max_ctx);
+  a.max_pages = 1; a.splits = static_cast<int>(splits); a.chunk_cap = static_cast<int>(chunk_cap);
+  a.scale = scale;
+  a.rel_bias = nullptr; a.rel_stride = 0; a.rel_center = 0;
+  a.kv_stride = kv_stride; a.q_stride = q_stride; a.append = 0;
   dim3 grid(static_cast<unsigned>(heads), static_cast<unsigned>(batch), static_cast<unsigned>(splits));
   return launch_pdl(paged_decode_attn_kernel, grid, dim3(128), smem, s, a);
 }
@@ -1126,6 +1169,7 @@ decode_step_kernel(const vb_decode_op* __restrict__ ops, int n_ops, int m, unsig
         a.heads = op.i32[0]; a.D = op.i32[1]; a.page_size = op.i32[2]; a.max_pages = op.i32[3];
         a.splits = op.i32[4]; a.chunk_cap = op.i32[5]; a.scale = op.f32[0];
         a.rel_bias = nullptr; a.rel_stride = 0; a.rel_center = 0;
+        a.kv_stride = 0; a.q_stride = 0; a.append = 1;
         const int sub = threadIdx.x >> 7, tid = threadIdx.x & 127;
         float* sm = reinterpret_cast<float*>(gsm) + static_cast<size_t>(sub) * attn_unit_smem_floats(a.D, a.chunk_cap);
         const int units = a.heads * m * a.splits;

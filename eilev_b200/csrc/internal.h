@@ -92,6 +92,11 @@ cudaError_t paged_decode_attention_launch(const void* qkv, void* k_cache, void* 
                                           long long heads, long long d, long long page_size,
                                           long long max_pages, float scale, const float* rel_bias,
                                           long long rel_stride, long long rel_center, cudaStream_t s);
+cudaError_t decode_cross_attention_launch(const void* q, long long q_stride, const void* k, const void* v,
+                                          long long kv_stride, const int* seq_ids, const int* ctx_len,
+                                          const int* first_valid, void* out, float* workspace, int* counters,
+                                          long long splits, long long batch, long long heads, long long d,
+                                          long long max_ctx, float scale, cudaStream_t s);
 cudaError_t paged_kv_write_launch(const void* k, const void* v, long long ld, void* k_cache,
                                   void* v_cache, const int* page_table, long long batch,
                                   long long seq, long long hd, long long page_size,

@@ -237,7 +237,16 @@ def t5_encode(lm, cache: PackCache, input_ids, attention_mask, video_mask, video
         x, _ = _ff_fwd(x_mid, lw["ff"], eps)
     enc_out = ops.rmsnorm(x, w["enc_ln"], eps)
     ckv = ops.gemm(enc_out, w["ckv_w"]).view(b, l, len(w["dec"]) * 2 * inner)
-    return dict(ckv=ckv, key_mask=key_mask, status=status, b=b, l=l, enc_out=enc_out.view(b, l, dm))
+    # valid encoder tokens as [first, end) per row for the one-query cross-attention of decode
+    # steps (padding at either end; a mask with holes falls back to the flash kernel)
+    am = attention_mask.bool()
+    n_valid = am.sum(dim=1)
+    first = am.int().argmax(dim=1)
+    idx = torch.arange(l, device=am.device)[None, :]
+    contiguous = bool(((idx >= first[:, None]) & (idx < (first + n_valid)[:, None]) == am).all())
+    return dict(ckv=ckv, key_mask=key_mask, status=status, b=b, l=l, enc_out=enc_out.view(b, l, dm),
+                enc_first=first.to(torch.int32).contiguous(), enc_end=(first + n_valid).to(torch.int32).contiguous(),
+                enc_contiguous=contiguous)
 
 
 def t5_decode_logits(lm, cache: PackCache, enc: dict, decoder_input_ids: torch.Tensor) -> torch.Tensor:
@@ -283,7 +292,12 @@ def t5_decode_init(lm, cache: PackCache, enc: dict, max_new: int) -> dict:
     dev = enc["ckv"].device
     tmax = max_new + 1
     kv = PagedKV(len(w["dec"]), b, tmax, inner, dev)
+    l = enc["l"]
+    csplits = max(1, min(8, (l + 127) // 128))
     return dict(kv=kv, tmax=tmax, bias=rel_bias_table(w["dec_rel"], tmax, tmax, False, cfg),
+                csplits=csplits, seq_ids=torch.arange(b, dtype=torch.int32, device=dev),
+                cws=torch.empty(b * heads * csplits * (cfg.d_kv + 2), dtype=torch.float32, device=dev),
+                ccnt=torch.zeros(b * heads, dtype=torch.int32, device=dev),
                 ctx_len=torch.zeros(b, dtype=torch.int32, device=dev),
                 first_valid=torch.zeros(b, dtype=torch.int32, device=dev),
                 ws=torch.empty(b * heads * (cfg.d_kv + 2), dtype=torch.float32, device=dev),
@@ -310,10 +324,15 @@ def t5_decode_step(lm, cache: PackCache, enc: dict, st: dict, tokens: torch.Tens
                                        kv.page_size, 1.0, workspace=st["ws"], counters=st["cnt"], splits=1,
                                        rel_bias=st["bias"], rel_center=st["tmax"] - 1)
         x1 = ops.gemv(o, lw["o_w"], residual=x)
-        cq = ops.gemv(x1, lw["cq_w"], ln=(lw["ln2"], None, eps)).view(b, 1, inner)
-        co = ops.attention(cq, ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner],
-                           ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner], heads, 1.0, key_mask=key_mask)
-        x2 = ops.gemv(co.view(b, inner), lw["co_w"], residual=x1)
+        cq = ops.gemv(x1, lw["cq_w"], ln=(lw["ln2"], None, eps))
+        ck = ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner]
+        cv = ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner]
+        if enc["enc_contiguous"]:
+            co = ops.decode_cross_attention(cq, ck, cv, st["seq_ids"], enc["enc_end"], enc["enc_first"], heads, 1.0,
+                                            workspace=st["cws"], counters=st["ccnt"], splits=st["csplits"])
+        else:
+            co = ops.attention(cq.view(b, 1, inner), ck, cv, heads, 1.0, key_mask=key_mask).view(b, inner)
+        x2 = ops.gemv(co, lw["co_w"], residual=x1)
         ff = lw["ff"]
         h01 = ops.gemv(x2, ff["wi_w"], ln=(ff["ln"], None, eps))
         x = ops.gemv(ops.gated_gelu(h01), ff["wo_w"], residual=x2)

@@ -523,6 +523,22 @@ def decode_step(ops_host, ops_dev: torch.Tensor, m: int, barrier: torch.Tensor) 
                                     barrier.data_ptr(), _stream()), "vb_decode_step")
 
 
+def decode_cross_attention(q, k, v, seq_ids, ctx_len, first_valid, heads: int, scale: float, *,
+                           workspace, counters, splits: int) -> torch.Tensor:
+    """One query per sequence over dense keys / values: q (B, H*D) bf16; k, v (B, L, H*D) bf16 views
+    (e.g. column slices of one projection output) with the same strides."""
+    _need(q, torch.bfloat16, "decode_cross_attention.q")
+    assert k.dim() == 3 and k.stride(2) == 1 and k.stride() == v.stride() and k.stride(0) == k.shape[1] * k.stride(1)
+    b, hd = q.shape
+    out = torch.empty((b, hd), dtype=torch.bfloat16, device=q.device)
+    check(_lib.lib().vb_decode_cross_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1),
+                                               seq_ids.data_ptr(), ctx_len.data_ptr(), first_valid.data_ptr(),
+                                               out.data_ptr(), workspace.data_ptr(), counters.data_ptr(), splits,
+                                               b, heads, hd // heads, k.shape[1], scale, _stream()),
+          "vb_decode_cross_attention")
+    return out
+
+
 def paged_kv_write(k, v, k_cache, v_cache, page_table, page_size: int) -> None:
     """k, v: (B, L, H*D) views with a common row stride."""
     b, l, hd = k.shape

@@ -369,6 +369,16 @@ int vb_paged_decode_attention(const void* qkv, void* k_cache, void* v_cache,
                               int64_t d, int64_t page_size, int64_t max_pages, float scale,
                               const float* rel_bias, int64_t rel_stride, int64_t rel_center,
                               void* stream);
+/* One-query cross-attention of a decoder step over the encoder's projected keys / values
+ * (HF:t5/modeling_t5.py EncDecAttention at tgt_len == 1): q (B, heads*d) bf16 with row stride
+ * q_stride; k, v: token l of sequence b at k + (seq_ids[b] * max_ctx + l) * kv_stride + h*d (dense
+ * (B, L, stride) buffers, K and V may be column slices of one GEMM output); tokens
+ * [first_valid[b], ctx_len[b]) are attended (padding at either end).  Same flash-decoding splits /
+ * workspace / counters contract as vb_paged_decode_attention; nothing is appended. */
+int vb_decode_cross_attention(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_stride,
+                              const int32_t* seq_ids, const int32_t* ctx_len, const int32_t* first_valid,
+                              void* out, float* workspace, int32_t* counters, int64_t splits, int64_t batch,
+                              int64_t heads, int64_t d, int64_t max_ctx, float scale, void* stream);
 /* Copy prefill K/V (B, L, ld) rows into the paged cache. */
 int vb_paged_kv_write(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,
                       const int32_t* page_table, int64_t batch, int64_t seq, int64_t hd,

@@ -600,3 +600,28 @@ def test_gemv_fused_rmsnorm(m, n, k):
     xn = (g * xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(torch.bfloat16).float()
     got = ops.gemv(x, w, ln=(g, None, 1e-6), out_dtype=torch.float32)
     _close(got, xn @ w.float().t(), atol=0.03, rtol=0.02, what="rms+gemv")
+
+
+@pytest.mark.parametrize("splits", [1, 4, 8])
+def test_decode_cross_attention_over_dense_encoder_kv(splits):
+    """One query per sequence over K / V that are column slices of one (B, L, n*H*D) projection
+    output, valid tokens [first, end) per row (right- and left-padded rows)."""
+    ops = _ops()
+    b, heads, d, l, n_slices = 3, 4, 64, 300, 6
+    hd = heads * d
+    ckv = _rand(b, l, n_slices * hd, seed=160)
+    k, v = ckv[:, :, 2 * hd:3 * hd], ckv[:, :, 3 * hd:4 * hd]
+    q = _rand(b, hd, seed=161)
+    first = torch.tensor([0, 17, 0], dtype=torch.int32, device="cuda")
+    end = torch.tensor([l, l, 211], dtype=torch.int32, device="cuda")
+    mask = torch.zeros(b, l, dtype=torch.uint8, device="cuda")
+    for i in range(b):
+        mask[i, int(first[i]):int(end[i])] = 1
+    ws = torch.empty(b * heads * splits * (d + 2), dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(b * heads, dtype=torch.int32, device="cuda")
+    seq = torch.arange(b, dtype=torch.int32, device="cuda")
+    for _ in range(2):  # twice: the counters must come back to zero
+        out = ops.decode_cross_attention(q, k, v, seq, end, first, heads, 0.7, workspace=ws, counters=cnt, splits=splits)
+    ref = _attn_ref(q[:, None, :], k, v, heads, 0.7, False, mask)[:, 0]
+    _close(out, ref, atol=0.02, rtol=0.02, what="decode cross attention")
+    assert int(cnt.abs().sum()) == 0
