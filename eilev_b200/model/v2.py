@@ -11,7 +11,6 @@ no CPU or library fallback: calling ``forward`` without a CUDA device raises.
 """
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.nn as nn
