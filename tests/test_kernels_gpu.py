@@ -397,7 +397,7 @@ def test_gemv_and_paged_decode():
 
 @pytest.mark.parametrize("m,n,k", [(1, 2560, 10240), (1, 1003, 2560), (2, 10240, 2560), (4, 50272, 2560),
                                    (8, 2560, 2560), (16, 2560, 2560), (16, 3000, 1024), (1, 77, 256),
-                                   (3, 2560, 10240), (8, 640, 10240)])
+                                   (3, 2560, 10240), (8, 640, 10240), (16, 2560, 10240), (11, 1003, 10240)])
 def test_gemv_bulk_ring_shapes(m, n, k):
     """Weight-streaming GEMV (bulk-copy ring kernel and its fall-backs) across the decode
     shapes: ragged N, every M bucket, K walked in slices, f32 output, residual + bias."""
