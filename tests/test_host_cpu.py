@@ -296,3 +296,33 @@ def test_decode_op_record_layout_matches_the_header():
     assert dt.itemsize == 192 and dt.fields["ptr"][1] == 32 and dt.fields["i64"][1] == 112 and dt.fields["f32"][1] == 176
     assert int(re.search(r"#define VB_DECODE_STEP_WS_BYTES \((\d+) \+ (\d+) \* (\d+)\)", header).group(1)) == 4096
     assert ops.DECODE_STEP_WS_BYTES == 4096 + 1008 * 512
+
+
+# ------------------------------------------------------------------ generation host logic
+def test_logit_processors_match_huggingface():
+    """The token-bookkeeping half of generate() (repetition penalty, min-new-tokens EOS
+    suppression, temperature / top-k / top-p warping) against the HuggingFace processors the
+    reference reaches through language_model.generate (samples/*.py pass these kwargs)."""
+    from transformers.generation.logits_process import (
+        MinNewTokensLengthLogitsProcessor, RepetitionPenaltyLogitsProcessor, TemperatureLogitsWarper,
+        TopKLogitsWarper, TopPLogitsWarper)
+    from eilev_b200.model import generation as G
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(3, 50, generator=g) * 3
+    generated = torch.randint(0, 50, (3, 6), generator=g)
+    # repetition penalty
+    want = RepetitionPenaltyLogitsProcessor(1.3)(generated, logits.clone())
+    got = G._process_logits(logits.clone(), generated, step=6, min_new_tokens=0, eos_ids=[2], repetition_penalty=1.3)
+    assert torch.allclose(got, want)
+    # min_new_tokens: EOS suppressed while fewer than min new tokens exist
+    mn = MinNewTokensLengthLogitsProcessor(prompt_length_to_skip=0, min_new_tokens=8, eos_token_id=[2, 7])
+    want = mn(generated, logits.clone())
+    got = G._process_logits(logits.clone(), generated, step=6, min_new_tokens=8, eos_ids=[2, 7], repetition_penalty=1.0)
+    assert torch.equal(torch.isinf(got), torch.isinf(want)) and torch.allclose(got[~torch.isinf(got)], want[~torch.isinf(want)])
+    got = G._process_logits(logits.clone(), generated, step=8, min_new_tokens=8, eos_ids=[2, 7], repetition_penalty=1.0)
+    assert not torch.isinf(got).any()
+    # warpers, in HF order: temperature, top-k, top-p
+    want = TopPLogitsWarper(0.8)(generated, TopKLogitsWarper(10)(generated, TemperatureLogitsWarper(0.7)(generated, logits.clone())))
+    got = G._warp(logits.clone(), 0.7, 10, 0.8)
+    assert torch.equal(torch.isinf(got), torch.isinf(want))
+    assert torch.allclose(got[~torch.isinf(got)], want[~torch.isinf(want)])
