@@ -214,7 +214,9 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
         attention_mask = attention_mask[rep_idx]
         video_mask = video_mask[rep_idx] if video_mask is not None else None
 
-    stepper = _OptStepper(lm) if model.config.use_decoder_only_language_model else _T5Stepper(lm)
+    stepper = kw.pop("_stepper", None)  # test seam: the decoding loops over an injected LM stepper
+    if stepper is None:
+        stepper = _OptStepper(lm) if model.config.use_decoder_only_language_model else _T5Stepper(lm)
     logits = stepper.prefill(input_ids, attention_mask, video_mask, video_features, max_new)
     model._last_splice_status = stepper.status
 
@@ -273,9 +275,10 @@ def _beam_search(stepper, logits, batch, nb, max_new, min_new, eos_ids, pad_id, 
         return min(h[0] for h in finished[i])
 
     for step in range(max_new):
-        scores = _process_logits(logits, generated, step, min_new_tokens=min_new, eos_ids=eos_ids,
-                                 repetition_penalty=rep)
-        logp = torch.log_softmax(scores, dim=-1)
+        # HF beam search normalises FIRST and runs the logits processors on the log-probabilities
+        # (generation/utils.py::_beam_search step b): a suppressed EOS does not renormalise the rest
+        logp = _process_logits(torch.log_softmax(logits.float(), dim=-1), generated, step, min_new_tokens=min_new,
+                               eos_ids=eos_ids, repetition_penalty=rep)
         if do_sample:
             logp = torch.log_softmax(_warp(logp, temperature, top_k, top_p), dim=-1)
         cand = (logp + beam_scores[:, None]).view(batch, nb * vocab)

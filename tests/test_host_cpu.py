@@ -326,3 +326,63 @@ def test_logit_processors_match_huggingface():
     got = G._warp(logits.clone(), 0.7, 10, 0.8)
     assert torch.equal(torch.isinf(got), torch.isinf(want))
     assert torch.allclose(got[~torch.isinf(got)], want[~torch.isinf(want)])
+
+
+def test_decoding_loops_match_huggingface_generate():
+    """generate()'s greedy and beam-search loops (host logic: hypothesis bookkeeping, length
+    penalty, early-stopping heuristic, min_new_tokens / repetition penalty on log-probs, EOS
+    padding) against HuggingFace generate fed with inputs_embeds — the reference's call
+    (eilev/model/v2.py:318-322) — on a tiny random OPT on CPU, through an injected stepper."""
+    import types
+    from transformers import OPTConfig, OPTForCausalLM
+    from eilev_b200.model import generation as G
+
+    class Stepper:
+        start_token = None
+        status = None
+
+        def __init__(self, lm):
+            self.lm, self.table = lm, lm.get_input_embeddings().weight.detach()
+
+        def _logits(self):
+            with torch.no_grad():
+                return self.lm(inputs_embeds=self.emb).logits[:, -1].float()
+
+        def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
+            self.emb = self.table[input_ids]
+            return self._logits()
+
+        def graph(self, rows, dev):
+            return None
+
+        def step(self, tokens):
+            self.emb = torch.cat([self.emb, self.table[tokens.view(-1)][:, None]], 1)
+            return self._logits()
+
+        def reorder(self, src):
+            self.emb = self.emb[src]
+
+    cases = [dict(num_beams=3), dict(num_beams=4, length_penalty=2.0, repetition_penalty=1.3),
+             dict(num_beams=2, early_stopping=True), dict(num_beams=3, length_penalty=0.5, min_new_tokens=3, repetition_penalty=1.2),
+             dict(num_beams=4, early_stopping="never"), dict(num_beams=1, min_new_tokens=2, repetition_penalty=1.5)]
+    bad = []
+    for seed in range(6):
+        torch.manual_seed(seed)
+        cfg = OPTConfig(hidden_size=16, num_hidden_layers=2, ffn_dim=32, num_attention_heads=2, vocab_size=24,
+                        max_position_embeddings=64, word_embed_proj_dim=16, pad_token_id=1, eos_token_id=2, bos_token_id=0)
+        lm = OPTForCausalLM(cfg).eval()
+        for p in lm.parameters():
+            p.data.normal_(0, 0.6)
+        ids = torch.randint(3, 24, (2, 5))
+        model = types.SimpleNamespace(config=types.SimpleNamespace(text_config=cfg, use_decoder_only_language_model=True),
+                                      language_model=lm)
+        for kw in cases:
+            kw = dict(kw, max_new_tokens=7, do_sample=False, pad_token_id=1, eos_token_id=2)
+            want = lm.generate(inputs_embeds=lm.get_input_embeddings()(ids).detach(), attention_mask=torch.ones_like(ids), **kw)
+            got = G.generate(model, ids, torch.ones_like(ids), None, None, _stepper=Stepper(lm), **kw)
+            n = max(got.shape[1], want.shape[1])
+            got = torch.cat([got, torch.full((2, n - got.shape[1]), 1)], 1)
+            want = torch.cat([want, torch.full((2, n - want.shape[1]), 1)], 1)
+            if not torch.equal(got, want):
+                bad.append((seed, kw, got.tolist(), want.tolist()))
+    assert not bad, bad[:3]
