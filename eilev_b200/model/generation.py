@@ -123,8 +123,13 @@ def _as_list(x):
     return [int(x)]
 
 
-def _process_logits(logits, generated, step, *, min_new_tokens, eos_ids, repetition_penalty):
-    """Logit processors in HF order: repetition penalty, then min-length EOS suppression."""
+def _process_logits(logits, generated, step, *, min_new_tokens, eos_ids, repetition_penalty, start_token=None):
+    """Logit processors in HF order: repetition penalty, then min-length EOS suppression.
+    start_token: an encoder-decoder LM's decoder_start_token — HF hands the processors the
+    decoder input ids, so the start token counts as "already generated" for the penalty."""
+    if start_token is not None:
+        generated = torch.cat([torch.full((generated.shape[0], 1), start_token, dtype=generated.dtype,
+                                          device=generated.device), generated], dim=1)
     if repetition_penalty and repetition_penalty != 1.0 and generated.shape[1] > 0:
         score = torch.gather(logits, 1, generated)
         score = torch.where(score < 0, score * repetition_penalty, score / repetition_penalty)
@@ -240,7 +245,7 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
     eos_t = torch.tensor(eos_ids, device=dev, dtype=torch.long) if eos_ids else None
     for step in range(max_new):
         scores = _process_logits(logits, generated, step, min_new_tokens=min_new, eos_ids=eos_ids,
-                                 repetition_penalty=rep)
+                                 repetition_penalty=rep, start_token=stepper.start_token)
         if do_sample:
             probs = _warp(scores, temperature, top_k, top_p).softmax(dim=-1)
             nxt = torch.multinomial(probs, 1).squeeze(1)
@@ -278,7 +283,7 @@ def _beam_search(stepper, logits, batch, nb, max_new, min_new, eos_ids, pad_id, 
         # HF beam search normalises FIRST and runs the logits processors on the log-probabilities
         # (generation/utils.py::_beam_search step b): a suppressed EOS does not renormalise the rest
         logp = _process_logits(torch.log_softmax(logits.float(), dim=-1), generated, step, min_new_tokens=min_new,
-                               eos_ids=eos_ids, repetition_penalty=rep)
+                               eos_ids=eos_ids, repetition_penalty=rep, start_token=stepper.start_token)
         if do_sample:
             logp = torch.log_softmax(_warp(logp, temperature, top_k, top_p), dim=-1)
         cand = (logp + beam_scores[:, None]).view(batch, nb * vocab)

@@ -386,3 +386,75 @@ def test_decoding_loops_match_huggingface_generate():
             if not torch.equal(got, want):
                 bad.append((seed, kw, got.tolist(), want.tolist()))
     assert not bad, bad[:3]
+
+
+def test_seq2seq_decoding_loops_match_huggingface_generate():
+    """Same as above for the encoder-decoder branch (flan-T5: [decoder_start] + new tokens, the
+    start token counts for the repetition penalty).  Rows are compared up to their first EOS:
+    the pinned transformers 4.33.1 pads finished beams with pad_token_id (as this code does),
+    the installed 5.5.0 fills with EOS when pad_token_id == 0 (`pad_token_id or eos_token_id`)."""
+    import types
+    from transformers import T5Config, T5ForConditionalGeneration
+    from eilev_b200.model import generation as G
+
+    class Stepper:
+        status = None
+
+        def __init__(self, lm):
+            self.lm, self.start_token = lm, lm.config.decoder_start_token_id
+
+        def _logits(self):
+            with torch.no_grad():
+                return self.lm(encoder_outputs=self.enc, attention_mask=self.am,
+                               decoder_input_ids=self.prefix).logits[:, -1].float()
+
+        def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
+            with torch.no_grad():
+                self.enc = self.lm.encoder(inputs_embeds=self.lm.shared(input_ids), attention_mask=attention_mask)
+            self.am = attention_mask
+            self.prefix = torch.full((input_ids.shape[0], 1), self.start_token, dtype=torch.long)
+            return self._logits()
+
+        def graph(self, rows, dev):
+            return None
+
+        def step(self, tokens):
+            self.prefix = torch.cat([self.prefix, tokens.view(-1, 1)], 1)
+            return self._logits()
+
+        def reorder(self, src):
+            self.prefix = self.prefix[src]
+
+    def trim(t, width):
+        t = torch.cat([t, torch.zeros((t.shape[0], width - t.shape[1]), dtype=torch.long)], 1)
+        for r in range(t.shape[0]):
+            e = (t[r, 1:] == 1).nonzero()
+            if e.numel():
+                t[r, int(e[0]) + 2:] = 0
+        return t
+
+    cases = [dict(num_beams=1), dict(num_beams=3), dict(num_beams=4, length_penalty=2.0),
+             dict(num_beams=2, early_stopping=True, min_new_tokens=2), dict(num_beams=1, repetition_penalty=1.4)]
+    bad = []
+    for seed in range(6):
+        torch.manual_seed(seed)
+        cfg = T5Config(d_model=16, d_kv=8, d_ff=32, num_layers=2, num_decoder_layers=2, num_heads=2, vocab_size=20,
+                       feed_forward_proj="gated-gelu", tie_word_embeddings=False, decoder_start_token_id=0,
+                       pad_token_id=0, eos_token_id=1)
+        lm = T5ForConditionalGeneration(cfg).eval()
+        for n_, p in lm.named_parameters():
+            if "layer_norm" not in n_:
+                p.data.normal_(0, 0.5)
+        ids = torch.randint(2, 20, (2, 6))
+        am = torch.ones_like(ids)
+        am[1, 4:] = 0
+        model = types.SimpleNamespace(config=types.SimpleNamespace(text_config=cfg, use_decoder_only_language_model=False),
+                                      language_model=lm)
+        for kw in cases:
+            kw = dict(kw, max_new_tokens=6, do_sample=False)
+            want = lm.generate(inputs_embeds=lm.shared(ids).detach(), attention_mask=am, **kw)
+            got = G.generate(model, ids, am, None, None, _stepper=Stepper(lm), **kw)
+            n = max(got.shape[1], want.shape[1])
+            if not torch.equal(trim(got, n), trim(want, n)):
+                bad.append((seed, kw, got.tolist(), want.tolist()))
+    assert not bad, bad[:3]
