@@ -1,8 +1,8 @@
 """Interleaved video/text tokenisation and collation — the integer input contract of the
 VideoBLIP path (eilev/data/utils.py:35-66 collator, :95-140 and :143-223 tokenisers,
 :69-92 narration clean-up).  Pure host-side integer work, bit-exact with the reference
-(golden vectors of the reference's tests/data/test_utils.py are replayed in
-tests/test_data_utils.py).  The raw-video clip sampler of the reference is out of scope.
+(the reference's tests/data/test_utils.py tables are replayed in tests/test_host_cpu.py,
+seeded outputs of the real reference functions in tests/test_data_utils_golden.py).  The raw-video clip sampler of the reference is out of scope.
 """
 from __future__ import annotations
 
