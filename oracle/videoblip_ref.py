@@ -11,7 +11,8 @@ Parity status: PINNED.  ``tests/golden/make_golden.py`` runs the *real* referenc
 pins 4.33.1, whose equations for this path are the same) on seeded inputs and commits
 inputs + outputs under ``tests/golden/`` (``make_golden_classify.py`` does the same for ``classify``
 — the reference's own method behind a tuple<->Cache shim —, ``make_golden_t5.py`` for the flan-T5
-branch incl. greedy ``generate``, ``make_golden_beams.py`` for HF beam search / repetition penalty);
+branch incl. greedy ``generate``, ``make_golden_beams.py`` for HF beam search / repetition penalty, ``make_golden_v1.py`` for
+the v1 class (eilev/model/v1.py behind a shim restoring the 4.33.1 prepend contract));
 ``tests/test_oracle.py`` checks this restatement against those fixtures (and against the live
 reference when ``/root/reference`` exists).
 The reference's own tests pin shapes only (tests/model/test_model_v2.py:53-83,185-186).
@@ -399,6 +400,78 @@ def greedy_generate_t5(sd, config, input_ids, attention_mask, pixel_values, vide
         if eos_token_id is not None and bool(done.all()):
             break
     return seq
+
+
+# --------------------------------------------------------------------------- v1 (HF 4.33.1 Blip2 forward)
+def videoblip_forward_v1(sd, config, pixel_values, input_ids, attention_mask=None, labels=None,
+                         decoder_input_ids=None):
+    """eilev/model/v1.py:95-119 inherits ``Blip2ForConditionalGeneration.forward`` of the pinned
+    transformers 4.33.1 (HF 4.33.1 blip_2/modeling_blip_2.py ~:1680-1780; not available offline,
+    restated from its published algorithm — transformers 5.5.0 keeps the same loss block,
+    HF:blip_2/modeling_blip_2.py:1802-1822): one video per row, the projected query rows are
+    CONCATENATED in front of the embedded prompt, the mask is ones(Q) ++ attention_mask, and the
+    decoder-only loss is the shifted CE over the last ``labels.size(1)`` logits, which are also the
+    logits returned.  Seq2seq: labels / decoder_input_ids go to T5 untouched."""
+    tcfg = config.text_config
+    b = input_ids.shape[0]
+    assert pixel_values.shape[0] == b
+    feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values)
+    q = config.num_query_tokens
+    lm_inputs = feats.view(b, q, -1)
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    full_mask = torch.cat([torch.ones(b, q, dtype=attention_mask.dtype), attention_mask], dim=1)
+    out = dict(video_features=feats, query_output=qout, image_embeds=image_embeds, pooler_output=pooled)
+    if config.use_decoder_only_language_model:
+        table = sd["language_model.model.decoder.embed_tokens.weight"].float()
+        emb = torch.cat([lm_inputs, table[input_ids]], dim=1)
+        hidden = opt_decoder(sd, tcfg, emb, full_mask)
+        logits = F.linear(hidden, table)
+        out["full_logits"] = logits
+        if labels is not None:
+            logits = logits[:, -labels.size(1):, :]
+            v = logits.shape[-1]
+            out["loss"] = F.cross_entropy(logits[:, :-1].reshape(-1, v), labels[:, 1:].reshape(-1))
+        out["logits"] = logits
+        return out
+    emb = torch.cat([lm_inputs, sd["language_model.shared.weight"].float()[input_ids]], dim=1)
+    enc = t5_encoder(sd, tcfg, emb, full_mask)
+    if decoder_input_ids is None:
+        decoder_input_ids = t5_shift_right(labels, tcfg)
+    dec = t5_decoder(sd, tcfg, decoder_input_ids, enc, full_mask)
+    if getattr(tcfg, "scale_decoder_outputs", tcfg.tie_word_embeddings):
+        dec = dec * tcfg.d_model ** -0.5
+    logits = F.linear(dec, sd["language_model.lm_head.weight"].float())
+    out.update(encoder_last_hidden_state=enc, logits=logits)
+    if labels is not None:
+        out["loss"] = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1), ignore_index=-100)
+    return out
+
+
+@torch.no_grad()
+def greedy_generate_v1(sd, config, pixel_values, input_ids=None, attention_mask=None, max_new_tokens=4):
+    """HF 4.33.1 ``Blip2ForConditionalGeneration.generate`` with a decoder-only LM and greedy search:
+    prompt defaults to [bos] per row; embeddings = cat([video rows, embed(prompt)]); only the new
+    tokens are returned.  No cache (prefix recomputed): small cases only."""
+    tcfg = config.text_config
+    b = pixel_values.shape[0]
+    if input_ids is None:
+        input_ids = torch.full((b, 1), tcfg.bos_token_id, dtype=torch.long)
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    q = config.num_query_tokens
+    feats = video_features(sd, config, pixel_values)[0]
+    table = sd["language_model.model.decoder.embed_tokens.weight"].float()
+    emb = torch.cat([feats.view(b, q, -1), table[input_ids]], dim=1)
+    mask = torch.cat([torch.ones(b, q, dtype=attention_mask.dtype), attention_mask], dim=1)
+    new = []
+    for _ in range(max_new_tokens):
+        hidden = opt_decoder(sd, tcfg, emb, mask)
+        nxt = F.linear(hidden[:, -1], table).argmax(-1)
+        new.append(nxt)
+        emb = torch.cat([emb, table[nxt][:, None]], dim=1)
+        mask = torch.cat([mask, torch.ones(b, 1, dtype=mask.dtype)], dim=1)
+    return torch.stack(new, dim=1)
 
 
 @torch.no_grad()

@@ -458,3 +458,109 @@ def test_seq2seq_decoding_loops_match_huggingface_generate():
             if not torch.equal(trim(got, n), trim(want, n)):
                 bad.append((seed, kw, got.tolist(), want.tolist()))
     assert not bad, bad[:3]
+
+
+# ------------------------------------------------------------------------------------- v1 wrapper
+def _v1_case(name):
+    base = torch.load(GOLDEN / f"{name}.pt", weights_only=False)
+    cfg = Blip2Config(**{k: base["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    return torch.load(GOLDEN / f"v1_{name}.pt", weights_only=False), base["state_dict"], cfg
+
+
+def test_v1_prepend_video_slots_and_compact_left():
+    from eilev_b200.model.v1 import compact_left, prepend_video_slots
+    ids = torch.tensor([[5, 6, 7, 1], [1, 1, 8, 9]])
+    am = torch.tensor([[1, 1, 1, 0], [0, 0, 1, 1]])
+    lab = torch.tensor([[5, 6, 7, -100], [-100, -100, 8, 9]])
+    fi, fa, fv, fl = prepend_video_slots(ids, am, lab, 3, 1, decoder_only=True)
+    assert fi.tolist() == [[1, 1, 1, 5, 6, 7, 1], [1, 1, 1, 1, 1, 8, 9]]
+    assert fa.tolist() == [[1, 1, 1, 1, 1, 1, 0], [1, 1, 1, 0, 0, 1, 1]]
+    assert fv.tolist() == [[1, 1, 1, 0, 0, 0, 0]] * 2
+    # HF 4.33.1 shifts the labels against the LAST L logits: labels[:, 0] is never a target
+    assert fl.tolist() == [[-100, -100, -100, -100, 6, 7, -100], [-100, -100, -100, -100, -100, 8, 9]]
+    _, _, _, same = prepend_video_slots(ids, None, lab, 3, 1, decoder_only=False)
+    assert same is lab  # seq2seq labels are decoder targets
+    ci, ca, cv = compact_left(fi, fa, fv)
+    assert ca.tolist() == [[0, 1, 1, 1, 1, 1, 1], [0, 0, 1, 1, 1, 1, 1]]
+    assert cv.tolist() == [[0, 1, 1, 1, 0, 0, 0], [0, 0, 1, 1, 1, 0, 0]]
+    assert ci.tolist() == [[1, 1, 1, 1, 5, 6, 7], [1, 1, 1, 1, 1, 8, 9]]
+
+
+@pytest.mark.parametrize("name", ["tiny_opt", "small_opt", "small_t5"])
+def test_v1_wrapper_over_an_oracle_backed_v2_forward_matches_the_reference(name, monkeypatch):
+    """The whole v1 wrapper on CPU: v2's ``forward`` (the CUDA engine) is replaced by the fp32
+    oracle, so what is checked is exactly the host logic v1 adds — slot layout, label masking,
+    logits slice, output packing — against the golden of the real eilev.model.v1 class."""
+    from transformers.modeling_outputs import BaseModelOutputWithPooling, CausalLMOutputWithPast
+    from transformers.models.blip_2.modeling_blip_2 import Blip2ForConditionalGenerationModelOutput
+
+    from eilev_b200.model import v1, v2
+    from oracle import videoblip_ref as R
+
+    fx, sd, cfg = _v1_case(name)
+    seen = {}
+
+    def oracle_forward(self, input_ids, attention_mask=None, pixel_values=None, video_input_mask=None,
+                       decoder_input_ids=None, decoder_attention_mask=None, output_attentions=None,
+                       output_hidden_states=None, labels=None, return_dict=None):
+        seen.update(input_ids=input_ids, video_input_mask=video_input_mask, labels=labels)
+        assert return_dict is True
+        if cfg.use_decoder_only_language_model:
+            o = R.videoblip_forward(sd, cfg, input_ids, attention_mask, pixel_values, video_input_mask, labels)
+        else:
+            o = R.videoblip_forward_t5(sd, cfg, input_ids, attention_mask, pixel_values, video_input_mask, labels,
+                                       decoder_input_ids)
+        return Blip2ForConditionalGenerationModelOutput(
+            loss=o.get("loss"), logits=o["logits"],
+            vision_outputs=BaseModelOutputWithPooling(last_hidden_state=o["image_embeds"], pooler_output=o["pooler_output"]),
+            qformer_outputs=BaseModelOutputWithPooling(last_hidden_state=o["query_output"], pooler_output=o["query_output"][:, 0]),
+            language_model_outputs=CausalLMOutputWithPast(loss=o.get("loss"), logits=o["logits"]))
+
+    monkeypatch.setattr(v2.VideoBlipForConditionalGeneration, "forward", oracle_forward)
+    m = v1.VideoBlipForConditionalGeneration(cfg)
+    with torch.no_grad():
+        out = m(**fx["inputs"])
+        tup = m(**fx["inputs"], return_dict=False)
+    nq = cfg.num_query_tokens
+    assert seen["input_ids"].shape[1] == fx["inputs"]["input_ids"].shape[1] + nq
+    assert seen["video_input_mask"][:, :nq].all() and not seen["video_input_mask"][:, nq:].any()
+    assert out.logits.shape == fx["logits"].shape
+    assert torch.allclose(out.logits, fx["logits"], atol=5e-5, rtol=1e-4)
+    assert abs(float(out.loss) - float(fx["loss"])) < 1e-5
+    assert len(tup) == 5 and torch.equal(tup[1], out.logits) and float(tup[0]) == float(out.loss)
+    assert out.language_model_outputs.logits.shape[1] == (
+        fx["logits_no_labels"].shape[1] if cfg.use_decoder_only_language_model else fx["logits"].shape[1])
+    with pytest.raises(ValueError):
+        m(pixel_values=None, input_ids=fx["inputs"]["input_ids"])
+    with pytest.raises(ValueError):
+        m(pixel_values=fx["inputs"]["pixel_values"][:1], input_ids=fx["inputs"]["input_ids"])
+
+
+def test_v1_generate_layout_and_kwargs(monkeypatch):
+    from eilev_b200.model import v1, v2
+
+    fx, sd, cfg = _v1_case("small_opt")
+    calls = []
+
+    def fake_generate(self, input_ids, pixel_values=None, video_input_mask=None, attention_mask=None, **kw):
+        calls.append(dict(ids=input_ids, vm=video_input_mask, am=attention_mask, kw=kw))
+        return torch.zeros(input_ids.shape[0], 1, dtype=torch.long)
+
+    monkeypatch.setattr(v2.VideoBlipForConditionalGeneration, "generate", fake_generate)
+    m = v1.VideoBlipForConditionalGeneration(cfg)
+    g = fx["gen_inputs"]
+    m.generate(**g, num_beams=4, top_p=0.9)
+    c = calls[-1]
+    nq, n_valid = cfg.num_query_tokens, g["attention_mask"].sum(1)
+    assert c["kw"] == dict(num_beams=4, top_p=0.9)
+    assert bool((c["am"][:, 1:] >= c["am"][:, :-1]).all())  # padding only at the left end
+    assert c["am"].sum(1).tolist() == (n_valid + nq).tolist()
+    for b in range(c["ids"].shape[0]):
+        n = int(n_valid[b])
+        assert c["ids"][b, -n:].tolist() == g["input_ids"][b, -n:].tolist()  # text stays last, in order
+        assert c["vm"][b, -n - nq:-n].all() and int(c["vm"][b].sum()) == nq  # video slots right before it
+    m.generate(pixel_values=g["pixel_values"])  # no prompt: [bos] per row (HF 4.33.1 generate)
+    c = calls[-1]
+    assert c["ids"].shape == (g["pixel_values"].shape[0], nq + 1)
+    assert c["ids"][:, -1].tolist() == [cfg.text_config.bos_token_id] * g["pixel_values"].shape[0]
+    assert bool(c["am"].all())

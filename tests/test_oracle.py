@@ -149,3 +149,78 @@ def test_oracle_t5_greedy_generate_matches_reference_golden():
     got = R.greedy_generate_t5(fx["state_dict"], cfg, i["input_ids"], i["attention_mask"], i["pixel_values"],
                                i["video_input_mask"], max_new_tokens=6, eos_token_id=cfg.text_config.eos_token_id)
     assert got.tolist() == fx["generated"].tolist()
+
+
+# ------------------------------------------------------------------------------------- v1
+V1_NAMES = ["tiny_opt", "small_opt", "small_t5"]
+
+
+def load_v1(name):
+    base, cfg = load(name)
+    return torch.load(GOLDEN / f"v1_{name}.pt", weights_only=False), base["state_dict"], cfg
+
+
+@pytest.mark.parametrize("name", V1_NAMES)
+def test_oracle_v1_forward_matches_reference_golden(name):
+    """The concatenation restatement of HF 4.33.1's Blip2 forward vs the real eilev.model.v1 class
+    (tests/golden/make_golden_v1.py)."""
+    fx, sd, cfg = load_v1(name)
+    out = R.videoblip_forward_v1(sd, cfg, **fx["inputs"])
+    assert out["logits"].shape == fx["logits"].shape
+    assert torch.allclose(out["query_output"], fx["query_output"], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(out["logits"], fx["logits"], atol=5e-5, rtol=1e-4)
+    assert abs(float(out["loss"]) - float(fx["loss"])) < 1e-5
+    i = fx["inputs"]
+    extra = {} if cfg.use_decoder_only_language_model else {"decoder_input_ids": torch.zeros(i["input_ids"].shape[0], 1, dtype=torch.long)}
+    nolab = R.videoblip_forward_v1(sd, cfg, i["pixel_values"], i["input_ids"], i["attention_mask"], **extra)
+    assert torch.allclose(nolab["logits"], fx["logits_no_labels"], atol=5e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", V1_NAMES)
+def test_oracle_v1_gradients_match_reference_golden(name):
+    fx, sd, cfg = load_v1(name)
+    sd = {k: v.clone() for k, v in sd.items()}
+    trainable = [k for k in sd if k in fx["grads"]]
+    assert len(trainable) == len(fx["grads"]) > 0
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    R.videoblip_forward_v1(sd, cfg, **fx["inputs"])["loss"].backward()
+    for k in trainable:
+        g, ref = sd[k].grad, fx["grads"][k]
+        assert torch.allclose(g, ref, atol=1e-6 + 1e-4 * float(ref.abs().max()), rtol=1e-3), k
+
+
+@pytest.mark.parametrize("name", ["tiny_opt", "small_opt"])
+def test_oracle_v1_greedy_generate_matches_reference_golden(name):
+    fx, sd, cfg = load_v1(name)
+    gen = R.greedy_generate_v1(sd, cfg, **fx["gen_inputs"], max_new_tokens=5)
+    assert gen.tolist() == fx["generated"].tolist()
+    gen = R.greedy_generate_v1(sd, cfg, fx["gen_inputs"]["pixel_values"], max_new_tokens=5)
+    assert gen.tolist() == fx["generated_no_prompt"].tolist()
+
+
+@pytest.mark.parametrize("name", ["tiny_opt", "small_opt"])
+def test_v1_is_v2_with_prepended_video_slots(name):
+    """The identity the CUDA v1 path rests on (eilev_b200/model/v1.py): the v2 forward on the
+    ``[video slots | text]`` layout with labels[:, 0] masked reproduces v1's loss and logits, and the
+    left-compacted layout ``[pad | video | text]`` reproduces v1's next-token logits."""
+    from eilev_b200.model.v1 import compact_left, prepend_video_slots
+
+    fx, sd, cfg = load_v1(name)
+    i = fx["inputs"]
+    ids, am, vm, lab = prepend_video_slots(i["input_ids"], i["attention_mask"], i["labels"],
+                                           cfg.num_query_tokens, cfg.text_config.pad_token_id, True)
+    out = R.videoblip_forward(sd, cfg, ids, am, i["pixel_values"], vm, lab)
+    L = i["labels"].shape[1]
+    assert torch.allclose(out["logits"][:, -L:], fx["logits"], atol=5e-5, rtol=1e-4)
+    assert abs(float(out["loss"]) - float(fx["loss"])) < 1e-5
+    g = fx["gen_inputs"]
+    ids, am, vm, _ = prepend_video_slots(g["input_ids"], g["attention_mask"], None, cfg.num_query_tokens,
+                                         cfg.text_config.pad_token_id, True)
+    holes = R.videoblip_forward(sd, cfg, ids, am, g["pixel_values"], vm)["logits"][:, -1]
+    cids, cam, cvm = compact_left(ids, am, vm)
+    assert bool((cam[:, 1:] >= cam[:, :-1]).all())  # left padded: zeros then ones
+    assert int(cvm.sum()) == int(vm.sum()) and bool((cam[cvm.bool()] == 1).all())
+    compact = R.videoblip_forward(sd, cfg, cids, cam, g["pixel_values"], cvm)["logits"][:, -1]
+    assert torch.allclose(holes, compact, atol=5e-5, rtol=1e-4)
+    assert compact.argmax(-1).tolist() == fx["generated"][:, 0].tolist()
