@@ -14,7 +14,8 @@ restores the 4.33.1 contract:
     them for a decoder-only LM fed with embeddings).
 The loss block (last ``labels.size(1)`` logits, shift, mean CE) is the same code in both versions.
 
-Writes tests/golden/v1_{tiny_opt,small_opt,small_t5}.pt: inputs + reference outputs only — the
+Writes tests/golden/v1_{tiny_opt,small_opt,small_t5}.pt: inputs + reference outputs (incl. the fp32
+top-2 logit margin of every greedy step, so a test can tell a numerical tie from an error) only — the
 weights are the ``state_dict`` of the v2 fixture of the same name (v1 and v2 share all keys).
 """
 import sys
@@ -126,12 +127,20 @@ def main():
                           return_dict=True)
             gids, gam = left_pad(ids, am, tcfg.pad_token_id) if decoder_only else (ids, am)
             s_gids, s_gam = shim(gids, gam)
-            kw = dict(max_new_tokens=5, min_new_tokens=5, do_sample=False, num_beams=1)
-            gen = model.generate(pixel_values=pixel_values, input_ids=s_gids, attention_mask=s_gam, **kw)
-            gen_noprompt = None
+            kw = dict(max_new_tokens=5, min_new_tokens=5, do_sample=False, num_beams=1, output_scores=True,
+                      return_dict_in_generate=True)
+
+            def margins(scores):  # (steps, rows) fp32 top-1 minus top-2 logit of every greedy step
+                top = torch.stack([s.float().topk(2, dim=-1).values for s in scores])
+                return top[..., 0] - top[..., 1]
+
+            res = model.generate(pixel_values=pixel_values, input_ids=s_gids, attention_mask=s_gam, **kw)
+            gen, gen_margins = res.sequences, margins(res.scores)
+            gen_noprompt = noprompt_margins = None
             if decoder_only:
                 gen = gen[:, s_gids.shape[1]:]
-                full = model.generate(pixel_values=pixel_values, **kw)
+                res = model.generate(pixel_values=pixel_values, **kw)
+                full, noprompt_margins = res.sequences, margins(res.scores)
                 gen_noprompt = full[:, nq + 1:]  # 5.5.0 returns [placeholders, bos] + new
                 assert gen.shape == (batch, 5) and gen_noprompt.shape == (batch, 5), (gen.shape, full.shape)
         fixture = dict(
@@ -141,11 +150,13 @@ def main():
             loss=out.loss.detach(), logits=out.logits.detach(), logits_no_labels=nolab.logits.detach(),
             query_output=out.qformer_outputs.last_hidden_state.detach(),
             grads=grads, generated=gen, generated_no_prompt=gen_noprompt,
+            generated_margins=gen_margins, generated_no_prompt_margins=noprompt_margins,
         )
         path = HERE / f"v1_{name}.pt"
         torch.save(fixture, path)
         print(name, "loss", float(out.loss), "logits", tuple(out.logits.shape), "no-labels", tuple(nolab.logits.shape),
               "grads", len(grads), "gen", gen.tolist(), "no prompt", None if gen_noprompt is None else gen_noprompt.tolist(),
+              "min margin", float(gen_margins.min()), None if noprompt_margins is None else float(noprompt_margins.min()),
               "bytes", path.stat().st_size)
 
 
