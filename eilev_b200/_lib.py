@@ -67,6 +67,7 @@ SIGNATURES: dict[str, list] = {
     "vb_attention_uses_tcgen05": [C.POINTER(AttnArgs)],
     "vb_attention_bwd": [C.POINTER(AttnBwdArgs), vp],
     "vb_patch_gather": [vp, i32, vp, i64, i64, i64, i64, i64, i64, i64, vp],
+    "vb_patch_gather_u8": [vp, vp, i64, i64, i64, i64, i64, i64, i64, C.c_double, C.POINTER(f32), C.POINTER(f32), vp],
     "vb_cls_rows": [vp, vp, vp, i64, i64, i64, vp],
     "vb_embed_splice": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
     "vb_splice_bwd": [vp, vp, vp, i64, i64, i64, vp],
@@ -131,7 +132,7 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "vb_last_error" else C.c_int
-    if handle.vb_abi_version() != 3:
+    if handle.vb_abi_version() != 4:
         raise VbError("ABI version mismatch between eilev_b200/_lib.py and the built library")
     _lib = handle
     return handle

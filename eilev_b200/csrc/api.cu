@@ -100,6 +100,18 @@ int vb_patch_gather(const void* pixels, int32_t px_dtype, void* out, int64_t nv,
            vb::patch_gather_launch(pixels, px_dtype, out, nv, c, t, h, w, patch, kpad, st(stream)));
 }
 
+int vb_patch_gather_u8(const void* pixels_u8, void* out, int64_t nv, int64_t c, int64_t t, int64_t h,
+                       int64_t w, int64_t patch, int64_t kpad, double rescale, const float* mean,
+                       const float* stdv, void* stream) {
+  if (pixels_u8 == nullptr || out == nullptr || mean == nullptr || stdv == nullptr || patch <= 0 ||
+      kpad < c * patch * patch || c < 1 || c > 4)
+    return fail_msg("vb_patch_gather_u8", "bad arguments");
+  for (int64_t i = 0; i < c; ++i)
+    if (!(stdv[i] > 0.0f)) return fail_msg("vb_patch_gather_u8", "std must be positive");
+  VB_CHECK("vb_patch_gather_u8", vb::patch_gather_u8_launch(pixels_u8, out, nv, c, t, h, w, patch, kpad,
+                                                           rescale, mean, stdv, st(stream)));
+}
+
 int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
                 int64_t dim, void* stream) {
   VB_CHECK("vb_cls_rows", vb::cls_rows_launch(cls, pos, hidden, frames, tokens, dim, st(stream)));

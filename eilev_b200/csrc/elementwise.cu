@@ -61,6 +61,60 @@ cudaError_t patch_gather_launch(const void* px, int dtype, void* out, long long 
   return cudaGetLastError();
 }
 
+// uint8 frames: the BlipImageProcessor arithmetic (rescale by 1/255 in fp64, then subtract the
+// channel mean and divide by the channel std in fp32) fused into the same gather, so decoded frames go from
+// one byte per sample in HBM straight to the bf16 patch matrix.  A warp covers 32 consecutive
+// columns of one patch row group: its byte loads fall into one or two 32-byte sectors.
+struct FrameNorm {
+  float mean[4];
+  float stdv[4];
+  double rescale;
+};
+
+__global__ void __launch_bounds__(256)
+patch_gather_u8_kernel(const unsigned char* __restrict__ px, __nv_bfloat16* __restrict__ out,
+                       long long C, long long T_, long long H, long long W, long long P,
+                       long long gh, long long gw, long long kpad, long long total, FrameNorm nrm) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long col = idx % kpad;
+  const long long row = idx / kpad;
+  float v = 0.0f;
+  if (col < C * P * P) {
+    const long long pxx = col % P, pyy = (col / P) % P, c = col / (P * P);
+    const long long gx = row % gw, gy = (row / gw) % gh, f = row / (gw * gh);
+    const long long t = f % T_, vid = f / T_;
+    const long long y = gy * P + pyy, x = gx * P + pxx;
+    const unsigned char raw = px[(((vid * C + c) * T_ + t) * H + y) * W + x];
+    // transformers 4.33.1 (the reference's pin): rescale in float64 (uint8 array * python float),
+    // cast to float32, then (x - mean) / std in float32
+    const float r = static_cast<float>(static_cast<double>(raw) * nrm.rescale);
+    v = __fdiv_rn(__fsub_rn(r, nrm.mean[c]), nrm.stdv[c]);
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+cudaError_t patch_gather_u8_launch(const void* px, void* out, long long nv, long long c, long long t,
+                                   long long h, long long w, long long patch, long long kpad,
+                                   double rescale, const float* mean, const float* stdv,
+                                   cudaStream_t s) {
+  if (c < 1 || c > 4) return cudaErrorInvalidValue;
+  const long long gh = h / patch, gw = w / patch;
+  const long long total = nv * t * gh * gw * kpad;
+  if (total <= 0) return cudaSuccess;
+  FrameNorm nrm;
+  for (int i = 0; i < 4; ++i) {
+    nrm.mean[i] = i < c ? mean[i] : 0.0f;
+    nrm.stdv[i] = i < c ? stdv[i] : 1.0f;
+  }
+  nrm.rescale = rescale;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  patch_gather_u8_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned char*>(px),
+                                              reinterpret_cast<__nv_bfloat16*>(out), c, t, h, w,
+                                              patch, gh, gw, kpad, total, nrm);
+  return cudaGetLastError();
+}
+
 __global__ void cls_rows_kernel(const __nv_bfloat16* cls, const __nv_bfloat16* pos,
                                 __nv_bfloat16* hidden, long long frames, long long tokens,
                                 long long dim) {

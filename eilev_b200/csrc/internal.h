@@ -24,6 +24,10 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
 cudaError_t patch_gather_launch(const void* px, int dtype, void* out, long long nv, long long c,
                                 long long t, long long h, long long w, long long patch,
                                 long long kpad, cudaStream_t s);
+cudaError_t patch_gather_u8_launch(const void* px, void* out, long long nv, long long c, long long t,
+                                   long long h, long long w, long long patch, long long kpad,
+                                   double rescale, const float* mean, const float* stdv,
+                                   cudaStream_t s);
 cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long long frames,
                             long long tokens, long long dim, cudaStream_t s);
 cudaError_t embed_splice_launch(const long long* ids, const long long* attn, const long long* vmask,

@@ -78,7 +78,12 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
     eps = cfg.layer_norm_eps
     frames = nv * t
     pixel_values = pixel_values.contiguous()
-    if pixel_values.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+    # decoded uint8 frames: the image processor's rescale + normalize run inside the patch gather
+    # (eilev/model/utils.py:5-26 -> BlipImageProcessor); float inputs are already normalised
+    frame_norm = None
+    if pixel_values.dtype == torch.uint8:
+        frame_norm = (float(model.rescale_factor), tuple(model.image_mean), tuple(model.image_std))
+    elif pixel_values.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         pixel_values = pixel_values.float()
 
     last = torch.empty((frames, tokens, dim), dtype=torch.bfloat16, device=pixel_values.device)
@@ -92,7 +97,10 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
         v1 = min(nv, v0 + clips_per)
         f0, f1 = v0 * t, v1 * t
         nf = f1 - f0
-        patches = ops.patch_gather(pixel_values[v0:v1], p, w["kpad"])
+        if frame_norm is not None:
+            patches = ops.patch_gather_u8(pixel_values[v0:v1], p, w["kpad"], *frame_norm)
+        else:
+            patches = ops.patch_gather(pixel_values[v0:v1], p, w["kpad"])
         hidden = torch.empty((nf, tokens, dim), dtype=torch.bfloat16, device=pixel_values.device)
         hid2 = hidden.view(nf * tokens, dim)
         ops.cls_rows(w["cls"], w["pos"], hidden)

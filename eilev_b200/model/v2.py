@@ -225,6 +225,21 @@ class VideoBlipVisionModel(PreTrainedModel):
     base_model_prefix = "blip"
     _no_split_modules = ["_VisionLayer"]
 
+    # Normalisation applied on the device when ``pixel_values`` are decoded uint8 frames (SURVEY §8f
+    # rank 3): BlipImageProcessor's defaults — rescale 1/255, OPENAI_CLIP mean / std
+    # (HF:models/blip/image_processing_blip.py; eilev/model/utils.py:5-26).  Float inputs are taken
+    # as already processed, exactly as the reference takes them.
+    rescale_factor: float = 1 / 255
+    image_mean: tuple = (0.48145466, 0.4578275, 0.40821073)
+    image_std: tuple = (0.26862954, 0.26130258, 0.27577711)
+
+    def set_frame_normalization(self, image_processor) -> None:
+        """Adopt ``rescale_factor`` / ``image_mean`` / ``image_std`` of a HF image processor
+        (``processor.image_processor``) for the uint8 frame path."""
+        self.rescale_factor = float(image_processor.rescale_factor)
+        self.image_mean = tuple(float(v) for v in image_processor.image_mean)
+        self.image_std = tuple(float(v) for v in image_processor.image_std)
+
     def __init__(self, config: Blip2VisionConfig) -> None:
         super().__init__(config)
         self.embeddings = _VisionEmbeddings(config)

@@ -251,6 +251,23 @@ def patch_gather(pixels: torch.Tensor, patch: int, kpad: int) -> torch.Tensor:
     return out
 
 
+def patch_gather_u8(frames: torch.Tensor, patch: int, kpad: int, rescale: float, mean, std) -> torch.Tensor:
+    """uint8 (NV, C, T, H, W) -> (NV*T*gh*gw, kpad) bf16 patch matrix of the normalised frames:
+    (u8 * rescale - mean[c]) / std[c] in fp32, fused into the gather."""
+    _need(frames, torch.uint8, "patch_gather_u8.frames")
+    assert frames.dim() == 5 and frames.is_contiguous()
+    nv, c, t, h, w = frames.shape
+    if len(mean) != c or len(std) != c or c > 4:
+        raise ValueError(f"patch_gather_u8: {c} channels need {c} (<= 4) mean / std values, got {len(mean)} / {len(std)}")
+    gh, gw = h // patch, w // patch
+    out = torch.empty((nv * t * gh * gw, kpad), dtype=torch.bfloat16, device=frames.device)
+    arr = C.c_float * c
+    check(_lib.lib().vb_patch_gather_u8(frames.data_ptr(), out.data_ptr(), nv, c, t, h, w, patch, kpad,
+                                        float(rescale), arr(*[float(m) for m in mean]),
+                                        arr(*[float(v) for v in std]), _stream()), "vb_patch_gather_u8")
+    return out
+
+
 def cls_rows(cls: torch.Tensor, pos: torch.Tensor, hidden: torch.Tensor) -> None:
     frames, tokens, dim = hidden.shape
     check(_lib.lib().vb_cls_rows(cls.data_ptr(), pos.data_ptr(), hidden.data_ptr(), frames, tokens,

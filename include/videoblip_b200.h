@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 3
+#define VB_ABI_VERSION 4
 
 /* dtype tags */
 #define VB_BF16 0
@@ -176,6 +176,15 @@ int vb_attention_bwd(const vb_attn_bwd_args* args, void* stream);
  * ---------------------------------------------------------------------- */
 int vb_patch_gather(const void* pixels, int32_t px_dtype, void* out, int64_t nv, int64_t c,
                     int64_t t, int64_t h, int64_t w, int64_t patch, int64_t kpad, void* stream);
+/* The same gather straight from decoded uint8 frames (NV, C, T, H, W), C <= 4, with the
+ * image-processor arithmetic fused:  v = (f32(f64(u8) * rescale) - mean[c]) / stdv[c]  (the
+ * float64 rescale then float32 normalize of the reference's pinned transformers 4.33.1)
+ * (BlipImageProcessor rescale + normalize, HF:models/blip/image_processing_blip.py, behind
+ * eilev/model/utils.py:5-26 `process`; the /255 + Normalize of scripts/general/train_v2.py:143-167).
+ * mean / stdv are HOST arrays of c floats, read during the call.  SURVEY §8(f) rank 3. */
+int vb_patch_gather_u8(const void* pixels_u8, void* out, int64_t nv, int64_t c, int64_t t, int64_t h,
+                       int64_t w, int64_t patch, int64_t kpad, double rescale, const float* mean,
+                       const float* stdv, void* stream);
 /* hidden[f, 0, :] = cls + pos[0]  for every frame f (HF:...:249-254). bf16. */
 int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
                 int64_t dim, void* stream);

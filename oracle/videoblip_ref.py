@@ -402,6 +402,27 @@ def greedy_generate_t5(sd, config, input_ids, attention_mask, pixel_values, vide
     return seq
 
 
+# --------------------------------------------------------------------------- frame normalisation
+OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def normalize_frames(frames_u8, rescale=1 / 255, mean=OPENAI_CLIP_MEAN, std=OPENAI_CLIP_STD):
+    """eilev/model/utils.py:5-26 ``process`` -> ``Blip2Processor`` -> ``BlipImageProcessor.preprocess``
+    of the pinned transformers 4.33.1 on frames that already have the target size: ``rescale``
+    (HF:image_transforms.py ``rescale``: uint8 array * python float in float64, cast to float32)
+    then ``normalize`` (HF:image_transforms.py ``normalize``: (image - mean) / std in float32).
+    frames_u8: (..., C, H, W) with C = len(mean) at dim -3, e.g. (N, C, T, H, W) after swapping —
+    here the channel axis is given by ``mean``'s broadcast over dim 1 of (N, C, T, H, W).
+    Pinned bit-exactly against those two HF functions in tests/test_oracle.py."""
+    shape = [1] * frames_u8.dim()
+    shape[1] = len(mean)
+    m = torch.tensor(mean, dtype=torch.float32).view(shape)
+    sd_ = torch.tensor(std, dtype=torch.float32).view(shape)
+    x = (frames_u8.to(torch.float64) * rescale).to(torch.float32)
+    return (x - m) / sd_
+
+
 # --------------------------------------------------------------------------- v1 (HF 4.33.1 Blip2 forward)
 def videoblip_forward_v1(sd, config, pixel_values, input_ids, attention_mask=None, labels=None,
                          decoder_input_ids=None):

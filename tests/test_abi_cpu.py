@@ -91,3 +91,19 @@ def test_product_does_not_import_the_oracle():
     for path in (ROOT / "eilev_b200").rglob("*.py"):
         text = path.read_text()
         assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_patch_gather_u8_validates_arguments_before_touching_the_device(lib):
+    """Argument marshalling of the uint8 frame entry point (double rescale, host float arrays):
+    a non-positive std / null pointers / too many channels are refused with a message and no launch."""
+    three = (C.c_float * 3)
+    buf = (C.c_uint8 * 64)()
+    out = (C.c_uint16 * 64)()
+    ok_mean, ok_std = three(0.5, 0.5, 0.5), three(0.25, 0.25, 0.25)
+    args = (1, 3, 1, 4, 4, 2, 12, 1 / 255)
+    assert lib.vb_patch_gather_u8(C.addressof(buf), C.addressof(out), *args, ok_mean, three(0.25, 0.0, 0.25), None) != 0
+    assert b"std must be positive" in lib.vb_last_error()
+    assert lib.vb_patch_gather_u8(None, C.addressof(out), *args, ok_mean, ok_std, None) != 0
+    assert b"bad arguments" in lib.vb_last_error()
+    assert lib.vb_patch_gather_u8(C.addressof(buf), C.addressof(out), 1, 5, 1, 4, 4, 2, 20, 1 / 255, ok_mean, ok_std, None) != 0
+    assert lib.vb_patch_gather_u8(C.addressof(buf), C.addressof(out), 1, 3, 1, 4, 4, 2, 11, 1 / 255, ok_mean, ok_std, None) != 0  # kpad < C*P*P

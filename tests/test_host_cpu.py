@@ -564,3 +564,46 @@ def test_v1_generate_layout_and_kwargs(monkeypatch):
     assert c["ids"].shape == (g["pixel_values"].shape[0], nq + 1)
     assert c["ids"][:, -1].tolist() == [cfg.text_config.bos_token_id] * g["pixel_values"].shape[0]
     assert bool(c["am"].all())
+
+
+# ------------------------------------------------------------------------------------- uint8 frame path
+def _image_only_processor(size):
+    """Blip2Processor stand-in (no tokenizer files offline): the real BlipImageProcessor behind the
+    processor call signature ``process`` uses."""
+    from transformers import BatchEncoding, BlipImageProcessor
+    ip = BlipImageProcessor(size={"height": size, "width": size})
+
+    def call(images=None, text=None, return_tensors=None, **kw):
+        return BatchEncoding(dict(ip(images=images, return_tensors=return_tensors, **kw)))
+    call.image_processor = ip
+    return call
+
+
+@pytest.mark.parametrize("hw", [(56, 56), (40, 72)])  # already at the target size / needs the bicubic resize
+def test_process_normalize_on_device_keeps_uint8_and_matches_the_stock_path(hw):
+    """process(normalize_on_device=True) hands over the RESIZED uint8 frames; normalising them with the
+    oracle restatement of BlipImageProcessor's rescale + normalize reproduces the stock float path."""
+    from eilev_b200.model.utils import process
+    from oracle import videoblip_ref as R
+    proc = _image_only_processor(56)
+    g = torch.Generator().manual_seed(1)
+    video = torch.randint(0, 256, (2, 3, 4, *hw), dtype=torch.uint8, generator=g)
+    stock = process(proc, video=video)["pixel_values"]
+    u8 = process(proc, video=video, normalize_on_device=True)["pixel_values"]
+    assert u8.dtype == torch.uint8 and u8.shape == stock.shape == (2, 3, 4, 56, 56)
+    if hw == (56, 56):
+        assert torch.equal(u8, video)
+    assert float((R.normalize_frames(u8) - stock).abs().max()) < 1e-6
+    with pytest.raises(ValueError):
+        process(proc, video=video.float(), normalize_on_device=True)
+
+
+def test_vision_model_frame_normalization_defaults_and_override():
+    from transformers import BlipImageProcessor
+    from eilev_b200.model.v2 import VideoBlipVisionModel
+    from oracle import videoblip_ref as R
+    m = VideoBlipVisionModel(small_cfg().vision_config)
+    assert m.image_mean == R.OPENAI_CLIP_MEAN and m.image_std == R.OPENAI_CLIP_STD and m.rescale_factor == 1 / 255
+    m.set_frame_normalization(BlipImageProcessor(image_mean=[0.5, 0.5, 0.5], image_std=[0.25, 0.5, 1.0]))
+    assert m.image_mean == (0.5, 0.5, 0.5) and m.image_std == (0.25, 0.5, 1.0)
+    assert VideoBlipVisionModel.image_mean == R.OPENAI_CLIP_MEAN  # class default untouched

@@ -224,3 +224,27 @@ def test_v1_is_v2_with_prepended_video_slots(name):
     compact = R.videoblip_forward(sd, cfg, cids, cam, g["pixel_values"], cvm)["logits"][:, -1]
     assert torch.allclose(holes, compact, atol=5e-5, rtol=1e-4)
     assert compact.argmax(-1).tolist() == fx["generated"][:, 0].tolist()
+
+
+# ------------------------------------------------------------------------------------- frames
+def test_oracle_normalize_frames_is_the_hf_rescale_and_normalize():
+    """Bit-exact against the numpy ``rescale`` / ``normalize`` the reference's pinned BlipImageProcessor
+    calls (transformers/image_transforms.py, unchanged in the installed version), and within 2 fp32
+    ulp (identical after bf16 rounding) of the installed torchvision-backed BlipImageProcessor."""
+    import numpy as np
+    from transformers import BlipImageProcessor
+    from transformers import image_transforms as IT
+
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (2, 3, 4, 32, 48), dtype=torch.uint8, generator=g)  # (N, C, T, H, W)
+    got = R.normalize_frames(frames)
+    flat = frames.permute(0, 2, 1, 3, 4).reshape(-1, 3, 32, 48)
+    want = np.stack([IT.normalize(IT.rescale(f.numpy(), 1 / 255), R.OPENAI_CLIP_MEAN, R.OPENAI_CLIP_STD,
+                                  data_format="channels_first", input_data_format="channels_first") for f in flat])
+    want = torch.from_numpy(want).view(2, 4, 3, 32, 48).permute(0, 2, 1, 3, 4)
+    assert want.dtype == torch.float32 and torch.equal(got, want)
+    ip = BlipImageProcessor(size={"height": 32, "width": 48})
+    assert tuple(ip.image_mean) == R.OPENAI_CLIP_MEAN and tuple(ip.image_std) == R.OPENAI_CLIP_STD
+    live = ip(images=flat, return_tensors="pt").pixel_values.view(2, 4, 3, 32, 48).permute(0, 2, 1, 3, 4)
+    assert float((got - live).abs().max()) < 1e-6
+    assert float((got.bfloat16() == live.bfloat16()).float().mean()) > 0.9999
