@@ -412,9 +412,8 @@ def normalize_frames(frames_u8, rescale=1 / 255, mean=OPENAI_CLIP_MEAN, std=OPEN
     of the pinned transformers 4.33.1 on frames that already have the target size: ``rescale``
     (HF:image_transforms.py ``rescale``: uint8 array * python float in float64, cast to float32)
     then ``normalize`` (HF:image_transforms.py ``normalize``: (image - mean) / std in float32).
-    frames_u8: (..., C, H, W) with C = len(mean) at dim -3, e.g. (N, C, T, H, W) after swapping —
-    here the channel axis is given by ``mean``'s broadcast over dim 1 of (N, C, T, H, W).
-    Pinned bit-exactly against those two HF functions in tests/test_oracle.py."""
+    frames_u8: uint8 with the channel axis at dim 1, e.g. (N, C, T, H, W) or (N*T, C, H, W), and
+    C = len(mean).  Pinned bit-exactly against those two HF functions in tests/test_oracle.py."""
     shape = [1] * frames_u8.dim()
     shape[1] = len(mean)
     m = torch.tensor(mean, dtype=torch.float32).view(shape)
