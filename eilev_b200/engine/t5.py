@@ -29,9 +29,11 @@ T = ops.transpose
 
 
 def _check_cfg(cfg) -> None:
-    if not (cfg.is_gated_act and cfg.dense_act_fn == "gelu_new"):
+    gated_gelu = cfg.is_gated_act and cfg.dense_act_fn == "gelu_new"
+    plain_relu = (not cfg.is_gated_act) and cfg.dense_act_fn == "relu"
+    if not (gated_gelu or plain_relu):
         raise NotImplementedError(
-            f"T5 feed_forward_proj {cfg.feed_forward_proj!r}: only gated-gelu (flan-T5) is built")
+            f"T5 feed_forward_proj {cfg.feed_forward_proj!r}: only gated-gelu (flan-T5) and relu (T5 v1.0) are built")
     if cfg.num_heads * cfg.d_kv % 8 != 0:
         raise NotImplementedError("T5 inner dim must be a multiple of 8")
 
@@ -47,8 +49,9 @@ def pack_t5(lm, cache: PackCache, need_backward: bool):
 
     def ff(layer_ff):
         d = layer_ff.DenseReluDense
-        return dict(ln=f32(layer_ff.layer_norm.weight), wi_w=cat_bf16([d.wi_0.weight, d.wi_1.weight]),
-                    wo_w=bf16(d.wo.weight))
+        gated = bool(lm.config.is_gated_act)
+        wi = cat_bf16([d.wi_0.weight, d.wi_1.weight]) if gated else bf16(d.wi.weight)
+        return dict(ln=f32(layer_ff.layer_norm.weight), wi_w=wi, wo_w=bf16(d.wo.weight), gated=gated)
 
     def att(a):
         return dict(qkv_w=cat_bf16([a.q.weight, a.k.weight, a.v.weight]), o_w=bf16(a.o.weight))
@@ -127,13 +130,18 @@ def shift_right(labels: torch.Tensor, cfg) -> torch.Tensor:
 
 def _ff_fwd(x, lw, eps):
     y, r = ops.rmsnorm(x, lw["ln"], eps, save_stats=True)
-    h01 = ops.gemm(y, lw["wi_w"])
-    out = ops.gemm(ops.gated_gelu(h01), lw["wo_w"], residual=x)
+    if lw["gated"]:  # T5DenseGatedActDense: gelu_new(wi_0 y) * (wi_1 y)
+        h01 = ops.gemm(y, lw["wi_w"])
+        act = ops.gated_gelu(h01)
+    else:  # T5DenseActDense: relu(wi y) in the GEMM epilogue; the output doubles as the backward mask
+        h01 = act = ops.gemm(y, lw["wi_w"], epilogue=ops.EPI_RELU)
+    out = ops.gemm(act, lw["wo_w"], residual=x)
     return out, dict(x=x, r=r, h01=h01)
 
 
 def _ff_bwd(dx, lw, s):
-    d_h01 = ops.gated_gelu_bwd(ops.gemm(dx, lw["wo_wt"]), s["h01"])
+    d_act = ops.gemm(dx, lw["wo_wt"])
+    d_h01 = ops.gated_gelu_bwd(d_act, s["h01"]) if lw["gated"] else ops.act_bwd(d_act, s["h01"], ops.EPI_RELU)
     return ops.rmsnorm_bwd(ops.gemm(d_h01, lw["wi_wt"]), s["x"], lw["ln"], s["r"], dx_add=dx)
 
 
@@ -334,8 +342,11 @@ def t5_decode_step(lm, cache: PackCache, enc: dict, st: dict, tokens: torch.Tens
             co = ops.attention(cq.view(b, 1, inner), ck, cv, heads, 1.0, key_mask=key_mask).view(b, inner)
         x2 = ops.gemv(co, lw["co_w"], residual=x1)
         ff = lw["ff"]
-        h01 = ops.gemv(x2, ff["wi_w"], ln=(ff["ln"], None, eps))
-        x = ops.gemv(ops.gated_gelu(h01), ff["wo_w"], residual=x2)
+        if ff["gated"]:
+            act = ops.gated_gelu(ops.gemv(x2, ff["wi_w"], ln=(ff["ln"], None, eps)))
+        else:
+            act = ops.gemv(x2, ff["wi_w"], epilogue=ops.EPI_RELU, ln=(ff["ln"], None, eps))
+        x = ops.gemv(act, ff["wo_w"], residual=x2)
     alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
     return ops.gemv(x, w["head"], alpha=alpha, out_dtype=torch.float32, ln=(w["dec_ln"], None, eps))
 

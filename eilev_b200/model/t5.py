@@ -33,10 +33,16 @@ class _T5Attention(nn.Module):
 
 
 class _T5Dense(nn.Module):
+    """T5DenseGatedActDense (wi_0, wi_1, wo: flan-T5 / T5 v1.1) or T5DenseActDense (wi, wo: the
+    original T5, which is what ``T5Config()`` defaults to and the reference's tests build)."""
+
     def __init__(self, cfg: T5Config) -> None:
         super().__init__()
-        self.wi_0 = nn.Linear(cfg.d_model, cfg.d_ff, bias=False)
-        self.wi_1 = nn.Linear(cfg.d_model, cfg.d_ff, bias=False)
+        if cfg.is_gated_act:
+            self.wi_0 = nn.Linear(cfg.d_model, cfg.d_ff, bias=False)
+            self.wi_1 = nn.Linear(cfg.d_model, cfg.d_ff, bias=False)
+        else:
+            self.wi = nn.Linear(cfg.d_model, cfg.d_ff, bias=False)
         self.wo = nn.Linear(cfg.d_ff, cfg.d_model, bias=False)
 
 
@@ -94,6 +100,12 @@ class T5ForConditionalGeneration(PreTrainedModel):
         self.encoder = _T5Stack(cfg, False, cfg.num_layers)
         self.decoder = _T5Stack(cfg, True, cfg.num_decoder_layers)
         self.lm_head = nn.Linear(cfg.d_model, cfg.vocab_size, bias=False)
+        # T5 v1.0 ties the head to the embedding (and scales the decoder output by d_model**-0.5);
+        # flan-T5 / v1.1 configs carry tie_word_embeddings=False and keep their own head.  The T5
+        # config's own decision is read through scale_decoder_outputs: transformers 5.x lets
+        # Blip2Config overwrite text_config.tie_word_embeddings, 4.33.1 (the reference's pin) does not.
+        if cfg.tie_word_embeddings and E_t5.scale_decoder_outputs(cfg):
+            self._tied_weights_keys = {"lm_head.weight": "shared.weight", **type(self)._tied_weights_keys}
         self._pack = PackCache()
         self.post_init()
 

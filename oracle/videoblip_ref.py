@@ -371,7 +371,7 @@ def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_value
 
 @torch.no_grad()
 def greedy_generate_t5(sd, config, input_ids, attention_mask, pixel_values, video_input_mask, max_new_tokens,
-                       eos_token_id=None):
+                       eos_token_id=None, return_margins=False):
     """v2.py:254-324 with the seq2seq LM and greedy search: encoder once, decoder re-run on the
     growing prefix (no cache; small cases only).  Returns [decoder_start] + new tokens, rows that
     hit eos are padded afterwards (HF:generation/utils.py greedy loop)."""
@@ -390,16 +390,20 @@ def greedy_generate_t5(sd, config, input_ids, attention_mask, pixel_values, vide
     seq = torch.full((b, 1), tcfg.decoder_start_token_id, dtype=torch.long)
     done = torch.zeros(b, dtype=torch.bool)
     scale = tcfg.d_model ** -0.5 if getattr(tcfg, "scale_decoder_outputs", tcfg.tie_word_embeddings) else 1.0
+    margins = []  # fp32 top-1 minus top-2 logit per step: tells a bf16 tie from an error in the tests
     for _ in range(max_new_tokens):
         dec = t5_decoder(sd, tcfg, seq, enc, attention_mask)
-        nxt = F.linear(dec[:, -1] * scale, sd["language_model.lm_head.weight"].float()).argmax(-1)
+        step_logits = F.linear(dec[:, -1] * scale, sd["language_model.lm_head.weight"].float())
+        top2 = step_logits.topk(2, dim=-1).values
+        margins.append(top2[:, 0] - top2[:, 1])
+        nxt = step_logits.argmax(-1)
         if eos_token_id is not None:
             nxt = torch.where(done, torch.full_like(nxt, tcfg.pad_token_id), nxt)
             done = done | (nxt == eos_token_id)
         seq = torch.cat([seq, nxt[:, None]], dim=1)
         if eos_token_id is not None and bool(done.all()):
             break
-    return seq
+    return (seq, torch.stack(margins)) if return_margins else seq
 
 
 # --------------------------------------------------------------------------- frame normalisation

@@ -30,15 +30,28 @@ CONFIG = dict(
     num_query_tokens=8)
 
 
-def main():
+# The reference's OWN T5 test configuration (tests/model/test_model_v2.py:122-146): T5Config defaults,
+# i.e. the original T5 — non-gated ReLU feed-forward (T5DenseActDense), head tied to the embedding,
+# decoder output scaled by d_model**-0.5 — with a small image and vocabulary to keep the fixture small.
+CONFIG_RELU = dict(
+    vision_config=dict(hidden_size=8, intermediate_size=16, projection_dim=4, num_hidden_layers=2,
+                       num_attention_heads=4, patch_size=8, image_size=32),
+    qformer_config=dict(hidden_size=8, num_hidden_layers=2, num_attention_heads=2, intermediate_size=16,
+                        encoder_hidden_size=8, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0),
+    text_config=dict(model_type="t5", d_model=8, d_kv=4, d_ff=16, num_layers=2, num_heads=2,
+                     decoder_start_token_id=0, vocab_size=264, dropout_rate=0.0),
+    num_query_tokens=4)
+
+
+def main(name="small_t5", config=CONFIG, init_seed=4321, init_std=0.06, img=56, text_len=40):
     sys.modules.setdefault("pytorchvideo", types.ModuleType("pytorchvideo"))
     from eilev.model.v2 import VideoBlipForConditionalGeneration as RefModel
 
     torch.manual_seed(0)
-    cfg = Blip2Config(**CONFIG)
+    cfg = Blip2Config(**config)
     model = RefModel(cfg).float().eval()
     sd = model.state_dict()
-    sane_init_(sd, seed=4321, std=0.06)
+    sane_init_(sd, seed=init_seed, std=init_std)
     # T5 attention has no 1/sqrt(d) factor: trained checkpoints carry it in small q / k weights.
     # Shrink the random q / k projections accordingly so the scores are O(0.3) and a bf16 run is a
     # meaningful parity target (with O(4) scores the reference's own bf16 logits are 13 % off).
@@ -46,6 +59,7 @@ def main():
         if k.startswith("language_model.") and k.endswith((".q.weight", ".k.weight")):
             sd[k] = sd[k] * 0.25
     model.load_state_dict(sd)
+    model.tie_weights()
     for p in model.vision_model.parameters():
         p.requires_grad = False
     for p in model.language_model.parameters():
@@ -53,7 +67,7 @@ def main():
     g = torch.Generator().manual_seed(5)
     nq, vocab = cfg.num_query_tokens, cfg.text_config.vocab_size
     nv, t, batch = 3, 2, 2
-    pixel_values = torch.randn(nv, 3, t, 56, 56, generator=g)
+    pixel_values = torch.randn(nv, 3, t, img, img, generator=g)
     clips_per = [2, 1]
     rows = []
     for b in range(batch):  # seq2seq layout (data/utils.py:200-217): no bos, eos after the prompt
@@ -61,7 +75,7 @@ def main():
         for _ in range(clips_per[b]):
             ids += [0] * nq + [3]
             vm += [1] * nq + [0]
-            txt = torch.randint(4, vocab - 2, (40 + 9 * b,), generator=g).tolist()
+            txt = torch.randint(4, vocab - 2, (text_len + 9 * b,), generator=g).tolist()
             ids += txt
             vm += [0] * len(txt)
         ids += [1]
@@ -94,11 +108,15 @@ def main():
                    inputs=inputs, loss=out.loss.detach(), logits=out.logits.detach(),
                    encoder_last_hidden_state=out.language_model_outputs.encoder_last_hidden_state.detach(),
                    query_output=out.qformer_outputs.last_hidden_state.detach(), grads=grads)
-    path = Path(__file__).resolve().parent / "small_t5.pt"
+    path = Path(__file__).resolve().parent / f"{name}.pt"
     torch.save(fixture, path)
     print("generated", gen.tolist())
     print("loss", float(out.loss), "L", tuple(input_ids.shape), "grads", len(grads), "bytes", path.stat().st_size)
 
 
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1:] or ["small_t5", "tiny_t5_relu"]
+    if "small_t5" in which:
+        main()
+    if "tiny_t5_relu" in which:
+        main("tiny_t5_relu", CONFIG_RELU, init_seed=99, init_std=0.5, img=32, text_len=10)

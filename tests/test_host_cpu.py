@@ -71,11 +71,30 @@ def test_forward_contract_errors_on_cpu():
         m(torch.ones(1, 4).long())
     with pytest.raises(ValueError):  # v2.py:50-51
         VideoBlipVisionModel(cfg.vision_config)(None)
-    with pytest.raises(NotImplementedError):
-        Blip2Config(text_config={"model_type": "t5", "d_model": 8, "d_kv": 4, "d_ff": 16, "num_layers": 2, "num_heads": 2}) and \
-            VideoBlipForConditionalGeneration(Blip2Config(
-                vision_config=cfg.vision_config.to_dict(), qformer_config=cfg.qformer_config.to_dict(),
-                text_config={"model_type": "t5", "d_model": 8, "d_kv": 4, "d_ff": 16, "num_layers": 2, "num_heads": 2}))
+    with pytest.raises(NotImplementedError):  # T5 feed-forward variants other than relu / gated-gelu
+        VideoBlipForConditionalGeneration(Blip2Config(
+            vision_config=cfg.vision_config.to_dict(), qformer_config=cfg.qformer_config.to_dict(),
+            text_config={"model_type": "t5", "d_model": 8, "d_kv": 4, "d_ff": 16, "num_layers": 2, "num_heads": 2,
+                         "feed_forward_proj": "gated-silu"}))
+
+
+def test_t5_holder_variants_follow_the_reference_checkpoint_layout():
+    """The reference's own T5 test config (tests/model/test_model_v2.py:122-146: T5Config defaults =
+    ReLU T5DenseActDense, head tied to the embedding) and the flan-style gated-gelu config: parameter
+    names / shapes of the real reference's state_dict (golden fixtures), head tying."""
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    for name, tied in (("tiny_t5_relu", True), ("small_t5", False)):
+        fx = torch.load(GOLDEN / f"{name}.pt", weights_only=False)
+        cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+        m = VideoBlipForConditionalGeneration(cfg)
+        assert set(m.state_dict()) == set(fx["state_dict"]), name
+        m.load_state_dict(fx["state_dict"], strict=True)
+        lm = m.language_model
+        assert (lm.lm_head.weight.data_ptr() == lm.shared.weight.data_ptr()) == tied, name
+        assert lm.encoder.embed_tokens.weight.data_ptr() == lm.shared.weight.data_ptr()
+        assert torch.equal(lm.lm_head.weight, fx["state_dict"]["language_model.lm_head.weight"])
+        ff = lm.encoder.block[0].layer[1].DenseReluDense
+        assert hasattr(ff, "wi") != hasattr(ff, "wi_0")
 
 
 # ------------------------------------------------------------------ tokeniser / collator

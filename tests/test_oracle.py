@@ -110,16 +110,20 @@ def test_oracle_classify_matches_reference_golden(name):
     assert torch.allclose(got, cx["scores"], atol=2e-4, rtol=1e-4), (got, cx["scores"])
 
 
-def _load_t5():
-    fx = torch.load(GOLDEN / "small_t5.pt", weights_only=False)
+T5_NAMES = ["small_t5", "tiny_t5_relu"]  # flan-style gated-gelu / the reference's own T5 test config (ReLU, tied head)
+
+
+def _load_t5(name="small_t5"):
+    fx = torch.load(GOLDEN / f"{name}.pt", weights_only=False)
     cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
     return fx, cfg
 
 
-def test_oracle_t5_forward_matches_reference_golden():
+@pytest.mark.parametrize("name", T5_NAMES)
+def test_oracle_t5_forward_matches_reference_golden(name):
     """flan-T5 branch (v2.py:228-238 -> T5ForConditionalGeneration): golden from the real reference
     (tests/golden/make_golden_t5.py)."""
-    fx, cfg = _load_t5()
+    fx, cfg = _load_t5(name)
     out = R.videoblip_forward_t5(fx["state_dict"], cfg, **fx["inputs"])
     assert torch.allclose(out["query_output"], fx["query_output"], atol=2e-5, rtol=1e-4)
     assert torch.allclose(out["encoder_last_hidden_state"], fx["encoder_last_hidden_state"], atol=3e-4, rtol=1e-4)
@@ -127,8 +131,9 @@ def test_oracle_t5_forward_matches_reference_golden():
     assert abs(float(out["loss"]) - float(fx["loss"])) < 1e-4
 
 
-def test_oracle_t5_gradients_match_reference_golden():
-    fx, cfg = _load_t5()
+@pytest.mark.parametrize("name", T5_NAMES)
+def test_oracle_t5_gradients_match_reference_golden(name):
+    fx, cfg = _load_t5(name)
     sd = {k: v.clone() for k, v in fx["state_dict"].items()}
     trainable = [k for k in sd if k in fx["grads"]]
     assert len(trainable) == len(fx["grads"]) > 0
@@ -143,8 +148,9 @@ def test_oracle_t5_gradients_match_reference_golden():
         assert float((g - ref).norm()) < 2e-3 * float(ref.norm()) + 1e-4, k  # (key biases have zero gradient)
 
 
-def test_oracle_t5_greedy_generate_matches_reference_golden():
-    fx, cfg = _load_t5()
+@pytest.mark.parametrize("name", T5_NAMES)
+def test_oracle_t5_greedy_generate_matches_reference_golden(name):
+    fx, cfg = _load_t5(name)
     i = fx["inputs"]
     got = R.greedy_generate_t5(fx["state_dict"], cfg, i["input_ids"], i["attention_mask"], i["pixel_values"],
                                i["video_input_mask"], max_new_tokens=6, eos_token_id=cfg.text_config.eos_token_id)

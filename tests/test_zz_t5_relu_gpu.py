@@ -1,0 +1,120 @@
+"""The reference's OWN T5 test configuration on the CUDA path (tests/model/test_model_v2.py:122-146:
+``T5Config`` defaults = the original T5 — non-gated ReLU feed-forward ``T5DenseActDense``, head tied to
+the embedding, decoder output scaled by d_model**-0.5) against the golden of the real reference
+(tests/golden/tiny_t5_relu.pt, make_golden_t5.py).  The ReLU feed-forward reuses kernels the OPT
+path already exercises (GEMM / GEMV ReLU epilogue, ``vb_act_bwd``).
+
+Tolerances (bf16 kernels vs the fp32 reference; the reference's own bf16-vs-fp32 gap on this
+width-8 fixture is 0.6-0.7 % on logits and 7.4-8.6 % on gradients): logits rel-L2 <= 3 %, loss
+|d| <= 0.03, gradients global rel-L2 <= 20 %; greedy ids exact up to numerical ties (fp32 top-2
+margin < 0.1 — the margins of this fixture are 0.03-0.2).
+
+Written after round 1's GPU budget was spent: this file first runs in the round-end
+``pytest -m gpu`` (it sorts last, so nothing else depends on it)."""
+import json
+import os
+from pathlib import Path
+
+import pytest
+import torch
+from transformers import Blip2Config
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+REPORT = {}
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _dump(key, **vals):
+    REPORT[key] = vals
+    out = Path(os.environ.get("GRAFT_REPO_ROOT", ".")) / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_report_t5_relu.json").write_text(json.dumps(REPORT, indent=1))
+
+
+def load():
+    fx = torch.load(GOLDEN / "tiny_t5_relu.pt", weights_only=False)
+    cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    return fx, cfg
+
+
+def build(cfg, sd):
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    m = VideoBlipForConditionalGeneration(cfg)
+    m.load_state_dict(sd)
+    return m.to("cuda").eval()
+
+
+def cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def test_relu_t5_forward_matches_reference_golden():
+    fx, cfg = load()
+    assert not cfg.text_config.is_gated_act and cfg.text_config.dense_act_fn == "relu"
+    m = build(cfg, fx["state_dict"])
+    i = cuda(fx["inputs"])
+    with torch.no_grad():
+        out = m(**i, return_dict=True)
+        text_only = m(i["input_ids"], attention_mask=i["attention_mask"], labels=i["labels"], return_dict=True)
+    m.check_splice()
+    valid = fx["inputs"]["attention_mask"].bool()
+    r = dict(logits=rel_l2(out.logits, fx["logits"]),
+             enc=rel_l2(out.language_model_outputs.encoder_last_hidden_state.cpu()[valid],
+                        fx["encoder_last_hidden_state"][valid]),
+             loss=float(out.loss), loss_ref=float(fx["loss"]))
+    _dump("t5_relu_forward", **r)
+    assert out.logits.shape == fx["logits"].shape
+    assert r["enc"] < 0.03 and r["logits"] < 0.03, r
+    assert abs(r["loss"] - r["loss_ref"]) < 0.03, r
+    assert torch.isfinite(text_only.loss)
+
+
+def test_relu_t5_backward_matches_reference_golden():
+    from eilev_b200.train import freeze_for_recipe
+    fx, cfg = load()
+    m = build(cfg, fx["state_dict"]).train()
+    freeze_for_recipe(m)
+    out = m(**cuda(fx["inputs"]), return_dict=True)
+    out.loss.backward()
+    got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(fx["grads"]), set(got) ^ set(fx["grads"])
+    num = den = 0.0
+    for n, ref in fx["grads"].items():
+        num += float((got[n].float().cpu() - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    glob = (num / den) ** 0.5
+    _dump("t5_relu_backward", global_rel_l2=glob, loss=float(out.loss.detach()), n=len(got))
+    assert glob < 0.20, glob
+
+
+def test_relu_t5_generate_matches_reference_golden_up_to_ties():
+    from oracle import videoblip_ref as R
+    fx, cfg = load()
+    m = build(cfg, fx["state_dict"])
+    i = cuda(fx["inputs"])
+    gen = m.generate(i["input_ids"], i["pixel_values"], i["video_input_mask"], i["attention_mask"],
+                     max_new_tokens=6, do_sample=False).cpu().tolist()
+    want = fx["generated"].tolist()
+    ci = fx["inputs"]
+    seq, margins = R.greedy_generate_t5(fx["state_dict"], cfg, ci["input_ids"], ci["attention_mask"],
+                                        ci["pixel_values"], ci["video_input_mask"], 6, return_margins=True)
+    assert seq.tolist() == want  # the oracle reproduces the reference's ids (also pinned in test_oracle.py)
+    flips = {}
+    for row, (g, w) in enumerate(zip(gen, want)):
+        assert len(g) == len(w) and g[0] == w[0] == cfg.text_config.decoder_start_token_id
+        for t in range(1, len(w)):
+            if g[t] != w[t]:
+                mg = float(margins[t - 1, row])
+                assert mg < 0.1, (row, t, g, w, mg)
+                flips[f"row{row}/step{t}"] = mg
+                break
+    _dump("t5_relu_generate", generated=gen, reference=want, tie_flips=flips)
+    beams = m.generate(i["input_ids"], i["pixel_values"], i["video_input_mask"], i["attention_mask"],
+                       max_new_tokens=4, num_beams=2)
+    assert beams.shape[0] == 2 and beams.shape[1] <= 5
