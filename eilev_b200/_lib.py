@@ -68,6 +68,9 @@ SIGNATURES: dict[str, list] = {
     "vb_attention_bwd": [C.POINTER(AttnBwdArgs), vp],
     "vb_patch_gather": [vp, i32, vp, i64, i64, i64, i64, i64, i64, i64, vp],
     "vb_patch_gather_u8": [vp, vp, i64, i64, i64, i64, i64, i64, i64, C.c_double, C.POINTER(f32), C.POINTER(f32), vp],
+    "vb_resize_bicubic_ksize": [i64, i64],
+    "vb_resize_bicubic_coeffs": [i64, i64, C.POINTER(i32), C.POINTER(i32), i64],
+    "vb_resize_u8_pass": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, i32, vp],
     "vb_cls_rows": [vp, vp, vp, i64, i64, i64, vp],
     "vb_embed_splice": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp],
     "vb_splice_bwd": [vp, vp, vp, i64, i64, i64, vp],

@@ -1,6 +1,8 @@
 // extern "C" surface of libvideoblip_b200.so — see include/videoblip_b200.h.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "gemm.h"
 #include "internal.h"
@@ -23,6 +25,14 @@ inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
     if (_e != cudaSuccess) return fail(where, _e);  \
     return 0;                                       \
   } while (0)
+// Keys cubic (a = -0.5) exactly as Pillow's Resample.c bicubic_filter evaluates it (host, double).
+inline double vb_bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
 }  // namespace
 
 extern "C" {
@@ -110,6 +120,64 @@ int vb_patch_gather_u8(const void* pixels_u8, void* out, int64_t nv, int64_t c, 
     if (!(stdv[i] > 0.0f)) return fail_msg("vb_patch_gather_u8", "std must be positive");
   VB_CHECK("vb_patch_gather_u8", vb::patch_gather_u8_launch(pixels_u8, out, nv, c, t, h, w, patch, kpad,
                                                            rescale, mean, stdv, st(stream)));
+}
+
+// ---- Pillow-exact antialiased bicubic resize of uint8 planes --------------------------------
+// Host side: the window bounds and 22-bit fixed-point weights of one axis, in double precision
+// with Pillow's own expression order (Resample.c precompute_coeffs + normalize_coeffs_8bpc; Keys
+// cubic a = -0.5, support 2 stretched by the scale when down-sampling).
+int vb_resize_bicubic_ksize(int64_t in_size, int64_t out_size) {
+  if (in_size <= 0 || out_size <= 0) return 0;
+  double filterscale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  if (filterscale < 1.0) filterscale = 1.0;
+  return static_cast<int>(std::ceil(2.0 * filterscale)) * 2 + 1;
+}
+
+int vb_resize_bicubic_coeffs(int64_t in_size, int64_t out_size, int32_t* bounds, int32_t* kk,
+                             int64_t kk_capacity) {
+  const int64_t ksize = vb_resize_bicubic_ksize(in_size, out_size);
+  if (ksize <= 0 || bounds == nullptr || kk == nullptr || kk_capacity < out_size * ksize)
+    return fail_msg("vb_resize_bicubic_coeffs", "bad arguments");
+  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const double ss = 1.0 / filterscale;
+  std::vector<double> w(static_cast<size_t>(ksize));
+  for (int64_t xx = 0; xx < out_size; ++xx) {
+    const double center = (static_cast<double>(xx) + 0.5) * scale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = static_cast<int>(in_size);
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = vb_bicubic_filter((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    int32_t* k = kk + xx * ksize;
+    for (int x = 0; x < xmax; ++x) {
+      const double v = ww != 0.0 ? w[x] / ww : w[x];
+      k[x] = v < 0 ? static_cast<int32_t>(-0.5 + v * (1 << 22)) : static_cast<int32_t>(0.5 + v * (1 << 22));
+    }
+    for (int64_t x = xmax; x < ksize; ++x) k[x] = 0;
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return 0;
+}
+
+int vb_resize_u8_pass(const void* in, void* out, const int32_t* bounds, const int32_t* kk, int64_t planes,
+                      int64_t lines, int64_t out_len, int64_t ksize, int64_t in_plane_stride,
+                      int64_t in_line_stride, int64_t in_elem_stride, int64_t out_plane_stride,
+                      int64_t out_line_stride, int64_t out_elem_stride, int32_t lines_fastest, void* stream) {
+  if (in == nullptr || out == nullptr || bounds == nullptr || kk == nullptr || ksize <= 0 || planes < 0 ||
+      lines < 0 || out_len < 0)
+    return fail_msg("vb_resize_u8_pass", "bad arguments");
+  VB_CHECK("vb_resize_u8_pass",
+           vb::resize_u8_pass_launch(in, out, bounds, kk, planes, lines, out_len, ksize, in_plane_stride,
+                                     in_line_stride, in_elem_stride, out_plane_stride, out_line_stride,
+                                     out_elem_stride, lines_fastest, st(stream)));
 }
 
 int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,

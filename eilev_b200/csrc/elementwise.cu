@@ -115,6 +115,47 @@ cudaError_t patch_gather_u8_launch(const void* px, void* out, long long nv, long
   return cudaGetLastError();
 }
 
+// One pass (horizontal or vertical) of Pillow's 8-bit two-pass resample (Resample.c
+// ImagingResampleHorizontal_8bpc / Vertical_8bpc): out = clip8((2^21 + sum_k in[xmin + k] * kk[k]) >> 22)
+// with 22-bit fixed-point weights and 32-bit integer accumulation, bit for bit.  The pass runs along
+// an arbitrary axis through element strides; `lines_fastest` picks which index varies fastest across a
+// warp so that both passes read and write consecutive bytes (horizontal: outputs of one row; vertical:
+// neighbouring columns of one output row).
+__global__ void __launch_bounds__(256)
+resize_u8_pass_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
+                      const int* __restrict__ bounds, const int* __restrict__ kk, long long planes,
+                      long long lines, long long out_len, int ksize, long long ips, long long ils,
+                      long long ies, long long ops, long long ols, long long oes, int lines_fastest) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_plane = lines * out_len;
+  if (idx >= planes * per_plane) return;
+  const long long p = idx / per_plane;
+  const long long r = idx % per_plane;
+  const long long l = lines_fastest ? r % lines : r / out_len;
+  const long long o = lines_fastest ? r / lines : r % out_len;
+  const int xmin = bounds[2 * o], cnt = bounds[2 * o + 1];
+  const int* __restrict__ k = kk + o * ksize;
+  const unsigned char* __restrict__ src = in + p * ips + l * ils + static_cast<long long>(xmin) * ies;
+  int acc = 1 << 21;
+  for (int x = 0; x < cnt; ++x) acc += static_cast<int>(src[x * ies]) * k[x];
+  acc >>= 22;
+  out[p * ops + l * ols + o * oes] = static_cast<unsigned char>(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+}
+
+cudaError_t resize_u8_pass_launch(const void* in, void* out, const int* bounds, const int* kk,
+                                  long long planes, long long lines, long long out_len, long long ksize,
+                                  long long ips, long long ils, long long ies, long long ops,
+                                  long long ols, long long oes, int lines_fastest, cudaStream_t s) {
+  const long long total = planes * lines * out_len;
+  if (total <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  resize_u8_pass_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned char*>(in),
+                                             reinterpret_cast<unsigned char*>(out), bounds, kk, planes,
+                                             lines, out_len, static_cast<int>(ksize), ips, ils, ies, ops,
+                                             ols, oes, lines_fastest);
+  return cudaGetLastError();
+}
+
 __global__ void cls_rows_kernel(const __nv_bfloat16* cls, const __nv_bfloat16* pos,
                                 __nv_bfloat16* hidden, long long frames, long long tokens,
                                 long long dim) {

@@ -28,6 +28,10 @@ cudaError_t patch_gather_u8_launch(const void* px, void* out, long long nv, long
                                    long long h, long long w, long long patch, long long kpad,
                                    double rescale, const float* mean, const float* stdv,
                                    cudaStream_t s);
+cudaError_t resize_u8_pass_launch(const void* in, void* out, const int* bounds, const int* kk,
+                                  long long planes, long long lines, long long out_len, long long ksize,
+                                  long long ips, long long ils, long long ies, long long ops,
+                                  long long ols, long long oes, int lines_fastest, cudaStream_t s);
 cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long long frames,
                             long long tokens, long long dim, cudaStream_t s);
 cudaError_t embed_splice_launch(const long long* ids, const long long* attn, const long long* vmask,

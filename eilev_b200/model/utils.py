@@ -40,3 +40,30 @@ def process(processor, video: torch.Tensor | None = None,
         pv = inputs.pixel_values
         inputs["pixel_values"] = pv.view(b, t, c, pv.shape[-2], pv.shape[-1]).permute(0, 2, 1, 3, 4)
     return inputs
+
+
+def process_on_device(processor, video: torch.Tensor, text: str | list[str] | None = None) -> BatchEncoding:
+    """``process`` for decoded uint8 frames that already live on the GPU: the
+    image processor's bicubic resize runs on the device, bit-exact with the PIL resize the reference's
+    ``BlipImageProcessor`` performs (``vb_resize_u8_pass``), the frames stay uint8, and the model
+    applies rescale + normalize inside its patch gather (``vb_patch_gather_u8``) — no float frame
+    tensor is ever materialised.  Text goes through the processor's tokenizer as in ``process``.
+
+    :param video: uint8 CUDA tensor (batch, channel, time, height, width) or (channel, time, height, width)
+    :returns: BatchEncoding with uint8 ``pixel_values`` (batch, channel, time, size_h, size_w) on the
+        device of ``video`` (+ the tokenizer's fields on the CPU when ``text`` is given)
+    """
+    from .. import ops
+
+    if video.dtype != torch.uint8:
+        raise ValueError("process_on_device expects decoded uint8 frames")
+    if video.dim() == 4:
+        video = video[None]
+    ip = getattr(processor, "image_processor", processor)
+    size = ip.size
+    height, width = int(size["height"]), int(size["width"])
+    if not getattr(ip, "do_resize", True):
+        height, width = video.shape[-2:]
+    inputs = processor(text=text, return_tensors="pt") if text is not None else BatchEncoding({})
+    inputs["pixel_values"] = ops.resize_bicubic_u8(video, height, width)
+    return inputs

@@ -268,6 +268,87 @@ def patch_gather_u8(frames: torch.Tensor, patch: int, kpad: int, rescale: float,
     return out
 
 
+_RESIZE_TABLES: dict = {}
+
+
+def resize_coeffs(in_size: int, out_size: int):
+    """Host tables of one axis of Pillow's antialiased bicubic: (ksize, bounds (out, 2) int32 =
+    [first tap, tap count], kk (out, ksize) int32 22-bit fixed-point weights).  Host arithmetic only
+    (``vb_resize_bicubic_coeffs``): no device work, no launch."""
+    lib = _lib.lib()
+    ksize = int(lib.vb_resize_bicubic_ksize(in_size, out_size))
+    if ksize <= 0:
+        raise ValueError(f"resize_coeffs: bad sizes {in_size} -> {out_size}")
+    bounds = torch.empty((out_size, 2), dtype=torch.int32)
+    kk = torch.empty((out_size, ksize), dtype=torch.int32)
+    rc = lib.vb_resize_bicubic_coeffs(in_size, out_size, C.cast(bounds.data_ptr(), C.POINTER(C.c_int32)),
+                                      C.cast(kk.data_ptr(), C.POINTER(C.c_int32)), kk.numel())
+    if rc != 0:
+        raise _lib.VbError(f"vb_resize_bicubic_coeffs failed: {lib.vb_last_error().decode()}")
+    return ksize, bounds, kk
+
+
+def resize_plan(in_h: int, in_w: int, out_h: int, out_w: int) -> list[dict]:
+    """The passes of Pillow's two-pass resample (ImagingResampleInner) as ``vb_resize_u8_pass``
+    argument sets — pure integer bookkeeping, shared by the device path and its CPU emulation test.
+    Horizontal pass first (when the width changes), restricted to source rows [first, last) that
+    the vertical pass reads; then the vertical pass with its windows shifted by ``first``."""
+    need_h, need_v = out_w != in_w, out_h != in_h
+    passes: list[dict] = []
+    first, rows = 0, in_h
+    if need_v:
+        _, vb, _ = resize_coeffs(in_h, out_h)
+        if need_h:
+            first = int(vb[0, 0])
+            rows = int(vb[-1, 0] + vb[-1, 1]) - first
+    if need_h:
+        passes.append(dict(axis=(in_w, out_w), shift=0, in_offset=first * in_w, lines=rows, out_len=out_w,
+                           in_strides=(in_h * in_w, in_w, 1), out_strides=(rows * out_w, out_w, 1),
+                           out_shape=(rows, out_w), lines_fastest=0))
+    if need_v:
+        passes.append(dict(axis=(in_h, out_h), shift=first, in_offset=0, lines=out_w, out_len=out_h,
+                           in_strides=(rows * out_w, 1, out_w), out_strides=(out_h * out_w, 1, out_w),
+                           out_shape=(out_h, out_w), lines_fastest=1))
+    return passes
+
+
+def _resize_tables(in_size: int, out_size: int, device, shift: int):
+    key = (in_size, out_size, shift, str(device))
+    hit = _RESIZE_TABLES.get(key)
+    if hit is None:
+        ksize, bounds, kk = resize_coeffs(in_size, out_size)
+        bounds = bounds.clone()
+        bounds[:, 0] -= shift
+        hit = (ksize, bounds.to(device), kk.to(device))
+        _RESIZE_TABLES[key] = hit
+    return hit
+
+
+def resize_bicubic_u8(frames: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """uint8 (..., H, W) -> (..., out_h, out_w) uint8: every plane resized as
+    ``PIL.Image.resize((out_w, out_h), BICUBIC)`` resizes it, bit for bit (Pillow's two-pass 8-bit
+    resample: horizontal pass over the source rows the vertical pass reads, then the vertical pass)."""
+    _need(frames, torch.uint8, "resize_bicubic_u8.frames")
+    assert frames.dim() >= 2
+    frames = frames.contiguous()
+    in_h, in_w = frames.shape[-2:]
+    lead = frames.shape[:-2]
+    planes = frames.numel() // (in_h * in_w) if in_h * in_w else 0
+    passes = resize_plan(in_h, in_w, out_h, out_w)
+    if not passes or planes == 0:
+        return frames.clone()
+    cur = frames
+    for ps in passes:
+        ksize, bounds, kk = _resize_tables(*ps["axis"], frames.device, ps["shift"])
+        out = torch.empty((planes, *ps["out_shape"]), dtype=torch.uint8, device=frames.device)
+        check(_lib.lib().vb_resize_u8_pass(cur.data_ptr() + ps["in_offset"], out.data_ptr(), bounds.data_ptr(),
+                                           kk.data_ptr(), planes, ps["lines"], ps["out_len"], ksize,
+                                           *ps["in_strides"], *ps["out_strides"], ps["lines_fastest"], _stream()),
+              "vb_resize_u8_pass")
+        cur = out
+    return cur.view(*lead, out_h, out_w)
+
+
 def cls_rows(cls: torch.Tensor, pos: torch.Tensor, hidden: torch.Tensor) -> None:
     frames, tokens, dim = hidden.shape
     check(_lib.lib().vb_cls_rows(cls.data_ptr(), pos.data_ptr(), hidden.data_ptr(), frames, tokens,

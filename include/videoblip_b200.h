@@ -185,6 +185,28 @@ int vb_patch_gather(const void* pixels, int32_t px_dtype, void* out, int64_t nv,
 int vb_patch_gather_u8(const void* pixels_u8, void* out, int64_t nv, int64_t c, int64_t t, int64_t h,
                        int64_t w, int64_t patch, int64_t kpad, double rescale, const float* mean,
                        const float* stdv, void* stream);
+/* ------------------------------------------------------------------------
+ * Antialiased bicubic resize of uint8 planes, bit-exact with PIL.Image.resize(size, BICUBIC) —
+ * the resize BlipImageProcessor performs for eilev/model/utils.py:5-26 `process` (transformers
+ * 4.33.1 image_transforms.resize -> Pillow src/libImaging/Resample.c).  SURVEY §8(f) rank 3.
+ *   vb_resize_bicubic_ksize  : taps per output sample of one axis (host only, no device work)
+ *   vb_resize_bicubic_coeffs : HOST arrays bounds[2*out] = {first tap, tap count} and
+ *                              kk[out*ksize] = 22-bit fixed-point weights (precompute_coeffs +
+ *                              normalize_coeffs_8bpc, double precision, Pillow's expression order)
+ *   vb_resize_u8_pass        : one pass along one axis on the device (bounds / kk are DEVICE copies):
+ *       out[p, l, o] = clip8((2^21 + sum_k in[p, l, bounds[2o] + k] * kk[o*ksize + k]) >> 22)
+ *     addressed through element strides, so the same kernel runs Pillow's horizontal pass (over
+ *     the source rows the vertical pass needs) and then its vertical pass; lines_fastest selects
+ *     which index is consecutive across a warp.
+ * ---------------------------------------------------------------------- */
+int vb_resize_bicubic_ksize(int64_t in_size, int64_t out_size);
+int vb_resize_bicubic_coeffs(int64_t in_size, int64_t out_size, int32_t* bounds, int32_t* kk,
+                             int64_t kk_capacity);
+int vb_resize_u8_pass(const void* in, void* out, const int32_t* bounds, const int32_t* kk, int64_t planes,
+                      int64_t lines, int64_t out_len, int64_t ksize, int64_t in_plane_stride,
+                      int64_t in_line_stride, int64_t in_elem_stride, int64_t out_plane_stride,
+                      int64_t out_line_stride, int64_t out_elem_stride, int32_t lines_fastest, void* stream);
+
 /* hidden[f, 0, :] = cls + pos[0]  for every frame f (HF:...:249-254). bf16. */
 int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
                 int64_t dim, void* stream);

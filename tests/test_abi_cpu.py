@@ -107,3 +107,72 @@ def test_patch_gather_u8_validates_arguments_before_touching_the_device(lib):
     assert b"bad arguments" in lib.vb_last_error()
     assert lib.vb_patch_gather_u8(C.addressof(buf), C.addressof(out), 1, 5, 1, 4, 4, 2, 20, 1 / 255, ok_mean, ok_std, None) != 0
     assert lib.vb_patch_gather_u8(C.addressof(buf), C.addressof(out), 1, 3, 1, 4, 4, 2, 11, 1 / 255, ok_mean, ok_std, None) != 0  # kpad < C*P*P
+
+
+def test_resize_coefficient_tables_equal_the_pillow_restatement(lib):
+    """vb_resize_bicubic_coeffs is host arithmetic (no device work): its window bounds and 22-bit
+    fixed-point weights must equal the oracle's restatement of Pillow's precompute_coeffs +
+    normalize_coeffs_8bpc — itself pinned bit-exactly to PIL.Image.resize — for every size pair."""
+    import numpy as np
+    from eilev_b200 import ops
+    from oracle import pil_resize_ref as P
+    pairs = [(448, 224), (224, 224), (100, 224), (160, 224), (300, 224), (500, 224), (1080, 224), (1920, 224),
+             (37, 56), (53, 56), (17, 64), (19, 48), (225, 224), (223, 224), (7, 3), (3, 7), (1, 5), (5, 1)]
+    for n_in, n_out in pairs:
+        ksize, bounds, kk = ops.resize_coeffs(n_in, n_out)
+        rk, rb, rkk = P.precompute_coeffs(n_in, n_out)
+        assert ksize == rk, (n_in, n_out)
+        assert np.array_equal(bounds.numpy(), rb), (n_in, n_out)
+        assert np.array_equal(kk.numpy(), rkk), (n_in, n_out)
+        assert int((bounds[:, 0] + bounds[:, 1]).max()) <= n_in and int(bounds[:, 0].min()) >= 0
+    with pytest.raises(ValueError):
+        ops.resize_coeffs(0, 4)
+    assert lib.vb_resize_bicubic_coeffs(8, 4, None, None, 0) != 0
+    assert lib.vb_resize_u8_pass(None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, None) != 0
+
+
+def _emulate_resize_pass(src, out, bounds, kk, planes, lines, out_len, ksize, ips, ils, ies, ops_, ols, oes,
+                         lines_fastest):
+    """resize_u8_pass_kernel (csrc/elementwise.cu) thread for thread, in numpy on flat byte arrays."""
+    import numpy as np
+    idx = np.arange(planes * lines * out_len, dtype=np.int64)
+    per_plane = lines * out_len
+    p, r = idx // per_plane, idx % per_plane
+    l = np.where(lines_fastest, r % lines, r // out_len)
+    o = np.where(lines_fastest, r // lines, r % out_len)
+    acc = np.full(idx.shape, 1 << 21, dtype=np.int32)
+    for x in range(ksize):
+        live = x < bounds[o, 1]
+        pos = p * ips + l * ils + (bounds[o, 0].astype(np.int64) + x) * ies
+        tap = src[np.where(live, pos, 0)].astype(np.int32)
+        acc = acc + np.where(live, tap * kk[o, x], 0).astype(np.int32)
+    out[p * ops_ + l * ols + o * oes] = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape,size", [((2, 3, 40, 72), (56, 56)), ((1, 2, 90, 60), (32, 48)), ((3, 56, 80), (56, 56)),
+                                        ((2, 70, 56), (56, 56)), ((1, 448, 448), (224, 224)), ((2, 56, 56), (56, 56))])
+def test_resize_plan_emulated_on_cpu_equals_pillow(lib, shape, size):
+    """The pass plan ops.resize_bicubic_u8 hands to vb_resize_u8_pass (offsets, strides, shifted
+    vertical windows, warp index order), executed by a numpy emulation of the kernel's per-thread
+    formula with the C library's own coefficient tables, reproduces PIL.Image.resize bit for bit."""
+    import numpy as np
+    from PIL import Image
+    from eilev_b200 import ops
+    rs = np.random.RandomState(sum(shape))
+    frames = rs.randint(0, 256, shape).astype(np.uint8)
+    in_h, in_w = shape[-2:]
+    out_h, out_w = size
+    planes = int(np.prod(shape[:-2]))
+    cur = frames.reshape(-1)
+    for ps in ops.resize_plan(in_h, in_w, out_h, out_w):
+        ksize, bounds, kk = ops.resize_coeffs(*ps["axis"])
+        bounds = bounds.numpy().copy()
+        bounds[:, 0] -= ps["shift"]
+        out = np.zeros(planes * ps["out_shape"][0] * ps["out_shape"][1], dtype=np.uint8)
+        _emulate_resize_pass(cur[ps["in_offset"]:], out, bounds, kk.numpy(), planes, ps["lines"], ps["out_len"], ksize,
+                             *ps["in_strides"], *ps["out_strides"], ps["lines_fastest"])
+        cur = out
+    got = cur.reshape(*shape[:-2], out_h, out_w)
+    want = np.stack([np.asarray(Image.fromarray(pl).resize((out_w, out_h), resample=Image.BICUBIC))
+                     for pl in frames.reshape(-1, in_h, in_w)]).reshape(got.shape)
+    assert np.array_equal(got, want)

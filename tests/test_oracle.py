@@ -254,3 +254,26 @@ def test_oracle_normalize_frames_is_the_hf_rescale_and_normalize():
     live = ip(images=flat, return_tensors="pt").pixel_values.view(2, 4, 3, 32, 48).permute(0, 2, 1, 3, 4)
     assert float((got - live).abs().max()) < 1e-6
     assert float((got.bfloat16() == live.bfloat16()).float().mean()) > 0.9999
+
+
+def test_oracle_pil_resize_is_bit_exact_with_pillow():
+    """oracle/pil_resize_ref.py (restatement of Pillow's Resample.c 8-bit bicubic) against the real
+    ``PIL.Image.resize(size, BICUBIC)`` — the resize of the reference's ``process`` — over down-/up-
+    scaling, non-square, odd sizes, identity, RGB (bands are independent) and saturating inputs."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle import pil_resize_ref as P
+    rs = np.random.RandomState(0)
+    for (h, w), (oh, ow) in [((448, 448), (224, 224)), ((100, 160), (224, 224)), ((224, 224), (224, 224)),
+                             ((37, 53), (56, 56)), ((300, 500), (224, 224)), ((224, 300), (224, 224)),
+                             ((301, 224), (224, 224)), ((17, 19), (64, 48)), ((720, 1280), (224, 224))]:
+        x = rs.randint(0, 256, (h, w)).astype(np.uint8)
+        want = np.asarray(Image.fromarray(x).resize((ow, oh), resample=Image.BICUBIC))
+        assert np.array_equal(P.resize_bicubic_u8(x, oh, ow), want), ((h, w), (oh, ow))
+    rgb = rs.randint(0, 256, (120, 90, 3)).astype(np.uint8)
+    want = np.asarray(Image.fromarray(rgb).resize((224, 224), resample=Image.BICUBIC))
+    assert np.array_equal(np.moveaxis(P.resize_bicubic_u8(np.moveaxis(rgb, -1, 0), 224, 224), 0, -1), want)
+    binary = ((rs.rand(64, 64) > 0.5) * 255).astype(np.uint8)  # overshoot of the negative lobes clips at 0 / 255
+    assert np.array_equal(P.resize_bicubic_u8(binary, 224, 224),
+                          np.asarray(Image.fromarray(binary).resize((224, 224), resample=Image.BICUBIC)))

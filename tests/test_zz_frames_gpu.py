@@ -1,5 +1,6 @@
-"""uint8 frame path (first slice): decoded frames go to the GPU as bytes and
-``vb_patch_gather_u8`` applies BlipImageProcessor's rescale + normalize inside the patch gather.
+"""uint8 frame path: decoded frames go to the GPU as bytes; ``vb_resize_u8_pass``
+resizes them exactly as PIL does and ``vb_patch_gather_u8`` applies BlipImageProcessor's rescale +
+normalize inside the patch gather.
 
 Checked against the oracle restatement ``normalize_frames`` (bit-exact with the HF functions the
 reference's pinned image processor calls, tests/test_oracle.py): the bf16 patch matrix built from
@@ -107,3 +108,54 @@ def test_model_on_uint8_frames_equals_model_on_processed_frames(name):
     assert float((vc.last_hidden_state.float() - vd.last_hidden_state.float()).abs().max()) <= \
         2e-3 * float(vd.last_hidden_state.float().abs().max())
     assert float((vc.last_hidden_state.float() - va.last_hidden_state.float()).abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("shape,size", [((2, 3, 2, 40, 72), (56, 56)), ((1, 3, 8, 448, 448), (224, 224)),
+                                        ((1, 2, 3, 90, 60), (32, 48)), ((2, 1, 1, 56, 80), (56, 56)),
+                                        ((1, 1, 2, 70, 56), (56, 56)), ((1, 3, 1, 360, 640), (224, 224)),
+                                        ((1, 3, 2, 56, 56), (56, 56))])
+def test_device_resize_is_bit_exact_with_pillow(shape, size):
+    """vb_resize_u8_pass (two passes) against the real PIL.Image.resize(size, BICUBIC) on every plane."""
+    import numpy as np
+    from PIL import Image
+    from eilev_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    frames = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+    frames[..., :4, :4] = 255
+    frames[..., 4:8, :4] = 0  # hard edges: the negative lobes overshoot and must clip like Pillow's clip8
+    out_h, out_w = size
+    got = ops.resize_bicubic_u8(frames.cuda(), out_h, out_w)
+    torch.cuda.synchronize()
+    planes = frames.reshape(-1, *shape[-2:]).numpy()
+    want = np.stack([np.asarray(Image.fromarray(p).resize((out_w, out_h), resample=Image.BICUBIC)) for p in planes])
+    want = torch.from_numpy(want.copy()).view(*shape[:-2], out_h, out_w)
+    assert got.shape == want.shape and got.dtype == torch.uint8
+    mism = int((got.cpu() != want).sum())
+    _dump(f"resize_u8/{'x'.join(map(str, shape))}->{out_h}x{out_w}", elements=want.numel(), mismatches=mism)
+    assert mism == 0, mism
+
+
+def test_process_on_device_matches_the_stock_processor_path():
+    """process_on_device (resize on the GPU, uint8 out) + the model's fused normalisation against the
+    stock path: BlipImageProcessor with the PIL backend semantics restated by the oracle."""
+    import numpy as np
+    from PIL import Image
+    from transformers import BlipImageProcessor
+    from eilev_b200 import ops
+    from eilev_b200.model.utils import process_on_device
+    from oracle import videoblip_ref as R
+    ip = BlipImageProcessor(size={"height": 56, "width": 56})
+    g = torch.Generator().manual_seed(9)
+    video = torch.randint(0, 256, (2, 3, 2, 48, 100), dtype=torch.uint8, generator=g)
+    out = process_on_device(ip, video.cuda())
+    pv = out["pixel_values"]
+    assert pv.dtype == torch.uint8 and pv.is_cuda and pv.shape == (2, 3, 2, 56, 56)
+    planes = video.reshape(-1, 48, 100).numpy()
+    resized = np.stack([np.asarray(Image.fromarray(p).resize((56, 56), resample=Image.BICUBIC)) for p in planes])
+    resized = torch.from_numpy(resized.copy()).view(2, 3, 2, 56, 56)
+    assert torch.equal(pv.cpu(), resized)
+    want = ops.patch_gather(R.normalize_frames(resized).cuda(), 14, 608)
+    got = ops.patch_gather_u8(pv, 14, 608, 1 / 255, R.OPENAI_CLIP_MEAN, R.OPENAI_CLIP_STD)
+    assert int((got.view(torch.int16) != want.view(torch.int16)).sum()) == 0
+    with pytest.raises(ValueError):
+        process_on_device(ip, video.float().cuda())
