@@ -320,6 +320,8 @@ def _resize_tables(in_size: int, out_size: int, device, shift: int):
         bounds = bounds.clone()
         bounds[:, 0] -= shift
         hit = (ksize, bounds.to(device), kk.to(device))
+        if len(_RESIZE_TABLES) >= 64:  # videos of many resolutions: keep the table cache bounded
+            _RESIZE_TABLES.pop(next(iter(_RESIZE_TABLES)))
         _RESIZE_TABLES[key] = hit
     return hit
 
