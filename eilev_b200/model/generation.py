@@ -109,6 +109,66 @@ class _T5Stepper:
             self.prefix = self.prefix[src]
 
 
+class _GroupedStepper:
+    """More rows (batch x beams) than one weight-streaming decode step takes (16): the rows are dealt
+    to groups of whole beam sets, each group a stepper of its own (own paged KV cache, own CUDA
+    graph); a step streams the weights once per group.  Beam search permutes rows only inside one
+    prompt's beams, so ``reorder`` never crosses a group.  Token bookkeeping only — the arithmetic
+    stays in the per-group steppers."""
+
+    def __init__(self, make, rows_per_group: int) -> None:
+        assert rows_per_group >= 1
+        self.make, self.rows_per_group = make, int(rows_per_group)
+        self.start_token = None
+        self.groups: list = []
+        self.bounds: list[tuple[int, int]] = []
+        self.graphs: list | None = None
+
+    def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
+        rows = input_ids.shape[0]
+        self.bounds = [(r0, min(rows, r0 + self.rows_per_group)) for r0 in range(0, rows, self.rows_per_group)]
+        # video features are spliced in row-major mask order: a group's rows own a contiguous slice
+        offsets = [0] * (rows + 1)
+        if feats is not None:
+            counts = video_mask.sum(dim=1).tolist()
+            for r, c in enumerate(counts):
+                offsets[r + 1] = offsets[r] + int(c)
+        logits, statuses = [], []
+        self.groups = []
+        for r0, r1 in self.bounds:
+            st = self.make()
+            self.groups.append(st)
+            logits.append(st.prefill(input_ids[r0:r1], attention_mask[r0:r1],
+                                     None if video_mask is None else video_mask[r0:r1],
+                                     None if feats is None else feats[offsets[r0]:offsets[r1]], max_new))
+            statuses.append(getattr(st, "status", None))
+        self.start_token = self.groups[0].start_token
+        live = [x for x in statuses if x is not None]
+        self.status = torch.stack(live).sum(dim=0).to(live[0].dtype) if live else None  # (mismatch flag, slot count)
+        return torch.cat(logits, dim=0)
+
+    def graph(self, rows, dev):
+        self.graphs = [st.graph(r1 - r0, dev) for st, (r0, r1) in zip(self.groups, self.bounds)]
+        return self
+
+    def step(self, tokens):
+        tokens = tokens.view(-1)
+        out = []
+        for i, (st, (r0, r1)) in enumerate(zip(self.groups, self.bounds)):
+            g = self.graphs[i] if self.graphs is not None else None
+            out.append((g if g is not None else st).step(tokens[r0:r1]))
+        return torch.cat(out, dim=0)  # copies: a graphed group returns its static logits buffer
+
+    def reorder(self, src) -> None:
+        for st, (r0, r1) in zip(self.groups, self.bounds):
+            local = src[r0:r1] - r0
+            if not bool(((local >= 0) & (local < r1 - r0)).all()):
+                raise RuntimeError("beam reorder crosses a decode group")
+            st.reorder(local)
+
+
+MAX_DECODE_ROWS = 16  # rows one weight-streaming decode step takes (engine/opt.py::opt_decode_step)
+
 _UNSUPPORTED = ("penalty_alpha", "num_beam_groups", "diversity_penalty", "constraints",
                 "force_words_ids", "assistant_model", "prompt_lookup_num_tokens")
 
@@ -221,7 +281,14 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
 
     stepper = kw.pop("_stepper", None)  # test seam: the decoding loops over an injected LM stepper
     if stepper is None:
-        stepper = _OptStepper(lm) if model.config.use_decoder_only_language_model else _T5Stepper(lm)
+        if not model.config.use_decoder_only_language_model:
+            stepper = _T5Stepper(lm)
+        elif input_ids.shape[0] <= MAX_DECODE_ROWS:
+            stepper = _OptStepper(lm)
+        else:
+            if num_beams > MAX_DECODE_ROWS:
+                raise NotImplementedError(f"num_beams > {MAX_DECODE_ROWS} is not supported")
+            stepper = _GroupedStepper(lambda: _OptStepper(lm), MAX_DECODE_ROWS // num_beams * num_beams)
     logits = stepper.prefill(input_ids, attention_mask, video_mask, video_features, max_new)
     model._last_splice_status = stepper.status
 
@@ -238,7 +305,7 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
                                    length_penalty, early_stopping, do_sample, temperature, top_k, top_p))
 
     rows = input_ids.shape[0]
-    use_graph = bool(kw.get("use_cuda_graph", max_new >= 8)) and rows <= 16
+    use_graph = bool(kw.get("use_cuda_graph", max_new >= 8)) and (rows <= MAX_DECODE_ROWS or isinstance(stepper, _GroupedStepper))
     dgraph = stepper.graph(rows, dev) if use_graph and max_new > 1 else None
     generated = torch.empty((rows, 0), dtype=torch.long, device=dev)
     unfinished = torch.ones(rows, dtype=torch.bool, device=dev)

@@ -626,3 +626,76 @@ def test_vision_model_frame_normalization_defaults_and_override():
     m.set_frame_normalization(BlipImageProcessor(image_mean=[0.5, 0.5, 0.5], image_std=[0.25, 0.5, 1.0]))
     assert m.image_mean == (0.5, 0.5, 0.5) and m.image_std == (0.25, 0.5, 1.0)
     assert VideoBlipVisionModel.image_mean == R.OPENAI_CLIP_MEAN  # class default untouched
+
+
+# ------------------------------------------------------------------------------------- > 16 decode rows
+def test_grouped_stepper_equals_one_stepper_over_all_rows():
+    """generate() deals more than 16 rows (batch x beams) to groups of whole beam sets
+    (_GroupedStepper).  With an injected per-group stepper over a tiny HF OPT the grouped run must
+    reproduce the single-stepper run exactly: greedy, beam search (reorder stays inside a group),
+    sampling; video features are split by the rows' slot counts; statuses add up."""
+    import types
+    from transformers import OPTConfig, OPTForCausalLM
+    from eilev_b200.model import generation as G
+
+    torch.manual_seed(0)
+    cfg = OPTConfig(hidden_size=16, num_hidden_layers=2, ffn_dim=32, num_attention_heads=2, vocab_size=24,
+                    max_position_embeddings=64, word_embed_proj_dim=16, pad_token_id=1, eos_token_id=2, bos_token_id=0)
+    lm = OPTForCausalLM(cfg).eval()
+    for p in lm.parameters():
+        p.data.normal_(0, 0.6)
+    seen = []
+
+    class Stepper:
+        start_token = None
+
+        def __init__(self):
+            self.table = lm.get_input_embeddings().weight.detach()
+
+        def _logits(self):
+            with torch.no_grad():
+                return lm(inputs_embeds=self.emb).logits[:, -1].float()
+
+        def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
+            self.emb = self.table[input_ids].clone()
+            if feats is not None:  # the reference's splice (v2.py:316): row-major over this stepper's rows
+                self.emb[video_mask.bool()] = feats
+            seen.append((input_ids.shape[0], None if feats is None else feats.shape[0]))
+            self.status = torch.tensor([0, 0 if feats is None else feats.shape[0]], dtype=torch.int32)
+            return self._logits()
+
+        def graph(self, rows, dev):
+            return None
+
+        def step(self, tokens):
+            self.emb = torch.cat([self.emb, self.table[tokens.view(-1)][:, None]], 1)
+            return self._logits()
+
+        def reorder(self, src):
+            self.emb = self.emb[src]
+
+    model = types.SimpleNamespace(config=types.SimpleNamespace(text_config=cfg, use_decoder_only_language_model=True),
+                                  language_model=lm)
+    batch = 7
+    ids = torch.randint(3, 24, (batch, 6))
+    vm = torch.zeros_like(ids)
+    for b in range(batch):  # a different number of video slots per row
+        vm[b, 1:1 + (b % 3)] = 1
+    feats = torch.randn(int(vm.sum()), 16)
+    am = torch.ones_like(ids)
+    for kw in (dict(num_beams=1, do_sample=False), dict(num_beams=3, do_sample=False, length_penalty=1.3),
+               dict(num_beams=5, early_stopping=True), dict(num_beams=1, do_sample=True, top_k=5, temperature=0.8)):
+        kw = dict(kw, max_new_tokens=6, pad_token_id=1, eos_token_id=2)
+        nb = kw["num_beams"]
+        torch.manual_seed(5)
+        want = G.generate(model, ids, am, vm, feats, _stepper=Stepper(), **kw)
+        seen.clear()
+        torch.manual_seed(5)
+        grouped = G._GroupedStepper(Stepper, max(nb, 4 // nb * nb))  # small groups: several per call
+        got = G.generate(model, ids, am, vm, feats, _stepper=grouped, **kw)
+        assert torch.equal(got, want), (kw, got.tolist(), want.tolist())
+        assert len(seen) > 1 and sum(r for r, _ in seen) == batch * nb
+        assert sum(f for _, f in seen) == int(vm.sum()) * nb
+        assert grouped.status.tolist() == [0, int(vm.sum()) * nb]
+    with pytest.raises(RuntimeError):  # a permutation that leaves its group is refused
+        grouped.reorder(torch.arange(batch * nb - 1, -1, -1))
