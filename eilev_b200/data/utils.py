@@ -127,3 +127,19 @@ class DataCollatorForInterleavedVideoSeq2Seq(DataCollatorForSeq2Seq):
             batch["video_input_mask"] = torch.stack(rows)
         batch["pixel_values"] = pixel_values
         return batch
+
+
+def generate_chunks(list_to_chunk: list, chunk_size: int):
+    """Consecutive slices of ``chunk_size`` items, the last one shorter (eilev/data/utils.py:229-231;
+    used by the evaluation scripts to batch prompts)."""
+    start = 0
+    while start < len(list_to_chunk):
+        yield list_to_chunk[start:start + chunk_size]
+        start += chunk_size
+
+
+def parse_timestamp(timestamp: str) -> float:
+    """``hh:mm:ss.cc`` -> seconds (eilev/data/utils.py:234-241).  Same float expression order as the
+    reference, so the results are bit-identical."""
+    hours, minutes, seconds = timestamp.split(":")
+    return float(hours) * 60 * 60 + float(minutes) * 60 + float(seconds)

@@ -699,3 +699,17 @@ def test_grouped_stepper_equals_one_stepper_over_all_rows():
         assert grouped.status.tolist() == [0, int(vm.sum()) * nb]
     with pytest.raises(RuntimeError):  # a permutation that leaves its group is refused
         grouped.reorder(torch.arange(batch * nb - 1, -1, -1))
+
+
+@pytest.mark.parametrize("timestamp,expected", [("00:00:00.560", 0.56), ("00:00:49.15", 49.15),
+                                                ("00:06:50.039", 410.039), ("02:06:50.039", 7610.039)])
+def test_parse_timestamp_reference_table(timestamp, expected):
+    """tests/data/test_utils.py:865-875 of the reference."""
+    from eilev_b200.data.utils import parse_timestamp
+    assert parse_timestamp(timestamp) == expected
+
+
+def test_generate_chunks():
+    from eilev_b200.data.utils import generate_chunks
+    assert list(generate_chunks(list(range(7)), 3)) == [[0, 1, 2], [3, 4, 5], [6]]
+    assert list(generate_chunks([], 3)) == [] and list(generate_chunks([1, 2], 2)) == [[1, 2]]
