@@ -107,8 +107,8 @@ def test_relu_t5_generate_matches_reference_golden_up_to_ties():
     assert seq.tolist() == want  # the oracle reproduces the reference's ids (also pinned in test_oracle.py)
     flips = {}
     for row, (g, w) in enumerate(zip(gen, want)):
-        assert len(g) == len(w) and g[0] == w[0] == cfg.text_config.decoder_start_token_id
-        for t in range(1, len(w)):
+        assert g[0] == w[0] == cfg.text_config.decoder_start_token_id and len(g) <= len(w)
+        for t in range(1, len(g)):  # (a row that flipped to EOS at a tie may end the batch early)
             if g[t] != w[t]:
                 mg = float(margins[t - 1, row])
                 assert mg < 0.1, (row, t, g, w, mg)
