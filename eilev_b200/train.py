@@ -212,3 +212,27 @@ def torch_adamw_reference(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2,
     bc2 = 1 - beta2 ** step
     denom = exp_avg_sq.sqrt() / math.sqrt(bc2) + eps
     param.addcdiv_(exp_avg, denom, value=-lr / bc1)
+
+
+def gather_generated(generated_ids: torch.Tensor, pad_token_id: int, group=None) -> torch.Tensor:
+    """Evaluation-time exchange of ``generate`` results (replicas only + an all-gather of
+    the generated ids; scripts/general/generate_narration_texts.py:120-124 does it with accelerate's
+    ``pad_across_processes(dim=1)`` + ``gather``).  Every rank holds (rows_r, len_r) token ids; they are
+    right-padded with ``pad_token_id`` to the longest length over ranks, rows to the largest row
+    count (the last batch of a sharded eval set may be short), gathered, and the filler rows dropped:
+    the result is the same (sum rows_r, max len_r) tensor on every rank, rank order preserved.
+    Integer bookkeeping over at most a few KB — NCCL's all_gather as is."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return generated_ids
+    world = dist.get_world_size(group)
+    dev = generated_ids.device
+    shape = torch.tensor([generated_ids.shape[0], generated_ids.shape[1]], dtype=torch.long, device=dev)
+    shapes = [torch.empty_like(shape) for _ in range(world)]
+    dist.all_gather(shapes, shape, group=group)
+    rows = [int(s[0]) for s in shapes]
+    max_rows, max_len = max(rows), max(int(s[1]) for s in shapes)
+    padded = torch.full((max_rows, max_len), int(pad_token_id), dtype=generated_ids.dtype, device=dev)
+    padded[:generated_ids.shape[0], :generated_ids.shape[1]] = generated_ids
+    out = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    return torch.cat([o[:r] for o, r in zip(out, rows)], dim=0)

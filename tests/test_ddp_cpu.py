@@ -107,3 +107,29 @@ def test_linear_schedule_matches_hf():
         assert abs(f(step) - opt.param_groups[0]["lr"]) < 1e-12, step
         opt.step()
         sch.step()
+
+
+def _gather_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from eilev_b200.train import gather_generated
+    # rank 0: 3 rows of 4 new tokens; rank 1: the short last batch, 1 row of 6 tokens
+    ids = torch.arange(12).view(3, 4) + 10 if rank == 0 else torch.arange(6).view(1, 6) + 100
+    torch.save(gather_generated(ids, pad_token_id=1), Path(out_dir) / f"gathered{rank}.pt")
+    dist.destroy_process_group()
+
+
+def test_gather_generated_pads_and_concatenates_in_rank_order(tmp_path):
+    """generate_narration_texts.py:120-124 (accelerate pad_across_processes + gather) on 2 gloo ranks."""
+    from eilev_b200.train import gather_generated
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g0, g1 = torch.load(tmp_path / "gathered0.pt"), torch.load(tmp_path / "gathered1.pt")
+    want = torch.full((4, 6), 1, dtype=torch.long)
+    want[:3, :4] = torch.arange(12).view(3, 4) + 10
+    want[3] = torch.arange(6) + 100
+    assert torch.equal(g0, want) and torch.equal(g1, want)
+    solo = torch.arange(6).view(2, 3)
+    assert gather_generated(solo, 0) is solo  # no process group: identity
