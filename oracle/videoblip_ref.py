@@ -15,6 +15,9 @@ branch incl. greedy ``generate``, ``make_golden_beams.py`` for HF beam search / 
 the v1 class (eilev/model/v1.py behind a shim restoring the 4.33.1 prepend contract));
 ``tests/test_oracle.py`` checks this restatement against those fixtures (and against the live
 reference when ``/root/reference`` exists).
+``normalize_frames`` (the image processor's rescale + normalize) is pinned bit-exactly to the HF
+``image_transforms.rescale`` / ``normalize`` functions; the frame resize lives in
+``oracle/pil_resize_ref.py`` (pinned bit-exactly to ``PIL.Image.resize``).
 The reference's own tests pin shapes only (tests/model/test_model_v2.py:53-83,185-186).
 
 Citations: ``v2.py`` = eilev/model/v2.py; ``HF:`` = transformers/models/…
