@@ -129,7 +129,9 @@ def workload_config(world: int, seq_len: int, cuda_graph, dropout: float = 0.1, 
            "global_batch": world, "seq_len": seq_len, "parallelism": f"dp{world}",
            "weights": "random-init (seeded N(0,0.02))",
            "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
-           "dropout": ("recipe: p=%.2f in train mode (Q-Former hidden + attention probs, OPT hidden)" % dropout)
+           "dropout": (("recipe: p=%.2f in train mode (Q-Former hidden + attention probs; the frozen T5's own "
+                        "dropout_rate is NOT applied yet, DESIGN.md section 7)" if lm == "t5" else
+                        "recipe: p=%.2f in train mode (Q-Former hidden + attention probs, OPT hidden)") % dropout)
            if dropout > 0 else "off"}
     if cuda_graph is not None:
         cfg["cuda_graph"] = cuda_graph
