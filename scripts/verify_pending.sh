@@ -6,7 +6,7 @@
 set -uo pipefail
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for t in test_za_fullsize_gpu test_zz_decode_rows_gpu test_zz_frames_gpu test_zz_t5_relu_gpu; do
+for t in test_za_fullsize_gpu test_zb_v1_real_dims_gpu test_zz_decode_rows_gpu test_zz_frames_gpu test_zz_t5_relu_gpu; do
   timeout 600 python -m pytest "tests/$t.py" -q 2>&1 | tail -25 > "gpurun_out/pending_$t.log"
   tail -3 "gpurun_out/pending_$t.log"
 done
