@@ -713,3 +713,41 @@ def test_generate_chunks():
     from eilev_b200.data.utils import generate_chunks
     assert list(generate_chunks(list(range(7)), 3)) == [[0, 1, 2], [3, 4, 5], [6]]
     assert list(generate_chunks([], 3)) == [] and list(generate_chunks([1, 2], 2)) == [[1, 2]]
+
+
+# ------------------------------------------------------------------------------------- frame directory format
+def test_frame_dataset_reads_the_extracted_frame_directory_format(tmp_path):
+    """eilev/data/frame.py:14-72 FrameDataset on a directory laid out as scripts/ego4d/extract_frames.py
+    writes it: narrated_actions.csv + one sub-directory of PNG frames per row."""
+    import csv
+    import numpy as np
+    from PIL import Image
+    from eilev_b200.data.frame import FrameDataset, read_frame_dir
+    rs = np.random.RandomState(0)
+    cols = ["frame_path", "video_uid", "clip_index", "narration_timestamp_sec", "narration_text",
+            "structured_verb", "structured_noun"]
+    rows, frames = [], {}
+    for uid, clip, n in (("vidA", 0, 8), ("vidA", 3, 12), ("vidB", 1, 8)):
+        fp = f"{uid}|{clip}"
+        (tmp_path / fp).mkdir()
+        frames[fp] = rs.randint(0, 256, (n, 20, 28, 3)).astype(np.uint8)
+        for i in range(n):  # unpadded indices: '…|10.png' must come after '…|9.png'
+            Image.fromarray(frames[fp][i]).save(tmp_path / fp / f"{fp}|{i}.png")
+        rows.append(dict(zip(cols, [fp, uid, clip, 1.5 * clip, f"#C C does {clip}", f"verb{clip}", "noun"])))
+    with open(tmp_path / "narrated_actions.csv", "w", newline="") as f:
+        w = csv.DictWriter(f, cols)
+        w.writeheader()
+        w.writerows(rows)
+    ds = FrameDataset(str(tmp_path))
+    assert len(ds) == 3
+    item = ds[1]
+    assert item["video"].dtype == torch.uint8 and item["video"].shape == (3, 12, 20, 28)
+    assert torch.equal(item["video"], torch.from_numpy(frames["vidA|3"]).permute(3, 0, 1, 2))
+    assert item["narration_text"] == "#C C does 3" and item["clip_index"] == "3"  # CSV fields stay strings
+    assert torch.equal(ds["vidB|1"]["video"], read_frame_dir(tmp_path / "vidB|1"))
+    only_b = FrameDataset(str(tmp_path), data_filter=lambda r: r["video_uid"] == "vidB",
+                          transform=lambda it: {**it, "n": it["video"].shape[1]}, return_frames=True)
+    assert len(only_b) == 1 and only_b[0]["n"] == 8
+    assert "video" not in FrameDataset(str(tmp_path), return_frames=False)[0]
+    with pytest.raises(AssertionError):
+        FrameDataset(str(tmp_path / "vidA|0"))  # no narrated_actions.csv
