@@ -751,3 +751,49 @@ def test_frame_dataset_reads_the_extracted_frame_directory_format(tmp_path):
     assert "video" not in FrameDataset(str(tmp_path), return_frames=False)[0]
     with pytest.raises(AssertionError):
         FrameDataset(str(tmp_path / "vidA|0"))  # no narrated_actions.csv
+
+
+def test_uint8_frames_flow_from_the_frame_directory_to_the_collated_batch(tmp_path):
+    """Host pipeline of the uint8 frame path, end to end on CPU: FrameDataset (PNG dirs) ->
+    process(normalize_on_device=True) (resize only, stays uint8) -> interleaved tokeniser -> collator.
+    The collated ``pixel_values`` are the uint8 clips in batch order — what the model's fused
+    normalisation consumes — and normalising them with the oracle equals the stock float path."""
+    import csv
+    import numpy as np
+    from PIL import Image
+    from eilev_b200.data.frame import FrameDataset
+    from eilev_b200.data.utils import (DataCollatorForInterleavedVideoSeq2Seq,
+                                       generate_input_ids_and_labels_from_interleaved as gen)
+    from eilev_b200.model.utils import process
+    from oracle import videoblip_ref as R
+    rs = np.random.RandomState(1)
+    cols = ["frame_path", "video_uid", "clip_index", "narration_timestamp_sec", "narration_text",
+            "structured_verb", "structured_noun"]
+    with open(tmp_path / "narrated_actions.csv", "w", newline="") as f:
+        w = csv.DictWriter(f, cols)
+        w.writeheader()
+        for k in range(3):
+            fp = f"vid|{k}"
+            (tmp_path / fp).mkdir()
+            for i in range(2):
+                Image.fromarray(rs.randint(0, 256, (40, 72, 3)).astype(np.uint8)).save(tmp_path / fp / f"{fp}|{i}.png")
+            w.writerow(dict(zip(cols, [fp, "vid", k, 0.0, "A text", "v", "n"])))
+    proc = _image_only_processor(56)
+    tok = opt_tok()
+    ds = FrameDataset(str(tmp_path))
+
+    def datapoint(clips, on_device):
+        video = torch.stack([ds[c]["video"] for c in clips])  # (N, C, T, H, W) uint8
+        enc = gen(tok, [("A prompt", len(clips))], "A text", 2, True)
+        px = process(proc, video=video, normalize_on_device=on_device)["pixel_values"]
+        return {**enc, "pixel_values": px}
+
+    col = DataCollatorForInterleavedVideoSeq2Seq(tok, pad_to_multiple_of=8)
+    u8 = col([datapoint([0, 1], True), datapoint([2], True)])
+    f32 = col([datapoint([0, 1], False), datapoint([2], False)])
+    assert u8["pixel_values"].dtype == torch.uint8 and u8["pixel_values"].shape == (3, 3, 2, 56, 56)
+    assert f32["pixel_values"].dtype == torch.float32
+    for k in ("input_ids", "attention_mask", "video_input_mask", "labels"):
+        assert torch.equal(u8[k], f32[k])
+    assert int(u8["video_input_mask"].sum()) == 3 * 2  # 3 clips x 2 query tokens
+    assert float((R.normalize_frames(u8["pixel_values"]) - f32["pixel_values"]).abs().max()) < 1e-6
