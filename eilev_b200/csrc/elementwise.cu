@@ -89,7 +89,11 @@ patch_gather_u8_kernel(const unsigned char* __restrict__ px, __nv_bfloat16* __re
     // transformers 4.33.1 (the reference's pin): rescale in float64 (uint8 array * python float),
     // cast to float32, then (x - mean) / std in float32
     const float r = static_cast<float>(static_cast<double>(raw) * nrm.rescale);
-    v = __fdiv_rn(__fsub_rn(r, nrm.mean[c]), nrm.stdv[c]);
+    // selects instead of a dynamic index: kernel-parameter arrays indexed at run time get copied to local memory
+    const int ci = static_cast<int>(c);
+    const float mean = ci == 0 ? nrm.mean[0] : ci == 1 ? nrm.mean[1] : ci == 2 ? nrm.mean[2] : nrm.mean[3];
+    const float stdv = ci == 0 ? nrm.stdv[0] : ci == 1 ? nrm.stdv[1] : ci == 2 ? nrm.stdv[2] : nrm.stdv[3];
+    v = __fdiv_rn(__fsub_rn(r, mean), stdv);
   }
   out[idx] = __float2bfloat16(v);
 }
