@@ -797,3 +797,23 @@ def test_uint8_frames_flow_from_the_frame_directory_to_the_collated_batch(tmp_pa
         assert torch.equal(u8[k], f32[k])
     assert int(u8["video_input_mask"].sum()) == 3 * 2  # 3 clips x 2 query tokens
     assert float((R.normalize_frames(u8["pixel_values"]) - f32["pixel_values"]).abs().max()) < 1e-6
+
+
+def test_forward_signatures_expose_the_collator_keys_to_hf_trainer():
+    """HF Trainer keeps the dataset columns named in ``inspect.signature(model.forward)``
+    (Trainer._set_signature_columns_if_needed) and calls ``model(**inputs)``: the v2 signature must
+    name exactly the interleaved collator's keys (eilev/model/v2.py:132-144), the v1 signature the
+    HF 4.33.1 Blip2 ones (pixel_values first)."""
+    import inspect
+    from eilev_b200.model import v1, v2
+    p2 = list(inspect.signature(v2.VideoBlipForConditionalGeneration.forward).parameters)
+    assert p2 == ["self", "input_ids", "attention_mask", "pixel_values", "video_input_mask", "decoder_input_ids",
+                  "decoder_attention_mask", "output_attentions", "output_hidden_states", "labels", "return_dict"]
+    p1 = list(inspect.signature(v1.VideoBlipForConditionalGeneration.forward).parameters)
+    assert p1 == ["self", "pixel_values", "input_ids", "attention_mask", "decoder_input_ids", "decoder_attention_mask",
+                  "output_attentions", "output_hidden_states", "labels", "return_dict"]
+    g2 = list(inspect.signature(v2.VideoBlipForConditionalGeneration.generate).parameters)
+    assert g2[:5] == ["self", "input_ids", "pixel_values", "video_input_mask", "attention_mask"]  # v2.py:254-261
+    c2 = list(inspect.signature(v2.VideoBlipForConditionalGeneration.classify).parameters)
+    assert c2 == ["self", "prompt_input_ids", "class_input_ids", "prompt_attention_mask", "pixel_values",
+                  "prompt_video_input_mask", "class_attention_mask", "class_batch_size"]  # v2.py:326-336
