@@ -101,9 +101,11 @@ class T5ForConditionalGeneration(PreTrainedModel):
         self.decoder = _T5Stack(cfg, True, cfg.num_decoder_layers)
         self.lm_head = nn.Linear(cfg.d_model, cfg.vocab_size, bias=False)
         # T5 v1.0 ties the head to the embedding (and scales the decoder output by d_model**-0.5);
-        # flan-T5 / v1.1 configs carry tie_word_embeddings=False and keep their own head.  The T5
-        # config's own decision is read through scale_decoder_outputs: transformers 5.x lets
-        # Blip2Config overwrite text_config.tie_word_embeddings, 4.33.1 (the reference's pin) does not.
+        # flan-T5 / v1.1 configs carry tie_word_embeddings=False and keep their own head.  That
+        # decision is read through scale_decoder_outputs: transformers 5.x's T5Config forces
+        # tie_word_embeddings to True and records the configured value there (configuration_t5.py:77-83;
+        # it then leaves a head that IS present in a checkpoint alone), 4.33.1 — the reference's pin —
+        # simply honours tie_word_embeddings.
         if cfg.tie_word_embeddings and E_t5.scale_decoder_outputs(cfg):
             self._tied_weights_keys = {"lm_head.weight": "shared.weight", **type(self)._tied_weights_keys}
         self._pack = PackCache()
