@@ -817,3 +817,31 @@ def test_forward_signatures_expose_the_collator_keys_to_hf_trainer():
     c2 = list(inspect.signature(v2.VideoBlipForConditionalGeneration.classify).parameters)
     assert c2 == ["self", "prompt_input_ids", "class_input_ids", "prompt_attention_mask", "pixel_values",
                   "prompt_video_input_mask", "class_attention_mask", "class_batch_size"]  # v2.py:326-336
+
+
+def test_flan_style_checkpoint_keeps_its_own_head_through_save_and_load(tmp_path):
+    """A flan-T5-style checkpoint (separate lm_head.weight, as the published eilev-blip2-flan-t5-xl has)
+    survives save_pretrained -> from_pretrained here, and — when the reference checkout is present —
+    loads into the real reference class with the same separate head (transformers 5.x un-ties a head
+    that the checkpoint carries)."""
+    import types
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    fx = torch.load(GOLDEN / "small_t5.pt", weights_only=False)
+    cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    m = VideoBlipForConditionalGeneration(cfg)
+    sd = {k: v.clone() for k, v in fx["state_dict"].items()}
+    sd["language_model.lm_head.weight"] = sd["language_model.lm_head.weight"] + 0.5  # a head of its own
+    m.load_state_dict(sd)
+    lm = m.language_model
+    assert lm.lm_head.weight.data_ptr() != lm.shared.weight.data_ptr()
+    m.save_pretrained(tmp_path)
+    m2 = VideoBlipForConditionalGeneration.from_pretrained(tmp_path)
+    assert torch.equal(m2.language_model.lm_head.weight, sd["language_model.lm_head.weight"])
+    assert torch.equal(m2.language_model.shared.weight, sd["language_model.shared.weight"])
+    if Path("/root/reference/eilev/model/v2.py").exists():
+        sys.path.insert(0, "/root/reference")
+        sys.modules.setdefault("pytorchvideo", types.ModuleType("pytorchvideo"))
+        from eilev.model.v2 import VideoBlipForConditionalGeneration as Ref
+        r = Ref.from_pretrained(tmp_path)
+        assert torch.equal(r.language_model.lm_head.weight, sd["language_model.lm_head.weight"])
+        assert torch.equal(r.language_model.shared.weight, sd["language_model.shared.weight"])
