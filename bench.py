@@ -208,6 +208,7 @@ def cpu_reference_step(sd, cfg, batch, trainable):
 
 
 def run_cpu_baseline(cfg, clips: int, steps: int, warmup: int, threads: int | None = None):
+    """The oracle PORT on the host cores (kind = "port"): only used when baseline/_ref is absent."""
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = build_cpu_state_dict(cfg)
@@ -225,19 +226,56 @@ def run_cpu_baseline(cfg, clips: int, steps: int, warmup: int, threads: int | No
                 ms_per_step=dt * 1e3)
 
 
+def run_reference(cfg, clips: int, steps: int, warmup: int, device: str = "cpu"):
+    """The REAL reference class (eilev.model.v2, installed unmodified into baseline/_ref by
+    baseline/install_ref.py) through model(**batch) + loss.backward(): fp32 on all host cores
+    (device="cpu") or bf16 + HF SDPA on the B200 (device="cuda", the library bar).  Falls back to the
+    oracle port on the CPU when the reference is not installed."""
+    from baseline import install_ref
+
+    threads = os.cpu_count() or 1
+    batch = synthetic_batch(1, clips=clips)
+    seq = int(batch["input_ids"].shape[1])
+    if not install_ref.available():
+        if device != "cpu":
+            raise RuntimeError("baseline/_ref is not installed (run baseline/install_ref.py where /root/reference exists)")
+        return run_cpu_baseline(cfg, clips, steps, warmup)
+    from baseline import reference_arm
+
+    dt, loss, build_s = reference_arm.run(cfg, batch, device, steps, warmup, threads)
+    what = ("fp32, %d host threads" % threads) if device == "cpu" else "bf16 weights, HF SDPA attention, one B200"
+    return dict(value=clips / dt, unit="clips/s", cores=threads if device == "cpu" else 0, kind="reference",
+                sample=f"{steps} x fwd+bwd of {clips} clip(s) x {FRAMES} frames (L={seq}) after {warmup} warm-up, full-size "
+                       f"random-init eilev-blip2-opt-2.7b, the reference's own VideoBlipForConditionalGeneration "
+                       f"(baseline/_ref, unmodified) via model(**batch) + loss.backward(), {what}",
+                ms_per_step=dt * 1e3, loss=loss, build_s=build_s, seq_len=seq, clips=clips)
+
+
 def reference_arm(args) -> None:
+    """bench.py --impl reference: ONE timed fwd+bwd of the TRUE benchmark datapoint (17 clips, L = 976)
+    by the real reference class on the host cores — about 2-3 minutes; --steps/--warmup are not
+    multiplied into it (20 steps would take the better part of an hour), and the line says so.
+    --device cuda times the same class on the B200 instead (bf16, SDPA): the library bar."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = full_config()
-    clips = args.cpu_clips
-    res = run_cpu_baseline(cfg, clips, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    cfg = full_config(args.dropout)
+    clips = args.cpu_clips if args.cpu_clips > 0 else CLIPS
+    if args.device == "cuda":
+        steps, warmup = max(1, min(args.steps, 10)), max(2, min(args.warmup, 3))
+    else:
+        steps, warmup = 1, 0
+    res = run_reference(cfg, clips, steps, warmup, args.device)
+    name = workload_config(args.gpus, res.get("seq_len", 976), None, args.dropout)
+    name["workload"] = (f"eilev-blip2-opt-2.7b 16-ctx x 8-frame fwd+bwd bs=1 ({clips} clips, L={res.get('seq_len', 976)}): "
+                        f"{res['sample']}; optimizer step not included")
+    name["steps_requested"] = args.steps
     line = {
         "impl": "reference", "metric": "clips/sec fwd+bwd (8-frame x 17-ctx)", "value": res["value"],
-        "unit": "clips/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(0, min(args.warmup, 1)),
+        "unit": "clips/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, 976, None, args.dropout),
+        "dtype": "f32" if args.device == "cpu" else "bf16", "data": "synthetic", "device": args.device,
+        "config": name,
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -303,12 +341,36 @@ class GemmProfiler:
         torch.cuda.synchronize()
         flops = ms = 0.0
         n = 0
+        self.shapes = []
         for m, nn_, k, s, e, tc in self.records:
             if tc and m >= 4096:  # the ViT-sized launches that dominate the step
                 flops += 2.0 * m * nn_ * k
                 ms += s.elapsed_time(e)
                 n += 1
+                self.shapes.append((m, nn_, k))
         return flops, ms, n
+
+
+def measured_traffic(shapes):
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one
+    ``ncu --set full`` capture per GEMM shape (committed summary profiles/r*_ncu_gemm_traffic.json, written
+    by scripts/ncu_summary.py --traffic), averaged over the launches `roofline.achieved` averages over.
+    Returns (bytes per launch | None, algorithmic bytes per launch, source file | None)."""
+    algo = [2.0 * (m * k + n * k + m * n) for m, n, k in shapes]  # bf16 A + B read once, C written once
+    algo_mean = sum(algo) / len(algo) if algo else None
+    files = sorted((ROOT / "profiles").glob("r*_ncu_gemm_traffic.json"))
+    if not files or not shapes:
+        return None, algo_mean, None
+    table = {tuple(r["mnk"]): float(r["dram_bytes"]) for r in json.loads(files[-1].read_text())["launches"]}
+    got = [table.get((m, n, k)) for m, n, k in shapes]
+    if any(g is None for g in got):
+        # shapes without a capture count with their algorithmic bytes scaled by the mean measured ratio
+        known = [(g, a) for g, a in zip(got, algo) if g is not None]
+        if not known:
+            return None, algo_mean, files[-1].name
+        ratio = sum(g for g, _ in known) / sum(a for _, a in known)
+        got = [g if g is not None else a * ratio for g, a in zip(got, algo)]
+    return sum(got) / len(got), algo_mean, files[-1].name
 
 
 def measure_decode(model, device, batch: int = 1):
@@ -348,6 +410,42 @@ def measure_decode(model, device, batch: int = 1):
     return {"metric": "decode tok/s (greedy, 16-ctx prompt, batch %d)" % batch, "value": batch / per_tok,
             "unit": "tok/s", "ms_per_token": per_tok * 1e3, "prompt_len": n, "batch": batch, "steps": steps,
             "bytes_per_token": 5.293e9 + 327680.0 * (n + 3 + steps / 2) * batch}
+
+
+def measure_generate(model, device, batch: int = 1, new_tokens: int = 64):
+    """Decode tok/s THROUGH THE PUBLIC API: wall-clock of ``model.generate(max_new_tokens=1 + n,
+    min_new_tokens=1 + n)`` minus ``model.generate(max_new_tokens=1, min_new_tokens=1)`` (vision tower +
+    Q-Former + prefill + first token), inputs copied from pinned host memory and the generated ids read
+    back to the host inside each call (eilev/model/v2.py:254-324; samples/eilev_generate_action_narration.py:60-75)."""
+    was_training = model.training
+    model.eval()
+    one = synthetic_batch(7)
+    n = int(one["attention_mask"].sum()) - TARGET_TOKENS
+    host = dict(input_ids=one["input_ids"][:, :n].repeat(batch, 1).pin_memory(),
+                video_input_mask=one["video_input_mask"][:, :n].repeat(batch, 1).pin_memory(),
+                attention_mask=torch.ones(batch, n, dtype=torch.long).pin_memory(),
+                pixel_values=one["pixel_values"].repeat(batch, 1, 1, 1, 1).pin_memory())
+
+    def call(k):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev = {key: v.to(device, non_blocking=True) for key, v in host.items()}
+        ids = model.generate(**dev, max_new_tokens=k, min_new_tokens=k, do_sample=False)
+        ids = ids.cpu()
+        dt = time.perf_counter() - t0
+        assert ids.shape == (batch, k), ids.shape
+        return dt
+
+    call(1 + new_tokens)  # warm-up: packs, graph capture paths, allocator
+    t_long = min(call(1 + new_tokens) for _ in range(3))
+    t_short = min(call(1) for _ in range(3))
+    model.train(was_training)
+    per_tok = (t_long - t_short) / new_tokens
+    return {"value": batch / per_tok, "unit": "tok/s", "ms_per_token": per_tok * 1e3,
+            "generate_ms": t_long * 1e3, "prefill_call_ms": t_short * 1e3, "new_tokens": new_tokens,
+            "h2d_bytes_per_call": sum(v.numel() * v.element_size() for v in host.values()),
+            "d2h_bytes_per_call": batch * (1 + new_tokens) * 8,
+            "how": "model.generate(max_new_tokens=65) minus model.generate(max_new_tokens=1), host wall clock, best of 3"}
 
 
 def measure_decode_t5(model, device, steps: int = 32):
@@ -410,7 +508,9 @@ def gpu_arm(args) -> None:
     if rank == 0 and not args.no_decode and not args.profile and args.lm == "opt":
         # independent workloads (BASELINE configs[4], batch sweep ends), measured before the training loop
         decode = measure_decode(model, device)
+        decode["e2e"] = measure_generate(model, device)
         decode8 = measure_decode(model, device, batch=8)
+        decode8["e2e"] = measure_generate(model, device, batch=8)
         torch.cuda.empty_cache()
     if rank == 0 and not args.no_decode and not args.profile and args.lm == "t5":
         decode = measure_decode_t5(model, device)
@@ -490,6 +590,7 @@ def gpu_arm(args) -> None:
             peaks = json.loads(pfile.read_text())
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        traffic, traffic_algo, traffic_src = measured_traffic(prof.shapes)
         clips_per_s = world * CLIPS * args.steps / (ms * 1e-3)
         e2e_clips = world * CLIPS * args.steps / (ms_e2e * 1e-3)
         h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -507,10 +608,10 @@ def gpu_arm(args) -> None:
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
-                         "traffic_note": "per-shape DRAM bytes from ncu --set full are in profiles/r01_ncu_gemm2cta_fc{1,2}.txt "
-                                         "(fc2 launch: 742 MB measured vs 643 MB algorithmic)",
-                         "kernel": "gemm_tcgen05_kernel (ViT/Q-Former launches with M>=4096)",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_algorithmic": traffic_algo, "traffic_source": traffic_src,
+                         "kernel": "gemm_tcgen05_2cta_kernel (ViT / cross-K|V launches with M>=4096)",
                          "launches": g_n, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"
                          if peaks else "fallback 1400"},
             "step_flops_frac": (FLOPS_PER_DATAPOINT if args.lm == "opt" else t5_flops_per_datapoint())
@@ -527,8 +628,23 @@ def gpu_arm(args) -> None:
                                        "peak": hbm, "unit": "GB/s",
                                        "frac": decode8["bytes_per_token"] / (decode8["ms_per_token"] * 1e-3) / 1e9 / hbm}
                 line["decode_batch8"] = decode8
+        if not args.no_library_bar and world == 1 and args.lm == "opt":
+            # the reference's own class on this B200 (bf16, HF SDPA): the bar the kernels have to beat
+            del trainer
+            model._pack.clear()
+            torch.cuda.empty_cache()
+            try:
+                res = run_reference(cfg, CLIPS, steps=5, warmup=2, device="cuda")
+                line["library_bar"] = {"value": res["value"], "unit": "clips/s", "ms_per_step": res["ms_per_step"],
+                                       "kind": res["kind"], "sample": res["sample"],
+                                       "speedup_device": clips_per_s / res["value"], "speedup_e2e": e2e_clips / res["value"]}
+            except Exception as exc:  # the reference is optional on the box; say why it is missing
+                line["library_bar"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
         if not args.no_cpu_baseline and world == 1 and args.lm == "opt":
-            res = run_cpu_baseline(cfg, clips=args.cpu_clips, steps=1, warmup=0)
+            # bounded sample of the same workload (2 of the 17 clips, L = 120) by the real reference class on
+            # the host cores; `bench.py --impl reference` times the whole 17-clip datapoint
+            res = run_reference(cfg, clips=args.cpu_clips if args.cpu_clips > 0 else 2, steps=2, warmup=0, device="cpu")
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -541,8 +657,14 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline sample step")
+    ap.add_argument("--cpu-clips", type=int, default=0,
+                    help="clips per CPU step: default 17 (the true datapoint) for --impl reference, 2 for the "
+                         "bounded cpu_baseline sample inside the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true", help="skip timing the reference class on the GPU")
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the reference arm (fp32, host cores); cuda = the library "
+                         "bar (the reference class in bf16 with HF SDPA on the B200)")
     ap.add_argument("--profile", action="store_true", help="run one profiler-bracketed step and exit")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA graph")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode tok/s measurement")

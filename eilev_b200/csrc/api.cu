@@ -193,8 +193,8 @@ int vb_embed_splice(const int64_t* input_ids, const int64_t* attention_mask,
                     int64_t n_features, void* stream) {
   if (input_ids == nullptr || embed_tokens == nullptr || slot_index == nullptr || pos_ids == nullptr)
     return fail_msg("vb_embed_splice", "null operand");
-  if (video_mask != nullptr && video_features == nullptr && n_features > 0)
-    return fail_msg("vb_embed_splice", "video_mask without video_features");
+  if (video_mask != nullptr && (video_features == nullptr || n_features <= 0))
+    return fail_msg("vb_embed_splice", "video_mask without video_features (pass a null mask when there are no features)");
   VB_CHECK("vb_embed_splice",
            vb::embed_splice_launch(reinterpret_cast<const long long*>(input_ids),
                                    reinterpret_cast<const long long*>(attention_mask),

@@ -307,26 +307,39 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
     rows = input_ids.shape[0]
     use_graph = bool(kw.get("use_cuda_graph", max_new >= 8)) and (rows <= MAX_DECODE_ROWS or isinstance(stepper, _GroupedStepper))
     dgraph = stepper.graph(rows, dev) if use_graph and max_new > 1 else None
-    generated = torch.empty((rows, 0), dtype=torch.long, device=dev)
+    # Token bookkeeping stays on the device: the new tokens go into a preallocated (rows, max_new)
+    # buffer and the "every row has emitted EOS" test (HF's stopping criterion) is read back only
+    # every `poll` steps, so the host keeps queueing decode steps instead of draining the stream
+    # once per token.  Rows that finished emit pad_id, so the columns decoded past the stopping
+    # step are cut off below and the returned ids equal the step-by-step loop's.
+    out = torch.full((rows, max_new), int(pad_id), dtype=torch.long, device=dev)
+    pad_t = torch.full((rows,), int(pad_id), dtype=torch.long, device=dev)
     unfinished = torch.ones(rows, dtype=torch.bool, device=dev)
     eos_t = torch.tensor(eos_ids, device=dev, dtype=torch.long) if eos_ids else None
+    alive = torch.ones(max_new, dtype=torch.int32, device=dev) if eos_t is not None else None
+    poll = int(kw.get("eos_poll_interval", 8))
+    n_done = max_new
     for step in range(max_new):
-        scores = _process_logits(logits, generated, step, min_new_tokens=min_new, eos_ids=eos_ids,
+        scores = _process_logits(logits, out[:, :step], step, min_new_tokens=min_new, eos_ids=eos_ids,
                                  repetition_penalty=rep, start_token=stepper.start_token)
         if do_sample:
             probs = _warp(scores, temperature, top_k, top_p).softmax(dim=-1)
             nxt = torch.multinomial(probs, 1).squeeze(1)
         else:
             nxt = scores.argmax(dim=-1)
-        nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_id))
-        generated = torch.cat([generated, nxt[:, None]], dim=1)
+        nxt = torch.where(unfinished, nxt, pad_t)
+        out[:, step] = nxt
         if eos_t is not None:
             unfinished = unfinished & ~torch.isin(nxt, eos_t)
-            if not bool(unfinished.any()):
-                break
+            alive[step] = unfinished.sum()
+            if step >= min_new - 1 and ((step + 1) % poll == 0 or step + 1 == max_new):
+                dead = (alive[: step + 1] == 0).nonzero()
+                if dead.numel():  # one device -> host read per `poll` tokens
+                    n_done = int(dead[0]) + 1
+                    break
         if step + 1 < max_new:
             logits = dgraph.step(nxt) if dgraph is not None else stepper.step(nxt)
-    return finish(generated)
+    return finish(out[:, :n_done])
 
 
 def _beam_search(stepper, logits, batch, nb, max_new, min_new, eos_ids, pad_id, rep,

@@ -503,6 +503,8 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         if pixel_values is not None:
             assert video_input_mask is not None  # v2.py:154-157
             video_input_mask = video_input_mask.bool()
+        else:
+            video_input_mask = None  # the reference ignores the mask without pixel values (v2.py:205-213)
         if output_attentions:
             raise NotImplementedError("output_attentions=True is not supported by the fused kernels")
         return_dict = return_dict if return_dict is not None else getattr(self.config, "return_dict", True)
@@ -605,6 +607,8 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         if pixel_values is not None:
             assert video_input_mask is not None  # v2.py:274
             video_input_mask = video_input_mask.bool()
+        else:
+            video_input_mask = None  # no features to splice: the mask is ignored as in v2.py:300-308
         _require_cuda(input_ids, "VideoBlipForConditionalGeneration.generate")
         feats = None
         if pixel_values is not None:
@@ -612,8 +616,10 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
             feats, _, _ = self._video_features(pixel_values, False, train=False)
         if attention_mask is None:
             attention_mask = torch.ones_like(input_ids)
-        return generation.generate(self, input_ids, attention_mask, video_input_mask, feats,
-                                   **generate_kwargs)
+        out = generation.generate(self, input_ids, attention_mask, video_input_mask, feats,
+                                  **generate_kwargs)
+        self.check_splice()  # the decoding loop has already synchronised: the reference's shape error is free here
+        return out
 
     # ------------------------------------------------------------------ classify
     @torch.no_grad()
@@ -646,4 +652,5 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
             prompt_video_input_mask if pixel_values is not None else None, feats,
             class_input_ids, class_attention_mask, class_batch_size)
         self._last_splice_status = status
+        self.check_splice()
         return scores  # f32 (the reference returns the LM dtype; f32 keeps the sums exact)

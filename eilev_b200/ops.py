@@ -370,6 +370,8 @@ def embed_splice(input_ids, attention_mask, video_mask, embed_tokens, video_feat
     if video_mask is not None:
         video_mask = video_mask.to(torch.int64).contiguous()
     n_feat = 0 if video_features is None else video_features.shape[0]
+    if n_feat == 0:
+        video_mask = None  # nothing to splice: the reference ignores the mask without pixel values (v2.py:205-213)
     if video_features is not None:
         _need(video_features, torch.bfloat16, "embed_splice.video_features")
         assert video_features.is_contiguous() and video_features.shape[1] == dim

@@ -35,15 +35,26 @@ def freeze_for_recipe(model) -> None:
     model.enable_input_require_grads()
 
 
+def no_weight_decay(name: str) -> bool:
+    """Trainer.get_decay_parameter_names: parameters of LayerNorm modules and every ``bias`` are
+    excluded from weight decay (transformers/trainer.py ``create_optimizer``)."""
+    low = name.lower()
+    return "bias" in low or "layernorm" in low or "layer_norm" in low
+
+
 class FlatBuffers:
     """f32 master parameters / gradients of the trainable tensors in two contiguous buffers;
     ``param.data`` and ``param.grad`` become views, so autograd accumulates straight into the
     buffer the collective and the optimizer consume."""
 
     def __init__(self, named_params: Iterable[tuple[str, torch.nn.Parameter]]) -> None:
-        self.named = [(n, p) for n, p in named_params if p.requires_grad]
-        if not self.named:
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        if not named:
             raise ValueError("no trainable parameters")
+        # HF Trainer (the reference's optimizer factory, train_v2.py:207-218 -> Trainer.create_optimizer)
+        # applies weight decay to everything EXCEPT LayerNorm parameters and biases.  The decayed
+        # tensors come first, so the fused AdamW runs as two launches over two contiguous segments.
+        self.named = [x for x in named if not no_weight_decay(x[0])] + [x for x in named if no_weight_decay(x[0])]
         dev = self.named[0][1].device
         self.offsets = []
         total = 0
@@ -51,6 +62,8 @@ class FlatBuffers:
             self.offsets.append(total)
             total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
         self.numel = total
+        # first element of the no-decay segment (== numel when every tensor is decayed)
+        self.decay_numel = next((off for (n, _), off in zip(self.named, self.offsets) if no_weight_decay(n)), total)
         self.params = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         with torch.no_grad():
@@ -86,6 +99,7 @@ class DataParallelTrainer:
         self.opt_step = 0
         self.micro = 0
         self._update = update_fn or self._fused_adamw
+        self._pool_fresh = False
         dev = self.flat.params.device
         self._sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self._scale = torch.ones((), dtype=torch.float32, device=dev)
@@ -129,6 +143,7 @@ class DataParallelTrainer:
             self._static_loss_warm = self._fwd_bwd(self._static)
         self.launches_per_graph = _lib.launch_count() - before
         self.flat.zero_grad()  # capture itself does not execute, but keep the contract explicit
+        self._pool_fresh = False  # nothing has been replayed yet
 
     def micro_step(self, batch: dict) -> torch.Tensor:
         """One datapoint: forward + backward, gradients accumulate locally (DDP no_sync)."""
@@ -139,9 +154,13 @@ class DataParallelTrainer:
             for k, v in batch.items():
                 if v.data_ptr() != self._static[k].data_ptr():
                     self._static[k].copy_(v, non_blocking=True)
-            if self.micro % self.grad_accum == 0:  # parameters changed since the last replay
+            if not self._pool_fresh:
+                # the packed bf16 Q-Former operands inside the graphs' pool are older than the
+                # parameters (an optimizer step happened, possibly followed by eager micro-steps
+                # of other shapes): replay the graph that re-packs them
                 graph.replay()
                 loss = self._static_loss
+                self._pool_fresh = True
             else:
                 self._graph_warm.replay()
                 loss = self._static_loss_warm
@@ -176,11 +195,15 @@ class DataParallelTrainer:
         self.grad_norm_and_scale()
         self.opt_step += 1
         lr = self.lr_schedule(self.opt_step) if self.lr_schedule is not None else self.lr
-        self._update(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=lr,
-                     beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
-                     weight_decay=self.weight_decay, step=self.opt_step, grad_scale=self._scale)
+        cut = self.flat.decay_numel
+        for lo, hi, wd in ((0, cut, self.weight_decay), (cut, self.flat.numel, 0.0)):
+            if hi > lo:
+                self._update(self.flat.params[lo:hi], self.flat.grads[lo:hi], self.exp_avg[lo:hi],
+                             self.exp_avg_sq[lo:hi], lr=lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                             weight_decay=wd, step=self.opt_step, grad_scale=self._scale)
         # parameters changed in place through the flat buffer: drop the packed bf16 copies
         self.model._pack.clear()
+        self._pool_fresh = False
         self.flat.zero_grad()
 
     @staticmethod

@@ -65,7 +65,12 @@ def test_two_rank_step_equals_single_process_mean_gradient(tmp_path):
                              update_fn=torch_adamw_reference)
     params = [p for _, p in tr.flat.named]
     ref = [torch.nn.Parameter(p.detach().clone()) for p in params]
-    opt = torch.optim.AdamW(ref, lr=1e-2, weight_decay=0.05)
+    from eilev_b200.train import no_weight_decay
+    decay = [q for (n, _), q in zip(tr.flat.named, ref) if not no_weight_decay(n)]
+    plain = [q for (n, _), q in zip(tr.flat.named, ref) if no_weight_decay(n)]
+    assert decay and plain
+    # HF Trainer's two parameter groups: LayerNorm parameters and biases are not decayed
+    opt = torch.optim.AdamW([dict(params=decay, weight_decay=0.05), dict(params=plain, weight_decay=0.0)], lr=1e-2)
     for step in range(2):
         grads = []
         for rank in range(world):
@@ -94,6 +99,63 @@ def test_flat_buffers_alias_params_and_grads():
     assert all(float(p.grad.min()) == 2.0 for _, p in fb.named)
     fb.zero_grad()
     assert float(fb.grads.abs().sum()) == 0.0
+
+
+def test_weight_decay_groups_match_hf_trainer():
+    """The decayed / undecayed split of the flat buffer equals Trainer.get_decay_parameter_names
+    (what train_v2.py's Trainer builds its AdamW groups from) on the trainable tensors."""
+    from transformers.trainer_pt_utils import get_parameter_names
+    from eilev_b200.train import FlatBuffers, no_weight_decay
+    from eilev_b200.engine.qformer import qformer_param_list
+    from transformers import Blip2Config, Blip2QFormerModel
+    fx = torch.load(GOLDEN / "tiny_opt.pt", weights_only=False)
+    cfg = Blip2Config(**{k: fx["config"][k] for k in ("vision_config", "qformer_config", "text_config", "num_query_tokens")})
+    hf_qformer = Blip2QFormerModel(cfg.qformer_config)  # the module the reference trains (v2.py:116)
+    hf_decay = {"qformer." + n for n in get_parameter_names(hf_qformer, [torch.nn.LayerNorm]) if "bias" not in n}
+    hf_all = {"qformer." + n for n, _ in hf_qformer.named_parameters()}
+    m = _tiny_model()
+    fb = FlatBuffers(qformer_param_list(m))
+    names = [n for n, _ in fb.named]
+    ours_decay = {n for n in names if not no_weight_decay(n)}
+    for n in names:
+        if n in hf_all:
+            assert (n in hf_decay) == (n in ours_decay), n
+    assert "query_tokens" in ours_decay and "language_projection.weight" in ours_decay
+    assert "language_projection.bias" not in ours_decay
+    # decayed tensors are one contiguous prefix of the flat buffer
+    cut = fb.decay_numel
+    for (n, p), off in zip(fb.named, fb.offsets):
+        assert (off < cut) == (not no_weight_decay(n)), n
+    assert 0 < cut < fb.numel
+
+
+def test_stale_graph_pool_flag_forces_the_repack_graph():
+    """after an optimizer step every same-shape micro-step must replay the re-pack graph
+    first, even when eager (other-shape) micro-steps came in between."""
+    from eilev_b200.train import DataParallelTrainer, torch_adamw_reference
+
+    class FakeGraph:
+        def __init__(self, log, name):
+            self.log, self.name = log, name
+
+        def replay(self):
+            self.log.append(self.name)
+
+    m = _tiny_model()
+    tr = DataParallelTrainer(m, lr=1e-2, grad_accum=2, update_fn=torch_adamw_reference)
+    log = []
+    tr._static = {"x": torch.zeros(2, 3)}
+    tr._graph, tr._graph_warm = FakeGraph(log, "repack"), FakeGraph(log, "warm")
+    tr._static_loss = tr._static_loss_warm = torch.zeros(())
+    tr._fwd_bwd = lambda batch: (log.append("eager"), torch.zeros(()))[1]
+    same, other = {"x": torch.ones(2, 3)}, {"x": torch.ones(2, 5)}
+    tr.micro_step(same)    # first after capture: re-pack
+    tr.micro_step(same)    # warm; optimizer step follows (accum 2)
+    tr.micro_step(other)   # eager: the graphs' pool is still stale
+    tr.micro_step(same)    # must re-pack, not replay the warm graph; optimizer step follows
+    tr.micro_step(same)    # re-pack again
+    tr.micro_step(same)    # warm
+    assert log == ["repack", "warm", "eager", "repack", "repack", "warm"], log
 
 
 def test_linear_schedule_matches_hf():

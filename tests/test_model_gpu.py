@@ -559,8 +559,11 @@ def test_trainer_graphs_and_inplace_grad_accumulation_match_plain_autograd():
     assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5  # same kernels, bf16 wgrad operands
     l_tr.append(float(tr.micro_step(batch)))  # second micro-step -> optimizer step
     assert abs(l_tr[0] - l_ref[0]) < 1e-3 and abs(l_tr[1] - l_ref[1]) < 1e-3, (l_tr, l_ref)
-    opt = torch.optim.AdamW([p for p in ref.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.05,
-                            betas=(0.9, 0.999), eps=1e-8)
+    from eilev_b200.train import no_weight_decay
+    tp = [(n, p) for n, p in ref.named_parameters() if p.requires_grad]
+    opt = torch.optim.AdamW([dict(params=[p for n, p in tp if not no_weight_decay(n)], weight_decay=0.05),
+                             dict(params=[p for n, p in tp if no_weight_decay(n)], weight_decay=0.0)],
+                            lr=1e-3, betas=(0.9, 0.999), eps=1e-8)  # HF Trainer's groups
     torch.nn.utils.clip_grad_norm_([p for p in ref.parameters() if p.requires_grad], 1.0)
     opt.step()
     pr = dict(ref.named_parameters())
