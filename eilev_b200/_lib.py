@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("alpha_cols", i64), ("row_group", i64),
         ("epilogue", i32), ("out_dtype", i32), ("backend", i32), ("reserved", i32),
         ("dropout_p", f32), ("reserved2", i32), ("dropout_seed", vp), ("dropout_salt", C.c_uint64),
+        ("ln_stats", vp), ("ln_colsum", vp), ("ln_eps", f32), ("reserved3", i32), ("stats_out", vp), ("stats_zero", vp),
     ]
 
 
@@ -63,6 +64,7 @@ SIGNATURES: dict[str, list] = {
     "vb_gemm_uses_tcgen05": [C.POINTER(GemmArgs)],
     "vb_layernorm": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp],
     "vb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, vp],
+    "vb_row_stats": [vp, vp, i64, i64, i64, vp],
     "vb_attention_fwd": [C.POINTER(AttnArgs), vp],
     "vb_attention_uses_tcgen05": [C.POINTER(AttnArgs)],
     "vb_attention_bwd": [C.POINTER(AttnBwdArgs), vp],
@@ -135,7 +137,7 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "vb_last_error" else C.c_int
-    if handle.vb_abi_version() != 4:
+    if handle.vb_abi_version() != 5:
         raise VbError("ABI version mismatch between eilev_b200/_lib.py and the built library")
     _lib = handle
     return handle

@@ -63,6 +63,18 @@ int vb_gemm(const vb_gemm_args* a, void* stream) {
   const bool elig = vb::gemm_tcgen05_eligible(*a);
   if (a->backend == VB_GEMM_TCGEN05 && !elig)
     return fail_msg("vb_gemm", "shape/alignment not eligible for the tcgen05 path");
+  if ((a->ln_stats != nullptr) != (a->ln_colsum != nullptr))
+    return fail_msg("vb_gemm", "ln_stats and ln_colsum go together");
+  if (a->ln_stats != nullptr || a->stats_out != nullptr || a->stats_zero != nullptr) {
+    if (!elig || a->backend == VB_GEMM_GENERIC)
+      return fail_msg("vb_gemm", "the LayerNorm fold / row statistics need the tcgen05 path");
+    if (a->stats_out != nullptr && (a->out_dtype != VB_BF16 || a->beta != 0.0f))
+      return fail_msg("vb_gemm", "stats_out needs a bf16 output and beta == 0");
+    if (a->stats_zero != nullptr && (a->stats_zero == a->stats_out || a->stats_zero == a->ln_stats || a->row_group != 0))
+      return fail_msg("vb_gemm", "stats_zero must be a buffer this launch neither reads nor fills");
+    if ((reinterpret_cast<uintptr_t>(a->stats_zero) & 7u) != 0 || (reinterpret_cast<uintptr_t>(a->ln_stats) & 7u) != 0 || (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15u) != 0)
+      return fail_msg("vb_gemm", "ln_stats / ln_colsum alignment");
+  }
   if (a->backend != VB_GEMM_GENERIC && elig) VB_CHECK("vb_gemm[tcgen05]", vb::gemm_tcgen05_launch(*a, st(stream)));
   VB_CHECK("vb_gemm[generic]", vb::gemm_generic_launch(*a, st(stream)));
 }
@@ -74,6 +86,12 @@ int vb_layernorm(const void* x, const void* residual, const float* gamma, const 
     return fail_msg("vb_layernorm", "null operand");
   VB_CHECK("vb_layernorm", vb::layernorm_fwd(x, residual, gamma, beta, y, mean, rstd, rows, cols,
                                              ldx, ldr, ldy, eps, st(stream)));
+}
+
+int vb_row_stats(const void* x, float* stats, int64_t rows, int64_t cols, int64_t ldx, void* stream) {
+  if (x == nullptr || stats == nullptr || rows < 0 || cols <= 0 || ldx < cols)
+    return fail_msg("vb_row_stats", "bad arguments");
+  VB_CHECK("vb_row_stats", vb::row_stats_launch(x, stats, rows, cols, ldx, st(stream)));
 }
 
 int vb_layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,

@@ -15,6 +15,8 @@
 //            bf16 P back into TMEM (tcgen05.st), later O * 1/sum -> global.
 //
 // TMEM columns: [0,272) S (fp32) / [0,136) P (bf16x2, in place), [288,416) O.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -93,6 +95,7 @@ struct TaParams {
   int items;           // batch * heads
   int heads, s, d;
   float scale_log2;
+  int pv_n;            // N of the P.V instruction (128, or d rounded up to 16)
 };
 
 __global__ void __launch_bounds__(kTaThreads, 1)
@@ -190,7 +193,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (lane == 0) {
       const uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
       const uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 128) | (1u << 16);  // B is MN-major
+      // B is MN-major; pv_n = 128, or round_up(d, 16) (partial 64-element swizzle atoms) when p.pv_n is set
+      const uint32_t idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(p.pv_n)) | (1u << 16);
       const int k_steps = (p.d + 15) / 16;            // 16-wide steps along d (6 for d = 88)
       const int kv_steps = (p.s + 15) / 16;           // 16-key steps of P.V (17 for S = 257)
       const bool tail16 = p.s > 256;
@@ -390,6 +394,415 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
+// =====================================================================================
+// Ping-pong variant (round 2): two Q tiles in flight per CTA, S / P / O of each tile in its own
+// 256-column TMEM slot, so the tensor pipe works on one tile while the other tile's softmax runs.
+//
+//   slot s (columns [256 s, 256 s + 256)):  S = Q K^T over keys 0..255 (fp32, 256 columns)
+//       -> P (bf16 pairs) written IN PLACE into [0, 128) by the row's own thread while it streams S,
+//       -> O = P V accumulates into [128, 128 + dpad) (dead S columns), dpad = d rounded up to 16 <= 96,
+//       -> the 257th key (ViT-g: 256 patches + CLS) does not fit the slot: its score q.k_256 is
+//          computed by the softmax warp itself with mma.sync straight from the swizzled Q / K tiles
+//          in shared memory, and its probability goes into the 8 spare columns [224, 232) as one
+//          more 16-key block of P for the last P.V instruction.
+//   warp 0      TMA producer (Q tiles double-buffered; K and V single-buffered per (frame, head))
+//   warp 1      MMA issuer: QK^T of tile g, then P.V of tile g-1 (the other slot)
+//   warps 4-7   softmax + epilogue of the tiles in slot 0; warps 8-11: slot 1.  One thread owns one
+//               query row (TMEM lane): pass 1 = row maximum, pass 2 = exp2 / sum / pack / store P,
+//               epilogue = O * (1 / sum) -> global.  No cross-warp exchange.
+// Shape class: non-causal, unmasked, 64 <= S <= 257, d <= 96 (the old single-slot kernel above keeps
+// S <= 272 / d <= 128).
+constexpr int kPpColO = 128;
+constexpr int kPpColTail = 224;
+
+struct PpParams {
+  __nv_bfloat16* o;
+  long long o_rs;
+  int items, heads, s, d;
+  int dpad;            // d rounded up to 16: N of the P.V instruction
+  float scale_log2;
+};
+
+VB_DEVICE void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_addr));
+}
+VB_DEVICE void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kTaThreads, 1)
+attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const PpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                               // [2 buffers][2 chunks][128 rows][128 B]
+  uint8_t* sK = sQ + 4 * kTaChunkBytesQ;            // [2 chunks][272 rows][128 B]
+  uint8_t* sV = sK + 2 * kTaChunkBytesK;            // [2 chunks][272 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kTaChunkBytesK);
+  uint64_t* q_full = bars;          // [2]  TMA bytes of a Q tile
+  uint64_t* q_empty = bars + 2;     // [2]  QK^T retired (1) + the slot's 4 softmax warps read the tile (4)
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_empty = bars + 5;     // last QK^T of the item retired (1) + 4 warps per tile read row 256
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 8;      // [2]
+  uint64_t* p_ready = bars + 10;    // [2]  4 softmax warps
+  uint64_t* o_full = bars + 12;     // [2]
+  uint64_t* slot_free = bars + 14;  // [2]  4 softmax warps finished reading O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.s + kTaQRows - 1) / kTaQRows;
+  const bool has_tail = p.s > 256;           // exactly one key (index 256) beyond the slot
+  const int s_main = has_tail ? 256 : p.s;   // keys whose scores live in TMEM
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 5);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_free[i], 4);
+    }
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1 + 4 * m_tiles);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0};
+      int g = 0;  // running Q tile counter -> buffer = slot = g & 1
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int b = item / p.heads, h = item % p.heads;
+        const int row0 = b * p.s;
+        auto load_q = [&](int t) {
+          const int buf = g & 1;
+          mbar_wait(&q_empty[buf], q_ph[buf] ^ 1u);
+          q_ph[buf] ^= 1u;
+          mbar_expect_tx(&q_full[buf], 2 * kTaChunkBytesQ);
+          uint8_t* dst = sQ + buf * 2 * kTaChunkBytesQ;
+          tma_load_3d(dst, &tmap_q, &q_full[buf], 0, h, row0 + t * kTaQRows);
+          tma_load_3d(dst + kTaChunkBytesQ, &tmap_q, &q_full[buf], 64, h, row0 + t * kTaQRows);
+          ++g;
+        };
+        mbar_wait(k_empty, k_ph ^ 1u);
+        k_ph ^= 1u;
+        mbar_expect_tx(k_full, 2 * kTaChunkBytesK);
+        for (int c = 0; c < 2; ++c)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sK + c * kTaChunkBytesK + hf * kTaHalf * 128, &tmap_k, k_full, c * 64, h,
+                        row0 + hf * kTaHalf);
+        load_q(0);
+        if (m_tiles > 1) load_q(1);
+        mbar_wait(v_empty, v_ph ^ 1u);
+        v_ph ^= 1u;
+        mbar_expect_tx(v_full, 2 * kTaChunkBytesK);
+        for (int c = 0; c < 2; ++c)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(sV + c * kTaChunkBytesK + hf * kTaHalf * 128, &tmap_v, v_full, c * 64, h,
+                        row0 + hf * kTaHalf);
+        for (int t = 2; t < m_tiles; ++t) load_q(t);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 256);
+      const uint32_t idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(p.dpad)) | (1u << 16);  // B MN-major
+      const int k_steps = (p.d + 15) / 16;
+      const int kv_main = (s_main + 15) / 16;          // 16-key blocks of P in columns [0, 128)
+      uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0}, free_ph[2] = {0, 0}, p_ph[2] = {0, 0};
+      bool have_prev = false, prev_first = false, prev_last = false;
+      int prev_slot = 0;
+      auto issue_pv = [&]() {
+        const int slot = prev_slot;
+        if (prev_first) {
+          mbar_wait(v_full, v_ph);
+          v_ph ^= 1u;
+        }
+        mbar_wait(&p_ready[slot], p_ph[slot]);
+        p_ph[slot] ^= 1u;
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + slot * 256;
+        for (int js = 0; js < kv_main; ++js) {
+          const uint64_t b_desc = umma_desc_mn_sw128(smem_u32(sV + js * 16 * 128), kTaChunkBytesK);
+          umma_bf16_ts(t0 + kPpColO, t0 + js * 8, b_desc, idesc_o, js != 0 ? 1u : 0u);
+        }
+        if (has_tail) {  // keys 256..271: only key 256 has a non-zero probability
+          const uint64_t b_desc = umma_desc_mn_sw128(smem_u32(sV + 256 * 128), kTaChunkBytesK);
+          umma_bf16_ts(t0 + kPpColO, t0 + kPpColTail, b_desc, idesc_o, 1u);
+        }
+        if (prev_last) umma_commit(v_empty);
+        umma_commit(&o_full[slot]);
+      };
+      int g = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        mbar_wait(k_full, k_ph);
+        k_ph ^= 1u;
+        for (int t = 0; t < m_tiles; ++t) {
+          const int slot = g & 1;
+          mbar_wait(&q_full[slot], q_ph[slot]);
+          q_ph[slot] ^= 1u;
+          mbar_wait(&slot_free[slot], free_ph[slot] ^ 1u);  // epilogue of tile g-2 has drained O
+          free_ph[slot] ^= 1u;
+          tc_fence_after();
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const int c = ks >> 2, kk = ks & 3;
+            const uint64_t a_desc =
+                umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
+            umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&q_empty[slot]);
+          if (t == m_tiles - 1) umma_commit(k_empty);
+          umma_commit(&s_full[slot]);
+          if (have_prev) issue_pv();
+          have_prev = true;
+          prev_slot = slot;
+          prev_first = (t == 0);
+          prev_last = (t == m_tiles - 1);
+          ++g;
+        }
+      }
+      if (have_prev) issue_pv();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax + epilogue (one slot per warp group)
+    const int wg = (warp - 4) >> 2;  // == slot == Q buffer
+    const int quarter = warp & 3;
+    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + wg * 256;
+    const int n_chunks = (s_main + 31) / 32;   // 32-key chunks of S (8 for ViT-g)
+    const int k_steps = (p.d + 15) / 16;
+    const int n16 = p.dpad / 16;
+    uint32_t q_ph = 0, s_ph = 0, o_ph = 0;
+    int g = 0, n_item = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n_item) {
+      const int b = item / p.heads, h = item % p.heads;
+      for (int t = 0; t < m_tiles; ++t, ++g) {
+        if ((g & 1) != wg) continue;
+        const int qi = t * kTaQRows + r_in_tile;
+        const bool warp_has_rows = (t * kTaQRows + quarter * 32) < p.s;
+        // ---- score of key 256 for this warp's 32 rows: mma.sync from the swizzled Q / K tiles
+        mbar_wait(&q_full[wg], q_ph);
+        q_ph ^= 1u;
+        float tail = -INFINITY;
+        if (has_tail) {
+          mbar_wait(k_full, static_cast<uint32_t>(n_item & 1));
+          if (warp_has_rows) {
+            const uint32_t q_base = smem_u32(sQ + wg * 2 * kTaChunkBytesQ);
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            for (int ks = 0; ks < k_steps; ++ks) {
+              const int c = ks >> 2, kk = ks & 3;
+              uint32_t b0 = 0u, b1 = 0u;
+              if (lane < 4) {  // B fragment column n = 0 <-> key 256 (row 256: swizzle phase 0)
+                const uint8_t* kr = sK + c * kTaChunkBytesK + 256 * 128 + kk * 32 + lane * 4;
+                b0 = *reinterpret_cast<const uint32_t*>(kr);
+                b1 = *reinterpret_cast<const uint32_t*>(kr + 16);
+              }
+#pragma unroll
+              for (int rb = 0; rb < 2; ++rb) {
+                const int row = quarter * 32 + rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int unit = 2 * kk + (lane >> 4);
+                uint32_t a[4];
+                ldmatrix_x4(a, q_base + c * kTaChunkBytesQ + row * 128 + ((unit ^ (row & 7)) << 4));
+                mma_bf16_16816(acc[rb], a, b0, b1);
+              }
+            }
+            // column 0 of the C fragments sits in lanes 0, 4, ..., 28 (c0: row lane/4, c2: row lane/4 + 8)
+            const int src = (lane & 7) * 4;
+            const float v00 = __shfl_sync(0xffffffffu, acc[0][0], src);
+            const float v02 = __shfl_sync(0xffffffffu, acc[0][2], src);
+            const float v10 = __shfl_sync(0xffffffffu, acc[1][0], src);
+            const float v12 = __shfl_sync(0xffffffffu, acc[1][2], src);
+            tail = lane < 16 ? ((lane & 8) ? v02 : v00) : ((lane & 8) ? v12 : v10);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&q_empty[wg]);
+          mbar_arrive(k_empty);
+        }
+        mbar_wait(&s_full[wg], s_ph);
+        s_ph ^= 1u;
+        tc_fence_after();
+        float inv_sum = 0.0f;
+        if (warp_has_rows) {
+          // ---- pass 1: row maximum (two 32-column loads in flight)
+          float m0 = tail, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          for (int ch = 0; ch < n_chunks; ch += 2) {
+            uint32_t r0[32], r1[32];
+            const bool two = ch + 1 < n_chunks;
+            tmem_ld_32(t_row + ch * 32, r0);
+            if (two) tmem_ld_32(t_row + (ch + 1) * 32, r1);
+            tmem_ld_wait();
+            if (ch * 32 + 32 <= s_main) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                m0 = fmaxf(m0, __uint_as_float(r0[j]));
+                m1 = fmaxf(m1, __uint_as_float(r0[j + 1]));
+                m2 = fmaxf(m2, __uint_as_float(r0[j + 2]));
+                m3 = fmaxf(m3, __uint_as_float(r0[j + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ch * 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r0[j]));
+            }
+            if (two) {
+              if (ch * 32 + 64 <= s_main) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  m0 = fmaxf(m0, __uint_as_float(r1[j]));
+                  m1 = fmaxf(m1, __uint_as_float(r1[j + 1]));
+                  m2 = fmaxf(m2, __uint_as_float(r1[j + 2]));
+                  m3 = fmaxf(m3, __uint_as_float(r1[j + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (ch * 32 + 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r1[j]));
+              }
+            }
+          }
+          const float mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
+          // ---- pass 2: p = 2^(s*c - max*c), row sum, bf16 P over the consumed S columns; the load of
+          // chunk ch+1 is in flight while chunk ch is exponentiated
+          float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+          auto chunk = [&](const uint32_t (&r)[32], int ch) {
+            uint32_t pk[16];
+            if (ch * 32 + 32 <= s_main) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs));
+                const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs));
+                const float p2 = exp2f(fmaf(__uint_as_float(r[2 * j + 2]), p.scale_log2, -mxs));
+                const float p3 = exp2f(fmaf(__uint_as_float(r[2 * j + 3]), p.scale_log2, -mxs));
+                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                pk[j] = pack_bf16x2(p0, p1);
+                pk[j + 1] = pack_bf16x2(p2, p3);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int k0 = ch * 32 + 2 * j;
+                const float p0 = k0 < s_main ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs)) : 0.0f;
+                const float p1 = k0 + 1 < s_main ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs)) : 0.0f;
+                s0 += p0; s1 += p1;
+                pk[j] = pack_bf16x2(p0, p1);
+              }
+            }
+            // P columns [16 ch, 16 ch + 16) alias S columns of chunk ch / 2 <= ch: already consumed
+            tmem_st_16(t_row + ch * 16, pk);
+          };
+          {
+            uint32_t ra[32], rb[32];
+            tmem_ld_32(t_row, ra);
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+              tmem_ld_wait();
+              if (ch + 1 < n_chunks) tmem_ld_32(t_row + (ch + 1) * 32, rb);
+              chunk(ra, ch);
+              if (ch + 1 < n_chunks) {
+                tmem_ld_wait();
+                if (ch + 2 < n_chunks) tmem_ld_32(t_row + (ch + 2) * 32, ra);
+                chunk(rb, ch + 1);
+              }
+            }
+          }
+          if (has_tail) {
+            const float pt = exp2f(fmaf(tail, p.scale_log2, -mxs));
+            s0 += pt;
+            uint32_t pk8[8] = {pack_bf16x2(pt, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st_8(t_row + kPpColTail, pk8);
+          }
+          inv_sum = 1.0f / ((s0 + s1) + (s2 + s3));
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[wg]);
+        // ---- epilogue: O * 1/sum -> global
+        mbar_wait(&o_full[wg], o_ph);
+        o_ph ^= 1u;
+        tc_fence_after();
+        if (warp_has_rows) {
+          __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.s + qi) * p.o_rs + h * p.d;
+          for (int gi = 0; gi < n16; gi += 2) {
+            uint32_t r0[16], r1[16];
+            const bool two = gi + 1 < n16;
+            tmem_ld_16(t_row + kPpColO + gi * 16, r0);
+            if (two) tmem_ld_16(t_row + kPpColO + (gi + 1) * 16, r1);
+            tmem_ld_wait();
+            if (qi < p.s) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 8) {
+                const int c0 = gi * 16 + j;
+                if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
+                  uint4 u;
+                  u.x = pack_bf16x2(__uint_as_float(r0[j]) * inv_sum, __uint_as_float(r0[j + 1]) * inv_sum);
+                  u.y = pack_bf16x2(__uint_as_float(r0[j + 2]) * inv_sum, __uint_as_float(r0[j + 3]) * inv_sum);
+                  u.z = pack_bf16x2(__uint_as_float(r0[j + 4]) * inv_sum, __uint_as_float(r0[j + 5]) * inv_sum);
+                  u.w = pack_bf16x2(__uint_as_float(r0[j + 6]) * inv_sum, __uint_as_float(r0[j + 7]) * inv_sum);
+                  *reinterpret_cast<uint4*>(orow + c0) = u;
+                }
+              }
+              if (two) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                  const int c0 = (gi + 1) * 16 + j;
+                  if (c0 < p.d) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(r1[j]) * inv_sum, __uint_as_float(r1[j + 1]) * inv_sum);
+                    u.y = pack_bf16x2(__uint_as_float(r1[j + 2]) * inv_sum, __uint_as_float(r1[j + 3]) * inv_sum);
+                    u.z = pack_bf16x2(__uint_as_float(r1[j + 4]) * inv_sum, __uint_as_float(r1[j + 5]) * inv_sum);
+                    u.w = pack_bf16x2(__uint_as_float(r1[j + 6]) * inv_sum, __uint_as_float(r1[j + 7]) * inv_sum);
+                    *reinterpret_cast<uint4*>(orow + c0) = u;
+                  }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();  // O reads retire before the next QK^T overwrites the slot
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_free[wg]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -440,6 +853,16 @@ bool attention_tcgen05_eligible(const vb_attn_args& a) {
   return true;
 }
 
+// The two-slot ping-pong kernel takes d <= 96 (O fits 96 columns) and S <= 257 (at most one key beyond the
+// 256-column S slot).  VB_ATTN_PP=0 keeps the single-slot kernel (A/B measurements).
+static bool attention_pp_eligible(const vb_attn_args& a) {
+  static const bool on = [] {
+    const char* e = std::getenv("VB_ATTN_PP");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on && a.d <= 96 && a.sq <= 257;
+}
+
 cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream) {
   CUtensorMap tq, tk, tv;
   const long long rows = a.batch * a.sq;
@@ -452,6 +875,33 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
     if (e != cudaSuccess) return e;
     attr = true;
   }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  if (attention_pp_eligible(a)) {
+    static bool attr_pp = false;
+    if (!attr_pp) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTaSmem);
+      if (e != cudaSuccess) return e;
+      attr_pp = true;
+    }
+    PpParams pp;
+    pp.o = reinterpret_cast<__nv_bfloat16*>(a.o);
+    pp.o_rs = a.o_rs;
+    pp.items = static_cast<int>(a.batch * a.heads);
+    pp.heads = static_cast<int>(a.heads);
+    pp.s = static_cast<int>(a.sq);
+    pp.d = static_cast<int>(a.d);
+    pp.dpad = (pp.d + 15) / 16 * 16;
+    pp.scale_log2 = a.scale * 1.4426950408889634f;
+    const int grid_pp = pp.items < sms ? pp.items : sms;
+    attn_tcgen05_pp_kernel<<<grid_pp, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, pp);
+    return cudaGetLastError();
+  }
   TaParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(a.o);
   p.o_rs = a.o_rs;
@@ -460,13 +910,8 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
   p.s = static_cast<int>(a.sq);
   p.d = static_cast<int>(a.d);
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  p.pv_n = 128;
+  if (const char* e = std::getenv("VB_ATTN_PV_NPAD"); e != nullptr && e[0] == '1') p.pv_n = (p.d + 15) / 16 * 16;
   const int grid = p.items < sms ? p.items : sms;
   attn_tcgen05_kernel<<<grid, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, p);
   return cudaGetLastError();

@@ -22,7 +22,47 @@ struct EpiParams {
   int tma_store;             // 1: bf16 tile staged in smem and written with one TMA store per slab
   int epilogue;
   int out_f32;
+  // LayerNorm folded into this GEMM (vb_gemm_args.ln_stats / ln_colsum): per-row [sum, sum of squares]
+  // of A's rows over K columns; out = rstd * acc - rstd * mean * colsum[n] + bias[n]
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_inv_k, ln_eps;
+  float* stats_out;          // per stored row [sum, sum of squares] of the bf16 output, f32 atomics
+  float* stats_zero;         // (M, 2) buffer cleared by the tiles of the first column block
 };
+
+// (rstd, -rstd * mean) of row `row` from the [sum, sum of squares] pair
+VB_DEVICE float2 ln_fold_coeffs(const EpiParams& p, long long row) {
+  const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
+  const float mean = st.x * p.ln_inv_k;
+  const float var = fmaxf(fmaf(-mean, mean, st.y * p.ln_inv_k), 0.0f);
+  const float rstd = rsqrtf(var + p.ln_eps);
+  return make_float2(rstd, -rstd * mean);
+}
+// acc[j] <- rstd * acc[j] - rstd * mean * colsum[col0 + j]
+VB_DEVICE void ln_fold_apply(const EpiParams& p, long long row, long long col0, float (&v)[16]) {
+  const float2 c = ln_fold_coeffs(p, row);
+  if (col0 + 16 <= p.n) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + j));
+      v[j] = fmaf(v[j], c.x, c.y * cs.x);
+      v[j + 1] = fmaf(v[j + 1], c.x, c.y * cs.y);
+      v[j + 2] = fmaf(v[j + 2], c.x, c.y * cs.z);
+      v[j + 3] = fmaf(v[j + 3], c.x, c.y * cs.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < p.n) v[j] = fmaf(v[j], c.x, c.y * __ldg(p.ln_colsum + col0 + j));
+  }
+}
+// sum / sum of squares of the two bf16 values packed in `u` (the values as they are stored)
+VB_DEVICE void stats_accum(uint32_t u, float& s, float& q) {
+  const float2 f = unpack_bf16x2(u);
+  s += f.x + f.y;
+  q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+}
 
 // One thread finishes 16 consecutive columns of one row.
 VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
@@ -37,6 +77,8 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
   const bool full = (col0 + 16 <= p.n);
+  if (p.stats_zero != nullptr && col0 == 0) *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
+  if (p.ln_stats != nullptr) ln_fold_apply(p, row, col0, v);
   if (p.bias != nullptr) {
     if (full) {
 #pragma unroll
@@ -102,6 +144,7 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
     }
   } else {
     __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row * p.ldc + col0;
+    float st_s = 0.0f, st_q = 0.0f;
     if (full) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -120,13 +163,25 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
         o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
         o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
         *reinterpret_cast<uint4*>(c + 8 * h) = o;
+        if (p.stats_out != nullptr) {
+          stats_accum(o.x, st_s, st_q); stats_accum(o.y, st_s, st_q);
+          stats_accum(o.z, st_s, st_q); stats_accum(o.w, st_s, st_q);
+        }
       }
     } else {
       for (int j = 0; j < 16; ++j)
         if (col0 + j < p.n) {
           float o = v[j] + (p.beta != 0.0f ? p.beta * __bfloat162float(c[j]) : 0.0f);
-          c[j] = __float2bfloat16(o);
+          const __nv_bfloat16 ob = __float2bfloat16(o);
+          c[j] = ob;
+          const float of = __bfloat162float(ob);
+          st_s += of;
+          st_q = fmaf(of, of, st_q);
         }
+    }
+    if (p.stats_out != nullptr) {
+      atomicAdd(p.stats_out + 2 * out_row, st_s);
+      atomicAdd(p.stats_out + 2 * out_row + 1, st_q);
     }
   }
 }
@@ -138,10 +193,11 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
 // `slab_row` points at this thread's 128-byte row of a [128 rows][64 cols] SWIZZLE_128B slab,
 // `row7` = row & 7 (swizzle phase), `c16` = 16-column chunk inside the slab (0..3).
 VB_DEVICE void epilogue_row16_staged(const EpiParams& p, long long row, long long col0, const uint32_t (&acc)[16],
-                                     uint8_t* slab_row, int row7, int c16, bool has_res) {
+                                     uint8_t* slab_row, int row7, int c16, bool has_res, float& st_s, float& st_q) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.ln_stats != nullptr && row < p.m) ln_fold_apply(p, row, col0, v);
   if (p.bias != nullptr) {
     if (col0 + 16 <= p.n) {
 #pragma unroll
@@ -189,6 +245,10 @@ VB_DEVICE void epilogue_row16_staged(const EpiParams& p, long long row, long lon
     o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
     o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
     *cell = o;
+    if (p.stats_out != nullptr && col0 + 8 * h + 8 <= p.n) {  // n % 8 == 0: whole 8-column groups
+      stats_accum(o.x, st_s, st_q); stats_accum(o.y, st_s, st_q);
+      stats_accum(o.z, st_s, st_q); stats_accum(o.w, st_s, st_q);
+    }
   }
 }
 

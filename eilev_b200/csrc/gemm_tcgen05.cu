@@ -290,6 +290,12 @@ void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {
   ep.drop_salt = a.dropout_salt;
   ep.drop_thresh = drop ? dropout_threshold(a.dropout_p) : 0u;
   ep.drop_scale = drop ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+  ep.ln_stats = a.ln_colsum != nullptr ? a.ln_stats : nullptr;
+  ep.ln_colsum = a.ln_colsum;
+  ep.ln_inv_k = 1.0f / static_cast<float>(a.k);
+  ep.ln_eps = a.ln_eps;
+  ep.stats_out = a.stats_out;
+  ep.stats_zero = a.stats_zero;
 }
 
 cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t stream);

@@ -159,6 +159,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int row_in = quarter * 32 + lane;              // row inside this CTA's 128 rows
         const long long tile_row0 = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM;
         const bool has_res = p.residual != nullptr;
+        float st_s = 0.0f, st_q = 0.0f;  // row statistics of this thread's 128 output columns
 #pragma unroll 1
         for (int sl = 0; sl < 2; ++sl) {
           const long long col_slab = static_cast<long long>(n_blk) * BN + half * 128 + sl * 64;
@@ -195,8 +196,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (slab_live) {
               uint8_t* slab_row = slab + row_in * 128;
-              epilogue_row16_staged(p, row, col_slab + c16 * 16, r0, slab_row, row_in & 7, c16, has_res);
-              epilogue_row16_staged(p, row, col_slab + (c16 + 1) * 16, r1, slab_row, row_in & 7, c16 + 1, has_res);
+              epilogue_row16_staged(p, row, col_slab + c16 * 16, r0, slab_row, row_in & 7, c16, has_res, st_s, st_q);
+              epilogue_row16_staged(p, row, col_slab + (c16 + 1) * 16, r1, slab_row, row_in & 7, c16 + 1, has_res,
+                                    st_s, st_q);
             }
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
@@ -205,6 +207,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (slab_live) tma_store_2d(&tmap_c, slab, static_cast<int>(col_slab), static_cast<int>(tile_row0));
             bulk_commit();  // (an empty group keeps the wait_group bookkeeping uniform)
           }
+        }
+        if (p.stats_zero != nullptr && n_blk == 0 && half == 0 && row < p.m)
+          *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
+        if (p.stats_out != nullptr && row < p.m) {
+          atomicAdd(p.stats_out + 2 * row, st_s);
+          atomicAdd(p.stats_out + 2 * row + 1, st_q);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         continue;

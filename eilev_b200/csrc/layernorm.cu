@@ -328,4 +328,50 @@ cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, c
   return layernorm_bwd_launch(p, s);
 }
 
+
+// ------------------------------------------------------------------ row statistics
+// stats[row] = [sum_c x[row, c], sum_c x[row, c]^2] (f32): the input of a LayerNorm folded into
+// the consuming GEMM (vb_gemm_args.ln_stats) when the producer of x is not a GEMM epilogue.
+// One warp per row; read-only pass (2 B per element).
+__global__ void __launch_bounds__(kLnWarps * 32)
+row_stats_kernel(const __nv_bfloat16* x, float* stats, long long rows, long long cols, long long ldx) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * ldx;
+  float s = 0.0f, q = 0.0f;
+  if (cols % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    for (long long v = lane; v < cols / 8; v += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        s += f.x + f.y;
+        q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+      }
+    }
+  } else {
+    for (long long c = lane; c < cols; c += 32) {
+      const float f = __bfloat162float(xr[c]);
+      s += f;
+      q = fmaf(f, f, q);
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    stats[2 * row] = s;
+    stats[2 * row + 1] = q;
+  }
+}
+
+cudaError_t row_stats_launch(const void* x, float* stats, long long rows, long long cols, long long ldx,
+                             cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
+  row_stats_kernel<<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats, rows, cols, ldx);
+  return cudaGetLastError();
+}
+
 }  // namespace vb

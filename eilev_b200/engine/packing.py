@@ -74,3 +74,16 @@ def pad_k(w: torch.Tensor, kpad: int) -> torch.Tensor:
 def transposed(w_bf16: torch.Tensor) -> torch.Tensor:
     """(N, K) bf16 -> (K, N) bf16 with a 16-byte aligned row stride (dgrad operand)."""
     return ops.transpose(w_bf16)
+
+
+def ln_fold(w: torch.Tensor, b: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor):
+    """Weights of ``LayerNorm(x) @ w.T + b`` for the GEMM that consumes the UN-normalised x
+    (vb_gemm_args.ln_stats): LN(x) w^T + b = rstd (x (w*gamma)^T) - rstd mean colsum(w*gamma) + (b + w beta).
+    Returns (w*gamma as the bf16 operand, b + w beta f32, colsum f32 of the bf16-rounded operand, so the
+    mean term cancels against exactly what the tensor cores multiply).  One-time weight preparation."""
+    wf = w.detach().float()
+    wg = (wf * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+    bias = wf @ beta.detach().float()
+    if b is not None:
+        bias = bias + b.detach().float()
+    return wg, bias.contiguous(), wg.float().sum(dim=1).contiguous()

@@ -14,11 +14,17 @@ from __future__ import annotations
 import torch
 
 from .. import ops
-from .packing import PackCache, bf16, f32, pad_k
+from .packing import PackCache, bf16, f32, ln_fold, pad_k
 
 
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+def fold_layernorm_enabled() -> bool:
+    """VB_VIT_LN_FOLD=0 keeps the stand-alone LayerNorm kernel in the encoder layers (A/B measurements)."""
+    import os
+    return os.environ.get("VB_VIT_LN_FOLD", "1") != "0"
 
 
 def pack_vision(model, cache: PackCache):
@@ -39,16 +45,27 @@ def pack_vision(model, cache: PackCache):
             "post_b": f32(model.post_layernorm.bias),
             "layers": [],
         }
+        # LayerNorm folded into the consuming GEMM (vb_gemm_args.ln_stats): layer_norm1 -> qkv and
+        # layer_norm2 -> fc1 never write the normalised activations; the shapes must take the tcgen05 path
+        w["fold"] = fold_layernorm_enabled() and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0
         for layer in model.encoder.layers:
-            w["layers"].append(dict(
-                ln1_g=f32(layer.layer_norm1.weight), ln1_b=f32(layer.layer_norm1.bias),
-                qkv_w=bf16(layer.self_attn.qkv.weight),
-                qkv_b=None if layer.self_attn.qkv.bias is None else f32(layer.self_attn.qkv.bias),
+            lw = dict(
                 proj_w=bf16(layer.self_attn.projection.weight), proj_b=f32(layer.self_attn.projection.bias),
-                ln2_g=f32(layer.layer_norm2.weight), ln2_b=f32(layer.layer_norm2.bias),
-                fc1_w=bf16(layer.mlp.fc1.weight), fc1_b=f32(layer.mlp.fc1.bias),
                 fc2_w=bf16(layer.mlp.fc2.weight), fc2_b=f32(layer.mlp.fc2.bias),
-            ))
+            )
+            if w["fold"]:
+                lw["qkv_w"], lw["qkv_b"], lw["qkv_cs"] = ln_fold(layer.self_attn.qkv.weight, layer.self_attn.qkv.bias,
+                                                                 layer.layer_norm1.weight, layer.layer_norm1.bias)
+                lw["fc1_w"], lw["fc1_b"], lw["fc1_cs"] = ln_fold(layer.mlp.fc1.weight, layer.mlp.fc1.bias,
+                                                                 layer.layer_norm2.weight, layer.layer_norm2.bias)
+            else:
+                lw.update(
+                    ln1_g=f32(layer.layer_norm1.weight), ln1_b=f32(layer.layer_norm1.bias),
+                    qkv_w=bf16(layer.self_attn.qkv.weight),
+                    qkv_b=None if layer.self_attn.qkv.bias is None else f32(layer.self_attn.qkv.bias),
+                    ln2_g=f32(layer.layer_norm2.weight), ln2_b=f32(layer.layer_norm2.bias),
+                    fc1_w=bf16(layer.mlp.fc1.weight), fc1_b=f32(layer.mlp.fc1.bias))
+            w["layers"].append(lw)
         return w
 
     return cache.get("vision", params, build)
@@ -108,15 +125,32 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
         del patches
         if output_hidden_states:
             all_hidden.append(hidden.clone())
+        if w["fold"]:
+            # row [sum, sum of squares] of the residual stream: st1 feeds layer_norm1 (written by the
+            # previous layer's fc2 epilogue; by vb_row_stats for the embeddings), st2 feeds layer_norm2
+            # (written by the attention projection's epilogue)
+            # (each producer clears the other buffer in its epilogue: no memset launches in the loop)
+            st1 = ops.row_stats(hid2)
+            st2 = torch.zeros_like(st1)
         for lw in w["layers"]:
-            y = ops.layernorm(hid2, lw["ln1_g"], lw["ln1_b"], eps)
-            qkv = ops.gemm(y, lw["qkv_w"], lw["qkv_b"]).view(nf, tokens, 3 * dim)
-            o = ops.attention(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], heads, scale)
-            ops.gemm(o.view(nf * tokens, dim), lw["proj_w"], lw["proj_b"], residual=hid2, out=hid2)
-            y = ops.layernorm(hid2, lw["ln2_g"], lw["ln2_b"], eps)
-            h1 = ops.gemm(y, lw["fc1_w"], lw["fc1_b"], epilogue=act)
-            ops.gemm(h1, lw["fc2_w"], lw["fc2_b"], residual=hid2, out=hid2)
-            del y, qkv, o, h1
+            if w["fold"]:
+                qkv = ops.gemm(hid2, lw["qkv_w"], lw["qkv_b"], ln_fold=(st1, lw["qkv_cs"], eps)).view(nf, tokens, 3 * dim)
+                o = ops.attention(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], heads, scale)
+                ops.gemm(o.view(nf * tokens, dim), lw["proj_w"], lw["proj_b"], residual=hid2, out=hid2,
+                         stats_out=st2, stats_zero=st1)  # qkv has consumed st1
+                h1 = ops.gemm(hid2, lw["fc1_w"], lw["fc1_b"], epilogue=act, ln_fold=(st2, lw["fc1_cs"], eps))
+                ops.gemm(h1, lw["fc2_w"], lw["fc2_b"], residual=hid2, out=hid2,
+                         stats_out=st1, stats_zero=st2)  # fc1 has consumed st2
+                del qkv, o, h1
+            else:
+                y = ops.layernorm(hid2, lw["ln1_g"], lw["ln1_b"], eps)
+                qkv = ops.gemm(y, lw["qkv_w"], lw["qkv_b"]).view(nf, tokens, 3 * dim)
+                o = ops.attention(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], heads, scale)
+                ops.gemm(o.view(nf * tokens, dim), lw["proj_w"], lw["proj_b"], residual=hid2, out=hid2)
+                y = ops.layernorm(hid2, lw["ln2_g"], lw["ln2_b"], eps)
+                h1 = ops.gemm(y, lw["fc1_w"], lw["fc1_b"], epilogue=act)
+                ops.gemm(h1, lw["fc2_w"], lw["fc2_b"], residual=hid2, out=hid2)
+                del y, qkv, o, h1
             if output_hidden_states:
                 all_hidden.append(hidden.clone())
         ops.layernorm(hid2, w["post_g"], w["post_b"], eps, out=last[f0:f1].view(nf * tokens, dim))

@@ -70,6 +70,83 @@ def test_gemm_epilogues(backend, epi):
     _close(c, a.float() @ w.float().t() + bias + 1.0, atol=0.03, rtol=0.01, what="f32 beta")
 
 
+@pytest.mark.parametrize("m,n,k,bn,epi", [(1000, 4224, 1408, 0, "none"), (5000, 6144, 1408, 0, "gelu"),
+                                           (300, 704, 320, 1256, "gelu"), (257, 264, 72, 0, "none"),
+                                           (640, 1408, 1408, 1176, "relu"), (130, 24, 8, 0, "none")])
+def test_gemm_layernorm_fold(m, n, k, bn, epi):
+    """LayerNorm folded into the consuming GEMM (vb_gemm_args.ln_stats): act(LN(x) W^T + b) from the
+    un-normalised x, W*gamma, b + W beta, the row statistics and colsum(W*gamma).  The rows carry a
+    mean of the size of their spread so the -rstd*mean*colsum term matters."""
+    ops = _ops()
+    from eilev_b200.engine.packing import ln_fold
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = (torch.randn(m, k, generator=g, device="cuda") * (0.5 + torch.rand(m, 1, generator=g, device="cuda") * 3)
+         + torch.randn(m, 1, generator=g, device="cuda") * 2).to(torch.bfloat16)
+    w = _rand(n, k, scale=0.05, seed=22)
+    b = torch.randn(n, device="cuda") * 0.1
+    gamma = 1.0 + 0.3 * torch.randn(k, device="cuda")
+    beta = 0.2 * torch.randn(k, device="cuda")
+    wg, bias, cs = ln_fold(w, b, gamma, beta)
+    st = ops.row_stats(x)
+    assert torch.allclose(st[:, 0], x.float().sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], x.float().pow(2).sum(1), rtol=1e-4, atol=1e-2)
+    e = {"none": ops.EPI_NONE, "gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[epi]
+    out = ops.gemm(x, wg, bias, epilogue=e, ln_fold=(st, cs, 1e-6), backend=ops.GEMM_TCGEN05, block_n=bn)
+    pre = torch.nn.functional.layer_norm(x.float(), (k,), gamma, beta, 1e-6) @ w.float().t() + b
+    ref = {"none": lambda t: t, "gelu": torch.nn.functional.gelu, "relu": torch.relu}[epi](pre)
+    # the stand-alone path rounds LN(x) to bf16 before the GEMM: same error budget as test_gemm_epilogues
+    _close(out, ref, atol=0.03 + 0.004 * math.sqrt(k) * 0.05 * 8, rtol=0.01, what=f"ln fold {m}x{n}x{k} {epi}")
+    y = ops.layernorm(x, gamma, beta, 1e-6)
+    two_step = ops.gemm(y, w, b, epilogue=e, backend=ops.GEMM_TCGEN05, block_n=bn)
+    err_fold = (out.float() - ref).pow(2).mean().sqrt().item()
+    err_two = (two_step.float() - ref).pow(2).mean().sqrt().item()
+    assert err_fold <= 1.5 * err_two + 1e-3, (err_fold, err_two)  # no less accurate than LayerNorm kernel + GEMM
+
+
+@pytest.mark.parametrize("m,n,k,bn", [(1000, 1408, 1408, 0), (5000, 1408, 6144, 0), (300, 704, 320, 1256),
+                                      (300, 704, 320, 1176), (257, 264, 72, 0), (640, 1408, 1408, 256)])
+def test_gemm_output_row_statistics(m, n, k, bn):
+    """stats_out: the epilogue adds [sum, sum of squares] of the bf16 values it stores (residual GEMM in
+    place, as in the ViT layer); stats_zero: the other buffer is cleared by the same launch."""
+    ops = _ops()
+    a, w = _rand(m, k, scale=0.5, seed=31), _rand(n, k, scale=0.05, seed=32)
+    bias = torch.randn(n, device="cuda") * 0.1
+    x = _rand(m, n, seed=33)
+    ref = (a.float() @ w.float().t() + bias + x.float()).to(torch.bfloat16)
+    st = torch.zeros(m, 2, device="cuda")
+    other = torch.full((m, 2), 7.0, device="cuda")
+    ops.gemm(a, w, bias, residual=x, out=x, stats_out=st, stats_zero=other, backend=ops.GEMM_TCGEN05, block_n=bn)
+    _close(x, ref, atol=0.03, rtol=0.01, what="residual gemm")
+    got = x.float()
+    assert torch.allclose(st[:, 0], got.sum(1), rtol=1e-4, atol=2e-2), (st[:, 0] - got.sum(1)).abs().max()
+    assert torch.allclose(st[:, 1], got.pow(2).sum(1), rtol=1e-4, atol=2e-2), (st[:, 1] - got.pow(2).sum(1)).abs().max()
+    assert float(other.abs().max()) == 0.0
+    # a second launch accumulates on top (the caller owns the zeroing)
+    y = _rand(m, n, seed=34)
+    ops.gemm(a, w, bias, residual=y, out=y, stats_out=st, backend=ops.GEMM_TCGEN05, block_n=bn)
+    assert torch.allclose(st[:, 0], got.sum(1) + y.float().sum(1), rtol=1e-4, atol=4e-2)
+
+
+def test_gemm_gelu_epilogue_accuracy():
+    """The epilogue's GELU (sigmoid of an odd quintic, common.cuh::gelu_fast) against the exact erf GELU
+    the reference uses (HF hidden_act="gelu"): f32 output, inputs spread over [-12, 12]."""
+    ops = _ops()
+    m, n, k = 256, 512, 64
+    a = torch.zeros(m, k, dtype=torch.bfloat16, device="cuda")
+    a[:, 0] = 1.0
+    w = torch.zeros(n, k, dtype=torch.bfloat16, device="cuda")
+    bias = torch.linspace(-12.0, 12.0, n, device="cuda")
+    out = torch.empty(m, n, device="cuda")
+    ops.gemm(a, w, bias, out=out, epilogue=ops.EPI_GELU, backend=ops.GEMM_TCGEN05)
+    ref = torch.nn.functional.gelu(bias.double()).float()
+    err = (out[0] - ref).abs().max().item()
+    assert err < 6e-5, err
+    assert (out - out[0:1]).abs().max().item() == 0.0
+    big = torch.tensor([-1e4, -50.0, 50.0, 1e4], device="cuda").repeat(n // 4)
+    ops.gemm(a, w, big, out=out, epilogue=ops.EPI_GELU, backend=ops.GEMM_TCGEN05)
+    assert torch.equal(out[0], torch.nn.functional.gelu(big))
+
+
 def test_gemm_generic_odd_shapes():
     ops = _ops()
     for (m, n, k) in [(5, 7, 3), (65, 24, 192), (130, 8, 8), (33, 100, 50)]:
