@@ -64,7 +64,8 @@ def test_ctypes_structs_follow_the_header(cname, pyname):
 
 def test_struct_sizes():
     from eilev_b200 import _lib
-    assert C.sizeof(_lib.GemmArgs) == 5 * 8 + 7 * 8 + 2 * 4 + 2 * 8 + 4 * 4 + 8 + 16
+    # + ln_stats, ln_colsum, (ln_eps, reserved3), stats_out, stats_zero (ABI 5)
+    assert C.sizeof(_lib.GemmArgs) == 5 * 8 + 7 * 8 + 2 * 4 + 2 * 8 + 4 * 4 + 8 + 16 + 5 * 8
     assert C.sizeof(_lib.AttnArgs) == 6 * 8 + 13 * 8 + 8 + 8 + 16 + 16  # + rel_bias, rel_bias_stride
     assert C.sizeof(_lib.AttnBwdArgs) == C.sizeof(_lib.AttnArgs) + 4 * 8 + 6 * 8 + 2 * 8 + 8
 
