@@ -304,13 +304,31 @@ class PagedKV:
                 pool[li].copy_(view[idx].reshape(pool[li].shape))  # in place: pointers stay valid
 
 
+_STATE_PAGES_ROUND = 4   # reusable decode states round their capacity up to 4 pages (256 tokens)
+_STATE_CACHE_MAX = 2     # generation states kept alive per LM (each owns its KV pools)
+
+
 def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features,
-                max_new_tokens: int):
-    """Runs the prompt, fills a paged KV cache, returns (last-position logits f32 (B, V), state)."""
+                max_new_tokens: int, reuse_slot: int | None = None):
+    """Runs the prompt, fills a paged KV cache, returns (last-position logits f32 (B, V), state).
+
+    reuse_slot: generate() passes an integer so that consecutive calls with the same batch and (rounded)
+    capacity write into the SAME KV pools / counters; the CUDA graph of the decode step captured for that
+    state (``state["_graph"]``) then survives from one generate() call to the next instead of being
+    re-captured (~20 ms) for every prompt.  Steppers alive at the same time use different slots."""
     cfg = lm.config
     dim, heads, hd = _dims(cfg)
     b, l = input_ids.shape
-    kv = PagedKV(cfg.num_hidden_layers, b, l + max_new_tokens, dim, input_ids.device)
+    prev = None
+    capacity = l + max_new_tokens
+    if reuse_slot is not None:
+        pages = (capacity + 63) // 64
+        pages = (pages + _STATE_PAGES_ROUND - 1) // _STATE_PAGES_ROUND * _STATE_PAGES_ROUND
+        capacity = pages * 64
+        states = lm.__dict__.setdefault("_decode_states", {})
+        key = (int(reuse_slot), b, pages, str(input_ids.device))
+        prev = states.get(key)
+    kv = prev["kv"] if prev is not None else PagedKV(cfg.num_hidden_layers, b, capacity, dim, input_ids.device)
 
     def sink(li, k, v):
         ops.paged_kv_write(k, v, kv.k[li], kv.v[li], kv.table, kv.page_size)
@@ -324,11 +342,22 @@ def opt_prefill(lm, cache: PackCache, input_ids, attention_mask, video_mask, vid
     am = attention_mask if attention_mask is not None else torch.ones_like(input_ids)
     first_valid = (am != 0).to(torch.int32).argmax(dim=1).to(torch.int32).contiguous()
     n_valid = am.sum(dim=1).to(torch.int32).contiguous()
+    if prev is not None:  # same buffers (the captured graph holds their addresses), new contents
+        prev["ctx_len"].fill_(l)
+        prev["first_valid"].copy_(first_valid)
+        prev["n_valid"].copy_(n_valid)
+        prev["attn_cnt"].zero_()
+        prev["status"] = out["status"]
+        return logits, prev
     state = dict(kv=kv, ctx_len=torch.full((b,), l, dtype=torch.int32, device=input_ids.device),
                  first_valid=first_valid, n_valid=n_valid, status=out["status"])
+    if reuse_slot is not None:
+        while len(states) >= _STATE_CACHE_MAX:
+            states.pop(next(iter(states)))
+        states[key] = state
     # flash-decoding splits: enough (head, sequence, split) units to cover the SMs, no more —
     # every extra split adds to the merge (measured at ctx ~ 1000: batch 1 best at 8, batch 8 at 4)
-    total = l + max_new_tokens
+    total = capacity
     hb = heads * b
     splits = 8 if hb <= 64 else (4 if hb <= 256 else 2)
     if total <= 256:
@@ -463,6 +492,19 @@ def opt_decode_step(lm, cache: PackCache, tokens: torch.Tensor, state: dict) -> 
         f1 = ops.gemv(x, lw["fc1_w"], lw["fc1_b"], epilogue=act, ln=(lw["ln2_g"], lw["ln2_b"], 1e-5))
         x = ops.gemv(f1, lw["fc2_w"], lw["fc2_b"], residual=x)
     return ops.gemv(x, w["embed"], out_dtype=torch.float32, ln=(w["lnf_g"], w["lnf_b"], 1e-5))
+
+
+def decode_graph_for(lm, cache: PackCache, state: dict, batch: int, device) -> "DecodeGraph":
+    """The decode-step graph of `state`, captured once per (state, packed weights): a reused state
+    (opt_prefill(reuse_slot=...)) keeps its graph across generate() calls as long as the packed LM
+    operands the graph points at are still the cached ones."""
+    w = pack_opt(lm, cache, need_backward=False)
+    g = state.get("_graph")
+    if g is not None and state.get("_graph_pack") is w and g.tokens.shape[0] == batch:
+        return g
+    g = DecodeGraph(lm, cache, state, batch, device)
+    state["_graph"], state["_graph_pack"] = g, w
+    return g
 
 
 class DecodeGraph:

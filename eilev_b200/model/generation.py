@@ -25,17 +25,18 @@ class _OptStepper:
 
     start_token = None
 
-    def __init__(self, lm) -> None:
+    def __init__(self, lm, slot: int = 0) -> None:
         self.lm = lm
+        self.slot = slot  # generation-state slot: steppers alive at the same time must not share KV pools
 
     def prefill(self, input_ids, attention_mask, video_mask, feats, max_new):
         logits, self.state = E_opt.opt_prefill(self.lm, self.lm._pack, input_ids, attention_mask, video_mask,
-                                               feats, max_new)
+                                               feats, max_new, reuse_slot=self.slot)
         self.status = self.state["status"]
         return logits
 
     def graph(self, rows, dev):
-        return E_opt.DecodeGraph(self.lm, self.lm._pack, self.state, rows, dev)
+        return E_opt.decode_graph_for(self.lm, self.lm._pack, self.state, rows, dev)
 
     def step(self, tokens):
         return E_opt.opt_decode_step(self.lm, self.lm._pack, tokens, self.state)
@@ -288,7 +289,8 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
         else:
             if num_beams > MAX_DECODE_ROWS:
                 raise NotImplementedError(f"num_beams > {MAX_DECODE_ROWS} is not supported")
-            stepper = _GroupedStepper(lambda: _OptStepper(lm), MAX_DECODE_ROWS // num_beams * num_beams)
+            slots = iter(range(1, 1 << 20))
+            stepper = _GroupedStepper(lambda: _OptStepper(lm, next(slots)), MAX_DECODE_ROWS // num_beams * num_beams)
     logits = stepper.prefill(input_ids, attention_mask, video_mask, video_features, max_new)
     model._last_splice_status = stepper.status
 
