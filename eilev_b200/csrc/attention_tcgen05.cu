@@ -560,36 +560,71 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         if (prev_last) umma_commit(v_empty);
         umma_commit(&o_full[slot]);
       };
-      int g = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        mbar_wait(k_full, k_ph);
-        k_ph ^= 1u;
-        for (int t = 0; t < m_tiles; ++t) {
-          const int slot = g & 1;
-          mbar_wait(&q_full[slot], q_ph[slot]);
-          q_ph[slot] ^= 1u;
-          mbar_wait(&slot_free[slot], free_ph[slot] ^ 1u);  // epilogue of tile g-2 has drained O
-          free_ph[slot] ^= 1u;
-          tc_fence_after();
-          for (int ks = 0; ks < k_steps; ++ks) {
-            const int c = ks >> 2, kk = ks & 3;
-            const uint64_t a_desc =
-                umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
-            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
-            umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
+      // QK^T of the next tile and P.V of the oldest tile whose softmax is pending are issued in whichever
+      // order their inputs become ready (non-blocking probes): a P.V never waits behind a QK^T whose slot
+      // is still being drained by the other warp group's epilogue, and vice versa.
+      struct Pend { int slot; bool first, last; };
+      Pend pend[2];
+      int n_pend = 0;
+      int g = 0, t = 0;
+      int item = blockIdx.x;
+      bool k_ready = false;
+      long long t_idle = clock64();
+      while (item < p.items || n_pend > 0) {
+        bool progressed = false;
+        if (n_pend > 0) {
+          const Pend f = pend[0];
+          const bool v_ok = !f.first || mbar_test(v_full, v_ph);
+          if (v_ok && mbar_test(&p_ready[f.slot], p_ph[f.slot])) {
+            prev_slot = f.slot;
+            prev_first = f.first;
+            prev_last = f.last;
+            issue_pv();  // its own waits return immediately: both barriers were just observed complete
+            pend[0] = pend[1];
+            --n_pend;
+            progressed = true;
           }
-          umma_commit(&q_empty[slot]);
-          if (t == m_tiles - 1) umma_commit(k_empty);
-          umma_commit(&s_full[slot]);
-          if (have_prev) issue_pv();
-          have_prev = true;
-          prev_slot = slot;
-          prev_first = (t == 0);
-          prev_last = (t == m_tiles - 1);
-          ++g;
+        }
+        if (item < p.items && n_pend < 2) {
+          const int slot = g & 1;
+          if (!k_ready && t == 0) k_ready = mbar_test(k_full, k_ph);
+          if ((t > 0 || k_ready) && mbar_test(&q_full[slot], q_ph[slot]) &&
+              mbar_test(&slot_free[slot], free_ph[slot] ^ 1u)) {
+            if (t == 0) {
+              k_ph ^= 1u;
+              k_ready = false;
+            }
+            q_ph[slot] ^= 1u;
+            free_ph[slot] ^= 1u;
+            tc_fence_after();
+            for (int ks = 0; ks < k_steps; ++ks) {
+              const int c = ks >> 2, kk = ks & 3;
+              const uint64_t a_desc =
+                  umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
+              const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
+              umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
+            }
+            umma_commit(&q_empty[slot]);
+            if (t == m_tiles - 1) umma_commit(k_empty);
+            umma_commit(&s_full[slot]);
+            pend[n_pend].slot = slot;
+            pend[n_pend].first = (t == 0);
+            pend[n_pend].last = (t == m_tiles - 1);
+            ++n_pend;
+            ++g;
+            if (++t == m_tiles) {
+              t = 0;
+              item += gridDim.x;
+            }
+            progressed = true;
+          }
+        }
+        if (progressed) {
+          t_idle = clock64();
+        } else if (clock64() - t_idle > 4000000000LL) {
+          __trap();  // a mis-programmed pipeline surfaces as a CUDA error instead of a hang
         }
       }
-      if (have_prev) issue_pv();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax + epilogue (one slot per warp group)

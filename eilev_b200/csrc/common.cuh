@@ -57,6 +57,18 @@ VB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (no hardware suspend): for threads that poll several barriers at once.
+VB_DEVICE bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a mis-programmed pipeline traps (surfacing as a CUDA error on the
 // host) instead of hanging the GPU box.
 VB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {

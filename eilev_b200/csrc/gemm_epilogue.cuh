@@ -39,9 +39,8 @@ VB_DEVICE float2 ln_fold_coeffs(const EpiParams& p, long long row) {
   const float rstd = rsqrtf(var + p.ln_eps);
   return make_float2(rstd, -rstd * mean);
 }
-// acc[j] <- rstd * acc[j] - rstd * mean * colsum[col0 + j]
-VB_DEVICE void ln_fold_apply(const EpiParams& p, long long row, long long col0, float (&v)[16]) {
-  const float2 c = ln_fold_coeffs(p, row);
+// acc[j] <- rstd * acc[j] - rstd * mean * colsum[col0 + j];  c = ln_fold_coeffs(row)
+VB_DEVICE void ln_fold_apply(const EpiParams& p, const float2 c, long long col0, float (&v)[16]) {
   if (col0 + 16 <= p.n) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -78,7 +77,7 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
   const bool full = (col0 + 16 <= p.n);
   if (p.stats_zero != nullptr && col0 == 0) *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
-  if (p.ln_stats != nullptr) ln_fold_apply(p, row, col0, v);
+  if (p.ln_stats != nullptr) ln_fold_apply(p, ln_fold_coeffs(p, row), col0, v);
   if (p.bias != nullptr) {
     if (full) {
 #pragma unroll
@@ -193,11 +192,12 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
 // `slab_row` points at this thread's 128-byte row of a [128 rows][64 cols] SWIZZLE_128B slab,
 // `row7` = row & 7 (swizzle phase), `c16` = 16-column chunk inside the slab (0..3).
 VB_DEVICE void epilogue_row16_staged(const EpiParams& p, long long row, long long col0, const uint32_t (&acc)[16],
-                                     uint8_t* slab_row, int row7, int c16, bool has_res, float& st_s, float& st_q) {
+                                     uint8_t* slab_row, int row7, int c16, bool has_res, const float2 ln_c,
+                                     float& st_s, float& st_q) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-  if (p.ln_stats != nullptr && row < p.m) ln_fold_apply(p, row, col0, v);
+  if (p.ln_stats != nullptr) ln_fold_apply(p, ln_c, col0, v);  // ln_c: per-row coefficients, once per tile
   if (p.bias != nullptr) {
     if (col0 + 16 <= p.n) {
 #pragma unroll

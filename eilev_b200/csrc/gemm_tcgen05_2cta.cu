@@ -8,7 +8,10 @@
 //   warp 0   TMA producer (both CTAs; transaction bytes are credited to the leader's barrier)
 //   warp 1   MMA issuer   (leader CTA only, one thread; commits multicast to both CTAs)
 //   warp 2   TMEM allocator (cta_group::2)
-//   warps 4-11 epilogue (each CTA drains its own 128 accumulator rows)
+//   warps 4-19 epilogue (each CTA drains its own 128 accumulator rows; four warps per TMEM lane quarter,
+//              one per 64-column slab of the tile: the K = 1408 launches of the ViT are epilogue-bound, and an
+//              epilogue of dependent MUFU / FMA chains needs four warps per scheduler to hide its latencies —
+//              profiles/r02_ncu_gemm_shapes.txt)
 #include "common.cuh"
 #include "gemm.h"
 #include "gemm_epilogue.cuh"
@@ -17,16 +20,16 @@ namespace vb {
 
 constexpr int k2BM = 128;  // rows per CTA (256 per pair)
 constexpr int k2BK = 64;
-constexpr int k2Threads = 384;
-constexpr int k2EpiWarps = 8;
+constexpr int k2EpiWarps = 16;
+constexpr int k2Threads = (4 + k2EpiWarps) * 32;  // 640: <= 96 registers per thread
 
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kABytes = k2BM * k2BK * 2;
   static constexpr int kBBytes = (BN / 2) * k2BK * 2;  // this CTA's half of B
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // output staging for the TMA-store epilogue: [2 column halves][2 ping-pong slabs] of
-  // 128 rows x 64 cols bf16 (SWIZZLE_128B) = 64 KB
+  // output staging for the TMA-store epilogue: four slabs (one per 64-column quarter of the tile, each
+  // owned by four warps) of 128 rows x 64 cols bf16 (SWIZZLE_128B) = 64 KB
   static constexpr int kSlabBytes = k2BM * 128;
   static constexpr int kStagingBytes = 4 * kSlabBytes;
   static constexpr int kStages = (226 * 1024 - kStagingBytes - 1280) / kStageBytes > 8
@@ -139,84 +142,89 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (own 128 rows)
     const int ew = warp - 4;
-    const int quarter = warp & 3;
-    const int half = ew >> 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    const int cq = ew >> 2;         // column group: 64-column slab (staged path) / quarter of the chunks
     constexpr int kChunks = BN / 16;
-    constexpr int kHalfChunks = (kChunks + 1) / 2;
-    const int c_begin = half * kHalfChunks;
-    const int c_end = (c_begin + kHalfChunks < kChunks) ? c_begin + kHalfChunks : kChunks;
+    constexpr int kGroupChunks = (kChunks + 3) / 4;
+    const int c_begin = cq * kGroupChunks;
+    const int c_end = (c_begin + kGroupChunks < kChunks) ? c_begin + kGroupChunks : kChunks;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const long long row = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
       if (BN == 256 && p.tma_store) {
-        // ---- staged path: this warp group (`half`) owns columns [128*half, 128*half+128) of the
-        // tile = two 64-column slabs; the four quarter-warps fill a slab, one thread TMA-stores it.
+        // ---- staged path: the four warps of column group `cq` fill one [128 rows][64 cols] slab
+        // (bias / LayerNorm fold / activation / residual), one thread stores it with TMA.
         const int row_in = quarter * 32 + lane;              // row inside this CTA's 128 rows
         const long long tile_row0 = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM;
         const bool has_res = p.residual != nullptr;
-        float st_s = 0.0f, st_q = 0.0f;  // row statistics of this thread's 128 output columns
-#pragma unroll 1
-        for (int sl = 0; sl < 2; ++sl) {
-          const long long col_slab = static_cast<long long>(n_blk) * BN + half * 128 + sl * 64;
-          uint8_t* slab = smem_c + (half * 2 + sl) * Cfg::kSlabBytes;
-          const bool slab_live = col_slab < p.n;
-          // the TMA store that last read this slab (previous tile) must have drained
-          if (ew % 4 == 0 && lane == 0) bulk_wait_read<1>();
-          named_bar_sync(1 + half, 128);
-          if (has_res && slab_live) {
-            // coalesced residual fetch: 8 lanes cover one 128-byte row, 4 rows per instruction
+        const long long col_slab = static_cast<long long>(n_blk) * BN + cq * 64;
+        uint8_t* slab = smem_c + cq * Cfg::kSlabBytes;
+        const bool slab_live = col_slab < p.n;
+        // the TMA store that last read this slab (previous tile) must have drained
+        if (quarter == 0 && lane == 0) bulk_wait_read<0>();
+        named_bar_sync(1 + cq, 128);
+        if (has_res && slab_live) {
+          // coalesced residual fetch, in flight while the accumulator is still being computed:
+          // 8 lanes cover one 128-byte row, 4 rows per instruction
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = quarter * 32 + i * 4 + (lane >> 3);
-              const int c16b = lane & 7;
-              const long long grow = tile_row0 + r, gcol = col_slab + c16b * 8;
-              uint8_t* dst = slab + r * 128 + ((c16b ^ (r & 7)) << 4);
-              if (grow < p.m && gcol + 8 <= p.n) cp_async_16(dst, p.residual + grow * p.ldr + gcol);
-              else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-            }
-            cp_async_commit_wait_all();
-            __syncwarp();  // each warp reads back only rows it fetched itself
-          }
-#pragma unroll
-          for (int c16 = 0; c16 < 4; c16 += 2) {
-            uint32_t r0[16], r1[16];
-            const int ch = (half * 128 + sl * 64) / 16 + c16;
-            tmem_ld_16(t_row + ch * 16, r0);
-            tmem_ld_16(t_row + (ch + 1) * 16, r1);
-            tmem_ld_wait();
-            if (sl == 1 && c16 == 2) {  // last TMEM read of this warp for this tile
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
-            }
-            if (slab_live) {
-              uint8_t* slab_row = slab + row_in * 128;
-              epilogue_row16_staged(p, row, col_slab + c16 * 16, r0, slab_row, row_in & 7, c16, has_res, st_s, st_q);
-              epilogue_row16_staged(p, row, col_slab + (c16 + 1) * 16, r1, slab_row, row_in & 7, c16 + 1, has_res,
-                                    st_s, st_q);
-            }
-          }
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
-          named_bar_sync(1 + half, 128);
-          if (ew % 4 == 0 && lane == 0) {
-            if (slab_live) tma_store_2d(&tmap_c, slab, static_cast<int>(col_slab), static_cast<int>(tile_row0));
-            bulk_commit();  // (an empty group keeps the wait_group bookkeeping uniform)
+          for (int i = 0; i < 8; ++i) {
+            const int r = quarter * 32 + i * 4 + (lane >> 3);
+            const int c16b = lane & 7;
+            const long long grow = tile_row0 + r, gcol = col_slab + c16b * 8;
+            uint8_t* dst = slab + r * 128 + ((c16b ^ (r & 7)) << 4);
+            if (grow < p.m && gcol + 8 <= p.n) cp_async_16(dst, p.residual + grow * p.ldr + gcol);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
           }
         }
-        if (p.stats_zero != nullptr && n_blk == 0 && half == 0 && row < p.m)
+        // per-row LayerNorm coefficients of a folded LayerNorm: fetched while the accumulator is in flight
+        float2 ln_c = make_float2(1.0f, 0.0f);
+        if (p.ln_stats != nullptr && row < p.m) ln_c = ln_fold_coeffs(p, row);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (has_res && slab_live) {
+          cp_async_commit_wait_all();
+          __syncwarp();  // each warp reads back only rows it fetched itself
+        }
+        float st_s = 0.0f, st_q = 0.0f;  // row statistics of this thread's 64 output columns
+        uint8_t* slab_row = slab + row_in * 128;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r0[16], r1[16];
+          tmem_ld_16(t_row + cq * 64 + hf * 32, r0);
+          tmem_ld_16(t_row + cq * 64 + hf * 32 + 16, r1);
+          tmem_ld_wait();
+          if (hf == 1) {  // last TMEM read of this warp for this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+          }
+          if (slab_live) {
+            epilogue_row16_staged(p, row, col_slab + hf * 32, r0, slab_row, row_in & 7, 2 * hf, has_res, ln_c,
+                                  st_s, st_q);
+            epilogue_row16_staged(p, row, col_slab + hf * 32 + 16, r1, slab_row, row_in & 7, 2 * hf + 1, has_res,
+                                  ln_c, st_s, st_q);
+          }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(1 + cq, 128);
+        if (quarter == 0 && lane == 0) {
+          if (slab_live) tma_store_2d(&tmap_c, slab, static_cast<int>(col_slab), static_cast<int>(tile_row0));
+          bulk_commit();  // (an empty group keeps the wait_group bookkeeping uniform)
+        }
+        if (p.stats_zero != nullptr && n_blk == 0 && cq == 0 && row < p.m)
           *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
-        if (p.stats_out != nullptr && row < p.m) {
+        if (p.stats_out != nullptr && row < p.m && slab_live) {
           atomicAdd(p.stats_out + 2 * row, st_s);
           atomicAdd(p.stats_out + 2 * row + 1, st_q);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       int ch = c_begin;
       for (; ch + 1 < c_end; ch += 2) {  // two 16-column loads in flight per wait
         uint32_t r0[16], r1[16];
@@ -239,6 +247,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
         epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + ch * 16, r0);
+      } else if (c_begin >= c_end) {  // a column group without chunks (narrow tiles) still releases the stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }

@@ -11,7 +11,7 @@ DEV uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_gener
 
 template <int N> struct Ld;
 template <> struct Ld<32> {
-  DEV static void go(uint32_t a, uint32_t (&r)[128]) {
+  DEV static void go(uint32_t a, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
       : "=r"(r[0]),"=r"(r[1]),"=r"(r[2]),"=r"(r[3]),"=r"(r[4]),"=r"(r[5]),"=r"(r[6]),"=r"(r[7]),"=r"(r[8]),"=r"(r[9]),"=r"(r[10]),"=r"(r[11]),"=r"(r[12]),"=r"(r[13]),"=r"(r[14]),"=r"(r[15]),
@@ -20,7 +20,8 @@ template <> struct Ld<32> {
   }
 };
 
-__global__ void __launch_bounds__(384, 1) tmem_read_kernel(int mode, int warps, int iters, long long* out, float* sink) {
+template <int mode>
+__global__ void __launch_bounds__(384, 1) tmem_read_kernel(int warps, int iters, long long* out, float* sink) {
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
@@ -43,28 +44,28 @@ __global__ void __launch_bounds__(384, 1) tmem_read_kernel(int mode, int warps, 
     for (int it = 0; it < iters; ++it) {
       if (mode == 0) {          // one x32 load per wait
         for (int c = c0; c < c1; c += 32) {
-          uint32_t r[128];
+          uint32_t r[32];
           Ld<32>::go(row + c, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          acc += __uint_as_float(r[lane & 31]);
+          acc += __uint_as_float(r[0]) + __uint_as_float(r[31]);
         }
       } else if (mode == 1) {   // two x32 loads in flight per wait
         for (int c = c0; c < c1; c += 64) {
-          uint32_t r[128], q[128];
+          uint32_t r[32], q[32];
           Ld<32>::go(row + c, r);
           Ld<32>::go(row + c + 32, q);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          acc += __uint_as_float(r[lane & 31]) + __uint_as_float(q[3]);
+          acc += __uint_as_float(r[0]) + __uint_as_float(r[31]) + __uint_as_float(q[3]) + __uint_as_float(q[30]);
         }
       } else {                  // four x32 loads in flight per wait
         for (int c = c0; c < c1; c += 128) {
-          uint32_t r[128], q[128], s[128], u[128];
+          uint32_t r[32], q[32], s[32], u[32];
           Ld<32>::go(row + c, r);
           Ld<32>::go(row + c + 32, q);
           Ld<32>::go(row + c + 64, s);
           Ld<32>::go(row + c + 96, u);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          acc += __uint_as_float(r[lane & 31]) + __uint_as_float(q[3]) + __uint_as_float(s[5]) + __uint_as_float(u[7]);
+          acc += __uint_as_float(r[0]) + __uint_as_float(r[31]) + __uint_as_float(q[3]) + __uint_as_float(s[5]) + __uint_as_float(u[7]) + __uint_as_float(u[31]);
         }
       }
     }
@@ -106,7 +107,9 @@ int main() {
   const int iters = 200;
   for (int warps : {4, 8}) for (int mode : {0, 1, 2}) {
     long long h = 0;
-    tmem_read_kernel<<<148, 384>>>(mode, warps, iters, out, sink);
+    if (mode == 0) tmem_read_kernel<0><<<148, 384>>>(warps, iters, out, sink);
+    else if (mode == 1) tmem_read_kernel<1><<<148, 384>>>(warps, iters, out, sink);
+    else tmem_read_kernel<2><<<148, 384>>>(warps, iters, out, sink);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
     printf("tmem_read warps=%d loads_in_flight=%d : %.1f clk per 128x256 fp32 tile (128 KB) -> %.1f B/clk/SM  [%s]\n", warps,
