@@ -46,7 +46,7 @@ def full_config(dropout: float = 0.0, lm: str = "opt"):
     if lm == "t5":
         text = dict(model_type="t5", d_model=2048, d_kv=64, d_ff=5120, num_layers=24, num_decoder_layers=24,
                     num_heads=32, vocab_size=32128, feed_forward_proj="gated-gelu", tie_word_embeddings=False,
-                    decoder_start_token_id=0, pad_token_id=0, eos_token_id=1, dropout_rate=0.0,
+                    decoder_start_token_id=0, pad_token_id=0, eos_token_id=1, dropout_rate=dropout,
                     relative_attention_num_buckets=32, relative_attention_max_distance=128)
         return Blip2Config(
             vision_config=dict(hidden_size=1408, intermediate_size=6144, num_hidden_layers=39,
@@ -129,8 +129,8 @@ def workload_config(world: int, seq_len: int, cuda_graph, dropout: float = 0.1, 
            "global_batch": world, "seq_len": seq_len, "parallelism": f"dp{world}",
            "weights": "random-init (seeded N(0,0.02))",
            "l2": "per-step working set (7.3 GB bf16 weights + activations) >> 126 MB L2",
-           "dropout": (("recipe: p=%.2f in train mode (Q-Former hidden + attention probs; the frozen T5's own "
-                        "dropout_rate is NOT applied yet, DESIGN.md section 7)" if lm == "t5" else
+           "dropout": (("recipe: p=%.2f in train mode (Q-Former hidden + attention probs; T5 dropout_rate at every "
+                        "site of both stacks)" if lm == "t5" else
                         "recipe: p=%.2f in train mode (Q-Former hidden + attention probs, OPT hidden)") % dropout)
            if dropout > 0 else "off"}
     if cuda_graph is not None:

@@ -621,8 +621,11 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         }
         if (progressed) {
           t_idle = clock64();
-        } else if (clock64() - t_idle > 4000000000LL) {
-          __trap();  // a mis-programmed pipeline surfaces as a CUDA error instead of a hang
+        } else {
+          // yield the scheduler: this lane shares its SM sub-partition with two softmax warps, and a tight
+          // probe loop took a third of their issue slots (profiles/r02_attn_pp_notes.txt)
+          __nanosleep(40);
+          if (clock64() - t_idle > 4000000000LL) __trap();  // a mis-programmed pipeline surfaces as an error
         }
       }
     }

@@ -128,28 +128,55 @@ def shift_right(labels: torch.Tensor, cfg) -> torch.Tensor:
     return out.masked_fill(out == -100, cfg.pad_token_id)
 
 
-def _ff_fwd(x, lw, eps):
+# Dropout sites (T5's own ``dropout_rate``, active in train mode exactly as in the reference — the frozen
+# LM runs in train() under HF Trainer, eilev/model/v2.py:228-238 + scripts/general/train_v2.py:123-130):
+#   per block   0 self-attention probabilities (T5Attention)       1 self-attention output (T5LayerSelfAttention)
+#               2 feed-forward inner activation (T5Dense*ActDense)  3 feed-forward output (T5LayerFF)
+#               4 cross-attention probabilities                     5 cross-attention output (T5LayerCrossAttention)
+#   per stack   embeddings and the final-layer-norm output (T5Stack)
+# Masks are counter hashes of (seed, salt, element index), regenerated in the backward pass.
+_SALT_T5 = 1 << 18
+_T5_DEC = 1 << 12          # decoder blocks
+_T5_STACK = 1 << 13        # + 0 encoder embeddings, 1 encoder output, 2 decoder embeddings, 3 decoder output
+
+
+def _drop(p: float, seed, salt: int):
+    return (p, seed, _SALT_T5 + salt) if (seed is not None and p > 0.0) else None
+
+
+def _masked(t, d):
+    """dropout(t) with the mask of site d (forward activations and, with the same site, their gradients)."""
+    return t if d is None else ops.dropout(t, d[0], d[1], d[2])
+
+
+def _ff_fwd(x, lw, eps, d_inner=None, d_out=None):
     y, r = ops.rmsnorm(x, lw["ln"], eps, save_stats=True)
     if lw["gated"]:  # T5DenseGatedActDense: gelu_new(wi_0 y) * (wi_1 y)
         h01 = ops.gemm(y, lw["wi_w"])
         act = ops.gated_gelu(h01)
     else:  # T5DenseActDense: relu(wi y) in the GEMM epilogue; the output doubles as the backward mask
         h01 = act = ops.gemm(y, lw["wi_w"], epilogue=ops.EPI_RELU)
-    out = ops.gemm(act, lw["wo_w"], residual=x)
+    out = ops.gemm(_masked(act, d_inner), lw["wo_w"], residual=x, dropout=d_out)
     return out, dict(x=x, r=r, h01=h01)
 
 
-def _ff_bwd(dx, lw, s):
-    d_act = ops.gemm(dx, lw["wo_wt"])
+def _ff_bwd(dx, lw, s, d_inner=None, d_out=None):
+    d_act = _masked(ops.gemm(_masked(dx, d_out), lw["wo_wt"]), d_inner)
     d_h01 = ops.gated_gelu_bwd(d_act, s["h01"]) if lw["gated"] else ops.act_bwd(d_act, s["h01"], ops.EPI_RELU)
     return ops.rmsnorm_bwd(ops.gemm(d_h01, lw["wi_wt"]), s["x"], lw["ln"], s["r"], dx_add=dx)
 
 
 def t5_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, video_features, labels=None,
-               decoder_input_ids=None, save: bool = False):
-    """Returns dict(logits (B, Ld, V), loss, encoder_last_hidden_state, status, ctx)."""
+               decoder_input_ids=None, save: bool = False, seed=None):
+    """Returns dict(logits (B, Ld, V), loss, encoder_last_hidden_state, status, ctx).
+    seed (device uint64 tensor): train mode — T5's dropout_rate is applied at every site HF applies it."""
     cfg = lm.config
     _check_cfg(cfg)
+    p = float(cfg.dropout_rate) if seed is not None else 0.0
+
+    def d(salt):
+        return _drop(p, seed, salt)
+
     w = pack_t5(lm, cache, need_backward=save)
     dm, heads, dkv = cfg.d_model, cfg.num_heads, cfg.d_kv
     inner = heads * dkv
@@ -160,19 +187,20 @@ def t5_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vide
                                                video_features, None, 0, want_hidden=False)
     key_mask = attention_mask.to(torch.uint8).contiguous()
     enc_bias = rel_bias_table(w["enc_rel"], l, l, True, cfg)
-    x = emb.view(rows, dm)
+    x = _masked(emb.view(rows, dm), d(_T5_STACK + 0))
     enc_saved = []
-    for lw in w["enc"]:
+    for li, lw in enumerate(w["enc"]):
         y, r1 = ops.rmsnorm(x, lw["ln1"], eps, save_stats=True)
         qkv = ops.gemm(y, lw["qkv_w"]).view(b, l, 3 * inner)
         o, lse = ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], heads, 1.0,
-                               key_mask=key_mask, need_lse=True, rel_bias=enc_bias)
-        x_mid = ops.gemm(o.view(rows, inner), lw["o_w"], residual=x)
-        x_out, sff = _ff_fwd(x_mid, lw["ff"], eps)
+                               key_mask=key_mask, need_lse=True, rel_bias=enc_bias, dropout=d(li * 8 + 0))
+        x_mid = ops.gemm(o.view(rows, inner), lw["o_w"], residual=x, dropout=d(li * 8 + 1))
+        x_out, sff = _ff_fwd(x_mid, lw["ff"], eps, d(li * 8 + 2), d(li * 8 + 3))
         if save:
             enc_saved.append(dict(x=x, r1=r1, qkv=qkv, o=o, lse=lse, ff=sff))
         x = x_out
     enc_out, r_enc = ops.rmsnorm(x, w["enc_ln"], eps, save_stats=True)
+    enc_out = _masked(enc_out, d(_T5_STACK + 1))
     x_enc_last = x
 
     if decoder_input_ids is None:
@@ -182,27 +210,29 @@ def t5_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vide
     ld = decoder_input_ids.shape[1]
     rows_d = b * ld
     n_dec = len(w["dec"])
-    xd = ops.embedding(decoder_input_ids, w["shared"]).view(rows_d, dm)
+    xd = _masked(ops.embedding(decoder_input_ids, w["shared"]).view(rows_d, dm), d(_T5_STACK + 2))
     ckv = ops.gemm(enc_out, w["ckv_w"]).view(b, l, n_dec * 2 * inner)
     dec_bias = rel_bias_table(w["dec_rel"], ld, ld, False, cfg)
     dec_saved = []
     for li, lw in enumerate(w["dec"]):
+        sl = _T5_DEC + li * 8
         y, r1 = ops.rmsnorm(xd, lw["ln1"], eps, save_stats=True)
         qkv = ops.gemm(y, lw["qkv_w"]).view(b, ld, 3 * inner)
         o, lse = ops.attention(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], heads, 1.0,
-                               causal=True, need_lse=True, rel_bias=dec_bias)
-        x1 = ops.gemm(o.view(rows_d, inner), lw["o_w"], residual=xd)
+                               causal=True, need_lse=True, rel_bias=dec_bias, dropout=d(sl + 0))
+        x1 = ops.gemm(o.view(rows_d, inner), lw["o_w"], residual=xd, dropout=d(sl + 1))
         y2, r2 = ops.rmsnorm(x1, lw["ln2"], eps, save_stats=True)
         cq = ops.gemm(y2, lw["cq_w"]).view(b, ld, inner)
         ck = ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner]
         cv = ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner]
-        co, clse = ops.attention(cq, ck, cv, heads, 1.0, key_mask=key_mask, need_lse=True)
-        x2 = ops.gemm(co.view(rows_d, inner), lw["co_w"], residual=x1)
-        x3, sff = _ff_fwd(x2, lw["ff"], eps)
+        co, clse = ops.attention(cq, ck, cv, heads, 1.0, key_mask=key_mask, need_lse=True, dropout=d(sl + 4))
+        x2 = ops.gemm(co.view(rows_d, inner), lw["co_w"], residual=x1, dropout=d(sl + 5))
+        x3, sff = _ff_fwd(x2, lw["ff"], eps, d(sl + 2), d(sl + 3))
         if save:
             dec_saved.append(dict(x=xd, r1=r1, qkv=qkv, o=o, lse=lse, x1=x1, r2=r2, cq=cq, co=co, clse=clse, ff=sff))
         xd = x3
     final, r_dec = ops.rmsnorm(xd, w["dec_ln"], eps, save_stats=True)
+    final = _masked(final, d(_T5_STACK + 3))
     alpha = dm ** -0.5 if scale_decoder_outputs(cfg) else 1.0
     logits = ops.gemm(final, w["head"], alpha=alpha).view(b, ld, -1)
     out = dict(logits=logits, loss=None, status=status, ctx=None,
@@ -214,7 +244,7 @@ def t5_forward(lm, cache: PackCache, input_ids, attention_mask, video_mask, vide
             out["ctx"] = dict(enc=enc_saved, dec=dec_saved, x_enc_last=x_enc_last, r_enc=r_enc, x_dec_last=xd,
                               r_dec=r_dec, ckv=ckv, logits=logits, labels=labels, row_lse=row_lse,
                               n_valid=n_valid, slot=slot, key_mask=key_mask, enc_bias=enc_bias, dec_bias=dec_bias,
-                              alpha=alpha, b=b, l=l, ld=ld,
+                              alpha=alpha, b=b, l=l, ld=ld, seed=seed, p=p,
                               n_features=0 if video_features is None else video_features.shape[0])
     return out
 
@@ -362,46 +392,55 @@ def t5_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None)
     gs = None
     if grad_loss is not None:
         gs = grad_loss.detach().to(torch.float32).reshape(()).contiguous()
+    seed, p = ctx.get("seed"), ctx.get("p", 0.0)
+
+    def d(salt):
+        return _drop(p, seed, salt)
+
     dlogits = ops.cross_entropy_bwd(ctx["logits"], ctx["labels"], ctx["row_lse"], ctx["n_valid"], gs, shift=0)
-    d_final = ops.gemm(dlogits, w["head_t"], alpha=ctx["alpha"])
+    d_final = _masked(ops.gemm(dlogits, w["head_t"], alpha=ctx["alpha"]), d(_T5_STACK + 3))
     dx = ops.rmsnorm_bwd(d_final, ctx["x_dec_last"], w["dec_ln"], ctx["r_dec"])
     del dlogits, d_final
     d_ckv = torch.empty_like(ctx["ckv"])  # every layer writes its own K | V slice
     ckv = ctx["ckv"]
     for li in range(len(w["dec"]) - 1, -1, -1):
         lw, s = w["dec"][li], ctx["dec"][li]
-        d_x2 = _ff_bwd(dx, lw["ff"], s["ff"])
-        d_co = ops.gemm(d_x2, lw["co_wt"]).view(b, ld, inner)
+        sl = _T5_DEC + li * 8
+        d_x2 = _ff_bwd(dx, lw["ff"], s["ff"], d(sl + 2), d(sl + 3))
+        d_co = ops.gemm(_masked(d_x2, d(sl + 5)), lw["co_wt"]).view(b, ld, inner)
         ck = ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner]
         cv = ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner]
         dcq, _, _ = ops.attention_bwd(s["cq"], ck, cv, s["co"], s["clse"], d_co, heads, 1.0,
                                       key_mask=ctx["key_mask"],
                                       dk=d_ckv[:, :, (2 * li) * inner:(2 * li + 1) * inner],
-                                      dv=d_ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner])
+                                      dv=d_ckv[:, :, (2 * li + 1) * inner:(2 * li + 2) * inner],
+                                      dropout=d(sl + 4))
         d_x1 = ops.rmsnorm_bwd(ops.gemm(dcq.view(rows_d, inner), lw["cq_wt"]), s["x1"], lw["ln2"], s["r2"],
                                dx_add=d_x2)
-        d_o = ops.gemm(d_x1, lw["o_wt"]).view(b, ld, inner)
+        d_o = ops.gemm(_masked(d_x1, d(sl + 1)), lw["o_wt"]).view(b, ld, inner)
         qkv = s["qkv"]
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], s["o"], s["lse"],
                           d_o, heads, 1.0, causal=True, rel_bias=ctx["dec_bias"],
-                          dq=dqkv[:, :, :inner], dk=dqkv[:, :, inner:2 * inner], dv=dqkv[:, :, 2 * inner:])
+                          dq=dqkv[:, :, :inner], dk=dqkv[:, :, inner:2 * inner], dv=dqkv[:, :, 2 * inner:],
+                          dropout=d(sl + 0))
         dx = ops.rmsnorm_bwd(ops.gemm(dqkv.view(rows_d, 3 * inner), lw["qkv_wt"]), s["x"], lw["ln1"], s["r1"],
                              dx_add=d_x1)
     # encoder output <- all cross-attention K / V projections at once
-    d_enc = ops.gemm(d_ckv.view(rows, -1), w["ckv_wt"])
+    d_enc = _masked(ops.gemm(d_ckv.view(rows, -1), w["ckv_wt"]), d(_T5_STACK + 1))
     dx = ops.rmsnorm_bwd(d_enc, ctx["x_enc_last"], w["enc_ln"], ctx["r_enc"])
     for li in range(len(w["enc"]) - 1, -1, -1):
         lw, s = w["enc"][li], ctx["enc"][li]
-        d_mid = _ff_bwd(dx, lw["ff"], s["ff"])
-        d_o = ops.gemm(d_mid, lw["o_wt"]).view(b, l, inner)
+        d_mid = _ff_bwd(dx, lw["ff"], s["ff"], d(li * 8 + 2), d(li * 8 + 3))
+        d_o = ops.gemm(_masked(d_mid, d(li * 8 + 1)), lw["o_wt"]).view(b, l, inner)
         qkv = s["qkv"]
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:], s["o"], s["lse"],
                           d_o, heads, 1.0, key_mask=ctx["key_mask"], rel_bias=ctx["enc_bias"],
-                          dq=dqkv[:, :, :inner], dk=dqkv[:, :, inner:2 * inner], dv=dqkv[:, :, 2 * inner:])
+                          dq=dqkv[:, :, :inner], dk=dqkv[:, :, inner:2 * inner], dv=dqkv[:, :, 2 * inner:],
+                          dropout=d(li * 8 + 0))
         dx = ops.rmsnorm_bwd(ops.gemm(dqkv.view(rows, 3 * inner), lw["qkv_wt"]), s["x"], lw["ln1"], s["r1"],
                              dx_add=d_mid)
     if ctx["n_features"] == 0:
         return None
-    return ops.splice_bwd(dx, ctx["slot"], ctx["n_features"])
+    return ops.splice_bwd(_masked(dx, d(_T5_STACK + 0)), ctx["slot"], ctx["n_features"])

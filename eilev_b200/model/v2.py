@@ -370,10 +370,10 @@ class _Seq2SeqLossFn(torch.autograd.Function):
     through decoder, cross-attention K/V, encoder and splice down to the video slots."""
 
     @staticmethod
-    def forward(ctx, model, video_features, input_ids, attention_mask, video_mask, labels):
+    def forward(ctx, model, video_features, input_ids, attention_mask, video_mask, labels, seed):
         lm = model.language_model
         out = E_t5.t5_forward(lm, lm._pack, input_ids, attention_mask, video_mask, video_features,
-                              labels=labels, save=True)
+                              labels=labels, save=True, seed=seed)
         ctx.model, ctx.saved = model, out["ctx"]
         ctx.feat_dtype = video_features.dtype
         ctx.mark_non_differentiable(out["logits"], out["status"], out["encoder_last_hidden_state"])
@@ -384,7 +384,7 @@ class _Seq2SeqLossFn(torch.autograd.Function):
         lm = ctx.model.language_model
         d_feats = E_t5.t5_backward(lm, lm._pack, ctx.saved, grad_loss)
         ctx.saved = None
-        return None, d_feats.to(ctx.feat_dtype), None, None, None, None
+        return None, d_feats.to(ctx.feat_dtype), None, None, None, None, None
 
 
 # =============================================================================== full model
@@ -532,7 +532,7 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         if not self.config.use_decoder_only_language_model:
             return self._forward_seq2seq(input_ids, attention_mask, video_input_mask, feats, labels,
                                          decoder_input_ids, decoder_attention_mask, want_hidden, train,
-                                         vision_outputs, query_outputs, return_dict)
+                                         vision_outputs, query_outputs, return_dict, seed)
         if train:
             loss, logits, status = _LMLossFn.apply(self, feats, input_ids, attention_mask,
                                                    video_input_mask, labels, seed)
@@ -554,7 +554,8 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
             qformer_outputs=query_outputs, language_model_outputs=lm_outputs)
 
     def _forward_seq2seq(self, input_ids, attention_mask, video_input_mask, feats, labels, decoder_input_ids,
-                         decoder_attention_mask, want_hidden, train, vision_outputs, query_outputs, return_dict):
+                         decoder_attention_mask, want_hidden, train, vision_outputs, query_outputs, return_dict,
+                         seed=None):
         """v2.py:228-238: the interleaved embeddings go to the T5 encoder, the labels
         (shifted right) to the decoder."""
         if want_hidden:
@@ -564,7 +565,7 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         lm = self.language_model
         if train:
             loss, logits, status, enc = _Seq2SeqLossFn.apply(self, feats, input_ids, attention_mask,
-                                                             video_input_mask, labels)
+                                                             video_input_mask, labels, seed)
         else:
             with torch.no_grad():
                 out = E_t5.t5_forward(lm, lm._pack, input_ids, attention_mask, video_input_mask, feats,

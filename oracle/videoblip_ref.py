@@ -274,60 +274,70 @@ def t5_position_bias(table, lq, lk, bidirectional, tcfg):
     return table.float()[bucket].permute(2, 0, 1)[None]
 
 
-def _t5_attention(sd, tcfg, x, kv, p, bias):
-    """T5Attention.forward: no 1/sqrt(d) scaling, no projection biases, additive bias."""
+def _t5_attention(sd, tcfg, x, kv, p, bias, drop=_no_drop, site=None):
+    """T5Attention.forward: no 1/sqrt(d) scaling, no projection biases, additive bias; dropout on the
+    probabilities (`site`, tests only)."""
     b, lq, _ = x.shape
     lk = kv.shape[1]
     h, d = tcfg.num_heads, tcfg.d_kv
     q = _lin(x, sd, p + "q", bias=False).reshape(b, lq, h, d).transpose(1, 2)
     k = _lin(kv, sd, p + "k", bias=False).reshape(b, lk, h, d).transpose(1, 2)
     v = _lin(kv, sd, p + "v", bias=False).reshape(b, lk, h, d).transpose(1, 2)
-    probs = torch.softmax(q @ k.transpose(-1, -2) + bias, dim=-1)
+    probs = drop(site, torch.softmax(q @ k.transpose(-1, -2) + bias, dim=-1))
     return _lin((probs @ v).transpose(1, 2).reshape(b, lq, h * d), sd, p + "o", bias=False)
 
 
-def _t5_ff(sd, tcfg, x, p):
-    """T5DenseGatedActDense (gated-gelu: gelu_new(wi_0 x) * wi_1 x) or T5DenseActDense (relu)."""
+def _t5_ff(sd, tcfg, x, p, drop=_no_drop, site=None):
+    """T5DenseGatedActDense (gated-gelu: gelu_new(wi_0 x) * wi_1 x) or T5DenseActDense (relu); dropout on
+    the inner activation (`site`)."""
     if tcfg.is_gated_act:
         act = F.gelu(_lin(x, sd, p + "wi_0", bias=False), approximate="tanh")
-        return _lin(act * _lin(x, sd, p + "wi_1", bias=False), sd, p + "wo", bias=False)
-    return _lin(F.relu(_lin(x, sd, p + "wi", bias=False)), sd, p + "wo", bias=False)
+        return _lin(drop(site, act * _lin(x, sd, p + "wi_1", bias=False)), sd, p + "wo", bias=False)
+    return _lin(drop(site, F.relu(_lin(x, sd, p + "wi", bias=False))), sd, p + "wo", bias=False)
 
 
-def t5_encoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.encoder."):
-    """T5Stack (encoder): pre-RMSNorm blocks; block 0 owns the bidirectional relative bias."""
+def t5_encoder(sd, tcfg, inputs_embeds, attention_mask, p="language_model.encoder.", drop=_no_drop):
+    """T5Stack (encoder): pre-RMSNorm blocks; block 0 owns the bidirectional relative bias.
+    drop sites (HF T5, tests only): ("t5e", layer, 0) attention probabilities, 1 attention output, 2 feed-forward
+    inner activation, 3 feed-forward output; ("t5", -1, 0) the embeddings, ("t5", -1, 1) the stack output."""
     b, l, _ = inputs_embeds.shape
     eps = tcfg.layer_norm_epsilon
     neg = torch.finfo(torch.float32).min
     bias = t5_position_bias(sd[p + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"], l, l, True, tcfg)
     bias = bias + (1.0 - attention_mask[:, None, None, :].float()) * neg
-    x = inputs_embeds.float()
+    x = drop(("t5", -1, 0), inputs_embeds.float())
     for i in range(tcfg.num_layers):
         bp = f"{p}block.{i}."
         y = _rms(x, sd[bp + "layer.0.layer_norm.weight"], eps)
-        x = x + _t5_attention(sd, tcfg, y, y, bp + "layer.0.SelfAttention.", bias)
-        x = x + _t5_ff(sd, tcfg, _rms(x, sd[bp + "layer.1.layer_norm.weight"], eps), bp + "layer.1.DenseReluDense.")
-    return _rms(x, sd[p + "final_layer_norm.weight"], eps)
+        x = x + drop(("t5e", i, 1), _t5_attention(sd, tcfg, y, y, bp + "layer.0.SelfAttention.", bias, drop, ("t5e", i, 0)))
+        x = x + drop(("t5e", i, 3), _t5_ff(sd, tcfg, _rms(x, sd[bp + "layer.1.layer_norm.weight"], eps),
+                                           bp + "layer.1.DenseReluDense.", drop, ("t5e", i, 2)))
+    return drop(("t5", -1, 1), _rms(x, sd[p + "final_layer_norm.weight"], eps))
 
 
-def t5_decoder(sd, tcfg, decoder_input_ids, enc, enc_mask, p="language_model.decoder."):
+def t5_decoder(sd, tcfg, decoder_input_ids, enc, enc_mask, p="language_model.decoder.", drop=_no_drop):
     """T5Stack (decoder): causal self-attention with the unidirectional relative bias,
-    cross-attention over the encoder states (mask only), feed-forward."""
+    cross-attention over the encoder states (mask only), feed-forward.
+    drop sites: ("t5d", layer, 0..3) as in the encoder, 4 cross-attention probabilities, 5 cross-attention
+    output; ("t5", -1, 2) the embeddings, ("t5", -1, 3) the stack output."""
     b, l = decoder_input_ids.shape
     eps = tcfg.layer_norm_epsilon
     neg = torch.finfo(torch.float32).min
-    x = sd["language_model.shared.weight"].float()[decoder_input_ids]
+    x = drop(("t5", -1, 2), sd["language_model.shared.weight"].float()[decoder_input_ids])
     self_bias = t5_position_bias(sd[p + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"], l, l, False, tcfg)
     self_bias = self_bias.masked_fill(~torch.ones(l, l, dtype=torch.bool).tril()[None, None], neg)
     cross_bias = (1.0 - enc_mask[:, None, None, :].float()) * neg
     for i in range(tcfg.num_decoder_layers):
         bp = f"{p}block.{i}."
         y = _rms(x, sd[bp + "layer.0.layer_norm.weight"], eps)
-        x = x + _t5_attention(sd, tcfg, y, y, bp + "layer.0.SelfAttention.", self_bias)
+        x = x + drop(("t5d", i, 1), _t5_attention(sd, tcfg, y, y, bp + "layer.0.SelfAttention.", self_bias, drop,
+                                                  ("t5d", i, 0)))
         y = _rms(x, sd[bp + "layer.1.layer_norm.weight"], eps)
-        x = x + _t5_attention(sd, tcfg, y, enc, bp + "layer.1.EncDecAttention.", cross_bias)
-        x = x + _t5_ff(sd, tcfg, _rms(x, sd[bp + "layer.2.layer_norm.weight"], eps), bp + "layer.2.DenseReluDense.")
-    return _rms(x, sd[p + "final_layer_norm.weight"], eps)
+        x = x + drop(("t5d", i, 5), _t5_attention(sd, tcfg, y, enc, bp + "layer.1.EncDecAttention.", cross_bias, drop,
+                                                  ("t5d", i, 4)))
+        x = x + drop(("t5d", i, 3), _t5_ff(sd, tcfg, _rms(x, sd[bp + "layer.2.layer_norm.weight"], eps),
+                                           bp + "layer.2.DenseReluDense.", drop, ("t5d", i, 2)))
+    return drop(("t5", -1, 3), _rms(x, sd[p + "final_layer_norm.weight"], eps))
 
 
 def t5_shift_right(labels, tcfg):
@@ -339,7 +349,7 @@ def t5_shift_right(labels, tcfg):
 
 
 def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_values=None,
-                         video_input_mask=None, labels=None, decoder_input_ids=None):
+                         video_input_mask=None, labels=None, decoder_input_ids=None, drop=_no_drop):
     """v2.py:132-252 with the seq2seq branch (:228-238) -> T5ForConditionalGeneration.forward:
     encoder over the interleaved embeddings, decoder over shift_right(labels), untied or tied
     (x d_model**-0.5) head, unshifted CE with ignore_index -100."""
@@ -348,7 +358,7 @@ def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_value
     feats = None
     if pixel_values is not None:
         assert video_input_mask is not None
-        feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values)
+        feats, qout, image_embeds, pooled = video_features(sd, config, pixel_values, drop)
         out.update(video_features=feats, query_output=qout, image_embeds=image_embeds, pooler_output=pooled)
     emb = sd["language_model.shared.weight"].float()[input_ids]
     if feats is not None:
@@ -356,10 +366,10 @@ def videoblip_forward_t5(sd, config, input_ids, attention_mask=None, pixel_value
         emb[video_input_mask.bool()] = feats
     if attention_mask is None:
         attention_mask = torch.ones_like(input_ids)
-    enc = t5_encoder(sd, tcfg, emb, attention_mask)
+    enc = t5_encoder(sd, tcfg, emb, attention_mask, drop=drop)
     if decoder_input_ids is None:
         decoder_input_ids = t5_shift_right(labels, tcfg)
-    dec = t5_decoder(sd, tcfg, decoder_input_ids, enc, attention_mask)
+    dec = t5_decoder(sd, tcfg, decoder_input_ids, enc, attention_mask, drop=drop)
     # 4.33.1 scales the decoder output by d_model**-0.5 iff tie_word_embeddings; 5.5.0 froze that
     # decision into config.scale_decoder_outputs (flan-t5: untied head, no scaling, in both)
     if getattr(tcfg, "scale_decoder_outputs", tcfg.tie_word_embeddings):

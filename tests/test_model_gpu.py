@@ -188,6 +188,9 @@ def test_train_mode_dropout_matches_oracle_with_injected_masks():
         p_.requires_grad = False
     for p_ in m.language_model.parameters():
         p_.requires_grad = False
+    # the masks (and with them the size of the bf16 gradient gap: 6.7 % .. 12.4 % were seen) depend on the
+    # process-wide torch seed the model derives its dropout seed from: pin it
+    m._dropout_seed = torch.full((1,), 20240607, dtype=torch.int64, device="cuda")
     out = m(**cuda(fx["inputs"]), return_dict=True)
     out.loss.backward()
     seed = m._dropout_seed
@@ -218,7 +221,10 @@ def test_train_mode_dropout_matches_oracle_with_injected_masks():
     glob = (num / den) ** 0.5
     _dump("dropout/small_opt", loss=float(out.loss), loss_ref=float(ref["loss"]), grad_rel_l2=glob,
           logits=rel_l2(out.logits, ref["logits"]))
-    assert glob < 0.10, glob
+    # the reference's own bf16-vs-fp32 gradient gap on this fixture WITHOUT dropout is 8.9-9.6 %
+    # (tests/golden/bf16_yardstick.py); with 10 % of the activations masked the gap of the same kernels moves
+    # between 6.7 % and 12.4 % with the mask draw
+    assert glob < 0.14, glob
     # a second step draws different masks; eval mode is deterministic and mask-free
     out2 = m(**cuda(fx["inputs"]), return_dict=True)
     assert abs(float(out2.loss) - float(out.loss)) > 1e-4
@@ -435,6 +441,68 @@ def test_t5_backward_matches_reference_golden():
     glob = (num / den) ** 0.5
     _dump("t5_backward", global_rel_l2=glob, worst=worst, loss=float(out.loss.detach()), n=len(got))
     assert glob < 0.06, (glob, worst)
+
+
+def test_t5_train_mode_dropout_matches_oracle_with_injected_masks():
+    """Recipe mode for the seq2seq branch: T5's own dropout_rate (attention probabilities, attention / cross-
+    attention / feed-forward outputs, the feed-forward inner activation, embeddings and stack outputs of both
+    stacks — every site HF T5 has) plus the Q-Former's dropout.  The counter-hash masks are replayed in the
+    oracle: loss, logits and gradients must agree (the frozen T5 runs in train() under HF Trainer:
+    eilev/model/v2.py:228-238, scripts/general/train_v2.py:123-130)."""
+    from eilev_b200 import ops
+    from eilev_b200.engine import qformer as E_qf, t5 as E_t5
+    from eilev_b200.train import freeze_for_recipe
+    from oracle import videoblip_ref as R
+    fx, cfg = _load_t5()
+    cfg.qformer_config.hidden_dropout_prob = 0.1
+    cfg.qformer_config.attention_probs_dropout_prob = 0.1
+    cfg.text_config.dropout_rate = 0.1
+    m = build(cfg, fx["state_dict"]).train()
+    freeze_for_recipe(m)
+    m._dropout_seed = torch.full((1,), 777, dtype=torch.int64, device="cuda")
+    out = m(**cuda(fx["inputs"]), return_dict=True)
+    out.loss.backward()
+    seed = m._dropout_seed
+    used = set()
+
+    def drop(site, t):
+        if site is None:
+            return t
+        tower, layer, k = site
+        salt = {"qf": E_qf._SALT_QF + (layer * 8 + k if layer >= 0 else k),
+                "t5e": E_t5._SALT_T5 + layer * 8 + k,
+                "t5d": E_t5._SALT_T5 + E_t5._T5_DEC + layer * 8 + k,
+                "t5": E_t5._SALT_T5 + E_t5._T5_STACK + k}[tower]
+        used.add(tower)
+        rows = t.numel() // t.shape[-1]
+        mask = ops.dropout(torch.ones(rows, t.shape[-1], dtype=torch.bfloat16, device="cuda"), 0.1, seed, salt)
+        return t * mask.float().cpu().view(t.shape)
+
+    sd = {k: v.clone() for k, v in fx["state_dict"].items()}
+    for k in fx["grads"]:
+        sd[k].requires_grad_(True)
+    ref = R.videoblip_forward_t5(sd, cfg, **fx["inputs"], drop=drop)
+    ref["loss"].backward()
+    assert used == {"qf", "t5e", "t5d", "t5"}, used
+    assert abs(float(ref["loss"]) - float(fx["loss"])) > 1e-3  # the masks really changed the computation
+    num = den = 0.0
+    for n_, p_ in m.named_parameters():
+        if p_.grad is not None:
+            rg = sd[n_].grad
+            num += float((p_.grad.float().cpu() - rg).pow(2).sum())
+            den += float(rg.pow(2).sum())
+    glob = (num / den) ** 0.5
+    r = dict(loss=float(out.loss.detach()), loss_ref=float(ref["loss"]), logits=rel_l2(out.logits, ref["logits"]),
+             grad_rel_l2=glob)
+    _dump("dropout/small_t5", **r)
+    assert abs(r["loss"] - r["loss_ref"]) < 0.05, r
+    assert r["logits"] < 0.03, r
+    assert glob < 0.08, r   # no-dropout gap of this fixture: 1.3 % (test_t5_backward_matches_reference_golden)
+    # eval mode stays mask-free
+    m.eval()
+    with torch.no_grad():
+        e1 = m(**cuda(fx["inputs"]), return_dict=True)
+    assert abs(float(e1.loss) - float(fx["loss"])) < 0.03
 
 
 def test_t5_generate_matches_reference_golden_and_text_only():
