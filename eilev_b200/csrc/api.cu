@@ -198,6 +198,22 @@ int vb_resize_u8_pass(const void* in, void* out, const int32_t* bounds, const in
                                      out_elem_stride, lines_fastest, st(stream)));
 }
 
+int vb_crop_resize_normalize_u8(const void* frames_u8, int64_t c, int64_t t, int64_t h, int64_t w, int64_t crop_top,
+                                int64_t crop_left, int64_t crop_h, int64_t crop_w, int32_t flip, void* out,
+                                int32_t out_dtype, int64_t out_h, int64_t out_w, double rescale, const float* mean,
+                                const float* stdv, void* stream) {
+  if (frames_u8 == nullptr || out == nullptr || mean == nullptr || stdv == nullptr || c < 1 || c > 4 || t < 1 ||
+      crop_h < 1 || crop_w < 1 || crop_top < 0 || crop_left < 0 || crop_top + crop_h > h || crop_left + crop_w > w ||
+      out_h < 1 || out_w < 1 || (out_dtype != VB_F32 && out_dtype != VB_BF16))
+    return fail_msg("vb_crop_resize_normalize_u8", "bad arguments");
+  for (int64_t i = 0; i < c; ++i)
+    if (!(stdv[i] > 0.0f)) return fail_msg("vb_crop_resize_normalize_u8", "std must be positive");
+  VB_CHECK("vb_crop_resize_normalize_u8",
+           vb::crop_resize_normalize_launch(frames_u8, c, t, h, w, crop_top, crop_left, crop_h, crop_w, flip, out,
+                                            out_dtype == VB_BF16 ? 1 : 0, out_h, out_w, static_cast<float>(rescale),
+                                            mean, stdv, st(stream)));
+}
+
 int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
                 int64_t dim, void* stream) {
   VB_CHECK("vb_cls_rows", vb::cls_rows_launch(cls, pos, hidden, frames, tokens, dim, st(stream)));

@@ -38,6 +38,14 @@ VB_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a 3-D box (no shared memory, no barrier): the later cp.async.bulk.tensor load of the same box
+// hits L2 instead of paying the DRAM latency.
+VB_DEVICE void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // A operand from TMEM (bf16 pairs per 32-bit column), B from shared memory.
 VB_DEVICE void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                             uint32_t accumulate) {
@@ -421,6 +429,7 @@ struct PpParams {
   int items, heads, s, d;
   int dpad;            // d rounded up to 16: N of the P.V instruction
   float scale_log2;
+  int poll;            // MMA issuer probes QK^T / P.V readiness instead of a fixed issue order
 };
 
 VB_DEVICE void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
@@ -510,6 +519,25 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           tma_load_3d(dst + kTaChunkBytesQ, &tmap_q, &q_full[buf], 64, h, row0 + t * kTaQRows);
           ++g;
         };
+        {
+          // K and V live in single buffers, so the next item's loads can only be issued once this item has
+          // released them and their latency lands on the critical path (profiles/r02_attn_pp_notes.txt: 30 %
+          // of the softmax warps' time was spent waiting for P.V, i.e. for V).  Pull the next item's
+          // K / V / Q rows into L2 now; the loads then pay an L2 hit instead of a DRAM round trip.
+          const int nxt = item + gridDim.x;
+          if (nxt < p.items) {
+            const int nb = nxt / p.heads, nh = nxt % p.heads;
+            const int nrow0 = nb * p.s;
+            const int n_c = (p.d + 63) / 64;
+            for (int c = 0; c < n_c; ++c)
+              for (int hf = 0; hf < 2; ++hf) {
+                tma_prefetch_3d(&tmap_k, c * 64, nh, nrow0 + hf * kTaHalf);
+                tma_prefetch_3d(&tmap_v, c * 64, nh, nrow0 + hf * kTaHalf);
+              }
+            for (int t = 0; t < m_tiles; ++t)
+              for (int c = 0; c < n_c; ++c) tma_prefetch_3d(&tmap_q, c * 64, nh, nrow0 + t * kTaQRows);
+          }
+        }
         mbar_wait(k_empty, k_ph ^ 1u);
         k_ph ^= 1u;
         mbar_expect_tx(k_full, 2 * kTaChunkBytesK);
@@ -570,7 +598,39 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       int item = blockIdx.x;
       bool k_ready = false;
       long long t_idle = clock64();
-      while (item < p.items || n_pend > 0) {
+      if (!p.poll) {
+        // fixed issue order: QK^T of tile g, then P.V of tile g-1 (A/B switch VB_ATTN_POLL=0)
+        for (; item < p.items; item += gridDim.x) {
+          mbar_wait(k_full, k_ph);
+          k_ph ^= 1u;
+          for (t = 0; t < m_tiles; ++t) {
+            const int slot = g & 1;
+            mbar_wait(&q_full[slot], q_ph[slot]);
+            q_ph[slot] ^= 1u;
+            mbar_wait(&slot_free[slot], free_ph[slot] ^ 1u);
+            free_ph[slot] ^= 1u;
+            tc_fence_after();
+            for (int ks = 0; ks < k_steps; ++ks) {
+              const int c = ks >> 2, kk = ks & 3;
+              const uint64_t a_desc =
+                  umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
+              const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
+              umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
+            }
+            umma_commit(&q_empty[slot]);
+            if (t == m_tiles - 1) umma_commit(k_empty);
+            umma_commit(&s_full[slot]);
+            if (have_prev) issue_pv();
+            have_prev = true;
+            prev_slot = slot;
+            prev_first = (t == 0);
+            prev_last = (t == m_tiles - 1);
+            ++g;
+          }
+        }
+        if (have_prev) issue_pv();
+      }
+      while (p.poll && (item < p.items || n_pend > 0)) {
         bool progressed = false;
         if (n_pend > 0) {
           const Pend f = pend[0];
@@ -936,6 +996,11 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
     pp.d = static_cast<int>(a.d);
     pp.dpad = (pp.d + 15) / 16 * 16;
     pp.scale_log2 = a.scale * 1.4426950408889634f;
+    static const int poll = [] {
+      const char* e = std::getenv("VB_ATTN_POLL");
+      return (e != nullptr && e[0] == '1') ? 1 : 0;
+    }();
+    pp.poll = poll;
     const int grid_pp = pp.items < sms ? pp.items : sms;
     attn_tcgen05_pp_kernel<<<grid_pp, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, pp);
     return cudaGetLastError();

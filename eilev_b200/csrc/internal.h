@@ -35,6 +35,10 @@ cudaError_t resize_u8_pass_launch(const void* in, void* out, const int* bounds, 
                                   long long planes, long long lines, long long out_len, long long ksize,
                                   long long ips, long long ils, long long ies, long long ops,
                                   long long ols, long long oes, int lines_fastest, cudaStream_t s);
+cudaError_t crop_resize_normalize_launch(const void* in, long long c, long long t, long long h, long long w,
+                                         long long top, long long left, long long ch, long long cw, int flip,
+                                         void* out, int out_bf16, long long oh, long long ow, float rescale,
+                                         const float* mean, const float* stdv, cudaStream_t s);
 cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long long frames,
                             long long tokens, long long dim, cudaStream_t s);
 cudaError_t embed_splice_launch(const long long* ids, const long long* attn, const long long* vmask,

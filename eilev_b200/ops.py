@@ -299,6 +299,31 @@ def patch_gather_u8(frames: torch.Tensor, patch: int, kpad: int, rescale: float,
     return out
 
 
+def crop_resize_normalize_u8(frames: torch.Tensor, box: tuple[int, int, int, int], out_size: tuple[int, int],
+                             rescale: float, mean, std, *, flip: bool = False,
+                             out: torch.Tensor | None = None, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Training-time frame transform of one decoded clip (train_v2.py:143-167): uint8 (C, T, H, W) ->
+    (C, T, out_h, out_w) f32 | bf16 = flip(bicubic_interpolate(crop(frames, box))) * rescale, normalised.
+    box = (top, left, height, width), drawn on the host (data/preprocess.py::resized_crop_params)."""
+    _need(frames, torch.uint8, "crop_resize_normalize_u8.frames")
+    assert frames.dim() == 4 and frames.is_contiguous()
+    c, t, h, w = frames.shape
+    top, left, ch, cw = (int(v) for v in box)
+    oh, ow = int(out_size[0]), int(out_size[1])
+    if len(mean) != c or len(std) != c or c > 4:
+        raise ValueError(f"crop_resize_normalize_u8: {c} channels need {c} (<= 4) mean / std values")
+    if out is None:
+        out = torch.empty((c, t, oh, ow), dtype=dtype, device=frames.device)
+    else:
+        assert out.shape == (c, t, oh, ow) and out.is_contiguous() and out.dtype in (torch.float32, torch.bfloat16)
+    arr = C.c_float * c
+    check(_lib.lib().vb_crop_resize_normalize_u8(frames.data_ptr(), c, t, h, w, top, left, ch, cw, int(bool(flip)),
+                                                 out.data_ptr(), _DT[out.dtype], oh, ow, float(rescale),
+                                                 arr(*[float(m) for m in mean]), arr(*[float(v) for v in std]),
+                                                 _stream()), "vb_crop_resize_normalize_u8")
+    return out
+
+
 _RESIZE_TABLES: dict = {}
 
 

@@ -234,6 +234,18 @@ int vb_resize_u8_pass(const void* in, void* out, const int32_t* bounds, const in
                       int64_t in_line_stride, int64_t in_elem_stride, int64_t out_plane_stride,
                       int64_t out_line_stride, int64_t out_elem_stride, int32_t lines_fastest, void* stream);
 
+/* Training-time frame transform of one clip on the device (scripts/general/train_v2.py:143-167: pytorchvideo
+ * ConvertUint8ToFloat -> Normalize -> RandomResizedCrop(bicubic) -> RandomHorizontalFlip): reads the crop box
+ * [crop_top, crop_top + crop_h) x [crop_left, crop_left + crop_w) of every plane of a decoded uint8 clip
+ * (c, t, h, w), resizes it to (out_h, out_w) as torch.nn.functional.interpolate(mode="bicubic",
+ * align_corners=False) does (cubic convolution, A = -0.75, taps clamped to the crop), mirrors the columns when
+ * flip != 0 and writes (x * rescale - mean[c]) / std[c] as f32 or bf16 (c, t, out_h, out_w), contiguous.
+ * The crop box and the flip are drawn on the host (integer bookkeeping). */
+int vb_crop_resize_normalize_u8(const void* frames_u8, int64_t c, int64_t t, int64_t h, int64_t w, int64_t crop_top,
+                                int64_t crop_left, int64_t crop_h, int64_t crop_w, int32_t flip, void* out,
+                                int32_t out_dtype, int64_t out_h, int64_t out_w, double rescale, const float* mean,
+                                const float* stdv, void* stream);
+
 /* hidden[f, 0, :] = cls + pos[0]  for every frame f (HF:...:249-254). bf16. */
 int vb_cls_rows(const void* cls, const void* pos, void* hidden, int64_t frames, int64_t tokens,
                 int64_t dim, void* stream);
