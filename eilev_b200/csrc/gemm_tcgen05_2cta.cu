@@ -66,6 +66,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int num_tiles = m_tiles * n_tiles;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
+  // width of the last column block: the real columns rounded up to 32 (UMMA N % 16 per CTA half), <= BN
+  const int n_rem = static_cast<int>(p.n - static_cast<long long>(n_tiles - 1) * BN);
+  const int n_last = (n_rem + 31) / 32 * 32 < BN ? (n_rem + 31) / 32 * 32 : BN;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -101,7 +104,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_a = m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
-        const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);
+        // the pair's B tile is split in halves along N; a narrower last column block (n_last < BN) splits
+        // its own width, so each CTA's half starts n_last / 2 rows apart
+        const int tile_n = (n_blk == n_tiles - 1) ? n_last : BN;
+        const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (tile_n / 2);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
@@ -115,7 +121,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN);
+      constexpr uint32_t idesc_full = umma_idesc_bf16(2 * k2BM, BN);
+      // last column block of an N that is not a multiple of BN (ViT: 1408 = 5 x 256 + 128): issue the MMA at
+      // the width that holds real columns (rounded up to 32) instead of multiplying zero-filled rows
+      const uint32_t idesc_last = umma_idesc_bf16(2 * k2BM, static_cast<uint32_t>(n_last));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -124,6 +133,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t idesc = (tile % n_tiles == n_tiles - 1) ? idesc_last : idesc_full;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
