@@ -91,6 +91,8 @@ struct AttnParams {
 
 template <int DP>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   constexpr int LDS = DP + 8;
   constexpr int KS = DP / 16;  // k-steps of Q.K^T
   constexpr int NB = DP / 8;   // n-blocks of the output
@@ -310,7 +312,7 @@ static cudaError_t launch_fwd(const AttnParams& p, int batch, cudaStream_t strea
     attr = true;
   }
   dim3 grid(p.heads, (p.sq + kAM - 1) / kAM, batch);
-  attn_fwd_kernel<DP><<<grid, kAttnThreads, smem, stream>>>(p);
+  launch_pdl(attn_fwd_kernel<DP>, dim3(grid), dim3(kAttnThreads), smem, stream, p);
   return cudaGetLastError();
 }
 
@@ -387,6 +389,8 @@ struct AttnBwdParams {
 __global__ void __launch_bounds__(128)
 attn_delta_kernel(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta, int sq, int heads,
                   int D, long long o_bs, long long o_rs, long long total) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= total) return;
@@ -403,6 +407,8 @@ attn_delta_kernel(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta
 
 template <int DP>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdParams bp) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const AttnParams& p = bp.f;
   constexpr int LDS = DP + 8;
   constexpr int LDP = 72;
@@ -618,6 +624,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
 __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* dq_acc, __nv_bfloat16* dq, int sq, int hd, long long dq_bs,
                        long long dq_rs, float mul, long long total) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long c = i % hd;
@@ -638,7 +646,7 @@ static cudaError_t launch_bwd(const AttnBwdParams& bp, int batch, cudaStream_t s
     attr = true;
   }
   dim3 grid(bp.f.heads, (bp.f.skv + kAN - 1) / kAN, batch);
-  attn_bwd_kernel<DP><<<grid, kAttnThreads, smem, stream>>>(bp);
+  launch_pdl(attn_bwd_kernel<DP>, dim3(grid), dim3(kAttnThreads), smem, stream, bp);
   return cudaGetLastError();
 }
 
@@ -683,7 +691,7 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   bp.scale = f.scale;
 
   const long long rows = f.batch * f.heads * f.sq;
-  attn_delta_kernel<<<static_cast<unsigned>((rows * 32 + 127) / 128), 128, 0, stream>>>(
+  launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((rows * 32 + 127) / 128)), dim3(128), 0, stream, 
       p.o, bp.d_o, a.delta, p.sq, p.heads, p.d, p.o_bs, p.o_rs, rows);
   const long long hd = f.heads * f.d;
   const long long total = f.batch * f.sq * hd;
@@ -704,7 +712,7 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   }
   if (e != cudaSuccess) return e;
   const unsigned grid = static_cast<unsigned>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
-  attn_dq_convert_kernel<<<grid, 256, 0, stream>>>(a.dq_acc, reinterpret_cast<__nv_bfloat16*>(a.dq),
+  launch_pdl(attn_dq_convert_kernel, dim3(grid), dim3(256), 0, stream, a.dq_acc, reinterpret_cast<__nv_bfloat16*>(a.dq),
                                                    p.sq, static_cast<int>(hd), a.dq_bs, a.dq_rs,
                                                    a.dq_scale == 0.0f ? 1.0f : a.dq_scale, total);
   return cudaGetLastError();

@@ -38,14 +38,6 @@ VB_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// L2 prefetch of a 3-D box (no shared memory, no barrier): the later cp.async.bulk.tensor load of the same box
-// hits L2 instead of paying the DRAM latency.
-VB_DEVICE void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 // A operand from TMEM (bf16 pairs per 32-bit column), B from shared memory.
 VB_DEVICE void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                             uint32_t accumulate) {
@@ -429,7 +421,6 @@ struct PpParams {
   int items, heads, s, d;
   int dpad;            // d rounded up to 16: N of the P.V instruction
   float scale_log2;
-  int poll;            // MMA issuer probes QK^T / P.V readiness instead of a fixed issue order
 };
 
 VB_DEVICE void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
@@ -504,40 +495,21 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t k_ph = 0, v_ph = 0, q_ph = 0;  // q_ph: one phase bit per Q buffer (no local-memory arrays)
+      uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0};
       int g = 0;  // running Q tile counter -> buffer = slot = g & 1
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int b = item / p.heads, h = item % p.heads;
         const int row0 = b * p.s;
         auto load_q = [&](int t) {
           const int buf = g & 1;
-          mbar_wait(&q_empty[buf], ((q_ph >> buf) & 1u) ^ 1u);
-          q_ph ^= 1u << buf;
+          mbar_wait(&q_empty[buf], q_ph[buf] ^ 1u);
+          q_ph[buf] ^= 1u;
           mbar_expect_tx(&q_full[buf], 2 * kTaChunkBytesQ);
           uint8_t* dst = sQ + buf * 2 * kTaChunkBytesQ;
           tma_load_3d(dst, &tmap_q, &q_full[buf], 0, h, row0 + t * kTaQRows);
           tma_load_3d(dst + kTaChunkBytesQ, &tmap_q, &q_full[buf], 64, h, row0 + t * kTaQRows);
           ++g;
         };
-        {
-          // K and V live in single buffers, so the next item's loads can only be issued once this item has
-          // released them and their latency lands on the critical path (profiles/r02_attn_pp_notes.txt: 30 %
-          // of the softmax warps' time was spent waiting for P.V, i.e. for V).  Pull the next item's
-          // K / V / Q rows into L2 now; the loads then pay an L2 hit instead of a DRAM round trip.
-          const int nxt = item + gridDim.x;
-          if (nxt < p.items) {
-            const int nb = nxt / p.heads, nh = nxt % p.heads;
-            const int nrow0 = nb * p.s;
-            const int n_c = (p.d + 63) / 64;
-            for (int c = 0; c < n_c; ++c)
-              for (int hf = 0; hf < 2; ++hf) {
-                tma_prefetch_3d(&tmap_k, c * 64, nh, nrow0 + hf * kTaHalf);
-                tma_prefetch_3d(&tmap_v, c * 64, nh, nrow0 + hf * kTaHalf);
-              }
-            for (int t = 0; t < m_tiles; ++t)
-              for (int c = 0; c < n_c; ++c) tma_prefetch_3d(&tmap_q, c * 64, nh, nrow0 + t * kTaQRows);
-          }
-        }
         mbar_wait(k_empty, k_ph ^ 1u);
         k_ph ^= 1u;
         mbar_expect_tx(k_full, 2 * kTaChunkBytesK);
@@ -564,7 +536,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       const uint32_t idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(p.dpad)) | (1u << 16);  // B MN-major
       const int k_steps = (p.d + 15) / 16;
       const int kv_main = (s_main + 15) / 16;          // 16-key blocks of P in columns [0, 128)
-      uint32_t k_ph = 0, v_ph = 0, q_ph = 0, free_ph = 0, p_ph = 0;  // one phase bit per slot
+      uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0}, free_ph[2] = {0, 0}, p_ph[2] = {0, 0};
       bool have_prev = false, prev_first = false, prev_last = false;
       int prev_slot = 0;
       auto issue_pv = [&]() {
@@ -573,8 +545,8 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           mbar_wait(v_full, v_ph);
           v_ph ^= 1u;
         }
-        mbar_wait(&p_ready[slot], (p_ph >> slot) & 1u);
-        p_ph ^= 1u << slot;
+        mbar_wait(&p_ready[slot], p_ph[slot]);
+        p_ph[slot] ^= 1u;
         tc_fence_after();
         const uint32_t t0 = tmem_base + slot * 256;
         for (int js = 0; js < kv_main; ++js) {
@@ -588,106 +560,36 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         if (prev_last) umma_commit(v_empty);
         umma_commit(&o_full[slot]);
       };
-      // QK^T of the next tile and P.V of the oldest tile whose softmax is pending are issued in whichever
-      // order their inputs become ready (non-blocking probes): a P.V never waits behind a QK^T whose slot
-      // is still being drained by the other warp group's epilogue, and vice versa.  QK^T is probed first:
-      // it starts a softmax (the long pole), a P.V only an epilogue.
-      struct Pend { int slot; bool first, last; };
-      Pend pend0 = {0, false, false}, pend1 = {0, false, false};  // oldest first
-      int n_pend = 0;
-      int g = 0, t = 0;
-      int item = blockIdx.x;
-      bool k_ready = false;
-      long long t_idle = clock64();
-      if (!p.poll) {
-        // fixed issue order: QK^T of tile g, then P.V of tile g-1 (A/B switch VB_ATTN_POLL=0)
-        for (; item < p.items; item += gridDim.x) {
-          mbar_wait(k_full, k_ph);
-          k_ph ^= 1u;
-          for (t = 0; t < m_tiles; ++t) {
-            const int slot = g & 1;
-            mbar_wait(&q_full[slot], (q_ph >> slot) & 1u);
-            q_ph ^= 1u << slot;
-            mbar_wait(&slot_free[slot], ((free_ph >> slot) & 1u) ^ 1u);
-            free_ph ^= 1u << slot;
-            tc_fence_after();
-            for (int ks = 0; ks < k_steps; ++ks) {
-              const int c = ks >> 2, kk = ks & 3;
-              const uint64_t a_desc =
-                  umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
-              const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
-              umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
-            }
-            umma_commit(&q_empty[slot]);
-            if (t == m_tiles - 1) umma_commit(k_empty);
-            umma_commit(&s_full[slot]);
-            if (have_prev) issue_pv();
-            have_prev = true;
-            prev_slot = slot;
-            prev_first = (t == 0);
-            prev_last = (t == m_tiles - 1);
-            ++g;
-          }
-        }
-        if (have_prev) issue_pv();
-      }
-      while (p.poll && (item < p.items || n_pend > 0)) {
-        bool progressed = false;
-        if (item < p.items && n_pend < 2) {
+      int g = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        mbar_wait(k_full, k_ph);
+        k_ph ^= 1u;
+        for (int t = 0; t < m_tiles; ++t) {
           const int slot = g & 1;
-          if (!k_ready && t == 0) k_ready = mbar_test(k_full, k_ph);
-          if ((t > 0 || k_ready) && mbar_test(&q_full[slot], (q_ph >> slot) & 1u) &&
-              mbar_test(&slot_free[slot], ((free_ph >> slot) & 1u) ^ 1u)) {
-            if (t == 0) {
-              k_ph ^= 1u;
-              k_ready = false;
-            }
-            q_ph ^= 1u << slot;
-            free_ph ^= 1u << slot;
-            tc_fence_after();
-            for (int ks = 0; ks < k_steps; ++ks) {
-              const int c = ks >> 2, kk = ks & 3;
-              const uint64_t a_desc =
-                  umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
-              const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
-              umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
-            }
-            umma_commit(&q_empty[slot]);
-            if (t == m_tiles - 1) umma_commit(k_empty);
-            umma_commit(&s_full[slot]);
-            const Pend np = {slot, t == 0, t == m_tiles - 1};
-            if (n_pend == 0) pend0 = np; else pend1 = np;
-            ++n_pend;
-            ++g;
-            if (++t == m_tiles) {
-              t = 0;
-              item += gridDim.x;
-            }
-            progressed = true;
+          mbar_wait(&q_full[slot], q_ph[slot]);
+          q_ph[slot] ^= 1u;
+          mbar_wait(&slot_free[slot], free_ph[slot] ^ 1u);  // epilogue of tile g-2 has drained O
+          free_ph[slot] ^= 1u;
+          tc_fence_after();
+          for (int ks = 0; ks < k_steps; ++ks) {
+            const int c = ks >> 2, kk = ks & 3;
+            const uint64_t a_desc =
+                umma_desc_k_sw128(smem_u32(sQ + slot * 2 * kTaChunkBytesQ + c * kTaChunkBytesQ)) + 2 * kk;
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(sK + c * kTaChunkBytesK)) + 2 * kk;
+            umma_bf16(tmem_base + slot * 256, a_desc, b_desc, idesc_s, ks != 0 ? 1u : 0u);
           }
-        }
-        if (n_pend > 0) {
-          const Pend f = pend0;
-          const bool v_ok = !f.first || mbar_test(v_full, v_ph);
-          if (v_ok && mbar_test(&p_ready[f.slot], (p_ph >> f.slot) & 1u)) {
-            prev_slot = f.slot;
-            prev_first = f.first;
-            prev_last = f.last;
-            issue_pv();  // its own waits return immediately: both barriers were just observed complete
-            pend0 = pend1;
-            --n_pend;
-            progressed = true;
-          }
-        }
-        if (progressed) {
-          t_idle = clock64();
-        } else {
-          // yield the scheduler: this lane shares its SM sub-partition with two softmax warps, and a tight
-          // probe loop took a third of their issue slots (profiles/r02_attn_pp_notes.txt)
-          __nanosleep(40);
-          if (clock64() - t_idle > 4000000000LL) __trap();  // a mis-programmed pipeline surfaces as an error
+          umma_commit(&q_empty[slot]);
+          if (t == m_tiles - 1) umma_commit(k_empty);
+          umma_commit(&s_full[slot]);
+          if (have_prev) issue_pv();
+          have_prev = true;
+          prev_slot = slot;
+          prev_first = (t == 0);
+          prev_last = (t == m_tiles - 1);
+          ++g;
         }
       }
+      if (have_prev) issue_pv();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax + epilogue (one slot per warp group)
@@ -751,31 +653,42 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         tc_fence_after();
         float inv_sum = 0.0f;
         if (warp_has_rows) {
-          // ---- pass 1: row maximum, three 32-column loads in flight per wait (a TMEM load + wait costs
-          // ~150 cycles of latency under load; the maximum needs 8 of them)
+          // ---- pass 1: row maximum (two 32-column loads in flight)
           float m0 = tail, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-          auto chunk_max = [&](const uint32_t (&r)[32], int ch) {
+          for (int ch = 0; ch < n_chunks; ch += 2) {
+            uint32_t r0[32], r1[32];
+            const bool two = ch + 1 < n_chunks;
+            tmem_ld_32(t_row + ch * 32, r0);
+            if (two) tmem_ld_32(t_row + (ch + 1) * 32, r1);
+            tmem_ld_wait();
             if (ch * 32 + 32 <= s_main) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                m0 = fmaxf(m0, __uint_as_float(r[j]));
-                m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
-                m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
-                m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+                m0 = fmaxf(m0, __uint_as_float(r0[j]));
+                m1 = fmaxf(m1, __uint_as_float(r0[j + 1]));
+                m2 = fmaxf(m2, __uint_as_float(r0[j + 2]));
+                m3 = fmaxf(m3, __uint_as_float(r0[j + 3]));
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (ch * 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r[j]));
+                if (ch * 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r0[j]));
             }
-          };
-          for (int ch = 0; ch < n_chunks; ch += 2) {
-            uint32_t r0[32], r1[32];
-            tmem_ld_32(t_row + ch * 32, r0);
-            if (ch + 1 < n_chunks) tmem_ld_32(t_row + (ch + 1) * 32, r1);
-            tmem_ld_wait();
-            chunk_max(r0, ch);
-            if (ch + 1 < n_chunks) chunk_max(r1, ch + 1);
+            if (two) {
+              if (ch * 32 + 64 <= s_main) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  m0 = fmaxf(m0, __uint_as_float(r1[j]));
+                  m1 = fmaxf(m1, __uint_as_float(r1[j + 1]));
+                  m2 = fmaxf(m2, __uint_as_float(r1[j + 2]));
+                  m3 = fmaxf(m3, __uint_as_float(r1[j + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (ch * 32 + 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r1[j]));
+              }
+            }
           }
           const float mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
           // ---- pass 2: p = 2^(s*c - max*c), row sum, bf16 P over the consumed S columns; the load of
@@ -839,29 +752,36 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         tc_fence_after();
         if (warp_has_rows) {
           __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.s + qi) * p.o_rs + h * p.d;
-          // O (dpad <= 96 columns) in two batches of three 16-column loads, one wait each
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t ro[3][16];
-#pragma unroll
-            for (int gi = 0; gi < 3; ++gi)
-              if (half * 3 + gi < n16) tmem_ld_16(t_row + kPpColO + (half * 3 + gi) * 16, ro[gi]);
+          for (int gi = 0; gi < n16; gi += 2) {
+            uint32_t r0[16], r1[16];
+            const bool two = gi + 1 < n16;
+            tmem_ld_16(t_row + kPpColO + gi * 16, r0);
+            if (two) tmem_ld_16(t_row + kPpColO + (gi + 1) * 16, r1);
             tmem_ld_wait();
             if (qi < p.s) {
 #pragma unroll
-              for (int gi = 0; gi < 3; ++gi) {
-                if (half * 3 + gi < n16) {
+              for (int j = 0; j < 16; j += 8) {
+                const int c0 = gi * 16 + j;
+                if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
+                  uint4 u;
+                  u.x = pack_bf16x2(__uint_as_float(r0[j]) * inv_sum, __uint_as_float(r0[j + 1]) * inv_sum);
+                  u.y = pack_bf16x2(__uint_as_float(r0[j + 2]) * inv_sum, __uint_as_float(r0[j + 3]) * inv_sum);
+                  u.z = pack_bf16x2(__uint_as_float(r0[j + 4]) * inv_sum, __uint_as_float(r0[j + 5]) * inv_sum);
+                  u.w = pack_bf16x2(__uint_as_float(r0[j + 6]) * inv_sum, __uint_as_float(r0[j + 7]) * inv_sum);
+                  *reinterpret_cast<uint4*>(orow + c0) = u;
+                }
+              }
+              if (two) {
 #pragma unroll
-                  for (int j = 0; j < 16; j += 8) {
-                    const int c0 = (half * 3 + gi) * 16 + j;
-                    if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
-                      uint4 u;
-                      u.x = pack_bf16x2(__uint_as_float(ro[gi][j]) * inv_sum, __uint_as_float(ro[gi][j + 1]) * inv_sum);
-                      u.y = pack_bf16x2(__uint_as_float(ro[gi][j + 2]) * inv_sum, __uint_as_float(ro[gi][j + 3]) * inv_sum);
-                      u.z = pack_bf16x2(__uint_as_float(ro[gi][j + 4]) * inv_sum, __uint_as_float(ro[gi][j + 5]) * inv_sum);
-                      u.w = pack_bf16x2(__uint_as_float(ro[gi][j + 6]) * inv_sum, __uint_as_float(ro[gi][j + 7]) * inv_sum);
-                      *reinterpret_cast<uint4*>(orow + c0) = u;
-                    }
+                for (int j = 0; j < 16; j += 8) {
+                  const int c0 = (gi + 1) * 16 + j;
+                  if (c0 < p.d) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(r1[j]) * inv_sum, __uint_as_float(r1[j + 1]) * inv_sum);
+                    u.y = pack_bf16x2(__uint_as_float(r1[j + 2]) * inv_sum, __uint_as_float(r1[j + 3]) * inv_sum);
+                    u.z = pack_bf16x2(__uint_as_float(r1[j + 4]) * inv_sum, __uint_as_float(r1[j + 5]) * inv_sum);
+                    u.w = pack_bf16x2(__uint_as_float(r1[j + 6]) * inv_sum, __uint_as_float(r1[j + 7]) * inv_sum);
+                    *reinterpret_cast<uint4*>(orow + c0) = u;
                   }
                 }
               }
@@ -978,11 +898,6 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
     pp.d = static_cast<int>(a.d);
     pp.dpad = (pp.d + 15) / 16 * 16;
     pp.scale_log2 = a.scale * 1.4426950408889634f;
-    static const int poll = [] {
-      const char* e = std::getenv("VB_ATTN_POLL");
-      return (e != nullptr && e[0] == '0') ? 0 : 1;
-    }();
-    pp.poll = poll;
     const int grid_pp = pp.items < sms ? pp.items : sms;
     attn_tcgen05_pp_kernel<<<grid_pp, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, pp);
     return cudaGetLastError();

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256)
 patch_gather_kernel(const T* __restrict__ px, __nv_bfloat16* __restrict__ out, long long nv,
                     long long C, long long T_, long long H, long long W, long long P, long long gh,
                     long long gw, long long kpad, long long total) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const long long col = idx % kpad;
@@ -48,13 +50,13 @@ cudaError_t patch_gather_launch(const void* px, int dtype, void* out, long long 
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (dtype == VB_F32)
-    patch_gather_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(px), o, nv, c, t,
+    launch_pdl(patch_gather_kernel<float>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float*>(px), o, nv, c, t,
                                                     h, w, patch, gh, gw, kpad, total);
   else if (dtype == VB_BF16)
-    patch_gather_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
+    launch_pdl(patch_gather_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, 
         reinterpret_cast<const __nv_bfloat16*>(px), o, nv, c, t, h, w, patch, gh, gw, kpad, total);
   else if (dtype == VB_F16)
-    patch_gather_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(px), o, nv, c,
+    launch_pdl(patch_gather_kernel<__half>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __half*>(px), o, nv, c,
                                                      t, h, w, patch, gh, gw, kpad, total);
   else
     return cudaErrorInvalidValue;
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(256)
 patch_gather_u8_kernel(const unsigned char* __restrict__ px, __nv_bfloat16* __restrict__ out,
                        long long C, long long T_, long long H, long long W, long long P,
                        long long gh, long long gw, long long kpad, long long total, FrameNorm nrm) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const long long col = idx % kpad;
@@ -113,7 +117,7 @@ cudaError_t patch_gather_u8_launch(const void* px, void* out, long long nv, long
   }
   nrm.rescale = rescale;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  patch_gather_u8_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned char*>(px),
+  launch_pdl(patch_gather_u8_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const unsigned char*>(px),
                                               reinterpret_cast<__nv_bfloat16*>(out), c, t, h, w,
                                               patch, gh, gw, kpad, total, nrm);
   return cudaGetLastError();
@@ -130,6 +134,8 @@ resize_u8_pass_kernel(const unsigned char* __restrict__ in, unsigned char* __res
                       const int* __restrict__ bounds, const int* __restrict__ kk, long long planes,
                       long long lines, long long out_len, int ksize, long long ips, long long ils,
                       long long ies, long long ops, long long ols, long long oes, int lines_fastest) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per_plane = lines * out_len;
   if (idx >= planes * per_plane) return;
@@ -153,7 +159,7 @@ cudaError_t resize_u8_pass_launch(const void* in, void* out, const int* bounds, 
   const long long total = planes * lines * out_len;
   if (total <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  resize_u8_pass_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned char*>(in),
+  launch_pdl(resize_u8_pass_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const unsigned char*>(in),
                                              reinterpret_cast<unsigned char*>(out), bounds, kk, planes,
                                              lines, out_len, static_cast<int>(ksize), ips, ils, ies, ops,
                                              ols, oes, lines_fastest);
@@ -163,6 +169,8 @@ cudaError_t resize_u8_pass_launch(const void* in, void* out, const int* bounds, 
 __global__ void cls_rows_kernel(const __nv_bfloat16* cls, const __nv_bfloat16* pos,
                                 __nv_bfloat16* hidden, long long frames, long long tokens,
                                 long long dim) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= frames * dim) return;
   const long long f = idx / dim, c = idx % dim;
@@ -174,7 +182,7 @@ cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long
                             long long tokens, long long dim, cudaStream_t s) {
   const long long total = frames * dim;
   if (total <= 0) return cudaSuccess;
-  cls_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+  launch_pdl(cls_rows_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(cls), reinterpret_cast<const __nv_bfloat16*>(pos),
       reinterpret_cast<__nv_bfloat16*>(hidden), frames, tokens, dim);
   return cudaGetLastError();
@@ -187,6 +195,8 @@ __global__ void __launch_bounds__(1024)
 splice_index_kernel(const long long* attn, const long long* vmask, int* slot_index, int* pos_ids,
                     int* status, long long batch, long long seq, long long pos_offset,
                     long long n_features) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ int partial[1024];
   const long long n = batch * seq;
   const int tid = threadIdx.x;
@@ -230,6 +240,8 @@ splice_gather_kernel(const long long* ids, const int* slot_index, const int* pos
                      const __nv_bfloat16* embed, const __nv_bfloat16* feats,
                      const __nv_bfloat16* pos_table, __nv_bfloat16* inputs_embeds,
                      __nv_bfloat16* hidden, long long dim, long long vocab, long long n_features) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long pos = blockIdx.x;
   const int slot = slot_index[pos];
   const __nv_bfloat16* src;
@@ -256,6 +268,8 @@ splice_gather_kernel(const long long* ids, const int* slot_index, const int* pos
 __global__ void __launch_bounds__(128)
 splice_bwd_kernel(const __nv_bfloat16* d_embeds, const int* slot_index, __nv_bfloat16* d_feats,
                   long long dim, long long n_features) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long pos = blockIdx.x;
   const int slot = slot_index[pos];
   if (slot < 0 || slot >= n_features) return;
@@ -268,6 +282,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ce_row_kernel(const T* logits, const long long* labels, float* row_lse, long long seq,
               long long vocab, long long ldl, int shift) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   // block r handles logits row (b, l); target = labels[b, l+shift] (1: causal LM, 0: seq2seq)
   const long long r = blockIdx.x;
   const long long l = r % seq;
@@ -309,6 +325,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ce_finalize_kernel(const T* logits, const long long* labels, const float* row_lse, float* loss,
                    int* n_valid, long long rows, long long seq, long long vocab, long long ldl, int shift) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ float ssum[256];
   __shared__ int scnt[256];
   float acc = 0.0f;
@@ -343,6 +361,8 @@ __global__ void __launch_bounds__(256)
 ce_bwd_kernel(const T* logits, const long long* labels, const float* row_lse, const int* n_valid,
               const float* grad_scale, __nv_bfloat16* dlogits, long long seq, long long vocab,
               long long ldl, long long ldd, int shift) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long r = blockIdx.x;
   const long long l = r % seq;
   bool valid = (l + shift < seq);
@@ -373,12 +393,12 @@ cudaError_t ce_launch(const void* logits, int dtype, const long long* labels, fl
   if (rows <= 0 || shift < 0 || shift > 1) return cudaErrorInvalidValue;
   if (dtype == VB_BF16) {
     const __nv_bfloat16* lg = reinterpret_cast<const __nv_bfloat16*>(logits);
-    ce_row_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl, shift);
-    ce_finalize_kernel<__nv_bfloat16><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl, shift);
+    launch_pdl(ce_row_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, s, lg, labels, row_lse, seq, vocab, ldl, shift);
+    launch_pdl(ce_finalize_kernel<__nv_bfloat16>, dim3(1), dim3(256), 0, s, lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl, shift);
   } else if (dtype == VB_F32) {
     const float* lg = reinterpret_cast<const float*>(logits);
-    ce_row_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(lg, labels, row_lse, seq, vocab, ldl, shift);
-    ce_finalize_kernel<float><<<1, 256, 0, s>>>(lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl, shift);
+    launch_pdl(ce_row_kernel<float>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, s, lg, labels, row_lse, seq, vocab, ldl, shift);
+    launch_pdl(ce_finalize_kernel<float>, dim3(1), dim3(256), 0, s, lg, labels, row_lse, loss, n_valid, rows, seq, vocab, ldl, shift);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -393,10 +413,10 @@ cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels
   if (rows <= 0 || shift < 0 || shift > 1) return cudaErrorInvalidValue;
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dlogits);
   if (dtype == VB_BF16)
-    ce_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, s>>>(
+    launch_pdl(ce_bwd_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, s, 
         reinterpret_cast<const __nv_bfloat16*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd, shift);
   else if (dtype == VB_F32)
-    ce_bwd_kernel<float><<<static_cast<unsigned>(rows), 256, 0, s>>>(
+    launch_pdl(ce_bwd_kernel<float>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, s, 
         reinterpret_cast<const float*>(logits), labels, row_lse, n_valid, grad_scale, d, seq, vocab, ldl, ldd, shift);
   else
     return cudaErrorInvalidValue;
@@ -407,6 +427,8 @@ cudaError_t ce_bwd_launch(const void* logits, int dtype, const long long* labels
 __global__ void __launch_bounds__(256)
 transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                  long long rows, long long cols, long long ld_in, long long ld_out) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ __nv_bfloat16 tile[32][34];
   const long long c0 = static_cast<long long>(blockIdx.x) * 32;
   const long long r0 = static_cast<long long>(blockIdx.y) * 32;
@@ -429,7 +451,7 @@ cudaError_t transpose_launch(const void* in, void* out, long long rows, long lon
   if (rows <= 0 || cols <= 0) return cudaSuccess;
   dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
   if (grid.y > 65535) return cudaErrorInvalidValue;
-  transpose_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+  launch_pdl(transpose_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(in),
                                         reinterpret_cast<__nv_bfloat16*>(out), rows, cols, ld_in,
                                         ld_out);
   return cudaGetLastError();
@@ -437,6 +459,8 @@ cudaError_t transpose_launch(const void* in, void* out, long long rows, long lon
 
 template <typename S, typename D>
 __global__ void __launch_bounds__(256) convert_kernel(const S* src, D* dst, long long n) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = from_f32<D>(to_f32<S>(src[i]));
@@ -445,9 +469,9 @@ __global__ void __launch_bounds__(256) convert_kernel(const S* src, D* dst, long
 template <typename S>
 static cudaError_t convert_from(const S* src, void* dst, int dd, long long n, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
-  if (dd == VB_BF16) convert_kernel<S, __nv_bfloat16><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
-  else if (dd == VB_F32) convert_kernel<S, float><<<grid, 256, 0, s>>>(src, reinterpret_cast<float*>(dst), n);
-  else if (dd == VB_F16) convert_kernel<S, __half><<<grid, 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  if (dd == VB_BF16) launch_pdl(convert_kernel<S, __nv_bfloat16>, dim3(grid), dim3(256), 0, s, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  else if (dd == VB_F32) launch_pdl(convert_kernel<S, float>, dim3(grid), dim3(256), 0, s, src, reinterpret_cast<float*>(dst), n);
+  else if (dd == VB_F16) launch_pdl(convert_kernel<S, __half>, dim3(grid), dim3(256), 0, s, src, reinterpret_cast<__half*>(dst), n);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -464,6 +488,8 @@ cudaError_t convert_launch(const void* src, int sd, void* dst, int dd, long long
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* saved, __nv_bfloat16* dx, int epi,
                long long n) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float g = __bfloat162float(dy[i]);
@@ -480,7 +506,7 @@ cudaError_t act_bwd_launch(const void* dy, const void* saved, void* dx, int epi,
                            cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
-  act_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+  launch_pdl(act_bwd_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(dy),
                                       reinterpret_cast<const __nv_bfloat16*>(saved),
                                       reinterpret_cast<__nv_bfloat16*>(dx), epi, n);
   return cudaGetLastError();
@@ -489,6 +515,8 @@ cudaError_t act_bwd_launch(const void* dy, const void* saved, void* dx, int epi,
 // Block = 32 columns x 8 row lanes; grid.y splits rows; atomics only across grid.y.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* x, float* out, long long rows, long long cols, long long ldx) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ float sm[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const long long c = static_cast<long long>(blockIdx.x) * 32 + cx;
@@ -520,12 +548,14 @@ cudaError_t colsum_launch(const void* x, float* out, long long rows, long long c
   unsigned gy = static_cast<unsigned>(rows / 2048 + 1);
   if (gy > 64) gy = 64;
   dim3 grid(static_cast<unsigned>((cols + 31) / 32), gy);
-  colsum_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ldx);
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ldx);
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
 add_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, long long n) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = __float2bfloat16(__bfloat162float(a[i]) + __bfloat162float(b[i]));
@@ -534,7 +564,7 @@ add_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, lon
 cudaError_t add_launch(const void* a, const void* b, void* y, long long n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
-  add_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+  launch_pdl(add_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(a),
                                   reinterpret_cast<const __nv_bfloat16*>(b),
                                   reinterpret_cast<__nv_bfloat16*>(y), n);
   return cudaGetLastError();
@@ -544,6 +574,8 @@ __global__ void __launch_bounds__(256)
 dropout_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, long long rows, long long cols, long long ldx,
                long long ldy, unsigned int thresh, float scale, const unsigned long long* seed_ptr,
                unsigned long long salt) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const uint64_t seed = *seed_ptr + salt;
   const long long total = rows * cols;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -561,7 +593,7 @@ cudaError_t dropout_launch(const void* x, void* y, long long rows, long long col
   if (n <= 0) return cudaSuccess;
   if (seed == nullptr || !(p >= 0.0f) || p >= 1.0f) return cudaErrorInvalidValue;
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
-  dropout_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_pdl(dropout_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(x),
                                       reinterpret_cast<__nv_bfloat16*>(y), rows, cols, ldx, ldy,
                                       dropout_threshold(p), 1.0f / (1.0f - p), seed, salt);
   return cudaGetLastError();
@@ -571,6 +603,8 @@ cudaError_t dropout_launch(const void* x, void* y, long long rows, long long col
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
              float b2, float eps, float wd, float bc1, float bc2_sqrt, const float* grad_scale) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const float gs = grad_scale != nullptr ? *grad_scale : 1.0f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -594,11 +628,13 @@ cudaError_t adamw_launch(float* p, const float* g, float* m, float* v, long long
   const float bc1 = 1.0f - powf(b1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(b2, static_cast<float>(step));
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
-  adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+  launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
   return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* x, long long n, float* out) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ float red[8];
   float acc = 0.0f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -618,7 +654,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* x, long long n,
 cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 4 ? n / 256 + 1 : 148 * 4);
-  sumsq_kernel<<<grid, 256, 0, s>>>(x, n, out);
+  launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, x, n, out);
   return cudaGetLastError();
 }
 
@@ -629,6 +665,8 @@ cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s
 __global__ void __launch_bounds__(256)
 attn_merge_kernel(const __nv_bfloat16* o1, const float* lse1, long long s1, const __nv_bfloat16* o2,
                   const float* lse2, long long s2, __nv_bfloat16* out, long long rows, int heads, int d) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long hd = static_cast<long long>(heads) * d;
   const long long total = rows * hd;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -657,7 +695,7 @@ cudaError_t attn_merge_launch(const void* o1, const float* lse1, long long s1, c
   const long long total = rows * heads * d;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  attn_merge_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+  launch_pdl(attn_merge_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(o1), lse1, s1, reinterpret_cast<const __nv_bfloat16*>(o2),
       lse2, s2, reinterpret_cast<__nv_bfloat16*>(out), rows, static_cast<int>(heads), static_cast<int>(d));
   return cudaGetLastError();
@@ -669,6 +707,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 token_logprob_kernel(const T* logits, const long long* row_index, const long long* targets, float* out,
                      long long vocab, long long ldl) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long i = blockIdx.x;
   const long long target = targets[i];
   if (target < 0 || target >= vocab) {
@@ -704,10 +744,10 @@ cudaError_t token_logprob_launch(const void* logits, int dtype, const long long*
                                  long long ldl, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   if (dtype == VB_BF16)
-    token_logprob_kernel<__nv_bfloat16><<<static_cast<unsigned>(n), 256, 0, s>>>(
+    launch_pdl(token_logprob_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(n)), dim3(256), 0, s, 
         reinterpret_cast<const __nv_bfloat16*>(logits), row_index, targets, out, vocab, ldl);
   else if (dtype == VB_F32)
-    token_logprob_kernel<float><<<static_cast<unsigned>(n), 256, 0, s>>>(
+    launch_pdl(token_logprob_kernel<float>, dim3(static_cast<unsigned>(n)), dim3(256), 0, s, 
         reinterpret_cast<const float*>(logits), row_index, targets, out, vocab, ldl);
   else
     return cudaErrorInvalidValue;
@@ -723,9 +763,9 @@ cudaError_t embed_splice_launch(const long long* ids, const long long* attn, con
                                 cudaStream_t s) {
   const long long n = batch * seq;
   if (n <= 0) return cudaErrorInvalidValue;
-  splice_index_kernel<<<1, 1024, 0, s>>>(attn, vmask, slot_index, pos_ids, status, batch, seq,
+  launch_pdl(splice_index_kernel, dim3(1), dim3(1024), 0, s, attn, vmask, slot_index, pos_ids, status, batch, seq,
                                          pos_offset, n_features);
-  splice_gather_kernel<<<static_cast<unsigned>(n), 128, 0, s>>>(
+  launch_pdl(splice_gather_kernel, dim3(static_cast<unsigned>(n)), dim3(128), 0, s, 
       ids, slot_index, pos_ids, reinterpret_cast<const __nv_bfloat16*>(embed),
       reinterpret_cast<const __nv_bfloat16*>(feats), reinterpret_cast<const __nv_bfloat16*>(pos_table),
       reinterpret_cast<__nv_bfloat16*>(inputs_embeds), reinterpret_cast<__nv_bfloat16*>(hidden), dim,
@@ -737,7 +777,7 @@ cudaError_t splice_bwd_launch(const void* d_embeds, const int* slot_index, void*
                               long long positions, long long dim, long long n_features,
                               cudaStream_t s) {
   if (positions <= 0) return cudaSuccess;
-  splice_bwd_kernel<<<static_cast<unsigned>(positions), 128, 0, s>>>(
+  launch_pdl(splice_bwd_kernel, dim3(static_cast<unsigned>(positions)), dim3(128), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(d_embeds), slot_index,
       reinterpret_cast<__nv_bfloat16*>(d_feats), dim, n_features);
   return cudaGetLastError();

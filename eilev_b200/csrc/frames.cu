@@ -38,6 +38,8 @@ struct CropParams {
 };
 
 __global__ void __launch_bounds__(256) crop_resize_normalize_kernel(const CropParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per_plane = p.oh * p.ow;
   if (idx >= p.c * p.t * per_plane) return;
@@ -96,7 +98,7 @@ cudaError_t crop_resize_normalize_launch(const void* in, long long c, long long 
   }
   p.flip = flip;
   p.out_bf16 = out_bf16;
-  crop_resize_normalize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(p);
+  launch_pdl(crop_resize_normalize_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, p);
   return cudaGetLastError();
 }
 

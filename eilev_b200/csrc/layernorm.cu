@@ -24,6 +24,8 @@ struct LnParams {
 // VPL = 16-byte vectors per lane; cols <= VPL*256, cols % 8 == 0.
 template <int VPL>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParam
 }
 
 __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_generic_kernel(const LnParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_generic_kernel(const LnP
 template <int VPL>
 static void launch_vec(const LnParams& p, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
-  ln_fwd_vec_kernel<VPL><<<grid, kLnWarps * 32, 0, s>>>(p);
+  launch_pdl(ln_fwd_vec_kernel<VPL>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
 }
 
 cudaError_t layernorm_launch(const LnParams& p, cudaStream_t s) {
@@ -146,7 +150,7 @@ cudaError_t layernorm_launch(const LnParams& p, cudaStream_t s) {
     else launch_vec<12>(p, s);
   } else {
     const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
-    ln_fwd_generic_kernel<<<grid, kLnWarps * 32, 0, s>>>(p);
+    launch_pdl(ln_fwd_generic_kernel, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
   }
   return cudaGetLastError();
 }
@@ -167,6 +171,8 @@ struct LnBwdParams {
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.  One warp per row.
 __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_kernel(const LnBwdParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_kernel(const LnBwdPar
 // reductions and the store, 16-byte loads/stores (cols % 8 == 0, cols <= VPL*256).
 template <int VPL>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBwdParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -258,6 +266,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBw
 // dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy.  Block = 32 columns x 8 row lanes;
 // every column is owned by exactly one block, so the accumulation is deterministic.
 __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const LnBwdParams p) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ float sg[8][33], sb[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const long long c = static_cast<long long>(blockIdx.x) * 32 + cx;
@@ -289,14 +299,14 @@ cudaError_t layernorm_bwd_launch(const LnBwdParams& p, cudaStream_t s) {
   const bool vec = p.cols % 8 == 0 && p.cols <= 12 * 256 && al(p.dy) && al(p.xin) && al(p.dx) &&
                    al(p.gamma) && (p.dx_add == nullptr || al(p.dx_add));
   const int vpl = static_cast<int>((p.cols / 8 + 31) / 32);
-  if (!vec) ln_bwd_dx_kernel<<<grid, kLnWarps * 32, 0, s>>>(p);
-  else if (vpl <= 1) ln_bwd_dx_vec_kernel<1><<<grid, kLnWarps * 32, 0, s>>>(p);
-  else if (vpl <= 3) ln_bwd_dx_vec_kernel<3><<<grid, kLnWarps * 32, 0, s>>>(p);
-  else if (vpl <= 6) ln_bwd_dx_vec_kernel<6><<<grid, kLnWarps * 32, 0, s>>>(p);
-  else if (vpl <= 10) ln_bwd_dx_vec_kernel<10><<<grid, kLnWarps * 32, 0, s>>>(p);
-  else ln_bwd_dx_vec_kernel<12><<<grid, kLnWarps * 32, 0, s>>>(p);
+  if (!vec) launch_pdl(ln_bwd_dx_kernel, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 1) launch_pdl(ln_bwd_dx_vec_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 3) launch_pdl(ln_bwd_dx_vec_kernel<3>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 6) launch_pdl(ln_bwd_dx_vec_kernel<6>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 10) launch_pdl(ln_bwd_dx_vec_kernel<10>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else launch_pdl(ln_bwd_dx_vec_kernel<12>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
   if (p.dgamma != nullptr && p.dbeta != nullptr) {
-    ln_bwd_param_kernel<<<static_cast<unsigned>((p.cols + 31) / 32), 256, 0, s>>>(p);
+    launch_pdl(ln_bwd_param_kernel, dim3(static_cast<unsigned>((p.cols + 31) / 32)), dim3(256), 0, s, p);
   }
   return cudaGetLastError();
 }
@@ -335,6 +345,8 @@ cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, c
 // One warp per row; read-only pass (2 B per element).
 __global__ void __launch_bounds__(kLnWarps * 32)
 row_stats_kernel(const __nv_bfloat16* x, float* stats, long long rows, long long cols, long long ldx) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -370,7 +382,7 @@ cudaError_t row_stats_launch(const void* x, float* stats, long long rows, long l
                              cudaStream_t s) {
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
-  row_stats_kernel<<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), stats, rows, cols, ldx);
+  launch_pdl(row_stats_kernel, dim3(grid), dim3(kLnWarps * 32), 0, s, reinterpret_cast<const __nv_bfloat16*>(x), stats, rows, cols, ldx);
   return cudaGetLastError();
 }
 

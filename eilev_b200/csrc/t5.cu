@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                    __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, long long rows, int cols,
                    long long ldx, long long ldy, float eps, int vec) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -55,7 +57,7 @@ cudaError_t rmsnorm_fwd_launch(const void* x, const float* gamma, void* y, float
   if (x == nullptr || gamma == nullptr || y == nullptr) return cudaErrorInvalidValue;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const int vec = (cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && al(x) && al(y) && al(gamma)) ? 1 : 0;
-  rmsnorm_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
+  launch_pdl(rmsnorm_fwd_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(y), rstd, rows,
       static_cast<int>(cols), ldx, ldy, eps, vec);
   return cudaGetLastError();
@@ -68,6 +70,8 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
                    const float* __restrict__ gamma, const float* __restrict__ rstd,
                    const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx, long long rows,
                    int cols, int vec) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -125,7 +129,7 @@ cudaError_t rmsnorm_bwd_launch(const void* dy, const void* x, const float* gamma
     return cudaErrorInvalidValue;
   auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const int vec = (cols % 8 == 0 && al(dy) && al(x) && al(gamma) && al(dx_add) && al(dx)) ? 1 : 0;
-  rmsnorm_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
+  launch_pdl(rmsnorm_bwd_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), gamma, rstd,
       reinterpret_cast<const __nv_bfloat16*>(dx_add), reinterpret_cast<__nv_bfloat16*>(dx), rows,
       static_cast<int>(cols), vec);
@@ -148,6 +152,8 @@ VB_DEVICE float gelu_tanh_grad(float x) {
 __global__ void __launch_bounds__(256)
 gated_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h01, __nv_bfloat16* __restrict__ out, long long rows,
                       long long dff, int vec) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long step = vec ? 8 : 1;
   const long long total = rows * dff / step;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -176,6 +182,8 @@ gated_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h01, __nv_bfloat16* __re
 __global__ void __launch_bounds__(256)
 gated_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ h01,
                       __nv_bfloat16* __restrict__ d_h01, long long rows, long long dff, int vec) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long step = vec ? 8 : 1;
   const long long total = rows * dff / step;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -216,7 +224,7 @@ static unsigned ew_grid(long long total) {
 cudaError_t gated_gelu_fwd_launch(const void* h01, void* out, long long rows, long long dff, cudaStream_t s) {
   if (rows * dff <= 0) return cudaSuccess;
   const int vec = (dff % 8 == 0 && al16(h01) && al16(out)) ? 1 : 0;
-  gated_gelu_fwd_kernel<<<ew_grid(rows * dff / (vec ? 8 : 1)), 256, 0, s>>>(
+  launch_pdl(gated_gelu_fwd_kernel, dim3(ew_grid(rows * dff / (vec ? 8 : 1))), dim3(256), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(h01), reinterpret_cast<__nv_bfloat16*>(out), rows, dff, vec);
   return cudaGetLastError();
 }
@@ -225,7 +233,7 @@ cudaError_t gated_gelu_bwd_launch(const void* d_out, const void* h01, void* d_h0
                                   long long dff, cudaStream_t s) {
   if (rows * dff <= 0) return cudaSuccess;
   const int vec = (dff % 8 == 0 && al16(d_out) && al16(h01) && al16(d_h01)) ? 1 : 0;
-  gated_gelu_bwd_kernel<<<ew_grid(rows * dff / (vec ? 8 : 1)), 256, 0, s>>>(
+  launch_pdl(gated_gelu_bwd_kernel, dim3(ew_grid(rows * dff / (vec ? 8 : 1))), dim3(256), 0, s, 
       reinterpret_cast<const __nv_bfloat16*>(d_out), reinterpret_cast<const __nv_bfloat16*>(h01),
       reinterpret_cast<__nv_bfloat16*>(d_h01), rows, dff, vec);
   return cudaGetLastError();
@@ -234,6 +242,8 @@ cudaError_t gated_gelu_bwd_launch(const void* d_out, const void* h01, void* d_h0
 __global__ void __launch_bounds__(128)
 embedding_kernel(const long long* ids, const __nv_bfloat16* __restrict__ table, __nv_bfloat16* __restrict__ out,
                  long long dim, long long vocab) {
+  pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
+  pdl_trigger();  // the next kernel of the stream may start its prologue
   const long long i = blockIdx.x;
   long long id = ids[i];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -243,7 +253,7 @@ embedding_kernel(const long long* ids, const __nv_bfloat16* __restrict__ table, 
 cudaError_t embedding_launch(const long long* ids, const void* table, void* out, long long n, long long dim,
                              long long vocab, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  embedding_kernel<<<static_cast<unsigned>(n), 128, 0, s>>>(ids, reinterpret_cast<const __nv_bfloat16*>(table),
+  launch_pdl(embedding_kernel, dim3(static_cast<unsigned>(n)), dim3(128), 0, s, ids, reinterpret_cast<const __nv_bfloat16*>(table),
                                                             reinterpret_cast<__nv_bfloat16*>(out), dim, vocab);
   return cudaGetLastError();
 }
