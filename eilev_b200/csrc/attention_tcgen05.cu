@@ -150,6 +150,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // programmatic dependent launch: q / k / v of the preceding GEMM are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -491,6 +493,8 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // programmatic dependent launch: q / k / v of the preceding GEMM are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -899,8 +903,8 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
     pp.dpad = (pp.d + 15) / 16 * 16;
     pp.scale_log2 = a.scale * 1.4426950408889634f;
     const int grid_pp = pp.items < sms ? pp.items : sms;
-    attn_tcgen05_pp_kernel<<<grid_pp, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, pp);
-    return cudaGetLastError();
+    return launch_pdl(attn_tcgen05_pp_kernel, dim3(static_cast<unsigned>(grid_pp)), dim3(kTaThreads), kTaSmem, stream,
+                      tq, tk, tv, pp);
   }
   TaParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(a.o);
@@ -913,8 +917,8 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
   p.pv_n = 128;
   if (const char* e = std::getenv("VB_ATTN_PV_NPAD"); e != nullptr && e[0] == '1') p.pv_n = (p.d + 15) / 16 * 16;
   const int grid = p.items < sms ? p.items : sms;
-  attn_tcgen05_kernel<<<grid, kTaThreads, kTaSmem, stream>>>(tq, tk, tv, p);
-  return cudaGetLastError();
+  return launch_pdl(attn_tcgen05_kernel, dim3(static_cast<unsigned>(grid)), dim3(kTaThreads), kTaSmem, stream, tq, tk,
+                    tv, p);
 }
 
 }  // namespace vb

@@ -79,6 +79,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch)
+  // may run under the tail of the preceding kernel; its results are visible from here on.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -269,9 +273,8 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
   long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   int grid = static_cast<int>(tiles < sms ? tiles : sms);
   if (force_grid > 0 && force_grid < grid) grid = force_grid;
-  gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ep, k_blocks,
-                                                                          m_tiles, n_tiles);
-  return cudaGetLastError();
+  return launch_pdl(gemm_tcgen05_kernel<BN>, dim3(static_cast<unsigned>(grid)), dim3(kGemmThreads), Cfg::kSmemBytes,
+                    stream, ta, tb, ep, k_blocks, m_tiles, n_tiles);
 }
 
 void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {

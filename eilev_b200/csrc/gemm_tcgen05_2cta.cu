@@ -95,6 +95,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: the set-up above may overlap the tail of the preceding kernel
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -313,9 +316,8 @@ static cudaError_t launch_2cta(const vb_gemm_args& a, cudaStream_t stream) {
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   long long pairs = sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm_tcgen05_2cta_kernel<BN><<<static_cast<unsigned>(2 * pairs), k2Threads, Cfg::kSmemBytes, stream>>>(
-      ta, tb, tc, ep, k_blocks, m_tiles, n_tiles);
-  return cudaGetLastError();
+  return launch_pdl(gemm_tcgen05_2cta_kernel<BN>, dim3(static_cast<unsigned>(2 * pairs)), dim3(k2Threads),
+                    Cfg::kSmemBytes, stream, ta, tb, tc, ep, k_blocks, m_tiles, n_tiles);
 }
 
 // bn: 256 or 176 (the ViT widths 1408 / 4224 are multiples of 176)
