@@ -68,6 +68,7 @@ SIGNATURES: dict[str, list] = {
     "vb_crop_resize_normalize_u8": [vp, i64, i64, i64, i64, i64, i64, i64, i64, i32, vp, i32, i64, i64, C.c_double,
                                     C.POINTER(C.c_float), C.POINTER(C.c_float), vp],
     "vb_attention_fwd": [C.POINTER(AttnArgs), vp],
+    "vb_attention_probs": [C.POINTER(AttnArgs), vp, i32, vp],
     "vb_attention_uses_tcgen05": [C.POINTER(AttnArgs)],
     "vb_attention_bwd": [C.POINTER(AttnBwdArgs), vp],
     "vb_patch_gather": [vp, i32, vp, i64, i64, i64, i64, i64, i64, i64, vp],

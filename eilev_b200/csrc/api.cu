@@ -110,6 +110,14 @@ int vb_attention_fwd(const vb_attn_args* a, void* stream) {
   VB_CHECK("vb_attention_fwd", vb::attention_fwd_launch(*a, st(stream)));
 }
 
+int vb_attention_probs(const vb_attn_args* a, void* probs, int32_t probs_dtype, void* stream) {
+  if (a == nullptr || a->q == nullptr || a->k == nullptr || probs == nullptr)
+    return fail_msg("vb_attention_probs", "null operand");
+  if (probs_dtype != VB_F32 && probs_dtype != VB_BF16) return fail_msg("vb_attention_probs", "bad probs_dtype");
+  if (a->d <= 0 || (a->d + a->skv) * 4 > 48 * 1024) return fail_msg("vb_attention_probs", "d + skv too large");
+  VB_CHECK("vb_attention_probs", vb::attention_probs_launch(*a, probs, probs_dtype == VB_BF16 ? 1 : 0, st(stream)));
+}
+
 int vb_attention_uses_tcgen05(const vb_attn_args* a) {
   return (a != nullptr && vb::attention_tcgen05_eligible(*a)) ? 1 : 0;
 }

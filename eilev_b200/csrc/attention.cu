@@ -718,4 +718,89 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------ attention maps (diagnostic output)
+// probs[b, h, i, :] = softmax_j(scale * q_i . k_j (+ causal / key-padding mask)) written out in full — the
+// `attentions` the reference returns with output_attentions=True (eilev/model/v2.py:87-95;
+// HF:blip_2/modeling_blip_2.py:319-353).  The fused kernels never materialise these maps; this plain CUDA-core
+// kernel (one CTA per query row, keys dealt to the threads) exists only for that optional output and is not on
+// the training / generation path.
+struct ProbsParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const uint8_t* key_mask;
+  int sq, skv, d, heads;
+  long long q_bs, q_rs, k_bs, k_rs;
+  float scale;
+  int causal;
+};
+
+__global__ void __launch_bounds__(128) attn_probs_kernel(const ProbsParams p, void* probs, int out_bf16) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sh[];            // [d] q row, then [skv] scores
+  float* sq = sh;
+  float* sc = sh + p.d;
+  __shared__ float red[4];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const __nv_bfloat16* q = p.q + static_cast<long long>(b) * p.q_bs + static_cast<long long>(i) * p.q_rs + h * p.d;
+  for (int c = tid; c < p.d; c += 128) sq[c] = __bfloat162float(q[c]);
+  __syncthreads();
+  const int limit = p.causal ? (i + (p.skv - p.sq) + 1) : p.skv;  // keys j < limit are visible
+  float mx = -INFINITY;
+  for (int j = tid; j < p.skv; j += 128) {
+    float s = -INFINITY;
+    const bool ok = j < limit && (p.key_mask == nullptr || p.key_mask[static_cast<long long>(b) * p.skv + j] != 0);
+    if (ok) {
+      const __nv_bfloat16* k = p.k + static_cast<long long>(b) * p.k_bs + static_cast<long long>(j) * p.k_rs + h * p.d;
+      float acc = 0.0f;
+      for (int c = 0; c < p.d; ++c) acc = fmaf(sq[c], __bfloat162float(k[c]), acc);
+      s = acc * p.scale;
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.0f;
+  for (int j = tid; j < p.skv; j += 128) {
+    const float e = sc[j] == -INFINITY ? 0.0f : __expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  sum = (red[0] + red[1]) + (red[2] + red[3]);
+  const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+  const long long base = ((static_cast<long long>(b) * p.heads + h) * p.sq + i) * p.skv;
+  for (int j = tid; j < p.skv; j += 128) {
+    const float v = sc[j] * inv;
+    if (out_bf16) reinterpret_cast<__nv_bfloat16*>(probs)[base + j] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(probs)[base + j] = v;
+  }
+}
+
+cudaError_t attention_probs_launch(const vb_attn_args& a, void* probs, int out_bf16, cudaStream_t stream) {
+  if (a.batch <= 0 || a.sq <= 0 || a.skv <= 0) return cudaSuccess;
+  if (a.heads > 65535 || a.batch > 65535) return cudaErrorInvalidValue;
+  ProbsParams p;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(a.k);
+  p.key_mask = a.key_mask;
+  p.sq = static_cast<int>(a.sq); p.skv = static_cast<int>(a.skv);
+  p.d = static_cast<int>(a.d); p.heads = static_cast<int>(a.heads);
+  p.q_bs = a.q_bs; p.q_rs = a.q_rs; p.k_bs = a.k_bs; p.k_rs = a.k_rs;
+  p.scale = a.scale;
+  p.causal = a.causal;
+  const size_t smem = static_cast<size_t>(a.d + a.skv) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  const dim3 grid(static_cast<unsigned>(a.sq), static_cast<unsigned>(a.heads), static_cast<unsigned>(a.batch));
+  return launch_pdl(attn_probs_kernel, grid, dim3(128), smem, stream, p, probs, out_bf16);
+}
+
 }  // namespace vb

@@ -420,6 +420,9 @@ constexpr int kPpColTail = 224;
 struct PpParams {
   __nv_bfloat16* o;
   long long o_rs;
+  const __nv_bfloat16* q;   // raw q rows (row stride q_rs): the 257th query row is read straight from global memory
+  long long q_rs;
+  int row256;               // 1: the last query row of S = 257 is computed by warps 2-3 (no third Q tile)
   int items, heads, s, d;
   int dpad;            // d rounded up to 16: N of the P.V instruction
   float scale_log2;
@@ -461,7 +464,12 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.s + kTaQRows - 1) / kTaQRows;
+  // S = 257 = 2 x 128 + 1: a third 128-row tile for ONE query row would cost a full QK^T / softmax / P.V
+  // round (a third of the kernel).  That row is computed instead by the two otherwise idle warps 2-3 with
+  // mma.sync straight from the K / V tiles already in shared memory (below), and only two tiles go through
+  // the TMEM pipeline.
+  const bool row256 = p.row256 != 0 && p.s == 257;
+  const int m_tiles = row256 ? 2 : (p.s + kTaQRows - 1) / kTaQRows;
   const bool has_tail = p.s > 256;           // exactly one key (index 256) beyond the slot
   const int s_main = has_tail ? 256 : p.s;   // keys whose scores live in TMEM
 
@@ -480,9 +488,9 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       mbar_init(&slot_free[i], 4);
     }
     mbar_init(k_full, 1);
-    mbar_init(k_empty, 1 + 4 * m_tiles);
+    mbar_init(k_empty, 1 + 4 * m_tiles + (row256 ? 2 : 0));
     mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
+    mbar_init(v_empty, 1 + (row256 ? 2 : 0));
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -594,6 +602,114 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         }
       }
       if (have_prev) issue_pv();
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------ warps 2-3: the 257th query row
+    if (row256) {
+      const int w = warp - 2;
+      const int k_steps = (p.d + 15) / 16;
+      const int n_mb = p.dpad / 16;                      // 16-wide blocks of the head dim (6 for d = 88)
+      const int d_lo = w == 0 ? 0 : (n_mb + 1) / 2, d_hi = w == 0 ? (n_mb + 1) / 2 : n_mb;
+      const int kb_lo = w == 0 ? 0 : 9, kb_hi = w == 0 ? 9 : 17;   // 16-key blocks of the 272 staged keys
+      __nv_bfloat16* pbuf = reinterpret_cast<__nv_bfloat16*>(bars + 20);   // [272] probabilities (bf16)
+      float* xch = reinterpret_cast<float*>(bars + 20) + 140;              // [4] max / sum of the two warps
+      int n_item = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n_item) {
+        const int b = item / p.heads, h = item % p.heads;
+        const long long row = static_cast<long long>(b) * p.s + 256;
+        // q_256 as the n = 0 column of the B fragments (lanes 0-3), 16 head-dim elements per k-step
+        uint32_t qb[8][2];
+        {
+          const __nv_bfloat16* qrow = p.q + row * p.q_rs + h * p.d;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const int d0 = ks * 16 + lane * 2;
+            qb[ks][0] = (lane < 4 && ks < k_steps && d0 < p.d) ? *reinterpret_cast<const uint32_t*>(qrow + d0) : 0u;
+            qb[ks][1] = (lane < 4 && ks < k_steps && d0 + 8 < p.d) ? *reinterpret_cast<const uint32_t*>(qrow + d0 + 8) : 0u;
+          }
+        }
+        mbar_wait(k_full, static_cast<uint32_t>(n_item & 1));
+        // scores s_j = q_256 . k_j: A = 16 keys x 16 dims of the swizzled K tile, D column 0 holds the scores
+        float sc[9][2];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const int kb = kb_lo + i;
+          sc[i][0] = sc[i][1] = -INFINITY;
+          if (kb < kb_hi) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              if (ks < k_steps) {
+                const int c = ks >> 2, kk = ks & 3;
+                const int krow = kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int unit = 2 * kk + (lane >> 4);
+                uint32_t a[4];
+                ldmatrix_x4(a, smem_u32(sK + c * kTaChunkBytesK + krow * 128 + ((unit ^ (krow & 7)) << 4)));
+                mma_bf16_16816(acc, a, qb[ks][0], qb[ks][1]);
+              }
+            }
+            const int key0 = kb * 16 + (lane >> 2);
+            if ((lane & 3) == 0) {
+              if (key0 < p.s) sc[i][0] = acc[0];
+              if (key0 + 8 < p.s) sc[i][1] = acc[2];
+            }
+            mx = fmaxf(mx, fmaxf(sc[i][0], sc[i][1]));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(k_empty);   // this warp is done with K
+        mx = warp_max(mx);
+        if (lane == 0) xch[w] = mx;
+        named_bar_sync(5, 64);
+        mx = fmaxf(xch[0], xch[1]);
+        const float mxs = mx * p.scale_log2;
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const int kb = kb_lo + i;
+          if (kb < kb_hi && (lane & 3) == 0) {
+            const int key0 = kb * 16 + (lane >> 2);
+            const float p0 = sc[i][0] == -INFINITY ? 0.0f : exp2f(fmaf(sc[i][0], p.scale_log2, -mxs));
+            const float p1 = sc[i][1] == -INFINITY ? 0.0f : exp2f(fmaf(sc[i][1], p.scale_log2, -mxs));
+            sum += p0 + p1;
+            pbuf[key0] = __float2bfloat16(p0);
+            pbuf[key0 + 8] = __float2bfloat16(p1);
+          }
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) xch[2 + w] = sum;
+        named_bar_sync(5, 64);                 // probabilities of both warps are in pbuf
+        const float inv_sum = 1.0f / (xch[2] + xch[3]);
+        // o[d] = sum_j p_j V[j][d]: A = V^T (16 dims x 16 keys, transposed on load), B column 0 = p
+        mbar_wait(v_full, static_cast<uint32_t>(n_item & 1));
+        __nv_bfloat16* orow = p.o + row * p.o_rs + h * p.d;
+        for (int mb = d_lo; mb < d_hi; ++mb) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int ks = 0; ks < 17; ++ks) {
+            const int key = ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+            const int ug = 2 * mb + ((lane >> 3) & 1);
+            uint32_t a[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                         : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                         : "r"(smem_u32(sV + (ug >> 3) * kTaChunkBytesK + key * 128 + (((ug & 7) ^ (key & 7)) << 4))));
+            uint32_t b0 = 0u, b1 = 0u;
+            if (lane < 4) {
+              b0 = *reinterpret_cast<const uint32_t*>(pbuf + ks * 16 + lane * 2);
+              b1 = *reinterpret_cast<const uint32_t*>(pbuf + ks * 16 + lane * 2 + 8);
+            }
+            mma_bf16_16816(acc, a, b0, b1);
+          }
+          if ((lane & 3) == 0) {
+            const int d0 = mb * 16 + (lane >> 2);
+            if (d0 < p.d) orow[d0] = __float2bfloat16(acc[0] * inv_sum);
+            if (d0 + 8 < p.d) orow[d0 + 8] = __float2bfloat16(acc[2] * inv_sum);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(v_empty);   // this warp is done with V
+        named_bar_sync(5, 64);                 // pbuf / xch are free for the next item
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax + epilogue (one slot per warp group)
@@ -902,6 +1018,13 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
     pp.d = static_cast<int>(a.d);
     pp.dpad = (pp.d + 15) / 16 * 16;
     pp.scale_log2 = a.scale * 1.4426950408889634f;
+    pp.q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+    pp.q_rs = a.q_rs;
+    static const int row256 = [] {
+      const char* e = std::getenv("VB_ATTN_ROW256");
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
+    pp.row256 = row256;
     const int grid_pp = pp.items < sms ? pp.items : sms;
     return launch_pdl(attn_tcgen05_pp_kernel, dim3(static_cast<unsigned>(grid_pp)), dim3(kTaThreads), kTaSmem, stream,
                       tq, tk, tv, pp);

@@ -72,10 +72,12 @@ def pack_vision(model, cache: PackCache):
 
 
 def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
-                   output_hidden_states: bool = False, max_frames: int = 192):
+                   output_hidden_states: bool = False, max_frames: int = 192, output_attentions: bool = False):
     """pixel_values (N, C, T, H, W) on the GPU -> (last_hidden (N*T, S, D) bf16,
-    pooled (N*T, D) bf16, hidden_states list|None).  Frames are processed in chunks of
-    `max_frames` to bound activation memory for large eval batches."""
+    pooled (N*T, D) bf16, hidden_states list|None[, attentions list of (N*T, H, S, S) f32]).  Frames are
+    processed in chunks of `max_frames` to bound activation memory for large eval batches.
+    output_attentions: the per-layer attention maps (v2.py:87-95) are computed by a separate plain kernel
+    from the same q / k the fused attention consumes; the fused path itself is unchanged."""
     cfg = model.config
     w = pack_vision(model, cache)
     nv, c, t, h, wd = pixel_values.shape
@@ -106,7 +108,8 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
     last = torch.empty((frames, tokens, dim), dtype=torch.bfloat16, device=pixel_values.device)
     pooled = torch.empty((frames, dim), dtype=torch.bfloat16, device=pixel_values.device)
     all_hidden = [] if output_hidden_states else None
-    if output_hidden_states:
+    all_attn = [] if output_attentions else None
+    if output_hidden_states or output_attentions:
         max_frames = frames  # keep layer outputs aligned
     # whole clips per chunk so patch_gather can address (clip, t) directly
     clips_per = max(1, max_frames // t)
@@ -135,6 +138,8 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
         for lw in w["layers"]:
             if w["fold"]:
                 qkv = ops.gemm(hid2, lw["qkv_w"], lw["qkv_b"], ln_fold=(st1, lw["qkv_cs"], eps)).view(nf, tokens, 3 * dim)
+                if output_attentions:
+                    all_attn.append(ops.attention_probs(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], heads, scale))
                 o = ops.attention(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], heads, scale)
                 ops.gemm(o.view(nf * tokens, dim), lw["proj_w"], lw["proj_b"], residual=hid2, out=hid2,
                          stats_out=st2, stats_zero=st1)  # qkv has consumed st1
@@ -145,6 +150,8 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
             else:
                 y = ops.layernorm(hid2, lw["ln1_g"], lw["ln1_b"], eps)
                 qkv = ops.gemm(y, lw["qkv_w"], lw["qkv_b"]).view(nf, tokens, 3 * dim)
+                if output_attentions:
+                    all_attn.append(ops.attention_probs(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], heads, scale))
                 o = ops.attention(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], heads, scale)
                 ops.gemm(o.view(nf * tokens, dim), lw["proj_w"], lw["proj_b"], residual=hid2, out=hid2)
                 y = ops.layernorm(hid2, lw["ln2_g"], lw["ln2_b"], eps)
@@ -157,4 +164,6 @@ def vision_forward(model, cache: PackCache, pixel_values: torch.Tensor,
         # pooler = post_layernorm applied a second time to the CLS row (HF :525-526)
         cls_rows = last[f0:f1, 0, :].contiguous()
         pooled[f0:f1] = ops.layernorm(cls_rows, w["post_g"], w["post_b"], eps)
+    if output_attentions:
+        return last, pooled, all_hidden, all_attn
     return last, pooled, all_hidden

@@ -266,16 +266,21 @@ class VideoBlipVisionModel(PreTrainedModel):
         hidden_states tuple of (num_videos, time*seq_len, hidden) — v2.py:31-49."""
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")  # v2.py:50-51
-        if output_attentions:
-            raise NotImplementedError(
-                "output_attentions=True: the fused attention kernel never materialises the "
-                "(frames, heads, 257, 257) probability maps")
         _require_cuda(pixel_values, "VideoBlipVisionModel.forward")
         return_dict = return_dict if return_dict is not None else getattr(self.config, "return_dict", True)
         num_videos, _, time, _, _ = pixel_values.size()
+        attentions = None
         with torch.no_grad():  # frozen tower: never builds an autograd graph (train_v2.py:124-125)
-            last, pooled, hidden = E_vis.vision_forward(self, self._pack, pixel_values,
-                                                        bool(output_hidden_states))
+            if output_attentions:
+                # v2.py:87-95: one (num_videos, time, heads, seq_len, seq_len) map per layer; computed by a
+                # separate plain kernel next to the fused attention (which never materialises them)
+                last, pooled, hidden, maps = E_vis.vision_forward(self, self._pack, pixel_values,
+                                                                  bool(output_hidden_states), output_attentions=True)
+                attentions = tuple(a.view(num_videos, time, a.shape[1], a.shape[2], a.shape[3]).to(self.dtype)
+                                   for a in maps)
+            else:
+                last, pooled, hidden = E_vis.vision_forward(self, self._pack, pixel_values,
+                                                            bool(output_hidden_states))
         seq_len = last.size(1)
         dt = self.dtype
         last_hidden_state = last.view(num_videos, time * seq_len, -1).to(dt)
@@ -286,8 +291,8 @@ class VideoBlipVisionModel(PreTrainedModel):
         if return_dict:
             return BaseModelOutputWithPooling(last_hidden_state=last_hidden_state,
                                               pooler_output=pooler_output,
-                                              hidden_states=hidden_states, attentions=None)
-        return (last_hidden_state, pooler_output, hidden_states, None)
+                                              hidden_states=hidden_states, attentions=attentions)
+        return (last_hidden_state, pooler_output, hidden_states, attentions)
 
 
 def _init_weights(owner: PreTrainedModel, module: nn.Module) -> None:
@@ -455,11 +460,13 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         return seed
 
     def _video_features(self, pixel_values: torch.Tensor, output_hidden_states: bool, train: bool,
-                        seed=None):
-        vis_last, vis_pooled, vis_hidden = None, None, None
+                        seed=None, output_attentions: bool = False):
+        vis_last, vis_pooled, vis_hidden, vis_attn = None, None, None, None
         with torch.no_grad():
-            vis_last, vis_pooled, vis_hidden = E_vis.vision_forward(
-                self.vision_model, self.vision_model._pack, pixel_values, output_hidden_states)
+            res = E_vis.vision_forward(self.vision_model, self.vision_model._pack, pixel_values,
+                                       output_hidden_states, output_attentions=output_attentions)
+            vis_last, vis_pooled, vis_hidden = res[:3]
+            vis_attn = res[3] if output_attentions else None
         n, _, t, _, _ = pixel_values.shape
         s = vis_last.size(1)
         image_embeds = vis_last.view(n, t * s, -1)
@@ -469,16 +476,17 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         else:
             with torch.no_grad():
                 feats, qout, _ = E_qf.qformer_forward(self, self._pack, image_embeds, save=False)
-        return feats, qout, (image_embeds, vis_pooled.view(n, t, -1), vis_hidden, n, t, s)
+        return feats, qout, (image_embeds, vis_pooled.view(n, t, -1), vis_hidden, n, t, s, vis_attn)
 
     def _pack_vision_outputs(self, vis, return_dict: bool):
-        image_embeds, pooled, hidden, n, t, s = vis
+        image_embeds, pooled, hidden, n, t, s, maps = vis
         dt = self.dtype
         hs = None if hidden is None else tuple(h.view(n, t * s, -1).to(dt) for h in hidden)
+        at = None if maps is None else tuple(a.view(n, t, a.shape[1], s, s).to(dt) for a in maps)
         if return_dict:
             return BaseModelOutputWithPooling(last_hidden_state=image_embeds.to(dt),
-                                              pooler_output=pooled.to(dt), hidden_states=hs)
-        return (image_embeds.to(dt), pooled.to(dt), hs, None)
+                                              pooler_output=pooled.to(dt), hidden_states=hs, attentions=at)
+        return (image_embeds.to(dt), pooled.to(dt), hs, at)
 
     # ------------------------------------------------------------------ forward
     def forward(
@@ -505,8 +513,8 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
             video_input_mask = video_input_mask.bool()
         else:
             video_input_mask = None  # the reference ignores the mask without pixel values (v2.py:205-213)
-        if output_attentions:
-            raise NotImplementedError("output_attentions=True is not supported by the fused kernels")
+        # output_attentions: the vision tower's maps are returned in vision_outputs.attentions (v2.py:169-177);
+        # the Q-Former's and the LM's fused attention kernels produce none (their `attentions` stay None)
         return_dict = return_dict if return_dict is not None else getattr(self.config, "return_dict", True)
         _require_cuda(input_ids, "VideoBlipForConditionalGeneration.forward")
         want_hidden = bool(output_hidden_states)
@@ -520,7 +528,8 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
         seed = self._next_dropout_seed(input_ids.device) if train else None
         if pixel_values is not None:
             _require_cuda(pixel_values, "VideoBlipForConditionalGeneration.forward")
-            feats, qout, vis = self._video_features(pixel_values, want_hidden, train, seed)
+            feats, qout, vis = self._video_features(pixel_values, want_hidden, train, seed,
+                                                    output_attentions=bool(output_attentions))
             vision_outputs = self._pack_vision_outputs(vis, return_dict)
             q = qout.to(self.dtype)
             query_outputs = (BaseModelOutputWithPoolingAndCrossAttentions(last_hidden_state=q, pooler_output=q[:, 0])

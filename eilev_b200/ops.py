@@ -204,6 +204,20 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     return (o, lse) if need_lse else o
 
 
+def attention_probs(q: torch.Tensor, k: torch.Tensor, heads: int, scale: float, *, causal: bool = False,
+                    key_mask: torch.Tensor | None = None, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """The attention maps softmax(scale * q k^T + masks), (B, H, Sq, Skv): the optional ``attentions`` output
+    (output_attentions=True), computed by a plain kernel off the hot path."""
+    for t, nme in ((q, "q"), (k, "k")):
+        _need(t, torch.bfloat16, f"attention_probs.{nme}")
+        assert t.dim() == 3 and t.stride(2) == 1
+    hd = q.shape[2]
+    probs = torch.empty((q.shape[0], heads, q.shape[1], k.shape[1]), dtype=dtype, device=q.device)
+    a = _attn_args(q, k, k, q, None, key_mask, heads, hd // heads, scale, causal)
+    check(_lib.lib().vb_attention_probs(C.byref(a), probs.data_ptr(), _DT[dtype], _stream()), "vb_attention_probs")
+    return probs
+
+
 def attention_uses_tcgen05(q, k, v, heads: int, *, causal=False, key_mask=None, need_lse=False) -> bool:
     hd = q.shape[2]
     o = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.bfloat16, device=q.device)

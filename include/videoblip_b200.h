@@ -173,6 +173,11 @@ typedef struct vb_attn_args {
   int64_t rel_bias_stride;
 } vb_attn_args;
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
+/* The attention MAPS probs[b, h, i, j] = softmax_j(scale * q_i . k_j + masks), f32 or bf16, (batch, heads, sq, skv)
+ * contiguous: the `attentions` of output_attentions=True (eilev/model/v2.py:87-95).  Only q, k, key_mask, the
+ * shapes / strides, scale and causal of `args` are read.  A diagnostic output computed by a plain CUDA-core
+ * kernel; the fused kernels of vb_attention_fwd never materialise it. */
+int vb_attention_probs(const vb_attn_args* args, void* probs, int32_t probs_dtype, void* stream);
 /* 1 if vb_attention_fwd takes the tcgen05/TMEM kernel (non-causal, unmasked, no lse,
  * 64 <= S <= 272, d <= 128: the ViT shape class), 0 for the mma.sync flash kernel. */
 int vb_attention_uses_tcgen05(const vb_attn_args* args);

@@ -274,6 +274,29 @@ def test_attention_tcgen05_vit_class(b, heads, d, s):
     _close(o, o2, atol=0.02, rtol=0.02, what="tcgen05 vs mma.sync")
 
 
+@pytest.mark.parametrize("b,heads,d,sq,skv,causal", [(3, 4, 88, 257, 257, False), (2, 2, 64, 40, 300, False),
+                                                     (2, 3, 80, 64, 64, True)])
+def test_attention_probs_maps(b, heads, d, sq, skv, causal):
+    """vb_attention_probs: the `attentions` output (eilev/model/v2.py:87-95) = softmax(scale q k^T + masks)."""
+    ops = _ops()
+    hd = heads * d
+    q, k = _rand(b, sq, hd, seed=90), _rand(b, skv, hd, seed=91)
+    key_mask = torch.ones(b, skv, dtype=torch.uint8, device="cuda")
+    key_mask[0, skv - 5:] = 0
+    scale = d ** -0.5
+    probs = ops.attention_probs(q, k, heads, scale, causal=causal, key_mask=key_mask)
+    qf = q.float().view(b, sq, heads, d).transpose(1, 2)
+    kf = k.float().view(b, skv, heads, d).transpose(1, 2)
+    logits = qf @ kf.transpose(-1, -2) * scale
+    logits = logits.masked_fill(key_mask[:, None, None, :] == 0, float("-inf"))
+    if causal:
+        logits = logits.masked_fill(~torch.ones(sq, skv, dtype=torch.bool, device="cuda").tril(skv - sq), float("-inf"))
+    ref = torch.softmax(logits, dim=-1)
+    assert probs.shape == (b, heads, sq, skv) and probs.dtype == torch.float32
+    _close(probs, ref, atol=2e-5, rtol=1e-4, what="attention maps")
+    assert torch.allclose(probs.sum(-1), torch.ones_like(probs.sum(-1)), atol=1e-4)
+
+
 def test_patch_gather_and_cls():
     ops = _ops()
     px = torch.randn(2, 3, 4, 28, 28, device="cuda")

@@ -156,6 +156,45 @@ def test_vision_model_standalone_shapes_and_bf16():
         vm(None)
 
 
+def test_output_attentions_shapes_and_values():
+    """output_attentions=True (eilev/model/v2.py:78-95; the reference's own test parametrises over it,
+    tests/model/test_model_v2.py:8-83): one (num_videos, time, heads, S, S) map per layer, rows sum to 1, equal to
+    the oracle's softmax(q k^T / sqrt(d)) of the first layer; the full model accepts the flag."""
+    from eilev_b200.model.v2 import VideoBlipVisionModel
+    from oracle import videoblip_ref as R
+    fx, cfg = load("small_opt")
+    vm = VideoBlipVisionModel(cfg.vision_config)
+    sd = {k[len("vision_model."):]: v for k, v in fx["state_dict"].items() if k.startswith("vision_model.")}
+    vm.load_state_dict(sd)
+    vm = vm.to("cuda").eval()
+    px = fx["inputs"]["pixel_values"]
+    n, _, t, _, _ = px.shape
+    last, pooled, hidden, attn = vm(pixel_values=px.cuda(), output_attentions=True, output_hidden_states=True,
+                                    return_dict=False)
+    vc = cfg.vision_config
+    s = (vc.image_size // vc.patch_size) ** 2 + 1
+    assert len(attn) == vc.num_hidden_layers and len(hidden) == vc.num_hidden_layers + 1
+    for a in attn:
+        assert a.shape == (n, t, vc.num_attention_heads, s, s)
+        assert torch.allclose(a.float().sum(-1), torch.ones(n, t, vc.num_attention_heads, s, device="cuda"), atol=1e-3)
+    # first layer against the oracle's functions
+    frames = px.permute(0, 2, 1, 3, 4).flatten(end_dim=1)
+    x = R.vision_embeddings(fx["state_dict"], vc, frames)
+    p0 = "vision_model.encoder.layers.0."
+    y = R._ln(x, fx["state_dict"], p0 + "layer_norm1", vc.layer_norm_eps)
+    h, d = vc.num_attention_heads, vc.hidden_size // vc.num_attention_heads
+    qkv = R._lin(y, fx["state_dict"], p0 + "self_attn.qkv").reshape(n * t, s, 3, h, d).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1).view(n, t, h, s, s)
+    assert (attn[0].float().cpu() - ref).abs().max().item() < 5e-3
+    # the maps do not disturb the fused path
+    last2 = vm(pixel_values=px.cuda(), return_dict=False)[0]
+    assert torch.equal(last, last2)
+    m = build(cfg, fx["state_dict"])
+    with torch.no_grad():
+        out = m(**cuda(fx["inputs"]), output_attentions=True, return_dict=True)
+    assert out.logits.shape == fx["logits"].shape and len(out.vision_outputs.attentions) == vc.num_hidden_layers
+
+
 def test_errors_match_reference_contract():
     fx, cfg = load("tiny_opt")
     m = build(cfg, fx["state_dict"])
