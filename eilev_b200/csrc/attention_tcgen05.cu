@@ -423,6 +423,7 @@ struct PpParams {
   const __nv_bfloat16* q;   // raw q rows (row stride q_rs): the 257th query row is read straight from global memory
   long long q_rs;
   int row256;               // 1: the last query row of S = 257 is computed by warps 2-3 (no third Q tile)
+  int stagger;              // cycles the first tile of slot 1 is held back (phase offset between the warp groups)
   int items, heads, s, d;
   int dpad;            // d rounded up to 16: N of the P.V instruction
   float scale_log2;
@@ -582,6 +583,16 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           q_ph[slot] ^= 1u;
           mbar_wait(&slot_free[slot], free_ph[slot] ^ 1u);  // epilogue of tile g-2 has drained O
           free_ph[slot] ^= 1u;
+          if (g == 1 && p.stagger > 0) {
+            // With two tiles per item both warp groups would start every item together and stay in lockstep:
+            // softmax of both tiles at the same time (contending for the MUFU pipe) with the tensor pipe idle,
+            // then both P.V back to back with the softmax warps idle.  Each slot's chain (QK^T -> softmax ->
+            // P.V -> epilogue) is self-timed, so holding back the very first tile of slot 1 by about half a
+            // period keeps the two groups out of phase for the rest of the kernel.
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.stagger) {
+            }
+          }
           tc_fence_after();
           for (int ks = 0; ks < k_steps; ++ks) {
             const int c = ks >> 2, kk = ks & 3;
@@ -1025,6 +1036,11 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
       return (e != nullptr && e[0] == '0') ? 0 : 1;
     }();
     pp.row256 = row256;
+    static const int stagger = [] {
+      const char* e = std::getenv("VB_ATTN_STAGGER");
+      return e != nullptr ? std::atoi(e) : 4500;
+    }();
+    pp.stagger = stagger;
     const int grid_pp = pp.items < sms ? pp.items : sms;
     return launch_pdl(attn_tcgen05_pp_kernel, dim3(static_cast<unsigned>(grid_pp)), dim3(kTaThreads), kTaSmem, stream,
                       tq, tk, tv, pp);

@@ -185,7 +185,7 @@ def test_output_attentions_shapes_and_values():
     h, d = vc.num_attention_heads, vc.hidden_size // vc.num_attention_heads
     qkv = R._lin(y, fx["state_dict"], p0 + "self_attn.qkv").reshape(n * t, s, 3, h, d).permute(2, 0, 3, 1, 4)
     ref = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1).view(n, t, h, s, s)
-    assert (attn[0].float().cpu() - ref).abs().max().item() < 5e-3
+    assert (attn[0].float().cpu() - ref).abs().max().item() < 2e-2  # bf16 q, k vs the fp32 oracle, probabilities up to ~0.5
     # the maps do not disturb the fused path
     last2 = vm(pixel_values=px.cuda(), return_dict=False)[0]
     assert torch.equal(last, last2)
