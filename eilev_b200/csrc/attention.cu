@@ -7,6 +7,8 @@
 // Addressing: element (b, s, h, d) at base + b*bs + s*rs + h*D + d, so q/k/v may alias
 // one fused-QKV activation buffer and o may be written straight into the (tokens, H*D)
 // layout the following projection GEMM consumes — no transposes anywhere.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -384,6 +386,7 @@ struct AttnBwdParams {
   const float* delta;
   float* dq_acc;
   float scale;
+  int kt_per_cta;   // key tiles walked by one CTA (> 1 only with a single, non-causal query tile)
 };
 
 __global__ void __launch_bounds__(128)
@@ -405,7 +408,9 @@ attn_delta_kernel(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta
   if (lane == 0) delta[wid] = acc;
 }
 
-template <int DP>
+// KEEP_DQ: the CTA walks several key tiles and keeps dQ in registers (single query tile, not causal); a
+// template parameter so that the general instantiation pays no registers for it.
+template <int DP, bool KEEP_DQ>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdParams bp) {
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
@@ -422,16 +427,29 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   __nv_bfloat16* sP = sdO + 64 * LDS;
   __nv_bfloat16* sdS = sP + 64 * LDP;
 
-  // grid = (heads, key tiles, batch): with a causal mask key tile 0 is the heaviest, and it
-  // is issued first for every head
-  const int n0 = blockIdx.y * kAN;
+  // grid = (heads, key-tile groups, batch): with a causal mask key tile 0 is the heaviest, and it
+  // is issued first for every head.  A group is ONE key tile in general; when all queries fit one tile
+  // (the Q-Former's 32 queries against 2 056 image tokens) a CTA walks `kt_per_cta` key tiles and keeps dQ
+  // in registers across them: one round of f32 atomics per group instead of one per key tile (33 CTAs used
+  // to hit every dQ element).
   const int h = blockIdx.x, b = blockIdx.z;
+  const int key_tiles = (p.skv + kAN - 1) / kAN;
+  const int kt_begin = blockIdx.y * bp.kt_per_cta;
+  const int kt_end = kt_begin + bp.kt_per_cta < key_tiles ? kt_begin + bp.kt_per_cta : key_tiles;
+  constexpr bool keep_dq = KEEP_DQ;  // host guarantees: a single query tile, not causal
+  float dq_sum[KEEP_DQ ? NB : 1][4];
+#pragma unroll
+  for (int i = 0; i < (KEEP_DQ ? NB : 1); ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq_sum[i][j] = 0.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int D = p.d;
   const bool vec = p.vec != 0;
   const int causal_off = p.skv - p.sq;
   constexpr float kLog2e = 1.4426950408889634f;
+  for (int kt = kt_begin; kt < kt_end; ++kt) {
+  const int n0 = kt * kAN;
 
   const __nv_bfloat16* kg = p.k + b * p.k_bs + static_cast<long long>(n0) * p.k_rs + h * D;
   const __nv_bfloat16* vg = p.v + b * p.v_bs + static_cast<long long>(n0) * p.v_rs + h * D;
@@ -563,16 +581,23 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
           mma_bf16(dq[2 * dpi + 1], af, kf[2], kf[3]);
         }
       }
+      if constexpr (KEEP_DQ) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int qi = m0 + warp * 16 + g + r * 8;
-        if (qi >= p.sq) continue;
-        float* dst = bp.dq_acc + (static_cast<long long>(b) * p.sq + qi) * (static_cast<long long>(p.heads) * D) + h * D;
+        for (int i = 0; i < NB; ++i)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          const int c = nb * 8 + 2 * t;
-          if (c < D) atomicAdd(dst + c, dq[nb][2 * r] * bp.scale);
-          if (c + 1 < D) atomicAdd(dst + c + 1, dq[nb][2 * r + 1] * bp.scale);
+          for (int j = 0; j < 4; ++j) dq_sum[i][j] += dq[i][j];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int qi = m0 + warp * 16 + g + r * 8;
+          if (qi >= p.sq) continue;
+          float* dst = bp.dq_acc + (static_cast<long long>(b) * p.sq + qi) * (static_cast<long long>(p.heads) * D) + h * D;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int c = nb * 8 + 2 * t;
+            if (c < D) atomicAdd(dst + c, dq[nb][2 * r] * bp.scale);
+            if (c + 1 < D) atomicAdd(dst + c + 1, dq[nb][2 * r + 1] * bp.scale);
+          }
         }
       }
     }
@@ -619,6 +644,22 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
       }
     }
   }
+  __syncthreads();  // the K / V tiles are reloaded by the next key tile of this CTA
+  }  // key tiles of this CTA
+  if constexpr (KEEP_DQ) {  // single query tile (m0 = 0): the group's dQ in one round of atomics
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = warp * 16 + g + r * 8;
+      if (qi >= p.sq) continue;
+      float* dst = bp.dq_acc + (static_cast<long long>(b) * p.sq + qi) * (static_cast<long long>(p.heads) * D) + h * D;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int c = nb * 8 + 2 * t;
+        if (c < D) atomicAdd(dst + c, dq_sum[nb][2 * r] * bp.scale);
+        if (c + 1 < D) atomicAdd(dst + c + 1, dq_sum[nb][2 * r + 1] * bp.scale);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -640,13 +681,17 @@ static cudaError_t launch_bwd(const AttnBwdParams& bp, int batch, cudaStream_t s
   constexpr int smem = (4 * 64 * (DP + 8) + 2 * 64 * 72) * 2;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DP>,
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DP, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid(bp.f.heads, (bp.f.skv + kAN - 1) / kAN, batch);
-  launch_pdl(attn_bwd_kernel<DP>, dim3(grid), dim3(kAttnThreads), smem, stream, bp);
+  const int key_tiles = (bp.f.skv + kAN - 1) / kAN;
+  dim3 grid(bp.f.heads, (key_tiles + bp.kt_per_cta - 1) / bp.kt_per_cta, batch);
+  if (bp.kt_per_cta > 1) launch_pdl(attn_bwd_kernel<DP, true>, dim3(grid), dim3(kAttnThreads), smem, stream, bp);
+  else launch_pdl(attn_bwd_kernel<DP, false>, dim3(grid), dim3(kAttnThreads), smem, stream, bp);
   return cudaGetLastError();
 }
 
@@ -689,6 +734,17 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   bp.delta = a.delta;
   bp.dq_acc = a.dq_acc;
   bp.scale = f.scale;
+  // cross-attention of a few queries over a long memory (Q-Former: 32 x 2 056): one CTA per 8 key tiles,
+  // dQ accumulated in registers; VB_ATTN_BWD_KT overrides (1 = one key tile per CTA, the general scheme)
+  bp.kt_per_cta = 1;
+  if (f.sq <= kAM && !f.causal && f.skv >= 8 * kAN) {
+    static const int kt = [] {
+      const char* e = std::getenv("VB_ATTN_BWD_KT");
+      const int v = e != nullptr ? std::atoi(e) : 8;
+      return v < 1 ? 1 : v;
+    }();
+    bp.kt_per_cta = kt;
+  }
 
   const long long rows = f.batch * f.heads * f.sq;
   launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((rows * 32 + 127) / 128)), dim3(128), 0, stream, 

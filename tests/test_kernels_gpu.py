@@ -213,6 +213,8 @@ ATTN_CASES = [
     (3, 16, 88, 257, 257, False, False),
     (2, 12, 64, 32, 32, False, False),
     (2, 12, 64, 32, 2056, False, False),
+    (1, 3, 64, 40, 700, False, True),      # few queries over a long memory, masked: several key tiles per CTA in bwd
+    (2, 2, 88, 64, 1030, False, False),
     (1, 32, 80, 976, 976, True, False),
     (2, 32, 80, 200, 200, True, True),
     (2, 4, 2, 11, 11, True, False),
