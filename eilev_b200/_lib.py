@@ -16,6 +16,7 @@ LIB_PATH = _PKG / "libvideoblip_b200.so"
 
 VB_BF16, VB_F32, VB_F16 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_RELU = 0, 1, 2
+EPI_GELU_BWD, EPI_RELU_BWD = 3, 4  # C = acc * act'(residual): activation backward fused into the dgrad GEMM
 GEMM_AUTO, GEMM_TCGEN05, GEMM_GENERIC = 0, 1, 2
 
 i64, i32, f32, vp = C.c_int64, C.c_int32, C.c_float, C.c_void_p

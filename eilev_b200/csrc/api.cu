@@ -63,6 +63,9 @@ int vb_gemm(const vb_gemm_args* a, void* stream) {
   const bool elig = vb::gemm_tcgen05_eligible(*a);
   if (a->backend == VB_GEMM_TCGEN05 && !elig)
     return fail_msg("vb_gemm", "shape/alignment not eligible for the tcgen05 path");
+  if ((a->epilogue == VB_EPI_GELU_BWD || a->epilogue == VB_EPI_RELU_BWD) &&
+      (a->residual == nullptr || a->row_group != 0 || a->dropout_p > 0.0f))
+    return fail_msg("vb_gemm", "the activation-backward epilogues take the saved forward tensor as `residual`");
   if ((a->ln_stats != nullptr) != (a->ln_colsum != nullptr))
     return fail_msg("vb_gemm", "ln_stats and ln_colsum go together");
   if (a->ln_stats != nullptr || a->stats_out != nullptr || a->stats_zero != nullptr) {

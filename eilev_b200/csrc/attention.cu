@@ -420,12 +420,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   constexpr int KS = DP / 16;
   constexpr int NB = DP / 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sV = sK + 64 * LDS;
-  __nv_bfloat16* sQ = sV + 64 * LDS;
+  __nv_bfloat16* sK0 = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sV0 = sK0 + 64 * LDS;
+  __nv_bfloat16* sQ = sV0 + 64 * LDS;
   __nv_bfloat16* sdO = sQ + 64 * LDS;
   __nv_bfloat16* sP = sdO + 64 * LDS;
   __nv_bfloat16* sdS = sP + 64 * LDP;
+  // KEEP_DQ: second K / V buffers, the next key tile is fetched while the current one is processed
+  __nv_bfloat16* sK1 = sdS + 64 * LDP;
+  __nv_bfloat16* sV1 = sK1 + 64 * LDS;
 
   // grid = (heads, key-tile groups, batch): with a causal mask key tile 0 is the heaviest, and it
   // is issued first for every head.  A group is ONE key tile in general; when all queries fit one tile
@@ -448,15 +451,35 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   const bool vec = p.vec != 0;
   const int causal_off = p.skv - p.sq;
   constexpr float kLog2e = 1.4426950408889634f;
+  auto load_kv = [&](int tile, __nv_bfloat16* dk_s, __nv_bfloat16* dv_s) {
+    const int n_first = tile * kAN;
+    const int rows_kv = p.skv - n_first < kAN ? p.skv - n_first : kAN;
+    load_tile<DP>(dk_s, p.k + b * p.k_bs + static_cast<long long>(n_first) * p.k_rs + h * D, p.k_rs, rows_kv, D, vec);
+    load_tile<DP>(dv_s, p.v + b * p.v_bs + static_cast<long long>(n_first) * p.v_rs + h * D, p.v_rs, rows_kv, D, vec);
+  };
+  if constexpr (KEEP_DQ) {  // the single Q / dO tile and the first key tile, once
+    const int q_rows0 = p.sq < kAM ? p.sq : kAM;
+    load_kv(kt_begin, sK0, sV0);
+    load_tile<DP>(sQ, p.q + b * p.q_bs + h * D, p.q_rs, q_rows0, D, vec);
+    load_tile<DP>(sdO, bp.d_o + b * p.o_bs + h * D, p.o_rs, q_rows0, D, vec);
+    cp_async_commit();
+  }
   for (int kt = kt_begin; kt < kt_end; ++kt) {
   const int n0 = kt * kAN;
-
-  const __nv_bfloat16* kg = p.k + b * p.k_bs + static_cast<long long>(n0) * p.k_rs + h * D;
-  const __nv_bfloat16* vg = p.v + b * p.v_bs + static_cast<long long>(n0) * p.v_rs + h * D;
-  const int kv_rows = p.skv - n0 < kAN ? p.skv - n0 : kAN;
-  load_tile<DP>(sK, kg, p.k_rs, kv_rows, D, vec);
-  load_tile<DP>(sV, vg, p.v_rs, kv_rows, D, vec);
-  cp_async_commit();
+  const bool odd = KEEP_DQ && (((kt - kt_begin) & 1) != 0);
+  __nv_bfloat16* sK = odd ? sK1 : sK0;
+  __nv_bfloat16* sV = odd ? sV1 : sV0;
+  if constexpr (KEEP_DQ) {
+    cp_async_wait<0>();
+    __syncthreads();  // this tile has landed; the other buffer's readers finished at the end of the last tile
+    if (kt + 1 < kt_end) {
+      load_kv(kt + 1, odd ? sK0 : sK1, odd ? sV0 : sV1);
+      cp_async_commit();
+    }
+  } else {
+    load_kv(kt, sK, sV);
+    cp_async_commit();
+  }
 
   float dk_acc[NB][4], dv_acc[NB][4];
 #pragma unroll
@@ -479,13 +502,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   for (int mt = m_start; mt < m_tiles; ++mt) {
     const int m0 = mt * kAM;
     const int q_rows = p.sq - m0 < kAM ? p.sq - m0 : kAM;
-    load_tile<DP>(sQ, p.q + b * p.q_bs + static_cast<long long>(m0) * p.q_rs + h * D, p.q_rs,
-                  q_rows, D, vec);
-    load_tile<DP>(sdO, bp.d_o + b * p.o_bs + static_cast<long long>(m0) * p.o_rs + h * D, p.o_rs,
-                  q_rows, D, vec);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
+    if constexpr (!KEEP_DQ) {
+      load_tile<DP>(sQ, p.q + b * p.q_bs + static_cast<long long>(m0) * p.q_rs + h * D, p.q_rs,
+                    q_rows, D, vec);
+      load_tile<DP>(sdO, bp.d_o + b * p.o_bs + static_cast<long long>(m0) * p.o_rs + h * D, p.o_rs,
+                    q_rows, D, vec);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+    }
 
     // ---- S and dP for this warp's 16 query rows
     float s[8][4], dp[8][4];
@@ -623,7 +648,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
     }
     __syncthreads();
   }
-  cp_async_wait<0>();
+  if constexpr (!KEEP_DQ) cp_async_wait<0>();
 
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -679,18 +704,19 @@ attn_dq_convert_kernel(const float* dq_acc, __nv_bfloat16* dq, int sq, int hd, l
 template <int DP>
 static cudaError_t launch_bwd(const AttnBwdParams& bp, int batch, cudaStream_t stream) {
   constexpr int smem = (4 * 64 * (DP + 8) + 2 * 64 * 72) * 2;
+  constexpr int smem_keep = smem + 2 * 64 * (DP + 8) * 2;  // + the second K / V buffers
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DP, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      e = cudaFuncSetAttribute(attn_bwd_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_keep);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   const int key_tiles = (bp.f.skv + kAN - 1) / kAN;
   dim3 grid(bp.f.heads, (key_tiles + bp.kt_per_cta - 1) / bp.kt_per_cta, batch);
-  if (bp.kt_per_cta > 1) launch_pdl(attn_bwd_kernel<DP, true>, dim3(grid), dim3(kAttnThreads), smem, stream, bp);
+  if (bp.kt_per_cta > 1) launch_pdl(attn_bwd_kernel<DP, true>, dim3(grid), dim3(kAttnThreads), smem_keep, stream, bp);
   else launch_pdl(attn_bwd_kernel<DP, false>, dim3(grid), dim3(kAttnThreads), smem, stream, bp);
   return cudaGetLastError();
 }

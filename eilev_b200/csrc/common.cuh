@@ -352,4 +352,6 @@ enum VbEpilogue : int {
   VB_EPI_NONE = 0,       // C = alpha*(A.B^T) (+bias)
   VB_EPI_GELU = 1,       // exact (erf) GELU
   VB_EPI_RELU = 2,
+  VB_EPI_GELU_BWD = 3,   // C = acc * gelu'(residual): activation backward fused into the dgrad GEMM
+  VB_EPI_RELU_BWD = 4,   // C = residual > 0 ? acc : 0
 };

@@ -31,6 +31,14 @@ struct EpiParams {
   float* stats_zero;         // (M, 2) buffer cleared by the tiles of the first column block
 };
 
+// acc (+) the `residual` operand: a residual add, or — for the activation-backward epilogues — the product
+// with the activation's derivative at the saved forward value
+VB_DEVICE float epi_combine(int epilogue, bool act_bwd, float acc, float saved) {
+  if (!act_bwd) return acc + saved;
+  if (epilogue == VB_EPI_RELU_BWD) return saved > 0.0f ? acc : 0.0f;
+  return acc * gelu_erf_grad(saved);
+}
+
 // (rstd, -rstd * mean) of row `row` from the [sum, sum of squares] pair
 VB_DEVICE float2 ln_fold_coeffs(const EpiParams& p, long long row) {
   const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
@@ -111,18 +119,20 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
   }
   if (p.residual != nullptr) {
     const __nv_bfloat16* r = p.residual + res_row * p.ldr + col0;
+    const bool act_bwd = p.epilogue == VB_EPI_GELU_BWD || p.epilogue == VB_EPI_RELU_BWD;
     if (full) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(r + 8 * h));
         float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
                f3 = unpack_bf16x2(u.w);
-        v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
-        v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+        const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * h + j] = epi_combine(p.epilogue, act_bwd, v[8 * h + j], f[j]);
       }
     } else {
       for (int j = 0; j < 16; ++j)
-        if (col0 + j < p.n) v[j] += __bfloat162float(r[j]);
+        if (col0 + j < p.n) v[j] = epi_combine(p.epilogue, act_bwd, v[j], __bfloat162float(r[j]));
     }
   }
   if (p.out_f32) {
@@ -236,8 +246,10 @@ VB_DEVICE void epilogue_row16_staged(const EpiParams& p, long long row, long lon
     if (has_res) {
       const uint4 u = *cell;
       const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
-      v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+      const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+      const bool act_bwd = p.epilogue == VB_EPI_GELU_BWD || p.epilogue == VB_EPI_RELU_BWD;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * h + j] = epi_combine(p.epilogue, act_bwd, v[8 * h + j], f[j]);
     }
     uint4 o;
     o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);

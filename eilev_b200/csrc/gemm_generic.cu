@@ -90,7 +90,12 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(const GenParams p) {
       if (p.drop_thresh != 0u)
         v = dropout_keep(*p.drop_seed + p.drop_salt, static_cast<uint64_t>(row) * p.n + col, p.drop_thresh)
                 ? v * p.drop_scale : 0.0f;
-      if (p.residual != nullptr) v += __bfloat162float(p.residual[res_row * p.ldr + col]);
+      if (p.residual != nullptr) {
+        const float sv = __bfloat162float(p.residual[res_row * p.ldr + col]);
+        if (p.epilogue == VB_EPI_RELU_BWD) v = sv > 0.0f ? v : 0.0f;
+        else if (p.epilogue == VB_EPI_GELU_BWD) v *= gelu_erf_grad(sv);
+        else v += sv;
+      }
       if (p.out_f32) {
         float* c = reinterpret_cast<float*>(p.c) + out_row * p.ldc + col;
         if (p.beta != 0.0f) v += p.beta * *c;

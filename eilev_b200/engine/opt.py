@@ -174,12 +174,10 @@ def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None
 
     for li in range(len(w["layers"]) - 1, -1, -1):
         lw, s = w["layers"][li], ctx["saved"][li]
-        d_f1 = ops.gemm(masked(dx, li, 2), lw["fc2_wt"])
-        if act == ops.EPI_RELU:
-            d_pre = ops.act_bwd(d_f1, s["f1"], act)
-        else:
-            pre = ops.gemm(s["y2"], lw["fc1_w"], lw["fc1_b"])
-            d_pre = ops.act_bwd(d_f1, pre, act)
+        # fc2 dgrad with the activation's backward in its epilogue (ReLU: mask by the saved output; GELU: the
+        # pre-activation is recomputed)
+        saved_act = s["f1"] if act == ops.EPI_RELU else ops.gemm(s["y2"], lw["fc1_w"], lw["fc1_b"])
+        d_pre = ops.gemm_act_bwd(masked(dx, li, 2), lw["fc2_wt"], saved_act, act)
         d_y2 = ops.gemm(d_pre, lw["fc1_wt"])
         d_mid = ops.layernorm_bwd(d_y2, s["x_mid"], lw["ln2_g"], s["m2"], s["r2"], dx_add=dx)
         d_o = ops.gemm(masked(d_mid, li, 1), lw["out_wt"]).view(b, l, dim)

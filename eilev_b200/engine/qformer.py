@@ -236,12 +236,9 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor, 
         dsm = masked(ds, i, 4)
         g.weight(p + "output_query.dense.weight", dsm, s["inter"])
         g.bias(p + "output_query.dense.bias", dsm)
-        d_inter = ops.gemm(dsm, lw["o2_wt"])
-        if act == ops.EPI_GELU:
-            pre = ops.gemm(s["x2"], lw["i_w"], lw["i_b"])  # recompute the pre-activation
-            d_pre = ops.act_bwd(d_inter, pre, act)
-        else:
-            d_pre = ops.act_bwd(d_inter, s["inter"], act)
+        # dgrad of output_query.dense with the activation's backward in its epilogue
+        saved_act = ops.gemm(s["x2"], lw["i_w"], lw["i_b"]) if act == ops.EPI_GELU else s["inter"]  # GELU: recompute
+        d_pre = ops.gemm_act_bwd(dsm, lw["o2_wt"], saved_act, act)
         g.weight(p + "intermediate_query.dense.weight", d_pre, s["x2"])
         g.bias(p + "intermediate_query.dense.bias", d_pre)
         dx2 = ops.gemm(d_pre, lw["i_wt"], residual=ds)

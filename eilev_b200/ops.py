@@ -7,11 +7,12 @@ There is no CPU path — a CPU tensor raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
-from ._lib import (EPI_GELU, EPI_NONE, EPI_RELU, GEMM_AUTO, GEMM_GENERIC,  # noqa: F401
+from ._lib import (EPI_GELU, EPI_GELU_BWD, EPI_NONE, EPI_RELU, EPI_RELU_BWD, GEMM_AUTO, GEMM_GENERIC,  # noqa: F401
                    GEMM_TCGEN05, VB_BF16, VB_F16, VB_F32, AttnArgs, AttnBwdArgs, GemmArgs, check)
 
 _DT = {torch.bfloat16: VB_BF16, torch.float32: VB_F32, torch.float16: VB_F16}
@@ -105,6 +106,16 @@ def row_stats(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     check(_lib.lib().vb_row_stats(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0), _stream()),
           "vb_row_stats")
     return out
+
+
+def gemm_act_bwd(dy: torch.Tensor, w_t: torch.Tensor, saved: torch.Tensor, act: int) -> torch.Tensor:
+    """d_pre = (dy @ w_t.T) * act'(saved): the dgrad GEMM of the layer AFTER an activation with the activation's
+    backward in its epilogue (saved = the pre-activation for GELU, the activation output for ReLU)."""
+    epi = {EPI_GELU: EPI_GELU_BWD, EPI_RELU: EPI_RELU_BWD}[act]
+    assert saved.shape == (dy.shape[0], w_t.shape[0]) and saved.dtype == torch.bfloat16
+    if os.environ.get("VB_ACT_BWD_FUSED", "1") == "0":  # measurement knob: the two-kernel form
+        return act_bwd(gemm(dy, w_t), saved, act)
+    return gemm(dy, w_t, residual=saved, epilogue=epi)
 
 
 def gemm_uses_tcgen05(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> bool:

@@ -36,6 +36,11 @@ extern "C" {
 #define VB_EPI_NONE 0
 #define VB_EPI_GELU 1 /* exact erf GELU  (HF:blip_2/modeling_blip_2.py:365-369, :686-689) */
 #define VB_EPI_RELU 2 /* OPT FFN        (HF:opt/modeling_opt.py:238-239) */
+/* Backward of an activation fused into the dgrad GEMM that produces its output gradient:
+ * C = (alpha * A.B^T) * act'(S), S = `residual` (the saved forward tensor, bf16, same shape as C; for GELU the
+ * pre-activation, for ReLU the activation output).  Replaces vb_act_bwd after the GEMM. */
+#define VB_EPI_GELU_BWD 3
+#define VB_EPI_RELU_BWD 4
 
 /* GEMM backend selector (vb_gemm_args.backend) */
 #define VB_GEMM_AUTO 0    /* tcgen05 when the shape allows, else generic */

@@ -147,6 +147,26 @@ def test_gemm_gelu_epilogue_accuracy():
     assert torch.equal(out[0], torch.nn.functional.gelu(big))
 
 
+@pytest.mark.parametrize("backend,bn", [("tcgen05", 0), ("tcgen05", 1256), ("tcgen05", 1176), ("generic", 0)])
+@pytest.mark.parametrize("act", ["gelu", "relu"])
+def test_gemm_activation_backward_epilogue(backend, bn, act):
+    """VB_EPI_{GELU,RELU}_BWD: d_pre = (dy W) * act'(saved) in the dgrad GEMM's epilogue == GEMM then vb_act_bwd."""
+    ops = _ops()
+    m, n, k = 640, 768, 320
+    dy, wt = _rand(m, k, scale=0.5, seed=41), _rand(n, k, scale=0.1, seed=42)
+    saved = _rand(m, n, seed=43)
+    a = {"gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[act]
+    be = ops.GEMM_GENERIC if backend == "generic" else ops.GEMM_TCGEN05
+    e = {"gelu": ops.EPI_GELU_BWD, "relu": ops.EPI_RELU_BWD}[act]
+    got = ops.gemm(dy, wt, residual=saved, epilogue=e, backend=be, block_n=bn)
+    pre = saved.float().requires_grad_(True)
+    y = torch.nn.functional.gelu(pre) if act == "gelu" else torch.relu(pre)
+    y.backward(dy.float() @ wt.float().t())
+    _close(got, pre.grad, atol=0.03, rtol=0.01, what=f"act bwd epilogue {backend}/{bn}/{act}")
+    two = ops.act_bwd(ops.gemm(dy, wt, backend=be, block_n=bn), saved, a)
+    _close(got, two, atol=0.03, rtol=0.02, what="fused vs gemm + act_bwd")
+
+
 def test_gemm_generic_odd_shapes():
     ops = _ops()
     for (m, n, k) in [(5, 7, 3), (65, 24, 192), (130, 8, 8), (33, 100, 50)]:
