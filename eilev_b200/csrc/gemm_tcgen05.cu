@@ -303,17 +303,30 @@ void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {
 
 cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t stream);
 
-// CTA-pair 256 x 256 tiles win on every large launch measured on B200 (sweep in
+// CTA-pair 256-row tiles win on every large launch measured on B200 (sweep in
 // profiles/r01_gemm_tile_sweep.txt: +6..+12 % over the best 1-CTA tile, including N = 1408
-// where 8 % of the tile is padding); they need a few waves of pair-tiles to pay off.
+// where 8 % of the tile is padding).  Returns the tile WIDTH (0 = use the 1-CTA kernel).
+// Many waves (the ViT, M = 34952): 256 wide, the best arithmetic intensity.  A few waves (OPT at M = 976: four
+// row tiles): the width whose tile count fills whole waves of the 74 pairs, time ~ waves x (width + per-tile
+// overhead) -- N = 2560 -> 144 (72 tiles, one wave), N = 7680 -> 208 (148 tiles, two), N = 10240 -> 192.
 static int pick_2cta_block_n(long long m, long long n) {
-  if (m < 512) return 0;
-  const long long tiles = ((m + 255) / 256) * ((n + 255) / 256);
-  return tiles >= 100 ? 256 : 0;  // >= ~1.4 waves of the 74 CTA pairs (OPT qkv / fc1 at M = 976)
+  if (m < 768) return 0;
+  const long long pairs = 74;
+  const long long m_tiles = (m + 255) / 256;
+  if (m_tiles * ((n + 255) / 256) >= 4 * pairs) return 256;
+  int best = 0;
+  double best_cost = 1e300;
+  for (int tn = 256; tn >= 128; tn -= 16) {
+    const long long tiles = m_tiles * ((n + tn - 1) / tn);
+    const long long waves = (tiles + pairs - 1) / pairs;
+    const double cost = static_cast<double>(waves) * (tn + 24);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = tn; }
+  }
+  return best;
 }
 
 // vb_gemm_args.reserved: 0 = automatic; 64/128/176/256 = force the 1-CTA kernel with that
-// BLOCK_N; 1000 + {128,176,256} = force the CTA-pair kernel (used by the tests).
+// BLOCK_N; 1000 + width (a multiple of 16, 32..256) = force the CTA-pair kernel at that tile width.
 cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
   if (a.reserved >= 1000) return gemm_tcgen05_2cta_launch(a, a.reserved - 1000, stream);
   if (a.reserved == 0) {

@@ -1,5 +1,8 @@
 // CTA-pair variant of the tcgen05 GEMM (tcgen05.mma.cta_group::2): two CTAs of one cluster
-// (one TPC) compute a 256 x BN tile together.  Each CTA stages its own 128 rows of A and
+// (one TPC) compute a 256 x tn tile together.  tn (<= BN = 256, a multiple of 16) is a RUN-TIME width: the
+// host picks the width whose tile count fills whole waves of the 74 pairs (OPT at M = 976: N = 2560 -> 144,
+// 72 tiles in one wave; N = 7680 -> 208, 148 tiles in two; N = 10240 -> 192), the TMA box, the transaction
+// bytes and the UMMA instruction descriptor follow it.  Each CTA stages its own 128 rows of A and
 // HALF of the B tile; the pair's tensor cores read both halves, so per-SM shared-memory fill
 // traffic and L2->SM traffic drop by a third against the single-CTA 128 x BN tile and the
 // freed shared memory buys a deeper TMA ring (6-7 stages).  Used for the large-M launches
@@ -44,7 +47,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const EpiParams p,
-                         const int num_k_blocks, const int m_tiles, const int n_tiles) {
+                         const int num_k_blocks, const int m_tiles, const int n_tiles, const int tn) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -67,8 +70,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   // width of the last column block: the real columns rounded up to 32 (UMMA N % 16 per CTA half), <= BN
-  const int n_rem = static_cast<int>(p.n - static_cast<long long>(n_tiles - 1) * BN);
-  const int n_last = (n_rem + 31) / 32 * 32 < BN ? (n_rem + 31) / 32 * 32 : BN;
+  const int n_rem = static_cast<int>(p.n - static_cast<long long>(n_tiles - 1) * tn);
+  const int n_last = (n_rem + 31) / 32 * 32 < tn ? (n_rem + 31) / 32 * 32 : tn;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -104,16 +107,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t stage_tx = 2u * (Cfg::kABytes + static_cast<uint32_t>(tn / 2) * (k2BK * 2));  // both CTAs
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_a = m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
         // the pair's B tile is split in halves along N; a narrower last column block (n_last < BN) splits
         // its own width, so each CTA's half starts n_last / 2 rows apart
-        const int tile_n = (n_blk == n_tiles - 1) ? n_last : BN;
-        const int row_b = n_blk * BN + static_cast<int>(cta_rank) * (tile_n / 2);
+        const int tile_n = (n_blk == n_tiles - 1) ? n_last : tn;
+        const int row_b = n_blk * tn + static_cast<int>(cta_rank) * (tile_n / 2);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
           else mbar_arrive_remote(&full_bar[stage], 0);
           tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * k2BK, row_a);
           tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * k2BK, row_b);
@@ -124,7 +128,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc_full = umma_idesc_bf16(2 * k2BM, BN);
+      const uint32_t idesc_full = umma_idesc_bf16(2 * k2BM, static_cast<uint32_t>(tn));
       // last column block of an N that is not a multiple of BN (ViT: 1408 = 5 x 256 + 128): issue the MMA at
       // the width that holds real columns (rounded up to 32) instead of multiplying zero-filled rows
       const uint32_t idesc_last = umma_idesc_bf16(2 * k2BM, static_cast<uint32_t>(n_last));
@@ -157,23 +161,26 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int ew = warp - 4;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int cq = ew >> 2;         // column group: 64-column slab (staged path) / quarter of the chunks
-    constexpr int kChunks = BN / 16;
-    constexpr int kGroupChunks = (kChunks + 3) / 4;
-    const int c_begin = cq * kGroupChunks;
-    const int c_end = (c_begin + kGroupChunks < kChunks) ? c_begin + kGroupChunks : kChunks;
+    // 16-column chunks of this warp's column group.  With the TMA store the groups own whole 64-column slabs
+    // (a tile width that is not a multiple of 64 leaves its last, partial slab to direct stores); without it
+    // the chunks are split evenly.
+    const int chunks = tn / 16;
+    const int group_chunks = p.tma_store ? 4 : (chunks + 3) / 4;
+    const int c_begin = cq * group_chunks < chunks ? cq * group_chunks : chunks;
+    const int c_end = (c_begin + group_chunks < chunks) ? c_begin + group_chunks : chunks;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const long long row = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
-      if (BN == 256 && p.tma_store) {
+      if (p.tma_store && (cq + 1) * 64 <= tn) {
         // ---- staged path: the four warps of column group `cq` fill one [128 rows][64 cols] slab
         // (bias / LayerNorm fold / activation / residual), one thread stores it with TMA.
         const int row_in = quarter * 32 + lane;              // row inside this CTA's 128 rows
         const long long tile_row0 = static_cast<long long>(m_blk) * (2 * k2BM) + cta_rank * k2BM;
         const bool has_res = p.residual != nullptr;
-        const long long col_slab = static_cast<long long>(n_blk) * BN + cq * 64;
+        const long long col_slab = static_cast<long long>(n_blk) * tn + cq * 64;
         uint8_t* slab = smem_c + cq * Cfg::kSlabBytes;
         const bool slab_live = col_slab < p.n;
         // the TMA store that last read this slab (previous tile) must have drained
@@ -249,8 +256,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
         }
-        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + ch * 16, r0);
-        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + (ch + 1) * 16, r1);
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * tn + ch * 16, r0);
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * tn + (ch + 1) * 16, r1);
       }
       if (ch < c_end) {
         uint32_t r0[16];
@@ -259,7 +266,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);
-        epilogue_row16(p, row, static_cast<long long>(n_blk) * BN + ch * 16, r0);
+        epilogue_row16(p, row, static_cast<long long>(n_blk) * tn + ch * 16, r0);
       } else if (c_begin >= c_end) {  // a column group without chunks (narrow tiles) still releases the stage
         tc_fence_before();
         __syncwarp();
@@ -282,12 +289,25 @@ bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long l
                        long long ld, int box_rows);
 void fill_epi_params(EpiParams& ep, const vb_gemm_args& a);
 
-template <int BN>
-static cudaError_t launch_2cta(const vb_gemm_args& a, cudaStream_t stream) {
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// tn: tile width, a multiple of 16 in [32, 256]
+cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int tn, cudaStream_t stream) {
+  constexpr int BN = 256;
   using Cfg = Gemm2Cfg<BN>;
+  if (tn < 32 || tn > BN || tn % 16 != 0) return cudaErrorInvalidValue;
   CUtensorMap ta, tb;
   if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, k2BM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, BN / 2)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, tn / 2)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BN>,
@@ -300,34 +320,18 @@ static cudaError_t launch_2cta(const vb_gemm_args& a, cudaStream_t stream) {
   // TMA-store epilogue: bf16 output, plain row mapping, no accumulation into C
   CUtensorMap tc = ta;
   ep.tma_store = 0;
-  if (BN == 256 && a.out_dtype == VB_BF16 && a.beta == 0.0f && a.row_group == 0) {
+  if (tn >= 64 && a.out_dtype == VB_BF16 && a.beta == 0.0f && a.row_group == 0) {
     if (make_tmap_bf16_2d(&tc, a.c, a.m, a.n, a.ldc, k2BM)) ep.tma_store = 1;
   }
   const int m_tiles = static_cast<int>((a.m + 2 * k2BM - 1) / (2 * k2BM));
-  const int n_tiles = static_cast<int>((a.n + BN - 1) / BN);
+  const int n_tiles = static_cast<int>((a.n + tn - 1) / tn);
   const int k_blocks = static_cast<int>((a.k + k2BK - 1) / k2BK);
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = sm_count();
   const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   long long pairs = sms / 2;
   if (tiles < pairs) pairs = tiles;
   return launch_pdl(gemm_tcgen05_2cta_kernel<BN>, dim3(static_cast<unsigned>(2 * pairs)), dim3(k2Threads),
-                    Cfg::kSmemBytes, stream, ta, tb, tc, ep, k_blocks, m_tiles, n_tiles);
-}
-
-// bn: 256 or 176 (the ViT widths 1408 / 4224 are multiples of 176)
-cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t stream) {
-  switch (bn) {
-    case 256: return launch_2cta<256>(a, stream);
-    case 176: return launch_2cta<176>(a, stream);
-    case 128: return launch_2cta<128>(a, stream);
-    default: return cudaErrorInvalidValue;
-  }
+                    Cfg::kSmemBytes, stream, ta, tb, tc, ep, k_blocks, m_tiles, n_tiles, tn);
 }
 
 }  // namespace vb

@@ -19,6 +19,8 @@ SHAPES = [
     ("opt.fc1", 976, 10240, 2560, ops.EPI_RELU),
     ("opt.fc2", 976, 2560, 10240, ops.EPI_NONE),
     ("opt.head", 976, 50272, 2560, ops.EPI_NONE),
+    ("opt.proj", 976, 2560, 2560, ops.EPI_NONE),
+    ("opt.dqkv", 976, 2560, 7680, ops.EPI_NONE),
     ("qf.dense", 544, 768, 768, ops.EPI_NONE),
 ]
 
@@ -41,14 +43,16 @@ def timeit(fn, iters=5):
 
 def sweep():
     """--sweep: every tile variant (1-CTA 64..256, CTA-pair 1000+BN) on the big ViT shapes."""
-    which = SHAPES[5:9] if "--opt" in sys.argv else SHAPES[:5]
+    opt = "--opt" in sys.argv
+    which = [s for s in SHAPES if s[0].startswith("opt.")] if opt else SHAPES[:5]
     for name, m, n, k, epi in which:
         a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
         w = (torch.randn(n, k, device="cuda") * 0.05).to(torch.bfloat16)
         bias = torch.randn(n, device="cuda")
         out = torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
         res = {}
-        for bn in (64, 128, 176, 256, 1128, 1256):
+        widths = (0, 176, 256, 1128, 1144, 1160, 1176, 1192, 1208, 1224, 1256) if opt else (64, 128, 176, 256, 1128, 1256)
+        for bn in widths:
             best, _ = timeit(lambda: ops.gemm(a, w, bias, out=out, epilogue=epi, block_n=bn), iters=3)
             res[bn] = round(2.0 * m * n * k / best / 1e9)
         print(name, res, flush=True)

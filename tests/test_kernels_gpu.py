@@ -36,6 +36,10 @@ GEMM_SHAPES = [
     (512, 512, 256, 1256), (300, 1408, 1408, 1176), (257, 4224, 1408, 1256), (1000, 6144, 1408, 1176),
     (520, 1408, 6144, 1256), (200, 264, 72, 1128), (100, 256, 64, 1256), (8200, 1408, 1408, 0),
     (5000, 6144, 1408, 0), (4100, 768, 1408, 1128),
+    # run-time tile widths of the CTA-pair kernel (wave-filling widths of the OPT shapes at M = 976): widths that
+    # are not a multiple of 64 end in a partial slab written with direct stores
+    (976, 7680, 2560, 0), (976, 10240, 512, 0), (976, 2560, 512, 1144), (976, 1000, 256, 1208),
+    (600, 2048, 128, 1192), (976, 2560, 320, 1096), (1500, 1408, 192, 1240), (976, 2560, 192, 1032),
 ]
 
 
@@ -46,6 +50,23 @@ def test_gemm_tcgen05_plain(m, n, k, bn):
     out = ops.gemm(a, w, backend=ops.GEMM_TCGEN05, block_n=bn)
     ref = a.float() @ w.float().t()
     _close(out, ref, atol=0.02 * math.sqrt(k), rtol=0.01, what=f"gemm {m}x{n}x{k} bn={bn}")
+
+
+@pytest.mark.parametrize("bn", [1144, 1208, 1192, 0])
+def test_gemm_cta_pair_widths_with_full_epilogue(bn):
+    """bias + ReLU + dropout + residual through a tile width with a partial last slab (staged slabs and direct
+    chunks in one tile) at the OPT row count."""
+    ops = _ops()
+    m, n, k = 976, 2560, 384
+    a, w = _rand(m, k, scale=0.5, seed=13), _rand(n, k, scale=0.1, seed=14)
+    bias = torch.randn(n, device="cuda")
+    res = _rand(m, n, seed=15)
+    seed = torch.tensor([77], dtype=torch.int64, device="cuda")
+    out = ops.gemm(a, w, bias, residual=res, epilogue=ops.EPI_RELU, dropout=(0.25, seed, 5),
+                   backend=ops.GEMM_TCGEN05, block_n=bn)
+    keep = ops.dropout(torch.ones(m, n, dtype=torch.bfloat16, device="cuda"), 0.25, seed, 5).float()
+    ref = torch.relu(a.float() @ w.float().t() + bias) * keep + res.float()
+    _close(out, ref, atol=0.04, rtol=0.01, what=f"cta-pair width {bn}")
 
 
 @pytest.mark.parametrize("backend", ["tcgen05", "tcgen05_2cta", "generic"])
