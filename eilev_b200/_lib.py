@@ -12,7 +12,8 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 _ROOT = _PKG.parent
-LIB_PATH = _PKG / "libvideoblip_b200.so"
+# VB_LIB_PATH: an instrumented build of the same library (scripts/micro/gemm_trace.sh); measurement only
+LIB_PATH = Path(os.environ["VB_LIB_PATH"]) if os.environ.get("VB_LIB_PATH") else _PKG / "libvideoblip_b200.so"
 
 VB_BF16, VB_F32, VB_F16 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_RELU = 0, 1, 2

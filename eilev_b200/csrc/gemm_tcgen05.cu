@@ -305,18 +305,23 @@ cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t
 
 // CTA-pair 256-row tiles win on every large launch measured on B200 (sweep in
 // profiles/r01_gemm_tile_sweep.txt: +6..+12 % over the best 1-CTA tile, including N = 1408
-// where 8 % of the tile is padding).  Returns the tile WIDTH (0 = use the 1-CTA kernel).
-// Many waves (the ViT, M = 34952): 256 wide, the best arithmetic intensity.  A few waves (OPT at M = 976: four
-// row tiles): the width whose tile count fills whole waves of the 74 pairs, time ~ waves x (width + per-tile
-// overhead) -- N = 2560 -> 144 (72 tiles, one wave), N = 7680 -> 208 (148 tiles, two), N = 10240 -> 192.
+// where 8 % of the tile is padding); they need a few waves of pair-tiles to pay off.
+// Returns the tile WIDTH (0 = use the 1-CTA kernel).  Many waves (the ViT, M = 34952): 256 wide, the best
+// arithmetic intensity.  Two or three waves (OPT qkv / fc1 at M = 976: four row tiles): the width in 192..256
+// whose tile count fills whole waves of the 74 pairs (N = 7680 -> 208: 148 tiles; N = 10240 -> 192), +5 % in
+// profiles/r02_gemm_opt_widths.txt.  Narrower pair tiles lose to the 1-CTA kernel: per k-block a CTA pulls
+// (128 + width/2) rows from L2 whatever the width, so the k-loop does not get faster (same file: ~535 clk per
+// k-block at width 144 and at 256).
 static int pick_2cta_block_n(long long m, long long n) {
-  if (m < 768) return 0;
+  if (m < 512) return 0;
   const long long pairs = 74;
   const long long m_tiles = (m + 255) / 256;
-  if (m_tiles * ((n + 255) / 256) >= 4 * pairs) return 256;
-  int best = 0;
+  const long long tiles256 = m_tiles * ((n + 255) / 256);
+  if (tiles256 < 100) return 0;
+  if (tiles256 >= 4 * pairs) return 256;
+  int best = 256;
   double best_cost = 1e300;
-  for (int tn = 256; tn >= 128; tn -= 16) {
+  for (int tn = 256; tn >= 192; tn -= 16) {
     const long long tiles = m_tiles * ((n + tn - 1) / tn);
     const long long waves = (tiles + pairs - 1) / pairs;
     const double cost = static_cast<double>(waves) * (tn + 24);

@@ -1,8 +1,8 @@
 // CTA-pair variant of the tcgen05 GEMM (tcgen05.mma.cta_group::2): two CTAs of one cluster
-// (one TPC) compute a 256 x tn tile together.  tn (<= BN = 256, a multiple of 16) is a RUN-TIME width: the
-// host picks the width whose tile count fills whole waves of the 74 pairs (OPT at M = 976: N = 2560 -> 144,
-// 72 tiles in one wave; N = 7680 -> 208, 148 tiles in two; N = 10240 -> 192), the TMA box, the transaction
-// bytes and the UMMA instruction descriptor follow it.  Each CTA stages its own 128 rows of A and
+// (one TPC) compute a 256 x tn tile together.  tn (<= 256, a multiple of 16) is a RUN-TIME width: for launches
+// of two or three waves the host picks the width that fills whole waves of the 74 pairs (OPT at M = 976:
+// N = 7680 -> 208, 148 tiles in two waves; N = 10240 -> 192); the TMA box, the transaction bytes, the
+// shared-memory plan and the UMMA instruction descriptor follow it.  Each CTA stages its own 128 rows of A and
 // HALF of the B tile; the pair's tensor cores read both halves, so per-SM shared-memory fill
 // traffic and L2->SM traffic drop by a third against the single-CTA 128 x BN tile and the
 // freed shared memory buys a deeper TMA ring (6-7 stages).  Used for the large-M launches
@@ -21,49 +21,64 @@
 
 namespace vb {
 
+// -DVB_GEMM_TRACE (scripts/micro/gemm_trace.sh): per-CTA clock64 stamps of the kernel's phases, read back through
+// vb_debug_gemm_trace.  Off in the product build.
+#ifdef VB_GEMM_TRACE
+__device__ unsigned long long g_trace[296 * 16];
+#define VB_TRACE(i) g_trace[blockIdx.x * 16 + (i)] = clock64()
+#else
+#define VB_TRACE(i)
+#endif
+
 constexpr int k2BM = 128;  // rows per CTA (256 per pair)
 constexpr int k2BK = 64;
 constexpr int k2EpiWarps = 16;
 constexpr int k2Threads = (4 + k2EpiWarps) * 32;  // 640: <= 96 registers per thread
 
-template <int BN>
-struct Gemm2Cfg {
+// Shared-memory plan of one launch (all sizes follow the run-time tile width tn):
+//   [stages x A tile 16 KB][stages x this CTA's half of B, tn/2 rows x 128 B][tn/64 output slabs x 16 KB][barriers]
+// The output staging of the TMA-store epilogue takes one [128 rows][64 cols] bf16 slab (SWIZZLE_128B) per whole
+// 64-column group of the tile; what a narrow tile does not need buys TMA stages (tn = 144: 7 stages, 256: 5).
+struct Gemm2Plan {
   static constexpr int kABytes = k2BM * k2BK * 2;
-  static constexpr int kBBytes = (BN / 2) * k2BK * 2;  // this CTA's half of B
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  // output staging for the TMA-store epilogue: four slabs (one per 64-column quarter of the tile, each
-  // owned by four warps) of 128 rows x 64 cols bf16 (SWIZZLE_128B) = 64 KB
   static constexpr int kSlabBytes = k2BM * 128;
-  static constexpr int kStagingBytes = 4 * kSlabBytes;
-  static constexpr int kStages = (226 * 1024 - kStagingBytes - 1280) / kStageBytes > 8
-                                     ? 8 : (226 * 1024 - kStagingBytes - 1280) / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
-  static_assert(BN % 32 == 0 || BN == 176, "BN/2 must be a whole number of 8-row groups");
-  static_assert(kBBytes % 1024 == 0, "B half stage must keep 1024B alignment");
+  static constexpr int kMaxStages = 8;
+  static constexpr int kSmemBytes = 227 * 1024;             // the whole opt-in maximum
+  static constexpr int kBudget = kSmemBytes - 1024 - 256;   // alignment slack + barriers
+  static int b_bytes(int tn) { return (tn / 2) * k2BK * 2; }
+  static int slabs(int tn) { return tn / 64; }
+  static int stages(int tn) {
+    const int s = (kBudget - slabs(tn) * kSlabBytes) / (kABytes + b_bytes(tn));
+    return s > kMaxStages ? kMaxStages : s;
+  }
 };
+
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const EpiParams p,
-                         const int num_k_blocks, const int m_tiles, const int n_tiles, const int tn) {
-  using Cfg = Gemm2Cfg<BN>;
-  constexpr int kStages = Cfg::kStages;
+                         const int num_k_blocks, const int m_tiles, const int n_tiles, const int tn,
+                         const int kStages) {
+  using Cfg = Gemm2Plan;
+  static_assert(BN == 256, "one instantiation: the tile width is the run-time tn <= 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int b_bytes = (tn / 2) * (k2BK * 2);   // a multiple of 1024 (tn % 16 == 0)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint8_t* smem_c = smem + kStages * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStagingBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  uint8_t* smem_c = smem_b + kStages * b_bytes;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + (tn / 64) * Cfg::kSlabBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kMaxStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) VB_TRACE(0);
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
   const int num_tiles = m_tiles * n_tiles;
@@ -98,16 +113,18 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) VB_TRACE(1);
   // Programmatic dependent launch: the set-up above may overlap the tail of the preceding kernel
   pdl_wait();
   pdl_trigger();
+  if (threadIdx.x == 0) VB_TRACE(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = 2u * (Cfg::kABytes + static_cast<uint32_t>(tn / 2) * (k2BK * 2));  // both CTAs
+      const uint32_t stage_tx = 2u * static_cast<uint32_t>(Cfg::kABytes + b_bytes);  // both CTAs
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_a = m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
@@ -120,7 +137,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (leader) mbar_expect_tx(&full_bar[stage], stage_tx);
           else mbar_arrive_remote(&full_bar[stage], 0);
           tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * k2BK, row_a);
-          tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * k2BK, row_b);
+          tma_load_2d_2sm(smem_b + stage * b_bytes, &tmap_b, &full_bar[stage], kb * k2BK, row_b);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -144,8 +161,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+#ifdef VB_GEMM_TRACE
+          if (tile == pair && kb < 4) VB_TRACE(3 + kb);
+#endif
           const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * b_bytes));
 #pragma unroll
           for (int k = 0; k < k2BK / 16; ++k)
             umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -153,6 +173,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_2sm(&tmem_full[acc]);  // accumulators of both CTAs complete
+        VB_TRACE(7);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -204,6 +225,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (p.ln_stats != nullptr && row < p.m) ln_c = ln_fold_coeffs(p, row);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        if (ew == 0 && lane == 0) VB_TRACE(8);
         if (has_res && slab_live) {
           cp_async_commit_wait_all();
           __syncwarp();  // each warp reads back only rows it fetched itself
@@ -233,6 +255,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (quarter == 0 && lane == 0) {
           if (slab_live) tma_store_2d(&tmap_c, slab, static_cast<int>(col_slab), static_cast<int>(tile_row0));
           bulk_commit();  // (an empty group keeps the wait_group bookkeeping uniform)
+          if (cq == 0) VB_TRACE(9);
         }
         if (p.stats_zero != nullptr && n_blk == 0 && cq == 0 && row < p.m)
           *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
@@ -277,13 +300,22 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   if (warp >= 4 && ((warp - 4) & 3) == 0 && lane == 0) bulk_wait_read<0>();  // smem must outlive the stores
+  if (threadIdx.x == 128) VB_TRACE(10);
   tc_fence_before();
   cluster_sync_all();  // both CTAs are done with TMEM / remote barriers
+  if (threadIdx.x == 0) VB_TRACE(11);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 512);
+    if (lane == 0) VB_TRACE(12);
   }
 }
+
+#ifdef VB_GEMM_TRACE
+extern "C" int vb_debug_gemm_trace(unsigned long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(g_trace)));
+}
+#endif
 
 bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols,
                        long long ld, int box_rows);
@@ -303,7 +335,7 @@ static int sm_count() {
 // tn: tile width, a multiple of 16 in [32, 256]
 cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int tn, cudaStream_t stream) {
   constexpr int BN = 256;
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Plan;
   if (tn < 32 || tn > BN || tn % 16 != 0) return cudaErrorInvalidValue;
   CUtensorMap ta, tb;
   if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, k2BM)) return cudaErrorInvalidValue;
@@ -331,7 +363,7 @@ cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int tn, cudaStream_t
   long long pairs = sms / 2;
   if (tiles < pairs) pairs = tiles;
   return launch_pdl(gemm_tcgen05_2cta_kernel<BN>, dim3(static_cast<unsigned>(2 * pairs)), dim3(k2Threads),
-                    Cfg::kSmemBytes, stream, ta, tb, tc, ep, k_blocks, m_tiles, n_tiles, tn);
+                    Cfg::kSmemBytes, stream, ta, tb, tc, ep, k_blocks, m_tiles, n_tiles, tn, Cfg::stages(tn));
 }
 
 }  // namespace vb
