@@ -73,6 +73,7 @@ SIGNATURES: dict[str, list] = {
     "vb_attention_probs": [C.POINTER(AttnArgs), vp, i32, vp],
     "vb_attention_uses_tcgen05": [C.POINTER(AttnArgs)],
     "vb_attention_bwd": [C.POINTER(AttnBwdArgs), vp],
+    "vb_attention_bwd_uses_tcgen05": [C.POINTER(AttnBwdArgs)],
     "vb_patch_gather": [vp, i32, vp, i64, i64, i64, i64, i64, i64, i64, vp],
     "vb_patch_gather_u8": [vp, vp, i64, i64, i64, i64, i64, i64, i64, C.c_double, C.POINTER(f32), C.POINTER(f32), vp],
     "vb_resize_bicubic_ksize": [i64, i64],
@@ -142,7 +143,7 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "vb_last_error" else C.c_int
-    if handle.vb_abi_version() != 5:
+    if handle.vb_abi_version() != 6:
         raise VbError("ABI version mismatch between eilev_b200/_lib.py and the built library")
     _lib = handle
     return handle

@@ -131,6 +131,11 @@ int vb_attention_bwd(const vb_attn_bwd_args* a, void* stream) {
   VB_CHECK("vb_attention_bwd", vb::attention_bwd_launch(*a, st(stream)));
 }
 
+int vb_attention_bwd_uses_tcgen05(const vb_attn_bwd_args* a) {
+  if (a == nullptr) return 0;
+  return vb::attention_bwd_tcgen05_eligible(*a) ? 1 : 0;
+}
+
 int vb_patch_gather(const void* pixels, int32_t px_dtype, void* out, int64_t nv, int64_t c,
                     int64_t t, int64_t h, int64_t w, int64_t patch, int64_t kpad, void* stream) {
   if (pixels == nullptr || out == nullptr || patch <= 0 || kpad < c * patch * patch)

@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const AttnBwdPar
   const int key_tiles = (p.skv + kAN - 1) / kAN;
   const int kt_begin = blockIdx.y * bp.kt_per_cta;
   const int kt_end = kt_begin + bp.kt_per_cta < key_tiles ? kt_begin + bp.kt_per_cta : key_tiles;
-  constexpr bool keep_dq = KEEP_DQ;  // host guarantees: a single query tile, not causal
+  // KEEP_DQ: the host guarantees a single query tile, not causal
   float dq_sum[KEEP_DQ ? NB : 1][4];
 #pragma unroll
   for (int i = 0; i < (KEEP_DQ ? NB : 1); ++i)
@@ -775,6 +775,9 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   const long long rows = f.batch * f.heads * f.sq;
   launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((rows * 32 + 127) / 128)), dim3(128), 0, stream, 
       p.o, bp.d_o, a.delta, p.sq, p.heads, p.d, p.o_bs, p.o_rs, rows);
+  // tcgen05 path (attention_bwd_tcgen05.cu): dK / dV and dQ by two passes with the reduction index on the TMEM
+  // columns; no dq_acc round trip
+  if (attention_bwd_tcgen05_eligible(a)) return attention_bwd_tcgen05_launch(a, stream);
   const long long hd = f.heads * f.d;
   const long long total = f.batch * f.sq * hd;
   cudaError_t e = cudaMemsetAsync(a.dq_acc, 0, sizeof(float) * total, stream);

@@ -238,7 +238,8 @@ def attention_uses_tcgen05(q, k, v, heads: int, *, causal=False, key_mask=None, 
 
 
 def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: bool = False,
-                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None, dropout=None, rel_bias=None):
+                  key_mask=None, dq_scale: float = 1.0, dq=None, dk=None, dv=None, dropout=None, rel_bias=None,
+                  _probe: bool = False):
     """Returns (dq, dk, dv) with the shapes of q, k, v (contiguous unless views are given)."""
     hd = q.shape[2]
     d = hd // heads
@@ -255,8 +256,15 @@ def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: boo
     b.dk_bs, b.dk_rs = dk.stride(0), dk.stride(1)
     b.dv_bs, b.dv_rs = dv.stride(0), dv.stride(1)
     b.delta, b.dq_acc, b.dq_scale = delta.data_ptr(), dq_acc.data_ptr(), dq_scale
+    if _probe:
+        return bool(_lib.lib().vb_attention_bwd_uses_tcgen05(C.byref(b)))
     check(_lib.lib().vb_attention_bwd(C.byref(b), _stream()), "vb_attention_bwd")
     return dq, dk, dv
+
+
+def attention_bwd_uses_tcgen05(*args, **kwargs) -> bool:
+    """True when ``attention_bwd`` with these arguments runs the tcgen05 / TMEM kernels."""
+    return attention_bwd(*args, _probe=True, **kwargs)
 
 
 def attention_merge(o1: torch.Tensor, lse1: torch.Tensor, o2: torch.Tensor, lse2: torch.Tensor,

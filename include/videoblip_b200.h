@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 5
+#define VB_ABI_VERSION 6
 
 /* dtype tags */
 #define VB_BF16 0
@@ -203,6 +203,9 @@ typedef struct vb_attn_bwd_args {
   int32_t reserved;
 } vb_attn_bwd_args;
 int vb_attention_bwd(const vb_attn_bwd_args* args, void* stream);
+/* 1 if vb_attention_bwd takes the tcgen05 / TMEM kernels (d % 16 == 0, 16-byte aligned operands, batches stored
+ * back to back), 0 for the mma.sync kernel. */
+int vb_attention_bwd_uses_tcgen05(const vb_attn_bwd_args* args);
 
 /* ------------------------------------------------------------------------
  * Patch gather for the ViT patch embedding (Conv2d k=s=P as a GEMM):

@@ -1,6 +1,7 @@
 """Kernel-level numerics on the B200: every C-ABI kernel family against a plain PyTorch
 fp32 evaluation of the same op on the same (bf16-rounded) inputs."""
 import math
+import os
 
 import pytest
 import torch
@@ -260,6 +261,13 @@ ATTN_CASES = [
     (2, 32, 80, 200, 200, True, True),
     (2, 4, 2, 11, 11, True, False),
     (2, 4, 2, 5, 37, False, False),
+    # tcgen05 backward: ragged tiles with more than one batch, causal with more keys than queries, d = 128 / 48
+    (2, 3, 80, 300, 300, True, False),
+    (2, 4, 64, 130, 515, False, True),
+    (1, 2, 128, 200, 200, True, False),
+    (2, 2, 80, 150, 260, True, False),
+    (1, 2, 48, 100, 100, True, True),
+    (1, 2, 80, 1500, 1500, True, False),
 ]
 
 
@@ -292,6 +300,9 @@ def test_attention_fwd_bwd(b, heads, d, sq, skv, causal, masked):
     d_o = d_o * valid[:, :, None]
     torch.nan_to_num(ref, nan=0.0).backward(d_o.float())
     dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal, key_mask=key_mask)
+    # head dims that are a multiple of 16 run the tcgen05 / TMEM backward (attention_bwd_tcgen05.cu)
+    assert ops.attention_bwd_uses_tcgen05(q, k, v, o, lse, d_o, heads, scale, causal=causal,
+                                          key_mask=key_mask) == (d % 16 == 0 and os.environ.get("VB_ATTN_BWD_TC") != "0")
     for got, want, nm in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
         want = torch.nan_to_num(want, nan=0.0)
         if nm == "dq":
