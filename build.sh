@@ -7,7 +7,7 @@ SRC=eilev_b200/csrc
 OBJ=build/obj
 mkdir -p "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math -Xcompiler -fPIC ${NVCC_EXTRA:-}"
-UNITS="api gemm_tcgen05 gemm_tcgen05_2cta gemm_generic attention attention_tcgen05 attention_bwd_tcgen05 layernorm elementwise decode t5 frames"
+UNITS="api gemm_tcgen05 gemm_tcgen05_2cta gemm_generic attention attention_tcgen05 attention_flash_tcgen05 layernorm elementwise decode t5 frames"
 newest_hdr=$(ls -t $SRC/*.cuh $SRC/*.h include/*.h build.sh | head -1)
 pids=()
 for u in $UNITS; do

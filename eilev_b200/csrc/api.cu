@@ -122,7 +122,9 @@ int vb_attention_probs(const vb_attn_args* a, void* probs, int32_t probs_dtype, 
 }
 
 int vb_attention_uses_tcgen05(const vb_attn_args* a) {
-  return (a != nullptr && vb::attention_tcgen05_eligible(*a)) ? 1 : 0;
+  if (a == nullptr) return 0;
+  if (vb::attention_tcgen05_eligible(*a)) return 1;
+  return vb::attention_flash_tcgen05_eligible(*a) ? 2 : 0;
 }
 
 int vb_attention_bwd(const vb_attn_bwd_args* a, void* stream) {

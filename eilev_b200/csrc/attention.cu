@@ -328,6 +328,7 @@ cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream) {
   if (a.batch <= 0 || a.heads <= 0 || a.sq <= 0) return cudaSuccess;
   if (a.d <= 0 || a.d > 128 || a.skv <= 0) return cudaErrorInvalidValue;
   if (attention_tcgen05_eligible(a)) return attention_tcgen05_launch(a, stream);
+  if (attention_flash_tcgen05_eligible(a)) return attention_flash_tcgen05_launch(a, stream);
   if (a.heads > 65535 || a.batch > 65535) return cudaErrorInvalidValue;
   AttnParams p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(a.q);
@@ -775,7 +776,7 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
   const long long rows = f.batch * f.heads * f.sq;
   launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((rows * 32 + 127) / 128)), dim3(128), 0, stream, 
       p.o, bp.d_o, a.delta, p.sq, p.heads, p.d, p.o_bs, p.o_rs, rows);
-  // tcgen05 path (attention_bwd_tcgen05.cu): dK / dV and dQ by two passes with the reduction index on the TMEM
+  // tcgen05 path (attention_flash_tcgen05.cu): dK / dV and dQ by two passes with the reduction index on the TMEM
   // columns; no dq_acc round trip
   if (attention_bwd_tcgen05_eligible(a)) return attention_bwd_tcgen05_launch(a, stream);
   const long long hd = f.heads * f.d;

@@ -22,6 +22,8 @@ cudaError_t row_stats_launch(const void* x, float* stats, long long rows, long l
 cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream);
 cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream);
 cudaError_t attention_probs_launch(const vb_attn_args& a, void* probs, int out_bf16, cudaStream_t stream);
+bool attention_flash_tcgen05_eligible(const vb_attn_args& a);
+cudaError_t attention_flash_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream);
 bool attention_bwd_tcgen05_eligible(const vb_attn_bwd_args& a);
 cudaError_t attention_bwd_tcgen05_launch(const vb_attn_bwd_args& a, cudaStream_t stream);
 bool attention_tcgen05_eligible(const vb_attn_args& a);

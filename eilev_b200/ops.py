@@ -234,7 +234,16 @@ def attention_uses_tcgen05(q, k, v, heads: int, *, causal=False, key_mask=None, 
     o = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.bfloat16, device=q.device)
     lse = torch.empty(1, device=q.device) if need_lse else None
     a = _attn_args(q, k, v, o, lse, key_mask, heads, hd // heads, 1.0, causal)
-    return bool(_lib.lib().vb_attention_uses_tcgen05(C.byref(a)))
+    return _lib.lib().vb_attention_uses_tcgen05(C.byref(a)) == 1
+
+
+def attention_kernel(q, k, v, heads: int, *, causal=False, key_mask=None, need_lse=False) -> str:
+    """The kernel ``attention`` runs for these arguments: "tcgen05_vit", "tcgen05_flash" or "mma_sync"."""
+    hd = q.shape[2]
+    o = torch.empty((q.shape[0], q.shape[1], hd), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(1, device=q.device) if need_lse else None
+    a = _attn_args(q, k, v, o, lse, key_mask, heads, hd // heads, 1.0, causal)
+    return ("mma_sync", "tcgen05_vit", "tcgen05_flash")[_lib.lib().vb_attention_uses_tcgen05(C.byref(a))]
 
 
 def attention_bwd(q, k, v, o, lse, d_o, heads: int, scale: float, *, causal: bool = False,

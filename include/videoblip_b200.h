@@ -183,8 +183,10 @@ int vb_attention_fwd(const vb_attn_args* args, void* stream);
  * shapes / strides, scale and causal of `args` are read.  A diagnostic output computed by a plain CUDA-core
  * kernel; the fused kernels of vb_attention_fwd never materialise it. */
 int vb_attention_probs(const vb_attn_args* args, void* probs, int32_t probs_dtype, void* stream);
-/* 1 if vb_attention_fwd takes the tcgen05/TMEM kernel (non-causal, unmasked, no lse,
- * 64 <= S <= 272, d <= 128: the ViT shape class), 0 for the mma.sync flash kernel. */
+/* Which kernel vb_attention_fwd takes: 1 = the single-pass tcgen05 / TMEM kernel (non-causal, unmasked, no lse,
+ * 64 <= S <= 272, d <= 128: the ViT shape class); 2 = the tcgen05 flash kernel (any Sq / Skv, causal, key mask,
+ * dropout, relative bias, lse; d % 16 == 0, 16-byte aligned operands, batches stored back to back);
+ * 0 = the mma.sync flash kernel. */
 int vb_attention_uses_tcgen05(const vb_attn_args* args);
 
 /* Backward of the above: dq, dk, dv (bf16, same addressing as q,k,v via the dq_, dk_, dv_

@@ -37,10 +37,11 @@ def case(name, b, heads, d, sq, skv, causal):
     t_f = timeit(lambda: ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True))
     t_b = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal))
     tc = ops.attention_bwd_uses_tcgen05(q, k, v, o, lse, d_o, heads, scale, causal=causal)
-    print(f"{name}: fwd {t_f * 1e3:.1f} us, bwd (delta + kernels) {t_b * 1e3:.1f} us, tcgen05 bwd = {tc}", flush=True)
+    kind = ops.attention_kernel(q, k, v, heads, causal=causal, need_lse=True)
+    print(f"{name}: fwd {t_f * 1e3:.1f} us ({kind}), bwd (delta + kernels) {t_b * 1e3:.1f} us, tcgen05 bwd = {tc}", flush=True)
 
 
-print("VB_ATTN_BWD_TC =", os.environ.get("VB_ATTN_BWD_TC", "(default on)"))
+print("VB_ATTN_BWD_TC =", os.environ.get("VB_ATTN_BWD_TC", "(default on)"), " VB_ATTN_FWD_TC =", os.environ.get("VB_ATTN_FWD_TC", "(default on)"))
 case("opt self-attention 976 x 976 causal", 1, 32, 80, 976, 976, True)
 case("q-former cross-attention 32 x 2056", 17, 12, 64, 32, 2056, False)
 case("q-former self-attention 32 x 32", 17, 12, 64, 32, 32, False)

@@ -250,6 +250,23 @@ def _attn_ref(q, k, v, heads, scale, causal, key_mask):
     return (p @ vh).transpose(1, 2).reshape(b, sq, hd)
 
 
+def _attn_lse_ref(q, k, heads, scale, causal, key_mask):
+    """log-sum-exp of the masked, scaled scores, (b, heads, sq); -inf for a row that sees no key."""
+    b, sq, hd = q.shape
+    skv = k.shape[1]
+    d = hd // heads
+    qh = q.float().view(b, sq, heads, d).transpose(1, 2)
+    kh = k.float().view(b, skv, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        i = torch.arange(sq, device=q.device)[:, None]
+        j = torch.arange(skv, device=q.device)[None, :]
+        s = s.masked_fill(j > i + (skv - sq), float("-inf"))
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[:, None, None, :] == 0, float("-inf"))
+    return torch.logsumexp(s, dim=-1)
+
+
 ATTN_CASES = [
     # b, heads, d, sq, skv, causal, masked
     (3, 16, 88, 257, 257, False, False),
@@ -288,6 +305,12 @@ def test_attention_fwd_bwd(b, heads, d, sq, skv, causal, masked):
         key_mask = torch.ones(b, skv, dtype=torch.uint8, device="cuda")
         key_mask[0, :17] = 0  # left padding on the first sequence
     o, lse = ops.attention(q, k, v, heads, scale, causal=causal, key_mask=key_mask, need_lse=True)
+    # head dims that are a multiple of 16 run the tcgen05 flash kernel (attention_flash_tcgen05.cu)
+    want_kernel = "tcgen05_flash" if d % 16 == 0 and os.environ.get("VB_ATTN_FWD_TC") != "0" else "mma_sync"
+    assert ops.attention_kernel(q, k, v, heads, causal=causal, key_mask=key_mask, need_lse=True) == want_kernel
+    lse_ref = _attn_lse_ref(q, k, heads, scale, causal, key_mask)
+    fin = torch.isfinite(lse_ref)
+    _close(lse[fin], lse_ref[fin], atol=0.02, rtol=0.01, what="attn lse")
     qf = q.float().detach().clone().requires_grad_(True)
     kf = k.float().detach().clone().requires_grad_(True)
     vf = v.float().detach().clone().requires_grad_(True)
@@ -324,8 +347,8 @@ def test_attention_tcgen05_vit_class(b, heads, d, s):
     o = ops.attention(q, k, v, heads, scale)
     ref = _attn_ref(q, k, v, heads, scale, False, None)
     _close(o, ref, atol=0.02, rtol=0.02, what="attn tcgen05")
-    o2, _ = ops.attention(q, k, v, heads, scale, need_lse=True)  # mma.sync kernel, same inputs
-    _close(o, o2, atol=0.02, rtol=0.02, what="tcgen05 vs mma.sync")
+    o2, _ = ops.attention(q, k, v, heads, scale, need_lse=True)  # the flash kernel (tcgen05 or mma.sync), same inputs
+    _close(o, o2, atol=0.02, rtol=0.02, what="single-pass vs flash kernel")
 
 
 @pytest.mark.parametrize("b,heads,d,sq,skv,causal", [(3, 4, 88, 257, 257, False), (2, 2, 64, 40, 300, False),
