@@ -75,7 +75,8 @@ int vb_gemm(const vb_gemm_args* a, void* stream) {
       return fail_msg("vb_gemm", "stats_out needs a bf16 output and beta == 0");
     if (a->stats_zero != nullptr && (a->stats_zero == a->stats_out || a->stats_zero == a->ln_stats || a->row_group != 0))
       return fail_msg("vb_gemm", "stats_zero must be a buffer this launch neither reads nor fills");
-    if ((reinterpret_cast<uintptr_t>(a->stats_zero) & 7u) != 0 || (reinterpret_cast<uintptr_t>(a->ln_stats) & 7u) != 0 || (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15u) != 0)
+    if ((reinterpret_cast<uintptr_t>(a->stats_zero) & 15u) != 0 || (reinterpret_cast<uintptr_t>(a->ln_stats) & 15u) != 0 ||
+        (reinterpret_cast<uintptr_t>(a->stats_out) & 7u) != 0 || (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15u) != 0)
       return fail_msg("vb_gemm", "ln_stats / ln_colsum alignment");
   }
   if (a->backend != VB_GEMM_GENERIC && elig) VB_CHECK("vb_gemm[tcgen05]", vb::gemm_tcgen05_launch(*a, st(stream)));
@@ -91,7 +92,7 @@ int vb_layernorm(const void* x, const void* residual, const float* gamma, const 
                                              ldx, ldr, ldy, eps, st(stream)));
 }
 
-int vb_row_stats(const void* x, float* stats, int64_t rows, int64_t cols, int64_t ldx, void* stream) {
+int vb_row_stats(const void* x, double* stats, int64_t rows, int64_t cols, int64_t ldx, void* stream) {
   if (x == nullptr || stats == nullptr || rows < 0 || cols <= 0 || ldx < cols)
     return fail_msg("vb_row_stats", "bad arguments");
   VB_CHECK("vb_row_stats", vb::row_stats_launch(x, stats, rows, cols, ldx, st(stream)));

@@ -19,9 +19,9 @@
 // Every product has its reduction index on the TMEM columns, so nothing is transposed through shared memory and
 // dQ needs no fp32 atomics (the mma.sync kernel's memset + atomics + convert pass): the backward computes the
 // scores twice instead, once per orientation.  The forward sweeps the keys twice — sweep 0 reduces the row
-// maximum / sum (the lse), sweep 1 multiplies the already normalised P with V — which keeps O accumulating in
-// TMEM without the rescaling of an online softmax; the tensor work is a few percent of the kernel, the exp2 of
-// the extra sweep is what it costs.
+// maximum / sum (the lse), sweep 1 multiplies P = exp2(s - max) with V and the epilogue divides by the sum —
+// which keeps O accumulating in TMEM without the rescaling of an online softmax; the tensor work is a few
+// percent of the kernel, the exp2 of the extra sweep is what it costs.
 //
 // The column side is walked in 64-column blocks ("items"), even items by warps 4-7 in TMEM slot 0, odd items by
 // warps 8-11 in slot 1:
@@ -343,6 +343,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
       // do the rows of this unit carry a term at all (other than the lse of a query row)?
       const bool rows_plain = MODE == kBwdKV ? (km == nullptr && rt * kFaEdge + kFaEdge <= p.skv) : false;
       float run_m = -INFINITY, run_l = 0.0f;  // forward, sweep 0: running maximum (log2 units) and sum
+      float fwd_scale = 0.0f;                 // forward: 1 / row sum, applied to O in the epilogue
       const int n_blk = c_end - c_begin;
       for (int sweep = 0; sweep < kSweeps; ++sweep) {
         for (int kb = 0; kb < n_blk; ++kb) {
@@ -487,13 +488,18 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
           named_bar_sync(3, 256);
           const float2 o = sStat[(grp ^ 1) * kFaEdge + r_in];
           const float m = fmaxf(run_m, o.x);
+          // sweep 1 forms P = exp2(s - max) (the row's largest term is exactly 1, as in an online softmax) and
+          // the epilogue divides by the sum
           neg_row = INFINITY;
+          fwd_scale = 0.0f;
+          float lse = -INFINITY;
           if (m != -INFINITY && row_g < p.sq) {
             const float l = run_l * exp2f(run_m - m) + o.y * exp2f(o.x - m);
-            neg_row = m + log2f(l);
+            neg_row = m;
+            fwd_scale = 1.0f / l;
+            lse = (m + log2f(l)) * 0.69314718055994531f;
           }
-          if (grp == 0 && row_g < p.sq && p.lse_out != nullptr)
-            p.lse_out[bh_off + row_g] = neg_row == INFINITY ? -INFINITY : neg_row * 0.69314718055994531f;
+          if (grp == 0 && row_g < p.sq && p.lse_out != nullptr) p.lse_out[bh_off + row_g] = lse;
           named_bar_sync(3, 256);  // sStat is free for the next unit
         }
       }
@@ -511,7 +517,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
       __nv_bfloat16* out = (MODE == kFwd || (MODE == kBwdKV && grp == 0)) ? p.out1 : p.out2;
       const bool first = MODE == kFwd || (MODE == kBwdKV && grp == 0);
       const long long bs = first ? p.out1_bs : p.out2_bs, rs = first ? p.out1_rs : p.out2_rs;
-      const float mul = first ? 1.0f : p.out2_mul;
+      const float mul = MODE == kFwd ? fwd_scale : (first ? 1.0f : p.out2_mul);
       const uint32_t acc_col = (MODE == kFwd || (MODE == kBwdKV && grp == 0)) ? col_acc1 : col_acc2;
       const int g_lo = MODE == kBwdKV ? 0 : (grp == 0 ? 0 : (n16 + 1) / 2);
       const int g_hi = MODE == kBwdKV ? n16 : (grp == 0 ? (n16 + 1) / 2 : n16);
@@ -578,7 +584,10 @@ static bool fa_layout_ok(const vb_attn_args& f) {
 
 bool attention_flash_tcgen05_eligible(const vb_attn_args& f) {
   static const bool on = fa_enabled("VB_ATTN_FWD_TC");
-  return on && fa_layout_ok(f);
+  // The forward has queries on the 128 TMEM lanes: with fewer than one full row tile (the Q-Former's 32 queries)
+  // most lanes idle and the mma.sync kernel's 64-row tiles are faster (profiles/r02_attn_flash.txt).  The
+  // backward keeps the tcgen05 path there: its dK / dV pass has the keys on the lanes.
+  return on && f.sq >= kFaEdge && fa_layout_ok(f);
 }
 
 bool attention_bwd_tcgen05_eligible(const vb_attn_bwd_args& a) {

@@ -24,11 +24,15 @@ struct EpiParams {
   int out_f32;
   // LayerNorm folded into this GEMM (vb_gemm_args.ln_stats / ln_colsum): per-row [sum, sum of squares]
   // of A's rows over K columns; out = rstd * acc - rstd * mean * colsum[n] + bias[n]
-  const float* ln_stats;
+  // The statistics are f64: a row's sum is assembled from up to N / 16 f32 partials by atomics in no fixed order,
+  // and f64 addition of a few dozen f32 values is exact (their bits fit the 53-bit mantissa), so the result does
+  // not depend on that order -- the step stays reproducible bit for bit (f32 atomics were not:
+  // scripts/micro/vision_repeat.py).
+  const double* ln_stats;
   const float* ln_colsum;
   float ln_inv_k, ln_eps;
-  float* stats_out;          // per stored row [sum, sum of squares] of the bf16 output, f32 atomics
-  float* stats_zero;         // (M, 2) buffer cleared by the tiles of the first column block
+  double* stats_out;         // per stored row [sum, sum of squares] of the bf16 output, f64 atomics
+  double* stats_zero;        // (M, 2) buffer cleared by the tiles of the first column block
 };
 
 // acc (+) the `residual` operand: a residual add, or — for the activation-backward epilogues — the product
@@ -41,9 +45,11 @@ VB_DEVICE float epi_combine(int epilogue, bool act_bwd, float acc, float saved) 
 
 // (rstd, -rstd * mean) of row `row` from the [sum, sum of squares] pair
 VB_DEVICE float2 ln_fold_coeffs(const EpiParams& p, long long row) {
-  const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
-  const float mean = st.x * p.ln_inv_k;
-  const float var = fmaxf(fmaf(-mean, mean, st.y * p.ln_inv_k), 0.0f);
+  const double2 st = __ldg(reinterpret_cast<const double2*>(p.ln_stats) + row);
+  const double inv_k = static_cast<double>(p.ln_inv_k);
+  const double mean_d = st.x * inv_k;
+  const float mean = static_cast<float>(mean_d);
+  const float var = fmaxf(static_cast<float>(fma(-mean_d, mean_d, st.y * inv_k)), 0.0f);
   const float rstd = rsqrtf(var + p.ln_eps);
   return make_float2(rstd, -rstd * mean);
 }
@@ -84,7 +90,7 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
   const bool full = (col0 + 16 <= p.n);
-  if (p.stats_zero != nullptr && col0 == 0) *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
+  if (p.stats_zero != nullptr && col0 == 0) *reinterpret_cast<double2*>(p.stats_zero + 2 * row) = make_double2(0.0, 0.0);
   if (p.ln_stats != nullptr) ln_fold_apply(p, ln_fold_coeffs(p, row), col0, v);
   if (p.bias != nullptr) {
     if (full) {
@@ -189,8 +195,8 @@ VB_DEVICE void epilogue_row16(const EpiParams& p, long long row, long long col0,
         }
     }
     if (p.stats_out != nullptr) {
-      atomicAdd(p.stats_out + 2 * out_row, st_s);
-      atomicAdd(p.stats_out + 2 * out_row + 1, st_q);
+      atomicAdd(p.stats_out + 2 * out_row, static_cast<double>(st_s));
+      atomicAdd(p.stats_out + 2 * out_row + 1, static_cast<double>(st_q));
     }
   }
 }

@@ -258,10 +258,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (cq == 0) VB_TRACE(9);
         }
         if (p.stats_zero != nullptr && n_blk == 0 && cq == 0 && row < p.m)
-          *reinterpret_cast<float2*>(p.stats_zero + 2 * row) = make_float2(0.0f, 0.0f);
+          *reinterpret_cast<double2*>(p.stats_zero + 2 * row) = make_double2(0.0, 0.0);
         if (p.stats_out != nullptr && row < p.m && slab_live) {
-          atomicAdd(p.stats_out + 2 * row, st_s);
-          atomicAdd(p.stats_out + 2 * row + 1, st_q);
+          atomicAdd(p.stats_out + 2 * row, static_cast<double>(st_s));
+          atomicAdd(p.stats_out + 2 * row + 1, static_cast<double>(st_q));
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         continue;

@@ -16,7 +16,7 @@ cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, c
                           const float* rstd, const void* dx_add, void* dx, float* dgamma,
                           float* dbeta, long long rows, long long cols, cudaStream_t s);
 
-cudaError_t row_stats_launch(const void* x, float* stats, long long rows, long long cols, long long ldx,
+cudaError_t row_stats_launch(const void* x, double* stats, long long rows, long long cols, long long ldx,
                              cudaStream_t s);
 
 cudaError_t attention_fwd_launch(const vb_attn_args& a, cudaStream_t stream);

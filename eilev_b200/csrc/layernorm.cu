@@ -344,7 +344,7 @@ cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, c
 // the consuming GEMM (vb_gemm_args.ln_stats) when the producer of x is not a GEMM epilogue.
 // One warp per row; read-only pass (2 B per element).
 __global__ void __launch_bounds__(kLnWarps * 32)
-row_stats_kernel(const __nv_bfloat16* x, float* stats, long long rows, long long cols, long long ldx) {
+row_stats_kernel(const __nv_bfloat16* x, double* stats, long long rows, long long cols, long long ldx) {
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
   const int lane = threadIdx.x & 31;
@@ -373,12 +373,12 @@ row_stats_kernel(const __nv_bfloat16* x, float* stats, long long rows, long long
   s = warp_sum(s);
   q = warp_sum(q);
   if (lane == 0) {
-    stats[2 * row] = s;
-    stats[2 * row + 1] = q;
+    stats[2 * row] = static_cast<double>(s);
+    stats[2 * row + 1] = static_cast<double>(q);
   }
 }
 
-cudaError_t row_stats_launch(const void* x, float* stats, long long rows, long long cols, long long ldx,
+cudaError_t row_stats_launch(const void* x, double* stats, long long rows, long long cols, long long ldx,
                              cudaStream_t s) {
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);

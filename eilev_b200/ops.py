@@ -42,10 +42,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
     """``out = act(alpha * (a @ w.T + bias)) + residual (+ beta*out)``.
 
     a: (M, K) bf16 (last dim contiguous), w: (N, K) bf16 — an ``nn.Linear`` weight.
-    ln_fold = (stats (M, 2) f32, colsum (N) f32, eps): ``a`` is the UN-normalised input of a LayerNorm
+    ln_fold = (stats (M, 2) f64, colsum (N) f32, eps): ``a`` is the UN-normalised input of a LayerNorm
     whose gamma is already folded into ``w`` and whose beta into ``bias`` (pack_ln_fold); the epilogue
-    applies the per-row mean / rstd.  stats_out (rows, 2) f32, zeroed by the caller: receives the row
-    [sum, sum of squares] of the stored output for the next folded LayerNorm.  stats_zero (M, 2) f32: a
+    applies the per-row mean / rstd.  stats_out (rows, 2) f64, zeroed by the caller: receives the row
+    [sum, sum of squares] of the stored output for the next folded LayerNorm.  stats_zero (M, 2) f64: a
     statistics buffer the stream has finished reading, cleared by this launch for its next producer.
     """
     _need(a, torch.bfloat16, "gemm.a")
@@ -81,16 +81,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
         args.dropout_p, args.dropout_seed, args.dropout_salt = float(dropout[0]), dropout[1].data_ptr(), int(dropout[2])
     if ln_fold is not None:
         stats, colsum, eps = ln_fold
-        _need(stats, torch.float32, "gemm.ln_fold.stats")
+        _need(stats, torch.float64, "gemm.ln_fold.stats")
         _need(colsum, torch.float32, "gemm.ln_fold.colsum")
         assert stats.is_contiguous() and stats.shape == (m, 2) and colsum.numel() == n
         args.ln_stats, args.ln_colsum, args.ln_eps = stats.data_ptr(), colsum.data_ptr(), float(eps)
     if stats_out is not None:
-        _need(stats_out, torch.float32, "gemm.stats_out")
+        _need(stats_out, torch.float64, "gemm.stats_out")
         assert stats_out.is_contiguous() and stats_out.shape == (out.shape[0], 2)
         args.stats_out = stats_out.data_ptr()
     if stats_zero is not None:
-        _need(stats_zero, torch.float32, "gemm.stats_zero")
+        _need(stats_zero, torch.float64, "gemm.stats_zero")
         assert stats_zero.is_contiguous() and stats_zero.shape == (m, 2)
         args.stats_zero = stats_zero.data_ptr()
     check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
@@ -98,11 +98,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
 
 
 def row_stats(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-    """(rows, 2) f32 [sum, sum of squares] of every row of a 2-D bf16 tensor (see gemm(ln_fold=...))."""
+    """(rows, 2) f64 [sum, sum of squares] of every row of a 2-D bf16 tensor (see gemm(ln_fold=...))."""
     _need(x, torch.bfloat16, "row_stats.x")
     assert x.dim() == 2 and x.stride(1) == 1
     if out is None:
-        out = torch.empty((x.shape[0], 2), dtype=torch.float32, device=x.device)
+        out = torch.empty((x.shape[0], 2), dtype=torch.float64, device=x.device)
+    assert out.dtype == torch.float64 and out.is_contiguous()
     check(_lib.lib().vb_row_stats(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0), _stream()),
           "vb_row_stats")
     return out

@@ -97,24 +97,26 @@ typedef struct vb_gemm_args {
   /* LayerNorm folded into the GEMM (ABI 5; tcgen05 path only).  For y = LN(x) W^T + b with
    * LN(x) = (x - mean) rstd * gamma + beta, the caller passes A = x (un-normalised), B = W * gamma
    * (column-scaled), bias = b + W beta, and
-   *   ln_stats  (M, 2) f32: [sum_k x[m,k], sum_k x[m,k]^2] of every A row (over all K columns),
+   *   ln_stats  (M, 2) f64: [sum_k x[m,k], sum_k x[m,k]^2] of every A row (over all K columns),
    *   ln_colsum (N) f32:    sum_k B[n,k],
    * and the epilogue forms  rstd_m * acc - rstd_m * mean_m * ln_colsum[n] + bias[n]  before alpha /
    * activation — the normalised activations are never written to memory
    * (HF:blip_2/modeling_blip_2.py:388-402: layer_norm1 -> qkv, layer_norm2 -> fc1).  NULL: off. */
-  const float* ln_stats;
+  const double* ln_stats;
   const float* ln_colsum;
   float ln_eps;
   int32_t reserved3;
   /* Row statistics of the OUTPUT for the next folded LayerNorm: when non-NULL, the epilogue adds
    * [sum_n C[m,n], sum_n C[m,n]^2] (of the bf16 values it stores) to stats_out[2 m'], [2 m' + 1]
-   * with f32 atomics (m' = the stored row).  The buffer must be zeroed by the caller. */
-  float* stats_out;
-  /* When non-NULL: rows [0, M) of this (M, 2) f32 buffer are set to zero by the epilogue (by the tiles of
+   * with f64 atomics (m' = the stored row).  f64 because the partial sums arrive in no fixed order: adding a few
+   * dozen f32 partials in f64 is exact, so the statistics — and with them the whole step — are reproducible bit
+   * for bit from run to run (ABI 6; they were f32 in ABI 5).  The buffer must be zeroed by the caller. */
+  double* stats_out;
+  /* When non-NULL: rows [0, M) of this (M, 2) f64 buffer are set to zero by the epilogue (by the tiles of
    * the first column block).  Lets the two statistics buffers of a transformer layer re-arm each other
    * without memset launches: the GEMM that fills one buffer clears the other, which its predecessor in
    * the stream has already consumed. */
-  float* stats_zero;
+  double* stats_zero;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
@@ -132,11 +134,11 @@ int vb_layernorm(const void* x, const void* residual, const float* gamma, const 
                  void* y, float* mean, float* rstd, int64_t rows, int64_t cols, int64_t ldx,
                  int64_t ldr, int64_t ldy, float eps, void* stream);
 
-/* stats[r] = [sum_c x[r,c], sum_c x[r,c]^2] (f32, rows x 2) of a bf16 matrix: the statistics a
+/* stats[r] = [sum_c x[r,c], sum_c x[r,c]^2] (f64, rows x 2) of a bf16 matrix: the statistics a
  * LayerNorm folded into the consuming GEMM needs (vb_gemm_args.ln_stats) when x was not produced
  * by a GEMM epilogue (vb_gemm_args.stats_out).  HF:blip_2/modeling_blip_2.py:388-389 (layer_norm1
  * of the first encoder layer, fed by the embeddings). */
-int vb_row_stats(const void* x, float* stats, int64_t rows, int64_t cols, int64_t ldx, void* stream);
+int vb_row_stats(const void* x, double* stats, int64_t rows, int64_t cols, int64_t ldx, void* stream);
 
 /* dx (+ optional dgamma/dbeta accumulation, f32 atomics) of the LayerNorm above.
  * xin is the tensor that was normalised (x + residual), bf16.  dx is bf16; when

@@ -40,8 +40,8 @@ def main():
             w, bias, cs = ln_fold(w, bias, torch.ones(k, device="cuda"), torch.zeros(k, device="cuda"))
             kw["ln_fold"] = (ops.row_stats(a), cs, 1e-6)
         if stats:
-            kw["stats_out"] = torch.zeros(m, 2, device="cuda")
-            kw["stats_zero"] = torch.zeros(m, 2, device="cuda")
+            kw["stats_out"] = torch.zeros(m, 2, device="cuda", dtype=torch.float64)
+            kw["stats_zero"] = torch.zeros(m, 2, device="cuda", dtype=torch.float64)
         cases.append((a, w, bias, kw))
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     for a, w, bias, kw in cases:  # warm-up (kernel attributes, allocator)
