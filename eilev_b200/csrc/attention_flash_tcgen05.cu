@@ -58,6 +58,17 @@ constexpr int kFaStatBytes = 2 * kFaEdge * 8;   // forward: [2 groups][128] (max
 constexpr int kFaSmem = 2 * kFaTile + kFaRing * 2 * kFaBlk + kFaColBytes + kFaStatBytes + 256 + 1024;
 constexpr float kFaLog2e = 1.4426950408889634f;
 
+// -DVB_FA_TRACE (scripts/micro/attn_trace.sh): clock64 stamps of CTA 0's MMA issuer and of one warp per group,
+// read back through vb_debug_attn_trace.  Off in the product build.
+#ifdef VB_FA_TRACE
+__device__ long long g_fa_trace[3 * 512];
+__device__ int g_fa_trace_n[3];
+#define FA_TRACE(who, tag) do { if (blockIdx.x == 0) { int i_ = g_fa_trace_n[who]; if (i_ < 255) { \
+  g_fa_trace[(who) * 512 + 2 * i_] = (tag); g_fa_trace[(who) * 512 + 2 * i_ + 1] = clock64(); g_fa_trace_n[who] = i_ + 1; } } } while (0)
+#else
+#define FA_TRACE(who, tag)
+#endif
+
 enum FaMode : int { kFwd = 0, kBwdQ = 1, kBwdKV = 2 };
 
 struct FaParams {
@@ -113,6 +124,60 @@ VB_DEVICE void fa_unit_coords(const FaParams& p, int unit, int& b, int& h, int& 
       if (e < c_end) c_end = e;
     }
   }
+}
+
+// (neg, delta) of two neighbouring columns from the per-column table in shared memory
+VB_DEVICE float4 fa_col_pair(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+  return v;
+}
+
+// 32 columns of one row, no per-element masks: P = exp2(T1 * c - neg), dS = P * (T2 - delta), packed to bf16
+// pairs.  neg / delta = the row's term plus (COL_TERMS) the column's, or (!ROW_TERMS) the column's alone.
+// Straight-line code: the variants are chosen once per item, outside the unrolled loop.
+template <bool HAS_P, bool HAS_DS, bool COL_TERMS, bool ROW_TERMS>
+VB_DEVICE void fa_chunk_plain(const uint32_t (&t1)[32], const uint32_t (&t2)[32], uint32_t (&u1)[16], uint32_t (&u2)[16],
+                              float c, float neg_row, float d_row, uint32_t col_addr) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float na = neg_row, nb = neg_row, da = d_row, db = d_row;
+    if (COL_TERMS) {
+      const float4 cc = fa_col_pair(col_addr + 8 * j);
+      if (ROW_TERMS) {
+        na += cc.x; nb += cc.z; da += cc.y; db += cc.w;
+      } else {
+        na = cc.x; nb = cc.z; da = cc.y; db = cc.w;
+      }
+    }
+    const float pa = exp2f(fmaf(__uint_as_float(t1[j]), c, -na));
+    const float pb = exp2f(fmaf(__uint_as_float(t1[j + 1]), c, -nb));
+    if (HAS_P) u1[j >> 1] = pack_bf16x2(pa, pb);
+    if (HAS_DS) u2[j >> 1] = pack_bf16x2(pa * (__uint_as_float(t2[j]) - da), pb * (__uint_as_float(t2[j + 1]) - db));
+  }
+}
+
+// Forward statistics of 32 unmasked columns: running maximum (log2 units) and sum, four independent chains
+VB_DEVICE void fa_stats_plain(const uint32_t (&t1)[32], float c, float& run_m, float& run_l) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    m0 = fmaxf(m0, __uint_as_float(t1[j]) * c);
+    m1 = fmaxf(m1, __uint_as_float(t1[j + 1]) * c);
+    m2 = fmaxf(m2, __uint_as_float(t1[j + 2]) * c);
+    m3 = fmaxf(m3, __uint_as_float(t1[j + 3]) * c);
+  }
+  const float m_new = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));  // finite: the scores are
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    s0 += exp2f(fmaf(__uint_as_float(t1[j]), c, -m_new));
+    s1 += exp2f(fmaf(__uint_as_float(t1[j + 1]), c, -m_new));
+    s2 += exp2f(fmaf(__uint_as_float(t1[j + 2]), c, -m_new));
+    s3 += exp2f(fmaf(__uint_as_float(t1[j + 3]), c, -m_new));
+  }
+  run_l = run_l * exp2f(run_m - m_new) + ((s0 + s1) + (s2 + s3));
+  run_m = m_new;
 }
 
 template <int MODE>
@@ -188,7 +253,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t r_ph = 0;
       int ct = 0;  // running item counter: ring slot = ct % kFaRing, phase = (ct / kFaRing) & 1
       for (int n = 0; n * static_cast<int>(gridDim.x) < units; ++n) {
@@ -223,7 +288,10 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // (elect_one, not lane == 0: ptxas keeps the operands of a region guarded by elect.sync in uniform registers;
+    // under a lane test every tcgen05.mma was wrapped in a waterfall loop, ~180 clk per instruction in
+    // profiles/r02_attn_flash_trace.txt, and the issuer paced the whole kernel)
+    if (elect_one()) {
       const uint32_t idesc_acc = umma_idesc_bf16(128, static_cast<uint32_t>(p.dpad)) | (1u << 16);  // B MN-major
       uint32_t r_ph = 0, u_ph[2] = {0, 0}, free_ph = 0;
       int ct = 0;
@@ -249,8 +317,10 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
         auto issue_acc = [&](int k) {
           const int s = k & 1;
           const int buf = (ct0 + k) % kFaRing;
+          FA_TRACE(0, 100 + k);
           mbar_wait(&u_ready[s], u_ph[s]);
           u_ph[s] ^= 1u;
+          FA_TRACE(0, 200 + k);
           if (!(MODE == kFwd && k < n_blk)) {  // (the forward's statistics sweep has nothing to accumulate)
             if (!acc_started) {  // the previous unit's accumulators have been read out
               mbar_wait(acc_free, free_ph ^ 1u);
@@ -273,12 +343,15 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             }
             acc_started = true;
           }
+          FA_TRACE(0, 300 + k);
           umma_commit(&c_empty[buf]);
         };
         auto issue_scores = [&](int k) {
           const int s = k & 1;
           const int buf = (ct0 + k) % kFaRing;
+          FA_TRACE(0, 400 + k);
           mbar_wait(&c_full[buf], ((ct0 + k) / kFaRing) & 1);
+          FA_TRACE(0, 500 + k);
           tc_fence_after();
           const int valid = blk_valid(c_begin + k % n_blk);
           const uint32_t idesc_t = umma_idesc_bf16(128, static_cast<uint32_t>((valid + 15) / 16 * 16));
@@ -298,6 +371,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             }
           }
           umma_commit(&t_full[s]);
+          FA_TRACE(0, 600 + k);
         };
         for (int k = 0; k < n_items; ++k) {
           if (k >= 2) issue_acc(k - 2);  // frees the group's TMEM slot (in issue order)
@@ -355,6 +429,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
           // ---- per-column terms -> shared memory (the group's first 64 threads, one column each).  Key columns
           // carry a term only when some key of the tile is masked or out of range.
           const bool cols_plain = kRowsAreKeys ? false : (km == nullptr && valid == kFaSub);
+          if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 100 + sweep * n_blk + kb);
           float2* col = sCol + (grp * 2 + (tt & 1)) * kFaSub;
           if (!cols_plain) {
             if (r_in < kFaSub) {
@@ -382,8 +457,10 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             slow = slow || key_max > q_min + off;
           }
           const int n_used = (valid + 15) / 16 * 16;  // columns the instructions computed / will read
+          if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 200 + sweep * n_blk + kb);
           mbar_wait(&t_full[grp], t_ph);
           t_ph ^= 1u;
+          if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 300 + sweep * n_blk + kb);
           tc_fence_after();
 #pragma unroll 1
           for (int c2 = 0; c2 < 2; ++c2) {
@@ -395,6 +472,10 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             tmem_ld_wait();
             if (MODE == kFwd && sweep == 0) {
               // ---- statistics sweep: running row maximum / sum of this half's columns
+              if (!slow && cols_plain) {
+                fa_stats_plain(t1, p.scale_log2, run_m, run_l);
+                continue;
+              }
               float cmax = -INFINITY;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -422,23 +503,13 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             }
             uint32_t u1[16], u2[16];
             if (!slow) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float na = neg_row, nb = neg_row, da = d_row, db = d_row;
-                if (!cols_plain) {
-                  const float2 ca = col[col0 + j], cb = col[col0 + j + 1];
-                  if (rows_plain) {
-                    na = ca.x; nb = cb.x; da = ca.y; db = cb.y;
-                  } else {
-                    na += ca.x; nb += cb.x; da += ca.y; db += cb.y;
-                  }
-                }
-                const float pa = exp2f(fmaf(__uint_as_float(t1[j]), p.scale_log2, -na));
-                const float pb = exp2f(fmaf(__uint_as_float(t1[j + 1]), p.scale_log2, -nb));
-                if constexpr (kHasAcc1) u1[j >> 1] = pack_bf16x2(pa, pb);
-                if constexpr (kHasAcc2)
-                  u2[j >> 1] = pack_bf16x2(pa * (__uint_as_float(t2[j]) - da), pb * (__uint_as_float(t2[j + 1]) - db));
-              }
+              const uint32_t col_addr = smem_u32(col + col0);
+              if (cols_plain)
+                fa_chunk_plain<kHasAcc1, kHasAcc2, false, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
+              else if (rows_plain)
+                fa_chunk_plain<kHasAcc1, kHasAcc2, true, false>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
+              else
+                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
@@ -481,6 +552,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&u_ready[grp]);
+          if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 400 + sweep * n_blk + kb);
         }
         if (MODE == kFwd && sweep == 0) {
           // ---- the two column halves of a row meet: lse = max + log2(sum)
@@ -704,5 +776,20 @@ cudaError_t attention_bwd_tcgen05_launch(const vb_attn_bwd_args& a, cudaStream_t
   return launch_pdl(attn_flash_tc_kernel<kBwdQ>, dim3(static_cast<unsigned>(units < sms ? units : sms)),
                     dim3(kFaThreads), kFaSmem, stream, tq, tdo, bk, bv, p);
 }
+
+#ifdef VB_FA_TRACE
+extern "C" int vb_debug_attn_trace(long long* host_out, int* host_n, int reset) {
+  int e = 0;
+  if (host_out != nullptr) {
+    e |= static_cast<int>(cudaMemcpyFromSymbol(host_out, g_fa_trace, sizeof(g_fa_trace)));
+    e |= static_cast<int>(cudaMemcpyFromSymbol(host_n, g_fa_trace_n, sizeof(g_fa_trace_n)));
+  }
+  if (reset) {
+    const int z[3] = {0, 0, 0};
+    e |= static_cast<int>(cudaMemcpyToSymbol(g_fa_trace_n, z, sizeof(z)));
+  }
+  return e;
+}
+#endif
 
 }  // namespace vb

@@ -98,7 +98,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // (not lane == 0: see gemm_tcgen05_2cta.cu)
       uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0};
       int qt = 0;  // running Q tile counter -> buffer = qt & 1
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -135,7 +135,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
       const uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
       // B is MN-major; pv_n = 128, or round_up(d, 16) (partial 64-element swizzle atoms) when p.pv_n is set
@@ -450,7 +450,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // (not lane == 0: see gemm_tcgen05_2cta.cu)
       uint32_t k_ph = 0, v_ph = 0, q_ph[2] = {0, 0};
       int g = 0;  // running Q tile counter -> buffer = slot = g & 1
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -487,7 +487,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 256);
       const uint32_t idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(p.dpad)) | (1u << 16);  // B MN-major
       const int k_steps = (p.d + 15) / 16;

@@ -86,7 +86,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {  // (not lane == 0: see gemm_tcgen05_2cta.cu)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -104,7 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;

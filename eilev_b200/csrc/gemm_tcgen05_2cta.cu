@@ -121,7 +121,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // (elect_one, not lane == 0: ptxas keeps the operands of a region guarded by elect.sync in uniform registers;
+    // under a lane test every TMA / MMA instruction is wrapped in a waterfall loop that re-derives them)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = 2u * static_cast<uint32_t>(Cfg::kABytes + b_bytes);  // both CTAs
@@ -144,7 +146,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader only)
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       const uint32_t idesc_full = umma_idesc_bf16(2 * k2BM, static_cast<uint32_t>(tn));
       // last column block of an N that is not a multiple of BN (ViT: 1408 = 5 x 256 + 128): issue the MMA at
       // the width that holds real columns (rounded up to 32) instead of multiplying zero-filled rows
@@ -252,7 +254,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
         named_bar_sync(1 + cq, 128);
-        if (quarter == 0 && lane == 0) {
+        if (quarter == 0 && elect_one()) {
           if (slab_live) tma_store_2d(&tmap_c, slab, static_cast<int>(col_slab), static_cast<int>(tile_row0));
           bulk_commit();  // (an empty group keeps the wait_group bookkeeping uniform)
           if (cq == 0) VB_TRACE(9);
