@@ -180,6 +180,30 @@ VB_DEVICE void fa_stats_plain(const uint32_t (&t1)[32], float c, float& run_m, f
   run_m = m_new;
 }
 
+// The same with a per-column term (+inf for a masked / out-of-range key: the column drops out of both reductions)
+VB_DEVICE void fa_stats_cols(const uint32_t (&t1)[32], float c, uint32_t col_addr, float& run_m, float& run_l) {
+  float x[32];
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float4 cc = fa_col_pair(col_addr + 8 * j);
+    x[j] = fmaf(__uint_as_float(t1[j]), c, -cc.x);
+    x[j + 1] = fmaf(__uint_as_float(t1[j + 1]), c, -cc.z);
+    m0 = fmaxf(m0, x[j]);
+    m1 = fmaxf(m1, x[j + 1]);
+  }
+  const float m_new = fmaxf(run_m, fmaxf(m0, m1));
+  if (m_new == -INFINITY) return;  // nothing visible so far
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    s0 += exp2f(x[j] - m_new);
+    s1 += exp2f(x[j + 1] - m_new);
+  }
+  run_l = run_l * exp2f(run_m - m_new) + (s0 + s1);
+  run_m = m_new;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kFaThreads, 1)
 attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
@@ -472,8 +496,9 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             tmem_ld_wait();
             if (MODE == kFwd && sweep == 0) {
               // ---- statistics sweep: running row maximum / sum of this half's columns
-              if (!slow && cols_plain) {
-                fa_stats_plain(t1, p.scale_log2, run_m, run_l);
+              if (!slow && valid == kFaSub) {  // (a ragged item reads TMEM columns no instruction wrote: general path)
+                if (cols_plain) fa_stats_plain(t1, p.scale_log2, run_m, run_l);
+                else fa_stats_cols(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l);
                 continue;
               }
               float cmax = -INFINITY;

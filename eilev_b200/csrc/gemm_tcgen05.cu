@@ -310,15 +310,22 @@ cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int bn, cudaStream_t
 // arithmetic intensity.  Two or three waves (OPT qkv / fc1 at M = 976: four row tiles): the width in 192..256
 // whose tile count fills whole waves of the 74 pairs (N = 7680 -> 208: 148 tiles; N = 10240 -> 192), +5 % in
 // profiles/r02_gemm_opt_widths.txt.  Narrower pair tiles lose to the 1-CTA kernel: per k-block a CTA pulls
-// (128 + width/2) rows from L2 whatever the width, so the k-loop does not get faster (same file: ~535 clk per
-// k-block at width 144 and at 256).
-static int pick_2cta_block_n(long long m, long long n) {
+// (128 + width/2) rows from L2 whatever the width.
+static int pick_2cta_block_n(long long m, long long n, long long k) {
   if (m < 512) return 0;
   const long long pairs = 74;
   const long long m_tiles = (m + 255) / 256;
   const long long tiles256 = m_tiles * ((n + 255) / 256);
-  if (tiles256 < 100) return 0;
   if (tiles256 >= 4 * pairs) return 256;
+  if (tiles256 < 100) {
+    // Less than a wave and a half of 256-wide tiles (OPT N = 2560 at M = 976).  With a long reduction (fc2: K =
+    // 10 240) the narrowest width that still fits ONE wave of pairs beats the 1-CTA kernel (width 144: 72 tiles,
+    // 983 vs 880 TFLOP/s in profiles/r02_gemm_opt_widths.txt); with a short one the 1-CTA kernel's 120 CTAs win.
+    if (k < 8192) return 0;
+    for (int tn = 128; tn <= 256; tn += 16)
+      if (m_tiles * ((n + tn - 1) / tn) <= pairs) return tn;
+    return 0;
+  }
   int best = 256;
   double best_cost = 1e300;
   for (int tn = 256; tn >= 192; tn -= 16) {
@@ -335,7 +342,7 @@ static int pick_2cta_block_n(long long m, long long n) {
 cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
   if (a.reserved >= 1000) return gemm_tcgen05_2cta_launch(a, a.reserved - 1000, stream);
   if (a.reserved == 0) {
-    const int bn2 = pick_2cta_block_n(a.m, a.n);
+    const int bn2 = pick_2cta_block_n(a.m, a.n, a.k);
     if (bn2 > 0) return gemm_tcgen05_2cta_launch(a, bn2, stream);
   }
   EpiParams ep;
