@@ -667,6 +667,14 @@ static bool fa_enabled(const char* env) {
 
 static bool fa_layout_ok(const vb_attn_args& f) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  // Dropout on the probabilities and the T5 relative bias run the per-element path in every item, where the
+  // mma.sync kernels are faster (flan-t5-xl step 112.0 vs 115.6 ms, profiles/r02_attn_flash.txt).  VB_ATTN_TC_SLOW=1
+  // sends them through the tcgen05 kernels anyway (parity tests of that path).
+  static const bool slow_ok = [] {
+    const char* e = std::getenv("VB_ATTN_TC_SLOW");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!slow_ok && (f.rel_bias != nullptr || (f.dropout_p > 0.0f && f.dropout_seed != nullptr))) return false;
   if (f.d % 16 != 0 || f.d < 16 || f.d > 128) return false;
   if (!al(f.q) || !al(f.k) || !al(f.v) || !al(f.o)) return false;
   if (f.q_rs % 8 || f.k_rs % 8 || f.v_rs % 8 || f.o_rs % 8 || f.o_bs % 8) return false;

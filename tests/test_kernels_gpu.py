@@ -811,3 +811,19 @@ def test_decode_cross_attention_over_dense_encoder_kv(splits):
     ref = _attn_ref(q[:, None, :], k, v, heads, 0.7, False, mask)[:, 0]
     _close(out, ref, atol=0.02, rtol=0.02, what="decode cross attention")
     assert int(cnt.abs().sum()) == 0
+
+
+def test_attention_tcgen05_per_element_path_in_a_subprocess():
+    """Dropout on the probabilities and the T5 relative bias default to the mma.sync kernels (faster there); the
+    tcgen05 flash kernels' per-element path for them stays covered: the same parity tests re-run with
+    VB_ATTN_TC_SLOW=1 (the switch is read once per process)."""
+    import subprocess
+    import sys
+    if os.environ.get("VB_ATTN_TC_SLOW") == "1":
+        pytest.skip("already the forced run")
+    env = dict(os.environ, VB_ATTN_TC_SLOW="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k",
+                        "attention_dropout_fwd_bwd or attention_relative_bias_fwd_bwd"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
