@@ -67,6 +67,7 @@ SIGNATURES: dict[str, list] = {
     "vb_layernorm": [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, f32, vp],
     "vb_layernorm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, vp],
     "vb_row_stats": [vp, vp, i64, i64, i64, vp],
+    "vb_layernorm_bwd_dropout": [vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, C.c_uint64, i64, i64, vp],
     "vb_crop_resize_normalize_u8": [vp, i64, i64, i64, i64, i64, i64, i64, i64, i32, vp, i32, i64, i64, C.c_double,
                                     C.POINTER(C.c_float), C.POINTER(C.c_float), vp],
     "vb_attention_fwd": [C.POINTER(AttnArgs), vp],

@@ -105,7 +105,20 @@ int vb_layernorm_bwd(const void* dy, const void* xin, const float* gamma, const 
       dx == nullptr)
     return fail_msg("vb_layernorm_bwd", "null operand");
   VB_CHECK("vb_layernorm_bwd", vb::layernorm_bwd(dy, xin, gamma, mean, rstd, dx_add, dx, dgamma,
-                                                 dbeta, rows, cols, st(stream)));
+                                                 dbeta, rows, cols, nullptr, 0.0f, nullptr, 0, st(stream)));
+}
+
+int vb_layernorm_bwd_dropout(const void* dy, const void* xin, const float* gamma, const float* mean,
+                             const float* rstd, const void* dx_add, void* dx, void* dx_drop, float dropout_p,
+                             const uint64_t* dropout_seed, uint64_t dropout_salt, int64_t rows, int64_t cols,
+                             void* stream) {
+  if (dy == nullptr || xin == nullptr || gamma == nullptr || mean == nullptr || rstd == nullptr ||
+      dx == nullptr || dx_drop == nullptr || dropout_seed == nullptr)
+    return fail_msg("vb_layernorm_bwd_dropout", "null operand");
+  if (!(dropout_p > 0.0f) || dropout_p >= 1.0f) return fail_msg("vb_layernorm_bwd_dropout", "dropout_p must be in (0, 1)");
+  VB_CHECK("vb_layernorm_bwd_dropout",
+           vb::layernorm_bwd(dy, xin, gamma, mean, rstd, dx_add, dx, nullptr, nullptr, rows, cols, dx_drop, dropout_p,
+                             reinterpret_cast<const unsigned long long*>(dropout_seed), dropout_salt, st(stream)));
 }
 
 int vb_attention_fwd(const vb_attn_args* a, void* stream) {

@@ -14,7 +14,8 @@ cudaError_t layernorm_fwd(const void* x, const void* residual, const float* gamm
                           long long ldx, long long ldr, long long ldy, float eps, cudaStream_t s);
 cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
                           const float* rstd, const void* dx_add, void* dx, float* dgamma,
-                          float* dbeta, long long rows, long long cols, cudaStream_t s);
+                          float* dbeta, long long rows, long long cols, void* dx_drop, float drop_p,
+                          const unsigned long long* drop_seed, unsigned long long drop_salt, cudaStream_t s);
 
 cudaError_t row_stats_launch(const void* x, double* stats, long long rows, long long cols, long long ldx,
                              cudaStream_t s);

@@ -167,6 +167,13 @@ struct LnBwdParams {
   float* dgamma;
   float* dbeta;
   long long rows, cols;
+  // optional second output: dropout(dx) with the counter-hash mask of (seed + salt, row * cols + col) — the
+  // gradient entering the dgrad GEMM of the linear layer in front of a residual dropout (OPT backward)
+  __nv_bfloat16* dx_drop;
+  const unsigned long long* drop_seed;
+  unsigned long long drop_salt;
+  unsigned int drop_thresh;
+  float drop_scale;
 };
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.  One warp per row.
@@ -193,7 +200,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_kernel(const LnBwdPar
     const float xh = (__bfloat162float(xr[c]) - mean) * rstd;
     float d = rstd * (g - s1 - xh * s2);
     if (p.dx_add != nullptr) d += __bfloat162float(p.dx_add[row * p.cols + c]);
-    p.dx[row * p.cols + c] = __float2bfloat16(d);
+    const __nv_bfloat16 db = __float2bfloat16(d);
+    p.dx[row * p.cols + c] = db;
+    if (p.dx_drop != nullptr) {
+      const bool keep = dropout_keep(*p.drop_seed + p.drop_salt, static_cast<uint64_t>(row * p.cols + c), p.drop_thresh);
+      p.dx_drop[row * p.cols + c] = __float2bfloat16(keep ? __bfloat162float(db) * p.drop_scale : 0.0f);
+    }
   }
 }
 
@@ -259,6 +271,19 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBw
       u.x = pack_bf16x2(d[0], d[1]); u.y = pack_bf16x2(d[2], d[3]);
       u.z = pack_bf16x2(d[4], d[5]); u.w = pack_bf16x2(d[6], d[7]);
       *reinterpret_cast<uint4*>(p.dx + row * p.cols + vi * 8) = u;
+      if (p.dx_drop != nullptr) {  // the mask applies to the stored (bf16-rounded) gradient, as vb_dropout would
+        const uint64_t seed = *p.drop_seed + p.drop_salt;
+        const uint64_t base = static_cast<uint64_t>(row * p.cols + vi * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          o[j] = pack_bf16x2(dropout_keep(seed, base + 2 * j, p.drop_thresh) ? f.x * p.drop_scale : 0.0f,
+                             dropout_keep(seed, base + 2 * j + 1, p.drop_thresh) ? f.y * p.drop_scale : 0.0f);
+        }
+        *reinterpret_cast<uint4*>(p.dx_drop + row * p.cols + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
@@ -297,7 +322,7 @@ cudaError_t layernorm_bwd_launch(const LnBwdParams& p, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool vec = p.cols % 8 == 0 && p.cols <= 12 * 256 && al(p.dy) && al(p.xin) && al(p.dx) &&
-                   al(p.gamma) && (p.dx_add == nullptr || al(p.dx_add));
+                   al(p.gamma) && (p.dx_add == nullptr || al(p.dx_add)) && (p.dx_drop == nullptr || al(p.dx_drop));
   const int vpl = static_cast<int>((p.cols / 8 + 31) / 32);
   if (!vec) launch_pdl(ln_bwd_dx_kernel, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
   else if (vpl <= 1) launch_pdl(ln_bwd_dx_vec_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
@@ -327,8 +352,15 @@ cudaError_t layernorm_fwd(const void* x, const void* residual, const float* gamm
 
 cudaError_t layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
                           const float* rstd, const void* dx_add, void* dx, float* dgamma,
-                          float* dbeta, long long rows, long long cols, cudaStream_t s) {
+                          float* dbeta, long long rows, long long cols, void* dx_drop, float drop_p,
+                          const unsigned long long* drop_seed, unsigned long long drop_salt, cudaStream_t s) {
   LnBwdParams p;
+  const bool drop = dx_drop != nullptr && drop_seed != nullptr && drop_p > 0.0f;
+  p.dx_drop = drop ? reinterpret_cast<__nv_bfloat16*>(dx_drop) : nullptr;
+  p.drop_seed = drop_seed;
+  p.drop_salt = drop_salt;
+  p.drop_thresh = drop ? dropout_threshold(drop_p) : 0u;
+  p.drop_scale = drop ? 1.0f / (1.0f - drop_p) : 1.0f;
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
   p.xin = reinterpret_cast<const __nv_bfloat16*>(xin);
   p.gamma = gamma; p.mean = mean; p.rstd = rstd;

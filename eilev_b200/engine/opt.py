@@ -164,23 +164,35 @@ def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None
         gs = grad_loss.detach().to(torch.float32).reshape(()).contiguous()
     dlogits = ops.cross_entropy_bwd(ctx["logits"], ctx["labels"], ctx["row_lse"], ctx["n_valid"], gs)
     d_final = ops.gemm(dlogits, w["embed_t"])
-    dx = ops.layernorm_bwd(d_final, ctx["x_last"], w["lnf_g"], ctx["mf"], ctx["rf"])
-    del dlogits, d_final
     seed, p_h, p_a = ctx["seed"], ctx["p_h"], ctx["p_a"]
+    n_layers = len(w["layers"])
 
-    def masked(t, layer, site):
-        d = _drop(p_h, seed, layer, site)
-        return t if d is None else ops.dropout(t, d[0], d[1], d[2])
+    def ln_bwd(dy, xin, gamma, mean, rstd, dx_add, layer, site):
+        """dx of a LayerNorm and, in train mode, the same gradient through the residual dropout of (layer, site):
+        the input of the next dgrad GEMM, written by the same kernel."""
+        d = _drop(p_h, seed, layer, site) if layer >= 0 else None
+        if d is None:
+            dx_ = ops.layernorm_bwd(dy, xin, gamma, mean, rstd, dx_add=dx_add)
+            return dx_, dx_
+        if os.environ.get("VB_OPT_FUSED_LN_DROP", "1") == "0":  # measurement knob: the two-kernel form
+            dx_ = ops.layernorm_bwd(dy, xin, gamma, mean, rstd, dx_add=dx_add)
+            return dx_, ops.dropout(dx_, d[0], d[1], d[2])
+        return ops.layernorm_bwd(dy, xin, gamma, mean, rstd, dx_add=dx_add, dropout=d)
 
-    for li in range(len(w["layers"]) - 1, -1, -1):
+    # gradient of the residual stream entering the top layer, and its copy through fc2's dropout (site 2)
+    dx, dx_m = ln_bwd(d_final, ctx["x_last"], w["lnf_g"], ctx["mf"], ctx["rf"], None, n_layers - 1, 2)
+    del dlogits, d_final
+
+    for li in range(n_layers - 1, -1, -1):
         lw, s = w["layers"][li], ctx["saved"][li]
         # fc2 dgrad with the activation's backward in its epilogue (ReLU: mask by the saved output; GELU: the
         # pre-activation is recomputed)
         saved_act = s["f1"] if act == ops.EPI_RELU else ops.gemm(s["y2"], lw["fc1_w"], lw["fc1_b"])
-        d_pre = ops.gemm_act_bwd(masked(dx, li, 2), lw["fc2_wt"], saved_act, act)
+        d_pre = ops.gemm_act_bwd(dx_m, lw["fc2_wt"], saved_act, act)
         d_y2 = ops.gemm(d_pre, lw["fc1_wt"])
-        d_mid = ops.layernorm_bwd(d_y2, s["x_mid"], lw["ln2_g"], s["m2"], s["r2"], dx_add=dx)
-        d_o = ops.gemm(masked(d_mid, li, 1), lw["out_wt"]).view(b, l, dim)
+        # ... and through the attention output projection's dropout (site 1)
+        d_mid, d_mid_m = ln_bwd(d_y2, s["x_mid"], lw["ln2_g"], s["m2"], s["r2"], dx, li, 1)
+        d_o = ops.gemm(d_mid_m, lw["out_wt"]).view(b, l, dim)
         qkv = s["qkv"]
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :, :dim], qkv[:, :, dim:2 * dim], qkv[:, :, 2 * dim:], s["o"], s["lse"],
@@ -188,7 +200,8 @@ def opt_backward(lm, cache: PackCache, ctx: dict, grad_loss: torch.Tensor | None
                           dq=dqkv[:, :, :dim], dk=dqkv[:, :, dim:2 * dim], dv=dqkv[:, :, 2 * dim:],
                           dropout=_drop(p_a, seed, li, 0))
         d_y = ops.gemm(dqkv.view(rows, 3 * dim), lw["qkv_wt"])
-        dx = ops.layernorm_bwd(d_y, s["x_in"], lw["ln1_g"], s["m1"], s["r1"], dx_add=d_mid)
+        # the layer below: its fc2 dropout (site 2)
+        dx, dx_m = ln_bwd(d_y, s["x_in"], lw["ln1_g"], s["m1"], s["r1"], d_mid, li - 1, 2)
     if ctx["n_features"] == 0:
         return None
     return ops.splice_bwd(dx, ctx["slot"], ctx["n_features"])

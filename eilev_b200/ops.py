@@ -157,7 +157,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return (y, mean, rstd) if save_stats else y
 
 
-def layernorm_bwd(dy, xin, gamma, mean, rstd, *, dx_add=None, dgamma=None, dbeta=None):
+def layernorm_bwd(dy, xin, gamma, mean, rstd, *, dx_add=None, dgamma=None, dbeta=None, dropout=None):
+    """dx of a LayerNorm (+ dx_add).  dropout = (p, seed tensor, salt): also returns dropout(dx) with that mask,
+    written in the same pass -> (dx, dx_dropped)."""
     _need(dy, torch.bfloat16, "layernorm_bwd.dy")
     _need(xin, torch.bfloat16, "layernorm_bwd.xin")
     assert dy.is_contiguous() and xin.is_contiguous()
@@ -165,6 +167,14 @@ def layernorm_bwd(dy, xin, gamma, mean, rstd, *, dx_add=None, dgamma=None, dbeta
     dx = torch.empty_like(dy)
     if dx_add is not None:
         assert dx_add.is_contiguous()
+    if dropout is not None and dropout[0] > 0.0:
+        assert dgamma is None and dbeta is None
+        dx_drop = torch.empty_like(dy)
+        check(_lib.lib().vb_layernorm_bwd_dropout(dy.data_ptr(), xin.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                                  rstd.data_ptr(), _ptr(dx_add), dx.data_ptr(), dx_drop.data_ptr(),
+                                                  float(dropout[0]), dropout[1].data_ptr(), int(dropout[2]), rows, cols,
+                                                  _stream()), "vb_layernorm_bwd_dropout")
+        return dx, dx_drop
     check(_lib.lib().vb_layernorm_bwd(dy.data_ptr(), xin.data_ptr(), gamma.data_ptr(),
                                       mean.data_ptr(), rstd.data_ptr(), _ptr(dx_add), dx.data_ptr(),
                                       _ptr(dgamma), _ptr(dbeta), rows, cols, 0.0, _stream()),

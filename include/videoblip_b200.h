@@ -146,6 +146,14 @@ int vb_row_stats(const void* x, double* stats, int64_t rows, int64_t cols, int64
 int vb_layernorm_bwd(const void* dy, const void* xin, const float* gamma, const float* mean,
                      const float* rstd, const void* dx_add, void* dx, float* dgamma, float* dbeta,
                      int64_t rows, int64_t cols, float eps_unused, void* stream);
+/* The same dx plus a second output dx_drop = vb_dropout(dx, dropout_p, seed, salt) written in the same pass: the
+ * gradient that enters the dgrad GEMM of the linear layer in front of a residual dropout (HF:opt/modeling_opt.py
+ * :230, :246 — `dropout(hidden) + residual`; in the backward the residual stream's gradient feeds both the branch,
+ * through the mask, and the previous residual, unmasked).  Saves the separate dropout pass over the gradient. */
+int vb_layernorm_bwd_dropout(const void* dy, const void* xin, const float* gamma, const float* mean,
+                             const float* rstd, const void* dx_add, void* dx, void* dx_drop, float dropout_p,
+                             const uint64_t* dropout_seed, uint64_t dropout_salt, int64_t rows, int64_t cols,
+                             void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused softmax attention, FlashAttention-style (online softmax, fp32 accumulate).

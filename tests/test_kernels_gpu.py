@@ -813,6 +813,21 @@ def test_decode_cross_attention_over_dense_encoder_kv(splits):
     assert int(cnt.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("rows,cols", [(976, 2560), (37, 80), (5, 24)])
+def test_layernorm_backward_with_fused_dropout_output(rows, cols):
+    """vb_layernorm_bwd_dropout: dx as vb_layernorm_bwd gives it, and dropout(dx) as vb_dropout gives it."""
+    ops = _ops()
+    dy, x, add = _rand(rows, cols, seed=61), _rand(rows, cols, seed=62), _rand(rows, cols, seed=63)
+    gamma = 1.0 + 0.2 * torch.randn(cols, device="cuda")
+    beta = torch.zeros(cols, device="cuda")
+    _, mean, rstd = ops.layernorm(x, gamma, beta, 1e-5, save_stats=True)
+    seed = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    dx_ref = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx_add=add)
+    dx, dxm = ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx_add=add, dropout=(0.1, seed, 9))
+    assert torch.equal(dx, dx_ref)
+    assert torch.equal(dxm, ops.dropout(dx_ref, 0.1, seed, 9))
+
+
 def test_attention_tcgen05_per_element_path_in_a_subprocess():
     """Dropout on the probabilities and the T5 relative bias default to the mma.sync kernels (faster there); the
     tcgen05 flash kernels' per-element path for them stays covered: the same parity tests re-run with
