@@ -542,3 +542,77 @@ class DecodeGraph:
         self.tokens.copy_(tokens)
         self.graph.replay()
         return self.logits
+
+    # ---- greedy decoding with the token bookkeeping inside the graph -------------------------------------
+    # generate()'s greedy loop (HF GenerationMixin greedy search: EOS suppression below min_new_tokens, argmax,
+    # finished rows emit pad, stop when every row has emitted EOS) costs ~10 small torch launches and ~0.3 ms of
+    # host time per token when written as Python between graph replays.  Here one graph replay does a whole
+    # iteration: bookkeeping of the logits at hand -> next token -> decode step -> next logits; the position is
+    # a device counter, so nothing but the replay itself is issued per token.
+    def _greedy_bookkeeping(self) -> None:
+        b = self.tokens.shape[0]
+        scores = self.g_logits
+        if self.g_eos.numel() > 0:
+            blocked = torch.where(self.g_pos < self.g_min_new, float("-inf"), 0.0).to(scores.dtype)  # (1,)
+            scores = scores.index_add(1, self.g_eos, blocked.expand(b, self.g_eos.numel()))
+        nxt = scores.argmax(dim=-1)
+        nxt = torch.where(self.g_unfinished, nxt, self.g_pad.expand(b))
+        self.g_out.scatter_(1, self.g_pos.expand(b, 1), nxt[:, None])
+        if self.g_eos.numel() > 0:
+            self.g_unfinished.logical_and_(~(nxt[:, None] == self.g_eos[None, :]).any(dim=1))
+        self.g_alive.scatter_(0, self.g_pos, self.g_unfinished.sum(dtype=torch.int32)[None])
+        self.g_pos.add_(1)
+        self.tokens.copy_(nxt)
+
+    def greedy_begin(self, lm, cache: PackCache, state: dict, logits: torch.Tensor, max_new: int, min_new: int,
+                     eos_ids, pad_id: int) -> None:
+        """Arms the greedy graph with the prefill's logits.  (Re)captures when the capacity or the number of EOS
+        ids grew; the captured kernels point at the static tensors below."""
+        b, dev = self.tokens.shape[0], self.tokens.device
+        n_eos = len(eos_ids) if eos_ids else 0
+        cap = -(-max_new // 64) * 64
+        stale = (getattr(self, "g_graph", None) is None or self.g_out.shape[1] < max_new or self.g_eos.numel() != n_eos)
+        if stale:
+            self.g_logits = torch.empty_like(self.logits)
+            self.g_out = torch.empty((b, cap), dtype=torch.long, device=dev)
+            self.g_pos = torch.zeros(1, dtype=torch.long, device=dev)
+            self.g_min_new = torch.zeros(1, dtype=torch.long, device=dev)
+            self.g_unfinished = torch.ones(b, dtype=torch.bool, device=dev)
+            self.g_alive = torch.ones(cap, dtype=torch.int32, device=dev)
+            self.g_eos = torch.zeros(n_eos, dtype=torch.long, device=dev)
+            self.g_pad = torch.zeros(1, dtype=torch.long, device=dev)
+        self.g_logits.copy_(logits)
+        self.g_out.fill_(int(pad_id))
+        self.g_pos.zero_()
+        self.g_min_new.fill_(int(min_new))
+        self.g_unfinished.fill_(True)
+        self.g_alive.fill_(1)
+        self.g_pad.fill_(int(pad_id))
+        if n_eos:
+            self.g_eos.copy_(torch.tensor(list(eos_ids), dtype=torch.long, device=dev))
+        if stale:
+            snap = {k: state[k].clone() for k in ("n_valid", "ctx_len")}
+            keep = {k: getattr(self, k).clone() for k in ("g_logits", "g_out", "g_pos", "g_unfinished", "g_alive")}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up of the bookkeeping ops (allocator)
+                self._greedy_bookkeeping()
+            torch.cuda.current_stream().wait_stream(side)
+            for k, v in keep.items():
+                getattr(self, k).copy_(v)
+            self.g_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_graph):
+                self._greedy_bookkeeping()
+                self.g_logits.copy_(opt_decode_step(lm, cache, self.tokens, state))
+            for k, v in snap.items():  # capture does not execute; restore defensively anyway
+                state[k].copy_(v)
+            for k, v in keep.items():
+                getattr(self, k).copy_(v)
+
+    def greedy_iteration(self) -> None:
+        """Token of the current position -> g_out, then the decode step that produces the next logits."""
+        self.g_graph.replay()
+
+    def greedy_last(self) -> None:
+        """The last position: bookkeeping only (its token is never fed back)."""
+        self._greedy_bookkeeping()

@@ -314,12 +314,31 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
     # every `poll` steps, so the host keeps queueing decode steps instead of draining the stream
     # once per token.  Rows that finished emit pad_id, so the columns decoded past the stopping
     # step are cut off below and the returned ids equal the step-by-step loop's.
+    poll = int(kw.get("eos_poll_interval", 8))
+    if (dgraph is not None and isinstance(stepper, _OptStepper) and not do_sample and (not rep or rep == 1.0)
+            and stepper.start_token is None and bool(kw.get("device_bookkeeping", True))):
+        # plain greedy search on the decoder-only LM: the whole iteration (EOS suppression, argmax, pad for
+        # finished rows, the write into the output buffer, the alive count, the next decode step) is one graph
+        # replay with a device-side position counter (engine/opt.py::DecodeGraph.greedy_*)
+        lm = stepper.lm
+        dgraph.greedy_begin(lm, lm._pack, stepper.state, logits, max_new, min_new, eos_ids, int(pad_id))
+        n_done = max_new
+        for step in range(max_new):
+            if step + 1 < max_new:
+                dgraph.greedy_iteration()
+            else:
+                dgraph.greedy_last()
+            if eos_ids and step >= min_new - 1 and ((step + 1) % poll == 0 or step + 1 == max_new):
+                dead = (dgraph.g_alive[: step + 1] == 0).nonzero()
+                if dead.numel():  # one device -> host read per `poll` tokens
+                    n_done = int(dead[0]) + 1
+                    break
+        return finish(dgraph.g_out[:, :n_done].clone())
     out = torch.full((rows, max_new), int(pad_id), dtype=torch.long, device=dev)
     pad_t = torch.full((rows,), int(pad_id), dtype=torch.long, device=dev)
     unfinished = torch.ones(rows, dtype=torch.bool, device=dev)
     eos_t = torch.tensor(eos_ids, device=dev, dtype=torch.long) if eos_ids else None
     alive = torch.ones(max_new, dtype=torch.int32, device=dev) if eos_t is not None else None
-    poll = int(kw.get("eos_poll_interval", 8))
     n_done = max_new
     for step in range(max_new):
         scores = _process_logits(logits, out[:, :step], step, min_new_tokens=min_new, eos_ids=eos_ids,

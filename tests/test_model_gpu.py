@@ -733,3 +733,25 @@ def test_beam_search_and_repetition_penalty_match_reference_golden(name):
     _dump(f"beams/{name}", mismatches=bad, ties=ties)
     assert not bad, bad
     assert len(ties) <= 1, ties
+
+
+@pytest.mark.parametrize("kw", [dict(max_new_tokens=12), dict(max_new_tokens=16, min_new_tokens=16),
+                                dict(max_new_tokens=24, min_new_tokens=3), dict(max_new_tokens=9, min_new_tokens=0)])
+def test_greedy_generate_with_device_side_bookkeeping_equals_the_python_loop(kw):
+    """generate()'s plain greedy search runs its token bookkeeping inside the decode graph
+    (DecodeGraph.greedy_*); the ids must equal the Python loop's (device_bookkeeping=False) — including the EOS
+    stop, the pad fill of finished rows and min_new_tokens — and a second call must reuse the captured graph."""
+    fx, cfg = load("small_opt")
+    m = build(cfg, fx["state_dict"])
+    gi = cuda(fx["gen_inputs"])
+    want = m.generate(**gi, device_bookkeeping=False, **kw)
+    got = m.generate(**gi, **kw)
+    assert torch.equal(got, want), (got.tolist(), want.tolist())
+    again = m.generate(**gi, **kw)
+    assert torch.equal(again, want)
+    # an EOS that is certain to appear: the most frequent generated token
+    eos = int(want.flatten().mode().values)
+    want_e = m.generate(**gi, device_bookkeeping=False, eos_token_id=eos, **kw)
+    got_e = m.generate(**gi, eos_token_id=eos, **kw)
+    assert torch.equal(got_e, want_e), (got_e.tolist(), want_e.tolist())
+
