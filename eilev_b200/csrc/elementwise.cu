@@ -189,45 +189,72 @@ cudaError_t cls_rows_launch(const void* cls, const void* pos, void* hidden, long
 }
 
 // ------------------------------------------------------------------ LM input assembly
+// Exclusive prefix sum of one int per thread over a 1024-thread block (warp shuffles + one shared-memory hop);
+// `total` = the block-wide sum.  All threads must call it.
+VB_DEVICE int block_scan_1024(int v, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += n;
+  }
+  __syncthreads();  // warp_sums may still be read by a previous call
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += n;
+    }
+    warp_sums[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  total = warp_sums[31];
+  return inc - v + (warp > 0 ? warp_sums[warp - 1] : 0);
+}
+
 // Single block: slot_index = exclusive rank among masked positions (row-major over
-// (batch, seq), the order of a boolean-mask assignment), pos_ids = OPT positions.
+// (batch, seq), the order of a boolean-mask assignment), pos_ids = OPT positions (cumsum(mask) * mask - 1 +
+// offset per batch row).  Both are block-wide scans over contiguous per-thread chunks (round 1 walked each batch
+// row with ONE thread: 88 us at batch 1).
 __global__ void __launch_bounds__(1024)
 splice_index_kernel(const long long* attn, const long long* vmask, int* slot_index, int* pos_ids,
                     int* status, long long batch, long long seq, long long pos_offset,
                     long long n_features) {
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
-  __shared__ int partial[1024];
+  __shared__ int warp_sums[32];
   const long long n = batch * seq;
   const int tid = threadIdx.x;
-  const long long chunk = (n + 1023) / 1024;
-  const long long lo = tid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
-  int cnt = 0;
-  if (vmask != nullptr)
-    for (long long i = lo; i < hi; ++i) cnt += vmask[i] != 0;
-  partial[tid] = cnt;
-  __syncthreads();
-  // inclusive Hillis-Steele scan
-  for (int off = 1; off < 1024; off <<= 1) {
-    int v = tid >= off ? partial[tid - off] : 0;
-    __syncthreads();
-    partial[tid] += v;
-    __syncthreads();
+  {
+    const long long chunk = (n + 1023) / 1024;
+    const long long lo = tid * chunk < n ? tid * chunk : n, hi = (lo + chunk < n) ? lo + chunk : n;
+    int cnt = 0;
+    if (vmask != nullptr)
+      for (long long i = lo; i < hi; ++i) cnt += vmask[i] != 0;
+    int total = 0;
+    int base = block_scan_1024(cnt, warp_sums, total);
+    for (long long i = lo; i < hi; ++i) {
+      if (vmask != nullptr && vmask[i] != 0) slot_index[i] = base++;
+      else slot_index[i] = -1;
+    }
+    if (tid == 0 && status != nullptr) {
+      status[0] = (vmask != nullptr && total != n_features) ? 1 : 0;
+      status[1] = total;
+    }
   }
-  int base = partial[tid] - cnt;
-  for (long long i = lo; i < hi; ++i) {
-    if (vmask != nullptr && vmask[i] != 0) slot_index[i] = base++;
-    else slot_index[i] = -1;
-  }
-  if (tid == 1023 && status != nullptr) {
-    const int total = partial[1023];
-    status[0] = (vmask != nullptr && total != n_features) ? 1 : 0;
-    status[1] = total;
-  }
-  // positions: one thread per batch row
-  for (long long b = tid; b < batch; b += 1024) {
-    long long run = 0;
-    for (long long l = 0; l < seq; ++l) {
+  // positions: a block-wide scan per batch row
+  const long long chunk = (seq + 1023) / 1024;
+  for (long long b = 0; b < batch; ++b) {
+    const long long lo = tid * chunk < seq ? tid * chunk : seq, hi = (lo + chunk < seq) ? lo + chunk : seq;
+    int cnt = 0;
+    for (long long l = lo; l < hi; ++l) cnt += attn != nullptr ? (attn[b * seq + l] != 0) : 1;
+    int total = 0;
+    long long run = block_scan_1024(cnt, warp_sums, total);
+    for (long long l = lo; l < hi; ++l) {
       const long long m = attn != nullptr ? (attn[b * seq + l] != 0) : 1;
       run += m;
       pos_ids[b * seq + l] = static_cast<int>(run * m - 1 + pos_offset);

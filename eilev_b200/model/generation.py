@@ -303,8 +303,15 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
                           tokens], dim=1)
 
     if num_beams > 1:
+        # the decode step of the beam rows as one CUDA graph (the reorder between steps permutes the state's page
+        # tables / counters in place, which is what the captured kernels read)
+        beam_rows = b * num_beams
+        graph_ok = bool(kw.get("use_cuda_graph", max_new >= 8)) and max_new > 1 and (
+            beam_rows <= MAX_DECODE_ROWS or isinstance(stepper, _GroupedStepper))
+        bgraph = stepper.graph(beam_rows, dev) if graph_ok else None
         return finish(_beam_search(stepper, logits, b, num_beams, max_new, min_new, eos_ids, pad_id, rep,
-                                   length_penalty, early_stopping, do_sample, temperature, top_k, top_p))
+                                   length_penalty, early_stopping, do_sample, temperature, top_k, top_p,
+                                   graph=bgraph))
 
     rows = input_ids.shape[0]
     use_graph = bool(kw.get("use_cuda_graph", max_new >= 8)) and (rows <= MAX_DECODE_ROWS or isinstance(stepper, _GroupedStepper))
@@ -364,7 +371,7 @@ def generate(model, input_ids, attention_mask, video_mask, video_features, **kw)
 
 
 def _beam_search(stepper, logits, batch, nb, max_new, min_new, eos_ids, pad_id, rep,
-                 length_penalty, early_stopping, do_sample, temperature, top_k, top_p):
+                 length_penalty, early_stopping, do_sample, temperature, top_k, top_p, graph=None):
     """Standard beam search with HF's scoring: hypotheses are ranked by
     sum_logprobs / generated_len**length_penalty (BeamHypotheses.add)."""
     dev = logits.device
@@ -439,7 +446,7 @@ def _beam_search(stepper, logits, batch, nb, max_new, min_new, eos_ids, pad_id, 
         if all(done) or step + 1 == max_new:
             break
         stepper.reorder(src)
-        logits = stepper.step(next_tokens.view(-1))
+        logits = (graph if graph is not None else stepper).step(next_tokens.view(-1))
 
     out = []
     for i in range(batch):

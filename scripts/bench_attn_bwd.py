@@ -25,7 +25,7 @@ def timeit(fn, iters=10):
     return min(ts)
 
 
-def case(name, b, heads, d, sq, skv, causal):
+def case(name, b, heads, d, sq, skv, causal, drop=False):
     hd = heads * d
     g = torch.Generator(device="cuda").manual_seed(0)
     q = torch.randn(b, sq, hd, device="cuda", generator=g).to(torch.bfloat16)
@@ -33,10 +33,11 @@ def case(name, b, heads, d, sq, skv, causal):
     v = torch.randn(b, skv, hd, device="cuda", generator=g).to(torch.bfloat16)
     d_o = torch.randn(b, sq, hd, device="cuda", generator=g).to(torch.bfloat16)
     scale = d ** -0.5
-    o, lse = ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True)
-    t_f = timeit(lambda: ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True))
-    t_b = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal))
-    tc = ops.attention_bwd_uses_tcgen05(q, k, v, o, lse, d_o, heads, scale, causal=causal)
+    dr = (0.1, torch.tensor([7], dtype=torch.int64, device="cuda"), 3) if drop else None
+    o, lse = ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=dr)
+    t_f = timeit(lambda: ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=dr))
+    t_b = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=dr))
+    tc = ops.attention_bwd_uses_tcgen05(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=dr)
     kind = ops.attention_kernel(q, k, v, heads, causal=causal, need_lse=True)
     print(f"{name}: fwd {t_f * 1e3:.1f} us ({kind}), bwd (delta + kernels) {t_b * 1e3:.1f} us, tcgen05 bwd = {tc}", flush=True)
 
@@ -46,3 +47,7 @@ case("opt self-attention 976 x 976 causal", 1, 32, 80, 976, 976, True)
 case("q-former cross-attention 32 x 2056", 17, 12, 64, 32, 2056, False)
 case("q-former self-attention 32 x 32", 17, 12, 64, 32, 32, False)
 case("t5 encoder 976 x 976", 1, 32, 64, 976, 976, False)
+case("q-former cross-attention 32 x 2056, dropout 0.1", 17, 12, 64, 32, 2056, False, drop=True)
+case("q-former self-attention 32 x 32, dropout 0.1", 17, 12, 64, 32, 32, False, drop=True)
+case("t5 encoder 976 x 976, dropout 0.1", 1, 32, 64, 976, 976, False, drop=True)
+

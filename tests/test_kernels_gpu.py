@@ -430,6 +430,26 @@ def test_embed_splice_and_bwd():
     assert st2.tolist()[0] == 1
 
 
+@pytest.mark.parametrize("b,l", [(1, 976), (3, 1500), (5, 2049), (2, 7)])
+def test_embed_splice_indices_at_sequence_lengths_beyond_one_chunk(b, l):
+    """slot indices (rank among the masked positions, row-major) and OPT positions (cumsum(mask) * mask - 1 + 2)
+    from the block-wide scans, on random masks with left padding."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(l)
+    dim, vocab = 16, 40
+    ids = torch.randint(0, vocab, (b, l), device="cuda", generator=g)
+    attn = (torch.rand(b, l, device="cuda", generator=g) > 0.1).long()
+    attn[0, : l // 7] = 0
+    vmask = ((torch.rand(b, l, device="cuda", generator=g) > 0.6) & (attn == 1)).long()
+    nfeat = int(vmask.sum())
+    emb, feats, ptab = _rand(vocab, dim, seed=1), _rand(max(nfeat, 1), dim, seed=2), _rand(l + 2, dim, seed=3)
+    e, h, slot, pos, status = ops.embed_splice(ids, attn, vmask, emb, feats, ptab, 2)
+    assert status.tolist() == [0, nfeat]
+    want_slot = torch.where(vmask.bool().flatten(), torch.cumsum(vmask.flatten(), 0) - 1, torch.full((b * l,), -1, device="cuda"))
+    assert torch.equal(slot.flatten().long(), want_slot)
+    assert torch.equal(pos.view(b, l).long(), torch.cumsum(attn, 1) * attn - 1 + 2)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_cross_entropy(dtype):
     ops = _ops()
