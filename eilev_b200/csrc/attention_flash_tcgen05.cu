@@ -126,6 +126,20 @@ VB_DEVICE void fa_unit_coords(const FaParams& p, int unit, int& b, int& h, int& 
   }
 }
 
+// Named barrier over `threads` threads that also ANDs a predicate across them
+VB_DEVICE bool named_bar_and(uint32_t id, uint32_t threads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %3, 0;\n\t"
+      "barrier.cta.red.and.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(r)
+      : "r"(id), "r"(threads), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return r != 0;
+}
+
 // (neg, delta) of two neighbouring columns from the per-column table in shared memory
 VB_DEVICE float4 fa_col_pair(uint32_t smem_addr) {
   float4 v;
@@ -452,10 +466,11 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
           const int col_g0 = blk * kFaSub;
           // ---- per-column terms -> shared memory (the group's first 64 threads, one column each).  Key columns
           // carry a term only when some key of the tile is masked or out of range.
-          const bool cols_plain = kRowsAreKeys ? false : (km == nullptr && valid == kFaSub);
+          bool cols_plain = kRowsAreKeys ? false : (km == nullptr && valid == kFaSub);
           if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 100 + sweep * n_blk + kb);
           float2* col = sCol + (grp * 2 + (tt & 1)) * kFaSub;
           if (!cols_plain) {
+            bool all_valid = true;
             if (r_in < kFaSub) {
               const int cg = col_g0 + r_in;
               float2 v = make_float2(INFINITY, 0.0f);
@@ -469,8 +484,12 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
                 if (cg < p.skv && (km == nullptr || km[cg] != 0)) v.x = 0.0f;
               }
               col[r_in] = v;
+              all_valid = v.x == 0.0f;
             }
-            named_bar_sync(1 + grp, 128);
+            // the barrier also tells whether any key of the block is masked at all: a key-padding mask that is all
+            // ones over this block (the common case away from the padded end) takes the term-free variants
+            all_valid = named_bar_and(1 + grp, 128, all_valid);
+            if (!kRowsAreKeys && all_valid && valid == kFaSub) cols_plain = true;
           }
           ++tt;
           // causal: is every (row, column) pair of this half visible?

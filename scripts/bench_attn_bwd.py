@@ -25,7 +25,7 @@ def timeit(fn, iters=10):
     return min(ts)
 
 
-def case(name, b, heads, d, sq, skv, causal, drop=False):
+def case(name, b, heads, d, sq, skv, causal, drop=False, mask=False):
     hd = heads * d
     g = torch.Generator(device="cuda").manual_seed(0)
     q = torch.randn(b, sq, hd, device="cuda", generator=g).to(torch.bfloat16)
@@ -34,10 +34,14 @@ def case(name, b, heads, d, sq, skv, causal, drop=False):
     d_o = torch.randn(b, sq, hd, device="cuda", generator=g).to(torch.bfloat16)
     scale = d ** -0.5
     dr = (0.1, torch.tensor([7], dtype=torch.int64, device="cuda"), 3) if drop else None
-    o, lse = ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=dr)
-    t_f = timeit(lambda: ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=dr))
-    t_b = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=dr))
-    tc = ops.attention_bwd_uses_tcgen05(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=dr)
+    km = None
+    if mask:  # a key-padding mask as the collator makes it: a few padded positions, the rest ones
+        km = torch.ones(b, skv, dtype=torch.uint8, device="cuda")
+        km[:, :6] = 0
+    o, lse = ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=dr, key_mask=km)
+    t_f = timeit(lambda: ops.attention(q, k, v, heads, scale, causal=causal, need_lse=True, dropout=dr, key_mask=km))
+    t_b = timeit(lambda: ops.attention_bwd(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=dr, key_mask=km))
+    tc = ops.attention_bwd_uses_tcgen05(q, k, v, o, lse, d_o, heads, scale, causal=causal, dropout=dr, key_mask=km)
     kind = ops.attention_kernel(q, k, v, heads, causal=causal, need_lse=True)
     print(f"{name}: fwd {t_f * 1e3:.1f} us ({kind}), bwd (delta + kernels) {t_b * 1e3:.1f} us, tcgen05 bwd = {tc}", flush=True)
 
@@ -47,6 +51,7 @@ case("opt self-attention 976 x 976 causal", 1, 32, 80, 976, 976, True)
 case("q-former cross-attention 32 x 2056", 17, 12, 64, 32, 2056, False)
 case("q-former self-attention 32 x 32", 17, 12, 64, 32, 32, False)
 case("t5 encoder 976 x 976", 1, 32, 64, 976, 976, False)
+case("opt self-attention 976 x 976 causal, key-padding mask", 1, 32, 80, 976, 976, True, mask=True)
 case("q-former cross-attention 32 x 2056, dropout 0.1", 17, 12, 64, 32, 2056, False, drop=True)
 case("q-former self-attention 32 x 32, dropout 0.1", 17, 12, 64, 32, 32, False, drop=True)
 case("t5 encoder 976 x 976, dropout 0.1", 1, 32, 64, 976, 976, False, drop=True)
