@@ -147,12 +147,23 @@ VB_DEVICE float4 fa_col_pair(uint32_t smem_addr) {
   return v;
 }
 
+// Dropout on the probabilities / T5 relative bias of one 32-column chunk of one row: column j hashes index
+// idx0 + j * idx_step and reads bias rb[clamp(rb0 + j * rb_step)] (the bias depends on key - query only)
+struct FaExtra {
+  uint64_t seed, idx0;
+  long long idx_step;
+  uint32_t thresh;
+  float scale;
+  const float* rb;
+  int rb0, rb_step, rb_lo, rb_hi;
+};
+
 // 32 columns of one row, no per-element masks: P = exp2(T1 * c - neg), dS = P * (T2 - delta), packed to bf16
 // pairs.  neg / delta = the row's term plus (COL_TERMS) the column's, or (!ROW_TERMS) the column's alone.
 // Straight-line code: the variants are chosen once per item, outside the unrolled loop.
-template <bool HAS_P, bool HAS_DS, bool COL_TERMS, bool ROW_TERMS>
+template <bool HAS_P, bool HAS_DS, bool COL_TERMS, bool ROW_TERMS, bool DROP = false, bool BIAS = false>
 VB_DEVICE void fa_chunk_plain(const uint32_t (&t1)[32], const uint32_t (&t2)[32], uint32_t (&u1)[16], uint32_t (&u2)[16],
-                              float c, float neg_row, float d_row, uint32_t col_addr) {
+                              float c, float neg_row, float d_row, uint32_t col_addr, const FaExtra& x = FaExtra()) {
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     float na = neg_row, nb = neg_row, da = d_row, db = d_row;
@@ -164,10 +175,26 @@ VB_DEVICE void fa_chunk_plain(const uint32_t (&t1)[32], const uint32_t (&t2)[32]
         na = cc.x; nb = cc.z; da = cc.y; db = cc.w;
       }
     }
+    if (BIAS) {  // exponent = T1 * c + bias * log2(e) - neg; an infinite neg still wins
+      const int ia = min(max(x.rb0 + j * x.rb_step, x.rb_lo), x.rb_hi);
+      const int ib = min(max(x.rb0 + (j + 1) * x.rb_step, x.rb_lo), x.rb_hi);
+      na = fmaf(-__ldg(x.rb + ia), kFaLog2e, na);
+      nb = fmaf(-__ldg(x.rb + ib), kFaLog2e, nb);
+    }
     const float pa = exp2f(fmaf(__uint_as_float(t1[j]), c, -na));
     const float pb = exp2f(fmaf(__uint_as_float(t1[j + 1]), c, -nb));
-    if (HAS_P) u1[j >> 1] = pack_bf16x2(pa, pb);
-    if (HAS_DS) u2[j >> 1] = pack_bf16x2(pa * (__uint_as_float(t2[j]) - da), pb * (__uint_as_float(t2[j + 1]) - db));
+    float ua = pa, ub = pb;                                                   // P that multiplies V / dO
+    float ga = HAS_DS ? __uint_as_float(t2[j]) : 0.0f, gb = HAS_DS ? __uint_as_float(t2[j + 1]) : 0.0f;  // dP
+    if (DROP) {  // the forward's mask, regenerated: dropped probabilities pass no value and no gradient
+      const bool ka = dropout_keep(x.seed, x.idx0 + static_cast<uint64_t>(j * x.idx_step), x.thresh);
+      const bool kb = dropout_keep(x.seed, x.idx0 + static_cast<uint64_t>((j + 1) * x.idx_step), x.thresh);
+      ua = ka ? pa * x.scale : 0.0f;
+      ub = kb ? pb * x.scale : 0.0f;
+      ga = ka ? ga * x.scale : 0.0f;
+      gb = kb ? gb * x.scale : 0.0f;
+    }
+    if (HAS_P) u1[j >> 1] = pack_bf16x2(ua, ub);
+    if (HAS_DS) u2[j >> 1] = pack_bf16x2(pa * (ga - da), pb * (gb - db));
   }
 }
 
@@ -195,14 +222,23 @@ VB_DEVICE void fa_stats_plain(const uint32_t (&t1)[32], float c, float& run_m, f
 }
 
 // The same with a per-column term (+inf for a masked / out-of-range key: the column drops out of both reductions)
-VB_DEVICE void fa_stats_cols(const uint32_t (&t1)[32], float c, uint32_t col_addr, float& run_m, float& run_l) {
+template <bool BIAS = false>
+VB_DEVICE void fa_stats_cols(const uint32_t (&t1)[32], float c, uint32_t col_addr, float& run_m, float& run_l,
+                             const FaExtra& e = FaExtra()) {
   float x[32];
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
     const float4 cc = fa_col_pair(col_addr + 8 * j);
-    x[j] = fmaf(__uint_as_float(t1[j]), c, -cc.x);
-    x[j + 1] = fmaf(__uint_as_float(t1[j + 1]), c, -cc.z);
+    float na = cc.x, nb = cc.z;
+    if (BIAS) {
+      const int ia = min(max(e.rb0 + j * e.rb_step, e.rb_lo), e.rb_hi);
+      const int ib = min(max(e.rb0 + (j + 1) * e.rb_step, e.rb_lo), e.rb_hi);
+      na = fmaf(-__ldg(e.rb + ia), kFaLog2e, na);
+      nb = fmaf(-__ldg(e.rb + ib), kFaLog2e, nb);
+    }
+    x[j] = fmaf(__uint_as_float(t1[j]), c, -na);
+    x[j + 1] = fmaf(__uint_as_float(t1[j + 1]), c, -nb);
     m0 = fmaxf(m0, x[j]);
     m1 = fmaxf(m1, x[j + 1]);
   }
@@ -429,7 +465,8 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_slot = t_row + static_cast<uint32_t>(128 * grp);
     const int off = p.skv - p.sq;
-    const bool slow_always = p.drop_thresh != 0u || p.rel_bias != nullptr;
+    const bool has_drop = p.drop_thresh != 0u, has_bias = p.rel_bias != nullptr;
+    const bool extras = has_drop || has_bias;  // handled by the branch-free variants, with the column terms on
     uint32_t t_ph = 0, acc_ph = 0;
     int tt = 0;  // items this group has worked on (per-column buffer = tt & 1)
     for (int n = 0; n * static_cast<int>(gridDim.x) < units; ++n) {
@@ -466,7 +503,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
           const int col_g0 = blk * kFaSub;
           // ---- per-column terms -> shared memory (the group's first 64 threads, one column each).  Key columns
           // carry a term only when some key of the tile is masked or out of range.
-          bool cols_plain = kRowsAreKeys ? false : (km == nullptr && valid == kFaSub);
+          bool cols_plain = (kRowsAreKeys || extras) ? false : (km == nullptr && valid == kFaSub);
           if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 100 + sweep * n_blk + kb);
           float2* col = sCol + (grp * 2 + (tt & 1)) * kFaSub;
           if (!cols_plain) {
@@ -489,11 +526,11 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             // the barrier also tells whether any key of the block is masked at all: a key-padding mask that is all
             // ones over this block (the common case away from the padded end) takes the term-free variants
             all_valid = named_bar_and(1 + grp, 128, all_valid);
-            if (!kRowsAreKeys && all_valid && valid == kFaSub) cols_plain = true;
+            if (!kRowsAreKeys && !extras && all_valid && valid == kFaSub) cols_plain = true;
           }
           ++tt;
           // causal: is every (row, column) pair of this half visible?
-          bool slow = slow_always;
+          bool slow = false;  // per-element path: causal-diagonal items only
           if (p.causal) {
             const int key_max = kRowsAreKeys ? rt * kFaEdge + kFaEdge - 1 : col_g0 + kFaSub - 1;
             const int q_min = kRowsAreKeys ? col_g0 : rt * kFaEdge;
@@ -513,11 +550,35 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             tmem_ld_32(t_slot + col0, t1);
             if constexpr (kHasT2) tmem_ld_32(t_slot + 64 + col0, t2);
             tmem_ld_wait();
+            // dropout index / bias index of this chunk's first column (see FaExtra)
+            FaExtra ex;
+            if (extras) {
+              const uint64_t bh = static_cast<uint64_t>(b) * p.heads + h;
+              const int c_first = col_g0 + col0;
+              ex.seed = has_drop ? *p.drop_seed + p.drop_salt : 0ull;
+              ex.thresh = p.drop_thresh;
+              ex.scale = p.drop_scale;
+              if (kRowsAreKeys) {  // row = key, columns = queries
+                ex.idx0 = (bh * p.sq + c_first) * p.skv + row_g;
+                ex.idx_step = p.skv;
+                ex.rb0 = row_g - c_first;
+                ex.rb_step = -1;
+              } else {             // row = query, columns = keys
+                ex.idx0 = (bh * p.sq + row_g) * p.skv + c_first;
+                ex.idx_step = 1;
+                ex.rb0 = c_first - row_g;
+                ex.rb_step = 1;
+              }
+              ex.rb = rb;
+              ex.rb_lo = -(p.sq - 1);
+              ex.rb_hi = p.skv - 1;
+            }
             if (MODE == kFwd && sweep == 0) {
               // ---- statistics sweep: running row maximum / sum of this half's columns
               if (!slow && valid == kFaSub) {  // (a ragged item reads TMEM columns no instruction wrote: general path)
                 if (cols_plain) fa_stats_plain(t1, p.scale_log2, run_m, run_l);
-                else fa_stats_cols(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l);
+                else if (has_bias) fa_stats_cols<true>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l, ex);
+                else fa_stats_cols<false>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l);
                 continue;
               }
               float cmax = -INFINITY;
@@ -548,7 +609,13 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             uint32_t u1[16], u2[16];
             if (!slow) {
               const uint32_t col_addr = smem_u32(col + col0);
-              if (cols_plain)
+              if (has_drop && has_bias)
+                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true, true, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr, ex);
+              else if (has_drop)
+                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true, true, false>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr, ex);
+              else if (has_bias)
+                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true, false, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr, ex);
+              else if (cols_plain)
                 fa_chunk_plain<kHasAcc1, kHasAcc2, false, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
               else if (rows_plain)
                 fa_chunk_plain<kHasAcc1, kHasAcc2, true, false>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
@@ -686,12 +753,11 @@ static bool fa_enabled(const char* env) {
 
 static bool fa_layout_ok(const vb_attn_args& f) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  // Dropout on the probabilities and the T5 relative bias run the per-element path in every item, where the
-  // mma.sync kernels are faster (flan-t5-xl step 112.0 vs 115.6 ms, profiles/r02_attn_flash.txt).  VB_ATTN_TC_SLOW=1
-  // sends them through the tcgen05 kernels anyway (parity tests of that path).
+  // Dropout on the probabilities and the T5 relative bias: branch-free variants of the elementwise code
+  // (fa_chunk_plain<.., DROP, BIAS>).  VB_ATTN_TC_SLOW=0 sends those calls to the mma.sync kernels (A/B).
   static const bool slow_ok = [] {
     const char* e = std::getenv("VB_ATTN_TC_SLOW");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr || e[0] != '0';
   }();
   if (!slow_ok && (f.rel_bias != nullptr || (f.dropout_p > 0.0f && f.dropout_seed != nullptr))) return false;
   if (f.d % 16 != 0 || f.d < 16 || f.d > 128) return false;

@@ -848,15 +848,15 @@ def test_layernorm_backward_with_fused_dropout_output(rows, cols):
     assert torch.equal(dxm, ops.dropout(dx_ref, 0.1, seed, 9))
 
 
-def test_attention_tcgen05_per_element_path_in_a_subprocess():
-    """Dropout on the probabilities and the T5 relative bias default to the mma.sync kernels (faster there); the
-    tcgen05 flash kernels' per-element path for them stays covered: the same parity tests re-run with
-    VB_ATTN_TC_SLOW=1 (the switch is read once per process)."""
+def test_attention_dropout_and_bias_on_the_other_kernels_in_a_subprocess():
+    """Dropout on the probabilities and the T5 relative bias run on the tcgen05 flash kernels by default (the tests
+    above); VB_ATTN_TC_SLOW=0 routes them to the mma.sync kernels, which stay covered by re-running the same parity
+    tests with the switch (it is read once per process)."""
     import subprocess
     import sys
-    if os.environ.get("VB_ATTN_TC_SLOW") == "1":
+    if os.environ.get("VB_ATTN_TC_SLOW") == "0":
         pytest.skip("already the forced run")
-    env = dict(os.environ, VB_ATTN_TC_SLOW="1")
+    env = dict(os.environ, VB_ATTN_TC_SLOW="0")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k",
                         "attention_dropout_fwd_bwd or attention_relative_bias_fwd_bwd"],
                        env=env, capture_output=True, text=True, timeout=600)
