@@ -34,7 +34,9 @@
 //
 // Masks are folded into the exponent: exponent = T1 * c - (row term + column term) where an invalid key (beyond
 // Skv, key-padding mask) or an invalid / fully masked query (beyond Sq, lse = -inf) contributes +inf, so P = 0
-// exactly; only causal-diagonal tiles, dropout and the T5 relative bias take the per-element path.
+// exactly.  Causal-diagonal items, dropout on the probabilities and the T5 relative bias are compile-time variants
+// of the same straight-line loop (fa_chunk_plain<.., DROP, BIAS, CAUSAL>): per-element branches made the ptxas
+// output three times slower.
 // Reference ops: HF OPTAttention / Blip2QFormerMultiHeadAttention / T5Attention forward and autograd backward of
 // softmax(Q K^T * scale + mask) V, reached from eilev/model/v2.py:132-252 through language_model / qformer.
 #include <cstdlib>
@@ -156,12 +158,14 @@ struct FaExtra {
   float scale;
   const float* rb;
   int rb0, rb_step, rb_lo, rb_hi;
+  int vis_lo, vis_hi;   // causal items: column j of the chunk is visible iff vis_lo <= j <= vis_hi
 };
 
 // 32 columns of one row, no per-element masks: P = exp2(T1 * c - neg), dS = P * (T2 - delta), packed to bf16
 // pairs.  neg / delta = the row's term plus (COL_TERMS) the column's, or (!ROW_TERMS) the column's alone.
 // Straight-line code: the variants are chosen once per item, outside the unrolled loop.
-template <bool HAS_P, bool HAS_DS, bool COL_TERMS, bool ROW_TERMS, bool DROP = false, bool BIAS = false>
+template <bool HAS_P, bool HAS_DS, bool COL_TERMS, bool ROW_TERMS, bool DROP = false, bool BIAS = false,
+          bool CAUSAL = false>
 VB_DEVICE void fa_chunk_plain(const uint32_t (&t1)[32], const uint32_t (&t2)[32], uint32_t (&u1)[16], uint32_t (&u2)[16],
                               float c, float neg_row, float d_row, uint32_t col_addr, const FaExtra& x = FaExtra()) {
 #pragma unroll
@@ -181,6 +185,10 @@ VB_DEVICE void fa_chunk_plain(const uint32_t (&t1)[32], const uint32_t (&t2)[32]
       na = fmaf(-__ldg(x.rb + ia), kFaLog2e, na);
       nb = fmaf(-__ldg(x.rb + ib), kFaLog2e, nb);
     }
+    if (CAUSAL) {  // an invisible pair gets an infinite neg: P = 0, dS = 0
+      na = (j >= x.vis_lo && j <= x.vis_hi) ? na : INFINITY;
+      nb = (j + 1 >= x.vis_lo && j + 1 <= x.vis_hi) ? nb : INFINITY;
+    }
     const float pa = exp2f(fmaf(__uint_as_float(t1[j]), c, -na));
     const float pb = exp2f(fmaf(__uint_as_float(t1[j + 1]), c, -nb));
     float ua = pa, ub = pb;                                                   // P that multiplies V / dO
@@ -196,6 +204,22 @@ VB_DEVICE void fa_chunk_plain(const uint32_t (&t1)[32], const uint32_t (&t2)[32]
     if (HAS_P) u1[j >> 1] = pack_bf16x2(ua, ub);
     if (HAS_DS) u2[j >> 1] = pack_bf16x2(pa * (ga - da), pb * (gb - db));
   }
+}
+
+// All variants with the column and row terms on: chosen by three run-time flags of the item
+template <bool HAS_P, bool HAS_DS>
+VB_DEVICE void fa_chunk_extras(bool causal, bool drop, bool bias, const uint32_t (&t1)[32], const uint32_t (&t2)[32],
+                               uint32_t (&u1)[16], uint32_t (&u2)[16], float c, float neg_row, float d_row,
+                               uint32_t col_addr, const FaExtra& x) {
+#define VB_FA_CALL(D, B, C) fa_chunk_plain<HAS_P, HAS_DS, true, true, D, B, C>(t1, t2, u1, u2, c, neg_row, d_row, col_addr, x)
+  if (causal) {
+    if (drop) { if (bias) VB_FA_CALL(true, true, true); else VB_FA_CALL(true, false, true); }
+    else { if (bias) VB_FA_CALL(false, true, true); else VB_FA_CALL(false, false, true); }
+  } else {
+    if (drop) { if (bias) VB_FA_CALL(true, true, false); else VB_FA_CALL(true, false, false); }
+    else { if (bias) VB_FA_CALL(false, true, false); else VB_FA_CALL(false, false, false); }
+  }
+#undef VB_FA_CALL
 }
 
 // Forward statistics of 32 unmasked columns: running maximum (log2 units) and sum, four independent chains
@@ -222,7 +246,7 @@ VB_DEVICE void fa_stats_plain(const uint32_t (&t1)[32], float c, float& run_m, f
 }
 
 // The same with a per-column term (+inf for a masked / out-of-range key: the column drops out of both reductions)
-template <bool BIAS = false>
+template <bool BIAS = false, bool CAUSAL = false>
 VB_DEVICE void fa_stats_cols(const uint32_t (&t1)[32], float c, uint32_t col_addr, float& run_m, float& run_l,
                              const FaExtra& e = FaExtra()) {
   float x[32];
@@ -236,6 +260,10 @@ VB_DEVICE void fa_stats_cols(const uint32_t (&t1)[32], float c, uint32_t col_add
       const int ib = min(max(e.rb0 + (j + 1) * e.rb_step, e.rb_lo), e.rb_hi);
       na = fmaf(-__ldg(e.rb + ia), kFaLog2e, na);
       nb = fmaf(-__ldg(e.rb + ib), kFaLog2e, nb);
+    }
+    if (CAUSAL) {
+      na = (j >= e.vis_lo && j <= e.vis_hi) ? na : INFINITY;
+      nb = (j + 1 >= e.vis_lo && j + 1 <= e.vis_hi) ? nb : INFINITY;
     }
     x[j] = fmaf(__uint_as_float(t1[j]), c, -na);
     x[j + 1] = fmaf(__uint_as_float(t1[j + 1]), c, -nb);
@@ -503,7 +531,16 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
           const int col_g0 = blk * kFaSub;
           // ---- per-column terms -> shared memory (the group's first 64 threads, one column each).  Key columns
           // carry a term only when some key of the tile is masked or out of range.
-          bool cols_plain = (kRowsAreKeys || extras) ? false : (km == nullptr && valid == kFaSub);
+          // causal: does the diagonal cut through this item?  (then the branch-free causal variants run, with the
+          // column terms on)
+          bool diag = false;
+          if (p.causal) {
+            const int key_max = kRowsAreKeys ? rt * kFaEdge + kFaEdge - 1 : col_g0 + kFaSub - 1;
+            const int q_min = kRowsAreKeys ? col_g0 : rt * kFaEdge;
+            diag = key_max > q_min + off;
+          }
+          const bool item_extras = extras || diag;
+          bool cols_plain = (kRowsAreKeys || item_extras) ? false : (km == nullptr && valid == kFaSub);
           if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 100 + sweep * n_blk + kb);
           float2* col = sCol + (grp * 2 + (tt & 1)) * kFaSub;
           if (!cols_plain) {
@@ -526,16 +563,10 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             // the barrier also tells whether any key of the block is masked at all: a key-padding mask that is all
             // ones over this block (the common case away from the padded end) takes the term-free variants
             all_valid = named_bar_and(1 + grp, 128, all_valid);
-            if (!kRowsAreKeys && !extras && all_valid && valid == kFaSub) cols_plain = true;
+            if (!kRowsAreKeys && !item_extras && all_valid && valid == kFaSub) cols_plain = true;
           }
           ++tt;
           // causal: is every (row, column) pair of this half visible?
-          bool slow = false;  // per-element path: causal-diagonal items only
-          if (p.causal) {
-            const int key_max = kRowsAreKeys ? rt * kFaEdge + kFaEdge - 1 : col_g0 + kFaSub - 1;
-            const int q_min = kRowsAreKeys ? col_g0 : rt * kFaEdge;
-            slow = slow || key_max > q_min + off;
-          }
           const int n_used = (valid + 15) / 16 * 16;  // columns the instructions computed / will read
           if (quarter == 0 && lane == 0) FA_TRACE(1 + grp, 200 + sweep * n_blk + kb);
           mbar_wait(&t_full[grp], t_ph);
@@ -552,7 +583,7 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             tmem_ld_wait();
             // dropout index / bias index of this chunk's first column (see FaExtra)
             FaExtra ex;
-            if (extras) {
+            if (item_extras) {
               const uint64_t bh = static_cast<uint64_t>(b) * p.heads + h;
               const int c_first = col_g0 + col0;
               ex.seed = has_drop ? *p.drop_seed + p.drop_salt : 0ull;
@@ -563,11 +594,15 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
                 ex.idx_step = p.skv;
                 ex.rb0 = row_g - c_first;
                 ex.rb_step = -1;
+                ex.vis_lo = row_g - off - c_first;   // key <= query + off  <=>  j >= key - off - first query
+                ex.vis_hi = 1 << 30;
               } else {             // row = query, columns = keys
                 ex.idx0 = (bh * p.sq + row_g) * p.skv + c_first;
                 ex.idx_step = 1;
                 ex.rb0 = c_first - row_g;
                 ex.rb_step = 1;
+                ex.vis_lo = -(1 << 30);
+                ex.vis_hi = row_g + off - c_first;   // key <= query + off  <=>  j <= query + off - first key
               }
               ex.rb = rb;
               ex.rb_lo = -(p.sq - 1);
@@ -575,17 +610,19 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
             }
             if (MODE == kFwd && sweep == 0) {
               // ---- statistics sweep: running row maximum / sum of this half's columns
-              if (!slow && valid == kFaSub) {  // (a ragged item reads TMEM columns no instruction wrote: general path)
+              if (valid == kFaSub) {  // (a ragged item reads TMEM columns no instruction wrote: per-element path)
                 if (cols_plain) fa_stats_plain(t1, p.scale_log2, run_m, run_l);
-                else if (has_bias) fa_stats_cols<true>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l, ex);
-                else fa_stats_cols<false>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l);
+                else if (diag && has_bias) fa_stats_cols<true, true>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l, ex);
+                else if (diag) fa_stats_cols<false, true>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l, ex);
+                else if (has_bias) fa_stats_cols<true, false>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l, ex);
+                else fa_stats_cols<false, false>(t1, p.scale_log2, smem_u32(col + col0), run_m, run_l);
                 continue;
               }
               float cmax = -INFINITY;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float v = __uint_as_float(t1[j]) * p.scale_log2;
-                if (slow || !cols_plain) {
+                {
                   const int key = col_g0 + col0 + j;
                   bool ok = col0 + j < valid;
                   if (!cols_plain && ok) ok = col[col0 + j].x == 0.0f;
@@ -607,53 +644,17 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
               continue;
             }
             uint32_t u1[16], u2[16];
-            if (!slow) {
+            {
               const uint32_t col_addr = smem_u32(col + col0);
-              if (has_drop && has_bias)
-                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true, true, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr, ex);
-              else if (has_drop)
-                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true, true, false>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr, ex);
-              else if (has_bias)
-                fa_chunk_plain<kHasAcc1, kHasAcc2, true, true, false, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr, ex);
+              if (item_extras)
+                fa_chunk_extras<kHasAcc1, kHasAcc2>(diag, has_drop, has_bias, t1, t2, u1, u2, p.scale_log2, neg_row, d_row,
+                                                    col_addr, ex);
               else if (cols_plain)
                 fa_chunk_plain<kHasAcc1, kHasAcc2, false, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
               else if (rows_plain)
                 fa_chunk_plain<kHasAcc1, kHasAcc2, true, false>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
               else
                 fa_chunk_plain<kHasAcc1, kHasAcc2, true, true>(t1, t2, u1, u2, p.scale_log2, neg_row, d_row, col_addr);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float pr[2], ds[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int cg = col_g0 + col0 + j + e;
-                  const int key = kRowsAreKeys ? row_g : cg;
-                  const int qi = kRowsAreKeys ? cg : row_g;
-                  float nn = neg_row, dd = d_row;
-                  if (!cols_plain) {
-                    const float2 cc = col[col0 + j + e];
-                    nn += cc.x;
-                    dd += cc.y;
-                  }
-                  float sv = __uint_as_float(t1[j + e]) * p.scale_log2;
-                  const bool vis = !p.causal || key <= qi + off;
-                  const bool inside = key < p.skv && qi < p.sq;
-                  if (rb != nullptr && inside) sv += rb[key - qi] * kFaLog2e;
-                  const float pe = (vis && inside) ? exp2f(sv - nn) : 0.0f;
-                  float p_used = pe, dpv = kHasT2 ? __uint_as_float(t2[j + e]) : 0.0f;
-                  if (p.drop_thresh != 0u) {  // the forward's mask, regenerated in the backward
-                    const uint64_t idx = ((static_cast<uint64_t>(b) * p.heads + h) * p.sq + qi) * p.skv + key;
-                    const bool keep = dropout_keep(*p.drop_seed + p.drop_salt, idx, p.drop_thresh);
-                    p_used = keep ? pe * p.drop_scale : 0.0f;
-                    dpv = keep ? dpv * p.drop_scale : 0.0f;
-                  }
-                  pr[e] = p_used;
-                  ds[e] = pe * (dpv - dd);
-                }
-                if constexpr (kHasAcc1) u1[j >> 1] = pack_bf16x2(pr[0], pr[1]);
-                if constexpr (kHasAcc2) u2[j >> 1] = pack_bf16x2(ds[0], ds[1]);
-              }
             }
             // bf16 pairs of columns [col0, col0 + 32) -> the first half of the columns just consumed
             if constexpr (kHasAcc1) tmem_st_16(t_slot + 16 * c2, u1);
