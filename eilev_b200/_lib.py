@@ -151,7 +151,7 @@ def lib() -> C.CDLL:
 
 
 # kernels launched per successful C-ABI call (lower bounds), for bench.py's gpu_launches
-_KERNELS_PER_CALL = {"vb_cross_entropy": 2, "vb_embed_splice": 2, "vb_attention_bwd": 3}
+_KERNELS_PER_CALL = {"vb_cross_entropy": 2, "vb_embed_splice": 2, "vb_attention_bwd": 2}
 _launches = 0
 
 

@@ -773,12 +773,12 @@ cudaError_t attention_bwd_launch(const vb_attn_bwd_args& a, cudaStream_t stream)
     bp.kt_per_cta = kt;
   }
 
+  // tcgen05 path (attention_flash_tcgen05.cu): dQ and dK / dV by two passes with the reduction index on the TMEM
+  // columns; no dq_acc round trip, delta computed inside the dQ pass
+  if (attention_bwd_tcgen05_eligible(a)) return attention_bwd_tcgen05_launch(a, stream);
   const long long rows = f.batch * f.heads * f.sq;
   launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>((rows * 32 + 127) / 128)), dim3(128), 0, stream, 
       p.o, bp.d_o, a.delta, p.sq, p.heads, p.d, p.o_bs, p.o_rs, rows);
-  // tcgen05 path (attention_flash_tcgen05.cu): dK / dV and dQ by two passes with the reduction index on the TMEM
-  // columns; no dq_acc round trip
-  if (attention_bwd_tcgen05_eligible(a)) return attention_bwd_tcgen05_launch(a, stream);
   const long long hd = f.heads * f.d;
   const long long total = f.batch * f.sq * hd;
   cudaError_t e = cudaMemsetAsync(a.dq_acc, 0, sizeof(float) * total, stream);

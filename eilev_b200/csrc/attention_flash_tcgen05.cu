@@ -76,7 +76,11 @@ enum FaMode : int { kFwd = 0, kBwdQ = 1, kBwdKV = 2 };
 struct FaParams {
   const float* lse;         // backward: (B, H, Sq) natural log
   float* lse_out;           // forward: optional
-  const float* delta;       // backward: (B, H, Sq) rowsum(dO o O)
+  const float* delta;       // backward, kBwdKV: (B, H, Sq) rowsum(dO o O), written by the kBwdQ pass
+  float* delta_out;         // kBwdQ: computes delta from o / d_o (below) and stores it here for the kBwdKV pass
+  const __nv_bfloat16* o;   // kBwdQ: forward output and its gradient, (b, s, h, d) through o_bs / o_rs
+  const __nv_bfloat16* d_o;
+  long long o_bs, o_rs;
   const uint8_t* key_mask;  // (B, Skv) or nullptr
   __nv_bfloat16* out1;      // kFwd: O, kBwdKV: dV
   __nv_bfloat16* out2;      // kBwdKV: dK, kBwdQ: dQ
@@ -514,7 +518,34 @@ attn_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_c
         if (row_g < p.sq) {
           const float l = p.lse[bh_off + row_g];
           if (l != -INFINITY) neg_row = l * kFaLog2e;
-          d_row = p.delta[bh_off + row_g];
+          // delta = rowsum(dO o O) of this query row, computed here (one pass over two d-element rows) instead of
+          // by a kernel of its own; the dK / dV pass, launched after this one, reads it back
+          const long long ro = b * p.o_bs + static_cast<long long>(row_g) * p.o_rs + h * p.d;
+          float acc = 0.0f;
+#pragma unroll
+          for (int c0 = 0; c0 < 128; c0 += 64) {  // eight 16-byte loads of each row in flight at a time
+            uint4 uo[8], ug[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = c0 + 8 * i;
+              uo[i] = ug[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (c < p.d) {
+                uo[i] = __ldg(reinterpret_cast<const uint4*>(p.o + ro + c));
+                ug[i] = __ldg(reinterpret_cast<const uint4*>(p.d_o + ro + c));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t wo[4] = {uo[i].x, uo[i].y, uo[i].z, uo[i].w}, wg[4] = {ug[i].x, ug[i].y, ug[i].z, ug[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 fo = unpack_bf16x2(wo[j]), fg = unpack_bf16x2(wg[j]);
+                acc = fmaf(fo.x, fg.x, fmaf(fo.y, fg.y, acc));
+              }
+            }
+          }
+          d_row = acc;
+          if (grp == 0) p.delta_out[bh_off + row_g] = acc;
         }
       }
       // do the rows of this unit carry a term at all (other than the lse of a query row)?
@@ -816,7 +847,8 @@ static cudaError_t fa_set_attrs() {
 }
 
 static void fa_common(FaParams& p, const vb_attn_args& f) {
-  p.lse = nullptr; p.lse_out = nullptr; p.delta = nullptr;
+  p.lse = nullptr; p.lse_out = nullptr; p.delta = nullptr; p.delta_out = nullptr;
+  p.o = nullptr; p.d_o = nullptr; p.o_bs = p.o_rs = 0;
   p.key_mask = f.key_mask;
   p.out1 = nullptr; p.out2 = nullptr;
   p.out1_bs = p.out1_rs = p.out2_bs = p.out2_rs = 0;
@@ -873,27 +905,33 @@ cudaError_t attention_bwd_tcgen05_launch(const vb_attn_bwd_args& a, cudaStream_t
   FaParams p;
   fa_common(p, f);
   p.lse = f.lse;
-  p.delta = a.delta;
   const int q_tiles = (p.sq + kFaEdge - 1) / kFaEdge, k_tiles = (p.skv + kFaEdge - 1) / kFaEdge;
   const float dq_scale = a.dq_scale == 0.0f ? 1.0f : a.dq_scale;
 
+  // dQ first: rows = queries; it also produces delta for the second pass
+  p.out1 = nullptr; p.out1_bs = 0; p.out1_rs = 0;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.out2_bs = a.dq_bs; p.out2_rs = a.dq_rs;
+  p.out2_mul = f.scale * dq_scale;
+  p.delta = nullptr;
+  p.delta_out = a.delta;
+  p.o = reinterpret_cast<const __nv_bfloat16*>(f.o);
+  p.d_o = reinterpret_cast<const __nv_bfloat16*>(a.d_o);
+  p.o_bs = f.o_bs; p.o_rs = f.o_rs;
+  p.row_tiles = q_tiles; p.col_blocks = (p.skv + kFaSub - 1) / kFaSub;
+  long long units = static_cast<long long>(p.batch) * p.heads * p.row_tiles;
+  e = launch_pdl(attn_flash_tc_kernel<kBwdQ>, dim3(static_cast<unsigned>(units < sms ? units : sms)),
+                 dim3(kFaThreads), kFaSmem, stream, tq, tdo, bk, bv, p);
+  if (e != cudaSuccess) return e;
   // dK, dV: rows = keys
   p.out1 = reinterpret_cast<__nv_bfloat16*>(a.dv); p.out1_bs = a.dv_bs; p.out1_rs = a.dv_rs;
   p.out2 = reinterpret_cast<__nv_bfloat16*>(a.dk); p.out2_bs = a.dk_bs; p.out2_rs = a.dk_rs;
   p.out2_mul = f.scale;
+  p.delta = a.delta;
+  p.delta_out = nullptr;
   p.row_tiles = k_tiles; p.col_blocks = (p.sq + kFaSub - 1) / kFaSub;
-  long long units = static_cast<long long>(p.batch) * p.heads * p.row_tiles;
-  e = launch_pdl(attn_flash_tc_kernel<kBwdKV>, dim3(static_cast<unsigned>(units < sms ? units : sms)),
-                 dim3(kFaThreads), kFaSmem, stream, tk, tv, bq, bdo, p);
-  if (e != cudaSuccess) return e;
-  // dQ: rows = queries
-  p.out1 = nullptr; p.out1_bs = 0; p.out1_rs = 0;
-  p.out2 = reinterpret_cast<__nv_bfloat16*>(a.dq); p.out2_bs = a.dq_bs; p.out2_rs = a.dq_rs;
-  p.out2_mul = f.scale * dq_scale;
-  p.row_tiles = q_tiles; p.col_blocks = (p.skv + kFaSub - 1) / kFaSub;
   units = static_cast<long long>(p.batch) * p.heads * p.row_tiles;
-  return launch_pdl(attn_flash_tc_kernel<kBwdQ>, dim3(static_cast<unsigned>(units < sms ? units : sms)),
-                    dim3(kFaThreads), kFaSmem, stream, tq, tdo, bk, bv, p);
+  return launch_pdl(attn_flash_tc_kernel<kBwdKV>, dim3(static_cast<unsigned>(units < sms ? units : sms)),
+                    dim3(kFaThreads), kFaSmem, stream, tk, tv, bq, bdo, p);
 }
 
 #ifdef VB_FA_TRACE

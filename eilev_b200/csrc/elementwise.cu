@@ -539,26 +539,29 @@ cudaError_t act_bwd_launch(const void* dy, const void* saved, void* dx, int epi,
   return cudaGetLastError();
 }
 
-// Block = 32 columns x 8 row lanes; grid.y splits rows; atomics only across grid.y.
-__global__ void __launch_bounds__(256)
+// Block = 32 columns x 32 row lanes (1024 threads, four loads in flight per thread); grid.y splits very tall
+// inputs, atomics only across grid.y (one row block up to 16 384 rows: a fixed summation order).
+__global__ void __launch_bounds__(1024)
 colsum_kernel(const __nv_bfloat16* x, float* out, long long rows, long long cols, long long ldx) {
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const long long c = static_cast<long long>(blockIdx.x) * 32 + cx;
   const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r_lo = static_cast<long long>(blockIdx.y) * rows_per;
   const long long r_hi = r_lo + rows_per < rows ? r_lo + rows_per : rows;
   float acc = 0.0f;
-  if (c < cols)
-    for (long long r = r_lo + ry; r < r_hi; r += 8) acc += __bfloat162float(x[r * ldx + c]);
+  if (c < cols) {
+#pragma unroll 4
+    for (long long r = r_lo + ry; r < r_hi; r += 32) acc += __bfloat162float(x[r * ldx + c]);
+  }
   sm[ry][cx] = acc;
   __syncthreads();
   if (ry == 0 && c < cols) {
     float t = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][cx];
+    for (int i = 0; i < 32; ++i) t += sm[i][cx];
     if (gridDim.y == 1) out[c] += t;
     else atomicAdd(&out[c], t);
   }
@@ -572,10 +575,10 @@ cudaError_t colsum_launch(const void* x, float* out, long long rows, long long c
     if (e != cudaSuccess) return e;
   }
   if (rows <= 0) return cudaSuccess;
-  unsigned gy = static_cast<unsigned>(rows / 2048 + 1);
+  unsigned gy = static_cast<unsigned>(rows / 16384 + 1);
   if (gy > 64) gy = 64;
   dim3 grid(static_cast<unsigned>((cols + 31) / 32), gy);
-  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ldx);
+  launch_pdl(colsum_kernel, dim3(grid), dim3(1024), 0, s, reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, ldx);
   return cudaGetLastError();
 }
 

@@ -288,17 +288,18 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBw
   }
 }
 
-// dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy.  Block = 32 columns x 8 row lanes;
+// dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy.  Block = 32 columns x 32 row lanes;
 // every column is owned by exactly one block, so the accumulation is deterministic.
-__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const LnBwdParams p) {
+__global__ void __launch_bounds__(1024) ln_bwd_param_kernel(const LnBwdParams p) {
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
-  __shared__ float sg[8][33], sb[8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  __shared__ float sg[32][33], sb[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;   // 32 columns x 32 row lanes
   const long long c = static_cast<long long>(blockIdx.x) * 32 + cx;
   float ag = 0.0f, ab = 0.0f;
   if (c < p.cols) {
-    for (long long r = ry; r < p.rows; r += 8) {
+#pragma unroll 4
+    for (long long r = ry; r < p.rows; r += 32) {
       const float dyv = __bfloat162float(p.dy[r * p.cols + c]);
       const float xh = (__bfloat162float(p.xin[r * p.cols + c]) - p.mean[r]) * p.rstd[r];
       ag += dyv * xh;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const LnBwdParams p) 
   if (ry == 0 && c < p.cols) {
     float tg = 0.0f, tb = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { tg += sg[i][cx]; tb += sb[i][cx]; }
+    for (int i = 0; i < 32; ++i) { tg += sg[i][cx]; tb += sb[i][cx]; }
     p.dgamma[c] += tg;
     p.dbeta[c] += tb;
   }
@@ -331,7 +332,7 @@ cudaError_t layernorm_bwd_launch(const LnBwdParams& p, cudaStream_t s) {
   else if (vpl <= 10) launch_pdl(ln_bwd_dx_vec_kernel<10>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
   else launch_pdl(ln_bwd_dx_vec_kernel<12>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
   if (p.dgamma != nullptr && p.dbeta != nullptr) {
-    launch_pdl(ln_bwd_param_kernel, dim3(static_cast<unsigned>((p.cols + 31) / 32)), dim3(256), 0, s, p);
+    launch_pdl(ln_bwd_param_kernel, dim3(static_cast<unsigned>((p.cols + 31) / 32)), dim3(1024), 0, s, p);
   }
   return cudaGetLastError();
 }
