@@ -61,6 +61,12 @@ int vb_gemm(const vb_gemm_args* a, void* stream) {
   if (a->a == nullptr || a->b == nullptr || a->c == nullptr) return fail_msg("vb_gemm", "null operand");
   if (a->out_dtype != VB_BF16 && a->out_dtype != VB_F32) return fail_msg("vb_gemm", "bad out_dtype");
   const bool elig = vb::gemm_tcgen05_eligible(*a);
+  if (a->reserved2 != 0) {
+    if (a->reserved2 != 1) return fail_msg("vb_gemm", "bad operand_layout");
+    if (!elig || a->backend == VB_GEMM_GENERIC || a->ln_stats != nullptr || a->stats_out != nullptr ||
+        a->stats_zero != nullptr || a->row_group != 0)
+      return fail_msg("vb_gemm", "transposed operands need the plain tcgen05 path (M, N, lda, ldb % 8 == 0)");
+  }
   if (a->backend == VB_GEMM_TCGEN05 && !elig)
     return fail_msg("vb_gemm", "shape/alignment not eligible for the tcgen05 path");
   if ((a->epilogue == VB_EPI_GELU_BWD || a->epilogue == VB_EPI_RELU_BWD) &&

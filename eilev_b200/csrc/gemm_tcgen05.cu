@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "gemm_epilogue.cuh"
+#include "tc_attention.cuh"
 
 namespace vb {
 
@@ -37,7 +38,10 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const EpiParams p,
-                    const int num_k_blocks, const int m_tiles, const int n_tiles) {
+                    const int num_k_blocks, const int m_tiles, const int n_tiles, const int transposed) {
+  // transposed = 1: both operands are given TRANSPOSED — a = A^T stored (K, M), b = B^T stored (K, N), row-major —
+  // and enter the instruction as MN-major tiles (rows = K index, 64 contiguous M / N elements per swizzled row):
+  // the wgrad product dW = dY^T X straight from the (tokens, features) activations, no transpose pass.
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -94,10 +98,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK,
-                      m_blk * kBM);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK,
-                      n_blk * BN);
+          if (!transposed) {
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK,
+                        m_blk * kBM);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK,
+                        n_blk * BN);
+          } else {  // boxes of 64 (M or N, contiguous) x 64 (K rows): one per 64-wide chunk of the tile
+            for (int c = 0; c < kBM / 64; ++c)
+              tma_load_2d(smem_a + stage * Cfg::kABytes + c * (kBK * 128), &tmap_a, &full_bar[stage],
+                          m_blk * kBM + 64 * c, kb * kBK);
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(smem_b + stage * Cfg::kBBytes + c * (kBK * 128), &tmap_b, &full_bar[stage],
+                          n_blk * BN + 64 * c, kb * kBK);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -117,12 +130,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          if (!transposed) {
+            const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in >>4 units
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in >>4 units
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          } else {
+            // MN-major: 16 K elements = 16 rows of 128 B; the next 64 M / N elements sit one chunk (8 KB) further
+            constexpr uint32_t idesc_mn = idesc | (1u << 15) | (1u << 16);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t a_desc = umma_desc_mn_sw128(smem_u32(smem_a + stage * Cfg::kABytes + k * 16 * 128), kBK * 128);
+              const uint64_t b_desc = umma_desc_mn_sw128(smem_u32(smem_b + stage * Cfg::kBBytes + k * 16 * 128), kBK * 128);
+              umma_bf16(d_tmem, a_desc, b_desc, idesc_mn, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -213,7 +237,11 @@ bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long l
 bool gemm_tcgen05_eligible(const vb_gemm_args& a) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (a.m <= 0 || a.n <= 0 || a.k <= 0) return false;
-  if (a.k % 8 != 0 || a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
+  if (a.reserved2 == 1) {  // transposed operands: the contiguous dims are M and N
+    if (a.m % 8 != 0 || a.n % 8 != 0 || a.lda % 8 != 0 || a.ldb % 8 != 0) return false;
+  } else if (a.k % 8 != 0 || a.lda % 8 != 0 || a.ldb % 8 != 0) {
+    return false;
+  }
   if (!al16(a.a) || !al16(a.b) || !al16(a.c)) return false;
   if (a.n % 8 != 0) return false;
   if (a.out_dtype == VB_BF16 ? (a.ldc % 8 != 0) : (a.ldc % 4 != 0)) return false;
@@ -247,8 +275,15 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
                              int force_grid) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
-  if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, kBM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, BN)) return cudaErrorInvalidValue;
+  const int transposed = a.reserved2 == 1 ? 1 : 0;  // vb_gemm_args.operand_layout
+  if (!transposed) {
+    if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, kBM)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, BN)) return cudaErrorInvalidValue;
+  } else {  // a = A^T (K, M), b = B^T (K, N): boxes of 64 contiguous M / N elements x 64 K rows
+    if (BN % 64 != 0) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_2d(&ta, a.a, a.k, a.m, a.lda, kBK)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_2d(&tb, a.b, a.k, a.n, a.ldb, kBK)) return cudaErrorInvalidValue;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
@@ -274,7 +309,7 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
   int grid = static_cast<int>(tiles < sms ? tiles : sms);
   if (force_grid > 0 && force_grid < grid) grid = force_grid;
   return launch_pdl(gemm_tcgen05_kernel<BN>, dim3(static_cast<unsigned>(grid)), dim3(kGemmThreads), Cfg::kSmemBytes,
-                    stream, ta, tb, ep, k_blocks, m_tiles, n_tiles);
+                    stream, ta, tb, ep, k_blocks, m_tiles, n_tiles, transposed);
 }
 
 void fill_epi_params(EpiParams& ep, const vb_gemm_args& a) {
@@ -340,6 +375,12 @@ static int pick_2cta_block_n(long long m, long long n, long long k) {
 // vb_gemm_args.reserved: 0 = automatic; 64/128/176/256 = force the 1-CTA kernel with that
 // BLOCK_N; 1000 + width (a multiple of 16, 32..256) = force the CTA-pair kernel at that tile width.
 cudaError_t gemm_tcgen05_launch(const vb_gemm_args& a, cudaStream_t stream) {
+  if (a.reserved2 == 1) {  // transposed operands: 1-CTA kernel, tile widths that are whole 64-element chunks
+    EpiParams ep;
+    fill_epi_params(ep, a);
+    if (a.reserved == 64 || (a.reserved == 0 && a.n <= 64)) return launch_bn<64>(a, ep, stream, 0);
+    return launch_bn<128>(a, ep, stream, 0);
+  }
   if (a.reserved >= 1000) return gemm_tcgen05_2cta_launch(a, a.reserved - 1000, stream);
   if (a.reserved == 0) {
     const int bn2 = pick_2cta_block_n(a.m, a.n, a.k);

@@ -159,7 +159,7 @@ def qformer_forward(model, cache: PackCache, image_embeds: torch.Tensor, save: b
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """dW (N_out, K_in) f32 = dy^T (N_out, M) . x (M, K_in)."""
-    return ops.gemm(T(dy), T(x), out_dtype=torch.float32)
+    return ops.gemm_tn(dy, x, out_dtype=torch.float32)
 
 
 class _GradOut(dict):
@@ -177,7 +177,7 @@ class _GradOut(dict):
     def weight(self, name: str, dy: torch.Tensor, x: torch.Tensor) -> None:
         dst = self.sink.get(name)
         if dst is not None:
-            ops.gemm(T(dy), T(x), out=dst, beta=1.0)
+            ops.gemm_tn(dy, x, out=dst, beta=1.0)
         else:
             self[name] = _wgrad(dy, x)
 

@@ -97,6 +97,39 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *,
     return out
 
 
+def gemm_tn(dy: torch.Tensor, x: torch.Tensor, *, out: torch.Tensor | None = None, beta: float = 0.0,
+            out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """``out = dy.T @ x (+ beta * out)``: the weight-gradient product of a linear layer, dy: (tokens, N_out),
+    x: (tokens, N_in) bf16, out: (N_out, N_in).  The activations enter the tcgen05 instruction as MN-major tiles
+    (vb_gemm_args.operand_layout = 1), so nothing is transposed; shapes the tensor maps cannot address (dims
+    that are not multiples of 8, unaligned views) go through two transpose kernels and the plain GEMM."""
+    _need(dy, torch.bfloat16, "gemm_tn.dy")
+    _need(x, torch.bfloat16, "gemm_tn.x")
+    assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0]
+    m, n, k = dy.shape[1], x.shape[1], dy.shape[0]
+    ok = (m % 8 == 0 and n % 8 == 0 and dy.stride(1) == 1 and x.stride(1) == 1 and dy.stride(0) % 8 == 0
+          and x.stride(0) % 8 == 0 and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0
+          and k <= 8192  # long reductions (the cross-K|V weight gradient over 34 952 tokens) keep the CTA-pair kernel
+          and os.environ.get("VB_GEMM_TN", "1") != "0")
+    if not ok:
+        return gemm(transpose(dy), transpose(x), out=out, beta=beta, out_dtype=out_dtype)
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=dy.device)
+    else:
+        assert out.shape == (m, n) and out.stride(-1) == 1
+    if out.data_ptr() % 16 != 0 or out.stride(0) % (8 if out.dtype == torch.bfloat16 else 4) != 0:
+        return gemm(transpose(dy), transpose(x), out=out, beta=beta, out_dtype=out_dtype)
+    args = GemmArgs()
+    args.a, args.b, args.c = dy.data_ptr(), x.data_ptr(), out.data_ptr()
+    args.m, args.n, args.k = m, n, k
+    args.lda, args.ldb, args.ldc = dy.stride(0), x.stride(0), out.stride(0)
+    args.alpha, args.beta = 1.0, beta
+    args.epilogue, args.out_dtype, args.backend = EPI_NONE, _DT[out.dtype], GEMM_TCGEN05
+    args.reserved2 = 1
+    check(_lib.lib().vb_gemm(C.byref(args), _stream()), "vb_gemm")
+    return out
+
+
 def row_stats(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """(rows, 2) f64 [sum, sum of squares] of every row of a 2-D bf16 tensor (see gemm(ln_fold=...))."""
     _need(x, torch.bfloat16, "row_stats.x")

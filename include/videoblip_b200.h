@@ -91,6 +91,11 @@ typedef struct vb_gemm_args {
    * (*dropout_seed + dropout_salt, row*n + col) — vb_dropout with the same seed/salt
    * regenerates it in the backward pass.  dropout_p == 0 or dropout_seed == NULL: off. */
   float dropout_p;
+  /* operand_layout: 0 = a is A (M, K) and b is B (N, K), both row-major (nn.Linear forward / dgrad).
+   * 1 = a is A^T stored (K, M) row-major with row stride lda, b is B^T stored (K, N) with row stride ldb: C = A B^T
+   * = a^T b, the weight-gradient product dW (N_out, N_in) = dY^T X taken straight from the (tokens, features)
+   * activations (M = N_out, N = N_in, K = tokens); tcgen05 path only (M, N, lda, ldb multiples of 8), no
+   * LayerNorm fold / row statistics. */
   int32_t reserved2;
   const uint64_t* dropout_seed; /* device pointer */
   uint64_t dropout_salt;

@@ -53,6 +53,28 @@ def test_gemm_tcgen05_plain(m, n, k, bn):
     _close(out, ref, atol=0.02 * math.sqrt(k), rtol=0.01, what=f"gemm {m}x{n}x{k} bn={bn}")
 
 
+@pytest.mark.parametrize("tokens,n_out,n_in", [(544, 768, 768), (544, 3072, 768), (544, 768, 3072), (100, 264, 72),
+                                               (1000, 128, 64), (37, 768, 1408), (544, 2560, 768)])
+def test_gemm_weight_gradient_from_untransposed_activations(tokens, n_out, n_in):
+    """gemm_tn: dW = dY^T X with both operands entering the instruction MN-major (operand_layout = 1), against
+    fp32 torch and against the transpose-kernel path; accumulation into an f32 buffer (beta = 1)."""
+    ops = _ops()
+    dy, x = _rand(tokens, n_out, scale=0.3, seed=71), _rand(tokens, n_in, scale=0.5, seed=72)
+    ref = dy.float().t() @ x.float()
+    got = ops.gemm_tn(dy, x)
+    assert got.dtype == torch.float32
+    _close(got, ref, atol=0.02 * math.sqrt(tokens), rtol=0.01, what=f"gemm_tn {tokens}x{n_out}x{n_in}")
+    two = ops.gemm(ops.transpose(dy), ops.transpose(x), out_dtype=torch.float32)
+    _close(got, two, atol=1e-3 * math.sqrt(tokens), rtol=1e-3, what="gemm_tn vs transposes")
+    acc = torch.ones(n_out, n_in, device="cuda")
+    ops.gemm_tn(dy, x, out=acc, beta=1.0)
+    _close(acc, ref + 1.0, atol=0.02 * math.sqrt(tokens), rtol=0.01, what="gemm_tn accumulate")
+    # column slices of a wider buffer (row stride != width)
+    wide = _rand(tokens, n_out + 64, scale=0.3, seed=73)
+    got2 = ops.gemm_tn(wide[:, 64:], x)
+    _close(got2, wide[:, 64:].float().t() @ x.float(), atol=0.02 * math.sqrt(tokens), rtol=0.01, what="gemm_tn strided")
+
+
 @pytest.mark.parametrize("bn", [1144, 1208, 1192, 0])
 def test_gemm_cta_pair_widths_with_full_epilogue(bn):
     """bias + ReLU + dropout + residual through a tile width with a partial last slab (staged slabs and direct
