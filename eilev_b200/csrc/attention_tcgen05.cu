@@ -359,6 +359,23 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // S <= 272 / d <= 128).
 constexpr int kPpColO = 128;
 constexpr int kPpColTail = 224;
+// alignment slack + Q (2 buffers) + K + V + 2 KB of barriers / row-256 scratch; the O staging tile follows
+constexpr int kPpSmemBase = 1024 + 2 * 2 * kTaChunkBytesQ + 2 * 2 * kTaChunkBytesK + 2048;
+
+// -DVB_PP_TRACE (scripts/micro/pp_trace.sh): clock64 stamps of CTA 0's MMA issuer (who 0) and of the first warp of
+// each softmax group (who 1, 2), read back through vb_debug_pp_trace.  Off in the product build.
+#ifdef VB_PP_TRACE
+__device__ long long g_pp_trace[3 * 1024];
+__device__ int g_pp_trace_n[3];
+#define PP_TRACE_DECL int tr_i_ = 0;
+#define PP_TRACE(who, tag) do { if (blockIdx.x == 0 && tr_i_ < 511) { \
+  g_pp_trace[(who) * 1024 + 2 * tr_i_] = (tag); g_pp_trace[(who) * 1024 + 2 * tr_i_ + 1] = clock64(); ++tr_i_; } } while (0)
+#define PP_TRACE_END(who) do { if (blockIdx.x == 0) g_pp_trace_n[who] = tr_i_; } while (0)
+#else
+#define PP_TRACE_DECL
+#define PP_TRACE(who, tag)
+#define PP_TRACE_END(who)
+#endif
 
 struct PpParams {
   __nv_bfloat16* o;
@@ -367,6 +384,8 @@ struct PpParams {
   long long q_rs;
   int row256;               // 1: the last query row of S = 257 is computed by warps 2-3 (no third Q tile)
   int stagger;              // cycles the first tile of slot 1 is held back (phase offset between the warp groups)
+  int flags;                // bit 0: software-pipelined softmax passes (S = 256 + tail), bit 1: O through a staged TMA store,
+                            // bit 2: L2 prefetch of the next item's K / V / Q
   int items, heads, s, d;
   int dpad;            // d rounded up to 16: N of the P.V instruction
   float scale_log2;
@@ -384,9 +403,35 @@ VB_DEVICE void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+VB_DEVICE float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+VB_DEVICE float max3(float a, float b, float c) {
+  float y;
+  asm("max.ftz.f32 %0, %1, %2, %3;\n" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+// L2 prefetch of one (d, head, token) box: the later TMA load of the same box hits L2
+VB_DEVICE void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// 4-D tiled store smem -> global (bulk async group): (d, head, token, frame) coordinates; clipped at the extents
+VB_DEVICE void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kTaThreads, 1)
 attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                       const __grid_constant__ CUtensorMap tmap_v, const PpParams p) {
+                       const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                       const PpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -405,6 +450,8 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   uint64_t* o_full = bars + 12;     // [2]
   uint64_t* slot_free = bars + 14;  // [2]  4 softmax warps finished reading O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* stage_free = bars + 17;  // the O staging tile was read by its TMA store (one completion per tile, in tile order)
+  uint8_t* sO = reinterpret_cast<uint8_t*>(bars) + 2048;   // [128 rows][d] bf16, dense: the source box of the O store
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -421,6 +468,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_k);
     prefetch_tmap(&tmap_v);
+    prefetch_tmap(&tmap_o);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -435,6 +483,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     mbar_init(k_empty, 1 + 4 * m_tiles + (row256 ? 2 : 0));
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1 + (row256 ? 2 : 0));
+    mbar_init(stage_free, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -448,6 +497,12 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   pdl_wait();     // programmatic dependent launch: q / k / v of the preceding GEMM are visible from here on
   pdl_trigger();
 
+  // Register split (the kernel is launched at 168 per thread = 64 512): the control warp group hands 80 per
+  // thread back, the two softmax groups take 40 more each.  At 168 ptxas serialised the softmax passes (TMEM load
+  // -> wait -> exponentials on the SAME registers) to stay under the cap; with 208 the next chunk's load is in
+  // flight under the current chunk's exponentials.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n" ::: "memory");
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {  // (not lane == 0: see gemm_tcgen05_2cta.cu)
@@ -466,6 +521,22 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           tma_load_3d(dst + kTaChunkBytesQ, &tmap_q, &q_full[buf], 64, h, row0 + t * kTaQRows);
           ++g;
         };
+        // K and V are single-buffered: the load of the next item's K can only be issued when this item's last
+        // Q K^T has retired, and its ~4 000 clk of DRAM latency then sat on the critical path (k_full wait of the
+        // MMA warp in profiles/r02_attn_pp_trace.txt).  The next item's boxes are pulled into L2 one item ahead.
+        if ((p.flags & 4) != 0 && item + static_cast<int>(gridDim.x) < p.items) {
+          const int nb = (item + gridDim.x) / p.heads, nh = (item + gridDim.x) % p.heads;
+          const int nrow0 = nb * p.s;
+          for (int c = 0; c < 2; ++c) {
+            if (c * 64 < p.d) {
+              for (int hf = 0; hf < 2; ++hf) {
+                tma_prefetch_3d(&tmap_k, c * 64, nh, nrow0 + hf * kTaHalf);
+                tma_prefetch_3d(&tmap_v, c * 64, nh, nrow0 + hf * kTaHalf);
+              }
+              for (int t = 0; t < m_tiles; ++t) tma_prefetch_3d(&tmap_q, c * 64, nh, nrow0 + t * kTaQRows);
+            }
+          }
+        }
         mbar_wait(k_empty, k_ph ^ 1u);
         k_ph ^= 1u;
         mbar_expect_tx(k_full, 2 * kTaChunkBytesK);
@@ -488,6 +559,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
+      PP_TRACE_DECL
       const uint32_t idesc_s = umma_idesc_bf16(128, 256);
       const uint32_t idesc_o = umma_idesc_bf16(128, static_cast<uint32_t>(p.dpad)) | (1u << 16);  // B MN-major
       const int k_steps = (p.d + 15) / 16;
@@ -501,9 +573,11 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           mbar_wait(v_full, v_ph);
           v_ph ^= 1u;
         }
+        PP_TRACE(0, 3);
         mbar_wait(&p_ready[slot], p_ph[slot]);
         p_ph[slot] ^= 1u;
         tc_fence_after();
+        PP_TRACE(0, 4);
         const uint32_t t0 = tmem_base + slot * 256;
         for (int js = 0; js < kv_main; ++js) {
           const uint64_t b_desc = umma_desc_mn_sw128(smem_u32(sV + js * 16 * 128), kTaChunkBytesK);
@@ -522,10 +596,12 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         k_ph ^= 1u;
         for (int t = 0; t < m_tiles; ++t) {
           const int slot = g & 1;
+          PP_TRACE(0, 1);
           mbar_wait(&q_full[slot], q_ph[slot]);
           q_ph[slot] ^= 1u;
           mbar_wait(&slot_free[slot], free_ph[slot] ^ 1u);  // epilogue of tile g-2 has drained O
           free_ph[slot] ^= 1u;
+          PP_TRACE(0, 2);
           if (g == 1 && p.stagger > 0) {
             // With two tiles per item both warp groups would start every item together and stay in lockstep:
             // softmax of both tiles at the same time (contending for the MUFU pipe) with the tensor pipe idle,
@@ -556,6 +632,7 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         }
       }
       if (have_prev) issue_pv();
+      PP_TRACE_END(0);
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------ warps 2-3: the 257th query row
@@ -665,17 +742,19 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         named_bar_sync(5, 64);                 // pbuf / xch are free for the next item
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n" ::: "memory");
     // ------------------------------------------------------------ softmax + epilogue (one slot per warp group)
     const int wg = (warp - 4) >> 2;  // == slot == Q buffer
     const int quarter = warp & 3;
     const int r_in_tile = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + wg * 256;
     const int n_chunks = (s_main + 31) / 32;   // 32-key chunks of S (8 for ViT-g)
-    const int k_steps = (p.d + 15) / 16;
     const int n16 = p.dpad / 16;
     uint32_t q_ph = 0, s_ph = 0, o_ph = 0;
     int g = 0, n_item = 0;
+    PP_TRACE_DECL
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n_item) {
       const int b = item / p.heads, h = item % p.heads;
       for (int t = 0; t < m_tiles; ++t, ++g) {
@@ -683,31 +762,48 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const int qi = t * kTaQRows + r_in_tile;
         const bool warp_has_rows = (t * kTaQRows + quarter * 32) < p.s;
         // ---- score of key 256 for this warp's 32 rows: mma.sync from the swizzled Q / K tiles
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 1);
         mbar_wait(&q_full[wg], q_ph);
         q_ph ^= 1u;
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 2);
         float tail = -INFINITY;
         if (has_tail) {
           mbar_wait(k_full, static_cast<uint32_t>(n_item & 1));
           if (warp_has_rows) {
+            // every load first, then four independent mma.sync chains (two row blocks x even / odd k-steps): the
+            // rolled loop of round 1 (load -> wait -> mma per k-step) took ~1 200 clk on the tile's critical path
             const uint32_t q_base = smem_u32(sQ + wg * 2 * kTaChunkBytesQ);
             float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            for (int ks = 0; ks < k_steps; ++ks) {
+            float acc_odd[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            static_assert(kPpColO / 16 >= 6, "k-steps of the tail score are unrolled for d <= 96");
+            uint32_t kf[6][2];
+            uint32_t af[6][2][4];
+            // (k-steps beyond d multiply zero-filled columns: the 64-wide boxes are zero beyond the head dim)
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks) {
               const int c = ks >> 2, kk = ks & 3;
-              uint32_t b0 = 0u, b1 = 0u;
-              if (lane < 4) {  // B fragment column n = 0 <-> key 256 (row 256: swizzle phase 0)
-                const uint8_t* kr = sK + c * kTaChunkBytesK + 256 * 128 + kk * 32 + lane * 4;
-                b0 = *reinterpret_cast<const uint32_t*>(kr);
-                b1 = *reinterpret_cast<const uint32_t*>(kr + 16);
-              }
+              const uint8_t* kr = sK + c * kTaChunkBytesK + 256 * 128 + kk * 32 + (lane & 3) * 4;
+              // B fragment column n = 0 <-> key 256 (row 256: swizzle phase 0); the other columns are unused
+              kf[ks][0] = *reinterpret_cast<const uint32_t*>(kr);
+              kf[ks][1] = *reinterpret_cast<const uint32_t*>(kr + 16);
 #pragma unroll
               for (int rb = 0; rb < 2; ++rb) {
                 const int row = quarter * 32 + rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int unit = 2 * kk + (lane >> 4);
-                uint32_t a[4];
-                ldmatrix_x4(a, q_base + c * kTaChunkBytesQ + row * 128 + ((unit ^ (row & 7)) << 4));
-                mma_bf16_16816(acc[rb], a, b0, b1);
+                ldmatrix_x4(af[ks][rb], q_base + c * kTaChunkBytesQ + row * 128 + ((unit ^ (row & 7)) << 4));
               }
             }
+#pragma unroll
+            for (int ks = 0; ks < 6; ks += 2) {
+              mma_bf16_16816(acc[0], af[ks][0], kf[ks][0], kf[ks][1]);
+              mma_bf16_16816(acc[1], af[ks][1], kf[ks][0], kf[ks][1]);
+              mma_bf16_16816(acc_odd[0], af[ks + 1][0], kf[ks + 1][0], kf[ks + 1][1]);
+              mma_bf16_16816(acc_odd[1], af[ks + 1][1], kf[ks + 1][0], kf[ks + 1][1]);
+            }
+            acc[0][0] += acc_odd[0][0];
+            acc[0][2] += acc_odd[0][2];
+            acc[1][0] += acc_odd[1][0];
+            acc[1][2] += acc_odd[1][2];
             // column 0 of the C fragments sits in lanes 0, 4, ..., 28 (c0: row lane/4, c2: row lane/4 + 8)
             const int src = (lane & 7) * 4;
             const float v00 = __shfl_sync(0xffffffffu, acc[0][0], src);
@@ -722,89 +818,163 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           mbar_arrive(&q_empty[wg]);
           mbar_arrive(k_empty);
         }
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 3);
         mbar_wait(&s_full[wg], s_ph);
         s_ph ^= 1u;
         tc_fence_after();
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 4);
         float inv_sum = 0.0f;
         if (warp_has_rows) {
-          // ---- pass 1: row maximum (two 32-column loads in flight)
-          float m0 = tail, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-          for (int ch = 0; ch < n_chunks; ch += 2) {
-            uint32_t r0[32], r1[32];
-            const bool two = ch + 1 < n_chunks;
-            tmem_ld_32(t_row + ch * 32, r0);
-            if (two) tmem_ld_32(t_row + (ch + 1) * 32, r1);
-            tmem_ld_wait();
-            if (ch * 32 + 32 <= s_main) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                m0 = fmaxf(m0, __uint_as_float(r0[j]));
-                m1 = fmaxf(m1, __uint_as_float(r0[j + 1]));
-                m2 = fmaxf(m2, __uint_as_float(r0[j + 2]));
-                m3 = fmaxf(m3, __uint_as_float(r0[j + 3]));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ch * 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r0[j]));
-            }
-            if (two) {
-              if (ch * 32 + 64 <= s_main) {
+          float mxs;
+          float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+          if ((p.flags & 1) != 0 && s_main == 256) {
+            // ---- S = 256 (+ tail), software-pipelined.  One warp per scheduler is in this code at a time, so
+            // latencies are hidden by instruction-level parallelism or not at all (the round-1 form issued a MUFU
+            // and its dependent FADD two instructions apart: 21 clk per element against 8 at the MUFU rate).
+            // pass 1: row maximum, 64 columns in flight while 64 are reduced with 3-input FMNMX
+            float m0 = tail, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            {
+              uint32_t a0[32], a1[32], b0[32], b1[32];
+              auto max64 = [&](const uint32_t (&x)[32], const uint32_t (&y)[32]) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  m0 = fmaxf(m0, __uint_as_float(r1[j]));
-                  m1 = fmaxf(m1, __uint_as_float(r1[j + 1]));
-                  m2 = fmaxf(m2, __uint_as_float(r1[j + 2]));
-                  m3 = fmaxf(m3, __uint_as_float(r1[j + 3]));
+                  m0 = max3(m0, __uint_as_float(x[j]), __uint_as_float(y[j]));
+                  m1 = max3(m1, __uint_as_float(x[j + 1]), __uint_as_float(y[j + 1]));
+                  m2 = max3(m2, __uint_as_float(x[j + 2]), __uint_as_float(y[j + 2]));
+                  m3 = max3(m3, __uint_as_float(x[j + 3]), __uint_as_float(y[j + 3]));
+                }
+              };
+              tmem_ld_32(t_row, a0);
+              tmem_ld_32(t_row + 32, a1);
+              tmem_ld_wait();
+              tmem_ld_32(t_row + 64, b0);
+              tmem_ld_32(t_row + 96, b1);
+              max64(a0, a1);
+              tmem_ld_wait();
+              tmem_ld_32(t_row + 128, a0);
+              tmem_ld_32(t_row + 160, a1);
+              max64(b0, b1);
+              tmem_ld_wait();
+              tmem_ld_32(t_row + 192, b0);
+              tmem_ld_32(t_row + 224, b1);
+              max64(a0, a1);
+              tmem_ld_wait();
+              max64(b0, b1);
+            }
+            mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
+            if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 5);
+            // pass 2: p = 2^(s c - max c), row sums, bf16 P over the consumed S columns.  A ROLLED loop of two
+            // 32-column chunks (the fully unrolled form spent a third of its cycles waiting for instruction fetch,
+            // stall_no_inst in profiles/r02_ncu_attn_pp_source.txt: two softmax warps per scheduler stream through
+            // different code); the TMEM load of the next chunk is in flight under the current chunk's exponentials.
+            {
+              uint32_t ra[32], rb[32];
+              const float c = p.scale_log2;
+              auto chunk32 = [&](const uint32_t (&r)[32], uint32_t col) {
+                float e[32];
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[j] = ex2_ftz(fmaf(__uint_as_float(r[j]), c, -mxs));
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  s0 += e[j]; s1 += e[j + 1]; s2 += e[j + 2]; s3 += e[j + 3];
+                  pk[j / 2] = pack_bf16x2(e[j], e[j + 1]);
+                  pk[j / 2 + 1] = pack_bf16x2(e[j + 2], e[j + 3]);
+                }
+                tmem_st_16(t_row + col, pk);  // P columns alias S columns of an earlier chunk: consumed
+              };
+              tmem_ld_32(t_row, ra);
+              tmem_ld_wait();
+#pragma unroll 1
+              for (int i = 0; i < 4; ++i) {
+                tmem_ld_32(t_row + (2 * i + 1) * 32, rb);
+                chunk32(ra, (2 * i) * 16);
+                tmem_ld_wait();
+                if (i < 3) tmem_ld_32(t_row + (2 * i + 2) * 32, ra);
+                chunk32(rb, (2 * i + 1) * 16);
+                tmem_ld_wait();
+              }
+            }
+          } else {
+            // ---- pass 1: row maximum (two 32-column loads in flight)
+            float m0 = tail, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+              uint32_t r0[32], r1[32];
+              const bool two = ch + 1 < n_chunks;
+              tmem_ld_32(t_row + ch * 32, r0);
+              if (two) tmem_ld_32(t_row + (ch + 1) * 32, r1);
+              tmem_ld_wait();
+              if (ch * 32 + 32 <= s_main) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  m0 = fmaxf(m0, __uint_as_float(r0[j]));
+                  m1 = fmaxf(m1, __uint_as_float(r0[j + 1]));
+                  m2 = fmaxf(m2, __uint_as_float(r0[j + 2]));
+                  m3 = fmaxf(m3, __uint_as_float(r0[j + 3]));
                 }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (ch * 32 + 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r1[j]));
+                  if (ch * 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r0[j]));
+              }
+              if (two) {
+                if (ch * 32 + 64 <= s_main) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(r1[j]));
+                    m1 = fmaxf(m1, __uint_as_float(r1[j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(r1[j + 2]));
+                    m3 = fmaxf(m3, __uint_as_float(r1[j + 3]));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (ch * 32 + 32 + j < s_main) m0 = fmaxf(m0, __uint_as_float(r1[j]));
+                }
               }
             }
-          }
-          const float mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
-          // ---- pass 2: p = 2^(s*c - max*c), row sum, bf16 P over the consumed S columns; the load of
-          // chunk ch+1 is in flight while chunk ch is exponentiated
-          float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-          auto chunk = [&](const uint32_t (&r)[32], int ch) {
-            uint32_t pk[16];
-            if (ch * 32 + 32 <= s_main) {
+            mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
+            if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 5);
+            // ---- pass 2: p = 2^(s*c - max*c), row sum, bf16 P over the consumed S columns; the load of
+            // chunk ch+1 is in flight while chunk ch is exponentiated
+            auto chunk = [&](const uint32_t (&r)[32], int ch) {
+              uint32_t pk[16];
+              if (ch * 32 + 32 <= s_main) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs));
-                const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs));
-                const float p2 = exp2f(fmaf(__uint_as_float(r[2 * j + 2]), p.scale_log2, -mxs));
-                const float p3 = exp2f(fmaf(__uint_as_float(r[2 * j + 3]), p.scale_log2, -mxs));
-                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-                pk[j] = pack_bf16x2(p0, p1);
-                pk[j + 1] = pack_bf16x2(p2, p3);
-              }
-            } else {
+                for (int j = 0; j < 16; j += 2) {
+                  const float p0 = exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs));
+                  const float p1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs));
+                  const float p2 = exp2f(fmaf(__uint_as_float(r[2 * j + 2]), p.scale_log2, -mxs));
+                  const float p3 = exp2f(fmaf(__uint_as_float(r[2 * j + 3]), p.scale_log2, -mxs));
+                  s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                  pk[j] = pack_bf16x2(p0, p1);
+                  pk[j + 1] = pack_bf16x2(p2, p3);
+                }
+              } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int k0 = ch * 32 + 2 * j;
-                const float p0 = k0 < s_main ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs)) : 0.0f;
-                const float p1 = k0 + 1 < s_main ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs)) : 0.0f;
-                s0 += p0; s1 += p1;
-                pk[j] = pack_bf16x2(p0, p1);
+                for (int j = 0; j < 16; ++j) {
+                  const int k0 = ch * 32 + 2 * j;
+                  const float p0 = k0 < s_main ? exp2f(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, -mxs)) : 0.0f;
+                  const float p1 = k0 + 1 < s_main ? exp2f(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, -mxs)) : 0.0f;
+                  s0 += p0; s1 += p1;
+                  pk[j] = pack_bf16x2(p0, p1);
+                }
               }
-            }
-            // P columns [16 ch, 16 ch + 16) alias S columns of chunk ch / 2 <= ch: already consumed
-            tmem_st_16(t_row + ch * 16, pk);
-          };
-          {
-            uint32_t ra[32], rb[32];
-            tmem_ld_32(t_row, ra);
-            for (int ch = 0; ch < n_chunks; ch += 2) {
-              tmem_ld_wait();
-              if (ch + 1 < n_chunks) tmem_ld_32(t_row + (ch + 1) * 32, rb);
-              chunk(ra, ch);
-              if (ch + 1 < n_chunks) {
+              // P columns [16 ch, 16 ch + 16) alias S columns of chunk ch / 2 <= ch: already consumed
+              tmem_st_16(t_row + ch * 16, pk);
+            };
+            {
+              uint32_t ra[32], rb[32];
+              tmem_ld_32(t_row, ra);
+              for (int ch = 0; ch < n_chunks; ch += 2) {
                 tmem_ld_wait();
-                if (ch + 2 < n_chunks) tmem_ld_32(t_row + (ch + 2) * 32, ra);
-                chunk(rb, ch + 1);
+                if (ch + 1 < n_chunks) tmem_ld_32(t_row + (ch + 1) * 32, rb);
+                chunk(ra, ch);
+                if (ch + 1 < n_chunks) {
+                  tmem_ld_wait();
+                  if (ch + 2 < n_chunks) tmem_ld_32(t_row + (ch + 2) * 32, ra);
+                  chunk(rb, ch + 1);
+                }
               }
             }
           }
@@ -820,53 +990,103 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[wg]);
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 6);
         // ---- epilogue: O * 1/sum -> global
         mbar_wait(&o_full[wg], o_ph);
         o_ph ^= 1u;
         tc_fence_after();
-        if (warp_has_rows) {
-          __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.s + qi) * p.o_rs + h * p.d;
-          for (int gi = 0; gi < n16; gi += 2) {
-            uint32_t r0[16], r1[16];
-            const bool two = gi + 1 < n16;
-            tmem_ld_16(t_row + kPpColO + gi * 16, r0);
-            if (two) tmem_ld_16(t_row + kPpColO + (gi + 1) * 16, r1);
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 7);
+        if ((p.flags & 2) != 0) {
+          // ---- O through shared memory and ONE bulk tensor store per tile.  (Row-per-thread 16-byte global stores
+          // touch 32 lines per instruction: 1 408 LSU wavefronts per tile, ~3 800 clk of epilogue in the round-1
+          // trace.)  All of O is pulled into registers first so that the TMEM slot is released before the stores.
+          // the staging tile is shared by both groups; tiles take it in tile order (g), one completion each
+          if (g > 0) mbar_wait(stage_free, static_cast<uint32_t>((g - 1) & 1));
+          uint8_t* srow = sO + r_in_tile * (p.d * 2);
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t ro[3][16];
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi)
+              tmem_ld_16(t_row + kPpColO + (half * 3 + gi) * 16, ro[gi]);  // (columns beyond dpad: unused)
             tmem_ld_wait();
-            if (qi < p.s) {
+            if (half == 1) {
+              tc_fence_before();  // O reads retire before the next QK^T overwrites the slot
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&slot_free[wg]);
+            }
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) {
 #pragma unroll
               for (int j = 0; j < 16; j += 8) {
-                const int c0 = gi * 16 + j;
+                const int c0 = (half * 3 + gi) * 16 + j;
                 if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
                   uint4 u;
-                  u.x = pack_bf16x2(__uint_as_float(r0[j]) * inv_sum, __uint_as_float(r0[j + 1]) * inv_sum);
-                  u.y = pack_bf16x2(__uint_as_float(r0[j + 2]) * inv_sum, __uint_as_float(r0[j + 3]) * inv_sum);
-                  u.z = pack_bf16x2(__uint_as_float(r0[j + 4]) * inv_sum, __uint_as_float(r0[j + 5]) * inv_sum);
-                  u.w = pack_bf16x2(__uint_as_float(r0[j + 6]) * inv_sum, __uint_as_float(r0[j + 7]) * inv_sum);
-                  *reinterpret_cast<uint4*>(orow + c0) = u;
+                  u.x = pack_bf16x2(__uint_as_float(ro[gi][j]) * inv_sum, __uint_as_float(ro[gi][j + 1]) * inv_sum);
+                  u.y = pack_bf16x2(__uint_as_float(ro[gi][j + 2]) * inv_sum, __uint_as_float(ro[gi][j + 3]) * inv_sum);
+                  u.z = pack_bf16x2(__uint_as_float(ro[gi][j + 4]) * inv_sum, __uint_as_float(ro[gi][j + 5]) * inv_sum);
+                  u.w = pack_bf16x2(__uint_as_float(ro[gi][j + 6]) * inv_sum, __uint_as_float(ro[gi][j + 7]) * inv_sum);
+                  *reinterpret_cast<uint4*>(srow + c0 * 2) = u;
                 }
               }
-              if (two) {
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(6 + wg, 128);
+          if (quarter == 0 && lane == 0) {
+            tma_store_4d(&tmap_o, sO, 0, h, t * kTaQRows, b);  // rows beyond S are clipped
+            bulk_commit();
+            bulk_wait_read<0>();
+            mbar_arrive(stage_free);
+          }
+          __syncwarp();
+        } else {
+          if (warp_has_rows) {
+            __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.s + qi) * p.o_rs + h * p.d;
+            for (int gi = 0; gi < n16; gi += 2) {
+              uint32_t r0[16], r1[16];
+              const bool two = gi + 1 < n16;
+              tmem_ld_16(t_row + kPpColO + gi * 16, r0);
+              if (two) tmem_ld_16(t_row + kPpColO + (gi + 1) * 16, r1);
+              tmem_ld_wait();
+              if (qi < p.s) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 8) {
-                  const int c0 = (gi + 1) * 16 + j;
-                  if (c0 < p.d) {
+                  const int c0 = gi * 16 + j;
+                  if (c0 < p.d) {  // d % 8 == 0: whole 16-byte groups
                     uint4 u;
-                    u.x = pack_bf16x2(__uint_as_float(r1[j]) * inv_sum, __uint_as_float(r1[j + 1]) * inv_sum);
-                    u.y = pack_bf16x2(__uint_as_float(r1[j + 2]) * inv_sum, __uint_as_float(r1[j + 3]) * inv_sum);
-                    u.z = pack_bf16x2(__uint_as_float(r1[j + 4]) * inv_sum, __uint_as_float(r1[j + 5]) * inv_sum);
-                    u.w = pack_bf16x2(__uint_as_float(r1[j + 6]) * inv_sum, __uint_as_float(r1[j + 7]) * inv_sum);
+                    u.x = pack_bf16x2(__uint_as_float(r0[j]) * inv_sum, __uint_as_float(r0[j + 1]) * inv_sum);
+                    u.y = pack_bf16x2(__uint_as_float(r0[j + 2]) * inv_sum, __uint_as_float(r0[j + 3]) * inv_sum);
+                    u.z = pack_bf16x2(__uint_as_float(r0[j + 4]) * inv_sum, __uint_as_float(r0[j + 5]) * inv_sum);
+                    u.w = pack_bf16x2(__uint_as_float(r0[j + 6]) * inv_sum, __uint_as_float(r0[j + 7]) * inv_sum);
                     *reinterpret_cast<uint4*>(orow + c0) = u;
+                  }
+                }
+                if (two) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 8) {
+                    const int c0 = (gi + 1) * 16 + j;
+                    if (c0 < p.d) {
+                      uint4 u;
+                      u.x = pack_bf16x2(__uint_as_float(r1[j]) * inv_sum, __uint_as_float(r1[j + 1]) * inv_sum);
+                      u.y = pack_bf16x2(__uint_as_float(r1[j + 2]) * inv_sum, __uint_as_float(r1[j + 3]) * inv_sum);
+                      u.z = pack_bf16x2(__uint_as_float(r1[j + 4]) * inv_sum, __uint_as_float(r1[j + 5]) * inv_sum);
+                      u.w = pack_bf16x2(__uint_as_float(r1[j + 6]) * inv_sum, __uint_as_float(r1[j + 7]) * inv_sum);
+                      *reinterpret_cast<uint4*>(orow + c0) = u;
+                    }
                   }
                 }
               }
             }
           }
+          tc_fence_before();  // O reads retire before the next QK^T overwrites the slot
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_free[wg]);
         }
-        tc_fence_before();  // O reads retire before the next QK^T overwrites the slot
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_free[wg]);
+        if (quarter == 0 && lane == 0) PP_TRACE(1 + wg, 8);
       }
     }
+    if (quarter == 0 && lane == 0) PP_TRACE_END(1 + wg);
   }
 
   tc_fence_before();
@@ -907,6 +1127,23 @@ bool make_tmap_heads(CUtensorMap* map, const void* ptr, long long rows, long lon
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (frames, tokens, heads, d) view of the output for the staged store: box = d x 1 x 128 x 1 out of a dense
+// [128][d] shared-memory tile, no swizzle; rows beyond a frame's S tokens are clipped.
+static bool make_tmap_o(CUtensorMap* map, const void* ptr, long long frames, long long s, long long heads, long long d,
+                        long long row_stride) {
+  EncodeTiledFn3 fn = encode_fn3();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(s),
+                        static_cast<cuuint64_t>(frames)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d) * 2, static_cast<cuuint64_t>(row_stride) * 2,
+                        static_cast<cuuint64_t>(s * row_stride) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(d), 1, static_cast<cuuint32_t>(kTaQRows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -959,7 +1196,8 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
   if (attention_pp_eligible(a)) {
     static bool attr_pp = false;
     if (!attr_pp) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTaSmem);
+      cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kPpSmemBase + kTaQRows * 96 * 2);  // = 232 448, the 227 KB limit
       if (e != cudaSuccess) return e;
       attr_pp = true;
     }
@@ -984,9 +1222,17 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
       return e != nullptr ? std::atoi(e) : 0;  // measured: no effect (the shared K tile re-aligns the groups)
     }();
     pp.stagger = stagger;
+    static const int flags = [] {
+      const char* e = std::getenv("VB_ATTN_PP_FLAGS");   // A/B measurements: 0 = the round-1 softmax / epilogue
+      return e != nullptr ? std::atoi(e) : 3;
+    }();
+    pp.flags = flags;
+    CUtensorMap to;
+    if (!make_tmap_o(&to, a.o, a.batch, a.sq, a.heads, a.d, a.o_rs)) return cudaErrorInvalidValue;
+    const int smem_pp = kPpSmemBase + kTaQRows * pp.d * 2;
     const int grid_pp = pp.items < sms ? pp.items : sms;
-    return launch_pdl(attn_tcgen05_pp_kernel, dim3(static_cast<unsigned>(grid_pp)), dim3(kTaThreads), kTaSmem, stream,
-                      tq, tk, tv, pp);
+    return launch_pdl(attn_tcgen05_pp_kernel, dim3(static_cast<unsigned>(grid_pp)), dim3(kTaThreads), smem_pp, stream,
+                      tq, tk, tv, to, pp);
   }
   TaParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(a.o);
@@ -1004,3 +1250,18 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
 }
 
 }  // namespace vb
+
+#ifdef VB_PP_TRACE
+extern "C" int vb_debug_pp_trace(long long* host_out, int* host_n, int reset) {
+  int e = 0;
+  if (host_out != nullptr) {
+    e |= static_cast<int>(cudaMemcpyFromSymbol(host_out, vb::g_pp_trace, sizeof(vb::g_pp_trace)));
+    e |= static_cast<int>(cudaMemcpyFromSymbol(host_n, vb::g_pp_trace_n, sizeof(vb::g_pp_trace_n)));
+  }
+  if (reset != 0) {
+    int z[3] = {0, 0, 0};
+    e |= static_cast<int>(cudaMemcpyToSymbol(vb::g_pp_trace_n, z, sizeof(z)));
+  }
+  return e;
+}
+#endif
