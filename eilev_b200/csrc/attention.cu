@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
 template <int DP>
 static cudaError_t launch_fwd(const AttnParams& p, int batch, cudaStream_t stream) {
   constexpr int smem = 5 * 64 * (DP + 8) * 2;
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -706,7 +707,8 @@ template <int DP>
 static cudaError_t launch_bwd(const AttnBwdParams& bp, int batch, cudaStream_t stream) {
   constexpr int smem = (4 * 64 * (DP + 8) + 2 * 64 * 72) * 2;
   constexpr int smem_keep = smem + 2 * 64 * (DP + 8) * 2;  // + the second K / V buffers
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<DP, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -823,19 +823,11 @@ bool attention_bwd_tcgen05_eligible(const vb_attn_bwd_args& a) {
   return true;
 }
 
-static int fa_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int fa_sm_count() { return device_sm_count(); }
 
 static cudaError_t fa_set_attrs() {
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once();
   if (attr) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(attn_flash_tc_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem);
   if (e == cudaSuccess)

@@ -1118,6 +1118,10 @@ static EncodeTiledFn3 encode_fn3() {
 // (rows, heads, d) view of a (rows, >= heads*d) bf16 buffer; box = 64 x 1 x box_rows.
 bool make_tmap_heads(CUtensorMap* map, const void* ptr, long long rows, long long heads,
                             long long d, long long row_stride, int box_rows) {
+  const TmapKey key = {{3ull, reinterpret_cast<unsigned long long>(ptr), static_cast<unsigned long long>(rows),
+                        static_cast<unsigned long long>(heads), static_cast<unsigned long long>(d),
+                        static_cast<unsigned long long>(row_stride), static_cast<unsigned long long>(box_rows), 0ull}};
+  if (tmap_cache_lookup(key, map)) return true;
   EncodeTiledFn3 fn = encode_fn3();
   if (fn == nullptr) return false;
   cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(heads),
@@ -1125,15 +1129,21 @@ bool make_tmap_heads(CUtensorMap* map, const void* ptr, long long rows, long lon
   cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d) * 2, static_cast<cuuint64_t>(row_stride) * 2};
   cuuint32_t box[3] = {64, 1, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[3] = {1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const bool ok = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (ok) tmap_cache_store(key, *map);
+  return ok;
 }
 
 // (frames, tokens, heads, d) view of the output for the staged store: box = d x 1 x 128 x 1 out of a dense
 // [128][d] shared-memory tile, no swizzle; rows beyond a frame's S tokens are clipped.
 static bool make_tmap_o(CUtensorMap* map, const void* ptr, long long frames, long long s, long long heads, long long d,
                         long long row_stride) {
+  const TmapKey key = {{4ull, reinterpret_cast<unsigned long long>(ptr), static_cast<unsigned long long>(frames),
+                        static_cast<unsigned long long>(s), static_cast<unsigned long long>(heads),
+                        static_cast<unsigned long long>(d), static_cast<unsigned long long>(row_stride), 0ull}};
+  if (tmap_cache_lookup(key, map)) return true;
   EncodeTiledFn3 fn = encode_fn3();
   if (fn == nullptr) return false;
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(s),
@@ -1142,9 +1152,11 @@ static bool make_tmap_o(CUtensorMap* map, const void* ptr, long long frames, lon
                         static_cast<cuuint64_t>(s * row_stride) * 2};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(d), 1, static_cast<cuuint32_t>(kTaQRows), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const bool ok = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (ok) tmap_cache_store(key, *map);
+  return ok;
 }
 
 bool attention_tcgen05_eligible(const vb_attn_args& a) {
@@ -1180,21 +1192,17 @@ cudaError_t attention_tcgen05_launch(const vb_attn_args& a, cudaStream_t stream)
   if (!make_tmap_heads(&tq, a.q, rows, a.heads, a.d, a.q_rs, kTaQRows)) return cudaErrorInvalidValue;
   if (!make_tmap_heads(&tk, a.k, rows, a.heads, a.d, a.k_rs, kTaHalf)) return cudaErrorInvalidValue;
   if (!make_tmap_heads(&tv, a.v, rows, a.heads, a.d, a.v_rs, kTaHalf)) return cudaErrorInvalidValue;
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTaSmem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   if (attention_pp_eligible(a)) {
-    static bool attr_pp = false;
+    static DeviceOnce attr_pp_once;
+  bool& attr_pp = attr_pp_once();
     if (!attr_pp) {
       cudaError_t e = cudaFuncSetAttribute(attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kPpSmemBase + kTaQRows * 96 * 2);  // = 232 448, the 227 KB limit

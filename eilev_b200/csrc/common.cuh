@@ -309,6 +309,44 @@ VB_DEVICE float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------- tensor-map cache
+// cuTensorMapEncodeTiled costs about a microsecond of host time per map and an eager launch needs two to four of
+// them (CUDA graphs hide it, short generate() calls and beam search run eagerly).  A map is a pure function of
+// (address, extents, strides, box), so a small direct-mapped table of the last encodings is always valid.
+struct TmapKey {
+  unsigned long long w[8];
+  bool operator==(const TmapKey& o) const {
+    for (int i = 0; i < 8; ++i)
+      if (w[i] != o.w[i]) return false;
+    return true;
+  }
+};
+bool tmap_cache_lookup(const TmapKey& key, CUtensorMap* out);   // gemm_tcgen05.cu
+void tmap_cache_store(const TmapKey& key, const CUtensorMap& map);
+
+// ---------------------------------------------------------------- per-device launch-time state
+// One process may drive several devices: function attributes (dynamic shared memory opt-in) are per device, and
+// so is the SM count a persistent grid is sized by.  (Round 1 kept these in per-process statics.)
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct DeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool& operator()() { return done[current_device()]; }
+};
+inline int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int d = current_device();
+  if (sms[d] == 0) {
+    cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+    if (sms[d] <= 0) sms[d] = 148;
+  }
+  return sms[d];
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
 // serialization attribute may become resident while its predecessor is still running.
 // Everything before pdl_wait() must touch only data no earlier kernel of the stream writes

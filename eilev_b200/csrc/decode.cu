@@ -544,15 +544,7 @@ __global__ void __launch_bounds__(kGW * 32, 2) gemv_mma_kernel(const vb_decode_o
   gemv_finalize<NT, kGW>(p, m, G, psum, threadIdx.x, nullptr, p.bias() != nullptr ? bias_s : nullptr);
 }
 
-static int sm_count() {
-  static const int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    return v;
-  }();
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 // Grid of the stand-alone tensor-core GEMV: two CTAs per SM when x + the partial-tile table
 // fit, more waves of smaller ranges otherwise; 0 = shape not taken.
@@ -583,7 +575,8 @@ static long long gemv_mma_grid(int nt, long long m, long long n, long long k, bo
 template <int NT>
 static cudaError_t launch_gemv_mma(const vb_decode_op& op, int m, long long grid, size_t smem, int rbmax,
                                    cudaStream_t s) {
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
@@ -1240,7 +1233,8 @@ cudaError_t decode_step_launch(const vb_decode_op* ops_host, const vb_decode_op*
   if (grid > kWsMaxCtas) return cudaErrorInvalidValue;
   const long long smem = decode_step_smem(ops_host, n_ops, m, grid);
   if (smem < 0 || smem > 200 * 1024) return cudaErrorInvalidValue;
-  static bool attr = false;
+  static DeviceOnce attr_once;
+  bool& attr = attr_once();
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);

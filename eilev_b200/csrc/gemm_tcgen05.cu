@@ -9,6 +9,8 @@
 // The two TMEM accumulator stages let the epilogue of tile i overlap the main loop of
 // tile i+1.  Used for every dense projection of the VideoBLIP path (see
 // include/videoblip_b200.h, vb_gemm).
+#include <mutex>
+
 #include "common.cuh"
 #include "gemm.h"
 #include "gemm_epilogue.cuh"
@@ -219,9 +221,44 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+namespace {
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid = false;
+};
+constexpr int kTmapSlots = 512;
+TmapSlot g_tmap_slots[kTmapSlots];
+std::mutex g_tmap_mutex;
+unsigned tmap_hash(const TmapKey& k) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < 8; ++i) h = (h ^ k.w[i]) * 0xBF58476D1CE4E5B9ull + (h >> 29);
+  return static_cast<unsigned>(h >> 40) % kTmapSlots;
+}
+}  // namespace
+
+bool tmap_cache_lookup(const TmapKey& key, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  const TmapSlot& s = g_tmap_slots[tmap_hash(key)];
+  if (!s.valid || !(s.key == key)) return false;
+  *out = s.map;
+  return true;
+}
+void tmap_cache_store(const TmapKey& key, const CUtensorMap& map) {
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  TmapSlot& s = g_tmap_slots[tmap_hash(key)];
+  s.key = key;
+  s.map = map;
+  s.valid = true;
+}
+
 // (rows, cols) bf16 row-major matrix with row stride ld; box = 64 columns x box_rows rows.
 bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols,
                        long long ld, int box_rows) {
+  const TmapKey key = {{2ull, reinterpret_cast<unsigned long long>(ptr), static_cast<unsigned long long>(rows),
+                        static_cast<unsigned long long>(cols), static_cast<unsigned long long>(ld),
+                        static_cast<unsigned long long>(box_rows), 0ull, 0ull}};
+  if (tmap_cache_lookup(key, map)) return true;
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -231,6 +268,7 @@ bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long l
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_cache_store(key, *map);
   return r == CUDA_SUCCESS;
 }
 
@@ -284,7 +322,8 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
     if (!make_tmap_bf16_2d(&ta, a.a, a.k, a.m, a.lda, kBK)) return cudaErrorInvalidValue;
     if (!make_tmap_bf16_2d(&tb, a.b, a.k, a.n, a.ldb, kBK)) return cudaErrorInvalidValue;
   }
-  static bool attr_set = false;
+  static DeviceOnce attr_set_once;
+  bool& attr_set = attr_set_once();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -294,17 +333,7 @@ static cudaError_t launch_bn(const vb_gemm_args& a, const EpiParams& ep, cudaStr
   const int m_tiles = static_cast<int>((a.m + kBM - 1) / kBM);
   const int n_tiles = static_cast<int>((a.n + BN - 1) / BN);
   const int k_blocks = static_cast<int>((a.k + kBK - 1) / kBK);
-  int sms = 148;
-  {
-    static int cached = 0;
-    if (cached == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-      if (cached <= 0) cached = 148;
-    }
-    sms = cached;
-  }
+  const int sms = device_sm_count();
   long long tiles = static_cast<long long>(m_tiles) * n_tiles;
   int grid = static_cast<int>(tiles < sms ? tiles : sms);
   if (force_grid > 0 && force_grid < grid) grid = force_grid;

@@ -323,16 +323,7 @@ bool make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long long rows, long l
                        long long ld, int box_rows);
 void fill_epi_params(EpiParams& ep, const vb_gemm_args& a);
 
-static int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 // tn: tile width, a multiple of 16 in [32, 256]
 cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int tn, cudaStream_t stream) {
@@ -342,7 +333,8 @@ cudaError_t gemm_tcgen05_2cta_launch(const vb_gemm_args& a, int tn, cudaStream_t
   CUtensorMap ta, tb;
   if (!make_tmap_bf16_2d(&ta, a.a, a.m, a.k, a.lda, k2BM)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_2d(&tb, a.b, a.n, a.k, a.ldb, tn / 2)) return cudaErrorInvalidValue;
-  static bool attr_set = false;
+  static DeviceOnce attr_set_once;
+  bool& attr_set = attr_set_once();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<BN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
