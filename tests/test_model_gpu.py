@@ -755,3 +755,38 @@ def test_greedy_generate_with_device_side_bookkeeping_equals_the_python_loop(kw)
     got_e = m.generate(**gi, eos_token_id=eos, **kw)
     assert torch.equal(got_e, want_e), (got_e.tolist(), want_e.tolist())
 
+
+
+def test_torch_ddp_wrap_returns_the_same_gradients(tmp_path):
+    """HF Trainer (scripts/general/train_v2.py:169-190) wraps the model in torch DistributedDataParallel when
+    launched on several GPUs: the Q-Former gradients leave our hand-written backward through ONE autograd
+    Function, so DDP's per-parameter hooks must still fire (bucketed all-reduce, here over a 1-rank NCCL
+    group) and hand back exactly the gradients of the unwrapped model."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    fx, cfg = load("small_opt")
+
+    def frozen(m):
+        for p in m.vision_model.parameters():
+            p.requires_grad = False
+        for p in m.language_model.parameters():
+            p.requires_grad = False
+        return m
+
+    plain = frozen(build(cfg, fx["state_dict"])).eval()   # eval(): no dropout, so both runs see the same function
+    plain(**cuda(fx["inputs"]), return_dict=True).loss.backward()
+    want = {n: p.grad.clone() for n, p in plain.named_parameters() if p.grad is not None}
+    assert want
+    dist.init_process_group("nccl", init_method=f"file://{tmp_path}/rendezvous", rank=0, world_size=1)
+    try:
+        wrapped = DDP(frozen(build(cfg, fx["state_dict"])).eval(), device_ids=[0])
+        out = wrapped(**cuda(fx["inputs"]), return_dict=True)
+        out.loss.backward()
+        got = {n: p.grad for n, p in wrapped.module.named_parameters() if p.grad is not None}
+        assert set(got) == set(want)
+        worst = max(max_abs(got[n], want[n]) for n in want)
+        _dump("ddp_wrap/small_opt", n=len(got), worst_abs_diff=worst)
+        for n in want:   # same kernels; only the mma.sync attention backward's fp32 atomics may reorder sums
+            assert rel_l2(got[n], want[n]) < 1e-3 or max_abs(got[n], want[n]) < 1e-6, (n, rel_l2(got[n], want[n]))
+    finally:
+        dist.destroy_process_group()
