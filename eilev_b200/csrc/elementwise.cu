@@ -662,10 +662,20 @@ cudaError_t adamw_launch(float* p, const float* g, float* m, float* v, long long
   return cudaGetLastError();
 }
 
+// Sum of squares of the flat gradient buffer (global-norm clipping).  DETERMINISTIC: every data-parallel rank must
+// derive the same clip coefficient from the same all-reduced gradient, or the replicas drift apart by an ulp per
+// step (an fp32 atomicAdd per block made the result depend on block arrival order).  Blocks write their partial sums
+// to a fixed slot; the last block to arrive (ticket) adds them up in slot order.  One launch at a time per device
+// (the optimizer step's only user).
+constexpr int kSumsqMaxBlocks = 148 * 4;
+__device__ float g_sumsq_part[kSumsqMaxBlocks];
+__device__ unsigned int g_sumsq_ticket;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* x, long long n, float* out) {
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
   __shared__ float red[8];
+  __shared__ int s_last;
   float acc = 0.0f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -677,13 +687,34 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* x, long long n,
     float t = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i];
-    atomicAdd(out, t);
+    g_sumsq_part[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&g_sumsq_ticket, 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last != 0) {
+    __threadfence();
+    // fixed order: thread t adds slots t, t + 256, ...; then the same warp / block tree as above
+    float v = 0.0f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) v += __ldcg(&g_sumsq_part[i]);
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i];
+      *out += t;            // the caller zeroes `out`; single writer
+      g_sumsq_ticket = 0;   // ready for the next launch / graph replay
+    }
   }
 }
 
 cudaError_t sumsq_launch(const float* x, long long n, float* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 4 ? n / 256 + 1 : 148 * 4);
+  const unsigned grid = static_cast<unsigned>(n / 256 + 1 < kSumsqMaxBlocks ? n / 256 + 1 : kSumsqMaxBlocks);
   launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, s, x, n, out);
   return cudaGetLastError();
 }

@@ -585,6 +585,19 @@ def test_adamw_matches_torch():
     acc = torch.zeros((), device="cuda")
     ops.sumsq(p, acc)
     assert abs(acc.item() - (p.double() ** 2).sum().item()) < 1e-2 * acc.item()
+    # the global-norm reduction is deterministic (data-parallel replicas must derive the same clip coefficient):
+    # a large buffer, repeated launches, accumulation into a non-zero `out`
+    big = torch.randn(3_000_001, device="cuda")
+    first = None
+    for _ in range(20):
+        acc = torch.zeros((), device="cuda")
+        ops.sumsq(big, acc)
+        first = acc.clone() if first is None else first
+        assert torch.equal(acc, first), (acc.item(), first.item())
+    assert abs(first.item() - (big.double() ** 2).sum().item()) < 1e-5 * first.item()
+    acc = torch.full((), 5.0, device="cuda")
+    ops.sumsq(p, acc)
+    assert abs(acc.item() - 5.0 - (p.double() ** 2).sum().item()) < 1e-4 * acc.item()
 
 
 def test_gemv_and_paged_decode():
