@@ -20,6 +20,14 @@ template <> struct Ld<32> {
   }
 };
 
+DEV void st16(uint32_t a, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(a),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+               "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+DEV float ex2f_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+DEV uint32_t packbf(float lo, float hi) { uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+
 template <int mode>
 __global__ void __launch_bounds__(384, 1) tmem_read_kernel(int warps, int iters, long long* out, float* sink) {
   __shared__ uint32_t slot;
@@ -32,7 +40,7 @@ __global__ void __launch_bounds__(384, 1) tmem_read_kernel(int warps, int iters,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t base = slot;
-  float acc = 0.f;
+  float acc = 0.f, acc2 = 0.f;
   long long t0 = 0, t1 = 0;
   if (warp >= 4 && warp < 4 + warps) {
     const int quarter = warp & 3, half = (warp - 4) >> 2;
@@ -57,6 +65,26 @@ __global__ void __launch_bounds__(384, 1) tmem_read_kernel(int warps, int iters,
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           acc += __uint_as_float(r[0]) + __uint_as_float(r[31]) + __uint_as_float(q[3]) + __uint_as_float(q[30]);
         }
+      } else if (mode == 3) {   // the softmax exp pass without the math: load x32, wait, store x16 (P in place)
+        for (int c = c0; c < c1; c += 32) {
+          uint32_t r[32], pk[16];
+          Ld<32>::go(row + c, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          for (int j = 0; j < 16; ++j) pk[j] = r[2 * j] ^ r[2 * j + 1];
+          st16(row + c / 2, pk);
+        }
+      } else if (mode == 4) {   // the softmax exp pass: load x32, wait, 32 x (fma, ex2, add) + 16 packs, store x16
+        for (int c = c0; c < c1; c += 32) {
+          uint32_t r[32], pk[16];
+          Ld<32>::go(row + c, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2f_(fmaf(__uint_as_float(r[j]), 1.0001f, -0.5f)), p1 = ex2f_(fmaf(__uint_as_float(r[j + 1]), 1.0001f, -0.5f));
+            acc += p0; acc2 += p1;
+            pk[j / 2] = packbf(p0, p1);
+          }
+          st16(row + c / 2, pk);
+        }
       } else {                  // four x32 loads in flight per wait
         for (int c = c0; c < c1; c += 128) {
           uint32_t r[32], q[32], s[32], u[32];
@@ -72,7 +100,7 @@ __global__ void __launch_bounds__(384, 1) tmem_read_kernel(int warps, int iters,
     asm volatile("bar.sync 1, %0;\n" ::"r"(warps * 32) : "memory");
     t1 = clock64();
     if (threadIdx.x == 128 && blockIdx.x == 0) out[0] = (t1 - t0);
-    sink[blockIdx.x * 384 + threadIdx.x] = acc;
+    sink[blockIdx.x * 384 + threadIdx.x] = acc + acc2;
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -105,6 +133,15 @@ int main() {
   long long* out; float* sink;
   cudaMalloc(&out, 8); cudaMalloc(&sink, 148 * 384 * 4);
   const int iters = 200;
+  for (int warps : {4, 8}) for (int mode : {3, 4}) {
+    long long h = 0;
+    if (mode == 3) tmem_read_kernel<3><<<148, 384>>>(warps, iters, out, sink);
+    else tmem_read_kernel<4><<<148, 384>>>(warps, iters, out, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+    printf("%s warps=%d : %.1f clk per 128x256 tile  [%s]\n", mode == 3 ? "ld x32 + wait + st x16         " : "ld x32 + wait + exp math + st x16", warps,
+           double(h) / iters, cudaGetErrorString(e));
+  }
   for (int warps : {4, 8}) for (int mode : {0, 1, 2}) {
     long long h = 0;
     if (mode == 0) tmem_read_kernel<0><<<148, 384>>>(warps, iters, out, sink);
