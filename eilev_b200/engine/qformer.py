@@ -286,7 +286,7 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor, 
     # ---- cross K/V projections of every cross layer in one wgrad GEMM
     if d_ckv is not None:
         d_ckv2 = d_ckv.view(n * skv, -1)
-        dw = ops.gemm(T(d_ckv2), T(ctx["img2"]), out_dtype=torch.float32)  # (n_cross*2*Dq, Dv)
+        dw = ops.gemm_tn(d_ckv2, ctx["img2"], out_dtype=torch.float32)  # (n_cross*2*Dq, Dv)
         dbias = ops.colsum(d_ckv2)
         for i, lw in enumerate(w["layers"]):
             if lw["cross"] is None:

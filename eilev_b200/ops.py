@@ -109,7 +109,9 @@ def gemm_tn(dy: torch.Tensor, x: torch.Tensor, *, out: torch.Tensor | None = Non
     m, n, k = dy.shape[1], x.shape[1], dy.shape[0]
     ok = (m % 8 == 0 and n % 8 == 0 and dy.stride(1) == 1 and x.stride(1) == 1 and dy.stride(0) % 8 == 0
           and x.stride(0) % 8 == 0 and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0
-          and k <= 8192  # long reductions (the cross-K|V weight gradient over 34 952 tokens) keep the CTA-pair kernel
+          # (VB_GEMM_TN_MAXK: A/B knob; long reductions such as the cross-K|V weight gradient over 34 952 tokens
+          # used to keep two transposes + the CTA-pair kernel: 0.5 ms per step slower, 740 MB of scratch)
+          and k <= int(os.environ.get("VB_GEMM_TN_MAXK", str(1 << 30)))
           and os.environ.get("VB_GEMM_TN", "1") != "0")
     if not ok:
         return gemm(transpose(dy), transpose(x), out=out, beta=beta, out_dtype=out_dtype)
