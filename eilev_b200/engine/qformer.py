@@ -225,7 +225,9 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor, 
     g.bias("language_projection.bias", d_feats)
     dx = ops.gemm(d_feats, w["proj_wt"])
 
-    d_ckv = torch.zeros_like(ctx["ckv"]) if ctx["ckv"] is not None else None
+    # every cross layer's attention backward WRITES its dK / dV slice (plain stores, no accumulation) and the slices
+    # tile the buffer: no 644 MB zero fill per micro-step
+    d_ckv = torch.empty_like(ctx["ckv"]) if ctx["ckv"] is not None else None
     n_layers = len(w["layers"])
     for i in range(n_layers - 1, -1, -1):
         lw, s = w["layers"][i], ctx["saved"][i]
