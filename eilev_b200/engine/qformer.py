@@ -188,6 +188,38 @@ class _GradOut(dict):
         else:
             self[name] = ops.colsum(dy)
 
+    def _fused_view(self, names):
+        """One (sum of rows, cols) view over the sink gradients of `names` if they sit back to back in the trainer's
+        flat buffer (query / key / value weights do: FlatBuffers keeps the parameter order inside its decay and
+        no-decay segments), else None."""
+        dsts = [self.sink.get(n) for n in names]
+        if any(d is None or not d.is_contiguous() for d in dsts):
+            return None
+        for a, b in zip(dsts, dsts[1:]):
+            if b.data_ptr() != a.data_ptr() + a.numel() * a.element_size() or b.shape[1:] != a.shape[1:]:
+                return None
+        first = dsts[0]
+        rows = sum(d.shape[0] for d in dsts)
+        if first.dim() == 1:
+            return torch.as_strided(first, (rows,), (1,))
+        return torch.as_strided(first, (rows, first.shape[1]), (first.stride(0), 1))
+
+    def weights_fused(self, names, dy: torch.Tensor, x: torch.Tensor) -> bool:
+        """The weight gradients of a fused projection (dy: (tokens, sum of N_out)) straight into their adjacent sink
+        views with ONE accumulating GEMM; False (nothing done) when the views are not adjacent."""
+        out = self._fused_view(names)
+        if out is None or out.shape[0] != dy.shape[1]:
+            return False
+        ops.gemm_tn(dy, x, out=out, beta=1.0)
+        return True
+
+    def biases_fused(self, names, dy: torch.Tensor) -> bool:
+        out = self._fused_view(names)
+        if out is None or out.shape[0] != dy.shape[1]:
+            return False
+        ops.colsum(dy, out=out)
+        return True
+
     def ln(self, wname: str, bname: str, cols: int):
         """(dgamma, dbeta) buffers for vb_layernorm_bwd, which accumulates into them."""
         dg, db = self.sink.get(wname), self.sink.get(bname)
@@ -278,11 +310,15 @@ def qformer_backward(model, cache: PackCache, ctx: dict, d_feats: torch.Tensor, 
                           d_ctx, heads, scale, dq=dqkv[:, :, :dq], dk=dqkv[:, :, dq:2 * dq],
                           dv=dqkv[:, :, 2 * dq:], dropout=_drop(p_a, seed, i, 0))
         dqkv2 = dqkv.view(rows, 3 * dq)
-        dw = _wgrad(dqkv2, s["x"])
-        dbias = ops.colsum(dqkv2)
-        for j, nm in enumerate(("query", "key", "value")):
-            g[p + f"attention.attention.{nm}.weight"] = dw[j * dq:(j + 1) * dq]
-            g[p + f"attention.attention.{nm}.bias"] = dbias[j * dq:(j + 1) * dq]
+        qkv_names = [p + f"attention.attention.{nm}" for nm in ("query", "key", "value")]
+        if not g.weights_fused([nm + ".weight" for nm in qkv_names], dqkv2, s["x"]):
+            dw = _wgrad(dqkv2, s["x"])
+            for j, nm in enumerate(qkv_names):
+                g[nm + ".weight"] = dw[j * dq:(j + 1) * dq]
+        if not g.biases_fused([nm + ".bias" for nm in qkv_names], dqkv2):
+            dbias = ops.colsum(dqkv2)
+            for j, nm in enumerate(qkv_names):
+                g[nm + ".bias"] = dbias[j * dq:(j + 1) * dq]
         dx = ops.gemm(dqkv2, lw["qkv_wt"], residual=ds1)
 
     # ---- cross K/V projections of every cross layer in one wgrad GEMM

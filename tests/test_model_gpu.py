@@ -649,6 +649,16 @@ def test_trainer_graphs_and_inplace_grad_accumulation_match_plain_autograd():
     tr = DataParallelTrainer(tr_model, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0, grad_accum=2)
     tr.capture_graph(batch)
     names = [n for n, p in ref.named_parameters() if p.requires_grad]
+    # the q / k / v weight (and bias) gradients of a layer sit back to back in the flat buffer, so the fused
+    # projection's wgrad GEMM accumulates into them directly (engine/qformer.py::_GradOut.weights_fused)
+    from eilev_b200.engine import qformer as E_qf
+    sink = {n: p.grad for n, p in E_qf.qformer_param_list(tr_model) if p.requires_grad and p.grad is not None}
+    pre = "qformer.encoder.layer.0.attention.attention."
+    gout = E_qf._GradOut(sink, torch.device("cuda"))
+    wv = gout._fused_view([pre + f"{nm}.weight" for nm in ("query", "key", "value")])
+    bv = gout._fused_view([pre + f"{nm}.bias" for nm in ("query", "key", "value")])
+    assert wv is not None and wv.shape[0] == 3 * sink[pre + "query.weight"].shape[0]
+    assert bv is not None and bv.data_ptr() == sink[pre + "query.bias"].data_ptr()
 
     def ref_micro():
         out = ref(**batch, return_dict=True)
