@@ -521,6 +521,22 @@ class VideoBlipForConditionalGeneration(PreTrainedModel):
 
         trainable = any(p.requires_grad for _, p in E_qf.qformer_param_list(self))
         train = torch.is_grad_enabled() and trainable and pixel_values is not None and labels is not None
+        if torch.is_grad_enabled() and not getattr(self, "_warned_frozen_towers", False):
+            # The reference's recipe freezes the ViT and the LM (scripts/general/train_v2.py:123-130) and this engine
+            # differentiates only what that recipe trains: say so once instead of silently returning no gradient.
+            loose = [n for n, p in self.named_parameters()
+                     if p.requires_grad and (n.startswith("vision_model.") or n.startswith("language_model."))]
+            if loose or (trainable and labels is None):
+                import warnings
+                warnings.warn(
+                    "eilev_b200 computes gradients for the Q-Former, query_tokens and language_projection only, and only "
+                    "through the returned loss (labels=...): "
+                    + (f"{len(loose)} vision_model / language_model parameters have requires_grad=True and will get no "
+                       f"gradient (first: {loose[0]}); " if loose else "")
+                    + ("labels is None, so the logits carry no graph; " if trainable and labels is None else "")
+                    + "freeze the towers as scripts/general/train_v2.py does (eilev_b200.train.freeze_for_recipe).",
+                    stacklevel=2)
+            self._warned_frozen_towers = True   # checked once, on the first grad-enabled call
 
         vision_outputs = None
         query_outputs = None

@@ -800,3 +800,24 @@ def test_torch_ddp_wrap_returns_the_same_gradients(tmp_path):
             assert rel_l2(got[n], want[n]) < 1e-3 or max_abs(got[n], want[n]) < 1e-6, (n, rel_l2(got[n], want[n]))
     finally:
         dist.destroy_process_group()
+
+
+def test_unfrozen_towers_are_reported_once():
+    """Only the recipe's parameters are differentiated (train_v2.py:123-130): a model whose ViT / LM still have
+    requires_grad=True gets a warning on its first grad-enabled forward instead of silently missing gradients."""
+    import warnings
+    fx, cfg = load("tiny_opt")
+    m = build(cfg, fx["state_dict"]).train()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        m(**cuda(fx["inputs"]), return_dict=True)
+        m(**cuda(fx["inputs"]), return_dict=True)
+    msgs = [str(w.message) for w in rec if "eilev_b200 computes gradients" in str(w.message)]
+    assert len(msgs) == 1 and "vision_model / language_model parameters" in msgs[0], msgs
+    from eilev_b200.train import freeze_for_recipe
+    m2 = build(cfg, fx["state_dict"]).train()
+    freeze_for_recipe(m2)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        m2(**cuda(fx["inputs"]), return_dict=True).loss.backward()
+    assert not [w for w in rec if "eilev_b200 computes gradients" in str(w.message)]
