@@ -2,6 +2,8 @@
 // The row is held in registers between the statistics and the normalisation pass
 // (16-byte vector loads) so HBM sees one read and one write per element; a strided
 // multi-pass variant covers shapes that break the vector path (tiny test configs).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -21,14 +23,32 @@ struct LnParams {
   float eps;
 };
 
-// VPL = 16-byte vectors per lane; cols <= VPL*256, cols % 8 == 0.
-template <int VPL>
+// Sum over the threads that share a row: one warp (WPR = 1) or the whole 4-warp block (WPR = 4: wide rows with few
+// of them — OPT's 976 x 2560 — leave one-warp-per-row at 6 warps per SM, each holding the row in 160 registers).
+template <int WPR>
+VB_DEVICE float row_sum(float v, float* red) {
+  v = warp_sum(v);
+  if (WPR == 1) return v;
+  __syncthreads();  // red[] may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < WPR; ++i) t += red[i];
+  return t;
+}
+
+// VPL = 16-byte vectors per thread; cols <= VPL * 256 * WPR, cols % 8 == 0.
+template <int VPL, int WPR>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParams p) {
+  static_assert(WPR == 1 || WPR == kLnWarps, "a row belongs to one warp or to the whole block");
+  __shared__ float red[kLnWarps];
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int lane = WPR == 1 ? (threadIdx.x & 31) : threadIdx.x;   // index of this thread within its row
+  constexpr int kStride = 32 * WPR;
+  const long long row = WPR == 1 ? static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5) : blockIdx.x;
+  if (row >= p.rows) return;   // (WPR = 4: grid == rows, never taken)
   const int nvec = static_cast<int>(p.cols / 8);
   float v[VPL][8];
   float sum = 0.0f;
@@ -36,7 +56,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParam
   const __nv_bfloat16* rr = p.res != nullptr ? p.res + row * p.ldr : nullptr;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * kStride;
     if (vi < nvec) {
       uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
       float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
@@ -57,11 +77,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParam
       for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
     }
   }
-  const float mean = warp_sum(sum) / static_cast<float>(p.cols);
+  const float mean = row_sum<WPR>(sum, red) / static_cast<float>(p.cols);
   float sq = 0.0f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    if (lane + i * 32 < nvec) {
+    if (lane + i * kStride < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = v[i][j] - mean;
@@ -69,7 +89,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParam
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.cols) + p.eps);
+  const float rstd = rsqrtf(row_sum<WPR>(sq, red) / static_cast<float>(p.cols) + p.eps);
   if (lane == 0) {
     if (p.mean != nullptr) p.mean[row] = mean;
     if (p.rstd != nullptr) p.rstd[row] = rstd;
@@ -77,7 +97,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_vec_kernel(const LnParam
   __nv_bfloat16* yr = p.y + row * p.ldy;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * kStride;
     if (vi < nvec) {
       float o[8];
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vi * 8));
@@ -129,7 +149,19 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_generic_kernel(const LnP
 template <int VPL>
 static void launch_vec(const LnParams& p, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>((p.rows + kLnWarps - 1) / kLnWarps);
-  launch_pdl(ln_fwd_vec_kernel<VPL>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  launch_pdl(ln_fwd_vec_kernel<VPL, 1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+}
+template <int VPL>
+static void launch_vec_block(const LnParams& p, cudaStream_t s) {   // one block per row
+  launch_pdl(ln_fwd_vec_kernel<VPL, kLnWarps>, dim3(static_cast<unsigned>(p.rows)), dim3(kLnWarps * 32), 0, s, p);
+}
+// rows of >= 2048 columns (OPT 2560, flan-T5 2048) are split over the block's four warps
+static bool ln_block_per_row(long long rows, long long cols) {
+  static const bool on = [] {
+    const char* e = std::getenv("VB_LN_BLOCK");   // A/B measurements: 0 = one warp per row for every shape
+    return e == nullptr || e[0] != '0';
+  }();
+  return on && cols >= 2048 && cols <= 3 * 8 * 32 * kLnWarps && rows < (1ll << 31);
 }
 
 cudaError_t layernorm_launch(const LnParams& p, cudaStream_t s) {
@@ -138,7 +170,10 @@ cudaError_t layernorm_launch(const LnParams& p, cudaStream_t s) {
   const bool vec = p.cols % 8 == 0 && p.cols <= 12 * 256 && al(p.x) && al(p.y) && al(p.gamma) &&
                    al(p.beta) && p.ldx % 8 == 0 && p.ldy % 8 == 0 &&
                    (p.res == nullptr || (al(p.res) && p.ldr % 8 == 0));
-  if (vec) {
+  if (vec && ln_block_per_row(p.rows, p.cols)) {
+    if (p.cols <= 2 * 8 * 32 * kLnWarps) launch_vec_block<2>(p, s);
+    else launch_vec_block<3>(p, s);
+  } else if (vec) {
     const int vpl = static_cast<int>((p.cols / 8 + 31) / 32);
     if (vpl <= 1) launch_vec<1>(p, s);
     else if (vpl <= 2) launch_vec<2>(p, s);
@@ -211,13 +246,16 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_kernel(const LnBwdPar
 
 // Vectorised variant: the row (g = dy*gamma and xhat) is held in registers between the two
 // reductions and the store, 16-byte loads/stores (cols % 8 == 0, cols <= VPL*256).
-template <int VPL>
+template <int VPL, int WPR>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBwdParams p) {
+  static_assert(WPR == 1 || WPR == kLnWarps, "a row belongs to one warp or to the whole block");
+  __shared__ float red[kLnWarps];
   pdl_wait();     // programmatic dependent launch: results of the preceding kernels are visible from here on
   pdl_trigger();  // the next kernel of the stream may start its prologue
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int lane = WPR == 1 ? (threadIdx.x & 31) : threadIdx.x;   // index of this thread within its row
+  constexpr int kStride = 32 * WPR;
+  const long long row = WPR == 1 ? static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5) : blockIdx.x;
+  if (row >= p.rows) return;   // (WPR = 4: grid == rows, never taken)
   const int nvec = static_cast<int>(p.cols / 8);
   const __nv_bfloat16* dyr = p.dy + row * p.cols;
   const __nv_bfloat16* xr = p.xin + row * p.cols;
@@ -226,7 +264,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBw
   float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * kStride;
     if (vi < nvec) {
       const uint4 ud = *reinterpret_cast<const uint4*>(dyr + vi * 8);
       const uint4 ux = *reinterpret_cast<const uint4*>(xr + vi * 8);
@@ -248,11 +286,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_dx_vec_kernel(const LnBw
       }
     }
   }
-  s1 = warp_sum(s1) / static_cast<float>(p.cols);
-  s2 = warp_sum(s2) / static_cast<float>(p.cols);
+  s1 = row_sum<WPR>(s1, red) / static_cast<float>(p.cols);
+  s2 = row_sum<WPR>(s2, red) / static_cast<float>(p.cols);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
+    const int vi = lane + i * kStride;
     if (vi < nvec) {
       float d[8];
 #pragma unroll
@@ -325,12 +363,17 @@ cudaError_t layernorm_bwd_launch(const LnBwdParams& p, cudaStream_t s) {
   const bool vec = p.cols % 8 == 0 && p.cols <= 12 * 256 && al(p.dy) && al(p.xin) && al(p.dx) &&
                    al(p.gamma) && (p.dx_add == nullptr || al(p.dx_add)) && (p.dx_drop == nullptr || al(p.dx_drop));
   const int vpl = static_cast<int>((p.cols / 8 + 31) / 32);
+  const dim3 row_grid(static_cast<unsigned>(p.rows));
   if (!vec) launch_pdl(ln_bwd_dx_kernel, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
-  else if (vpl <= 1) launch_pdl(ln_bwd_dx_vec_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
-  else if (vpl <= 3) launch_pdl(ln_bwd_dx_vec_kernel<3>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
-  else if (vpl <= 6) launch_pdl(ln_bwd_dx_vec_kernel<6>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
-  else if (vpl <= 10) launch_pdl(ln_bwd_dx_vec_kernel<10>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
-  else launch_pdl(ln_bwd_dx_vec_kernel<12>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (ln_block_per_row(p.rows, p.cols) && p.cols <= 2 * 8 * 32 * kLnWarps)
+    launch_pdl(ln_bwd_dx_vec_kernel<2, kLnWarps>, row_grid, dim3(kLnWarps * 32), 0, s, p);
+  else if (ln_block_per_row(p.rows, p.cols))
+    launch_pdl(ln_bwd_dx_vec_kernel<3, kLnWarps>, row_grid, dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 1) launch_pdl(ln_bwd_dx_vec_kernel<1, 1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 3) launch_pdl(ln_bwd_dx_vec_kernel<3, 1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 6) launch_pdl(ln_bwd_dx_vec_kernel<6, 1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else if (vpl <= 10) launch_pdl(ln_bwd_dx_vec_kernel<10, 1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
+  else launch_pdl(ln_bwd_dx_vec_kernel<12, 1>, dim3(grid), dim3(kLnWarps * 32), 0, s, p);
   if (p.dgamma != nullptr && p.dbeta != nullptr) {
     launch_pdl(ln_bwd_param_kernel, dim3(static_cast<unsigned>((p.cols + 31) / 32)), dim3(1024), 0, s, p);
   }

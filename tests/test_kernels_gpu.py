@@ -241,7 +241,8 @@ def test_gemm_patch_rowgroup():
     assert hidden[:, 0].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("rows,cols", [(1000, 1408), (544, 768), (976, 2560), (37, 8), (64, 100)])
+@pytest.mark.parametrize("rows,cols", [(1000, 1408), (544, 768), (976, 2560), (37, 8), (64, 100),
+                                       (301, 2048), (5, 3072), (3, 2056)])  # >= 2048 columns: one block per row
 def test_layernorm_fwd_bwd(rows, cols):
     ops = _ops()
     x, r = _rand(rows, cols, seed=11), _rand(rows, cols, seed=12)
