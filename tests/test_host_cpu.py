@@ -845,3 +845,47 @@ def test_flan_style_checkpoint_keeps_its_own_head_through_save_and_load(tmp_path
         r = Ref.from_pretrained(tmp_path)
         assert torch.equal(r.language_model.lm_head.weight, sd["language_model.lm_head.weight"])
         assert torch.equal(r.language_model.shared.weight, sd["language_model.shared.weight"])
+
+
+def test_fused_gradient_views_require_adjacent_flat_buffer_slices():
+    """engine/qformer.py::_GradOut._fused_view: the q / k / v gradients of one layer are written by ONE accumulating
+    GEMM only when their sink views sit back to back in the trainer's flat buffer; anything else falls back to
+    per-parameter accumulation."""
+    from eilev_b200.engine.qformer import _GradOut
+    flat = torch.zeros(3 * 8 * 4 + 3 * 8 + 5)
+    wq, wk, wv = (flat[i * 32:(i + 1) * 32].view(8, 4) for i in range(3))
+    bq, bk, bv = (flat[96 + i * 8:96 + (i + 1) * 8] for i in range(3))
+    g = _GradOut({"q.w": wq, "k.w": wk, "v.w": wv, "q.b": bq, "k.b": bk, "v.b": bv, "odd": flat[121:125]},
+                 torch.device("cpu"))
+    w = g._fused_view(["q.w", "k.w", "v.w"])
+    assert w is not None and w.shape == (24, 4) and w.data_ptr() == wq.data_ptr()
+    w += 1.0   # writes through to all three views and nothing else
+    assert float(wq.sum() + wk.sum() + wv.sum()) == 96.0 and float(flat.sum()) == 96.0
+    b = g._fused_view(["q.b", "k.b", "v.b"])
+    assert b is not None and b.shape == (24,) and b.data_ptr() == bq.data_ptr()
+    assert g._fused_view(["q.w", "v.w", "k.w"]) is None          # wrong order: not adjacent
+    assert g._fused_view(["q.w", "k.w", "missing"]) is None      # not in the sink
+    assert g._fused_view(["k.b", "v.b", "odd"]) is None          # a gap of one element before "odd"
+    assert g._fused_view(["q.w", "q.b"]) is None                 # different trailing shapes
+
+
+def test_flat_buffer_keeps_a_layers_qkv_gradients_adjacent():
+    """The trainer's flat buffer lists parameters in model order inside its decay / no-decay segments, which puts the
+    query / key / value weights (and biases) of a Q-Former layer back to back: the fused projection's gradient then
+    goes in with one accumulating launch per layer (engine/qformer.py::_GradOut.weights_fused)."""
+    from eilev_b200.engine import qformer as E_qf
+    from eilev_b200.model.v2 import VideoBlipForConditionalGeneration
+    from eilev_b200.train import FlatBuffers, freeze_for_recipe
+    m = VideoBlipForConditionalGeneration(small_cfg())
+    freeze_for_recipe(m)
+    FlatBuffers(m.named_parameters())
+    sink = {n: p.grad for n, p in E_qf.qformer_param_list(m) if p.requires_grad and p.grad is not None}
+    g = E_qf._GradOut(sink, torch.device("cpu"))
+    n_layers = m.qformer.config.num_hidden_layers
+    for i in range(n_layers):
+        pre = f"qformer.encoder.layer.{i}.attention.attention."
+        w = g._fused_view([pre + f"{nm}.weight" for nm in ("query", "key", "value")])
+        b = g._fused_view([pre + f"{nm}.bias" for nm in ("query", "key", "value")])
+        dq = sink[pre + "query.weight"].shape[0]
+        assert w is not None and w.shape == (3 * dq, sink[pre + "query.weight"].shape[1]), i
+        assert b is not None and b.shape == (3 * dq,), i
