@@ -557,17 +557,17 @@ def gpu_arm(args) -> None:
         trainer.capture_graph(resident)
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # untimed, up to the next accumulation boundary: the first optimizer step (global norm, clip, fused AdamW and the
-    # torch glue between them) pays its one-time launch costs here; the timed region still runs one per grad_accum
-    while trainer.micro % trainer.grad_accum != 0:
-        step_resident()
-    if args.profile:  # ncu --profile-from-start off: exactly one micro-step is captured
+    if args.profile:  # ncu --profile-from-start off: exactly one (warm, no re-pack) micro-step is captured
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         step_resident()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
+    # untimed, up to the next accumulation boundary: the first optimizer step (global norm, clip, fused AdamW and the
+    # torch glue between them) pays its one-time launch costs here; the timed region still runs one per grad_accum
+    while trainer.micro % trainer.grad_accum != 0:
+        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
